@@ -1,0 +1,322 @@
+"""Shared, implementation-agnostic drivers for the golden cases.
+
+Each ``run_*`` takes a namespace ``ns`` (the reference ``qinfer`` adapter, the
+oracle, or the B200 engine adapter) exposing the same plugin names, and drives
+it with identical inputs.  ``make_golden.py`` runs them against the unmodified
+reference to write ``*.npz``; the tests run them against the oracle (bit-exact)
+and the CUDA engine (tolerances stated in the tests).
+"""
+import numpy as np
+
+
+class Namespace(object):
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def oracle_namespace():
+    import smc_oracle as o
+    return Namespace(
+        name="oracle",
+        SMCUpdater=o.SMCUpdater, LiuWestResampler=o.LiuWestResampler,
+        ParticleDistribution=o.ParticleDistribution,
+        SimplePrecessionModel=o.SimplePrecessionModel, SimpleInversionModel=o.SimpleInversionModel,
+        RandomizedBenchmarkingModel=o.RandomizedBenchmarkingModel, BinomialModel=o.BinomialModel,
+        TomographyModel=o.TomographyModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
+        UniformDistribution=o.UniformDistribution, PostselectedDistribution=o.PostselectedDistribution,
+        sqrtm_psd=o.sqrtm_psd)
+
+
+def reference_namespace():
+    from ref_import import import_reference
+    q = import_reference()
+    import qinfer.tomography as qt
+    import qinfer.utils as qu
+    return Namespace(
+        name="reference",
+        SMCUpdater=q.SMCUpdater, LiuWestResampler=q.LiuWestResampler,
+        ParticleDistribution=q.ParticleDistribution,
+        SimplePrecessionModel=q.SimplePrecessionModel, SimpleInversionModel=q.SimpleInversionModel,
+        RandomizedBenchmarkingModel=q.RandomizedBenchmarkingModel, BinomialModel=q.BinomialModel,
+        TomographyModel=qt.TomographyModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
+        UniformDistribution=q.UniformDistribution, PostselectedDistribution=q.PostselectedDistribution,
+        sqrtm_psd=qu.sqrtm_psd)
+
+
+class FixedPrior(object):
+    """A prior that hands back a pre-drawn sample (keeps prior sampling out of
+    the RNG stream so every implementation starts from identical particles)."""
+
+    def __init__(self, sample):
+        self._sample = np.array(sample, dtype=float)
+
+    @property
+    def n_rvs(self):
+        return self._sample.shape[1]
+
+    def sample(self, n=1):
+        assert n == self._sample.shape[0]
+        return self._sample.copy()
+
+
+def recording_resampler(ns, log, **kw):
+    """Subclass the namespace's LiuWestResampler to snapshot its inputs/outputs."""
+    Base = ns.LiuWestResampler
+
+    class Recording(Base):
+        def __call__(self, model, particle_dist, *a, **k):
+            ev = dict(w=np.array(particle_dist.particle_weights, dtype=float, copy=True),
+                      x=np.array(particle_dist.particle_locations, dtype=float, copy=True),
+                      rng=np.random.get_state())
+            out = Base.__call__(self, model, particle_dist, *a, **k)
+            ev['new_x'] = np.array(out.particle_locations, dtype=float, copy=True)
+            log.append(ev)
+            return out
+
+    return Recording(**kw)
+
+
+def pack_rng_state(st):
+    return dict(key=np.asarray(st[1], dtype=np.uint32), pos=np.int64(st[2]),
+                has_gauss=np.int64(st[3]), cached=np.float64(st[4]))
+
+
+def unpack_rng_state(d, prefix):
+    return ('MT19937', d[prefix + 'key'], int(d[prefix + 'pos']),
+            int(d[prefix + 'has_gauss']), float(d[prefix + 'cached']))
+
+
+def exp_sparse_times(n, base=9.0 / 8.0):
+    return base ** np.arange(n)
+
+
+# ---------------------------------------------------------------------------
+# Inputs (generated once, with a private RandomState — never the global stream)
+# ---------------------------------------------------------------------------
+
+def precession_inputs(n_particles=1000, n_updates=100, true_omega=0.5, seed=1234):
+    rs = np.random.RandomState(seed)
+    prior = rs.random_sample((n_particles, 1))
+    ts = exp_sparse_times(n_updates)
+    pr0 = np.cos(ts * true_omega / 2) ** 2
+    outcomes = (rs.random_sample(n_updates) >= pr0).astype(np.int64)
+    return dict(prior=prior, ts=ts, outcomes=outcomes)
+
+
+def rb_inputs(n_particles=2000, n_updates=60, n_meas=25, seed=4321):
+    rs = np.random.RandomState(seed)
+    lo = np.array([0.8, 0.0, 0.0])
+    hi = np.array([1.0, 1.0, 1.0])
+    prior = np.empty((0, 3))
+    while prior.shape[0] < n_particles:       # postselected uniform box (simple_est.py:223-236)
+        c = lo + (hi - lo) * rs.random_sample((n_particles, 3))
+        p, A, B = c.T
+        ok = (A + B <= 1) & (A * p + B <= 1)
+        prior = np.concatenate([prior, c[ok]])[:n_particles]
+    p, A, B = 0.995, 0.5, 0.5
+    ms = np.linspace(1, 800, n_updates).astype(int)
+    counts = rs.binomial(n_meas, A * p ** ms + B)
+    return dict(prior=prior, ms=ms, counts=counts.astype(np.int64), n_meas=np.int64(n_meas))
+
+
+def ginibre_coords(rs, n, basis_data):
+    d = basis_data.shape[1]
+    X = rs.randn(n, d, d) + 1j * rs.randn(n, d, d)
+    rho = np.einsum('nij,nkj->nik', X, X.conj())
+    rho /= np.trace(rho, axis1=1, axis2=2)[:, None, None]
+    return np.real(np.einsum('aij,nij->na', basis_data.conj(), rho))
+
+
+def tomography_inputs(basis_data, n_particles=400, n_updates=40, seed=99):
+    rs = np.random.RandomState(seed)
+    d2 = basis_data.shape[0]
+    dim = basis_data.shape[1]
+    prior = ginibre_coords(rs, n_particles, basis_data)
+    true = ginibre_coords(rs, 1, basis_data)[0]
+    meas = np.zeros((n_updates, d2))
+    ks = rs.randint(1, d2, size=n_updates)
+    meas[:, 0] = np.sqrt(dim) / 2
+    meas[np.arange(n_updates), ks] = np.sqrt(dim) / 2
+    pr1 = np.clip(meas @ true, 0, 1)
+    outcomes = (rs.random_sample(n_updates) < pr1).astype(np.int64)
+    return dict(prior=prior, meas=meas, outcomes=outcomes, true=true)
+
+
+# ---------------------------------------------------------------------------
+# Drivers
+# ---------------------------------------------------------------------------
+
+def _finish(up, log):
+    out = dict(
+        weights=np.array(up.particle_weights, dtype=float),
+        locations=np.array(up.particle_locations, dtype=float),
+        normalization_record=np.array([float(np.ravel(v)[0]) for v in up.normalization_record]),
+        resample_count=np.int64(up.resample_count),
+        min_n_ess=np.float64(up.min_n_ess),
+        n_ess=np.float64(up.n_ess),
+        est_mean=np.array(up.est_mean(), dtype=float),
+        est_cov=np.array(up.est_covariance_mtx(), dtype=float),
+        n_events=np.int64(len(log)),
+    )
+    for i, ev in enumerate(log):
+        out['ev%d_w' % i] = ev['w']
+        out['ev%d_x' % i] = ev['x']
+        out['ev%d_new_x' % i] = ev['new_x']
+        for k, v in pack_rng_state(ev['rng']).items():
+            out['ev%d_rng_%s' % (i, k)] = v
+    return out
+
+
+def run_precession(ns, inp, seed=0, min_freq=0, a=0.98, trace=None):
+    """C1 shape: SimplePrecessionModel, exp-sparse times, default LW."""
+    model = ns.SimplePrecessionModel(min_freq=min_freq)
+    log = []
+    res = recording_resampler(ns, log, a=a)
+    np.random.seed(seed)
+    up = ns.SMCUpdater(model, inp['prior'].shape[0], FixedPrior(inp['prior']), resampler=res)
+    for k in range(len(inp['ts'])):
+        up.update(int(inp['outcomes'][k]), np.array([inp['ts'][k]]))
+        if trace is not None:
+            trace(k, up)
+    return _finish(up, log)
+
+
+def run_rb(ns, inp, seed=0, a=0.98, trace=None):
+    """C3 shape: BinomialModel(RandomizedBenchmarkingModel), batch_update(resample_interval=1)."""
+    model = ns.BinomialModel(ns.RandomizedBenchmarkingModel())
+    log = []
+    res = recording_resampler(ns, log, a=a)
+    np.random.seed(seed)
+    up = ns.SMCUpdater(model, inp['prior'].shape[0], FixedPrior(inp['prior']), resampler=res)
+    eps = np.empty((len(inp['ms']),), dtype=model.expparams_dtype)
+    eps['m'] = inp['ms']
+    eps['n_meas'] = inp['n_meas']
+    up.batch_update(inp['counts'], eps, resample_interval=1)
+    return _finish(up, log)
+
+
+def run_tomography(ns, inp, nq=2, seed=0, a=0.98):
+    """C4 shape: TomographyModel(pauli_basis(nq)), canonicalize after each resample."""
+    model = ns.TomographyModel(ns.pauli_basis(nq))
+    log = []
+    res = recording_resampler(ns, log, a=a)
+    np.random.seed(seed)
+    up = ns.SMCUpdater(model, inp['prior'].shape[0], FixedPrior(inp['prior']), resampler=res)
+    for k in range(inp['meas'].shape[0]):
+        ep = np.empty((1,), dtype=model.expparams_dtype)
+        ep['meas'][0] = inp['meas'][k]
+        up.update(int(inp['outcomes'][k]), ep)
+    return _finish(up, log)
+
+
+def likelihood_vectors(ns, seed=7):
+    """T1 vectors: model.likelihood on random and edge inputs."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    # precession: includes omega=0, large arguments up to ~6e4, outcome label 2 (treated as "not 0")
+    x = np.concatenate([rs.random_sample(253), [0.0, 1.0, 0.5]])[:, None]
+    ts = np.array([0.0, 1.0, 7.3, (9 / 8.) ** 50, (9 / 8.) ** 99])
+    m = ns.SimplePrecessionModel()
+    out['prec_x'] = x
+    out['prec_t'] = ts
+    out['prec_L'] = m.likelihood(np.array([0, 1, 2]), x, ts)
+    # RB: edges p in {0,1}, m = 0
+    xr = rs.random_sample((256, 3)) * np.array([0.3, 0.5, 0.5]) + np.array([0.7, 0.0, 0.0])
+    xr[0] = [1.0, 0.5, 0.5]
+    xr[1] = [0.0, 0.5, 0.25]
+    xr[2] = [0.99, 0.0, 0.0]
+    xr[3] = [0.99, 1.0, 0.0]
+    rbm = ns.RandomizedBenchmarkingModel()
+    ep = np.empty((4,), dtype=rbm.expparams_dtype)
+    ep['m'] = [0, 1, 37, 800]
+    out['rb_x'] = xr
+    out['rb_m'] = np.array([0, 1, 37, 800], dtype=np.int64)
+    out['rb_L'] = rbm.likelihood(np.array([0, 1]), xr, ep)
+    out['rb_valid'] = rbm.are_models_valid(np.concatenate([xr, xr * 1.4 - 0.1]))
+    out['rb_valid_x'] = np.concatenate([xr, xr * 1.4 - 0.1])
+    # Binomial(RB): k in {0, n}, pr1 in {0, 1} via A=0,B=0 / A=1,B=0,p=1
+    bm = ns.BinomialModel(ns.RandomizedBenchmarkingModel())
+    epb = np.empty((3,), dtype=bm.expparams_dtype)
+    epb['m'] = [1, 50, 400]
+    epb['n_meas'] = [25, 25, 25]
+    ks = np.array([0, 1, 12, 24, 25])
+    out['binrb_ks'] = ks
+    out['binrb_m'] = np.array([1, 50, 400], dtype=np.int64)
+    out['binrb_n'] = np.array([25, 25, 25], dtype=np.int64)
+    out['binrb_L'] = bm.likelihood(ks, xr, epb)
+    # Binomial(precession): scalar expparam renamed 'x'
+    bp = ns.BinomialModel(ns.SimplePrecessionModel())
+    epp = np.empty((2,), dtype=bp.expparams_dtype)
+    epp['x'] = [3.7, 91.25]
+    epp['n_meas'] = [10, 40]
+    kp = np.array([0, 3, 10])
+    out['binprec_x'] = np.array([3.7, 91.25])
+    out['binprec_n'] = np.array([10, 40], dtype=np.int64)
+    out['binprec_ks'] = kp
+    out['binprec_L'] = bp.likelihood(kp, x, epp)
+    # Tomography 1- and 2-qubit: includes clipping on both sides
+    for nq in (1, 2):
+        basis = ns.pauli_basis(nq)
+        tm = ns.TomographyModel(basis)
+        d2 = tm.n_modelparams
+        xt = ginibre_coords(rs, 128, np.asarray(basis.data))
+        xt[:8] *= 3.0                       # unphysical: drives pr1 outside [0, 1]
+        ept = np.empty((5,), dtype=tm.expparams_dtype)
+        meas = rs.randn(5, d2) * 0.4
+        meas[:, 0] = np.sqrt(tm.dim if hasattr(tm, 'dim') else basis.dim) / 2
+        ept['meas'] = meas
+        out['tomo%d_x' % nq] = xt
+        out['tomo%d_meas' % nq] = meas
+        out['tomo%d_L' % nq] = tm.likelihood(np.array([0, 1]), xt, ept)
+    return out
+
+
+def canonicalize_vectors(ns, seed=11):
+    """T6 vectors: TomographyModel.canonicalize on physical and unphysical coordinates."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for nq in (1, 2):
+        basis = ns.pauli_basis(nq)
+        data = np.asarray(basis.data)
+        tm = ns.TomographyModel(basis)
+        d2 = data.shape[0]
+        phys = ginibre_coords(rs, 64, data)
+        noisy = phys + 0.15 * rs.randn(64, d2)
+        noisy[:, 0] = phys[:, 0] * (1 + 0.05 * rs.randn(64))
+        x = np.concatenate([phys, noisy])
+        out['canon%d_x' % nq] = x
+        out['canon%d_y' % nq] = tm.canonicalize(x.copy())
+        tms = ns.TomographyModel(basis, allow_subnormalized=True)
+        out['canon%d_y_subnorm' % nq] = tms.canonicalize(x.copy())
+    g = ns.gell_mann_basis(3)
+    data = np.asarray(g.data)
+    tm = ns.TomographyModel(g)
+    phys = ginibre_coords(rs, 32, data)
+    noisy = phys + 0.2 * rs.randn(32, 9)
+    noisy[:, 0] = phys[:, 0]
+    x = np.concatenate([phys, noisy])
+    out['canon_gm3_x'] = x
+    out['canon_gm3_y'] = tm.canonicalize(x.copy())
+    return out
+
+
+def moment_vectors(ns, seed=5):
+    """T3 vectors + sqrtm_psd (tests/test_utils.py:132-152 shape)."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for d in (1, 3, 16):
+        n = 777
+        x = rs.randn(n, d) * (0.1 + rs.random_sample(d)) + rs.randn(d)
+        w = rs.random_sample(n) ** 3
+        w[::7] = 0.0
+        w /= w.sum()
+        pd = ns.ParticleDistribution(particle_locations=x, particle_weights=w)
+        out['mom%d_x' % d] = x
+        out['mom%d_w' % d] = np.array(pd.particle_weights)
+        out['mom%d_mean' % d] = pd.est_mean()
+        out['mom%d_cov' % d] = pd.est_covariance_mtx()
+        out['mom%d_ness' % d] = np.float64(pd.n_ess)
+        S, err = ns.sqrtm_psd(out['mom%d_cov' % d])
+        out['mom%d_S' % d] = S
+        out['mom%d_Serr' % d] = np.float64(err)
+    return out
