@@ -1,0 +1,193 @@
+/* qinfer_b200.h — C ABI of the B200-native SMC particle-filter hot path.
+ *
+ * This is the drop-in boundary for QInfer's Bayes-update + Liu-West resample
+ * path.  The reference (QInfer/python-qinfer @ 8170c84) is pure
+ * Python/NumPy and has no FFI of its own; these entry points are what a ctypes
+ * binding of that path binds (INTEGRATION.md shows the stub), one per reference
+ * function listed in SURVEY §8(a).  File:line citations are relative to
+ * /root/reference/src/qinfer/.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no framework types.  Every `*_dev` / `d_`
+ *     pointer is CUDA device memory owned by the caller (the Python host
+ *     allocates it with torch and passes `data_ptr()`); `stream` is a
+ *     `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *   - All particle data is float64.  Particle locations are row-major
+ *     `x[n][d]` exactly like `SMCUpdater.particle_locations` (smc.py:292-298).
+ *   - Weights are kept UNNORMALISED on the device together with a 16-double
+ *     `stats` block (layout below); the normalised weight of particle i is
+ *     `w[i] * stats[QB_STAT_INV_NORM]`.  This defers the division of
+ *     smc.py:373 into the next pass over the weights (8(d+2) B/particle-update).
+ *   - Every function returns QB_OK (0) or a negative QB_ERR_* code;
+ *     `qb_last_error()` returns a thread-local message.  Launches are
+ *     asynchronous on `stream`; nothing here synchronises unless stated.
+ *   - No entry point allocates device memory; workspaces are caller-provided
+ *     and sized by the `*_workspace_bytes` queries.
+ */
+#ifndef QINFER_B200_H
+#define QINFER_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_ABI_VERSION 1
+
+#define QB_OK 0
+#define QB_ERR_INVALID_ARGUMENT (-1)
+#define QB_ERR_UNSUPPORTED_MODEL (-2)
+#define QB_ERR_CUDA (-3)
+#define QB_ERR_WORKSPACE (-4)
+
+#define QB_MAX_D 64 /* max n_modelparams handled by the staged kernels (3-qubit tomography) */
+
+/* ---- model plugin descriptor ------------------------------------------- */
+/* Which built-in likelihood the kernels evaluate. */
+enum qb_model_kind {
+    QB_MODEL_PRECESSION = 1, /* SimpleInversionModel / SimplePrecessionModel  test_models.py:123-143,188-197 */
+    QB_MODEL_RB = 2,         /* RandomizedBenchmarkingModel                   rb.py:149-195                  */
+    QB_MODEL_TOMOGRAPHY = 3  /* tomography.TomographyModel                    tomography/models.py:143-226   */
+};
+
+typedef struct qb_model {
+    int32_t kind;         /* enum qb_model_kind */
+    int32_t d;            /* n_modelparams (abstract_model.py:96-104) */
+    int32_t binomial;     /* 1: wrapped in BinomialModel (derived_models.py:222-360) */
+    int32_t interleaved;  /* RB only: `_il` (rb.py:114-115) */
+    double min_freq;      /* precession only: `_min_freq` (test_models.py:78-80,109-110) */
+} qb_model;
+
+/* One experiment record (one element of the `expparams` array handed to
+ * Model.likelihood, abstract_model.py:443-468). */
+typedef struct qb_expparams {
+    double t;            /* precession: evolution time 't'                       */
+    double w_;           /* inversion model: reference frequency 'w_' (0 for SimplePrecessionModel) */
+    int64_t m;           /* RB: sequence length 'm' (uint in the reference)      */
+    int32_t reference;   /* interleaved RB: 'reference' flag                     */
+    int32_t reserved;
+    int64_t n_meas;      /* BinomialModel: 'n_meas'                              */
+    double meas[QB_MAX_D]; /* tomography: 'meas' coefficients (first d used)     */
+} qb_expparams;
+
+/* ---- device-side stats block (16 doubles) ------------------------------- */
+#define QB_STAT_NORM 0      /* sum_i w'_i of the last update  = normalization_record entry (smc.py:357,444) */
+#define QB_STAT_SUMSQ 1     /* sum_i w'_i^2                   -> n_ess = norm^2 / sumsq (distributions.py:299-307) */
+#define QB_STAT_MIN 2       /* min_i w'_i (negative-weight check, smc.py:416-418) */
+#define QB_STAT_NBAD 3      /* number of NaN or negative w'_i */
+#define QB_STAT_INV_NORM 4  /* 1/norm, or 1 if |norm| < eps (smc.py:369-373); applied lazily by the next kernel */
+#define QB_STAT_NESS 5      /* norm^2 / sumsq */
+#define QB_STAT_COUNT 16
+
+/* ---- library / device --------------------------------------------------- */
+int qb_abi_version(void);
+const char* qb_last_error(void);
+/* Number of SMs of the current device (grid sizing); negative on error. */
+int qb_device_sm_count(void);
+
+/* ---- weights utilities -------------------------------------------------- */
+/* w[i] = 1/n, stats = {norm 1, sumsq 1/n, min 1/n, nbad 0, inv 1, ness n}.
+ * smc.py:307 (reset) and resamplers.py:390-392 (post-resample weights). */
+int qb_weights_set_uniform(double* d_w, int64_t n, double* d_stats, void* stream);
+/* out[i] = w[i] * stats[INV_NORM]  — materialises `particle_weights` for the host. */
+int qb_weights_normalized(const double* d_w, int64_t n, const double* d_stats, double* d_out, void* stream);
+/* Re-derive stats from weights the host assigned (`particle_weights = ...`):
+ * stats from sum / sum of squares of w as given (no normalisation applied). */
+int qb_weights_restat(const double* d_w, int64_t n, double* d_stats, double* d_ws, size_t ws_bytes, void* stream);
+/* In-place clip of the NORMALISED weights to [0,1] (smc.py:418) and restat;
+ * afterwards w holds normalised, clipped weights and stats[INV_NORM] = 1. */
+int qb_weights_clip(double* d_w, int64_t n, double* d_stats, double* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- fused Bayes update (the hot kernel) --------------------------------- */
+size_t qb_update_workspace_bytes(int64_t n, int32_t d);
+/* One launch: w_out[i] = (w_in[i] * stats_in[INV_NORM]) * L(outcome | x_i; ep)
+ * fused with the block+warp reductions for sum, sum of squares, min and the
+ * bad-weight count, finished deterministically by the last block into
+ * stats_out (may alias stats_in).  Replaces SMCUpdater.hypothetical_update +
+ * the weight bookkeeping of SMCUpdater.update (smc.py:324-386, 413-453) and
+ * Model.likelihood for the built-in models.  w_out may alias w_in.
+ * `outcome`: the datum (0/1 label, or the count k under BinomialModel). */
+int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outcome,
+                    const double* d_x, int64_t n,
+                    const double* d_w_in, double* d_w_out,
+                    const double* d_stats_in, double* d_stats_out,
+                    void* d_ws, size_t ws_bytes, void* stream);
+
+/* Plain likelihood tensor L[o][i][e] (n_o, n, n_e) — Model.likelihood
+ * (abstract_model.py:443-468) for the built-in models; `eps`/`outcomes` are HOST arrays. */
+int qb_likelihood(const qb_model* model, const qb_expparams* eps, int32_t n_e,
+                  const int64_t* outcomes, int32_t n_o,
+                  const double* d_x, int64_t n, double* d_L, void* stream);
+
+/* Model.are_models_valid (test_models.py:109-110, rb.py:149-176,
+ * tomography/models.py:143-147): d_valid[i] in {0,1}. */
+int qb_are_models_valid(const qb_model* model, const double* d_x, int64_t n, uint8_t* d_valid, void* stream);
+
+/* ---- moments -------------------------------------------------------------- */
+size_t qb_moments_workspace_bytes(int64_t n, int32_t d);
+/* d_out[0] = sum w, d_out[1..d] = sum w x  (ParticleDistribution.particle_mean,
+ * distributions.py:337-348), d_out[1+d .. 1+d+d*d) = sum w x x^T row-major (the
+ * einsum of distributions.py:386-387); w = normalised weight.  The host forms
+ * cov = E[xx^T] - mu mu^T exactly as distributions.py:388-389. */
+int qb_moments(const double* d_x, const double* d_w, const double* d_stats, int64_t n, int32_t d,
+               double* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- Liu-West resampler --------------------------------------------------- */
+#define QB_SCAN_FAST 0   /* parallel (re-associated) prefix sum                              */
+#define QB_SCAN_EXACT 1  /* reproduces np.cumsum's sequential fp64 rounding bit for bit      */
+size_t qb_cdf_workspace_bytes(int64_t n);
+/* d_cdf[i] = cumsum of normalised weights (resamplers.py:308). */
+int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode,
+           void* d_ws, size_t ws_bytes, void* stream);
+/* d_js[i] = min(searchsorted(cdf, u[i], side='right'), n-1) (resamplers.py:318-321;
+ * the clamp is distributions.py:330-333's — the reference's resampler raises
+ * IndexError where the clamp acts).  *d_overflow counts clamped draws. */
+int qb_draw(const double* d_cdf, int64_t n, const double* d_u, int64_t n_draw,
+            int64_t* d_js, int64_t* d_overflow, void* stream);
+/* First Liu-West pass (resamplers.py:325-342): for i < n_new
+ *   mu_i = a * x_old[js[i]] + (1-a) * mean ;  x_new[i] = mu_i + S @ eps[:, i]
+ * `d_eps` is (d, n_new) row-major — the layout of `kernel(n_rvs, k)`.
+ * With postselect != 0, d_invalid[i] = !are_models_valid(x_new[i]) and
+ * *d_n_invalid is their count.  h_mean (d) and h_S (d*d, row-major, already
+ * scaled by h) are HOST arrays. */
+int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+               const int64_t* d_js, const double* h_mean, const double* h_S, double a,
+               const double* d_eps, int64_t n_new, double* d_x_new,
+               int32_t postselect, uint8_t* d_invalid, int64_t* d_n_invalid, void* stream);
+size_t qb_compact_workspace_bytes(int64_t n);
+/* Ordered compaction: d_idxs_out = ascending indices i with d_invalid[i] != 0
+ * (np.nonzero, resamplers.py:365-367); *d_count = how many. */
+int qb_compact_invalid(const uint8_t* d_invalid, int64_t n, int64_t* d_idxs_out, int64_t* d_count,
+                       void* d_ws, size_t ws_bytes, void* stream);
+/* Retry pass (resamplers.py:327-372) over the k still-invalid particles:
+ *   x_new[idxs[r]] = (a * x_old[js[r]] + (1-a) * mean) + S @ eps[:, r],  r < k
+ * NOTE js[r], not js[idxs[r]]: the reference re-slices `mus = mus[:k]`
+ * (resamplers.py:372), a prefix of the ORIGINAL means; parity replicates it.
+ * Sets d_invalid[idxs[r]] to the new validity and *d_n_invalid to the count. */
+int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                const int64_t* d_js, const int64_t* d_idxs, int64_t k,
+                const double* h_mean, const double* h_S, double a,
+                const double* d_eps, double* d_x_new,
+                uint8_t* d_invalid, int64_t* d_n_invalid, void* stream);
+
+/* ---- tomography canonicalize ---------------------------------------------- */
+/* TomographyModel.canonicalize (tomography/models.py:149-209): per particle
+ * rho = sum_a x_a conj(B_a); eigendecompose (Hermitian Jacobi); if any
+ * eigenvalue < 0 clip, rebuild and project back x_a = Re sum_ij B_a[ij] rho'[ij];
+ * then divide by x_0 sqrt(dim) unless allow_subnormalized.  `d_basis` is the
+ * (dim^2, dim, dim) complex128 basis tensor (interleaved re/im), dim in {2,3,4}. */
+int qb_tomo_canonicalize(double* d_x, int64_t n, int32_t dim, const double* d_basis,
+                         int32_t allow_subnormalized, void* stream);
+
+/* ---- device RNG (throughput mode; counter-based Philox4x32-10) ------------- */
+/* d_out[i] = uniform [0,1) with 53 random bits, element i of stream (seed, offset). */
+int qb_rng_uniform(double* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* d_out[i] = standard normal (Box-Muller on two 53-bit uniforms). */
+int qb_rng_normal(double* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QINFER_B200_H */

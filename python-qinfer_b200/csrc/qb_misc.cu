@@ -1,0 +1,256 @@
+// Library plumbing, weight utilities, plain likelihood and validity kernels.
+#include <cstdarg>
+#include <cstring>
+#include "qb_models.cuh"
+
+namespace qb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return QB_ERR_CUDA;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int validate_model(const qb_model* m);  // qb_update.cu
+
+// ---- weights ------------------------------------------------------------------
+__global__ void set_uniform_kernel(double* w, int64_t n, double* stats) {
+    const double v = 1.0 / static_cast<double>(n);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = v;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[QB_STAT_NORM] = 1.0;
+        stats[QB_STAT_SUMSQ] = v;
+        stats[QB_STAT_MIN] = v;
+        stats[QB_STAT_NBAD] = 0.0;
+        stats[QB_STAT_INV_NORM] = 1.0;
+        stats[QB_STAT_NESS] = static_cast<double>(n);
+    }
+}
+
+__global__ void normalized_kernel(const double* __restrict__ w, int64_t n, const double* __restrict__ stats,
+                                  double* __restrict__ out) {
+    const double inv = stats[QB_STAT_INV_NORM];
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = w[i] * inv;
+}
+
+// restat / clip share one reduction kernel: CLIP also rewrites w in place.
+template <bool CLIP>
+__global__ void __launch_bounds__(256) restat_kernel(double* w, int64_t n, const double* stats_in, double* partials) {
+    __shared__ double red[8 * 4];
+    const double inv = CLIP ? stats_in[QB_STAT_INV_NORM] : 1.0;
+    double s = 0.0, q = 0.0, mn = INFINITY, bad = 0.0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = w[i];
+        if (CLIP) {
+            v = v * inv;
+            // np.clip(weights, 0, 1) (smc.py:418); NaN propagates like NumPy's clip
+            v = (v < 0.0) ? 0.0 : ((v > 1.0) ? 1.0 : v);
+            w[i] = v;
+        }
+        s += v;
+        q = fma(v, v, q);
+        mn = fmin(mn, v);
+        bad += (v >= 0.0) ? 0.0 : 1.0;
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    mn = warp_min(mn);
+    bad = warp_sum(bad);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[wid * 4 + 0] = s;
+        red[wid * 4 + 1] = q;
+        red[wid * 4 + 2] = mn;
+        red[wid * 4 + 3] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            s += red[k * 4 + 0];
+            q += red[k * 4 + 1];
+            mn = fmin(mn, red[k * 4 + 2]);
+            bad += red[k * 4 + 3];
+        }
+        partials[blockIdx.x * 4 + 0] = s;
+        partials[blockIdx.x * 4 + 1] = q;
+        partials[blockIdx.x * 4 + 2] = mn;
+        partials[blockIdx.x * 4 + 3] = bad;
+    }
+}
+
+__global__ void restat_finish_kernel(const double* partials, int nblocks, double* stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0.0, q = 0.0, mn = INFINITY, bad = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        s += partials[b * 4 + 0];
+        q += partials[b * 4 + 1];
+        mn = fmin(mn, partials[b * 4 + 2]);
+        bad += partials[b * 4 + 3];
+    }
+    stats[QB_STAT_NORM] = s;
+    stats[QB_STAT_SUMSQ] = q;
+    stats[QB_STAT_MIN] = mn;
+    stats[QB_STAT_NBAD] = bad;
+    stats[QB_STAT_INV_NORM] = 1.0;  // weights are taken as given
+    stats[QB_STAT_NESS] = (s * s) / q;
+}
+
+// ---- plain likelihood + validity -----------------------------------------------
+struct LikParams {
+    const double* x;
+    double* out;   // L + (o * n) * n_e + e ; element i at stride n_e
+    int64_t n;
+    int32_t n_e;
+    ModelView mv;
+    ExpView ev;
+    double meas[QB_MAX_D];
+};
+
+template <int KIND, bool BINOM>
+__global__ void __launch_bounds__(256) likelihood_kernel(const __grid_constant__ LikParams p) {
+    const int d = p.mv.d;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const double* xr = p.x + i * d;
+        auto row = [&](int c) { return xr[c]; };
+        auto meas = [&](int c) { return p.meas[c]; };
+        p.out[i * p.n_e] = model_likelihood<KIND, BINOM>(p.mv, p.ev, row, meas, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) valid_kernel(ModelView mv, const double* __restrict__ x, int64_t n,
+                                                    uint8_t* __restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double* xr = x + i * mv.d;
+        auto row = [&](int c) { return xr[c]; };
+        out[i] = model_valid(mv, row) ? 1 : 0;
+    }
+}
+
+static int grid_for(int64_t n, int threads, int per_sm) {
+    int64_t g = (n + threads - 1) / threads;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" int qb_abi_version(void) { return QB_ABI_VERSION; }
+extern "C" const char* qb_last_error(void) { return qb::g_err; }
+extern "C" int qb_device_sm_count(void) { return qb::sm_count(); }
+
+extern "C" int qb_weights_set_uniform(double* d_w, int64_t n, double* d_stats, void* stream) {
+    QB_REQUIRE(d_w && d_stats && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_weights_set_uniform: bad arguments");
+    set_uniform_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(d_w, n, d_stats);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_weights_normalized(const double* d_w, int64_t n, const double* d_stats, double* d_out,
+                                     void* stream) {
+    QB_REQUIRE(d_w && d_stats && d_out && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_weights_normalized: bad arguments");
+    normalized_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(d_w, n, d_stats, d_out);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+static int restat_common(double* d_w, int64_t n, double* d_stats, double* d_ws, size_t ws_bytes, void* stream,
+                         bool clip) {
+    QB_REQUIRE(d_w && d_stats && d_ws && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_weights_restat/clip: bad arguments");
+    const int grid = grid_for(n, 256, 8);
+    QB_REQUIRE(ws_bytes >= static_cast<size_t>(grid) * 4 * sizeof(double) + 256, QB_ERR_WORKSPACE,
+               "qb_weights_restat/clip: workspace too small");
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);
+    if (clip)
+        restat_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(d_w, n, d_stats, partials);
+    else
+        restat_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(d_w, n, d_stats, partials);
+    QB_CUDA_CHECK(cudaGetLastError());
+    restat_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(partials, grid, d_stats);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_weights_restat(const double* d_w, int64_t n, double* d_stats, double* d_ws, size_t ws_bytes,
+                                 void* stream) {
+    return restat_common(const_cast<double*>(d_w), n, d_stats, d_ws, ws_bytes, stream, false);
+}
+
+extern "C" int qb_weights_clip(double* d_w, int64_t n, double* d_stats, double* d_ws, size_t ws_bytes, void* stream) {
+    return restat_common(d_w, n, d_stats, d_ws, ws_bytes, stream, true);
+}
+
+extern "C" int qb_likelihood(const qb_model* model, const qb_expparams* eps, int32_t n_e, const int64_t* outcomes,
+                             int32_t n_o, const double* d_x, int64_t n, double* d_L, void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(eps && outcomes && d_x && d_L && n >= 1 && n_e >= 1 && n_o >= 1, QB_ERR_INVALID_ARGUMENT,
+               "qb_likelihood: bad arguments");
+    LikParams p;
+    p.x = d_x;
+    p.n = n;
+    p.n_e = n_e;
+    p.mv = make_model_view(*model);
+    const int grid = grid_for(n, 256, 8);
+    for (int o = 0; o < n_o; ++o) {
+        for (int e = 0; e < n_e; ++e) {
+            p.ev = make_exp_view(*model, eps[e], outcomes[o]);
+            for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? eps[e].meas[c] : 0.0;
+            p.out = d_L + static_cast<int64_t>(o) * n * n_e + e;
+#define QB_LAUNCH_LIK(K)                                                                        \
+    if (model->binomial)                                                                        \
+        likelihood_kernel<K, true><<<grid, 256, 0, as_stream(stream)>>>(p);                     \
+    else                                                                                        \
+        likelihood_kernel<K, false><<<grid, 256, 0, as_stream(stream)>>>(p);
+            if (model->kind == QB_MODEL_PRECESSION) {
+                QB_LAUNCH_LIK(QB_MODEL_PRECESSION)
+            } else if (model->kind == QB_MODEL_RB) {
+                QB_LAUNCH_LIK(QB_MODEL_RB)
+            } else {
+                QB_LAUNCH_LIK(QB_MODEL_TOMOGRAPHY)
+            }
+#undef QB_LAUNCH_LIK
+            QB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    return QB_OK;
+}
+
+extern "C" int qb_are_models_valid(const qb_model* model, const double* d_x, int64_t n, uint8_t* d_valid,
+                                   void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_x && d_valid && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_are_models_valid: bad arguments");
+    valid_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(make_model_view(*model), d_x, n, d_valid);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}

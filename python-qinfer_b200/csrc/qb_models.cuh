@@ -1,0 +1,138 @@
+// Per-particle likelihoods and validity tests of the built-in models.
+//
+// Compiled with --fmad=false: the reference evaluates these expressions with
+// one rounding per NumPy ufunc, so every multiply/add here must round
+// separately (no silent FMA contraction); explicit fma() is used only where
+// the reference's BLAS call does.
+#pragma once
+#include "qb_common.cuh"
+
+namespace qb {
+
+// Device-side view of one (experiment, outcome) pair, prepared on the host.
+struct ExpView {
+    double t, w_;      // precession
+    double m;          // RB: sequence length as float64 (NumPy casts uint -> float64 for p ** m, rb.py:193)
+    int32_t reference; // interleaved RB
+    int32_t outcome0;  // 1 if the two-outcome label == 0 (abstract_model.py:683-686: anything else is "1")
+    double n_meas, k;  // BinomialModel: shots and observed count
+    double logc;       // lgamma(n+1) - lgamma(k+1) - lgamma(n-k+1), hoisted per update
+    int32_t k_in_range; // 0 <= k <= n
+    int32_t pad;
+};
+
+struct ModelView {
+    int32_t kind, d, binomial, interleaved;
+    double min_freq;
+};
+
+__host__ inline ExpView make_exp_view(const qb_model& m, const qb_expparams& ep, int64_t outcome) {
+    ExpView v;
+    v.t = ep.t;
+    v.w_ = ep.w_;
+    v.m = static_cast<double>(static_cast<uint64_t>(ep.m));
+    v.reference = ep.reference;
+    v.outcome0 = (outcome == 0) ? 1 : 0;
+    v.n_meas = static_cast<double>(ep.n_meas);
+    v.k = static_cast<double>(outcome);
+    v.k_in_range = (outcome >= 0 && outcome <= ep.n_meas) ? 1 : 0;
+    v.logc = 0.0;
+    if (m.binomial && v.k_in_range) {
+        v.logc = lgamma(v.n_meas + 1.0) - lgamma(v.k + 1.0) - lgamma(v.n_meas - v.k + 1.0);
+    }
+    v.pad = 0;
+    return v;
+}
+
+__host__ inline ModelView make_model_view(const qb_model& m) {
+    ModelView v;
+    v.kind = m.kind;
+    v.d = m.d;
+    v.binomial = m.binomial;
+    v.interleaved = m.interleaved;
+    v.min_freq = m.min_freq;
+    return v;
+}
+
+// pr0 of the underlying two-outcome model for one particle.  `row(c)` returns
+// model parameter c of this particle, `meas(c)` the tomography coefficient c.
+// `rot` rotates the summation start so that lanes of a warp touch different
+// shared-memory banks when rows are 128-B apart (d = 16, 64).
+template <int KIND, typename Row, typename Meas>
+__device__ __forceinline__ double model_pr0(const ModelView& mv, const ExpView& ev, Row row, Meas meas, int rot) {
+    if (KIND == QB_MODEL_PRECESSION) {
+        // test_models.py:134-140: cos(t * (omega - w_) / 2) ** 2
+        double dw = row(0) - ev.w_;
+        double c = cos((ev.t * dw) / 2.0);
+        return c * c;
+    } else if (KIND == QB_MODEL_RB) {
+        // rb.py:178-195: 1 - (A * p**m + B); interleaved: p <- p or p~ * p
+        double p, A, B;
+        if (mv.interleaved) {
+            double pt = row(0);
+            p = row(1);
+            A = row(2);
+            B = row(3);
+            if (!ev.reference) p = pt * p;
+        } else {
+            p = row(0);
+            A = row(1);
+            B = row(2);
+        }
+        double pm = pow(p, ev.m);
+        return 1.0 - (A * pm + B);
+    } else {
+        // tomography/models.py:214-226: pr1 = clip(<meas, x>, 0, 1); pr0 = 1 - pr1
+        const int d = mv.d;
+        double acc = 0.0;
+        int c = rot % d;
+        for (int j = 0; j < d; ++j) {
+            acc = fma(meas(c), row(c), acc);
+            c = (c + 1 == d) ? 0 : c + 1;
+        }
+        acc = fmin(fmax(acc, 0.0), 1.0);
+        return 1.0 - acc;
+    }
+}
+
+// Binomial pmf, SciPy's closed form (derived_models.py:324-327 -> utils.py:106-111):
+// exp(logC + xlogy(k, p) + xlog1py(n - k, -p)).
+__device__ __forceinline__ double binom_pmf(const ExpView& ev, double p) {
+    if (!ev.k_in_range) return 0.0;
+    double t1 = (ev.k == 0.0) ? 0.0 : ev.k * log(p);
+    double nk = ev.n_meas - ev.k;
+    double t2 = (nk == 0.0) ? 0.0 : nk * log1p(-p);
+    return exp(ev.logc + t1 + t2);
+}
+
+template <int KIND, bool BINOM, typename Row, typename Meas>
+__device__ __forceinline__ double model_likelihood(const ModelView& mv, const ExpView& ev, Row row, Meas meas,
+                                                   int rot) {
+    double pr0 = model_pr0<KIND>(mv, ev, row, meas, rot);
+    if (BINOM) {
+        double pr1 = 1.0 - pr0;  // underlying.likelihood([1], ...) (derived_models.py:318-321)
+        return binom_pmf(ev, pr1);
+    }
+    return ev.outcome0 ? pr0 : 1.0 - pr0;
+}
+
+// Model.are_models_valid for one particle.
+template <typename Row>
+__device__ __forceinline__ bool model_valid(const ModelView& mv, Row row) {
+    if (mv.kind == QB_MODEL_PRECESSION) {
+        return row(0) > mv.min_freq;  // test_models.py:109-110
+    } else if (mv.kind == QB_MODEL_RB) {
+        // rb.py:149-176 (the interleaved branch names the first parameter p_C and tests it as such)
+        if (mv.interleaved) {
+            double pc = row(0), p = row(1), A = row(2), B = row(3);
+            return (0.0 <= p) && (p <= 1.0) && (0.0 <= pc) && (pc <= 1.0) && (0.0 <= A) && (A <= 1.0) &&
+                   (0.0 <= B) && (B <= 1.0) && (A + B <= 1.0) && (A * p + B <= 1.0) && (A * pc + B <= 1.0);
+        }
+        double p = row(0), A = row(1), B = row(2);
+        return (0.0 <= p) && (p <= 1.0) && (0.0 <= A) && (A <= 1.0) && (0.0 <= B) && (B <= 1.0) &&
+               (A + B <= 1.0) && (A * p + B <= 1.0);
+    }
+    return true;  // tomography/models.py:143-147
+}
+
+}  // namespace qb

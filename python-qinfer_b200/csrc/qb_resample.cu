@@ -1,0 +1,532 @@
+// Liu-West resampler kernels (resamplers.py:308-372):
+//   qb_cdf      — prefix sum of the normalised weights (np.cumsum)
+//   qb_draw     — multinomial draw by right-bisection of the CDF (searchsorted)
+//   qb_lw_move  — gather x[js], shrink towards the mean, add S @ eps, validity
+//   qb_compact_invalid / qb_lw_retry — the postselection retry loop
+//
+// Compiled with --fmad=false (see qb_models.cuh).
+#include "qb_models.cuh"
+
+namespace qb {
+
+// =============================================================================
+// CDF
+// =============================================================================
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 weights per tile
+
+__device__ __forceinline__ double block_exclusive_scan(double v, double* warp_tot, double& block_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    double base = 0.0, tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < SCAN_THREADS / 32; ++k) {
+        const double t = warp_tot[k];
+        if (k < wid) base += t;
+        tot += t;
+    }
+    block_total = tot;
+    __syncthreads();
+    return base + (inc - v);
+}
+
+// pass 1: per-tile sums of normalised weights
+__global__ void __launch_bounds__(SCAN_THREADS) cdf_tile_sums_kernel(const double* __restrict__ w,
+                                                                     const double* __restrict__ stats, int64_t n,
+                                                                     double* __restrict__ tile_sums) {
+    __shared__ double warp_tot[SCAN_THREADS / 32];
+    const double inv = stats[QB_STAT_INV_NORM];
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * SCAN_TILE + static_cast<int64_t>(threadIdx.x) * SCAN_ITEMS;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const int64_t i = base + k;
+            if (i < n) s += w[i] * inv;
+        }
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int k = 0; k < SCAN_THREADS / 32; ++k) tot += warp_tot[k];
+            tile_sums[t] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2: exclusive scan of the tile sums by one block (sequential chunks per thread)
+__global__ void __launch_bounds__(SCAN_THREADS) cdf_scan_tiles_kernel(double* tile_sums, int64_t ntiles) {
+    __shared__ double warp_tot[SCAN_THREADS / 32];
+    const int64_t per = (ntiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int64_t lo = static_cast<int64_t>(threadIdx.x) * per;
+    const int64_t hi = (lo + per < ntiles) ? lo + per : ntiles;
+    double s = 0.0;
+    for (int64_t i = lo; i < hi; ++i) s += tile_sums[i];
+    double total;
+    double run = block_exclusive_scan(s, warp_tot, total);
+    for (int64_t i = lo; i < hi; ++i) {
+        const double v = tile_sums[i];
+        tile_sums[i] = run;
+        run += v;
+    }
+}
+
+// pass 3: per-tile inclusive scan + tile offset
+__global__ void __launch_bounds__(SCAN_THREADS) cdf_write_kernel(const double* __restrict__ w,
+                                                                 const double* __restrict__ stats, int64_t n,
+                                                                 const double* __restrict__ tile_offsets,
+                                                                 double* __restrict__ cdf) {
+    __shared__ double warp_tot[SCAN_THREADS / 32];
+    const double inv = stats[QB_STAT_INV_NORM];
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * SCAN_TILE + static_cast<int64_t>(threadIdx.x) * SCAN_ITEMS;
+        double v[SCAN_ITEMS];
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const int64_t i = base + k;
+            v[k] = (i < n) ? w[i] * inv : 0.0;
+            s += v[k];
+        }
+        double total;
+        double run = tile_offsets[t] + block_exclusive_scan(s, warp_tot, total);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const int64_t i = base + k;
+            run += v[k];
+            if (i < n) cdf[i] = run;
+        }
+    }
+}
+
+// Exact mode, first implementation: np.cumsum adds strictly left to right in
+// fp64, so one lane replays that chain out of shared memory while a second warp
+// streams weights in and finished CDF values out (triple-buffered chunks).
+constexpr int SEQ_CHUNK = 2048;
+__global__ void __launch_bounds__(64) cdf_sequential_kernel(const double* __restrict__ w,
+                                                            const double* __restrict__ stats, int64_t n,
+                                                            double* __restrict__ cdf) {
+    __shared__ double buf[3][SEQ_CHUNK];
+    const double inv = stats[QB_STAT_INV_NORM];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double run = 0.0;
+    const int64_t nchunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
+    for (int64_t c = 0; c < nchunks + 2; ++c) {
+        if (wid == 1) {
+            if (c < nchunks) {  // stage chunk c
+                const int64_t first = c * SEQ_CHUNK;
+                double* b = buf[c % 3];
+                for (int j = lane; j < SEQ_CHUNK; j += 32) b[j] = (first + j < n) ? w[first + j] * inv : 0.0;
+            }
+            if (c >= 2) {  // write back chunk c-2
+                const int64_t first = (c - 2) * SEQ_CHUNK;
+                const double* b = buf[(c - 2) % 3];
+                for (int j = lane; j < SEQ_CHUNK && first + j < n; j += 32) cdf[first + j] = b[j];
+            }
+        } else if (lane == 0 && c >= 1 && c <= nchunks) {  // the sequential fp64 chain on chunk c-1
+            double* b = buf[(c - 1) % 3];
+            const int64_t first = (c - 1) * SEQ_CHUNK;
+            const int cnt = static_cast<int>((n - first < SEQ_CHUNK) ? (n - first) : SEQ_CHUNK);
+            int j = 0;
+            if (c == 1) {  // cumsum's first element is w[0] itself
+                run = b[0];
+                j = 1;
+            }
+#pragma unroll 8
+            for (; j < cnt; ++j) {
+                run = run + b[j];
+                b[j] = run;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =============================================================================
+// Draw: js[i] = min(upper_bound(cdf, u[i]), n - 1)
+// =============================================================================
+__global__ void __launch_bounds__(256) draw_kernel(const double* __restrict__ cdf, int64_t n,
+                                                   const double* __restrict__ u, int64_t n_draw,
+                                                   int64_t* __restrict__ js, unsigned long long* overflow) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    unsigned int over = 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_draw; i += stride) {
+        const double ui = ldg_stream(u + i);
+        int64_t lo = 0, hi = n;  // first index with cdf[idx] > ui  (side='right')
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(cdf + mid) <= ui)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo >= n) {
+            lo = n - 1;
+            ++over;
+        }
+        js[i] = lo;
+    }
+    if (over) atomicAdd(overflow, static_cast<unsigned long long>(over));
+}
+
+// =============================================================================
+// Liu-West move
+// =============================================================================
+struct LwParams {
+    const double* x_old;
+    const int64_t* js;
+    const double* eps;    // (d, eps_ld) row-major
+    double* x_new;
+    uint8_t* invalid;
+    unsigned long long* n_invalid;
+    const int64_t* idxs;  // retry only
+    int64_t n_old, n_new, eps_ld;
+    int32_t d, tile, postselect, pad;
+    double a;
+    ModelView mv;
+    const double* consts;  // device: S (d*d) then (1-a)*mean (d)
+};
+
+// One CTA handles `tile` consecutive new particles.
+__global__ void __launch_bounds__(256) lw_move_kernel(const __grid_constant__ LwParams p) {
+    extern __shared__ double sm[];
+    const int d = p.d, T = p.tile, ld = d | 1;  // odd row pitch: conflict-free column walks
+    double* loc = sm;                 // [T][ld]
+    double* eps_s = loc + T * ld;     // [d][T]
+    double* S = eps_s + d * T;        // [d][d]
+    double* mshift = S + d * d;       // [d]  (1-a)*mean
+    __shared__ unsigned int block_bad;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < d * d + d; j += blockDim.x) S[j] = p.consts[j];
+    const int64_t ntiles = (p.n_new + T - 1) / T;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t first = t * T;
+        const int cnt = static_cast<int>((p.n_new - first < T) ? (p.n_new - first) : T);
+        if (tid == 0) block_bad = 0;
+        __syncthreads();
+        // gather + shrink: mu = a * x[js] + (1-a) * mean   (resamplers.py:325)
+        for (int j = tid; j < cnt * d; j += blockDim.x) {
+            const int r = j / d, c = j - r * d;
+            const int64_t src = p.js[first + r];
+            const double xv = __ldg(p.x_old + src * d + c);
+            loc[r * ld + c] = (p.a * xv) + mshift[c];
+        }
+        for (int j = tid; j < d * cnt; j += blockDim.x) {
+            const int m = j / cnt, r = j - m * cnt;
+            eps_s[m * T + r] = ldg_stream(p.eps + static_cast<int64_t>(m) * p.eps_ld + first + r);
+        }
+        __syncthreads();
+        // perturb: x' = mu + (S @ eps)[:, i]   (resamplers.py:332); dgemm-style k-ordered FMA chain
+        for (int j = tid; j < d * cnt; j += blockDim.x) {
+            const int c = j / cnt, r = j - c * cnt;
+            double z = 0.0;
+            for (int m = 0; m < d; ++m) z = fma(S[c * d + m], eps_s[m * T + r], z);
+            loc[r * ld + c] = loc[r * ld + c] + z;
+        }
+        __syncthreads();
+        if (p.postselect) {
+            unsigned int bad = 0;
+            for (int r = tid; r < cnt; r += blockDim.x) {
+                const double* xr = loc + r * ld;
+                auto row = [&](int c) { return xr[c]; };
+                const bool ok = model_valid(p.mv, row);
+                p.invalid[first + r] = ok ? 0 : 1;
+                bad += ok ? 0u : 1u;
+            }
+            if (bad) atomicAdd(&block_bad, bad);
+        }
+        for (int j = tid; j < cnt * d; j += blockDim.x) {
+            const int r = j / d, c = j - r * d;
+            stg_stream(p.x_new + first * d + j, loc[r * ld + c]);
+        }
+        __syncthreads();
+        if (tid == 0 && block_bad) atomicAdd(p.n_invalid, static_cast<unsigned long long>(block_bad));
+    }
+}
+
+// Retry: one thread per still-invalid particle r (few of them).
+__global__ void __launch_bounds__(128) lw_retry_kernel(const __grid_constant__ LwParams p, int64_t k) {
+    const int d = p.d;
+    const double* S = p.consts;
+    const double* mshift = p.consts + d * d;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < k; r += stride) {
+        const int64_t dst = p.idxs[r];
+        const int64_t src = p.js[r];  // prefix-of-the-original-means quirk (resamplers.py:372)
+        double xr[QB_MAX_D];
+        for (int c = 0; c < d; ++c) {
+            double z = 0.0;
+            for (int m = 0; m < d; ++m) z = fma(S[c * d + m], p.eps[static_cast<int64_t>(m) * p.eps_ld + r], z);
+            const double mu = (p.a * p.x_old[src * d + c]) + mshift[c];
+            xr[c] = mu + z;
+        }
+        for (int c = 0; c < d; ++c) p.x_new[dst * d + c] = xr[c];
+        bool ok = true;
+        if (p.postselect) {
+            auto row = [&](int c) { return xr[c]; };
+            ok = model_valid(p.mv, row);
+        }
+        p.invalid[dst] = ok ? 0 : 1;
+        if (!ok) atomicAdd(p.n_invalid, 1ull);
+    }
+}
+
+// =============================================================================
+// Ordered compaction of the invalid flags
+// =============================================================================
+constexpr int CMP_THREADS = 256;
+constexpr int CMP_ITEMS = 16;
+constexpr int CMP_TILE = CMP_THREADS * CMP_ITEMS;
+
+__global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(const uint8_t* __restrict__ flags, int64_t n,
+                                                                    unsigned long long* __restrict__ tile_counts) {
+    __shared__ unsigned int wsum[CMP_THREADS / 32];
+    const int64_t ntiles = (n + CMP_TILE - 1) / CMP_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * CMP_TILE + static_cast<int64_t>(threadIdx.x) * CMP_ITEMS;
+        unsigned int c = 0;
+#pragma unroll
+        for (int k = 0; k < CMP_ITEMS; ++k)
+            if (base + k < n && flags[base + k]) ++c;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tot = 0;
+            for (int k = 0; k < CMP_THREADS / 32; ++k) tot += wsum[k];
+            tile_counts[t] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void compact_scan_kernel(unsigned long long* tile_counts, int64_t ntiles, int64_t* total) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long run = 0;
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const unsigned long long c = tile_counts[t];
+        tile_counts[t] = run;
+        run += c;
+    }
+    *total = static_cast<int64_t>(run);
+}
+
+__global__ void __launch_bounds__(CMP_THREADS) compact_write_kernel(const uint8_t* __restrict__ flags, int64_t n,
+                                                                    const unsigned long long* __restrict__ tile_off,
+                                                                    int64_t* __restrict__ out) {
+    __shared__ unsigned int wsum[CMP_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t ntiles = (n + CMP_TILE - 1) / CMP_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * CMP_TILE + static_cast<int64_t>(threadIdx.x) * CMP_ITEMS;
+        unsigned int c = 0;
+#pragma unroll
+        for (int k = 0; k < CMP_ITEMS; ++k)
+            if (base + k < n && flags[base + k]) ++c;
+        unsigned int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        unsigned int wbase = 0;
+        for (int k = 0; k < wid; ++k) wbase += wsum[k];
+        unsigned long long pos = tile_off[t] + wbase + (inc - c);
+#pragma unroll
+        for (int k = 0; k < CMP_ITEMS; ++k)
+            if (base + k < n && flags[base + k]) out[pos++] = base + k;
+        __syncthreads();
+    }
+}
+
+static int capped_grid(int64_t want, int per_sm) {
+    const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
+int validate_model(const qb_model* m);
+
+// S (d*d) and (1-a)*mean (d) live in a small device buffer owned by the library
+// (one per stream would be needed for concurrent resamples; the reference path is
+// single-threaded, SURVEY §8b "Threading").
+static double* g_consts = nullptr;
+static int g_consts_dev = -1;
+
+static int upload_consts(const double* h_mean, const double* h_S, double a, int d, cudaStream_t st,
+                         const double** out) {
+    int dev = 0;
+    QB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_consts == nullptr || g_consts_dev != dev) {
+        QB_CUDA_CHECK(cudaMalloc(&g_consts, (QB_MAX_D * QB_MAX_D + QB_MAX_D) * sizeof(double)));
+        g_consts_dev = dev;
+    }
+    static thread_local double host[QB_MAX_D * QB_MAX_D + QB_MAX_D];
+    for (int j = 0; j < d * d; ++j) host[j] = h_S[j];
+    const double oma = 1.0 - a;
+    for (int c = 0; c < d; ++c) host[d * d + c] = oma * h_mean[c];  // (1 - a) * mean
+    QB_CUDA_CHECK(cudaMemcpyAsync(g_consts, host, (d * d + d) * sizeof(double), cudaMemcpyHostToDevice, st));
+    *out = g_consts;
+    return QB_OK;
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" size_t qb_cdf_workspace_bytes(int64_t n) {
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return static_cast<size_t>(ntiles + 1) * sizeof(double) + 256;
+}
+
+extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode, void* d_ws,
+                      size_t ws_bytes, void* stream) {
+    QB_REQUIRE(d_w && d_stats && d_cdf && d_ws && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_cdf: bad arguments");
+    QB_REQUIRE(ws_bytes >= qb_cdf_workspace_bytes(n), QB_ERR_WORKSPACE, "qb_cdf: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    if (mode == QB_SCAN_EXACT) {
+        cdf_sequential_kernel<<<1, 64, 0, st>>>(d_w, d_stats, n, d_cdf);
+        QB_CUDA_CHECK(cudaGetLastError());
+        return QB_OK;
+    }
+    QB_REQUIRE(mode == QB_SCAN_FAST, QB_ERR_INVALID_ARGUMENT, "qb_cdf: unknown mode %d", mode);
+    double* tiles = reinterpret_cast<double*>(d_ws);
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int grid = capped_grid(ntiles, 8);
+    cdf_tile_sums_kernel<<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles);
+    QB_CUDA_CHECK(cudaGetLastError());
+    cdf_scan_tiles_kernel<<<1, SCAN_THREADS, 0, st>>>(tiles, ntiles);
+    QB_CUDA_CHECK(cudaGetLastError());
+    cdf_write_kernel<<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles, d_cdf);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_draw(const double* d_cdf, int64_t n, const double* d_u, int64_t n_draw, int64_t* d_js,
+                       int64_t* d_overflow, void* stream) {
+    QB_REQUIRE(d_cdf && d_u && d_js && d_overflow && n >= 1 && n_draw >= 1, QB_ERR_INVALID_ARGUMENT,
+               "qb_draw: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    QB_CUDA_CHECK(cudaMemsetAsync(d_overflow, 0, sizeof(int64_t), st));
+    draw_kernel<<<capped_grid((n_draw + 255) / 256, 8), 256, 0, st>>>(
+        d_cdf, n, d_u, n_draw, d_js, reinterpret_cast<unsigned long long*>(d_overflow));
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d, const int64_t* d_js,
+                          const double* h_mean, const double* h_S, double a, const double* d_eps, int64_t n_new,
+                          double* d_x_new, int32_t postselect, uint8_t* d_invalid, int64_t* d_n_invalid,
+                          void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_x_old && d_js && h_mean && h_S && d_eps && d_x_new && d_invalid && d_n_invalid,
+               QB_ERR_INVALID_ARGUMENT, "qb_lw_move: NULL pointer argument");
+    QB_REQUIRE(d == model->d && n_old >= 1 && n_new >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_move: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    LwParams p;
+    rc = upload_consts(h_mean, h_S, a, d, st, &p.consts);
+    if (rc != QB_OK) return rc;
+    p.x_old = d_x_old;
+    p.js = d_js;
+    p.eps = d_eps;
+    p.x_new = d_x_new;
+    p.invalid = d_invalid;
+    p.n_invalid = reinterpret_cast<unsigned long long*>(d_n_invalid);
+    p.idxs = nullptr;
+    p.n_old = n_old;
+    p.n_new = n_new;
+    p.eps_ld = n_new;
+    p.d = d;
+    p.tile = (d <= 4) ? 512 : ((d <= 16) ? 128 : 32);
+    p.postselect = postselect;
+    p.pad = 0;
+    p.a = a;
+    p.mv = make_model_view(*model);
+    QB_CUDA_CHECK(cudaMemsetAsync(d_n_invalid, 0, sizeof(int64_t), st));
+    if (!postselect) QB_CUDA_CHECK(cudaMemsetAsync(d_invalid, 0, static_cast<size_t>(n_new), st));
+    const size_t smem = (static_cast<size_t>(p.tile) * (d | 1) + static_cast<size_t>(d) * p.tile + d * d + d) *
+                        sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        QB_CUDA_CHECK(cudaFuncSetAttribute(lw_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    const int64_t ntiles = (n_new + p.tile - 1) / p.tile;
+    lw_move_kernel<<<capped_grid(ntiles, 4), 256, smem, st>>>(p);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" size_t qb_compact_workspace_bytes(int64_t n) {
+    const int64_t ntiles = (n + CMP_TILE - 1) / CMP_TILE;
+    return static_cast<size_t>(ntiles + 1) * sizeof(unsigned long long) + 256;
+}
+
+extern "C" int qb_compact_invalid(const uint8_t* d_invalid, int64_t n, int64_t* d_idxs_out, int64_t* d_count,
+                                  void* d_ws, size_t ws_bytes, void* stream) {
+    QB_REQUIRE(d_invalid && d_idxs_out && d_count && d_ws && n >= 1, QB_ERR_INVALID_ARGUMENT,
+               "qb_compact_invalid: bad arguments");
+    QB_REQUIRE(ws_bytes >= qb_compact_workspace_bytes(n), QB_ERR_WORKSPACE, "qb_compact_invalid: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned long long* tiles = reinterpret_cast<unsigned long long*>(d_ws);
+    const int64_t ntiles = (n + CMP_TILE - 1) / CMP_TILE;
+    const int grid = capped_grid(ntiles, 8);
+    compact_count_kernel<<<grid, CMP_THREADS, 0, st>>>(d_invalid, n, tiles);
+    QB_CUDA_CHECK(cudaGetLastError());
+    compact_scan_kernel<<<1, 32, 0, st>>>(tiles, ntiles, d_count);
+    QB_CUDA_CHECK(cudaGetLastError());
+    compact_write_kernel<<<grid, CMP_THREADS, 0, st>>>(d_invalid, n, tiles, d_idxs_out);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d, const int64_t* d_js,
+                           const int64_t* d_idxs, int64_t k, const double* h_mean, const double* h_S, double a,
+                           const double* d_eps, double* d_x_new, uint8_t* d_invalid, int64_t* d_n_invalid,
+                           void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_x_old && d_js && d_idxs && h_mean && h_S && d_eps && d_x_new && d_invalid && d_n_invalid,
+               QB_ERR_INVALID_ARGUMENT, "qb_lw_retry: NULL pointer argument");
+    QB_REQUIRE(d == model->d && n_old >= 1 && k >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_retry: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    LwParams p;
+    rc = upload_consts(h_mean, h_S, a, d, st, &p.consts);
+    if (rc != QB_OK) return rc;
+    p.x_old = d_x_old;
+    p.js = d_js;
+    p.eps = d_eps;
+    p.x_new = d_x_new;
+    p.invalid = d_invalid;
+    p.n_invalid = reinterpret_cast<unsigned long long*>(d_n_invalid);
+    p.idxs = d_idxs;
+    p.n_old = n_old;
+    p.n_new = 0;
+    p.eps_ld = k;
+    p.d = d;
+    p.tile = 0;
+    p.postselect = 1;
+    p.pad = 0;
+    p.a = a;
+    p.mv = make_model_view(*model);
+    QB_CUDA_CHECK(cudaMemsetAsync(d_n_invalid, 0, sizeof(int64_t), st));
+    lw_retry_kernel<<<capped_grid((k + 127) / 128, 8), 128, 0, st>>>(p, k);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}

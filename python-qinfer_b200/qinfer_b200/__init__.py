@@ -1,0 +1,18 @@
+"""qinfer_b200 — B200-native SMC particle-filter engine behind QInfer's
+SMCUpdater / Model / Resampler plugin surface (hot path only)."""
+from ._exceptions import ApproximationWarning, ResamplerError, ResamplerWarning, UnsupportedModelError
+from .distributions import (GinibreTomographyPrior, ParticleDistribution, PostselectedDistribution,
+                            UniformDistribution)
+from .models import (BinomialModel, Model, RandomizedBenchmarkingModel, SimpleInversionModel,
+                     SimplePrecessionModel, TomographyBasis, TomographyModel, describe_model, gell_mann_basis,
+                     pauli_basis)
+from .resamplers import LiuWestResampler, Resampler, sqrtm_psd
+from .smc import SMCUpdater
+
+__all__ = [
+    'ApproximationWarning', 'ResamplerError', 'ResamplerWarning', 'UnsupportedModelError',
+    'GinibreTomographyPrior', 'ParticleDistribution', 'PostselectedDistribution', 'UniformDistribution',
+    'BinomialModel', 'Model', 'RandomizedBenchmarkingModel', 'SimpleInversionModel', 'SimplePrecessionModel',
+    'TomographyBasis', 'TomographyModel', 'describe_model', 'gell_mann_basis', 'pauli_basis',
+    'LiuWestResampler', 'Resampler', 'sqrtm_psd', 'SMCUpdater',
+]

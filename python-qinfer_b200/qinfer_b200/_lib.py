@@ -1,0 +1,105 @@
+"""ctypes binding of ``libqinfer_b200.so`` (the C ABI declared in include/qinfer_b200.h).
+
+The product has no CPU fallback: if the shared library is missing or a call
+fails this module raises, loudly.
+"""
+import ctypes
+import os
+
+QB_MAX_D = 64
+QB_STAT_NORM, QB_STAT_SUMSQ, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_INV_NORM, QB_STAT_NESS = range(6)
+QB_STAT_COUNT = 16
+QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY = 1, 2, 3
+QB_SCAN_FAST, QB_SCAN_EXACT = 0, 1
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqinfer_b200.so")
+
+
+class QbModel(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("d", ctypes.c_int32), ("binomial", ctypes.c_int32),
+                ("interleaved", ctypes.c_int32), ("min_freq", ctypes.c_double)]
+
+
+class QbExpparams(ctypes.Structure):
+    _fields_ = [("t", ctypes.c_double), ("w_", ctypes.c_double), ("m", ctypes.c_int64),
+                ("reference", ctypes.c_int32), ("reserved", ctypes.c_int32), ("n_meas", ctypes.c_int64),
+                ("meas", ctypes.c_double * QB_MAX_D)]
+
+
+class QbError(RuntimeError):
+    pass
+
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I32 = ctypes.c_int32
+_F64 = ctypes.c_double
+_SZ = ctypes.c_size_t
+_U64 = ctypes.c_uint64
+
+# name -> (restype, argtypes); every symbol include/qinfer_b200.h declares
+SIGNATURES = {
+    "qb_abi_version": (ctypes.c_int, []),
+    "qb_last_error": (ctypes.c_char_p, []),
+    "qb_device_sm_count": (ctypes.c_int, []),
+    "qb_weights_set_uniform": (ctypes.c_int, [_P, _I64, _P, _P]),
+    "qb_weights_normalized": (ctypes.c_int, [_P, _I64, _P, _P, _P]),
+    "qb_weights_restat": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P]),
+    "qb_weights_clip": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P]),
+    "qb_update_workspace_bytes": (_SZ, [_I64, _I32]),
+    "qb_fused_update": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I64, _P, _I64,
+                                       _P, _P, _P, _P, _P, _SZ, _P]),
+    "qb_likelihood": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I32,
+                                     ctypes.POINTER(_I64), _I32, _P, _I64, _P, _P]),
+    "qb_are_models_valid": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _P, _P]),
+    "qb_moments_workspace_bytes": (_SZ, [_I64, _I32]),
+    "qb_moments": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _SZ, _P]),
+    "qb_cdf_workspace_bytes": (_SZ, [_I64]),
+    "qb_cdf": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _P, _SZ, _P]),
+    "qb_draw": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _P]),
+    "qb_lw_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, ctypes.POINTER(_F64),
+                                  ctypes.POINTER(_F64), _F64, _P, _I64, _P, _I32, _P, _P, _P]),
+    "qb_compact_workspace_bytes": (_SZ, [_I64]),
+    "qb_compact_invalid": (ctypes.c_int, [_P, _I64, _P, _P, _P, _SZ, _P]),
+    "qb_lw_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _I64, ctypes.POINTER(_F64),
+                                   ctypes.POINTER(_F64), _F64, _P, _P, _P, _P, _P]),
+    "qb_tomo_canonicalize": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P]),
+    "qb_rng_uniform": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
+    "qb_rng_normal": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise QbError(
+            "libqinfer_b200.so is not built (%s). Run `python python-qinfer_b200/build.py`; "
+            "this engine has no CPU fallback." % _LIB_PATH)
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    if lib.qb_abi_version() != 1:
+        raise QbError("libqinfer_b200.so ABI version %d, expected 1" % lib.qb_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().qb_last_error()
+        raise QbError("qinfer_b200 call failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+
+
+def f64_array(values):
+    return (ctypes.c_double * len(values))(*[float(v) for v in values])

@@ -1,0 +1,310 @@
+"""Device-resident particle cloud: torch tensors for memory/streams, the C ABI for all math.
+
+``DeviceCloud`` is the single owner of the HBM state of one updater (or one
+shard of it): the (n, d) fp64 particle slab (double-buffered for resampling),
+the unnormalised weight vector (ping-pong so a rejected update leaves the old
+weights intact, smc.py:423-441), the 16-double stats block and the kernel
+workspaces.  Every arithmetic step is a call into ``libqinfer_b200.so``;
+nothing here computes on the CPU and nothing falls back to it.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (QB_STAT_COUNT, QB_STAT_INV_NORM, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NESS, QB_STAT_NORM,
+                   QB_STAT_SUMSQ, check)
+
+
+def _require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.QbError("qinfer_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    return dev
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceCloud(object):
+    def __init__(self, desc, n, device=None):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.desc = desc
+        self.n = int(n)
+        self.d = int(desc.d)
+        with torch.cuda.device(self.device):
+            f64 = dict(dtype=torch.float64, device=self.device)
+            self.x = torch.empty((self.n, self.d), **f64)
+            self.x_alt = None                     # allocated at the first resample
+            self.w = torch.empty((self.n,), **f64)
+            self.w_alt = torch.empty((self.n,), **f64)
+            self.stats = torch.zeros((QB_STAT_COUNT,), **f64)
+            self.stats_alt = torch.zeros((QB_STAT_COUNT,), **f64)
+            ws_bytes = max(self.lib.qb_update_workspace_bytes(self.n, self.d),
+                           self.lib.qb_moments_workspace_bytes(self.n, self.d),
+                           self.lib.qb_cdf_workspace_bytes(self.n),
+                           self.lib.qb_compact_workspace_bytes(self.n))
+            self.ws = torch.zeros(((ws_bytes + 7) // 8,), **f64)       # zeroed once: holds the launch ticket
+            self.ws_bytes = self.ws.numel() * 8
+            self.moments_out = torch.empty((1 + self.d + self.d * self.d,), **f64)
+            self.stats_host = torch.empty((QB_STAT_COUNT,), dtype=torch.float64, pin_memory=True)
+            self.counter = torch.zeros((2,), dtype=torch.int64, device=self.device)
+            self.counter_host = torch.empty((2,), dtype=torch.int64, pin_memory=True)
+            self.basis_dev = None
+            if desc.basis is not None:
+                b = np.ascontiguousarray(desc.basis).view(np.float64).reshape(-1)
+                self.basis_dev = torch.from_numpy(b.copy()).to(self.device)
+            self.lib_model = ctypes.pointer(desc.c_model)
+        # resample scratch, allocated lazily
+        self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = None
+        self.launches = 0
+        self.time_updates = False          # bench: CUDA events around each fused-update launch
+        self.last_update_events = None
+
+    # ---- host <-> device ---------------------------------------------------
+    def upload_locations(self, locs):
+        locs = np.ascontiguousarray(locs, dtype=np.float64)
+        if locs.shape != (self.n, self.d):
+            raise ValueError("particle_locations must have shape (%d, %d), got %s" % (self.n, self.d, locs.shape))
+        self.x.copy_(torch.from_numpy(locs))
+
+    def download_locations(self):
+        return self.x.cpu().numpy()
+
+    def upload_weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        if w.shape != (self.n,):
+            raise ValueError("particle_weights must have shape (%d,), got %s" % (self.n, w.shape))
+        self.w.copy_(torch.from_numpy(w))
+        check(self.lib.qb_weights_restat(_ptr(self.w), self.n, _ptr(self.stats), _ptr(self.ws), self.ws_bytes,
+                                         _stream()))
+        self.launches += 2
+
+    def download_weights(self):
+        """Normalised weights, materialised by a kernel then copied out."""
+        out = self.w_alt
+        check(self.lib.qb_weights_normalized(_ptr(self.w), self.n, _ptr(self.stats), _ptr(out), _stream()))
+        self.launches += 1
+        return out.cpu().numpy()
+
+    def set_uniform_weights(self):
+        check(self.lib.qb_weights_set_uniform(_ptr(self.w), self.n, _ptr(self.stats), _stream()))
+        self.launches += 1
+
+    def read_stats(self, which=None):
+        """Blocking read of a stats block (norm, sumsq, min, nbad, inv_norm, n_ess)."""
+        src = self.stats if which is None else which
+        self.stats_host.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.stats_host.numpy()
+
+    # ---- the hot kernel -------------------------------------------------------
+    def fused_update(self, ep_record, outcome):
+        """Launch the fused update into the alternate weight/stats buffers and
+        return the new stats (host).  Call ``commit_update`` to accept it."""
+        if self.time_updates:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep_record), int(outcome), _ptr(self.x), self.n,
+                                       _ptr(self.w), _ptr(self.w_alt), _ptr(self.stats), _ptr(self.stats_alt),
+                                       _ptr(self.ws), self.ws_bytes, _stream()))
+        if self.time_updates:
+            e1.record()
+            self.last_update_events = (e0, e1)
+        self.launches += 1
+
+    def commit_update(self):
+        self.w, self.w_alt = self.w_alt, self.w
+        self.stats, self.stats_alt = self.stats_alt, self.stats
+
+    def clip_weights(self):
+        """smc.py:416-418 on the committed weights."""
+        check(self.lib.qb_weights_clip(_ptr(self.w), self.n, _ptr(self.stats), _ptr(self.ws), self.ws_bytes,
+                                       _stream()))
+        self.launches += 2
+
+    # ---- moments ------------------------------------------------------------------
+    def moments(self):
+        """(sum w, mean (d,), second moment (d, d)) of the normalised cloud."""
+        check(self.lib.qb_moments(_ptr(self.x), _ptr(self.w), _ptr(self.stats), self.n, self.d,
+                                  _ptr(self.moments_out), _ptr(self.ws), self.ws_bytes, _stream()))
+        self.launches += 2
+        out = self.moments_out.cpu().numpy()
+        d = self.d
+        return out[0], out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
+
+    # ---- resampling -----------------------------------------------------------------
+    def _resample_scratch(self, n_new):
+        dev = self.device
+        if self._cdf is None or self._cdf.numel() != self.n:
+            self._cdf = torch.empty((self.n,), dtype=torch.float64, device=dev)
+        if self._js is None or self._js.numel() != n_new:
+            self._js = torch.empty((n_new,), dtype=torch.int64, device=dev)
+            self._u = torch.empty((n_new,), dtype=torch.float64, device=dev)
+            self._eps = torch.empty((self.d * n_new,), dtype=torch.float64, device=dev)
+            self._invalid = torch.zeros((n_new,), dtype=torch.uint8, device=dev)
+            self._idxs = torch.empty((n_new,), dtype=torch.int64, device=dev)
+
+    def preallocate_resample(self, n_new=None):
+        """Allocate the resampling scratch and the second particle slab up front (no allocation in the loop)."""
+        n_new = self.n if n_new is None else int(n_new)
+        self._resample_scratch(n_new)
+        if self.x_alt is None or self.x_alt.shape[0] != n_new:
+            self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+
+    def cdf(self, mode):
+        self._resample_scratch(self.n if self._js is None else self._js.numel())
+        check(self.lib.qb_cdf(_ptr(self.w), _ptr(self.stats), self.n, _ptr(self._cdf), int(mode), _ptr(self.ws),
+                              self.ws_bytes, _stream()))
+        self.launches += 1 if mode == _lib.QB_SCAN_EXACT else 3
+        return self._cdf
+
+    def draw(self, u_dev, n_new):
+        check(self.lib.qb_draw(_ptr(self._cdf), self.n, _ptr(u_dev), int(n_new), _ptr(self._js),
+                               _ptr(self.counter[1:]), _stream()))
+        self.launches += 1
+        return self._js
+
+    def lw_move(self, mean, S, a, eps_dev, n_new, postselect):
+        if self.x_alt is None or self.x_alt.shape[0] != n_new:
+            self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+        check(self.lib.qb_lw_move(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._js),
+                                  _lib.f64_array(mean), _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
+                                  _ptr(eps_dev), int(n_new), _ptr(self.x_alt), int(bool(postselect)),
+                                  _ptr(self._invalid), _ptr(self.counter), _stream()))
+        self.launches += 1
+
+    def read_counter(self):
+        self.counter_host.copy_(self.counter, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(self.counter_host[0]), int(self.counter_host[1])
+
+    def compact_invalid(self, n_new):
+        check(self.lib.qb_compact_invalid(_ptr(self._invalid), int(n_new), _ptr(self._idxs), _ptr(self.counter),
+                                          _ptr(self.ws), self.ws_bytes, _stream()))
+        self.launches += 3
+
+    def lw_retry(self, mean, S, a, eps_dev, k):
+        check(self.lib.qb_lw_retry(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._js), _ptr(self._idxs),
+                                   int(k), _lib.f64_array(mean), _lib.f64_array(np.asarray(S).reshape(-1)),
+                                   float(a), _ptr(eps_dev), _ptr(self.x_alt), _ptr(self._invalid),
+                                   _ptr(self.counter), _stream()))
+        self.launches += 1
+
+    def adopt_resampled(self, n_new):
+        """Make the freshly written slab current; weights become uniform."""
+        if n_new != self.n:
+            self.n = int(n_new)
+            f64 = dict(dtype=torch.float64, device=self.device)
+            self.w = torch.empty((self.n,), **f64)
+            self.w_alt = torch.empty((self.n,), **f64)
+            old_x = self.x
+            self.x = self.x_alt
+            self.x_alt = None
+            del old_x
+        else:
+            self.x, self.x_alt = self.x_alt, self.x
+        self.set_uniform_weights()
+
+    def canonicalize(self):
+        if self.desc.kind != _lib.QB_MODEL_TOMOGRAPHY:
+            return
+        check(self.lib.qb_tomo_canonicalize(_ptr(self.x), self.n, self.desc.dim, _ptr(self.basis_dev),
+                                            int(self.desc.allow_subnormalized), _stream()))
+        self.launches += 1
+
+    def rng_uniform(self, out, n, seed, offset):
+        check(self.lib.qb_rng_uniform(_ptr(out), int(n), int(seed), int(offset), _stream()))
+        self.launches += 1
+
+    def rng_normal(self, out, n, seed, offset):
+        check(self.lib.qb_rng_normal(_ptr(out), int(n), int(seed), int(offset), _stream()))
+        self.launches += 1
+
+
+# ---------------------------------------------------------------------------
+# Host-array conveniences used by the Model classes (upload, run kernel, download)
+# ---------------------------------------------------------------------------
+
+def device_likelihood(desc, x_dev, outcomes, expparams):
+    """L[o, i, e] for particles already in HBM (``x_dev``: (n, d) float64 cuda tensor)."""
+    lib = _lib.load()
+    outcomes = np.atleast_1d(np.asarray(outcomes)).astype(np.int64)
+    expparams = np.atleast_1d(np.asarray(expparams))
+    n, n_e, n_o = x_dev.shape[0], expparams.shape[0], outcomes.shape[0]
+    eps = (_lib.QbExpparams * n_e)(*[desc.expparams_record(expparams, e) for e in range(n_e)])
+    outs = (ctypes.c_int64 * n_o)(*[int(o) for o in outcomes])
+    L = torch.empty((n_o, n, n_e), dtype=torch.float64, device=x_dev.device)
+    check(lib.qb_likelihood(ctypes.pointer(desc.c_model), eps, n_e, outs, n_o, _ptr(x_dev), n, _ptr(L), _stream()))
+    return L.cpu().numpy()
+
+
+def host_likelihood(desc, outcomes, modelparams, expparams):
+    dev = _require_cuda()
+    x = np.ascontiguousarray(modelparams, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    if x.shape[1] != desc.d:
+        raise ValueError("modelparams has %d columns, model has %d parameters" % (x.shape[1], desc.d))
+    return device_likelihood(desc, torch.from_numpy(x).to(dev), outcomes, expparams)
+
+
+def host_are_models_valid(desc, modelparams):
+    lib = _lib.load()
+    dev = _require_cuda()
+    x = np.ascontiguousarray(modelparams, dtype=np.float64)
+    xd = torch.from_numpy(x).to(dev)
+    out = torch.empty((x.shape[0],), dtype=torch.uint8, device=dev)
+    check(lib.qb_are_models_valid(ctypes.pointer(desc.c_model), _ptr(xd), x.shape[0], _ptr(out), _stream()))
+    return out.cpu().numpy().astype(bool)
+
+
+def host_canonicalize(desc, modelparams):
+    lib = _lib.load()
+    dev = _require_cuda()
+    x = np.ascontiguousarray(modelparams, dtype=np.float64)
+    xd = torch.from_numpy(x).to(dev)
+    b = np.ascontiguousarray(desc.basis).view(np.float64).reshape(-1)
+    bd = torch.from_numpy(b.copy()).to(dev)
+    check(lib.qb_tomo_canonicalize(_ptr(xd), x.shape[0], desc.dim, _ptr(bd), int(desc.allow_subnormalized),
+                                   _stream()))
+    return xd.cpu().numpy()
+
+
+def host_weight_stats(weights):
+    """(sum w, sum w^2) of host weights, reduced on the device."""
+    lib = _lib.load()
+    dev = _require_cuda()
+    w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)
+    n = w.numel()
+    stats = torch.zeros((QB_STAT_COUNT,), dtype=torch.float64, device=dev)
+    ws_bytes = lib.qb_update_workspace_bytes(n, 1)
+    ws = torch.zeros(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
+    check(lib.qb_weights_restat(_ptr(w), n, _ptr(stats), _ptr(ws), ws.numel() * 8, _stream()))
+    s = stats.cpu().numpy()
+    return float(s[QB_STAT_NORM]), float(s[QB_STAT_SUMSQ])
+
+
+def host_moments(weights, locations):
+    """(sum w, mean, second moment) of a host-held particle set, reduced on the device."""
+    lib = _lib.load()
+    dev = _require_cuda()
+    x = np.ascontiguousarray(locations, dtype=np.float64)
+    n, d = x.shape
+    xd = torch.from_numpy(x).to(dev)
+    w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(dev)
+    stats = torch.zeros((QB_STAT_COUNT,), dtype=torch.float64, device=dev)
+    stats[QB_STAT_INV_NORM] = 1.0
+    ws_bytes = lib.qb_moments_workspace_bytes(n, d)
+    ws = torch.zeros(((ws_bytes + 7) // 8,), dtype=torch.float64, device=dev)
+    out = torch.empty((1 + d + d * d,), dtype=torch.float64, device=dev)
+    check(lib.qb_moments(_ptr(xd), _ptr(w), _ptr(stats), n, d, _ptr(out), _ptr(ws), ws.numel() * 8, _stream()))
+    o = out.cpu().numpy()
+    return o[0], o[1:1 + d].copy(), o[1 + d:].reshape(d, d).copy()

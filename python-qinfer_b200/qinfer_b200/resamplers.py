@@ -1,0 +1,195 @@
+"""Resampler plugin surface: ``Resampler`` ABC and the B200 ``LiuWestResampler``.
+
+Same call contract as qinfer.resamplers (resamplers.py:73-95, 223-392):
+``resampler(model, particle_dist, n_particles=None, precomputed_mean=None,
+precomputed_cov=None) -> particle distribution``.  The Liu-West steps run as
+CUDA kernels (moments, CDF scan, bisection draw, shrink+perturb+validity,
+ordered compaction, retry); the host keeps only what the reference keeps in
+scalar Python: the d x d ``sqrtm_psd`` and the control flow of the retry loop.
+
+Two extra, keyword-only knobs that the reference does not have:
+
+``rng``   ``'numpy'`` (default) draws the uniforms and the perturbation normals
+          from the legacy global ``np.random`` stream with exactly the calls,
+          shapes and order of resamplers.py:319,332 and uploads them — resample
+          indices are then bit-identical to the reference under the same seed.
+          ``'philox'`` generates both on the device (counter-based, seeded by
+          ``seed``) for throughput.
+``scan``  ``'exact'`` (default) reproduces ``np.cumsum``'s sequential fp64
+          rounding bit for bit; ``'fast'`` is a re-associated parallel scan.
+"""
+import abc
+import warnings
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from . import _lib
+from ._exceptions import ResamplerError, ResamplerWarning
+from .distributions import ParticleDistribution, covariance_from_moments
+
+
+def sqrtm_psd(A, est_error=True, check_finite=True):
+    """PSD matrix square root through ``scipy.linalg.eigh`` with non-positive
+    eigenvalues clipped — the same host call as utils.py:593-607 (d x d, d <= 64)."""
+    w, v = scipy.linalg.eigh(A, check_finite=check_finite)
+    w[w <= 0] = 0
+    np.sqrt(w, out=w)
+    A_sqrt = (v * w).dot(v.conj().T)
+    if est_error:
+        return A_sqrt, np.linalg.norm(np.dot(A_sqrt, A_sqrt) - A, 'fro')
+    return A_sqrt
+
+
+class Resampler(abc.ABC):
+    @abc.abstractmethod
+    def __call__(self, model, particle_dist, n_particles=None, precomputed_mean=None, precomputed_cov=None):
+        """Resample ``particle_dist`` into ``n_particles`` new particles."""
+
+
+class DeviceParticles(object):
+    """What the device path of a resampler returns: the new particles are already
+    in the cloud's alternate slab; host arrays are produced only on request."""
+
+    def __init__(self, cloud, n_particles):
+        self.cloud = cloud
+        self.n_particles = int(n_particles)
+
+    @property
+    def particle_weights(self):
+        return np.ones((self.n_particles,)) / self.n_particles
+
+    @property
+    def particle_locations(self):
+        return self.cloud.x_alt.cpu().numpy()
+
+    @property
+    def n_rvs(self):
+        return self.cloud.d
+
+
+class LiuWestResampler(Resampler):
+    def __init__(self, a=0.98, h=None, maxiter=1000, debug=False, postselect=True, zero_cov_comp=1e-10,
+                 default_n_particles=None, kernel=np.random.randn, *, rng='numpy', seed=None, scan='exact'):
+        self._default_n_particles = default_n_particles
+        self._override_h = False
+        self.a = a
+        if h is not None:
+            self._override_h = True
+            self._h = h
+        self._maxiter = maxiter
+        self._debug = debug
+        self._postselect = postselect
+        self._zero_cov_comp = zero_cov_comp
+        self._kernel = kernel
+        if rng not in ('numpy', 'philox'):
+            raise ValueError("rng must be 'numpy' or 'philox'")
+        if scan not in ('exact', 'fast'):
+            raise ValueError("scan must be 'exact' or 'fast'")
+        if rng == 'philox' and kernel is not np.random.randn:
+            raise ValueError("a custom perturbation kernel needs rng='numpy' (it is a host callable)")
+        self._rng = rng
+        self._scan = scan
+        self._seed = int(seed) if seed is not None else 0x5EED
+        self._philox_offset = 0
+        self.last_n_iters = 0
+        self.last_overflow = 0
+
+    @property
+    def a(self):
+        return self._a
+
+    @a.setter
+    def a(self, new_a):
+        self._a = new_a
+        if not self._override_h:
+            self._h = np.sqrt(1 - new_a ** 2)
+
+    @property
+    def h(self):
+        return self._h
+
+    # -- helpers ---------------------------------------------------------------
+    def _uniforms(self, cloud, n):
+        if self._rng == 'numpy':
+            u = np.random.random((n,))                       # resamplers.py:319
+            cloud._u.copy_(torch.from_numpy(u))
+        else:
+            cloud.rng_uniform(cloud._u, n, self._seed, self._philox_offset)
+            self._philox_offset += (n + 1) // 2
+        return cloud._u
+
+    def _normals(self, cloud, d, k):
+        buf = cloud._eps[:d * k]
+        if self._rng == 'numpy':
+            eps = np.ascontiguousarray(self._kernel(d, k), dtype=np.float64)   # resamplers.py:332, shape (d, k)
+            if eps.shape != (d, k):
+                raise ValueError("resampling kernel returned shape %s, expected %s" % (eps.shape, (d, k)))
+            buf.copy_(torch.from_numpy(eps.reshape(-1)))
+        else:
+            cloud.rng_normal(buf, d * k, self._seed ^ 0x9E3779B97F4A7C15, self._philox_offset)
+            self._philox_offset += (d * k + 1) // 2
+        return buf
+
+    # -- the call ------------------------------------------------------------------
+    def __call__(self, model, particle_dist, n_particles=None, precomputed_mean=None, precomputed_cov=None):
+        from .engine import DeviceCloud
+        from .models import describe_model
+
+        cloud = getattr(particle_dist, '_cloud', None)
+        on_device = cloud is not None
+        if not on_device:                  # stand-alone use on a host-held distribution: upload it
+            desc = describe_model(model)
+            cloud = DeviceCloud(desc, particle_dist.n_particles)
+            cloud.upload_locations(particle_dist.particle_locations)
+            cloud.upload_weights(particle_dist.particle_weights)
+
+        mean = particle_dist.est_mean() if precomputed_mean is None else precomputed_mean
+        cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
+        if n_particles is None:
+            n_particles = (particle_dist.n_particles if self._default_n_particles is None
+                           else self._default_n_particles)
+        n_particles = int(n_particles)
+
+        a, h = self._a, self._h
+        if scipy.linalg.norm(cov, 'fro') == 0:
+            warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
+                          "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
+            cov = self._zero_cov_comp * np.eye(cov.shape[0])
+        S, S_err = sqrtm_psd(cov)
+        if not np.isfinite(S_err):
+            raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
+                                 "Check that n_ess is not too small.")
+        S = np.real(h * S)
+
+        d = cloud.d
+        cloud._resample_scratch(n_particles)
+        cloud.cdf(_lib.QB_SCAN_EXACT if self._scan == 'exact' else _lib.QB_SCAN_FAST)
+        cloud.draw(self._uniforms(cloud, n_particles), n_particles)
+
+        n_iters = 0
+        n_invalid = n_particles
+        first = True
+        while n_invalid and n_iters < self._maxiter:
+            n_iters += 1
+            if first:
+                eps = self._normals(cloud, d, n_particles)
+                cloud.lw_move(mean, S, a, eps, n_particles, self._postselect)
+                first = False
+            else:
+                cloud.compact_invalid(n_particles)
+                eps = self._normals(cloud, d, n_invalid)
+                cloud.lw_retry(mean, S, a, eps, n_invalid)
+            n_invalid, overflow = cloud.read_counter()
+            if n_iters == 1:
+                self.last_overflow = overflow
+        if n_invalid:
+            warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                           "iterations.").format(n_invalid, self._maxiter), ResamplerWarning)
+        self.last_n_iters = n_iters
+
+        if on_device:
+            return DeviceParticles(cloud, n_particles)
+        return ParticleDistribution(particle_locations=cloud.x_alt.cpu().numpy(),
+                                    particle_weights=np.ones((n_particles,)) / n_particles)

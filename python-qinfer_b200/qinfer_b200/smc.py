@@ -1,0 +1,323 @@
+"""``SMCUpdater`` — the reference's updater surface (smc.py:97-551) over the B200 engine.
+
+Constructor arguments, methods, properties, warnings and errors follow
+qinfer.smc.SMCUpdater; the particle cloud lives in HBM (``engine.DeviceCloud``)
+and every Bayes update is ONE fused kernel launch (likelihood x weight multiply
+x normalisation sum x n_ess reduction).  ``particle_locations`` /
+``particle_weights`` stay readable and assignable as NumPy arrays (lazy D2H on
+read, H2D on assignment) so heuristics and user pickling keep working.
+
+Deliberate differences from the reference, all on its non-hot paths:
+  * in-place mutation of the arrays returned by ``particle_locations`` /
+    ``particle_weights`` does not reach the device — assign the attribute;
+  * ``track_resampling_divergence`` (an O(N^2) KL estimate) is out of scope;
+  * ``update_timestep`` is elided: none of the built-in models overrides the
+    identity default (abstract_model.py:357-374).
+"""
+import warnings
+
+import numpy as np
+import torch
+
+from ._exceptions import ApproximationWarning, ResamplerWarning
+from ._lib import QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NORM, QB_STAT_SUMSQ
+from .distributions import covariance_from_moments
+from .engine import DeviceCloud
+from .models import describe_model
+from .resamplers import DeviceParticles, LiuWestResampler
+
+_EPS = np.spacing(1)
+
+
+class SMCUpdater(object):
+    def __init__(self, model, n_particles, prior, resample_a=None, resampler=None, resample_thresh=0.5,
+                 debug_resampling=False, track_resampling_divergence=False, zero_weight_policy='error',
+                 zero_weight_thresh=None, canonicalize=True, device=None):
+        if track_resampling_divergence:
+            raise NotImplementedError("track_resampling_divergence is outside the B200 hot path (SURVEY §2 1b)")
+        self._desc = describe_model(model)        # raises UnsupportedModelError: no CPU fallback
+        self._device = device
+        self._cloud = None
+        self._resample_count = 0
+        self._min_n_ess = n_particles
+        self.model = model
+        self.prior = prior
+        self._canonicalize = bool(canonicalize)
+        self._debug_resampling = debug_resampling
+        if resample_a is not None:
+            warnings.warn("The 'resample_a' keyword argument is deprecated; use "
+                          "'resampler=LiuWestResampler(a)' instead.", DeprecationWarning)
+            if resampler is not None:
+                raise ValueError("Both a resample_a and an explicit resampler were provided; please provide only one.")
+            self.resampler = LiuWestResampler(a=resample_a)
+        elif resampler is None:
+            self.resampler = LiuWestResampler(default_n_particles=n_particles)
+        else:
+            self.resampler = resampler
+        self.resample_thresh = resample_thresh
+        self._just_resampled = False
+        self._data_record = []
+        self._normalization_record = []
+        self._resampling_divergences = None
+        self._zero_weight_policy = zero_weight_policy
+        self._zero_weight_thresh = zero_weight_thresh if zero_weight_thresh is not None else 10 * np.spacing(1)
+        self._host_locs = None
+        self._host_weights = None
+        self._n_ess = float(n_particles)
+        self.reset(n_particles)
+
+    # ---- bookkeeping properties (smc.py:182-259) ----------------------------------
+    resample_count = property(lambda self: self._resample_count)
+    just_resampled = property(lambda self: self._just_resampled)
+    normalization_record = property(lambda self: self._normalization_record)
+    min_n_ess = property(lambda self: self._min_n_ess)
+    data_record = property(lambda self: self._data_record[:])
+    resampling_divergences = property(lambda self: self._resampling_divergences)
+
+    @property
+    def log_total_likelihood(self):
+        return np.sum(np.log(self.normalization_record))
+
+    # ---- particle container surface (distributions.py:289-453) ---------------------
+    @property
+    def n_particles(self):
+        return self._cloud.n
+
+    @property
+    def n_rvs(self):
+        return self._cloud.d
+
+    @property
+    def n_ess(self):
+        return self._n_ess
+
+    @property
+    def particle_locations(self):
+        if self._host_locs is None:
+            self._host_locs = self._cloud.download_locations()
+        return self._host_locs
+
+    @particle_locations.setter
+    def particle_locations(self, value):
+        value = np.asarray(value, dtype=np.float64)
+        if value.shape[0] != self._cloud.n:
+            self._rebuild_cloud(value.shape[0])
+        self._cloud.upload_locations(value)
+        self._host_locs = None
+
+    @property
+    def particle_weights(self):
+        if self._host_weights is None:
+            self._host_weights = self._cloud.download_weights()
+        return self._host_weights
+
+    @particle_weights.setter
+    def particle_weights(self, value):
+        value = np.asarray(value, dtype=np.float64)
+        self._cloud.upload_weights(value)
+        st = self._cloud.read_stats()
+        self._n_ess = self._ness_from(st[QB_STAT_NORM], st[QB_STAT_SUMSQ], normalised=True)
+        self._host_weights = None
+
+    def _rebuild_cloud(self, n):
+        launches = self._cloud.launches if self._cloud is not None else 0
+        self._cloud = DeviceCloud(self._desc, n, self._device)
+        self._cloud.launches = launches
+        self._host_locs = self._host_weights = None
+
+    @staticmethod
+    def _ness_from(norm, sumsq, normalised=False):
+        """n_ess = 1 / sum(w_normalised^2) from the unnormalised reductions."""
+        with np.errstate(divide='ignore', invalid='ignore'):
+            if normalised or abs(norm) < _EPS:
+                return float(np.float64(1.0) / np.float64(sumsq))
+            return float((np.float64(norm) * np.float64(norm)) / np.float64(sumsq))
+
+    def sample(self, n=1):
+        """distributions.py:320-333: weighted draw (clamped), host RNG like the reference."""
+        from . import _lib
+        cloud = self._cloud
+        cloud._resample_scratch(cloud.n if cloud._js is None else cloud._js.numel())
+        cloud.cdf(_lib.QB_SCAN_EXACT)
+        u = torch.from_numpy(np.random.random((n,))).to(cloud.device)
+        js = torch.empty((n,), dtype=torch.int64, device=cloud.device)
+        from .engine import _ptr, _stream
+        _lib.check(cloud.lib.qb_draw(_ptr(cloud._cdf), cloud.n, _ptr(u), n, _ptr(js), _ptr(cloud.counter[1:]),
+                                     _stream()))
+        return cloud.x.index_select(0, js).cpu().numpy()
+
+    def est_mean(self):
+        return self._cloud.moments()[1]
+
+    def est_meanfn(self, fn):
+        return np.einsum('i...,i...', self.particle_weights, fn(self.particle_locations))
+
+    def est_covariance_mtx(self, corr=False):
+        _, mean, m2 = self._cloud.moments()
+        cov = covariance_from_moments(mean, m2)
+        if corr:
+            dstd = np.sqrt(np.diag(cov))
+            cov /= np.outer(dstd, dstd)
+        return cov
+
+    # ---- initialisation (smc.py:281-320) ---------------------------------------------
+    def reset(self, n_particles=None, only_params=None, reset_weights=True):
+        if n_particles is not None and only_params is not None:
+            raise ValueError("Cannot set both n_particles and only_params.")
+        if n_particles is None:
+            n_particles = self.n_particles
+        if self._cloud is None or self._cloud.n != n_particles:
+            self._rebuild_cloud(n_particles)
+        cloud = self._cloud
+        if reset_weights:
+            cloud.set_uniform_weights()
+            self._n_ess = float(n_particles)
+            self._host_weights = None
+        sample = np.asarray(self.prior.sample(n=n_particles), dtype=np.float64)
+        if only_params is None:
+            locs = sample
+        else:
+            locs = self.particle_locations.copy()
+            locs[:, only_params] = sample[:, only_params]
+        cloud.upload_locations(locs)
+        self._host_locs = None
+        if self._canonicalize:
+            cloud.canonicalize()
+
+    # ---- updates (smc.py:324-487) --------------------------------------------------------
+    def _count_calls(self, n):
+        m = self.model
+        while m is not None:
+            if hasattr(m, '_call_count'):
+                m._call_count += n
+            m = getattr(m, 'underlying_model', None)
+
+    def hypothetical_update(self, outcomes, expparams, return_likelihood=False, return_normalization=False):
+        """smc.py:324-386 on host arrays; the likelihood tensor comes from the CUDA kernel."""
+        from .engine import device_likelihood
+        if not isinstance(outcomes, np.ndarray):
+            outcomes = np.array([outcomes])
+        weights = self.particle_weights
+        expparams = np.atleast_1d(expparams)
+        self._count_calls(outcomes.shape[0] * self._cloud.n * expparams.shape[0])
+        L = device_likelihood(self._desc, self._cloud.x, outcomes, expparams).transpose([0, 2, 1])
+        hyp_weights = weights * L
+        norm_scale = np.sum(hyp_weights, axis=2)[..., np.newaxis]
+        fixed_norm_scale = norm_scale.copy()
+        fixed_norm_scale[np.abs(norm_scale) < np.spacing(1)] = 1
+        norm_weights = hyp_weights / fixed_norm_scale
+        out = (norm_weights,)
+        if return_likelihood:
+            out += (L,)
+        if return_normalization:
+            out += (norm_scale,)
+        return out[0] if len(out) == 1 else out
+
+    def update(self, outcome, expparams, check_for_resample=True):
+        cloud = self._cloud
+        self._data_record.append(outcome)
+        self._just_resampled = False
+
+        ep = self._desc.expparams_record(expparams, 0)
+        cloud.fused_update(ep, int(outcome))                 # one launch: L, w*L, sum, sum^2, min
+        self._count_calls(cloud.n)
+        st = cloud.read_stats(cloud.stats_alt)               # the only host sync of an update
+        norm, sumsq = float(st[QB_STAT_NORM]), float(st[QB_STAT_SUMSQ])
+        unnormalised = abs(norm) < _EPS                      # smc.py:369-370: then weights stay as w*L
+        total = norm if unnormalised else 1.0                # np.sum of the normalised weights
+
+        if st[QB_STAT_NBAD] > 0:                             # smc.py:416-418
+            smallest = st[QB_STAT_MIN] if unnormalised else st[QB_STAT_MIN] / norm
+            warnings.warn("Negative weights occured in particle approximation. Smallest weight observed == {}. "
+                          "Clipping weights.".format(smallest), ApproximationWarning)
+            cloud.commit_update()
+            cloud.clip_weights()
+            st = cloud.read_stats()
+            cloud.commit_update()                            # back to pending until the policy has spoken
+            total = float(st[QB_STAT_NORM])
+            norm_rec = norm
+            norm, sumsq, unnormalised = total, float(st[QB_STAT_SUMSQ]), True
+        else:
+            norm_rec = norm
+
+        if total <= self._zero_weight_thresh:                # smc.py:423-436 (a NaN total passes, as in the reference)
+            policy = self._zero_weight_policy
+            if policy == 'ignore':
+                pass
+            elif policy == 'skip':
+                return
+            elif policy == 'warn':
+                warnings.warn("All particle weights are zero. This will very likely fail quite badly.",
+                              ApproximationWarning)
+            elif policy == 'error':
+                raise RuntimeError("All particle weights are zero.")
+            elif policy == 'reset':
+                warnings.warn("All particle weights are zero. Resetting from initial prior.", ApproximationWarning)
+                self.reset()
+                cloud = self._cloud
+            else:
+                raise ValueError("Invalid zero-weight policy {} encountered.".format(policy))
+
+        cloud.commit_update()                                # smc.py:441
+        self._host_weights = None
+        self._normalization_record.append(norm_rec)          # smc.py:444
+        self._n_ess = self._ness_from(norm, sumsq, normalised=unnormalised)
+        if self._n_ess <= self._min_n_ess:                   # smc.py:452-453
+            self._min_n_ess = self._n_ess
+        if check_for_resample:
+            self._maybe_resample()
+
+    def batch_update(self, outcomes, expparams, resample_interval=5):
+        n_exps = outcomes.shape[0]
+        if expparams.shape[0] != n_exps:
+            raise ValueError("The number of outcomes and experiments must match.")
+        if len(expparams.shape) == 1:
+            expparams = expparams[:, None]
+        for idx_exp, (outcome, experiment) in enumerate(zip(iter(outcomes), iter(expparams))):
+            self.update(outcome, experiment, check_for_resample=False)
+            if (idx_exp + 1) % resample_interval == 0:
+                self._maybe_resample()
+
+    # ---- resampling (smc.py:263-277, 491-551) --------------------------------------------
+    def _maybe_resample(self):
+        ess = self.n_ess
+        if ess <= 10:
+            warnings.warn("Extremely small n_ess encountered ({}). Resampling is likely to fail. Consider adding "
+                          "particles, or resampling more often.".format(ess), ApproximationWarning)
+        if ess < self.n_particles * self.resample_thresh:
+            self.resample()
+
+    def resample(self):
+        if self.just_resampled:
+            warnings.warn("Resampling without additional data; this may not perform as desired.", ResamplerWarning)
+        self._just_resampled = True
+        self._resample_count += 1
+        if self._debug_resampling:
+            old_mean, old_cov = self.est_mean(), self.est_covariance_mtx()
+
+        new_dist = self.resampler(self.model, self)
+        if isinstance(new_dist, DeviceParticles) and new_dist.cloud is self._cloud:
+            self._cloud.adopt_resampled(new_dist.n_particles)
+        else:                                                # a foreign resampler working on host arrays
+            locs = np.asarray(new_dist.particle_locations, dtype=np.float64)
+            weights = np.asarray(new_dist.particle_weights, dtype=np.float64)
+            if locs.shape[0] != self._cloud.n:
+                self._rebuild_cloud(locs.shape[0])
+            self._cloud.upload_locations(locs)
+            self._cloud.upload_weights(weights)
+        self._host_locs = self._host_weights = None
+        st = self._cloud.read_stats()
+        self._n_ess = self._ness_from(st[QB_STAT_NORM], st[QB_STAT_SUMSQ], normalised=True)
+
+        if self._canonicalize:
+            self._cloud.canonicalize()
+        try:
+            self.model.clear_cache()
+        except Exception as e:  # pragma: no cover
+            warnings.warn("Exception raised when clearing model cache: {}. Ignoring.".format(e))
+
+        if self._debug_resampling:
+            import logging
+            new_mean, new_cov = self.est_mean(), self.est_covariance_mtx()
+            logging.getLogger(__name__).debug("Resampling changed mean by {}. Norm change in cov: {}.".format(
+                old_mean - new_mean, np.linalg.norm(new_cov - old_cov)))

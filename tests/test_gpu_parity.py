@@ -1,0 +1,487 @@
+"""GPU parity tests: every CUDA kernel of the hot path, called through the C ABI /
+plugin surface, against (a) the golden vectors produced by the unmodified
+reference and (b) the NumPy oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): resample indices bit-exact; posterior
+mean/covariance within 1e-6 relative; the per-kernel tolerances below are much
+tighter and are written next to each assertion.  Measured maxima are appended to
+gpurun_out/parity_report.txt so they can be quoted.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def report(name, value):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.txt"), "a") as f:
+        f.write("%s %r\n" % (name, value))
+
+
+def relerr(a, b, floor=0.0):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def qb():
+    import qinfer_b200
+    return qinfer_b200
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import smc_oracle
+    return smc_oracle
+
+
+def gpu_namespace(qb, **lw_kwargs):
+    return cases.Namespace(
+        name="b200", SMCUpdater=qb.SMCUpdater, LiuWestResampler=qb.LiuWestResampler,
+        ParticleDistribution=qb.ParticleDistribution, SimplePrecessionModel=qb.SimplePrecessionModel,
+        SimpleInversionModel=qb.SimpleInversionModel, RandomizedBenchmarkingModel=qb.RandomizedBenchmarkingModel,
+        BinomialModel=qb.BinomialModel, TomographyModel=qb.TomographyModel, pauli_basis=qb.pauli_basis,
+        gell_mann_basis=qb.gell_mann_basis, UniformDistribution=qb.UniformDistribution,
+        PostselectedDistribution=qb.PostselectedDistribution, sqrtm_psd=qb.sqrtm_psd)
+
+
+# ---------------------------------------------------------------------------
+# T1 — likelihood kernels vs the reference's Model.likelihood (golden vectors)
+# ---------------------------------------------------------------------------
+def test_t1_likelihood_vectors(qb, golden):
+    g = golden("likelihood_vectors")
+    got = cases.likelihood_vectors(gpu_namespace(qb))
+    # cos/pow/log/exp differ from glibc in the last ulp or two; 1 - pr0 near pr0 ~ 1 turns that into
+    # an absolute error of a few 1e-16, hence the absolute floor.
+    for key, rtol, atol in [("prec_L", 1e-12, 2e-15), ("rb_L", 1e-12, 2e-15), ("binrb_L", 2e-12, 1e-300),
+                            ("binprec_L", 2e-12, 1e-300), ("tomo1_L", 1e-13, 1e-15), ("tomo2_L", 1e-13, 1e-15)]:
+        assert got[key].shape == g[key].shape
+        np.testing.assert_allclose(got[key], g[key], rtol=rtol, atol=atol, err_msg=key)
+        report("t1_" + key + "_max_abs", float(np.max(np.abs(got[key] - g[key]))))
+    assert np.array_equal(got["rb_valid"], g["rb_valid"])          # validity masks are exact
+
+
+def test_t1_binomial_extremes(qb, oracle):
+    """k in {0, n}, pr1 exactly 0 and exactly 1 (A=B=0; A=1,B=0,p=1), large n_meas."""
+    x = np.array([[1.0, 0.0, 0.0], [1.0, 1.0, 0.0], [0.9, 0.5, 0.25], [0.99, 0.3, 0.6]])
+    m_b, m_o = qb.BinomialModel(qb.RandomizedBenchmarkingModel()), oracle.BinomialModel(
+        oracle.RandomizedBenchmarkingModel())
+    ep = np.empty((2,), dtype=m_b.expparams_dtype)
+    ep['m'] = [1, 10]
+    ep['n_meas'] = [30, 2000]
+    ks = np.array([0, 1, 30])
+    got = m_b.likelihood(ks, x, ep)
+    want = m_o.likelihood(ks, x, ep)
+    np.testing.assert_allclose(got, want, rtol=5e-11, atol=1e-300)
+    assert m_b.call_count == ks.size * x.shape[0] * ep.size        # abstract_model.py:466-468
+
+
+# ---------------------------------------------------------------------------
+# T2 — fused update vs SMCUpdater.hypothetical_update / update
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 1000, 1024, 100003, 3 * 10 ** 6 + 5])
+def test_t2_fused_update_precession(qb, oracle, n):
+    rs = np.random.RandomState(n % 1000)
+    x = rs.random_sample((n, 1))
+    w = rs.random_sample(n) ** 2
+    w /= w.sum()
+    t = np.array([17.3])
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), zero_weight_policy='ignore')
+    up.particle_weights = w
+    for outcome in (0, 1):
+        L = oracle.SimplePrecessionModel().likelihood(np.array([outcome]), x, t)[0, :, 0]
+        hyp = w * L
+        want_norm = np.sum(hyp)
+        want_w = hyp / want_norm
+        up.update(outcome, t, check_for_resample=False)
+        got_w = up.particle_weights
+        np.testing.assert_allclose(got_w, want_w, rtol=1e-12, atol=1e-300)
+        assert abs(up.normalization_record[-1] - want_norm) <= 1e-12 * want_norm
+        assert abs(up.n_ess - 1 / np.sum(want_w ** 2)) <= 1e-10 * up.n_ess
+        report("t2_prec_n%d_o%d_w_rel" % (n, outcome), relerr(got_w, want_w, 1e-300))
+        w = want_w
+        up.particle_weights = w
+
+
+def test_t2_fused_update_all_models_trajectory(qb, oracle, golden):
+    """Several consecutive lazy-normalised updates (no resampling) for each model family."""
+    rs = np.random.RandomState(5)
+    runs = []
+    # RB o Binomial (d = 3)
+    g = golden("rb_binomial_c3")
+    mb, mo = qb.BinomialModel(qb.RandomizedBenchmarkingModel()), oracle.BinomialModel(
+        oracle.RandomizedBenchmarkingModel())
+    eps = np.empty((6,), dtype=mb.expparams_dtype)
+    eps['m'] = g["ms"][:6]
+    eps['n_meas'] = int(g["n_meas"])
+    runs.append((mb, mo, g["prior"], [(int(g["counts"][k]), eps[k:k + 1]) for k in range(6)]))
+    # tomography 2 qubits (d = 16)
+    g = golden("tomography_c4")
+    tb, to = qb.TomographyModel(qb.pauli_basis(2)), oracle.TomographyModel(oracle.pauli_basis(2))
+    steps = []
+    for k in range(8):
+        ep = np.empty((1,), dtype=tb.expparams_dtype)
+        ep['meas'][0] = g["meas"][k]
+        steps.append((int(g["outcomes"][k]), ep))
+    runs.append((tb, to, g["prior"], steps))
+    # interleaved RB (d = 4)
+    xi = np.column_stack([0.9 + 0.1 * rs.random_sample(500), 0.9 + 0.1 * rs.random_sample(500),
+                          0.5 * rs.random_sample(500), 0.5 * rs.random_sample(500)])
+    ib, io = qb.RandomizedBenchmarkingModel(interleaved=True), oracle.RandomizedBenchmarkingModel(interleaved=True)
+    steps = []
+    for k in range(6):
+        ep = np.empty((1,), dtype=ib.expparams_dtype)
+        ep['m'] = 5 + 20 * k
+        ep['reference'] = bool(k % 2)
+        steps.append((k % 2, ep))
+    runs.append((ib, io, xi, steps))
+    # Binomial(precession): scalar expparam renamed 'x'
+    pb, po = qb.BinomialModel(qb.SimplePrecessionModel()), oracle.BinomialModel(oracle.SimplePrecessionModel())
+    steps = []
+    for k in range(6):
+        ep = np.empty((1,), dtype=pb.expparams_dtype)
+        ep['x'] = 1.5 ** k
+        ep['n_meas'] = 20
+        steps.append((3 + 2 * k, ep))
+    runs.append((pb, po, rs.random_sample((777, 1)), steps))
+
+    for mb, mo, prior, steps in runs:
+        n = prior.shape[0]
+        gb = qb.SMCUpdater(mb, n, cases.FixedPrior(prior), canonicalize=False)
+        ob = oracle.SMCUpdater(mo, n, cases.FixedPrior(prior), canonicalize=False)
+        for outcome, ep in steps:
+            gb.update(outcome, ep, check_for_resample=False)
+            ob.update(outcome, ep, check_for_resample=False)
+            np.testing.assert_allclose(gb.particle_weights, ob.particle_weights, rtol=2e-11, atol=1e-300)
+            np.testing.assert_allclose(gb.normalization_record[-1], np.ravel(ob.normalization_record[-1])[0],
+                                       rtol=1e-11)
+            np.testing.assert_allclose(gb.n_ess, ob.n_ess, rtol=1e-10)
+        report("t2_traj_%s_w_rel" % type(mb).__name__, relerr(gb.particle_weights, ob.particle_weights, 1e-300))
+        assert gb.min_n_ess == pytest.approx(ob.min_n_ess, rel=1e-10)
+        assert mb.call_count == len(steps) * n
+
+
+# ---------------------------------------------------------------------------
+# T3 — moments vs ParticleDistribution.est_mean / est_covariance_mtx (golden)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [1, 3, 16])
+def test_t3_moments_golden(qb, golden, d):
+    g = golden("moment_vectors")
+    pd = qb.ParticleDistribution(particle_locations=g["mom%d_x" % d], particle_weights=g["mom%d_w" % d])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean, cov = pd.est_mean(), pd.est_covariance_mtx()
+    np.testing.assert_allclose(mean, g["mom%d_mean" % d], rtol=1e-12, atol=1e-14)
+    scale = np.max(np.abs(g["mom%d_cov" % d]))
+    np.testing.assert_allclose(cov, g["mom%d_cov" % d], rtol=0, atol=1e-12 * max(scale, 1.0))   # north_star: 1e-6
+    assert pd.n_ess == pytest.approx(float(g["mom%d_ness" % d]), rel=1e-12)
+    report("t3_d%d_cov_abs" % d, float(np.max(np.abs(cov - g["mom%d_cov" % d]))))
+
+
+@pytest.mark.parametrize("d,n", [(1, 10 ** 6 + 3), (2, 33), (3, 400001), (4, 1000), (5, 7777), (9, 5000),
+                                 (16, 250007), (16, 3), (64, 2000)])
+def test_t3_moments_oracle_sizes(qb, oracle, d, n):
+    """Every moments kernel (register, DMMA d=16, generic) incl. ragged tails, vs np.dot / einsum."""
+    from qinfer_b200.engine import host_moments
+    rs = np.random.RandomState(d * 7 + 1)
+    x = rs.randn(n, d) * 0.3 + np.arange(d) * 0.1
+    w = rs.random_sample(n)
+    w /= w.sum()
+    sw, mean, m2 = host_moments(w, x)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want_mean, want_cov = oracle.particle_mean(w, x), oracle.particle_covariance_mtx(w, x)
+    cov = m2 - np.outer(mean, mean)
+    assert sw == pytest.approx(1.0, abs=1e-12)
+    np.testing.assert_allclose(mean, want_mean, rtol=1e-11, atol=1e-13)
+    # uncentred formula: error ~ eps * |mu|^2, far inside the 1e-6 bar here
+    np.testing.assert_allclose(cov, want_cov, rtol=0, atol=1e-11 * (1 + np.max(np.abs(want_mean)) ** 2))
+    assert np.array_equal(m2, m2.T)
+
+
+# ---------------------------------------------------------------------------
+# T4 — CDF + draw: bit-identical to np.cumsum(w).searchsorted(u, 'right') (clamped)
+# ---------------------------------------------------------------------------
+def _draw_on_gpu(qb, w, u, scan):
+    from qinfer_b200 import _lib
+    from qinfer_b200.engine import DeviceCloud
+    import torch
+    n = w.shape[0]
+    cloud = DeviceCloud(qb.describe_model(qb.SimplePrecessionModel()), n)
+    cloud.upload_locations(np.zeros((n, 1)))
+    cloud.upload_weights(w)
+    cloud._resample_scratch(u.shape[0])
+    cdf = cloud.cdf(_lib.QB_SCAN_EXACT if scan == 'exact' else _lib.QB_SCAN_FAST)
+    cloud._u.copy_(torch.from_numpy(u))
+    js = cloud.draw(cloud._u, u.shape[0])
+    n_bad, overflow = cloud.read_counter()
+    return cdf.cpu().numpy(), js.cpu().numpy(), overflow
+
+
+def _weight_cases():
+    rs = np.random.RandomState(42)
+    out = {}
+    w = rs.random_sample(5000); out["random"] = w / w.sum()
+    w = rs.random_sample(5000); w[rs.random_sample(5000) < 0.6] = 0.0; out["zeros"] = w / w.sum()
+    out["ties"] = np.full(4096, 1.0 / 4096)                       # exact ties / exactly representable steps
+    w = np.full(3000, 1e-310); w[1234] = 1.0; out["denormal_plus_onehot"] = w
+    w = np.zeros(777); w[5] = 1.0; out["onehot"] = w
+    w = rs.random_sample(100003) ** 8; out["skewed_100k"] = w / w.sum()
+    w = np.exp(-0.5 * ((np.arange(10 ** 6) - 3e5) / 2e4) ** 2) + 1e-30; out["gaussian_1m"] = w / w.sum()
+    w = rs.random_sample(1); out["single"] = w / w.sum()
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_weight_cases().keys()))
+def test_t4_exact_scan_and_draw_bit_identical(qb, name):
+    w = _weight_cases()[name]
+    rs = np.random.RandomState(len(name))
+    u = rs.random_sample(max(w.shape[0], 2000))
+    cdf, js, overflow = _draw_on_gpu(qb, w, u, 'exact')
+    want_cdf = np.cumsum(w)
+    assert np.array_equal(cdf, want_cdf), "sequential-order scan differs from np.cumsum"
+    want = want_cdf.searchsorted(u, side='right')
+    assert overflow == int(np.sum(want >= w.shape[0]))
+    assert np.array_equal(js, np.minimum(want, w.shape[0] - 1))
+
+
+def test_t4_draw_edges(qb):
+    """u exactly on a CDF step goes right (side='right'); u above cdf[-1] is clamped and counted."""
+    w = np.array([0.25, 0.25, 0.0, 0.25, 0.125])                  # cdf[-1] = 0.875 < 1
+    u = np.array([0.0, 0.25, 0.5, 0.4999999999999999, 0.75, 0.874, 0.875, 0.99])
+    cdf, js, overflow = _draw_on_gpu(qb, w, u, 'exact')
+    want = np.cumsum(w).searchsorted(u, side='right')
+    assert list(want) == [0, 1, 3, 1, 4, 4, 5, 5]
+    assert overflow == 2
+    assert np.array_equal(js, np.minimum(want, 4))
+
+
+def test_t4_fast_scan_is_close_and_indices_rarely_differ(qb):
+    rs = np.random.RandomState(9)
+    w = rs.random_sample(10 ** 6)
+    w /= w.sum()
+    u = rs.random_sample(10 ** 6)
+    cdf, js, _ = _draw_on_gpu(qb, w, u, 'fast')
+    want_cdf = np.cumsum(w)
+    assert np.max(np.abs(cdf - want_cdf)) < 1e-12
+    want = np.minimum(want_cdf.searchsorted(u, side='right'), w.shape[0] - 1)
+    mism = int(np.sum(js != want))
+    report("t4_fast_scan_index_mismatches_of_1e6", mism)
+    assert mism <= 5 and np.all(np.abs(js - want) <= 1)
+
+
+# ---------------------------------------------------------------------------
+# T5 — Liu-West: teacher-forced replay of the reference's recorded resample events
+# ---------------------------------------------------------------------------
+def _replay_events(qb, g, model, a):
+    """Teacher-forced: same weights, locations, legacy-RNG state and (mean, cov) as the reference saw."""
+    import smc_oracle as o
+    worst = 0.0
+    for i in range(int(g["n_events"])):
+        w, x, new_x = g["ev%d_w" % i], g["ev%d_x" % i], g["ev%d_new_x" % i]
+        pd = qb.ParticleDistribution(particle_locations=x, particle_weights=w)
+        pd.particle_weights = w                    # exactly the weights the reference's updater held
+        res = qb.LiuWestResampler(a=a)
+        np.random.set_state(cases.unpack_rng_state(g, "ev%d_rng_" % i))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            # moments as NumPy computes them (the device moments are checked in T3); sqrtm_psd of a
+            # rank-deficient covariance turns 1e-17 noise into 1e-9, so the move is compared on equal inputs
+            mean, cov = o.particle_mean(w, x), o.particle_covariance_mtx(w, x)
+            out = res(model, pd, precomputed_mean=mean, precomputed_cov=cov)
+        assert res.last_overflow == 0
+        got = out.particle_locations
+        assert got.shape == new_x.shape
+        worst = max(worst, relerr(got, new_x, 1e-12))
+        # d = 1 is bit-exact by construction; d > 1 differs only by BLAS's summation order in S @ eps
+        np.testing.assert_allclose(got, new_x, rtol=1e-12, atol=1e-14, err_msg="event %d" % i)
+    return worst
+
+
+def test_t5_resample_indices_bit_exact_all_cases(qb, golden):
+    """Same weights + same legacy-RNG state => the device draw returns the reference's indices bit for bit."""
+    for case in ("precession_c1", "precession_minfreq", "rb_binomial_c3", "tomography_c4"):
+        g = golden(case)
+        for i in range(int(g["n_events"])):
+            w, u = g["ev%d_w" % i], g["ev%d_u" % i]
+            cdf, js, overflow = _draw_on_gpu(qb, w, u, 'exact')
+            assert overflow == 0
+            assert np.array_equal(js, g["ev%d_js" % i]), "%s event %d" % (case, i)
+
+
+def test_t5_liu_west_events_precession(qb, golden):
+    report("t5_prec_locs_rel", _replay_events(qb, golden("precession_c1"), qb.SimplePrecessionModel(), 0.98))
+
+
+def test_t5_liu_west_retry_quirk(qb, golden):
+    """min_freq > 0 forces the postselection retry loop; parity needs the prefix-`mus` quirk (resamplers.py:372)."""
+    g = golden("precession_minfreq")
+    report("t5_minfreq_locs_rel", _replay_events(qb, g, qb.SimplePrecessionModel(min_freq=0.3), 0.9))
+
+
+def test_t5_liu_west_events_rb(qb, golden):
+    report("t5_rb_locs_rel", _replay_events(qb, golden("rb_binomial_c3"),
+                                            qb.BinomialModel(qb.RandomizedBenchmarkingModel()), 0.98))
+
+
+def test_t5_liu_west_events_tomography(qb, golden):
+    # the recorded new_x are pre-canonicalize (the resampler's own output)
+    report("t5_tomo_locs_rel", _replay_events(qb, golden("tomography_c4"), qb.TomographyModel(qb.pauli_basis(2)),
+                                              0.98))
+
+
+# ---------------------------------------------------------------------------
+# T6 — tomography canonicalize vs TomographyModel.canonicalize (golden)
+# ---------------------------------------------------------------------------
+def test_t6_canonicalize_golden(qb, golden):
+    g = golden("canonicalize_vectors")
+    for nq in (1, 2):
+        x = g["canon%d_x" % nq]
+        got = qb.TomographyModel(qb.pauli_basis(nq)).canonicalize(x.copy())
+        np.testing.assert_allclose(got, g["canon%d_y" % nq], rtol=0, atol=1e-10)
+        report("t6_pauli%d_abs" % nq, float(np.max(np.abs(got - g["canon%d_y" % nq]))))
+        got = qb.TomographyModel(qb.pauli_basis(nq), allow_subnormalized=True).canonicalize(x.copy())
+        np.testing.assert_allclose(got, g["canon%d_y_subnorm" % nq], rtol=0, atol=1e-10)
+        # physical (already PSD) inputs are passed through untouched when subnormalised states are allowed
+        assert np.array_equal(got[:64], x[:64])
+    got = qb.TomographyModel(qb.gell_mann_basis(3)).canonicalize(g["canon_gm3_x"].copy())
+    np.testing.assert_allclose(got, g["canon_gm3_y"], rtol=0, atol=1e-10)
+
+
+def test_t6_canonicalize_output_is_physical(qb):
+    """tests/base_test.py:413-420 (test_canonicalize): canonical states are valid density operators."""
+    rs = np.random.RandomState(2)
+    basis = qb.pauli_basis(2)
+    x = cases.ginibre_coords(rs, 5000, basis.data) + 0.2 * rs.randn(5000, 16)
+    x[:, 0] = 0.5
+    y = qb.TomographyModel(basis).canonicalize(x)
+    rho = np.einsum('na,aij->nij', y, basis.data)
+    ev = np.linalg.eigvalsh(rho)
+    assert ev.min() > -1e-12
+    np.testing.assert_allclose(np.trace(rho, axis1=1, axis2=2).real, 1.0, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------
+# T8 — free-running trajectories vs the reference (golden), legacy RNG seed 0
+# ---------------------------------------------------------------------------
+def _check_trajectory(name, out, g, mean_rtol=1e-6):
+    assert int(out["resample_count"]) == int(g["resample_count"])
+    np.testing.assert_allclose(out["normalization_record"], g["normalization_record"], rtol=1e-7)
+    np.testing.assert_allclose(out["est_mean"], g["est_mean"], rtol=mean_rtol)          # north_star: 1e-6
+    np.testing.assert_allclose(out["est_cov"], g["est_cov"], rtol=1e-6, atol=1e-6 * np.max(np.abs(g["est_cov"])))
+    np.testing.assert_allclose(out["min_n_ess"], g["min_n_ess"], rtol=1e-7)
+    report("t8_%s_mean_rel" % name, relerr(out["est_mean"], g["est_mean"], 1e-300))
+    report("t8_%s_locs_rel" % name, relerr(out["locations"], g["locations"], 1e-12))
+
+
+def test_t8_precession_c1_free_running(qb, golden):
+    g = golden("precession_c1")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cases.run_precession(gpu_namespace(qb), {k: g[k] for k in ("prior", "ts", "outcomes")})
+    _check_trajectory("prec_c1", out, g)
+    # the recorded resample events saw the same indices as the reference did
+    for i in range(int(g["n_events"])):
+        np.testing.assert_allclose(out["ev%d_new_x" % i], g["ev%d_new_x" % i], rtol=1e-6, atol=1e-9)
+
+
+def test_t8_precession_minfreq_free_running(qb, golden):
+    g = golden("precession_minfreq")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cases.run_precession(gpu_namespace(qb), {k: g[k] for k in ("prior", "ts", "outcomes")},
+                                   min_freq=0.3, a=0.9)
+    _check_trajectory("prec_minfreq", out, g)
+
+
+def test_t8_rb_binomial_c3_free_running(qb, golden):
+    g = golden("rb_binomial_c3")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cases.run_rb(gpu_namespace(qb), {k: g[k] for k in ("prior", "ms", "counts", "n_meas")})
+    _check_trajectory("rb_c3", out, g)
+
+
+def test_t8_tomography_c4_free_running(qb, golden):
+    g = golden("tomography_c4")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cases.run_tomography(gpu_namespace(qb), {k: g[k] for k in ("prior", "meas", "outcomes", "true")})
+    _check_trajectory("tomo_c4", out, g)
+
+
+# ---------------------------------------------------------------------------
+# Device RNG (throughput mode): known-answer for Philox4x32-10 + moments of the output
+# ---------------------------------------------------------------------------
+def test_philox_uniform_matches_numpy_philox(qb):
+    """Cross-check against NumPy's independent Philox4x64? No: 4x32 is not in NumPy — use the Random123
+    known-answer vector for Philox4x32-10 (counter 0, key 0) and a host restatement for a stream."""
+    import torch
+    from qinfer_b200.engine import DeviceCloud
+    cloud = DeviceCloud(qb.describe_model(qb.SimplePrecessionModel()), 16)
+    out = torch.empty((8,), dtype=torch.float64, device=cloud.device)
+    cloud.rng_uniform(out, 8, 0, 0)
+    got = out.cpu().numpy()
+    want = _philox_uniform_host(8, 0, 0)
+    assert np.array_equal(got, want)
+    # Random123 KAT: philox4x32_10(ctr=0, key=0) = 6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    r = _philox4x32_10(np.zeros(4, dtype=np.uint64), np.zeros(2, dtype=np.uint64))
+    assert [int(v) for v in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    big = torch.empty((10 ** 6,), dtype=torch.float64, device=cloud.device)
+    cloud.rng_uniform(big, 10 ** 6, 1234, 77)
+    b = big.cpu().numpy()
+    assert 0.0 <= b.min() and b.max() < 1.0 and abs(b.mean() - 0.5) < 2e-3 and abs(b.var() - 1 / 12) < 1e-3
+    cloud.rng_normal(big, 10 ** 6, 1234, 77)
+    z = big.cpu().numpy()
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1) < 5e-3 and abs((z ** 4).mean() - 3) < 5e-2
+
+
+def _philox4x32_10(ctr, key):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [int(v) for v in ctr]
+    k = [int(v) for v in key]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF,
+             ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def _philox_uniform_host(n, seed, offset):
+    out = np.empty(n)
+    for p in range((n + 1) // 2):
+        ctr = offset + p
+        r = _philox4x32_10([ctr & 0xFFFFFFFF, ctr >> 32, 0, 0], [seed & 0xFFFFFFFF, seed >> 32])
+        vals = [((r[0] >> 5) * 67108864.0 + (r[1] >> 6)) / 9007199254740992.0,
+                ((r[2] >> 5) * 67108864.0 + (r[3] >> 6)) / 9007199254740992.0]
+        out[2 * p] = vals[0]
+        if 2 * p + 1 < n:
+            out[2 * p + 1] = vals[1]
+    return out
+
+
+def test_philox_mode_resampling_preserves_moments(qb):
+    """Throughput mode (device RNG + fast scan): Liu-West preserves mean and covariance in expectation."""
+    n = 400000
+    rs = np.random.RandomState(1)
+    x = rs.random_sample((n, 1))
+    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=7, scan='fast')
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), resampler=res)
+    for k in range(12):
+        up.update(k % 2, np.array([1.3 ** k]), check_for_resample=False)
+    m0, c0 = up.est_mean(), up.est_covariance_mtx()
+    up.resample()
+    m1, c1 = up.est_mean(), up.est_covariance_mtx()
+    assert up.n_ess == pytest.approx(n)
+    sigma = np.sqrt(c0[0, 0])
+    assert abs(m1[0] - m0[0]) < 6 * sigma / np.sqrt(up.min_n_ess)
+    assert abs(c1[0, 0] / c0[0, 0] - 1) < 0.05

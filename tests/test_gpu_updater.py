@@ -1,0 +1,238 @@
+"""The reference's own behavioural tests for the hot path, restated against the B200 updater
+(SURVEY §4 / T7): tests/test_smc.py:84-137, tests/test_precession_model.py:58-111,
+tests/test_distributions.py:615-706, plus the zero-weight policies of smc.py:423-436."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qb():
+    import qinfer_b200
+    return qinfer_b200
+
+
+def _decimation_setup(qb, n, fraction_zero):
+    """The reference drives ESS with a DecimationModel (tests/test_smc.py:55-80) that zeroes the likelihood
+    of a chosen fraction of particles.  The same effect with a built-in model: 1-qubit tomography whose
+    measurement reads x_1 directly; particles with x_1 = 0 have likelihood exactly 0 for outcome 1."""
+    model = qb.TomographyModel(qb.pauli_basis(1))
+    x = np.zeros((n, 4))
+    x[:, 0] = 1 / np.sqrt(2)
+    x[:, 1] = 1.0
+    ep = np.empty((1,), dtype=model.expparams_dtype)
+    ep['meas'][0] = [0.0, 1.0, 0.0, 0.0]
+    return model, x, ep
+
+
+def test_min_n_ess_is_exactly_4_to_the_k(qb):
+    """tests/test_smc.py:122-137: after decimating to 1/4 of the survivors each time, min_n_ess == 4**k."""
+    n = 4 ** 6
+    model, x, ep = _decimation_setup(qb, n, 0.75)
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resample_thresh=0.0, canonicalize=False)
+    alive = n
+    for k in reversed(range(1, 6)):
+        locs = up.particle_locations.copy()
+        live = np.nonzero(locs[:, 1] == 1.0)[0]
+        locs[live[live.size // 4:], 1] = 0.0          # keep a quarter of the live particles
+        up.particle_locations = locs
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            up.update(1, ep)
+        alive //= 4
+        assert up.n_ess == 4 ** k == alive
+        assert up.min_n_ess == 4 ** k
+
+
+def test_resample_count_and_low_ess_warning(qb):
+    """tests/test_smc.py:98-120: ESS below threshold => exactly one resample per update; ESS <= 10 warns."""
+    n = 1000
+    rs = np.random.RandomState(0)
+    x = rs.random_sample((n, 1))
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), resample_thresh=1.1)
+    np.random.seed(0)
+    for k in range(5):
+        assert up.resample_count == k
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            up.update(k % 2, np.array([0.7 + k]))
+        assert up.just_resampled
+    assert up.resample_count == 5
+    # low ESS: all the weight on 5 particles
+    w = np.zeros(n)
+    w[:5] = 0.2
+    up.particle_weights = w
+    assert up.n_ess == pytest.approx(5.0)
+    with pytest.warns(qb.ApproximationWarning, match="Extremely small n_ess"):
+        up._maybe_resample()
+    with pytest.warns(qb.ResamplerWarning, match="without additional data"):
+        up.resample()
+
+
+def test_precession_estimate_quality(qb):
+    """tests/test_precession_model.py:86-110: N=1e4, 100 experiments t in linspace(1,10,100), prior U[0,2],
+    true omega = 1: mean to 2 decimals, covariance < 0.01, through batch_update."""
+    np.random.seed(0)
+    n, true = 10000, 1.0
+    model = qb.SimplePrecessionModel()
+    prior = qb.UniformDistribution([0, 2])
+    up = qb.SMCUpdater(model, n, prior, resampler=qb.LiuWestResampler(), zero_weight_policy='ignore')
+    ts = np.linspace(1, 10, 100)
+    rs = np.random.RandomState(1)
+    outcomes = (rs.random_sample(100) >= np.cos(ts * true / 2) ** 2).astype(int)
+    up.batch_update(outcomes, ts, 5)
+    assert abs(up.est_mean()[0] - true) < 0.05
+    assert up.est_covariance_mtx()[0, 0] < 0.01
+    assert len(up.data_record) == 100 and len(up.normalization_record) == 100
+    assert np.isfinite(up.log_total_likelihood)
+    assert model.call_count == 100 * n
+
+
+def test_particle_distribution_basics(qb):
+    """tests/test_distributions.py:622-706: weights rectified + normalised; n_ess N / 1; moments of an MVN cloud."""
+    rs = np.random.RandomState(3)
+    n = 100000
+    mu = np.array([0.3, -1.0, 2.0])
+    A = rs.randn(3, 3)
+    cov = A @ A.T / 3
+    x = rs.multivariate_normal(mu, cov, size=n)
+    pd = qb.ParticleDistribution(particle_locations=x, particle_weights=-np.ones(n) * 3)
+    assert np.all(pd.particle_weights > 0) and abs(pd.particle_weights.sum() - 1) < 1e-12
+    assert pd.n_ess == pytest.approx(n)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.testing.assert_allclose(pd.est_mean(), mu, atol=0.02)
+        assert np.linalg.norm(pd.est_covariance_mtx() - cov) < 0.05
+        corr = pd.est_covariance_mtx(corr=True)
+    np.testing.assert_allclose(np.diag(corr), 1.0, atol=1e-12)
+    w = np.zeros(n)
+    w[17] = 1.0
+    pd = qb.ParticleDistribution(particle_locations=x, particle_weights=w)
+    assert pd.n_ess == pytest.approx(1.0)
+    assert pd.sample(5).shape == (5, 3) and np.all(pd.sample(5) == x[17])
+
+
+@pytest.mark.parametrize("policy", ["ignore", "skip", "warn", "error", "reset", "bogus"])
+def test_zero_weight_policies(qb, policy):
+    """smc.py:423-436 with an impossible datum (every particle has likelihood exactly 0)."""
+    n = 256
+    model, x, ep = _decimation_setup(qb, n, 1.0)
+    x[:, 1] = 0.0                                       # pr1 = 0 everywhere: outcome 1 is impossible
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), zero_weight_policy=policy, canonicalize=False)
+    before = up.particle_weights.copy()
+    if policy == "error":
+        with pytest.raises(RuntimeError, match="All particle weights are zero."):
+            up.update(1, ep)
+        assert np.array_equal(up.particle_weights, before)       # state untouched, as in the reference
+        assert up.normalization_record == []
+    elif policy == "bogus":
+        with pytest.raises(ValueError, match="Invalid zero-weight policy"):
+            up.update(1, ep)
+    elif policy == "skip":
+        up.update(1, ep)
+        assert np.array_equal(up.particle_weights, before) and up.normalization_record == []
+        assert up.data_record == [1]
+    elif policy == "warn":
+        with pytest.warns(qb.ApproximationWarning, match="All particle weights are zero"):
+            up.update(1, ep, check_for_resample=False)
+        assert np.all(up.particle_weights == 0) and up.normalization_record == [0.0]
+    elif policy == "reset":
+        with pytest.warns(qb.ApproximationWarning, match="Resetting from initial prior"):
+            up.update(1, ep, check_for_resample=False)
+        assert np.all(up.particle_weights == 0)          # the reference overwrites the reset weights (smc.py:441)
+    else:
+        up.update(1, ep, check_for_resample=False)
+        assert np.all(up.particle_weights == 0)
+
+
+def test_negative_weights_are_clipped_with_warning(qb):
+    """smc.py:416-418.  A tomography 'measurement' with pr1 > 1 is clipped by the model itself, so negative
+    weights are injected through the weights attribute instead."""
+    n = 128
+    model, x, ep = _decimation_setup(qb, n, 0.0)
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), canonicalize=False)
+    w = np.full(n, 1.0 / (n - 2))
+    w[3] = -1.0 / (n - 2)
+    up.particle_weights = w
+    with pytest.warns(qb.ApproximationWarning, match="Negative weights"):
+        up.update(1, ep, check_for_resample=False)
+    got = up.particle_weights
+    assert got[3] == 0.0 and np.all(got >= 0) and got.max() <= 1.0
+
+
+def test_liu_west_zero_covariance_and_standalone_use(qb):
+    """resamplers.py:283-294: identical particles => zero-norm covariance => warning + zero_cov_comp."""
+    n = 512                                             # powers of two: every partial sum is exact,
+    x = np.full((n, 1), 0.375)                          # so E[x^2] - mu^2 is exactly zero
+    pd = qb.ParticleDistribution(particle_locations=x, particle_weights=np.ones(n))
+    np.random.seed(1)
+    with pytest.warns(qb.ResamplerWarning, match="zero norm"):
+        out = qb.LiuWestResampler(a=0.9, zero_cov_comp=1e-4)(qb.SimplePrecessionModel(), pd)
+    assert isinstance(out, qb.ParticleDistribution) and out.n_particles == n
+    spread = out.particle_locations.std()
+    assert 0.2 * np.sqrt(1e-4 * (1 - 0.81)) < spread < 5 * np.sqrt(1e-4 * (1 - 0.81))
+    # n_particles override
+    np.random.seed(1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = qb.LiuWestResampler(a=0.9)(qb.SimplePrecessionModel(), pd, n_particles=123)
+    assert out.particle_locations.shape == (123, 1)
+
+
+def test_liu_west_maxiter_warning_and_no_postselect(qb):
+    """resamplers.py:374-381: particles that stay invalid after maxiter iterations produce a warning."""
+    n = 400
+    rs = np.random.RandomState(0)
+    x = 0.1 * rs.random_sample((n, 1))                  # everything below min_freq = 0.5
+    pd = qb.ParticleDistribution(particle_locations=x, particle_weights=np.ones(n))
+    np.random.seed(2)
+    with pytest.warns(qb.ResamplerWarning, match="failed to find valid models"):
+        qb.LiuWestResampler(maxiter=3)(qb.SimplePrecessionModel(min_freq=0.5), pd)
+    np.random.seed(2)
+    r = qb.LiuWestResampler(postselect=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", qb.ResamplerWarning)
+        r(qb.SimplePrecessionModel(min_freq=0.5), pd)
+    assert r.last_n_iters == 1
+
+
+def test_hypothetical_update_shapes_and_values(qb):
+    """smc.py:324-386: (n_outcomes, n_expparams, n_particles) weights, normalisations, likelihoods."""
+    import smc_oracle as o
+    n = 300
+    rs = np.random.RandomState(4)
+    x = rs.random_sample((n, 1))
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x))
+    ou = o.SMCUpdater(o.SimplePrecessionModel(), n, cases.FixedPrior(x))
+    ts = np.array([0.5, 2.0, 9.0])
+    w, L, norm = up.hypothetical_update(np.array([0, 1]), ts, return_likelihood=True, return_normalization=True)
+    w0, L0, norm0 = ou.hypothetical_update(np.array([0, 1]), ts, return_likelihood=True, return_normalization=True)
+    assert w.shape == (2, 3, n) and L.shape == (2, 3, n) and norm.shape == (2, 3, 1)
+    np.testing.assert_allclose(w, w0, rtol=1e-12)
+    np.testing.assert_allclose(norm, norm0, rtol=1e-12)
+
+
+def test_reset_and_setters(qb):
+    n = 64
+    np.random.seed(5)
+    up = qb.SMCUpdater(qb.RandomizedBenchmarkingModel(), n, qb.UniformDistribution([[0.8, 1], [0.3, 0.5], [0.3, 0.5]]))
+    assert up.particle_locations.shape == (n, 3) and up.n_rvs == 3 and up.n_particles == n
+    assert up.n_ess == pytest.approx(n)
+    with pytest.raises(ValueError):
+        up.reset(n_particles=10, only_params=[0])
+    old = up.particle_locations.copy()
+    up.reset(only_params=[0])
+    new = up.particle_locations
+    assert np.array_equal(new[:, 1:], old[:, 1:]) and not np.array_equal(new[:, 0], old[:, 0])
+    with pytest.raises(qb.UnsupportedModelError):
+        qb.SMCUpdater(object(), n, qb.UniformDistribution([0, 1]))
+    with pytest.raises(ValueError, match="Both a resample_a"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            qb.SMCUpdater(qb.SimplePrecessionModel(), n, qb.UniformDistribution([0, 1]), resample_a=0.9,
+                          resampler=qb.LiuWestResampler())
