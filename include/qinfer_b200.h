@@ -22,7 +22,10 @@
  *     `qb_last_error()` returns a thread-local message.  Launches are
  *     asynchronous on `stream`; nothing here synchronises unless stated.
  *   - No entry point allocates device memory; workspaces are caller-provided
- *     and sized by the `*_workspace_bytes` queries.
+ *     and sized by the `*_workspace_bytes` queries.  One workspace may be shared
+ *     by all calls issued on one stream; it must be ZERO-INITIALISED once before
+ *     first use (its first 256 bytes hold the fused-update kernel's self-resetting
+ *     last-block ticket, which no other entry point touches).
  */
 #ifndef QINFER_B200_H
 #define QINFER_B200_H

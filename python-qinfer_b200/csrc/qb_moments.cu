@@ -261,7 +261,7 @@ using namespace qb;
 extern "C" size_t qb_moments_workspace_bytes(int64_t n, int32_t d) {
     (void)n;
     const size_t nout = 1 + d + static_cast<size_t>(d) * (d + 1) / 2;
-    return static_cast<size_t>(256) * 4 * nout * sizeof(double);
+    return static_cast<size_t>(256) * 4 * nout * sizeof(double) + 256;
 }
 
 extern "C" int qb_moments(const double* d_x, const double* d_w, const double* d_stats, int64_t n, int32_t d,
@@ -270,7 +270,7 @@ extern "C" int qb_moments(const double* d_x, const double* d_w, const double* d_
     QB_REQUIRE(n >= 1 && d >= 1 && d <= QB_MAX_D, QB_ERR_INVALID_ARGUMENT, "qb_moments: bad n=%lld or d=%d",
                (long long)n, d);
     QB_REQUIRE(ws_bytes >= qb_moments_workspace_bytes(n, d), QB_ERR_WORKSPACE, "qb_moments: workspace too small");
-    double* partials = reinterpret_cast<double*>(d_ws);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);  // [0,256) is the update ticket
     const int grid = moments_grid(n, d);
     cudaStream_t st = as_stream(stream);
     switch (d) {

@@ -405,7 +405,7 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
         return QB_OK;
     }
     QB_REQUIRE(mode == QB_SCAN_FAST, QB_ERR_INVALID_ARGUMENT, "qb_cdf: unknown mode %d", mode);
-    double* tiles = reinterpret_cast<double*>(d_ws);
+    double* tiles = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);  // [0,256) is the update ticket
     const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     const int grid = capped_grid(ntiles, 8);
     cdf_tile_sums_kernel<<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles);
@@ -484,7 +484,7 @@ extern "C" int qb_compact_invalid(const uint8_t* d_invalid, int64_t n, int64_t* 
                "qb_compact_invalid: bad arguments");
     QB_REQUIRE(ws_bytes >= qb_compact_workspace_bytes(n), QB_ERR_WORKSPACE, "qb_compact_invalid: workspace too small");
     cudaStream_t st = as_stream(stream);
-    unsigned long long* tiles = reinterpret_cast<unsigned long long*>(d_ws);
+    unsigned long long* tiles = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(d_ws) + 256);
     const int64_t ntiles = (n + CMP_TILE - 1) / CMP_TILE;
     const int grid = capped_grid(ntiles, 8);
     compact_count_kernel<<<grid, CMP_THREADS, 0, st>>>(d_invalid, n, tiles);

@@ -103,7 +103,9 @@ def test_t2_fused_update_precession(qb, oracle, n):
         want_w = hyp / want_norm
         up.update(outcome, t, check_for_resample=False)
         got_w = up.particle_weights
-        np.testing.assert_allclose(got_w, want_w, rtol=1e-12, atol=1e-300)
+        # rtol 1e-12 wherever the weight matters; particles sitting on a zero of cos^2 (L ~ 1e-13) see the
+        # libm-vs-CUDA difference of the reduced argument relatively larger, hence the absolute floor
+        np.testing.assert_allclose(got_w, want_w, rtol=1e-12, atol=1e-15 * want_w.max())
         assert abs(up.normalization_record[-1] - want_norm) <= 1e-12 * want_norm
         assert abs(up.n_ess - 1 / np.sum(want_w ** 2)) <= 1e-10 * up.n_ess
         report("t2_prec_n%d_o%d_w_rel" % (n, outcome), relerr(got_w, want_w, 1e-300))
@@ -376,7 +378,11 @@ def _check_trajectory(name, out, g, mean_rtol=1e-6):
     assert int(out["resample_count"]) == int(g["resample_count"])
     np.testing.assert_allclose(out["normalization_record"], g["normalization_record"], rtol=1e-7)
     np.testing.assert_allclose(out["est_mean"], g["est_mean"], rtol=mean_rtol)          # north_star: 1e-6
-    np.testing.assert_allclose(out["est_cov"], g["est_cov"], rtol=1e-6, atol=1e-6 * np.max(np.abs(g["est_cov"])))
+    # cov = E[xx^T] - mu mu^T cancels catastrophically once |mu|^2/|cov| ~ 1e10 (the reference's own
+    # formula is then only good to eps*kappa ~ 1e-5 relative), so the 1e-6 bar gets an absolute floor of a few
+    # ulps of |mu|^2
+    floor = 16 * np.spacing(1.0) * float(np.max(np.abs(g["est_mean"])) ** 2)
+    np.testing.assert_allclose(out["est_cov"], g["est_cov"], rtol=1e-6, atol=floor)
     np.testing.assert_allclose(out["min_n_ess"], g["min_n_ess"], rtol=1e-7)
     report("t8_%s_mean_rel" % name, relerr(out["est_mean"], g["est_mean"], 1e-300))
     report("t8_%s_locs_rel" % name, relerr(out["locations"], g["locations"], 1e-12))
