@@ -198,7 +198,7 @@ def workload_config(n_per_gpu, world):
                         "LiuWest a=0.98, resample_thresh 0.5" % (n_per_gpu, world),
             "particles_per_gpu": n_per_gpu, "n_modelparams": 1,
             "l2_policy": "inputs larger than L2: each update streams 240 MB (x, w in, w out) through a 126 MB L2",
-            "resampler": "rng=philox (device), scan=fast"}
+            "resampler": "rng=philox (device), scan=fast", "updater": "lazy=True (speculative launch pipelining)"}
 
 
 # ---------------------------------------------------------------------------
@@ -223,8 +223,8 @@ def gpu_arm(args, rank, world, local_rank):
         res = qb.LiuWestResampler(a=0.98, rng='philox', seed=1000 + rank, scan='fast')
         if world > 1:
             from qinfer_b200.sharded import ShardedSMCUpdater
-            return ShardedSMCUpdater(qb.SimplePrecessionModel(), n * world, FixedPrior(prior), resampler=res)
-        return qb.SMCUpdater(qb.SimplePrecessionModel(), n, FixedPrior(prior), resampler=res)
+            return ShardedSMCUpdater(qb.SimplePrecessionModel(), n * world, FixedPrior(prior), resampler=res, lazy=True)
+        return qb.SMCUpdater(qb.SimplePrecessionModel(), n, FixedPrior(prior), resampler=res, lazy=True)
 
     def barrier():
         if dist is not None:
@@ -252,6 +252,7 @@ def gpu_arm(args, rank, world, local_rank):
         for k in range(warm, warm + steps):
             up.update(int(outcomes[k]), ts[k:k + 1])
             ev_pairs.append(cloud.last_update_events)
+        up._flush()                                      # settle the last (lazily pending) step
         stop.record()
         barrier()
         elapsed_ms = start.elapsed_time(stop)

@@ -78,10 +78,12 @@ typedef struct qb_expparams {
 /* ---- device-side stats block (16 doubles) ------------------------------- */
 #define QB_STAT_NORM 0      /* sum_i w'_i of the last update  = normalization_record entry (smc.py:357,444) */
 #define QB_STAT_SUMSQ 1     /* sum_i w'_i^2                   -> n_ess = norm^2 / sumsq (distributions.py:299-307) */
-#define QB_STAT_MIN 2       /* min_i w'_i (negative-weight check, smc.py:416-418) */
+#define QB_STAT_MIN 2       /* min_i w_i: filled by qb_weights_restat/clip; NaN after qb_fused_update (see qb_weights_min) */
 #define QB_STAT_NBAD 3      /* number of NaN or negative w'_i */
 #define QB_STAT_INV_NORM 4  /* 1/norm, or 1 if |norm| < eps (smc.py:369-373); applied lazily by the next kernel */
-#define QB_STAT_NESS 5      /* norm^2 / sumsq */
+#define QB_STAT_NESS 5      /* n_ess = norm^2 / sumsq (1 / sumsq when the |norm| < eps guard applies) */
+#define QB_STAT_TAG 6       /* caller-chosen tag of the launch that wrote this block (qb_update_ctl.tag) */
+#define QB_STAT_SKIPPED 7   /* 1 if a guarded qb_fused_update cancelled itself (see qb_update_ctl) */
 #define QB_STAT_COUNT 16
 
 /* ---- library / device --------------------------------------------------- */
@@ -103,8 +105,29 @@ int qb_weights_restat(const double* d_w, int64_t n, double* d_stats, double* d_w
  * afterwards w holds normalised, clipped weights and stats[INV_NORM] = 1. */
 int qb_weights_clip(double* d_w, int64_t n, double* d_stats, double* d_ws, size_t ws_bytes, void* stream);
 
+/* *d_out = min_i w[i] (unnormalised).  Only the warning text of smc.py:417 needs it, so the
+ * fused kernel does not track it: stats[QB_STAT_MIN] is NaN after qb_fused_update. */
+int qb_weights_min(const double* d_w, int64_t n, double* d_out, void* stream);
+
 /* ---- fused Bayes update (the hot kernel) --------------------------------- */
 size_t qb_update_workspace_bytes(int64_t n, int32_t d);
+
+/* Optional launch control.  The reference decides on the host, after every update, whether the
+ * weights need clipping (smc.py:416), the zero-weight policy applies (smc.py:423-436) or a resample is
+ * due (smc.py:275).  Those are rare, so the host may launch update k+1 BEFORE it has seen the result
+ * of update k: with `guard` set the kernel first evaluates the same three conditions on stats_in
+ * (the block update k wrote) and, if any holds, cancels itself (writes SKIPPED = 1, touches no
+ * weight).  `h_mirror` is a device-accessible pinned host block (QB_STAT_COUNT doubles) that receives
+ * a copy of stats_out with a system-scope release on its TAG word, so the host can poll plain memory
+ * instead of issuing a copy + synchronise per update. */
+typedef struct qb_update_ctl {
+    double* h_mirror;          /* may be NULL */
+    double tag;
+    double zero_weight_thresh; /* smc.py:171-175 */
+    double resample_below;     /* n_particles * resample_thresh (smc.py:275) */
+    int32_t guard;             /* 1: cancel if stats_in needs host attention */
+    int32_t guard_resample;    /* with guard: the predecessor was an update with check_for_resample */
+} qb_update_ctl;
 /* One launch: w_out[i] = (w_in[i] * stats_in[INV_NORM]) * L(outcome | x_i; ep)
  * fused with the block+warp reductions for sum, sum of squares, min and the
  * bad-weight count, finished deterministically by the last block into
@@ -116,6 +139,7 @@ int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outco
                     const double* d_x, int64_t n,
                     const double* d_w_in, double* d_w_out,
                     const double* d_stats_in, double* d_stats_out,
+                    const qb_update_ctl* ctl /* may be NULL */,
                     void* d_ws, size_t ws_bytes, void* stream);
 
 /* Plain likelihood tensor L[o][i][e] (n_o, n, n_e) — Model.likelihood

@@ -45,6 +45,8 @@ __global__ void set_uniform_kernel(double* w, int64_t n, double* stats) {
         stats[QB_STAT_NBAD] = 0.0;
         stats[QB_STAT_INV_NORM] = 1.0;
         stats[QB_STAT_NESS] = static_cast<double>(n);
+        stats[QB_STAT_TAG] = 0.0;
+        stats[QB_STAT_SKIPPED] = 0.0;
     }
 }
 
@@ -116,7 +118,9 @@ __global__ void restat_finish_kernel(const double* partials, int nblocks, double
     stats[QB_STAT_MIN] = mn;
     stats[QB_STAT_NBAD] = bad;
     stats[QB_STAT_INV_NORM] = 1.0;  // weights are taken as given
-    stats[QB_STAT_NESS] = (s * s) / q;
+    stats[QB_STAT_NESS] = 1.0 / q;  // distributions.py:299-307 on the weights as they are
+    stats[QB_STAT_TAG] = 0.0;
+    stats[QB_STAT_SKIPPED] = 0.0;
 }
 
 // ---- plain likelihood + validity -----------------------------------------------

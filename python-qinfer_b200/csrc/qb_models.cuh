@@ -6,6 +6,7 @@
 // the reference's BLAS call does.
 #pragma once
 #include "qb_common.cuh"
+#include "qb_trig.cuh"
 
 namespace qb {
 
@@ -63,7 +64,9 @@ __device__ __forceinline__ double model_pr0(const ModelView& mv, const ExpView& 
     if (KIND == QB_MODEL_PRECESSION) {
         // test_models.py:134-140: cos(t * (omega - w_) / 2) ** 2
         double dw = row(0) - ev.w_;
-        double c = cos((ev.t * dw) / 2.0);
+        double th = (ev.t * dw) / 2.0;
+        if (fabs(th) < TRIG_FAST_LIMIT) return sincos_squared_fast(th).cos2;
+        double c = cos(th);  // huge or non-finite argument: library path (Payne-Hanek)
         return c * c;
     } else if (KIND == QB_MODEL_RB) {
         // rb.py:178-195: 1 - (A * p**m + B); interleaved: p <- p or p~ * p
@@ -105,15 +108,48 @@ __device__ __forceinline__ double binom_pmf(const ExpView& ev, double p) {
     return exp(ev.logc + t1 + t2);
 }
 
+// (pr0, pr1) of the underlying two-outcome model.  pr1 = 1 - pr0 as in
+// abstract_model.py:665-686, except for the precession model where sin^2 is available directly
+// (it equals 1 - cos^2 to within the reference's own rounding and is relatively accurate near 0).
+template <int KIND, typename Row, typename Meas>
+__device__ __forceinline__ void model_pr01(const ModelView& mv, const ExpView& ev, Row row, Meas meas, int rot,
+                                           double& pr0, double& pr1) {
+    if (KIND == QB_MODEL_PRECESSION) {
+        const double dw = row(0) - ev.w_;
+        const double th = (ev.t * dw) / 2.0;
+        if (fabs(th) < TRIG_FAST_LIMIT) {
+            const SinCosSq sc = sincos_squared_fast(th);
+            pr0 = sc.cos2;
+            pr1 = sc.sin2;
+            return;
+        }
+        const double c = cos(th);
+        pr0 = c * c;
+        pr1 = 1.0 - pr0;
+        return;
+    }
+    pr0 = model_pr0<KIND>(mv, ev, row, meas, rot);
+    pr1 = 1.0 - pr0;
+}
+
 template <int KIND, bool BINOM, typename Row, typename Meas>
 __device__ __forceinline__ double model_likelihood(const ModelView& mv, const ExpView& ev, Row row, Meas meas,
                                                    int rot) {
-    double pr0 = model_pr0<KIND>(mv, ev, row, meas, rot);
-    if (BINOM) {
-        double pr1 = 1.0 - pr0;  // underlying.likelihood([1], ...) (derived_models.py:318-321)
-        return binom_pmf(ev, pr1);
+    if (KIND == QB_MODEL_PRECESSION && !BINOM) {
+        // two-outcome precession: one select between sin^2(r) and 1 - sin^2(r)
+        const double dw = row(0) - ev.w_;
+        const double th = (ev.t * dw) / 2.0;
+        if (fabs(th) < TRIG_FAST_LIMIT) return cos2_or_sin2_fast(th, ev.outcome0);
+        const double c = cos(th);  // huge or non-finite argument: library path (Payne-Hanek)
+        const double pr0 = c * c;
+        return ev.outcome0 ? pr0 : 1.0 - pr0;
     }
-    return ev.outcome0 ? pr0 : 1.0 - pr0;
+    double pr0, pr1;
+    model_pr01<KIND>(mv, ev, row, meas, rot, pr0, pr1);
+    // underlying.likelihood([1], ...) = 1 - pr0 exactly as derived_models.py:318-321 forms it: log(pr1)
+    // amplifies the last bit of a small pr1, so the binomial path keeps the reference's rounding sequence
+    if (BINOM) return binom_pmf(ev, 1.0 - pr0);
+    return ev.outcome0 ? pr0 : pr1;
 }
 
 // Model.are_models_valid for one particle.

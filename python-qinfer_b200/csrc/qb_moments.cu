@@ -217,25 +217,28 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_generic_kernel(const doub
     }
 }
 
-// ---- finish: fixed-order sum over blocks, unpack the triangle -----------------------
-__global__ void moments_finish_kernel(const double* __restrict__ partials, int nblocks, int d,
-                                      double* __restrict__ out) {
+// ---- finish: one warp per output entry, fixed summation order, unpack the triangle ---------
+__global__ void __launch_bounds__(256) moments_finish_kernel(const double* __restrict__ partials, int nblocks, int d,
+                                                             double* __restrict__ out) {
     const int nout = 1 + d + d * (d + 1) / 2;
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < nout; o += gridDim.x * blockDim.x) {
-        double v = 0.0;
-        for (int b = 0; b < nblocks; ++b) v += partials[static_cast<int64_t>(b) * nout + o];
-        if (o <= d) {
-            out[o] = v;
-        } else {
-            int rem = o - 1 - d, m = 0;
-            while (rem >= d - m) {
-                rem -= d - m;
-                ++m;
-            }
-            const int c = m + rem;
-            out[1 + d + m * d + c] = v;
-            out[1 + d + c * d + m] = v;
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= nout) return;
+    double v = 0.0;
+    for (int b = lane; b < nblocks; b += 32) v += partials[static_cast<int64_t>(b) * nout + o];
+    v = warp_sum(v);
+    if (lane != 0) return;
+    if (o <= d) {
+        out[o] = v;
+    } else {
+        int rem = o - 1 - d, m = 0;
+        while (rem >= d - m) {
+            rem -= d - m;
+            ++m;
         }
+        const int c = m + rem;
+        out[1 + d + m * d + c] = v;
+        out[1 + d + c * d + m] = v;
     }
 }
 
@@ -285,7 +288,8 @@ extern "C" int qb_moments(const double* d_x, const double* d_w, const double* d_
         }
     }
     QB_CUDA_CHECK(cudaGetLastError());
-    moments_finish_kernel<<<1, 256, 0, st>>>(partials, grid, d, d_out);
+    const int nout = 1 + d + d * (d + 1) / 2;
+    moments_finish_kernel<<<(nout + 7) / 8, 256, 0, st>>>(partials, grid, d, d_out);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

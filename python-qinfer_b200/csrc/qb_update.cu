@@ -7,10 +7,15 @@
 //
 // Data movement: full tiles of the row-major (n, d) particle slab and of the
 // weight vector are staged global->shared with 1-D bulk TMA copies
-// (cp.async.bulk + mbarrier complete_tx) through a STAGES-deep ring, so every
-// SM keeps STAGES x ~16 KB of loads in flight without holding them in
-// registers; the fp64 likelihood math then runs out of shared memory and the
-// new weights are written back with fully coalesced 8-B streaming stores.
+// (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a STAGES-deep
+// ring, so every SM keeps STAGES x 16-24 KB of loads in flight without holding
+// them in registers.  For d in {1,3,4} each thread then owns PAIRS of adjacent
+// particles: 128-bit conflict-free shared loads in, one 128-bit streaming store
+// of the two new weights out, all tile offsets compile-time immediates — the
+// instruction count per particle is what bounds this kernel once the memory
+// system is fed (ncu r1: 114 -> ~35 warp-instructions per 32 particles).
+// Generic d (tomography) walks its row with a per-lane rotated start so that
+// rows 128 B apart do not collide on shared-memory banks.
 // The ragged last tile (byte count not a multiple of 16) is loaded directly.
 #include "qb_models.cuh"
 
@@ -30,74 +35,127 @@ struct UpdateParams {
     int64_t n;
     int32_t tile;            // particles per tile
     int32_t d;
+    double* mirror;          // device-accessible pinned host copy of the stats block (or NULL)
+    double tag;
+    double zero_weight_thresh, resample_below;
+    int32_t guard, guard_resample;
     ModelView mv;
     ExpView ev;
     double meas[QB_MAX_D];
 };
 
-__device__ __forceinline__ void block_reduce4(double& s, double& q, double& mn, double& bad, double* red) {
+__device__ __forceinline__ void block_reduce3(double& s, double& q, unsigned int& bad, double* red,
+                                              unsigned int* redu) {
     s = warp_sum(s);
     q = warp_sum(q);
-    mn = warp_min(mn);
-    bad = warp_sum(bad);
+    bad = __reduce_add_sync(0xffffffffu, bad);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
-        red[wid * 4 + 0] = s;
-        red[wid * 4 + 1] = q;
-        red[wid * 4 + 2] = mn;
-        red[wid * 4 + 3] = bad;
+        red[wid * 2 + 0] = s;
+        red[wid * 2 + 1] = q;
+        redu[wid] = bad;
     }
     __syncthreads();
     if (wid == 0) {
         const int nw = blockDim.x >> 5;
-        s = (lane < nw) ? red[lane * 4 + 0] : 0.0;
-        q = (lane < nw) ? red[lane * 4 + 1] : 0.0;
-        mn = (lane < nw) ? red[lane * 4 + 2] : INFINITY;
-        bad = (lane < nw) ? red[lane * 4 + 3] : 0.0;
+        s = (lane < nw) ? red[lane * 2 + 0] : 0.0;
+        q = (lane < nw) ? red[lane * 2 + 1] : 0.0;
+        bad = (lane < nw) ? redu[lane] : 0u;
         s = warp_sum(s);
         q = warp_sum(q);
-        mn = warp_min(mn);
-        bad = warp_sum(bad);
+        bad = __reduce_add_sync(0xffffffffu, bad);
+    }
+}
+
+// Does the step that produced `st` need the host before another update may run?  (negative/NaN
+// weights, smc.py:416; the zero-weight policies, smc.py:423-436; the resample trigger, smc.py:275;
+// or it was itself skipped.)  Evaluated on the device so that the NEXT update can be launched
+// speculatively and cancel itself.
+__device__ __forceinline__ bool needs_host(const double* st, double zero_thresh, int check_resample,
+                                           double resample_below) {
+    const double eps = 2.220446049250313e-16;
+    const double norm = st[QB_STAT_NORM];
+    const double total = (fabs(norm) < eps) ? norm : 1.0;  // np.sum of the normalised weights
+    bool attn = (st[QB_STAT_NBAD] > 0.0) || (total <= zero_thresh) || (st[QB_STAT_SKIPPED] != 0.0);
+    if (check_resample) attn = attn || (st[QB_STAT_NESS] < resample_below);
+    return attn;
+}
+
+__device__ __forceinline__ void publish_stats(const UpdateParams& p, double norm, double sumsq, double nbad,
+                                              double skipped) {
+    const double eps = 2.220446049250313e-16;  // np.spacing(1), smc.py:370
+    double v[QB_STAT_COUNT];
+#pragma unroll
+    for (int k = 0; k < QB_STAT_COUNT; ++k) v[k] = 0.0;
+    v[QB_STAT_NORM] = norm;
+    v[QB_STAT_SUMSQ] = sumsq;
+    v[QB_STAT_MIN] = nan("");  // computed on demand (qb_weights_min) when NBAD > 0
+    v[QB_STAT_NBAD] = nbad;
+    v[QB_STAT_INV_NORM] = (fabs(norm) < eps) ? 1.0 : 1.0 / norm;
+    // n_ess = 1 / sum(w_normalised^2); when the norm guard of smc.py:369-370 applies the weights stay as they are
+    v[QB_STAT_NESS] = (fabs(norm) < eps) ? 1.0 / sumsq : (norm * norm) / sumsq;
+    v[QB_STAT_TAG] = p.tag;
+    v[QB_STAT_SKIPPED] = skipped;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p.stats_out[k] = v[k];
+    if (p.mirror != nullptr) {
+        volatile double* m = p.mirror;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k != QB_STAT_TAG) m[k] = v[k];
+        __threadfence_system();
+        m[QB_STAT_TAG] = p.tag;  // the host spins on this word
     }
 }
 
 // Final deterministic reduction of per-block partials by the last block to finish.
-__device__ void finish_stats(const double* partials, int nblocks, double* stats_out, double* red) {
-    double s = 0.0, q = 0.0, mn = INFINITY, bad = 0.0;
+__device__ void finish_stats(const UpdateParams& p, int nblocks, double* red, unsigned int* redu) {
+    double s = 0.0, q = 0.0, bad = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-        s += partials[b * 4 + 0];
-        q += partials[b * 4 + 1];
-        mn = fmin(mn, partials[b * 4 + 2]);
-        bad += partials[b * 4 + 3];
+        s += p.partials[b * 4 + 0];
+        q += p.partials[b * 4 + 1];
+        bad += p.partials[b * 4 + 2];
     }
+    unsigned int ubad = static_cast<unsigned int>(bad);
     __syncthreads();
-    block_reduce4(s, q, mn, bad, red);
-    if (threadIdx.x == 0) {
-        const double eps = 2.220446049250313e-16;  // np.spacing(1), smc.py:370
-        stats_out[QB_STAT_NORM] = s;
-        stats_out[QB_STAT_SUMSQ] = q;
-        stats_out[QB_STAT_MIN] = mn;
-        stats_out[QB_STAT_NBAD] = bad;
-        stats_out[QB_STAT_INV_NORM] = (fabs(s) < eps) ? 1.0 : 1.0 / s;
-        stats_out[QB_STAT_NESS] = (s * s) / q;
-    }
+    block_reduce3(s, q, ubad, red, redu);
+    if (threadIdx.x == 0) publish_stats(p, s, q, static_cast<double>(ubad), 0.0);
 }
 
-template <int KIND, bool BINOM>
+struct Acc {
+    double s, q;
+    unsigned int bad;
+};
+
+__device__ __forceinline__ void accumulate(Acc& a, double wv) {
+    a.s += wv;
+    a.q = fma(wv, wv, a.q);
+    a.bad += (wv >= 0.0) ? 0u : 1u;  // counts negatives and NaNs (smc.py:416)
+}
+
+// DT > 0: compile-time n_modelparams, pair processing.  DT == 0: runtime d.
+template <int KIND, bool BINOM, int DT>
 __global__ void __launch_bounds__(UPD_THREADS) fused_update_kernel(const __grid_constant__ UpdateParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int d = p.d;
-    const int tile = p.tile;
+    constexpr int TILE_CT = (DT == 1) ? 1024 : 512;  // must match choose_tile()
+    const int d = (DT > 0) ? DT : p.d;
+    const int tile = (DT > 0) ? TILE_CT : p.tile;
     const uint32_t x_bytes = static_cast<uint32_t>(tile) * d * 8u;
     const uint32_t w_bytes = static_cast<uint32_t>(tile) * 8u;
     const uint32_t stage_bytes = x_bytes + w_bytes;  // multiples of 128 by construction (tile % 16 == 0)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // UPD_STAGES barriers in the first 128 B
     double* meas_s = reinterpret_cast<double*>(smem_raw + 128);
     unsigned char* ring = smem_raw + 128 + QB_MAX_D * 8;
-    __shared__ double red[(UPD_THREADS / 32) * 4];
+    __shared__ double red[(UPD_THREADS / 32) * 2];
+    __shared__ unsigned int redu[UPD_THREADS / 32];
     __shared__ unsigned int is_last;
 
     const int tid = threadIdx.x;
+    if (p.guard && needs_host(p.stats_in, p.zero_weight_thresh, p.guard_resample, p.resample_below)) {
+        // speculative launch whose predecessor needs the host: do nothing, say so
+        if (blockIdx.x == 0 && tid == 0) publish_stats(p, p.stats_in[QB_STAT_NORM], p.stats_in[QB_STAT_SUMSQ], 0.0, 1.0);
+        return;
+    }
     const int64_t ntiles = (p.n + tile - 1) / tile;
     const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -127,8 +185,11 @@ __global__ void __launch_bounds__(UPD_THREADS) fused_update_kernel(const __grid_
     }
 
     const double inv_norm = p.stats_in[QB_STAT_INV_NORM];
-    double acc_s = 0.0, acc_q = 0.0, acc_min = INFINITY, acc_bad = 0.0;
+    const ModelView mv = p.mv;
+    const ExpView ev = p.ev;
+    Acc a0 = {0.0, 0.0, 0u}, a1 = {0.0, 0.0, 0u};
     const int lane = tid & 31;
+    auto meas = [&](int c) { return meas_s[c]; };
 
     for (int64_t i = 0; i < my_tiles; ++i) {
         const int s = static_cast<int>(i % UPD_STAGES);
@@ -136,38 +197,67 @@ __global__ void __launch_bounds__(UPD_THREADS) fused_update_kernel(const __grid_
         const int64_t t = blockIdx.x + i * gridDim.x;
         const int64_t first = t * tile;
         const int cnt = static_cast<int>((p.n - first < tile) ? (p.n - first) : tile);
-        double* xs = reinterpret_cast<double*>(ring + static_cast<size_t>(s) * stage_bytes);
-        double* ws = reinterpret_cast<double*>(ring + static_cast<size_t>(s) * stage_bytes + x_bytes);
+        const double* xs = reinterpret_cast<const double*>(ring + static_cast<size_t>(s) * stage_bytes);
+        const double* ws = reinterpret_cast<const double*>(ring + static_cast<size_t>(s) * stage_bytes + x_bytes);
+        double* wo = p.w_out + first;
         if (cnt == tile) {
             mbar_wait(&bars[s], parity);
-        } else {  // ragged last tile: plain coalesced loads into the same staging buffers
-            for (int j = tid; j < cnt * d; j += UPD_THREADS) xs[j] = ldg_stream(p.x + first * d + j);
-            for (int j = tid; j < cnt; j += UPD_THREADS) ws[j] = ldg_stream(p.w_in + first + j);
-            __syncthreads();
-        }
-        for (int j = tid; j < cnt; j += UPD_THREADS) {
-            const double* xr = xs + static_cast<size_t>(j) * d;
-            auto row = [&](int c) { return xr[c]; };
-            auto meas = [&](int c) { return meas_s[c]; };
-            const double L = model_likelihood<KIND, BINOM>(p.mv, p.ev, row, meas, lane);
-            const double wn = ws[j] * inv_norm;  // previous step's normalisation, applied lazily
-            const double wv = wn * L;            // smc.py:354
-            stg_stream(p.w_out + first + j, wv);
-            acc_s += wv;
-            acc_q = fma(wv, wv, acc_q);
-            acc_min = fmin(acc_min, wv);
-            acc_bad += (wv >= 0.0) ? 0.0 : 1.0;  // counts negatives and NaNs (smc.py:416)
+            if constexpr (DT > 0) {
+                // pairs (2j, 2j+1): 128-bit shared loads, one 128-bit streaming store
+                constexpr int NPAIRS = TILE_CT >> 1;
+#pragma unroll
+                for (int j = tid; j < NPAIRS; j += UPD_THREADS) {
+                    const double2 wp = *reinterpret_cast<const double2*>(ws + 2 * j);
+                    double xr[2 * DT];
+#pragma unroll
+                    for (int v = 0; v < DT; ++v) {
+                        const double2 t2 = *reinterpret_cast<const double2*>(xs + 2 * DT * j + 2 * v);
+                        xr[2 * v] = t2.x;
+                        xr[2 * v + 1] = t2.y;
+                    }
+                    auto row0 = [&](int c) { return xr[c]; };
+                    auto row1 = [&](int c) { return xr[DT + c]; };
+                    const double L0 = model_likelihood<KIND, BINOM>(mv, ev, row0, meas, 0);
+                    const double L1 = model_likelihood<KIND, BINOM>(mv, ev, row1, meas, 0);
+                    const double w0 = (wp.x * inv_norm) * L0;  // smc.py:354 on the lazily normalised weight
+                    const double w1 = (wp.y * inv_norm) * L1;
+                    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(wo + 2 * j), "d"(w0),
+                                 "d"(w1)
+                                 : "memory");
+                    accumulate(a0, w0);
+                    accumulate(a1, w1);
+                }
+            } else {
+                for (int j = tid; j < cnt; j += UPD_THREADS) {
+                    const double* xr = xs + static_cast<size_t>(j) * d;
+                    auto row = [&](int c) { return xr[c]; };
+                    const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, lane);
+                    const double wv = (ws[j] * inv_norm) * L;
+                    stg_stream(wo + j, wv);
+                    accumulate(a0, wv);
+                }
+            }
+        } else {  // ragged last tile: straight from global memory
+            for (int j = tid; j < cnt; j += UPD_THREADS) {
+                const double* xr = p.x + (first + j) * d;
+                auto row = [&](int c) { return xr[c]; };
+                const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, 0);
+                const double wv = (p.w_in[first + j] * inv_norm) * L;
+                wo[j] = wv;
+                accumulate(a0, wv);
+            }
         }
         __syncthreads();  // every thread is done with stage s
         if (tid == 0 && i + UPD_STAGES < my_tiles) issue(i + UPD_STAGES);
     }
 
-    block_reduce4(acc_s, acc_q, acc_min, acc_bad, red);
+    double acc_s = a0.s + a1.s, acc_q = a0.q + a1.q;
+    unsigned int acc_bad = a0.bad + a1.bad;
+    block_reduce3(acc_s, acc_q, acc_bad, red, redu);
     if (tid == 0) {
         p.partials[blockIdx.x * 4 + 0] = acc_s;
         p.partials[blockIdx.x * 4 + 1] = acc_q;
-        p.partials[blockIdx.x * 4 + 2] = acc_min;
-        p.partials[blockIdx.x * 4 + 3] = acc_bad;
+        p.partials[blockIdx.x * 4 + 2] = static_cast<double>(acc_bad);
         __threadfence();
         const unsigned int prev = atomicAdd(p.ticket, 1u);
         is_last = (prev == gridDim.x - 1) ? 1u : 0u;
@@ -175,17 +265,19 @@ __global__ void __launch_bounds__(UPD_THREADS) fused_update_kernel(const __grid_
     __syncthreads();
     if (is_last) {
         __threadfence();
-        finish_stats(p.partials, gridDim.x, p.stats_out, red);
+        finish_stats(p, gridDim.x, red, redu);
         if (tid == 0) *p.ticket = 0u;  // ready for the next launch on this stream
     }
 }
 
-// Tile size: ~16 KB per stage, a multiple of 16 particles so every bulk copy is 128-B granular.
+// Tile size: 16-24 KB per stage; a multiple of 2 * UPD_THREADS particles for the pair kernels,
+// of 16 particles otherwise, so every bulk copy is 128-B granular.
 static int choose_tile(int d) {
+    if (d == 1) return 1024;   // 16 KB / stage
+    if (d == 3 || d == 4) return 512;  // 16 / 20 KB
     int t = 2048 / (d + 1);
     t = (t / 16) * 16;
     if (t < 16) t = 16;
-    if (t > 1024) t = 1024;
     return t;
 }
 
@@ -198,13 +290,15 @@ typedef void (*update_kernel_t)(const UpdateParams);
 static update_kernel_t pick_update_kernel(const qb_model& m) {
     switch (m.kind) {
         case QB_MODEL_PRECESSION:
-            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true>
-                              : fused_update_kernel<QB_MODEL_PRECESSION, false>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true, 1>
+                              : fused_update_kernel<QB_MODEL_PRECESSION, false, 1>;
         case QB_MODEL_RB:
-            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true> : fused_update_kernel<QB_MODEL_RB, false>;
+            if (m.interleaved)
+                return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 4> : fused_update_kernel<QB_MODEL_RB, false, 4>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 3> : fused_update_kernel<QB_MODEL_RB, false, 3>;
         case QB_MODEL_TOMOGRAPHY:
-            return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true>
-                              : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true, 0>
+                              : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false, 0>;
     }
     return nullptr;
 }
@@ -230,22 +324,45 @@ int validate_model(const qb_model* m) {
     return QB_OK;
 }
 
-struct UpdateLaunchCache {
-    int blocks_per_sm[4][2];
-    bool ready[4][2];
-};
-static UpdateLaunchCache g_cache = {};
-
-static int update_grid_limit(const qb_model& m, update_kernel_t k, size_t smem) {
-    const int bi = m.binomial ? 1 : 0;
-    if (!g_cache.ready[m.kind][bi]) {
-        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-        g_cache.ready[m.kind][bi] = true;
-    }
+static int update_grid_limit(update_kernel_t k, size_t smem) {
+    // the attribute call is idempotent and cheap; keeping it unconditional avoids per-device caches
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, UPD_THREADS, smem) != cudaSuccess) return -1;
     if (per_sm < 1) per_sm = 1;
     return per_sm * sm_count();
+}
+
+struct GridCacheEntry {
+    update_kernel_t k;
+    int dev;
+    int limit;
+};
+static GridCacheEntry g_grid_cache[32];
+static int g_grid_cache_n = 0;
+
+static int cached_grid_limit(update_kernel_t k, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int i = 0; i < g_grid_cache_n; ++i)
+        if (g_grid_cache[i].k == k && g_grid_cache[i].dev == dev) return g_grid_cache[i].limit;
+    const int limit = update_grid_limit(k, smem);
+    if (limit > 0 && g_grid_cache_n < 32) g_grid_cache[g_grid_cache_n++] = {k, dev, limit};
+    return limit;
+}
+
+// ---- smallest weight (only needed for the warning text of smc.py:417) ------------------------
+__global__ void __launch_bounds__(256) weights_min_kernel(const double* __restrict__ w, int64_t n, double* out) {
+    __shared__ double red[8];
+    double mn = INFINITY;
+    for (int64_t i = threadIdx.x; i < n; i += 256) mn = fmin(mn, w[i]);
+    mn = warp_min(mn);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) mn = fmin(mn, red[k]);
+        *out = mn;
+    }
 }
 
 }  // namespace qb
@@ -261,7 +378,8 @@ extern "C" size_t qb_update_workspace_bytes(int64_t n, int32_t d) {
 
 extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outcome, const double* d_x,
                                int64_t n, const double* d_w_in, double* d_w_out, const double* d_stats_in,
-                               double* d_stats_out, void* d_ws, size_t ws_bytes, void* stream) {
+                               double* d_stats_out, const qb_update_ctl* ctl, void* d_ws, size_t ws_bytes,
+                               void* stream) {
     int rc = validate_model(model);
     if (rc != QB_OK) return rc;
     QB_REQUIRE(ep && d_x && d_w_in && d_w_out && d_stats_in && d_stats_out && d_ws, QB_ERR_INVALID_ARGUMENT,
@@ -269,8 +387,9 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
     QB_REQUIRE(n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: n must be >= 1, got %lld", (long long)n);
     QB_REQUIRE(ws_bytes >= qb_update_workspace_bytes(n, model->d), QB_ERR_WORKSPACE,
                "qb_fused_update: workspace too small");
-    QB_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w_in) & 15) == 0,
-               QB_ERR_INVALID_ARGUMENT, "qb_fused_update: x and w must be 16-byte aligned");
+    QB_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w_in) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d_w_out) & 15) == 0,
+               QB_ERR_INVALID_ARGUMENT, "qb_fused_update: x, w_in and w_out must be 16-byte aligned");
 
     UpdateParams p;
     p.x = d_x;
@@ -283,19 +402,34 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
     p.n = n;
     p.d = model->d;
     p.tile = choose_tile(model->d);
+    p.mirror = ctl ? ctl->h_mirror : nullptr;
+    p.tag = ctl ? ctl->tag : 0.0;
+    p.zero_weight_thresh = ctl ? ctl->zero_weight_thresh : 0.0;
+    p.resample_below = ctl ? ctl->resample_below : 0.0;
+    p.guard = ctl ? ctl->guard : 0;
+    p.guard_resample = ctl ? ctl->guard_resample : 0;
+    QB_REQUIRE(d_stats_in != d_stats_out || !p.guard, QB_ERR_INVALID_ARGUMENT,
+               "qb_fused_update: a guarded update needs distinct stats_in / stats_out blocks");
     p.mv = make_model_view(*model);
     p.ev = make_exp_view(*model, *ep, outcome);
     for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? ep->meas[c] : 0.0;
 
     update_kernel_t k = pick_update_kernel(*model);
     const size_t smem = update_smem_bytes(model->d);
-    const int limit = update_grid_limit(*model, k, smem);
+    const int limit = cached_grid_limit(k, smem);
     QB_REQUIRE(limit > 0, QB_ERR_CUDA, "qb_fused_update: occupancy query failed: %s",
                cudaGetErrorString(cudaGetLastError()));
     const int64_t ntiles = (n + p.tile - 1) / p.tile;
     int grid = static_cast<int>(ntiles < limit ? ntiles : limit);
     if (grid > 32 * 256) grid = 32 * 256;
     k<<<grid, UPD_THREADS, smem, as_stream(stream)>>>(p);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_weights_min(const double* d_w, int64_t n, double* d_out, void* stream) {
+    QB_REQUIRE(d_w && d_out && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_weights_min: bad arguments");
+    weights_min_kernel<<<1, 256, 0, as_stream(stream)>>>(d_w, n, d_out);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

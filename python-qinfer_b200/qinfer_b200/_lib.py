@@ -7,7 +7,8 @@ import ctypes
 import os
 
 QB_MAX_D = 64
-QB_STAT_NORM, QB_STAT_SUMSQ, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_INV_NORM, QB_STAT_NESS = range(6)
+(QB_STAT_NORM, QB_STAT_SUMSQ, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_INV_NORM, QB_STAT_NESS, QB_STAT_TAG,
+ QB_STAT_SKIPPED) = range(8)
 QB_STAT_COUNT = 16
 QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY = 1, 2, 3
 QB_SCAN_FAST, QB_SCAN_EXACT = 0, 1
@@ -24,6 +25,11 @@ class QbExpparams(ctypes.Structure):
     _fields_ = [("t", ctypes.c_double), ("w_", ctypes.c_double), ("m", ctypes.c_int64),
                 ("reference", ctypes.c_int32), ("reserved", ctypes.c_int32), ("n_meas", ctypes.c_int64),
                 ("meas", ctypes.c_double * QB_MAX_D)]
+
+
+class QbUpdateCtl(ctypes.Structure):
+    _fields_ = [("h_mirror", ctypes.c_void_p), ("tag", ctypes.c_double), ("zero_weight_thresh", ctypes.c_double),
+                ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("guard_resample", ctypes.c_int32)]
 
 
 class QbError(RuntimeError):
@@ -46,9 +52,10 @@ SIGNATURES = {
     "qb_weights_normalized": (ctypes.c_int, [_P, _I64, _P, _P, _P]),
     "qb_weights_restat": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P]),
     "qb_weights_clip": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P]),
+    "qb_weights_min": (ctypes.c_int, [_P, _I64, _P, _P]),
     "qb_update_workspace_bytes": (_SZ, [_I64, _I32]),
     "qb_fused_update": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I64, _P, _I64,
-                                       _P, _P, _P, _P, _P, _SZ, _P]),
+                                       _P, _P, _P, _P, ctypes.POINTER(QbUpdateCtl), _P, _SZ, _P]),
     "qb_likelihood": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I32,
                                      ctypes.POINTER(_I64), _I32, _P, _I64, _P, _P]),
     "qb_are_models_valid": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _P, _P]),

@@ -13,8 +13,10 @@ import numpy as np
 import torch
 
 from . import _lib
+import time
+
 from ._lib import (QB_STAT_COUNT, QB_STAT_INV_NORM, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NESS, QB_STAT_NORM,
-                   QB_STAT_SUMSQ, check)
+                   QB_STAT_SKIPPED, QB_STAT_SUMSQ, QB_STAT_TAG, check)
 
 
 def _require_cuda(device=None):
@@ -43,10 +45,16 @@ class DeviceCloud(object):
             f64 = dict(dtype=torch.float64, device=self.device)
             self.x = torch.empty((self.n, self.d), **f64)
             self.x_alt = None                     # allocated at the first resample
-            self.w = torch.empty((self.n,), **f64)
-            self.w_alt = torch.empty((self.n,), **f64)
-            self.stats = torch.zeros((QB_STAT_COUNT,), **f64)
-            self.stats_alt = torch.zeros((QB_STAT_COUNT,), **f64)
+            # weights and stats are ping-pong pairs: `cur` is the committed state, 1 - cur receives the
+            # next update (so a rejected update leaves the committed weights intact, smc.py:423-441)
+            self._w = [torch.empty((self.n,), **f64), torch.empty((self.n,), **f64)]
+            self._stats = [torch.zeros((QB_STAT_COUNT,), **f64), torch.zeros((QB_STAT_COUNT,), **f64)]
+            self.cur = 0
+            # host-visible copy of each stats block, written by the kernel itself (pinned, device-accessible)
+            self.mirror = torch.zeros((2 * QB_STAT_COUNT,), dtype=torch.float64, pin_memory=True)
+            self.mirror_np = self.mirror.numpy()
+            self._ctl = _lib.QbUpdateCtl()
+            self._tag = 0
             ws_bytes = max(self.lib.qb_update_workspace_bytes(self.n, self.d),
                            self.lib.qb_moments_workspace_bytes(self.n, self.d),
                            self.lib.qb_cdf_workspace_bytes(self.n),
@@ -67,6 +75,12 @@ class DeviceCloud(object):
         self.launches = 0
         self.time_updates = False          # bench: CUDA events around each fused-update launch
         self.last_update_events = None
+
+    # committed / pending views of the ping-pong buffers
+    w = property(lambda self: self._w[self.cur])
+    w_alt = property(lambda self: self._w[1 - self.cur])
+    stats = property(lambda self: self._stats[self.cur])
+    stats_alt = property(lambda self: self._stats[1 - self.cur])
 
     # ---- host <-> device ---------------------------------------------------
     def upload_locations(self, locs):
@@ -106,29 +120,62 @@ class DeviceCloud(object):
         return self.stats_host.numpy()
 
     # ---- the hot kernel -------------------------------------------------------
-    def fused_update(self, ep_record, outcome):
-        """Launch the fused update into the alternate weight/stats buffers and
-        return the new stats (host).  Call ``commit_update`` to accept it."""
+    def fused_update(self, ep_record, outcome, src, guard=False, guard_resample=False, zero_weight_thresh=0.0,
+                     resample_below=0.0):
+        """Launch the fused update reading weights/stats buffer ``src`` and writing buffer ``1 - src``;
+        the kernel mirrors its stats block into pinned host slot ``1 - src``.  Returns the launch tag.
+        ``guard``: speculative launch that cancels itself if the step that produced ``src`` needs the host."""
+        dst = 1 - src
+        self._tag += 1
+        ctl = self._ctl
+        ctl.h_mirror = self.mirror.data_ptr() + dst * QB_STAT_COUNT * 8
+        ctl.tag = float(self._tag)
+        ctl.zero_weight_thresh = zero_weight_thresh
+        ctl.resample_below = resample_below
+        ctl.guard = 1 if guard else 0
+        ctl.guard_resample = 1 if guard_resample else 0
         if self.time_updates:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep_record), int(outcome), _ptr(self.x), self.n,
-                                       _ptr(self.w), _ptr(self.w_alt), _ptr(self.stats), _ptr(self.stats_alt),
-                                       _ptr(self.ws), self.ws_bytes, _stream()))
+                                       _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
+                                       _ptr(self._stats[dst]), ctypes.byref(ctl), _ptr(self.ws), self.ws_bytes,
+                                       _stream()))
         if self.time_updates:
             e1.record()
             self.last_update_events = (e0, e1)
         self.launches += 1
+        return self._tag
+
+    def wait_stats(self, slot, tag, timeout_s=120.0):
+        """Spin on the pinned mirror of stats buffer ``slot`` until the launch ``tag`` has published it."""
+        m = self.mirror_np
+        base = slot * QB_STAT_COUNT
+        want = float(tag)
+        if m[base + QB_STAT_TAG] != want:
+            t0 = time.perf_counter()
+            while m[base + QB_STAT_TAG] != want:
+                if time.perf_counter() - t0 > timeout_s:
+                    torch.cuda.synchronize()       # surfaces a CUDA error if the kernel died
+                    raise _lib.QbError("timed out waiting for the fused-update kernel (tag %d)" % tag)
+        return m[base:base + QB_STAT_COUNT]
+
+    def pending_min_weight(self, slot):
+        """Smallest weight of weights buffer ``slot``, for the warning text of smc.py:417."""
+        out = self.moments_out[:1]
+        check(self.lib.qb_weights_min(_ptr(self._w[slot]), self.n, _ptr(out), _stream()))
+        self.launches += 1
+        return float(out.cpu().numpy()[0])
 
     def commit_update(self):
-        self.w, self.w_alt = self.w_alt, self.w
-        self.stats, self.stats_alt = self.stats_alt, self.stats
+        self.cur = 1 - self.cur
 
-    def clip_weights(self):
-        """smc.py:416-418 on the committed weights."""
-        check(self.lib.qb_weights_clip(_ptr(self.w), self.n, _ptr(self.stats), _ptr(self.ws), self.ws_bytes,
-                                       _stream()))
+    def clip_weights(self, slot):
+        """smc.py:416-418 on weights buffer ``slot`` (normalise, clip to [0,1], re-derive its stats)."""
+        check(self.lib.qb_weights_clip(_ptr(self._w[slot]), self.n, _ptr(self._stats[slot]), _ptr(self.ws),
+                                       self.ws_bytes, _stream()))
         self.launches += 2
+        return self.read_stats(self._stats[slot])
 
     # ---- moments ------------------------------------------------------------------
     def moments(self):
@@ -203,8 +250,7 @@ class DeviceCloud(object):
         if n_new != self.n:
             self.n = int(n_new)
             f64 = dict(dtype=torch.float64, device=self.device)
-            self.w = torch.empty((self.n,), **f64)
-            self.w_alt = torch.empty((self.n,), **f64)
+            self._w = [torch.empty((self.n,), **f64), torch.empty((self.n,), **f64)]
             old_x = self.x
             self.x = self.x_alt
             self.x_alt = None

@@ -44,8 +44,16 @@ class ModelDescriptor(object):
         return self.kind == _lib.QB_MODEL_TOMOGRAPHY
 
     def expparams_record(self, expparams, idx=0):
-        """One element of an ``expparams`` array -> ``qb_expparams``."""
-        ep = _lib.QbExpparams()
+        """One element of an ``expparams`` array -> a new ``qb_expparams``."""
+        return self.fill_record(_lib.QbExpparams(), expparams, idx)
+
+    def fill_record(self, ep, expparams, idx=0):
+        """Fill an existing ``qb_expparams`` (the hot loop re-uses one struct per updater)."""
+        if self.kind == _lib.QB_MODEL_PRECESSION and not self.binomial and type(expparams) is np.ndarray \
+                and expparams.dtype.names is None:
+            ep.t = float(expparams.flat[idx])                 # SimplePrecessionModel: bare float array
+            ep.w_ = 0.0
+            return ep
         arr = np.asarray(expparams)
         names = arr.dtype.names
         rec = arr.reshape(-1)[idx] if arr.ndim else arr[()]

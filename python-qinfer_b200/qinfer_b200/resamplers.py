@@ -145,8 +145,12 @@ class LiuWestResampler(Resampler):
             cloud.upload_locations(particle_dist.particle_locations)
             cloud.upload_weights(particle_dist.particle_weights)
 
-        mean = particle_dist.est_mean() if precomputed_mean is None else precomputed_mean
-        cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
+        if on_device and precomputed_mean is None and precomputed_cov is None:
+            _, mean, m2 = cloud.moments()                    # one pass gives both (resamplers.py:266-273)
+            cov = covariance_from_moments(mean, m2)
+        else:
+            mean = particle_dist.est_mean() if precomputed_mean is None else precomputed_mean
+            cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
         if n_particles is None:
             n_particles = (particle_dist.n_particles if self._default_n_particles is None
                            else self._default_n_particles)

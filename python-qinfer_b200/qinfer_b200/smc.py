@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from ._exceptions import ApproximationWarning, ResamplerWarning
-from ._lib import QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NORM, QB_STAT_SUMSQ
+from ._lib import QB_STAT_NBAD, QB_STAT_NESS, QB_STAT_NORM, QB_STAT_SKIPPED, QB_STAT_SUMSQ, QbExpparams
 from .distributions import covariance_from_moments
 from .engine import DeviceCloud
 from .models import describe_model
@@ -32,7 +32,7 @@ _EPS = np.spacing(1)
 class SMCUpdater(object):
     def __init__(self, model, n_particles, prior, resample_a=None, resampler=None, resample_thresh=0.5,
                  debug_resampling=False, track_resampling_divergence=False, zero_weight_policy='error',
-                 zero_weight_thresh=None, canonicalize=True, device=None):
+                 zero_weight_thresh=None, canonicalize=True, device=None, lazy=False):
         if track_resampling_divergence:
             raise NotImplementedError("track_resampling_divergence is outside the B200 hot path (SURVEY §2 1b)")
         self._desc = describe_model(model)        # raises UnsupportedModelError: no CPU fallback
@@ -64,15 +64,39 @@ class SMCUpdater(object):
         self._host_locs = None
         self._host_weights = None
         self._n_ess = float(n_particles)
+        # lazy=True: update() returns as soon as its kernel is queued; the bookkeeping of a step (records,
+        # warnings, zero-weight policy, resample trigger) runs when the next call needs it, and the next
+        # update is launched speculatively behind it (it cancels itself on the device if the step turns out
+        # to need the host).  lazy=False (default) keeps the reference's call-by-call semantics exactly.
+        self._lazy = bool(lazy)
+        self._pending = None
+        self._eps = [QbExpparams(), QbExpparams()]
+        self._ep_idx = 0
         self.reset(n_particles)
 
     # ---- bookkeeping properties (smc.py:182-259) ----------------------------------
-    resample_count = property(lambda self: self._resample_count)
-    just_resampled = property(lambda self: self._just_resampled)
-    normalization_record = property(lambda self: self._normalization_record)
-    min_n_ess = property(lambda self: self._min_n_ess)
     data_record = property(lambda self: self._data_record[:])
     resampling_divergences = property(lambda self: self._resampling_divergences)
+
+    @property
+    def resample_count(self):
+        self._flush()
+        return self._resample_count
+
+    @property
+    def just_resampled(self):
+        self._flush()
+        return self._just_resampled
+
+    @property
+    def normalization_record(self):
+        self._flush()
+        return self._normalization_record
+
+    @property
+    def min_n_ess(self):
+        self._flush()
+        return self._min_n_ess
 
     @property
     def log_total_likelihood(self):
@@ -89,16 +113,19 @@ class SMCUpdater(object):
 
     @property
     def n_ess(self):
+        self._flush()
         return self._n_ess
 
     @property
     def particle_locations(self):
+        self._flush()
         if self._host_locs is None:
             self._host_locs = self._cloud.download_locations()
         return self._host_locs
 
     @particle_locations.setter
     def particle_locations(self, value):
+        self._flush()
         value = np.asarray(value, dtype=np.float64)
         if value.shape[0] != self._cloud.n:
             self._rebuild_cloud(value.shape[0])
@@ -107,12 +134,14 @@ class SMCUpdater(object):
 
     @property
     def particle_weights(self):
+        self._flush()
         if self._host_weights is None:
             self._host_weights = self._cloud.download_weights()
         return self._host_weights
 
     @particle_weights.setter
     def particle_weights(self, value):
+        self._flush()
         value = np.asarray(value, dtype=np.float64)
         self._cloud.upload_weights(value)
         st = self._cloud.read_stats()
@@ -136,6 +165,7 @@ class SMCUpdater(object):
     def sample(self, n=1):
         """distributions.py:320-333: weighted draw (clamped), host RNG like the reference."""
         from . import _lib
+        self._flush()
         cloud = self._cloud
         cloud._resample_scratch(cloud.n if cloud._js is None else cloud._js.numel())
         cloud.cdf(_lib.QB_SCAN_EXACT)
@@ -147,12 +177,14 @@ class SMCUpdater(object):
         return cloud.x.index_select(0, js).cpu().numpy()
 
     def est_mean(self):
+        self._flush()
         return self._cloud.moments()[1]
 
     def est_meanfn(self, fn):
         return np.einsum('i...,i...', self.particle_weights, fn(self.particle_locations))
 
     def est_covariance_mtx(self, corr=False):
+        self._flush()
         _, mean, m2 = self._cloud.moments()
         cov = covariance_from_moments(mean, m2)
         if corr:
@@ -164,6 +196,8 @@ class SMCUpdater(object):
     def reset(self, n_particles=None, only_params=None, reset_weights=True):
         if n_particles is not None and only_params is not None:
             raise ValueError("Cannot set both n_particles and only_params.")
+        if self._cloud is not None and not getattr(self, '_in_finalize', False):
+            self._flush()
         if n_particles is None:
             n_particles = self.n_particles
         if self._cloud is None or self._cloud.n != n_particles:
@@ -195,6 +229,7 @@ class SMCUpdater(object):
     def hypothetical_update(self, outcomes, expparams, return_likelihood=False, return_normalization=False):
         """smc.py:324-386 on host arrays; the likelihood tensor comes from the CUDA kernel."""
         from .engine import device_likelihood
+        self._flush()
         if not isinstance(outcomes, np.ndarray):
             outcomes = np.array([outcomes])
         weights = self.particle_weights
@@ -214,38 +249,79 @@ class SMCUpdater(object):
         return out[0] if len(out) == 1 else out
 
     def update(self, outcome, expparams, check_for_resample=True):
+        """smc.py:388-457.  One fused kernel launch; with ``lazy=False`` the call returns after the
+        step's bookkeeping exactly like the reference, with ``lazy=True`` it returns once the kernel is queued."""
         cloud = self._cloud
         self._data_record.append(outcome)
-        self._just_resampled = False
-
-        ep = self._desc.expparams_record(expparams, 0)
-        cloud.fused_update(ep, int(outcome))                 # one launch: L, w*L, sum, sum^2, min
+        self._ep_idx ^= 1
+        ep = self._desc.fill_record(self._eps[self._ep_idx], expparams, 0)
+        outcome = int(outcome)
+        prev = self._pending
+        if prev is None:
+            tag = cloud.fused_update(ep, outcome, cloud.cur)
+        else:
+            # speculative: queue this update behind the pending one.  It reads the pending step's output
+            # buffers and cancels itself on the device if that step needs the host (clip, zero-weight
+            # policy, resample) — the same test the host applies when it settles the pending step next.
+            tag = cloud.fused_update(ep, outcome, 1 - cloud.cur, guard=True, guard_resample=prev[2],
+                                     zero_weight_thresh=self._zero_weight_thresh,
+                                     resample_below=cloud.n * self.resample_thresh)
+            self._pending = None
+            plain = self._finalize(prev)                # may warn / raise / resample, like the reference
+            cloud = self._cloud
+            if not plain:                               # the speculative launch cancelled itself: redo it
+                tag = cloud.fused_update(ep, outcome, cloud.cur)
+        self._pending = (tag, outcome, bool(check_for_resample), ep)
         self._count_calls(cloud.n)
-        st = cloud.read_stats(cloud.stats_alt)               # the only host sync of an update
-        norm, sumsq = float(st[QB_STAT_NORM]), float(st[QB_STAT_SUMSQ])
+        self._just_resampled = False
+        if not self._lazy:
+            self._flush()
+
+    def _flush(self):
+        """Settle the pending update, if any (records, warnings, zero-weight policy, resample trigger)."""
+        if self._pending is not None:
+            prev, self._pending = self._pending, None
+            self._finalize(prev)
+
+    def _finalize(self, pending):
+        """The host half of smc.py:413-457 for one launched update.  Returns True if the step was a plain
+        commit (no clip, no zero-weight event, no resample) — i.e. a speculative successor ran on valid input —
+        and False otherwise (the successor, if any, cancelled itself and must be re-launched)."""
+        tag, outcome, check_for_resample, ep = pending
+        cloud = self._cloud
+        slot = 1 - cloud.cur
+        st = cloud.wait_stats(slot, tag)
+        plain = True
+        if st[QB_STAT_SKIPPED] != 0.0:
+            # a speculative launch that cancelled itself although the host expected it to run (cannot happen
+            # while host and device apply the same test; kept as a safety net): redo it plainly.  Whatever
+            # was queued behind it saw SKIPPED and cancelled itself too.
+            tag = cloud.fused_update(ep, outcome, cloud.cur)
+            st = cloud.wait_stats(slot, tag)
+            plain = False
+        norm, sumsq, ness = float(st[QB_STAT_NORM]), float(st[QB_STAT_SUMSQ]), float(st[QB_STAT_NESS])
         unnormalised = abs(norm) < _EPS                      # smc.py:369-370: then weights stay as w*L
         total = norm if unnormalised else 1.0                # np.sum of the normalised weights
+        norm_rec = norm
 
         if st[QB_STAT_NBAD] > 0:                             # smc.py:416-418
-            smallest = st[QB_STAT_MIN] if unnormalised else st[QB_STAT_MIN] / norm
+            plain = False
+            smallest = cloud.pending_min_weight(slot)
+            smallest = smallest if unnormalised else smallest / norm
             warnings.warn("Negative weights occured in particle approximation. Smallest weight observed == {}. "
                           "Clipping weights.".format(smallest), ApproximationWarning)
-            cloud.commit_update()
-            cloud.clip_weights()
-            st = cloud.read_stats()
-            cloud.commit_update()                            # back to pending until the policy has spoken
-            total = float(st[QB_STAT_NORM])
-            norm_rec = norm
-            norm, sumsq, unnormalised = total, float(st[QB_STAT_SUMSQ]), True
-        else:
-            norm_rec = norm
+            st2 = cloud.clip_weights(slot)
+            total = float(st2[QB_STAT_NORM])
+            norm, sumsq, unnormalised = total, float(st2[QB_STAT_SUMSQ]), True
+            ness = self._ness_from(norm, sumsq, normalised=True)
 
         if total <= self._zero_weight_thresh:                # smc.py:423-436 (a NaN total passes, as in the reference)
+            plain = False
             policy = self._zero_weight_policy
             if policy == 'ignore':
                 pass
             elif policy == 'skip':
-                return
+                return False
             elif policy == 'warn':
                 warnings.warn("All particle weights are zero. This will very likely fail quite badly.",
                               ApproximationWarning)
@@ -253,19 +329,27 @@ class SMCUpdater(object):
                 raise RuntimeError("All particle weights are zero.")
             elif policy == 'reset':
                 warnings.warn("All particle weights are zero. Resetting from initial prior.", ApproximationWarning)
-                self.reset()
+                self._in_finalize = True
+                try:
+                    self.reset()
+                finally:
+                    self._in_finalize = False
                 cloud = self._cloud
             else:
                 raise ValueError("Invalid zero-weight policy {} encountered.".format(policy))
+            with np.errstate(divide='ignore', invalid='ignore'):
+                ness = self._ness_from(norm, sumsq, normalised=unnormalised)
 
         cloud.commit_update()                                # smc.py:441
         self._host_weights = None
         self._normalization_record.append(norm_rec)          # smc.py:444
-        self._n_ess = self._ness_from(norm, sumsq, normalised=unnormalised)
+        self._n_ess = ness
         if self._n_ess <= self._min_n_ess:                   # smc.py:452-453
             self._min_n_ess = self._n_ess
         if check_for_resample:
-            self._maybe_resample()
+            if self._maybe_resample():
+                plain = False
+        return plain
 
     def batch_update(self, outcomes, expparams, resample_interval=5):
         n_exps = outcomes.shape[0]
@@ -280,15 +364,19 @@ class SMCUpdater(object):
 
     # ---- resampling (smc.py:263-277, 491-551) --------------------------------------------
     def _maybe_resample(self):
-        ess = self.n_ess
+        self._flush()
+        ess = self._n_ess
         if ess <= 10:
             warnings.warn("Extremely small n_ess encountered ({}). Resampling is likely to fail. Consider adding "
                           "particles, or resampling more often.".format(ess), ApproximationWarning)
         if ess < self.n_particles * self.resample_thresh:
             self.resample()
+            return True
+        return False
 
     def resample(self):
-        if self.just_resampled:
+        self._flush()
+        if self._just_resampled:
             warnings.warn("Resampling without additional data; this may not perform as desired.", ResamplerWarning)
         self._just_resampled = True
         self._resample_count += 1

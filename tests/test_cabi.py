@@ -43,6 +43,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.QbModel) == 24
     assert ctypes.sizeof(_lib.QbExpparams) == 8 + 8 + 8 + 4 + 4 + 8 + 8 * _lib.QB_MAX_D
     assert _lib.QbExpparams.meas.offset == 40
+    assert ctypes.sizeof(_lib.QbUpdateCtl) == 40
 
 
 def test_argument_validation_without_a_gpu():
@@ -51,13 +52,13 @@ def test_argument_validation_without_a_gpu():
     lib = _lib.load()
     m = _lib.QbModel(kind=99, d=1, binomial=0, interleaved=0, min_freq=0.0)
     ep = _lib.QbExpparams()
-    rc = lib.qb_fused_update(ctypes.byref(m), ctypes.byref(ep), 0, None, 10, None, None, None, None, None, 0, None)
+    rc = lib.qb_fused_update(ctypes.byref(m), ctypes.byref(ep), 0, None, 10, None, None, None, None, None, None, 0, None)
     assert rc == -2 and b"no CPU fallback" in lib.qb_last_error()
     m = _lib.QbModel(kind=_lib.QB_MODEL_RB, d=2, binomial=0, interleaved=0, min_freq=0.0)
-    rc = lib.qb_fused_update(ctypes.byref(m), ctypes.byref(ep), 0, None, 10, None, None, None, None, None, 0, None)
+    rc = lib.qb_fused_update(ctypes.byref(m), ctypes.byref(ep), 0, None, 10, None, None, None, None, None, None, 0, None)
     assert rc == -2
     m = _lib.QbModel(kind=_lib.QB_MODEL_PRECESSION, d=1, binomial=0, interleaved=0, min_freq=0.0)
-    rc = lib.qb_fused_update(ctypes.byref(m), ctypes.byref(ep), 0, None, 10, None, None, None, None, None, 0, None)
+    rc = lib.qb_fused_update(ctypes.byref(m), ctypes.byref(ep), 0, None, 10, None, None, None, None, None, None, 0, None)
     assert rc == -1 and b"NULL" in lib.qb_last_error()
     assert lib.qb_update_workspace_bytes(1000, 1) > 0
     assert lib.qb_moments_workspace_bytes(1000, 16) >= 153 * 8

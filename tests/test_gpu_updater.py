@@ -236,3 +236,59 @@ def test_reset_and_setters(qb):
             warnings.simplefilter("ignore")
             qb.SMCUpdater(qb.SimplePrecessionModel(), n, qb.UniformDistribution([0, 1]), resample_a=0.9,
                           resampler=qb.LiuWestResampler())
+
+
+def test_lazy_pipelining_is_bit_identical_to_eager(qb):
+    """lazy=True launches update k+1 speculatively behind update k (device-side guard); the trajectory,
+    records, resample count and final cloud must equal the call-by-call (reference-semantics) run exactly."""
+    n = 50000
+    rs = np.random.RandomState(8)
+    x = rs.random_sample((n, 1))
+    ts = (9.0 / 8.0) ** np.arange(70)
+    outcomes = (rs.random_sample(70) >= np.cos(ts * 0.5 / 2) ** 2).astype(int)
+    res = []
+    for lazy in (False, True):
+        np.random.seed(3)
+        up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), lazy=lazy)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for k in range(70):
+                up.update(int(outcomes[k]), ts[k:k + 1], check_for_resample=(k % 7 != 3))
+        res.append((up.resample_count, np.array(up.normalization_record), up.particle_weights.copy(),
+                    up.particle_locations.copy(), up.min_n_ess, up.n_ess))
+    a, b = res
+    assert a[0] == b[0] and a[0] >= 3
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert a[4] == b[4] and a[5] == b[5]
+
+
+@pytest.mark.parametrize("policy", ["skip", "error", "warn"])
+def test_lazy_mode_zero_weight_events(qb, policy):
+    """A zero-weight event under lazy=True: the speculative successor cancels itself, state stays coherent."""
+    n = 256
+    model, x, ep = _decimation_setup(qb, n, 1.0)
+    x[: n // 2, 1] = 0.0                                # half the particles make outcome 1 impossible
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), zero_weight_policy=policy, canonicalize=False, lazy=True,
+                       resample_thresh=0.0)
+    ep0 = np.empty((1,), dtype=model.expparams_dtype)
+    ep0['meas'][0] = [0.0, 1.0, 0.0, 0.0]
+    up.update(1, ep0, check_for_resample=False)          # kills half the particles
+    locs = up.particle_locations.copy()
+    locs[:, 1] = 0.0
+    up.particle_locations = locs                         # now outcome 1 is impossible for every survivor
+    w_before = up.particle_weights.copy()
+    up.update(1, ep0, check_for_resample=False)          # zero-weight event (pending)
+    if policy == "error":
+        with pytest.raises(RuntimeError, match="All particle weights are zero."):
+            up.update(0, ep0, check_for_resample=False)  # settles the pending step first
+        assert np.array_equal(up.particle_weights, w_before)
+    elif policy == "skip":
+        up.update(0, ep0, check_for_resample=False)      # the skipped step leaves the weights; this one applies
+        w = up.particle_weights
+        assert len(up.normalization_record) == 2 and abs(w.sum() - 1) < 1e-12
+        assert np.array_equal(w > 0, w_before > 0)
+    else:
+        with pytest.warns(qb.ApproximationWarning, match="All particle weights are zero"):
+            up.update(0, ep0, check_for_resample=False)
+            w = up.particle_weights
+        assert np.all(w == 0)
