@@ -91,7 +91,7 @@ class ClockSampler(object):
         try:
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -246,6 +246,7 @@ def gpu_arm(args, rank, world, local_rank):
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+            time.sleep(0.35)                             # let nvidia-smi take its first samples
         barrier()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()

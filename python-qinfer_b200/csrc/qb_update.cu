@@ -21,7 +21,8 @@
 
 namespace qb {
 
-constexpr int UPD_THREADS = 256;
+constexpr int UPD_CONSUMER_WARPS = 8;
+constexpr int UPD_THREADS = (UPD_CONSUMER_WARPS + 1) * 32;  // + one TMA producer warp
 constexpr int UPD_STAGES = 3;
 
 struct UpdateParams {
@@ -134,16 +135,21 @@ __device__ __forceinline__ void accumulate(Acc& a, double wv) {
 }
 
 // DT > 0: compile-time n_modelparams, pair processing.  DT == 0: runtime d.
+//
+// Warp-specialised: warps 0..UPD_CONSUMER_WARPS-1 compute, the last warp's lane 0 is the TMA producer.
+// full[s]  (count 1)  : producer's expect_tx + the bulk copies' complete_tx  -> consumers may read stage s
+// empty[s] (count NCW): one arrive per consumer warp                        -> producer may refill stage s
+// No CTA-wide barrier in the tile loop: warps drift freely across the ring.
 template <int KIND, bool BINOM, int DT>
-__global__ void __launch_bounds__(UPD_THREADS) fused_update_kernel(const __grid_constant__ UpdateParams p) {
+__global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __grid_constant__ UpdateParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TILE_CT = (DT == 1) ? 1024 : 512;  // must match choose_tile()
+    constexpr int NCT = UPD_CONSUMER_WARPS * 32;     // consumer threads
     const int d = (DT > 0) ? DT : p.d;
     const int tile = (DT > 0) ? TILE_CT : p.tile;
     const uint32_t x_bytes = static_cast<uint32_t>(tile) * d * 8u;
     const uint32_t w_bytes = static_cast<uint32_t>(tile) * 8u;
     const uint32_t stage_bytes = x_bytes + w_bytes;  // multiples of 128 by construction (tile % 16 == 0)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);  // UPD_STAGES barriers in the first 128 B
     double* meas_s = reinterpret_cast<double*>(smem_raw + 128);
     unsigned char* ring = smem_raw + 128 + QB_MAX_D * 8;
     __shared__ double red[(UPD_THREADS / 32) * 2];
@@ -156,99 +162,121 @@ __global__ void __launch_bounds__(UPD_THREADS) fused_update_kernel(const __grid_
         if (blockIdx.x == 0 && tid == 0) publish_stats(p, p.stats_in[QB_STAT_NORM], p.stats_in[QB_STAT_SUMSQ], 0.0, 1.0);
         return;
     }
-    const int64_t ntiles = (p.n + tile - 1) / tile;
-    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t bar0 = smem_u32(smem_raw);            // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
+    const uint32_t ring0 = smem_u32(ring);
+    const int ntiles = static_cast<int>((p.n + tile - 1) / tile);
+    const int my_tiles = (ntiles > static_cast<int>(blockIdx.x))
+                             ? (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                   static_cast<int>(gridDim.x)
+                             : 0;
 
     if (KIND == QB_MODEL_TOMOGRAPHY) {
         for (int c = tid; c < d; c += UPD_THREADS) meas_s[c] = p.meas[c];
     }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < UPD_STAGES; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < UPD_STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);
+            mbar_init(bar0 + 64 + 8 * s, UPD_CONSUMER_WARPS);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto issue = [&](int64_t i) {  // thread 0: start the bulk loads of my i-th tile if it is a full one
-        const int64_t t = blockIdx.x + i * gridDim.x;
-        const int64_t first = t * tile;
-        if (first + tile <= p.n) {
-            const int s = static_cast<int>(i % UPD_STAGES);
-            unsigned char* dst = ring + static_cast<size_t>(s) * stage_bytes;
-            mbar_expect_tx(&bars[s], stage_bytes);
-            tma_load_1d(dst, p.x + first * d, x_bytes, &bars[s]);
-            tma_load_1d(dst + x_bytes, p.w_in + first, w_bytes, &bars[s]);
-        }
-    };
-    if (tid == 0) {
-        for (int64_t i = 0; i < my_tiles && i < UPD_STAGES; ++i) issue(i);
-    }
-
-    const double inv_norm = p.stats_in[QB_STAT_INV_NORM];
-    const ModelView mv = p.mv;
-    const ExpView ev = p.ev;
     Acc a0 = {0.0, 0.0, 0u}, a1 = {0.0, 0.0, 0u};
-    const int lane = tid & 31;
-    auto meas = [&](int c) { return meas_s[c]; };
+    const int64_t tile_stride = static_cast<int64_t>(gridDim.x) * tile;
 
-    for (int64_t i = 0; i < my_tiles; ++i) {
-        const int s = static_cast<int>(i % UPD_STAGES);
-        const uint32_t parity = static_cast<uint32_t>((i / UPD_STAGES) & 1);
-        const int64_t t = blockIdx.x + i * gridDim.x;
-        const int64_t first = t * tile;
-        const int cnt = static_cast<int>((p.n - first < tile) ? (p.n - first) : tile);
-        const double* xs = reinterpret_cast<const double*>(ring + static_cast<size_t>(s) * stage_bytes);
-        const double* ws = reinterpret_cast<const double*>(ring + static_cast<size_t>(s) * stage_bytes + x_bytes);
-        double* wo = p.w_out + first;
-        if (cnt == tile) {
-            mbar_wait(&bars[s], parity);
-            if constexpr (DT > 0) {
-                // pairs (2j, 2j+1): 128-bit shared loads, one 128-bit streaming store
-                constexpr int NPAIRS = TILE_CT >> 1;
-#pragma unroll
-                for (int j = tid; j < NPAIRS; j += UPD_THREADS) {
-                    const double2 wp = *reinterpret_cast<const double2*>(ws + 2 * j);
-                    double xr[2 * DT];
-#pragma unroll
-                    for (int v = 0; v < DT; ++v) {
-                        const double2 t2 = *reinterpret_cast<const double2*>(xs + 2 * DT * j + 2 * v);
-                        xr[2 * v] = t2.x;
-                        xr[2 * v + 1] = t2.y;
-                    }
-                    auto row0 = [&](int c) { return xr[c]; };
-                    auto row1 = [&](int c) { return xr[DT + c]; };
-                    const double L0 = model_likelihood<KIND, BINOM>(mv, ev, row0, meas, 0);
-                    const double L1 = model_likelihood<KIND, BINOM>(mv, ev, row1, meas, 0);
-                    const double w0 = (wp.x * inv_norm) * L0;  // smc.py:354 on the lazily normalised weight
-                    const double w1 = (wp.y * inv_norm) * L1;
-                    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(wo + 2 * j), "d"(w0),
-                                 "d"(w1)
-                                 : "memory");
-                    accumulate(a0, w0);
-                    accumulate(a1, w1);
+    if (tid >= NCT) {
+        // ===== producer warp: one lane streams my tiles into the ring =====
+        if (tid == NCT) {
+            int s = 0;
+            uint32_t phase = 0;
+            int64_t first = static_cast<int64_t>(blockIdx.x) * tile;
+            for (int i = 0; i < my_tiles; ++i, first += tile_stride) {
+                if (first + tile <= p.n) {  // full tile (the ragged last one is read directly by the consumers)
+                    mbar_wait(bar0 + 64 + 8 * s, phase ^ 1u);  // passes at once the first time round the ring
+                    const uint32_t dst = ring0 + static_cast<uint32_t>(s) * stage_bytes;
+                    mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+                    tma_load_1d(dst, p.x + first * d, x_bytes, bar0 + 8 * s);
+                    tma_load_1d(dst + x_bytes, p.w_in + first, w_bytes, bar0 + 8 * s);
                 }
-            } else {
-                for (int j = tid; j < cnt; j += UPD_THREADS) {
-                    const double* xr = xs + static_cast<size_t>(j) * d;
+                if (++s == UPD_STAGES) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== consumer warps =====
+        const double inv_norm = p.stats_in[QB_STAT_INV_NORM];
+        const ModelView mv = p.mv;
+        const ExpView ev = p.ev;
+        const int lane = tid & 31;
+        auto meas = [&](int c) { return meas_s[c]; };
+        int s = 0;
+        uint32_t phase = 0;
+        int64_t first = static_cast<int64_t>(blockIdx.x) * tile;
+        for (int i = 0; i < my_tiles; ++i, first += tile_stride) {
+            double* wo = p.w_out + first;
+            if (first + tile <= p.n) {
+                const unsigned char* stage = ring + static_cast<size_t>(s) * stage_bytes;
+                const double* xs = reinterpret_cast<const double*>(stage);
+                const double* ws = reinterpret_cast<const double*>(stage + x_bytes);
+                mbar_wait(bar0 + 8 * s, phase);
+                if constexpr (DT > 0) {
+                    // pairs (2j, 2j+1): 128-bit shared loads, one 128-bit streaming store
+                    constexpr int NPAIRS = TILE_CT >> 1;
+#pragma unroll
+                    for (int j0 = 0; j0 < NPAIRS; j0 += NCT) {
+                        const int j = j0 + tid;
+                        const double2 wp = *reinterpret_cast<const double2*>(ws + 2 * j);
+                        double xr[2 * DT];
+#pragma unroll
+                        for (int v = 0; v < DT; ++v) {
+                            const double2 t2 = *reinterpret_cast<const double2*>(xs + 2 * DT * j + 2 * v);
+                            xr[2 * v] = t2.x;
+                            xr[2 * v + 1] = t2.y;
+                        }
+                        auto row0 = [&](int c) { return xr[c]; };
+                        auto row1 = [&](int c) { return xr[DT + c]; };
+                        const double L0 = model_likelihood<KIND, BINOM>(mv, ev, row0, meas, 0);
+                        const double L1 = model_likelihood<KIND, BINOM>(mv, ev, row1, meas, 0);
+                        const double w0 = (wp.x * inv_norm) * L0;  // smc.py:354 on the lazily normalised weight
+                        const double w1 = (wp.y * inv_norm) * L1;
+                        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(wo + 2 * j), "d"(w0),
+                                     "d"(w1)
+                                     : "memory");
+                        accumulate(a0, w0);
+                        accumulate(a1, w1);
+                    }
+                } else {
+                    for (int j = tid; j < tile; j += NCT) {
+                        const double* xr = xs + static_cast<size_t>(j) * d;
+                        auto row = [&](int c) { return xr[c]; };
+                        const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, lane);
+                        const double wv = (ws[j] * inv_norm) * L;
+                        stg_stream(wo + j, wv);
+                        accumulate(a0, wv);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 64 + 8 * s);  // this warp is done with stage s
+            } else {  // ragged last tile: straight from global memory
+                const int cnt = static_cast<int>(p.n - first);
+                for (int j = tid; j < cnt; j += NCT) {
+                    const double* xr = p.x + (first + j) * d;
                     auto row = [&](int c) { return xr[c]; };
-                    const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, lane);
-                    const double wv = (ws[j] * inv_norm) * L;
-                    stg_stream(wo + j, wv);
+                    const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, 0);
+                    const double wv = (p.w_in[first + j] * inv_norm) * L;
+                    wo[j] = wv;
                     accumulate(a0, wv);
                 }
             }
-        } else {  // ragged last tile: straight from global memory
-            for (int j = tid; j < cnt; j += UPD_THREADS) {
-                const double* xr = p.x + (first + j) * d;
-                auto row = [&](int c) { return xr[c]; };
-                const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, 0);
-                const double wv = (p.w_in[first + j] * inv_norm) * L;
-                wo[j] = wv;
-                accumulate(a0, wv);
+            if (++s == UPD_STAGES) {
+                s = 0;
+                phase ^= 1u;
             }
         }
-        __syncthreads();  // every thread is done with stage s
-        if (tid == 0 && i + UPD_STAGES < my_tiles) issue(i + UPD_STAGES);
     }
 
     double acc_s = a0.s + a1.s, acc_q = a0.q + a1.q;

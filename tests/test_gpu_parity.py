@@ -163,7 +163,10 @@ def test_t2_fused_update_all_models_trajectory(qb, oracle, golden):
         for outcome, ep in steps:
             gb.update(outcome, ep, check_for_resample=False)
             ob.update(outcome, ep, check_for_resample=False)
-            np.testing.assert_allclose(gb.particle_weights, ob.particle_weights, rtol=2e-11, atol=1e-300)
+            # absolute floor: under BinomialModel, k*log(pr1) turns the last-ulp difference between CUDA's and
+            # glibc's cos into ~1e-16 * k / pr1 relative, which only shows on particles of negligible weight
+            ow = ob.particle_weights
+            np.testing.assert_allclose(gb.particle_weights, ow, rtol=2e-11, atol=1e-15 * ow.max())
             np.testing.assert_allclose(gb.normalization_record[-1], np.ravel(ob.normalization_record[-1])[0],
                                        rtol=1e-11)
             np.testing.assert_allclose(gb.n_ess, ob.n_ess, rtol=1e-10)

@@ -213,7 +213,12 @@ def test_hypothetical_update_shapes_and_values(qb):
     w, L, norm = up.hypothetical_update(np.array([0, 1]), ts, return_likelihood=True, return_normalization=True)
     w0, L0, norm0 = ou.hypothetical_update(np.array([0, 1]), ts, return_likelihood=True, return_normalization=True)
     assert w.shape == (2, 3, n) and L.shape == (2, 3, n) and norm.shape == (2, 3, 1)
-    np.testing.assert_allclose(w, w0, rtol=1e-12)
+    # The reference forms L(1) = 1 - fl(cos^2) (abstract_model.py:679): one ulp of pr0 ~ 1 is an ABSOLUTE error
+    # of ~2e-16 in L, i.e. up to 1e-10 relative when L ~ 1e-6 (the kernel's sin^2 is the accurate one — checked
+    # against long double).  So: likelihoods to 4e-16 absolute, weights to that floor scaled by prior / norm.
+    np.testing.assert_allclose(L, L0, rtol=1e-12, atol=4e-16)
+    floor = 4e-16 * (1.0 / n) / norm0
+    assert np.all(np.abs(w - w0) <= 1e-12 * np.abs(w0) + floor)
     np.testing.assert_allclose(norm, norm0, rtol=1e-12)
 
 

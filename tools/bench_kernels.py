@@ -1,0 +1,109 @@
+"""Scratch micro-benchmarks of individual kernels (not part of the judged bench):
+    python tools/bench_kernels.py update [n] | resample [n] | all
+Times back-to-back launches with CUDA events and prints achieved algorithmic GB/s."""
+import os
+import sys
+import ctypes
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "python-qinfer_b200"))
+import qinfer_b200 as qb
+from qinfer_b200 import _lib
+from qinfer_b200.engine import DeviceCloud, _ptr, _stream
+
+
+def timed(fn, reps=50, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3   # us
+
+
+def bench_update(n, model, ep_setup, d, label):
+    desc = qb.describe_model(model)
+    cloud = DeviceCloud(desc, n)
+    rs = np.random.RandomState(0)
+    if d == 1:
+        x = rs.random_sample((n, 1))
+    elif d == 3:
+        x = np.column_stack([0.9 + 0.1 * rs.random_sample(n), 0.5 * rs.random_sample(n), 0.5 * rs.random_sample(n)])
+    else:
+        x = rs.random_sample((n, d)) / d
+    cloud.upload_locations(x)
+    cloud.set_uniform_weights()
+    ep = _lib.QbExpparams()
+    outcome = ep_setup(ep)
+    state = {"src": 0}
+
+    def step():
+        cloud.fused_update(ep, outcome, state["src"])
+        state["src"] ^= 1
+    us = timed(step, reps=100)
+    gb = 8.0 * (d + 2) * n / (us * 1e-6) / 1e9
+    print("%-28s n=%d  %8.1f us/launch  %7.1f GB/s algorithmic  (%.1f%% of 6540)" % (label, n, us, gb, gb / 65.40))
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10 ** 7
+    if what in ("update", "all"):
+        def prec(ep):
+            ep.t = 17.3
+            return 1
+        bench_update(n, qb.SimplePrecessionModel(), prec, 1, "update precession d=1")
+
+        def rbb(ep):
+            ep.m = 37
+            ep.n_meas = 25
+            return 12
+        bench_update(n // 4, qb.BinomialModel(qb.RandomizedBenchmarkingModel()), rbb, 3, "update binomial(RB) d=3")
+
+        def rb(ep):
+            ep.m = 37
+            return 1
+        bench_update(n // 4, qb.RandomizedBenchmarkingModel(), rb, 3, "update RB d=3")
+
+        def tomo(ep):
+            for c in range(16):
+                ep.meas[c] = 0.1 * (c % 3)
+            ep.meas[0] = 1.0
+            return 1
+        bench_update(n // 8, qb.TomographyModel(qb.pauli_basis(2)), tomo, 16, "update tomography d=16")
+    if what in ("resample", "all"):
+        for d, model in ((1, qb.SimplePrecessionModel()), (3, qb.RandomizedBenchmarkingModel()),
+                         (16, qb.TomographyModel(qb.pauli_basis(2)))):
+            nn = n if d == 1 else n // 8
+            desc = qb.describe_model(model)
+            cloud = DeviceCloud(desc, nn)
+            rs = np.random.RandomState(0)
+            x = rs.random_sample((nn, d)) * 0.2 + 0.4
+            cloud.upload_locations(x)
+            w = rs.random_sample(nn) ** 4
+            cloud.upload_weights(w / w.sum())
+            cloud.preallocate_resample()
+            print("--- resample kernels d=%d n=%d" % (d, nn))
+            print("  moments      %8.1f us" % timed(lambda: cloud.lib.qb_moments(_ptr(cloud.x), _ptr(cloud.w), _ptr(cloud.stats), nn, d, _ptr(cloud.moments_out), _ptr(cloud.ws), cloud.ws_bytes, _stream()), 20))
+            print("  cdf fast     %8.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_FAST), 20))
+            if nn <= 2 * 10 ** 6:
+                print("  cdf exact    %8.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_EXACT), 3, 1))
+            cloud.rng_uniform(cloud._u, nn, 1, 0)
+            print("  rng uniform  %8.1f us" % timed(lambda: cloud.rng_uniform(cloud._u, nn, 1, 0), 20))
+            print("  rng normal   %8.1f us" % timed(lambda: cloud.rng_normal(cloud._eps, nn * d, 1, 0), 20))
+            print("  draw         %8.1f us" % timed(lambda: cloud.draw(cloud._u, nn), 20))
+            mean = np.full(d, 0.5)
+            S = np.eye(d) * 0.01
+            print("  lw_move      %8.1f us" % timed(lambda: cloud.lw_move(mean, S, 0.98, cloud._eps, nn, True), 20))
+            if d == 16:
+                print("  canonicalize %8.1f us" % timed(lambda: cloud.canonicalize(), 10))
+
+
+if __name__ == "__main__":
+    main()
