@@ -264,6 +264,8 @@ def gpu_arm(args, rank, world, local_rank):
         posterior_mean = float(up.est_mean()[0])
 
         # ---------------- e2e: from host arrays, through the public API ----------------
+        if world > 1:
+            up.close()
         del up
         torch.cuda.empty_cache()
         host_prior = prior                               # pageable NumPy array, as a user holds it
@@ -315,6 +317,10 @@ def gpu_arm(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu_baseline(n)
         print(json.dumps(line))
     if dist is not None:
+        try:
+            up.close()
+        except Exception:
+            pass
         dist.destroy_process_group()
 
 

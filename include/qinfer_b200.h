@@ -46,6 +46,7 @@ extern "C" {
 #define QB_ERR_WORKSPACE (-4)
 
 #define QB_MAX_D 64 /* max n_modelparams handled by the staged kernels (3-qubit tomography) */
+#define QB_MAX_RANKS 16 /* GPUs of one NVLink domain that may share a particle cloud */
 
 /* ---- model plugin descriptor ------------------------------------------- */
 /* Which built-in likelihood the kernels evaluate. */
@@ -96,6 +97,8 @@ int qb_device_sm_count(void);
 /* w[i] = 1/n, stats = {norm 1, sumsq 1/n, min 1/n, nbad 0, inv 1, ness n}.
  * smc.py:307 (reset) and resamplers.py:390-392 (post-resample weights). */
 int qb_weights_set_uniform(double* d_w, int64_t n, double* d_stats, void* stream);
+/* Same for one slab of a sharded cloud: n_local weights of 1/n_global, stats describe the GLOBAL cloud. */
+int qb_weights_set_uniform_global(double* d_w, int64_t n_local, int64_t n_global, double* d_stats, void* stream);
 /* out[i] = w[i] * stats[INV_NORM]  — materialises `particle_weights` for the host. */
 int qb_weights_normalized(const double* d_w, int64_t n, const double* d_stats, double* d_out, void* stream);
 /* Re-derive stats from weights the host assigned (`particle_weights = ...`):
@@ -127,6 +130,13 @@ typedef struct qb_update_ctl {
     double resample_below;     /* n_particles * resample_thresh (smc.py:275) */
     int32_t guard;             /* 1: cancel if stats_in needs host attention */
     int32_t guard_resample;    /* with guard: the predecessor was an update with check_for_resample */
+    /* Sharded cloud: with n_ranks > 1 the kernel all-reduces (sum w', sum w'^2, #bad) over
+     * the peers' mailboxes (qb_mailbox_create / qb_ipc_*) before publishing, so stats_out holds the GLOBAL
+     * normalisation and n_ess on every rank, bit-identical, with no NCCL call and no extra launch.  All
+     * ranks must issue the same sequence of launches with the same tags. */
+    int32_t n_ranks, rank;
+    double* d_peer_mailbox[QB_MAX_RANKS]; /* [r] = rank r's mailbox as mapped in THIS process */
+    int32_t* d_error_flag;     /* optional device int, set to 1 if a peer never answered */
 } qb_update_ctl;
 /* One launch: w_out[i] = (w_in[i] * stats_in[INV_NORM]) * L(outcome | x_i; ep)
  * fused with the block+warp reductions for sum, sum of squares, min and the
@@ -197,7 +207,32 @@ int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int
                 const int64_t* d_js, const int64_t* d_idxs, int64_t k,
                 const double* h_mean, const double* h_S, double a,
                 const double* d_eps, double* d_x_new,
-                uint8_t* d_invalid, int64_t* d_n_invalid, void* stream);
+                uint8_t* d_invalid, int64_t* d_n_invalid,
+                int32_t own_mean /* 0: the reference's js[r] quirk; 1: js[idxs[r]] (sharded clouds) */,
+                void* stream);
+
+/* ---- sharded cloud: peer mailboxes and the resample exchange ------------------- */
+#define QB_IPC_HANDLE_BYTES 64
+/* cudaMalloc + zero a mailbox of 2 * n_ranks * 4 doubles (the only entry points that allocate). */
+int qb_mailbox_create(int32_t n_ranks, double** d_mailbox);
+int qb_mailbox_destroy(double* d_mailbox);
+/* CUDA IPC plumbing so that a peer PROCESS can map the mailbox (handles travel over torch.distributed). */
+int qb_ipc_get_handle(const void* d_ptr, unsigned char handle[QB_IPC_HANDLE_BYTES]);
+int qb_ipc_open_handle(const unsigned char handle[QB_IPC_HANDLE_BYTES], void** d_ptr);
+int qb_ipc_close_handle(void* d_ptr);
+/* Resample routing.  bounds[r] = global CDF value at the START of shard r (bounds[n_ranks] = total), HOST
+ * array.  For each of the n uniforms: owner = the shard whose CDF range contains it.
+ *   d_counts[r]  (int64, zeroed by the call) = how many of my draws shard r owns
+ * then, given the exclusive prefix d_bucket_start of those counts (HOST int64[n_ranks]):
+ *   d_req[pos]   = u - bounds[owner]   (the owner-local CDF coordinate, bucketed by owner)
+ *   d_perm[i]    = pos                 (where draw i's row will come back) */
+int qb_shard_classify(const double* d_u, int64_t n, const double* h_bounds, int32_t n_ranks,
+                      int32_t* d_owner, int64_t* d_counts, void* stream);
+int qb_shard_bucket(const double* d_u, const int32_t* d_owner, int64_t n, const double* h_bounds,
+                    const int64_t* h_bucket_start, int32_t n_ranks, int64_t* d_cursor /* n_ranks, scratch */,
+                    double* d_req, int64_t* d_perm, void* stream);
+/* d_out[i][:] = d_x[d_js[i]][:]  — the owner's reply to a batch of resolved requests. */
+int qb_gather_rows(const double* d_x, int32_t d, const int64_t* d_js, int64_t n, double* d_out, void* stream);
 
 /* ---- tomography canonicalize ---------------------------------------------- */
 /* TomographyModel.canonicalize (tomography/models.py:149-209): per particle

@@ -34,8 +34,8 @@ int sm_count() {
 int validate_model(const qb_model* m);  // qb_update.cu
 
 // ---- weights ------------------------------------------------------------------
-__global__ void set_uniform_kernel(double* w, int64_t n, double* stats) {
-    const double v = 1.0 / static_cast<double>(n);
+__global__ void set_uniform_kernel(double* w, int64_t n, int64_t n_global, double* stats) {
+    const double v = 1.0 / static_cast<double>(n_global);
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = v;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -44,7 +44,7 @@ __global__ void set_uniform_kernel(double* w, int64_t n, double* stats) {
         stats[QB_STAT_MIN] = v;
         stats[QB_STAT_NBAD] = 0.0;
         stats[QB_STAT_INV_NORM] = 1.0;
-        stats[QB_STAT_NESS] = static_cast<double>(n);
+        stats[QB_STAT_NESS] = static_cast<double>(n_global);
         stats[QB_STAT_TAG] = 0.0;
         stats[QB_STAT_SKIPPED] = 0.0;
     }
@@ -173,8 +173,14 @@ extern "C" const char* qb_last_error(void) { return qb::g_err; }
 extern "C" int qb_device_sm_count(void) { return qb::sm_count(); }
 
 extern "C" int qb_weights_set_uniform(double* d_w, int64_t n, double* d_stats, void* stream) {
-    QB_REQUIRE(d_w && d_stats && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_weights_set_uniform: bad arguments");
-    set_uniform_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(d_w, n, d_stats);
+    return qb_weights_set_uniform_global(d_w, n, n, d_stats, stream);
+}
+
+extern "C" int qb_weights_set_uniform_global(double* d_w, int64_t n_local, int64_t n_global, double* d_stats,
+                                             void* stream) {
+    QB_REQUIRE(d_w && d_stats && n_local >= 1 && n_global >= n_local, QB_ERR_INVALID_ARGUMENT,
+               "qb_weights_set_uniform: bad arguments");
+    set_uniform_kernel<<<grid_for(n_local, 256, 8), 256, 0, as_stream(stream)>>>(d_w, n_local, n_global, d_stats);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(128) lw_retry_kernel(const __grid_constant__ L
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < k; r += stride) {
         const int64_t dst = p.idxs[r];
-        const int64_t src = p.js[r];  // prefix-of-the-original-means quirk (resamplers.py:372)
+        // pad == 0: prefix-of-the-original-means quirk (resamplers.py:372); pad == 1: the particle's own mean
+        const int64_t src = p.pad ? p.js[dst] : p.js[r];
         double xr[QB_MAX_D];
         for (int c = 0; c < d; ++c) {
             double z = 0.0;
@@ -499,7 +500,7 @@ extern "C" int qb_compact_invalid(const uint8_t* d_invalid, int64_t n, int64_t* 
 extern "C" int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d, const int64_t* d_js,
                            const int64_t* d_idxs, int64_t k, const double* h_mean, const double* h_S, double a,
                            const double* d_eps, double* d_x_new, uint8_t* d_invalid, int64_t* d_n_invalid,
-                           void* stream) {
+                           int32_t own_mean, void* stream) {
     int rc = validate_model(model);
     if (rc != QB_OK) return rc;
     QB_REQUIRE(d_x_old && d_js && d_idxs && h_mean && h_S && d_eps && d_x_new && d_invalid && d_n_invalid,
@@ -522,7 +523,7 @@ extern "C" int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t
     p.d = d;
     p.tile = 0;
     p.postselect = 1;
-    p.pad = 0;
+    p.pad = own_mean ? 1 : 0;
     p.a = a;
     p.mv = make_model_view(*model);
     QB_CUDA_CHECK(cudaMemsetAsync(d_n_invalid, 0, sizeof(int64_t), st));

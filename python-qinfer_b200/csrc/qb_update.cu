@@ -40,6 +40,9 @@ struct UpdateParams {
     double tag;
     double zero_weight_thresh, resample_below;
     int32_t guard, guard_resample;
+    int32_t n_ranks, rank;   // > 1: all-reduce the three sums over the peers' mailboxes inside this launch
+    double* peer_mbox[QB_MAX_RANKS];
+    int32_t* error_flag;     // device int set to 1 if the peer wait timed out
     ModelView mv;
     ExpView ev;
     double meas[QB_MAX_D];
@@ -109,8 +112,55 @@ __device__ __forceinline__ void publish_stats(const UpdateParams& p, double norm
     }
 }
 
+// In-kernel all-reduce of (norm, sumsq, nbad) across the ranks of one NVLink domain.  Every rank owns a
+// mailbox of 2 x n_ranks x 4 doubles mapped into all peers (CUDA IPC).  Launch `tag` uses half (tag & 1):
+// lane q stores this rank's three sums into peer q's mailbox row [half][rank] and then, after a
+// system-scope fence, the tag word; it then spins on its own mailbox row [half][q] until peer q's tag
+// arrives.  The rows are summed in rank order, so every rank obtains bit-identical global sums.
+// Two halves suffice: a rank can only be one launch ahead of the slowest peer (it needs that peer's
+// previous-launch row to finish its own previous launch).
+__device__ void peer_allreduce3(const UpdateParams& p, double& s, double& q, double& bad, double* red) {
+    const int G = p.n_ranks;
+    const int half = static_cast<int>(static_cast<long long>(p.tag) & 1LL);
+    const int lane = threadIdx.x;
+    if (lane < G) {
+        volatile double* dst = p.peer_mbox[lane] + (static_cast<size_t>(half) * G + p.rank) * 4;
+        dst[0] = s;
+        dst[1] = q;
+        dst[2] = bad;
+        __threadfence_system();
+        dst[3] = p.tag;
+        volatile double* src = p.peer_mbox[p.rank] + (static_cast<size_t>(half) * G + lane) * 4;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (src[3] != p.tag) {
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; do not hang the GPU
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        red[lane * 3 + 0] = ok ? src[0] : nan("");
+        red[lane * 3 + 1] = ok ? src[1] : nan("");
+        red[lane * 3 + 2] = ok ? src[2] : 0.0;
+        if (!ok && p.error_flag != nullptr) *p.error_flag = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0, tb = 0.0;
+        for (int r = 0; r < G; ++r) {
+            ts += red[r * 3 + 0];
+            tq += red[r * 3 + 1];
+            tb += red[r * 3 + 2];
+        }
+        s = ts;
+        q = tq;
+        bad = tb;
+    }
+}
+
 // Final deterministic reduction of per-block partials by the last block to finish.
-__device__ void finish_stats(const UpdateParams& p, int nblocks, double* red, unsigned int* redu) {
+__device__ void finish_stats(const UpdateParams& p, int nblocks, double* red, unsigned int* redu, double* redp) {
     double s = 0.0, q = 0.0, bad = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
         s += p.partials[b * 4 + 0];
@@ -120,7 +170,22 @@ __device__ void finish_stats(const UpdateParams& p, int nblocks, double* red, un
     unsigned int ubad = static_cast<unsigned int>(bad);
     __syncthreads();
     block_reduce3(s, q, ubad, red, redu);
-    if (threadIdx.x == 0) publish_stats(p, s, q, static_cast<double>(ubad), 0.0);
+    double dbad = static_cast<double>(ubad);
+    if (p.n_ranks > 1) {
+        // broadcast the block totals held by thread 0 to the lanes that talk to the peers
+        if (threadIdx.x == 0) {
+            redp[3 * QB_MAX_RANKS + 0] = s;
+            redp[3 * QB_MAX_RANKS + 1] = q;
+            redp[3 * QB_MAX_RANKS + 2] = dbad;
+        }
+        __syncthreads();
+        s = redp[3 * QB_MAX_RANKS + 0];
+        q = redp[3 * QB_MAX_RANKS + 1];
+        dbad = redp[3 * QB_MAX_RANKS + 2];
+        __syncthreads();
+        peer_allreduce3(p, s, q, dbad, redp);
+    }
+    if (threadIdx.x == 0) publish_stats(p, s, q, dbad, 0.0);
 }
 
 struct Acc {
@@ -154,6 +219,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
     unsigned char* ring = smem_raw + 128 + QB_MAX_D * 8;
     __shared__ double red[(UPD_THREADS / 32) * 2];
     __shared__ unsigned int redu[UPD_THREADS / 32];
+    __shared__ double redp[3 * QB_MAX_RANKS + 3];
     __shared__ unsigned int is_last;
 
     const int tid = threadIdx.x;
@@ -293,7 +359,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
     __syncthreads();
     if (is_last) {
         __threadfence();
-        finish_stats(p, gridDim.x, red, redu);
+        finish_stats(p, gridDim.x, red, redu, redp);
         if (tid == 0) *p.ticket = 0u;  // ready for the next launch on this stream
     }
 }
@@ -436,6 +502,16 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
     p.resample_below = ctl ? ctl->resample_below : 0.0;
     p.guard = ctl ? ctl->guard : 0;
     p.guard_resample = ctl ? ctl->guard_resample : 0;
+    p.n_ranks = ctl ? ctl->n_ranks : 0;
+    p.rank = ctl ? ctl->rank : 0;
+    p.error_flag = ctl ? ctl->d_error_flag : nullptr;
+    QB_REQUIRE(p.n_ranks <= QB_MAX_RANKS, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: at most %d ranks", QB_MAX_RANKS);
+    for (int r = 0; r < QB_MAX_RANKS; ++r) p.peer_mbox[r] = (ctl && r < p.n_ranks) ? ctl->d_peer_mailbox[r] : nullptr;
+    if (p.n_ranks > 1) {
+        QB_REQUIRE(p.rank >= 0 && p.rank < p.n_ranks, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: bad rank");
+        for (int r = 0; r < p.n_ranks; ++r)
+            QB_REQUIRE(p.peer_mbox[r] != nullptr, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: NULL peer mailbox %d", r);
+    }
     QB_REQUIRE(d_stats_in != d_stats_out || !p.guard, QB_ERR_INVALID_ARGUMENT,
                "qb_fused_update: a guarded update needs distinct stats_in / stats_out blocks");
     p.mv = make_model_view(*model);

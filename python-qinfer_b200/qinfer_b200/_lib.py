@@ -7,6 +7,8 @@ import ctypes
 import os
 
 QB_MAX_D = 64
+QB_MAX_RANKS = 16
+QB_IPC_HANDLE_BYTES = 64
 (QB_STAT_NORM, QB_STAT_SUMSQ, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_INV_NORM, QB_STAT_NESS, QB_STAT_TAG,
  QB_STAT_SKIPPED) = range(8)
 QB_STAT_COUNT = 16
@@ -29,7 +31,9 @@ class QbExpparams(ctypes.Structure):
 
 class QbUpdateCtl(ctypes.Structure):
     _fields_ = [("h_mirror", ctypes.c_void_p), ("tag", ctypes.c_double), ("zero_weight_thresh", ctypes.c_double),
-                ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("guard_resample", ctypes.c_int32)]
+                ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("guard_resample", ctypes.c_int32),
+                ("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("d_peer_mailbox", ctypes.c_void_p * QB_MAX_RANKS), ("d_error_flag", ctypes.c_void_p)]
 
 
 class QbError(RuntimeError):
@@ -49,6 +53,7 @@ SIGNATURES = {
     "qb_last_error": (ctypes.c_char_p, []),
     "qb_device_sm_count": (ctypes.c_int, []),
     "qb_weights_set_uniform": (ctypes.c_int, [_P, _I64, _P, _P]),
+    "qb_weights_set_uniform_global": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
     "qb_weights_normalized": (ctypes.c_int, [_P, _I64, _P, _P, _P]),
     "qb_weights_restat": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P]),
     "qb_weights_clip": (ctypes.c_int, [_P, _I64, _P, _P, _SZ, _P]),
@@ -69,7 +74,16 @@ SIGNATURES = {
     "qb_compact_workspace_bytes": (_SZ, [_I64]),
     "qb_compact_invalid": (ctypes.c_int, [_P, _I64, _P, _P, _P, _SZ, _P]),
     "qb_lw_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _I64, ctypes.POINTER(_F64),
-                                   ctypes.POINTER(_F64), _F64, _P, _P, _P, _P, _P]),
+                                   ctypes.POINTER(_F64), _F64, _P, _P, _P, _P, _I32, _P]),
+    "qb_mailbox_create": (ctypes.c_int, [_I32, ctypes.POINTER(_P)]),
+    "qb_mailbox_destroy": (ctypes.c_int, [_P]),
+    "qb_ipc_get_handle": (ctypes.c_int, [_P, ctypes.c_char_p]),
+    "qb_ipc_open_handle": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_P)]),
+    "qb_ipc_close_handle": (ctypes.c_int, [_P]),
+    "qb_shard_classify": (ctypes.c_int, [_P, _I64, ctypes.POINTER(_F64), _I32, _P, _P, _P]),
+    "qb_shard_bucket": (ctypes.c_int, [_P, _P, _I64, ctypes.POINTER(_F64), ctypes.POINTER(_I64), _I32, _P, _P, _P,
+                                       _P]),
+    "qb_gather_rows": (ctypes.c_int, [_P, _I32, _P, _I64, _P, _P]),
     "qb_tomo_canonicalize": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P]),
     "qb_rng_uniform": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
     "qb_rng_normal": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),

@@ -108,8 +108,9 @@ class DeviceCloud(object):
         self.launches += 1
         return out.cpu().numpy()
 
-    def set_uniform_weights(self):
-        check(self.lib.qb_weights_set_uniform(_ptr(self.w), self.n, _ptr(self.stats), _stream()))
+    def set_uniform_weights(self, n_global=None):
+        n_global = self.n if n_global is None else int(n_global)
+        check(self.lib.qb_weights_set_uniform_global(_ptr(self.w), self.n, n_global, _ptr(self.stats), _stream()))
         self.launches += 1
 
     def read_stats(self, which=None):
@@ -219,10 +220,13 @@ class DeviceCloud(object):
         self.launches += 1
         return self._js
 
-    def lw_move(self, mean, S, a, eps_dev, n_new, postselect):
+    def lw_move(self, mean, S, a, eps_dev, n_new, postselect, x_src=None, js=None):
+        """x_alt[i] = a * x_src[js[i]] + (1-a) * mean + S @ eps[:, i] (x_src defaults to the current slab)."""
         if self.x_alt is None or self.x_alt.shape[0] != n_new:
             self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
-        check(self.lib.qb_lw_move(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._js),
+        src = self.x if x_src is None else x_src
+        js = self._js if js is None else js
+        check(self.lib.qb_lw_move(self.lib_model, _ptr(src), src.shape[0], self.d, _ptr(js),
                                   _lib.f64_array(mean), _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
                                   _ptr(eps_dev), int(n_new), _ptr(self.x_alt), int(bool(postselect)),
                                   _ptr(self._invalid), _ptr(self.counter), _stream()))
@@ -238,11 +242,13 @@ class DeviceCloud(object):
                                           _ptr(self.ws), self.ws_bytes, _stream()))
         self.launches += 3
 
-    def lw_retry(self, mean, S, a, eps_dev, k):
-        check(self.lib.qb_lw_retry(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._js), _ptr(self._idxs),
-                                   int(k), _lib.f64_array(mean), _lib.f64_array(np.asarray(S).reshape(-1)),
-                                   float(a), _ptr(eps_dev), _ptr(self.x_alt), _ptr(self._invalid),
-                                   _ptr(self.counter), _stream()))
+    def lw_retry(self, mean, S, a, eps_dev, k, x_src=None, own_mean=False):
+        src = self.x if x_src is None else x_src
+        check(self.lib.qb_lw_retry(self.lib_model, _ptr(src), src.shape[0], self.d, _ptr(self._js),
+                                   _ptr(self._idxs), int(k), _lib.f64_array(mean),
+                                   _lib.f64_array(np.asarray(S).reshape(-1)), float(a), _ptr(eps_dev),
+                                   _ptr(self.x_alt), _ptr(self._invalid), _ptr(self.counter),
+                                   1 if own_mean else 0, _stream()))
         self.launches += 1
 
     def adopt_resampled(self, n_new):

@@ -1,0 +1,449 @@
+"""Sharded particle cloud: one contiguous slab of particles per GPU.
+
+The reference's only multi-process strategy splits the particle axis of
+``likelihood`` across ipyparallel engines (parallel.py:183-224).  Here the whole
+updater is sharded the same way, one process per GPU:
+
+  update    each rank runs the fused kernel on its slab; the three sums it needs globally (sum w', sum w'^2,
+            #bad) are all-reduced INSIDE that launch over the peers' NVLink-mapped mailboxes (qb_update.cu),
+            so every rank publishes bit-identical global stats with no NCCL call and no extra launch.
+  resample  all-reduce of the 1 + d + d^2 moment sums, all-gather of the G shard totals (the global CDF is the
+            shard CDFs offset by their exclusive prefix), then ONE request/response all-to-all: every draw is
+            classified to the shard that owns its CDF range, the owner bisects its local CDF and sends the
+            row back; shrink + perturb + validity run locally (NCCL through torch.distributed).
+
+``ShardComm`` is the only place that touches torch.distributed, and the routing of a resample is written against
+a small ``ops`` interface so that it runs unchanged on CPU tensors under gloo (tests/test_sharded_cpu.py).
+
+Deviations from the single-GPU path, both documented in DESIGN.md: the CDF is the re-associated (fast) scan, so
+resample indices are not bit-identical to the single-process reference; and the postselection retry re-centres a
+particle on its OWN shrunk mean instead of replicating the reference's prefix-slice quirk (resamplers.py:372),
+which would need a second exchange.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import scipy.linalg
+import torch
+
+from . import _lib
+from ._exceptions import ResamplerError, ResamplerWarning
+
+
+# ---------------------------------------------------------------------------
+# layout + communication (host logic, runs on CPU under gloo as well)
+# ---------------------------------------------------------------------------
+class ShardLayout(object):
+    """Contiguous slabs: global index = offsets[rank] + local index (parallel.py:218 uses the same split)."""
+
+    def __init__(self, n_global, world):
+        if n_global < world:
+            raise ValueError("need at least one particle per rank")
+        base, extra = divmod(int(n_global), int(world))
+        self.n_global = int(n_global)
+        self.world = int(world)
+        self.counts = [base + (1 if r < extra else 0) for r in range(world)]
+        self.offsets = [0]
+        for c in self.counts:
+            self.offsets.append(self.offsets[-1] + c)
+
+    def count(self, rank):
+        return self.counts[rank]
+
+    def owner_of_index(self, global_index):
+        return int(np.searchsorted(self.offsets, global_index, side='right') - 1)
+
+
+def cdf_bounds(shard_totals):
+    """bounds[r] = global CDF value at the start of shard r; bounds[G] = total (fixed rank order => identical
+    on every rank)."""
+    b = [0.0]
+    for t in shard_totals:
+        b.append(b[-1] + float(t))
+    return b
+
+
+class ShardComm(object):
+    """torch.distributed plumbing.  Works on CUDA tensors with NCCL and on CPU tensors with gloo."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather_scalars(self, value, device):
+        """[value of rank 0, ..., value of rank G-1] as Python floats."""
+        mine = torch.tensor([float(value)], dtype=torch.float64, device=device)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine, group=self.group)
+        return [float(o.item()) for o in out]
+
+    def exchange_counts(self, send_counts, device):
+        """all-to-all of one int64 per peer: recv[r] = how many items rank r sends me."""
+        send = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=device)
+        recv = torch.empty_like(send)
+        self.dist.all_to_all_single(recv, send, group=self.group)
+        return [int(c) for c in recv.tolist()]
+
+    def all_to_all_v(self, send, send_counts, recv_counts, width=1):
+        """Variable all-to-all of rows of ``width`` elements; ``send`` is bucketed by destination rank."""
+        recv = torch.empty((int(sum(recv_counts)) * width,), dtype=send.dtype, device=send.device)
+        self.dist.all_to_all_single(recv, send.reshape(-1),
+                                    output_split_sizes=[int(c) * width for c in recv_counts],
+                                    input_split_sizes=[int(c) * width for c in send_counts], group=self.group)
+        return recv
+
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+def route_resample(comm, ops, u, shard_total, width):
+    """The request/response exchange of one sharded multinomial draw.
+
+    ``u``: this rank's uniforms (one per particle it will own after the resample).  ``shard_total``: the sum of
+    this rank's normalised weights.  ``ops`` supplies the local arithmetic (CUDA kernels in the product, NumPy in
+    the CPU tests): classify / bucket / local_draw / gather_rows.  Returns ``(rows, perm)``: ``rows[perm[i]]`` is
+    the old particle drawn for slot ``i`` (``rows`` is (n, width) flattened).
+    """
+    device = u.device
+    bounds = cdf_bounds(comm.all_gather_scalars(shard_total, device))
+    owner, counts = ops.classify(u, bounds)                      # counts[r]: how many of my draws shard r owns
+    starts = [0]
+    for c in counts[:-1]:
+        starts.append(starts[-1] + int(c))
+    req, perm = ops.bucket(u, owner, bounds, starts)             # owner-local CDF coordinates, bucketed by owner
+    recv_counts = comm.exchange_counts(counts, device)
+    req_in = comm.all_to_all_v(req, counts, recv_counts, 1)
+    js = ops.local_draw(req_in)                                  # bisect my local CDF for everybody's requests
+    rows_out = ops.gather_rows(js)
+    rows = comm.all_to_all_v(rows_out, recv_counts, counts, width)
+    return rows, perm, bounds
+
+
+# ---------------------------------------------------------------------------
+# device ops + sharded updater
+# ---------------------------------------------------------------------------
+class _DeviceOps(object):
+    def __init__(self, cloud, world):
+        self.cloud = cloud
+        self.world = world
+        dev = cloud.device
+        self.owner = torch.empty((cloud.n,), dtype=torch.int32, device=dev)
+        self.counts = torch.zeros((world,), dtype=torch.int64, device=dev)
+        self.cursor = torch.zeros((world,), dtype=torch.int64, device=dev)
+        self.req = torch.empty((cloud.n,), dtype=torch.float64, device=dev)
+        self.perm = torch.empty((cloud.n,), dtype=torch.int64, device=dev)
+        self.overflow = torch.zeros((1,), dtype=torch.int64, device=dev)
+
+    def classify(self, u, bounds):
+        from .engine import _ptr, _stream
+        c = self.cloud
+        _lib.check(c.lib.qb_shard_classify(_ptr(u), u.numel(), _lib.f64_array(bounds), self.world, _ptr(self.owner),
+                                           _ptr(self.counts), _stream()))
+        c.launches += 1
+        return self.owner, [int(v) for v in self.counts.tolist()]
+
+    def bucket(self, u, owner, bounds, starts):
+        from .engine import _ptr, _stream
+        c = self.cloud
+        st = (ctypes.c_int64 * self.world)(*[int(s) for s in starts])
+        _lib.check(c.lib.qb_shard_bucket(_ptr(u), _ptr(owner), u.numel(), _lib.f64_array(bounds), st, self.world,
+                                         _ptr(self.cursor), _ptr(self.req), _ptr(self.perm), _stream()))
+        c.launches += 1
+        return self.req[:u.numel()], self.perm[:u.numel()]
+
+    def local_draw(self, req_in):
+        from .engine import _ptr, _stream
+        c = self.cloud
+        m = req_in.numel()
+        js = torch.empty((max(m, 1),), dtype=torch.int64, device=c.device)
+        if m:
+            _lib.check(c.lib.qb_draw(_ptr(c._cdf), c.n, _ptr(req_in), m, _ptr(js), _ptr(self.overflow), _stream()))
+            c.launches += 1
+        return js[:m]
+
+    def gather_rows(self, js):
+        from .engine import _ptr, _stream
+        c = self.cloud
+        m = js.numel()
+        out = torch.empty((max(m, 1) * c.d,), dtype=torch.float64, device=c.device)
+        if m:
+            _lib.check(c.lib.qb_gather_rows(_ptr(c.x), c.d, _ptr(js), m, _ptr(out), _stream()))
+            c.launches += 1
+        return out[:m * c.d]
+
+
+class PeerMailboxes(object):
+    """One mailbox per rank, mapped into every peer process through CUDA IPC."""
+
+    def __init__(self, comm):
+        lib = _lib.load()
+        self.lib = lib
+        self.comm = comm
+        mine = ctypes.c_void_p()
+        _lib.check(lib.qb_mailbox_create(comm.world, ctypes.byref(mine)))
+        self.mine = mine
+        handle = ctypes.create_string_buffer(_lib.QB_IPC_HANDLE_BYTES)
+        _lib.check(lib.qb_ipc_get_handle(mine, handle))
+        handles = comm.all_gather_object(bytes(handle.raw))
+        self.ptrs = []
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == comm.rank:
+                self.ptrs.append(mine.value)
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(lib.qb_ipc_open_handle(ctypes.create_string_buffer(h, _lib.QB_IPC_HANDLE_BYTES),
+                                                  ctypes.byref(p)))
+                self.ptrs.append(p.value)
+                self._opened.append(p)
+        self.error_flag = torch.zeros((1,), dtype=torch.int32, device='cuda')
+        comm.barrier()
+
+    def install(self, ctl):
+        ctl.n_ranks = self.comm.world
+        ctl.rank = self.comm.rank
+        for r, p in enumerate(self.ptrs):
+            ctl.d_peer_mailbox[r] = p
+        ctl.d_error_flag = self.error_flag.data_ptr()
+
+    def close(self):
+        try:
+            torch.cuda.synchronize()
+            self.comm.barrier()
+            for p in self._opened:
+                self.lib.qb_ipc_close_handle(p)
+            self._opened = []
+            self.comm.barrier()
+            if self.mine is not None:
+                self.lib.qb_mailbox_destroy(self.mine)
+                self.mine = None
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+
+def _make_sharded_updater_class():
+    from .smc import SMCUpdater
+    from .distributions import covariance_from_moments
+    from .resamplers import sqrtm_psd
+
+    class ShardedSMCUpdater(SMCUpdater):
+        """``SMCUpdater`` whose cloud is sharded over the ranks of the default process group.
+
+        ``n_particles`` is the GLOBAL particle count; ``prior.sample(n)`` is called with this rank's slab size
+        (seed the ranks differently).  ``particle_locations`` / ``particle_weights`` are this rank's slab (weights
+        normalised globally); ``est_mean`` / ``est_covariance_mtx`` / ``n_ess`` / records are global and identical
+        on every rank, so the control flow (resample decisions, policies) stays in lockstep without extra
+        communication.
+        """
+
+        def __init__(self, model, n_particles, prior, group=None, **kwargs):
+            self._comm = ShardComm(group)
+            self._layout = ShardLayout(n_particles, self._comm.world)
+            self._n_global = int(n_particles)
+            self._mail = None
+            self._ops = None
+            resampler = kwargs.get('resampler')
+            if resampler is not None and getattr(resampler, '_rng', 'philox') != 'philox':
+                raise ValueError("a sharded cloud needs LiuWestResampler(rng='philox'): the legacy NumPy stream "
+                                 "is a single sequential generator")
+            super(ShardedSMCUpdater, self).__init__(model, self._layout.count(self._comm.rank), prior, **kwargs)
+            if resampler is None:
+                from .resamplers import LiuWestResampler
+                self.resampler = LiuWestResampler(rng='philox', scan='fast', seed=0x5EED)
+            self._min_n_ess = self._n_global
+            self._n_ess = float(self._n_global)
+
+        # -- plumbing ----------------------------------------------------------------------
+        def _rebuild_cloud(self, n):
+            super(ShardedSMCUpdater, self)._rebuild_cloud(n)
+            if self._comm.world > 1:
+                if self._mail is None:
+                    self._mail = PeerMailboxes(self._comm)
+                self._mail.install(self._cloud._ctl)
+            self._ops = _DeviceOps(self._cloud, self._comm.world)
+
+        def close(self):
+            if self._mail is not None:
+                self._flush()
+                self._mail.close()
+                self._mail = None
+
+        @property
+        def n_particles(self):
+            return self._n_global
+
+        @property
+        def n_local(self):
+            return self._cloud.n
+
+        def reset(self, n_particles=None, only_params=None, reset_weights=True):
+            if self._cloud is not None and n_particles not in (None, self._cloud.n, self._n_global):
+                raise ValueError("changing the particle count of a sharded cloud is not supported")
+            local = self._layout.count(self._comm.rank)
+            super(ShardedSMCUpdater, self).reset(local if self._cloud is None else None, only_params, reset_weights)
+            if reset_weights:
+                self._set_global_uniform()               # w = 1 / N_global on every slab
+
+        def _set_global_uniform(self):
+            self._cloud.set_uniform_weights(self._n_global)
+            self._n_ess = float(self._n_global)
+            self._host_weights = None
+
+        def _restat_global(self):
+            """After the host assigned slab weights: make the stats block describe the GLOBAL weight vector."""
+            cloud = self._cloud
+            st = cloud.read_stats().copy()
+            sums = torch.tensor([st[_lib.QB_STAT_NORM], st[_lib.QB_STAT_SUMSQ]], dtype=torch.float64,
+                                device=cloud.device)
+            self._comm.all_reduce_sum(sums)
+            norm, sumsq = [float(v) for v in sums.tolist()]
+            host = np.zeros((_lib.QB_STAT_COUNT,))
+            host[_lib.QB_STAT_NORM], host[_lib.QB_STAT_SUMSQ] = norm, sumsq
+            host[_lib.QB_STAT_INV_NORM] = 1.0
+            host[_lib.QB_STAT_NESS] = 1.0 / sumsq
+            cloud.stats.copy_(torch.from_numpy(host))
+            self._n_ess = 1.0 / sumsq
+
+        @property
+        def particle_weights(self):
+            return SMCUpdater.particle_weights.fget(self)
+
+        @particle_weights.setter
+        def particle_weights(self, value):
+            SMCUpdater.particle_weights.fset(self, value)
+            self._restat_global()
+
+        # -- global reductions ---------------------------------------------------------------
+        def _global_moments(self):
+            cloud = self._cloud
+            _lib.check(cloud.lib.qb_moments(ctypes.c_void_p(cloud.x.data_ptr()), ctypes.c_void_p(cloud.w.data_ptr()),
+                                            ctypes.c_void_p(cloud.stats.data_ptr()), cloud.n, cloud.d,
+                                            ctypes.c_void_p(cloud.moments_out.data_ptr()),
+                                            ctypes.c_void_p(cloud.ws.data_ptr()), cloud.ws_bytes,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            cloud.launches += 2
+            self._comm.all_reduce_sum(cloud.moments_out)
+            out = cloud.moments_out.cpu().numpy()
+            d = cloud.d
+            return out[0], out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
+
+        def est_mean(self):
+            self._flush()
+            return self._global_moments()[1]
+
+        def est_covariance_mtx(self, corr=False):
+            self._flush()
+            _, mean, m2 = self._global_moments()
+            cov = covariance_from_moments(mean, m2)
+            if corr:
+                dstd = np.sqrt(np.diag(cov))
+                cov /= np.outer(dstd, dstd)
+            return cov
+
+        def sample(self, n=1):
+            raise NotImplementedError("sample() on a sharded cloud is outside the hot path")
+
+        def hypothetical_update(self, *a, **k):
+            raise NotImplementedError("hypothetical_update() on a sharded cloud is outside the hot path")
+
+        # -- resampling -------------------------------------------------------------------------
+        def resample(self):
+            self._flush()
+            if self._just_resampled:
+                warnings.warn("Resampling without additional data; this may not perform as desired.",
+                              ResamplerWarning)
+            self._just_resampled = True
+            self._resample_count += 1
+            res = self.resampler
+            cloud = self._cloud
+            comm = self._comm
+            n_local, d = cloud.n, cloud.d
+
+            _, mean, m2 = self._global_moments()
+            cov = covariance_from_moments(mean, m2)
+            a, h = res._a, res._h
+            if scipy.linalg.norm(cov, 'fro') == 0:
+                warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
+                              "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
+                cov = res._zero_cov_comp * np.eye(cov.shape[0])
+            S, S_err = sqrtm_psd(cov)
+            if not np.isfinite(S_err):
+                raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
+                                     "Check that n_ess is not too small.")
+            S = np.real(h * S)
+
+            cloud._resample_scratch(n_local)
+            cdf = cloud.cdf(_lib.QB_SCAN_FAST)                       # local scan of globally normalised weights
+            shard_total = float(cdf[-1].item())
+            # counter-based streams indexed by GLOBAL slot: rank r uses the sub-stream of its slab
+            goff = self._layout.offsets[comm.rank]
+            base = res._philox_offset
+            cloud.rng_uniform(cloud._u, n_local, res._seed, base + (goff + 1) // 2)
+            rows, perm, _ = route_resample(comm, self._ops, cloud._u[:n_local], shard_total, d)
+            res._philox_offset = base + (self._n_global + 1) // 2 + 1
+
+            rows2d = rows.reshape(-1, d)
+            n_iters, local_invalid, first = 0, n_local, True
+            while True:
+                n_iters += 1
+                k = n_local if first else local_invalid
+                if k > 0:
+                    eps = cloud._eps[:d * k]
+                    cloud.rng_normal(eps, d * k, res._seed ^ 0x9E3779B97F4A7C15,
+                                     res._philox_offset + (goff * d + 1) // 2)
+                    if first:
+                        cloud.lw_move(mean, S, a, eps, n_local, res._postselect, x_src=rows2d, js=perm)
+                        cloud._js.copy_(perm)                         # the retry kernel indexes the same rows
+                    else:
+                        cloud.compact_invalid(n_local)
+                        cloud.lw_retry(mean, S, a, eps, k, x_src=rows2d, own_mean=True)
+                    local_invalid, _ = cloud.read_counter()
+                first = False
+                res._philox_offset += (self._n_global * d + 1) // 2 + 1   # every rank advances in lockstep
+                tot = torch.tensor([float(local_invalid)], dtype=torch.float64, device=cloud.device)
+                comm.all_reduce_sum(tot)
+                if tot.item() == 0:
+                    break
+                if n_iters >= res._maxiter:
+                    warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                                   "iterations.").format(int(tot.item()), res._maxiter), ResamplerWarning)
+                    break
+            res.last_n_iters = n_iters
+
+            cloud.x, cloud.x_alt = cloud.x_alt, cloud.x
+            cloud.cur = cloud.cur                                     # weights buffer stays, contents reset:
+            self._set_global_uniform()
+            self._host_locs = self._host_weights = None
+            if self._canonicalize:
+                cloud.canonicalize()
+            try:
+                self.model.clear_cache()
+            except Exception as e:  # pragma: no cover
+                warnings.warn("Exception raised when clearing model cache: {}. Ignoring.".format(e))
+
+    return ShardedSMCUpdater
+
+
+_cls = None
+
+
+def __getattr__(name):
+    global _cls
+    if name == 'ShardedSMCUpdater':
+        if _cls is None:
+            _cls = _make_sharded_updater_class()
+        return _cls
+    raise AttributeError(name)

@@ -199,7 +199,7 @@ class SMCUpdater(object):
         if self._cloud is not None and not getattr(self, '_in_finalize', False):
             self._flush()
         if n_particles is None:
-            n_particles = self.n_particles
+            n_particles = self._cloud.n
         if self._cloud is None or self._cloud.n != n_particles:
             self._rebuild_cloud(n_particles)
         cloud = self._cloud
@@ -265,7 +265,7 @@ class SMCUpdater(object):
             # policy, resample) — the same test the host applies when it settles the pending step next.
             tag = cloud.fused_update(ep, outcome, 1 - cloud.cur, guard=True, guard_resample=prev[2],
                                      zero_weight_thresh=self._zero_weight_thresh,
-                                     resample_below=cloud.n * self.resample_thresh)
+                                     resample_below=self.n_particles * self.resample_thresh)
             self._pending = None
             plain = self._finalize(prev)                # may warn / raise / resample, like the reference
             cloud = self._cloud

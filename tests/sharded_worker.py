@@ -1,0 +1,117 @@
+"""Worker for tests/test_gpu_sharded.py: run under torchrun with 2+ GPUs (NCCL)."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "python-qinfer_b200"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+import qinfer_b200 as qb                                   # noqa: E402
+from qinfer_b200.sharded import ShardedSMCUpdater, ShardLayout   # noqa: E402
+
+
+class Fixed(object):
+    def __init__(self, s):
+        self._s = s
+        self.n_rvs = s.shape[1]
+
+    def sample(self, n=1):
+        assert n == self._s.shape[0]
+        return self._s.copy()
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl")
+    n_global = 200003
+    layout = ShardLayout(n_global, world)
+    lo, hi = layout.offsets[rank], layout.offsets[rank + 1]
+    rs = np.random.RandomState(5)
+    x = rs.random_sample((n_global, 1))
+    ts = (9.0 / 8.0) ** np.arange(40)
+    outcomes = (rs.random_sample(40) >= np.cos(ts * 0.5 / 2) ** 2).astype(int)
+    fails = []
+
+    def check(cond, msg):
+        if not cond:
+            fails.append(msg)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for lazy in (False, True):
+            res = qb.LiuWestResampler(rng='philox', scan='fast', seed=11)
+            up = ShardedSMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x[lo:hi]), resampler=res, lazy=lazy,
+                                   resample_thresh=0.0)
+            ref = None
+            if rank == 0:      # single-GPU engine on the whole cloud as the comparison
+                ref = qb.SMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x), resample_thresh=0.0)
+            # (a) updates: global stats and slab weights equal the single-GPU run
+            for k in range(6):
+                up.update(int(outcomes[k]), ts[k:k + 1])
+                if ref is not None:
+                    ref.update(int(outcomes[k]), ts[k:k + 1])
+            check(up.n_particles == n_global and up.n_local == hi - lo, "counts")
+            if ref is not None:
+                check(abs(up.n_ess - ref.n_ess) <= 1e-11 * ref.n_ess, "n_ess %r vs %r" % (up.n_ess, ref.n_ess))
+                check(np.allclose(up.normalization_record, ref.normalization_record, rtol=1e-12, atol=0),
+                      "normalization record")
+                check(np.allclose(up.particle_weights, ref.particle_weights[lo:hi], rtol=1e-11,
+                                  atol=1e-15 * ref.particle_weights.max()), "slab weights")
+                check(np.allclose(up.est_mean(), ref.est_mean(), rtol=1e-11), "mean")
+                check(np.allclose(up.est_covariance_mtx(), ref.est_covariance_mtx(), rtol=1e-8), "cov")
+            else:
+                up.particle_weights
+                up.est_mean()
+                up.est_covariance_mtx()
+            # all ranks hold identical global numbers
+            t = torch.tensor([up.n_ess, up.normalization_record[-1]], dtype=torch.float64, device='cuda')
+            g = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            check(all(torch.equal(g[0], q) for q in g), "ranks disagree on global stats")
+            # (b) a forced resample preserves the first two moments and leaves uniform global weights
+            m0, c0 = up.est_mean(), up.est_covariance_mtx()
+            ess0 = up.n_ess
+            up.resample()
+            m1, c1 = up.est_mean(), up.est_covariance_mtx()
+            check(abs(up.n_ess - n_global) < 1e-6 * n_global, "n_ess after resample %r" % up.n_ess)
+            check(abs(m1[0] - m0[0]) < 8 * np.sqrt(c0[0, 0] / ess0), "mean moved %r -> %r" % (m0, m1))
+            check(abs(c1[0, 0] / c0[0, 0] - 1) < 0.1, "cov moved %r -> %r" % (c0, c1))
+            w = up.particle_weights
+            check(np.all(w == 1.0 / n_global), "weights not uniform")
+            locs = up.particle_locations
+            check(locs.shape == (hi - lo, 1) and np.all(locs > 0), "invalid locations")
+            up.close()
+        # (c) a free-running sharded trajectory lands on the same posterior as the oracle (statistically)
+        import smc_oracle as oracle
+        res = qb.LiuWestResampler(rng='philox', scan='fast', seed=3)
+        up = ShardedSMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x[lo:hi]), resampler=res, lazy=True)
+        for k in range(40):
+            up.update(int(outcomes[k]), ts[k:k + 1])
+        mean, cov, nres = up.est_mean(), up.est_covariance_mtx(), up.resample_count
+        up.close()
+        if rank == 0:
+            np.random.seed(0)
+            ou = oracle.SMCUpdater(oracle.SimplePrecessionModel(), 20000, Fixed(x[:20000]))
+            for k in range(40):
+                ou.update(int(outcomes[k]), np.array([ts[k]]))
+            om, oc = ou.est_mean(), ou.est_covariance_mtx()
+            check(nres >= 3, "too few resamples %d" % nres)
+            check(abs(mean[0] - om[0]) < 6 * np.sqrt(oc[0, 0]), "posterior mean %r vs oracle %r" % (mean, om))
+            check(0.3 < cov[0, 0] / oc[0, 0] < 3.0, "posterior cov %r vs oracle %r" % (cov, oc))
+    flag = torch.tensor([len(fails)], dtype=torch.int64, device='cuda')
+    dist.all_reduce(flag)
+    for f in fails:
+        print("[rank %d] FAIL: %s" % (rank, f), flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+"""N > 1 host logic on CPU: world_size-2 (and 3) gloo process groups exercise the shard layout, the collectives
+wrapper and the request/response routing of a sharded resample, with NumPy standing in for the device kernels
+(the same ``route_resample`` code path the CUDA engine runs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from qinfer_b200.sharded import ShardComm, ShardLayout, cdf_bounds, route_resample
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class NumpyOps(object):
+    """CPU stand-in for the device kernels (qb_shard_classify / qb_shard_bucket / qb_draw / qb_gather_rows)."""
+
+    def __init__(self, x_local, w_local):
+        self.x = x_local
+        self.cdf = np.cumsum(w_local)
+
+    def classify(self, u, bounds):
+        un = u.numpy()
+        owner = np.searchsorted(np.asarray(bounds[1:-1]), un, side='right').astype(np.int32)
+        counts = np.bincount(owner, minlength=len(bounds) - 1)
+        return torch.from_numpy(owner), [int(c) for c in counts]
+
+    def bucket(self, u, owner, bounds, starts):
+        un, on = u.numpy(), owner.numpy()
+        order = np.argsort(on, kind='stable')
+        perm = np.empty_like(order)
+        perm[order] = np.arange(order.size)
+        req = (un - np.asarray(bounds)[on])[order]
+        return torch.from_numpy(req), torch.from_numpy(perm.astype(np.int64))
+
+    def local_draw(self, req_in):
+        js = np.minimum(self.cdf.searchsorted(req_in.numpy(), side='right'), self.cdf.size - 1)
+        return torch.from_numpy(js.astype(np.int64))
+
+    def gather_rows(self, js):
+        return torch.from_numpy(np.ascontiguousarray(self.x[js.numpy()]).reshape(-1))
+
+
+def _worker(rank, world, port, n_global, d, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ShardComm()
+        layout = ShardLayout(n_global, world)
+        rs = np.random.RandomState(123)                    # every rank builds the same global problem
+        x = rs.random_sample((n_global, d))
+        w = rs.random_sample(n_global) ** 3
+        w /= w.sum()
+        u = rs.random_sample(n_global)
+        lo, hi = layout.offsets[rank], layout.offsets[rank + 1]
+        ops = NumpyOps(x[lo:hi], w[lo:hi])
+        rows, perm, bounds = route_resample(comm, ops, torch.from_numpy(u[lo:hi].copy()), float(w[lo:hi].sum()), d)
+        got = rows.numpy().reshape(-1, d)[perm.numpy()]
+        # collectives wrapper
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        comm.all_reduce_sum(t)
+        scal = comm.all_gather_scalars(rank * 2.5, torch.device("cpu"))
+        cnt = comm.exchange_counts([rank * 10 + r for r in range(world)], torch.device("cpu"))
+        objs = comm.all_gather_object(("rank", rank))
+        np.savez(os.path.join(out_dir, "r%d.npz" % rank), got=got, bounds=np.asarray(bounds), allred=t.numpy(),
+                 scal=np.asarray(scal), cnt=np.asarray(cnt), nobj=len(objs))
+        comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_global,d", [(2, 1001, 1), (2, 4096, 3), (3, 500, 16)])
+def test_route_resample_matches_single_process(tmp_path, world, n_global, d):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_global, d, str(tmp_path)), nprocs=world, join=True)
+    rs = np.random.RandomState(123)
+    x = rs.random_sample((n_global, d))
+    w = rs.random_sample(n_global) ** 3
+    w /= w.sum()
+    u = rs.random_sample(n_global)
+    layout = ShardLayout(n_global, world)
+    # single-process ground truth with the same shard-offset CDF the engine uses
+    totals = [w[layout.offsets[r]:layout.offsets[r + 1]].sum() for r in range(world)]
+    bounds = cdf_bounds(totals)
+    global_cdf = np.concatenate([bounds[r] + np.cumsum(w[layout.offsets[r]:layout.offsets[r + 1]])
+                                 for r in range(world)])
+    plain = np.cumsum(w)
+    assert np.max(np.abs(global_cdf - plain)) < 1e-13
+    for r in range(world):
+        f = np.load(os.path.join(str(tmp_path), "r%d.npz" % r))
+        lo, hi = layout.offsets[r], layout.offsets[r + 1]
+        # what the routing must return: the owner-local bisection of (u - bounds[owner])
+        owner = np.searchsorted(np.asarray(bounds[1:-1]), u[lo:hi], side='right')
+        want = np.empty((hi - lo, d))
+        for i, (ui, o) in enumerate(zip(u[lo:hi], owner)):
+            olo, ohi = layout.offsets[o], layout.offsets[o + 1]
+            j = min(np.cumsum(w[olo:ohi]).searchsorted(ui - bounds[o], side='right'), ohi - olo - 1)
+            want[i] = x[olo + j]
+        assert np.array_equal(f["got"], want)
+        # and that equals the plain global draw except where u sits within rounding of a CDF step
+        js_plain = np.minimum(plain.searchsorted(u[lo:hi], side='right'), n_global - 1)
+        assert np.mean(np.all(f["got"] == x[js_plain], axis=1)) > 0.995
+        assert np.allclose(f["bounds"], bounds)
+        assert f["allred"][0] == sum(range(1, world + 1))
+        assert list(f["scal"]) == [2.5 * q for q in range(world)]
+        assert list(f["cnt"]) == [q * 10 + r for q in range(world)]
+        assert int(f["nobj"]) == world
+
+
+def test_shard_layout():
+    L = ShardLayout(10, 3)
+    assert L.counts == [4, 3, 3] and L.offsets == [0, 4, 7, 10]
+    assert [L.owner_of_index(i) for i in (0, 3, 4, 6, 7, 9)] == [0, 0, 1, 1, 2, 2]
+    assert ShardLayout(10 ** 8, 8).counts == [12500000] * 8
+    with pytest.raises(ValueError):
+        ShardLayout(2, 3)
+    assert cdf_bounds([0.25, 0.5, 0.25]) == [0.0, 0.25, 0.75, 1.0]
