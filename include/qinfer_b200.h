@@ -92,6 +92,8 @@ int qb_abi_version(void);
 const char* qb_last_error(void);
 /* Number of SMs of the current device (grid sizing); negative on error. */
 int qb_device_sm_count(void);
+/* sizeof(qb_model), sizeof(qb_expparams), sizeof(qb_update_ctl) as compiled — lets a binding check its layouts. */
+void qb_struct_sizes(int32_t out[3]);
 
 /* ---- weights utilities -------------------------------------------------- */
 /* w[i] = 1/n, stats = {norm 1, sumsq 1/n, min 1/n, nbad 0, inv 1, ness n}.

@@ -171,6 +171,11 @@ using namespace qb;
 extern "C" int qb_abi_version(void) { return QB_ABI_VERSION; }
 extern "C" const char* qb_last_error(void) { return qb::g_err; }
 extern "C" int qb_device_sm_count(void) { return qb::sm_count(); }
+extern "C" void qb_struct_sizes(int32_t out[3]) {
+    out[0] = static_cast<int32_t>(sizeof(qb_model));
+    out[1] = static_cast<int32_t>(sizeof(qb_expparams));
+    out[2] = static_cast<int32_t>(sizeof(qb_update_ctl));
+}
 
 extern "C" int qb_weights_set_uniform(double* d_w, int64_t n, double* d_stats, void* stream) {
     return qb_weights_set_uniform_global(d_w, n, n, d_stats, stream);

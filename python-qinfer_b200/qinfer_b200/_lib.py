@@ -52,6 +52,7 @@ SIGNATURES = {
     "qb_abi_version": (ctypes.c_int, []),
     "qb_last_error": (ctypes.c_char_p, []),
     "qb_device_sm_count": (ctypes.c_int, []),
+    "qb_struct_sizes": (None, [ctypes.POINTER(ctypes.c_int32)]),
     "qb_weights_set_uniform": (ctypes.c_int, [_P, _I64, _P, _P]),
     "qb_weights_set_uniform_global": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
     "qb_weights_normalized": (ctypes.c_int, [_P, _I64, _P, _P, _P]),
@@ -112,6 +113,10 @@ def load():
         fn.argtypes = args
     if lib.qb_abi_version() != 1:
         raise QbError("libqinfer_b200.so ABI version %d, expected 1" % lib.qb_abi_version())
+    sizes = (ctypes.c_int32 * 3)()
+    lib.qb_struct_sizes(sizes)
+    if list(sizes) != [ctypes.sizeof(QbModel), ctypes.sizeof(QbExpparams), ctypes.sizeof(QbUpdateCtl)]:
+        raise QbError("struct layout mismatch between the binding and libqinfer_b200.so: %r" % list(sizes))
     _lib = lib
     return lib
 

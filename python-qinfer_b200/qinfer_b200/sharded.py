@@ -265,6 +265,17 @@ def _make_sharded_updater_class():
                 self.resampler = LiuWestResampler(rng='philox', scan='fast', seed=0x5EED)
             self._min_n_ess = self._n_global
             self._n_ess = float(self._n_global)
+            self._warm_collectives()
+
+        def _warm_collectives(self):
+            """Create the NCCL channels the resample exchange uses now, not inside the first resample."""
+            dev = self._cloud.device
+            comm = self._comm
+            comm.all_reduce_sum(torch.zeros((4,), dtype=torch.float64, device=dev))
+            comm.all_gather_scalars(0.0, dev)
+            cnt = comm.exchange_counts([1] * comm.world, dev)
+            comm.all_to_all_v(torch.zeros((comm.world,), dtype=torch.float64, device=dev), [1] * comm.world, cnt, 1)
+            torch.cuda.synchronize()
 
         # -- plumbing ----------------------------------------------------------------------
         def _rebuild_cloud(self, n):

@@ -43,7 +43,11 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.QbModel) == 24
     assert ctypes.sizeof(_lib.QbExpparams) == 8 + 8 + 8 + 4 + 4 + 8 + 8 * _lib.QB_MAX_D
     assert _lib.QbExpparams.meas.offset == 40
-    assert ctypes.sizeof(_lib.QbUpdateCtl) == 40
+    sizes = (ctypes.c_int32 * 3)()
+    _lib.load().qb_struct_sizes(sizes)                       # what the C compiler actually laid out
+    assert list(sizes) == [ctypes.sizeof(_lib.QbModel), ctypes.sizeof(_lib.QbExpparams),
+                           ctypes.sizeof(_lib.QbUpdateCtl)]
+    assert ctypes.sizeof(_lib.QbUpdateCtl) == 48 + 8 * _lib.QB_MAX_RANKS + 8
 
 
 def test_argument_validation_without_a_gpu():
