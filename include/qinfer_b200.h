@@ -122,9 +122,10 @@ size_t qb_update_workspace_bytes(int64_t n, int32_t d);
  * due (smc.py:275).  Those are rare, so the host may launch update k+1 BEFORE it has seen the result
  * of update k: with `guard` set the kernel first evaluates the same three conditions on stats_in
  * (the block update k wrote) and, if any holds, cancels itself (writes SKIPPED = 1, touches no
- * weight).  `h_mirror` is a device-accessible pinned host block (QB_STAT_COUNT doubles) that receives
- * a copy of stats_out with a system-scope release on its TAG word, so the host can poll plain memory
- * instead of issuing a copy + synchronise per update. */
+ * weight).  `h_mirror` is a device-accessible, 32-byte aligned pinned host block of 8 doubles that receives
+ *   {NORM, SUMSQ, NBAD, TAG | INV_NORM, NESS, TAG, SKIPPED}
+ * as two 32-byte stores, each carrying the tag: the host polls plain memory and accepts a snapshot when both
+ * tags equal the launch's tag — no copy + synchronise per update and no system fence in the kernel. */
 typedef struct qb_update_ctl {
     double* h_mirror;          /* may be NULL */
     double tag;
@@ -182,9 +183,12 @@ int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, i
            void* d_ws, size_t ws_bytes, void* stream);
 /* d_js[i] = min(searchsorted(cdf, u[i], side='right'), n-1) (resamplers.py:318-321;
  * the clamp is distributions.py:330-333's — the reference's resampler raises
- * IndexError where the clamp acts).  *d_overflow counts clamped draws. */
+ * IndexError where the clamp acts).  *d_overflow counts clamped draws.  With a workspace of
+ * qb_draw_workspace_bytes(n) the search goes through a power-of-two guide table built on the fly
+ * (same indices bit for bit, ~3 instead of ~8 random sectors per draw); d_ws may be NULL. */
+size_t qb_draw_workspace_bytes(int64_t n);
 int qb_draw(const double* d_cdf, int64_t n, const double* d_u, int64_t n_draw,
-            int64_t* d_js, int64_t* d_overflow, void* stream);
+            int64_t* d_js, int64_t* d_overflow, void* d_ws, size_t ws_bytes, void* stream);
 /* First Liu-West pass (resamplers.py:325-342): for i < n_new
  *   mu_i = a * x_old[js[i]] + (1-a) * mean ;  x_new[i] = mu_i + S @ eps[:, i]
  * `d_eps` is (d, n_new) row-major — the layout of `kernel(n_rvs, k)`.

@@ -157,20 +157,83 @@ __global__ void __launch_bounds__(64) cdf_sequential_kernel(const double* __rest
 // =============================================================================
 // Draw: js[i] = min(upper_bound(cdf, u[i]), n - 1)
 // =============================================================================
+// Plain right-bisection (24 dependent probes at n = 1e7, ~8 of them distinct random sectors).
+__device__ __forceinline__ int64_t upper_bound_range(const double* __restrict__ cdf, int64_t lo, int64_t hi,
+                                                     double ui) {
+    while (lo < hi) {  // first index in [lo, hi] with cdf[idx] > ui  (side='right')
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(cdf + mid) <= ui)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256) draw_kernel(const double* __restrict__ cdf, int64_t n,
                                                    const double* __restrict__ u, int64_t n_draw,
                                                    int64_t* __restrict__ js, unsigned long long* overflow) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     unsigned int over = 0;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_draw; i += stride) {
+        int64_t lo = upper_bound_range(cdf, 0, n, ldg_stream(u + i));
+        if (lo >= n) {
+            lo = n - 1;
+            ++over;
+        }
+        js[i] = lo;
+    }
+    if (over) atomicAdd(overflow, static_cast<unsigned long long>(over));
+}
+
+// Guide table (the classic indexed-search method for discrete sampling): g[b] = upper_bound(cdf, b / mult)
+// for b = 0..M.  mult = M * 2^-e is a POWER OF TWO chosen so that cdf[n-1] * 2^-e lies in [1/2, 1): both
+// u * mult and b / mult are exact in fp64, hence for b = floor(u * mult) the exact answer is bracketed,
+// g[b] <= upper_bound(cdf, u) <= g[b+1], and the bisection inside the bracket returns bit-for-bit the
+// same index as the full search.  With M ~ n/2..n the bracket holds one or two CDF entries, so a draw
+// costs ~3 random sectors (one guide pair, one or two CDF sectors) instead of ~8.
+__device__ __forceinline__ double guide_mult(const double* __restrict__ cdf, int64_t n, int64_t M) {
+    int e;
+    const double total = __ldg(cdf + n - 1);
+    (void)frexp(total, &e);  // total = f * 2^e, f in [1/2, 1)
+    return ldexp(static_cast<double>(M), -e);
+}
+
+__global__ void __launch_bounds__(256) guide_build_kernel(const double* __restrict__ cdf, int64_t n, int64_t M,
+                                                          int32_t* __restrict__ guide) {
+    const double mult = guide_mult(cdf, n, M);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; b <= M; b += stride) {
+        const double key = static_cast<double>(b) / mult;  // exact: mult is a power of two
+        guide[b] = static_cast<int32_t>(upper_bound_range(cdf, 0, n, key));
+    }
+}
+
+__global__ void __launch_bounds__(256) draw_guided_kernel(const double* __restrict__ cdf, int64_t n,
+                                                          const double* __restrict__ u, int64_t n_draw, int64_t M,
+                                                          const int32_t* __restrict__ guide,
+                                                          int64_t* __restrict__ js, unsigned long long* overflow) {
+    const double mult = guide_mult(cdf, n, M);
+    const double limit = static_cast<double>(M) / mult;  // = 2^e > cdf[n-1]
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    unsigned int over = 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_draw; i += stride) {
         const double ui = ldg_stream(u + i);
-        int64_t lo = 0, hi = n;  // first index with cdf[idx] > ui  (side='right')
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(cdf + mid) <= ui)
-                lo = mid + 1;
-            else
-                hi = mid;
+        int64_t lo;
+        if (ui >= 0.0 && ui < limit) {
+            const int64_t b = static_cast<int64_t>(ui * mult);
+            const int2 g = *reinterpret_cast<const int2*>(guide + (b & ~1LL));  // entries b&~1, (b&~1)+1
+            int64_t glo, ghi;
+            if (b & 1) {
+                glo = g.y;
+                ghi = __ldg(guide + b + 1);
+            } else {
+                glo = g.x;
+                ghi = g.y;
+            }
+            lo = upper_bound_range(cdf, glo, ghi, ui);
+        } else {
+            lo = upper_bound_range(cdf, 0, n, ui);  // out-of-range or NaN uniforms: plain search
         }
         if (lo >= n) {
             lo = n - 1;
@@ -179,6 +242,12 @@ __global__ void __launch_bounds__(256) draw_kernel(const double* __restrict__ cd
         js[i] = lo;
     }
     if (over) atomicAdd(overflow, static_cast<unsigned long long>(over));
+}
+
+static int64_t guide_size(int64_t n) {  // M: the power of two in (n/2, n]
+    int64_t m = 1;
+    while (m * 2 <= n) m *= 2;
+    return m;
 }
 
 // =============================================================================
@@ -418,14 +487,31 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
     return QB_OK;
 }
 
+extern "C" size_t qb_draw_workspace_bytes(int64_t n) {
+    if (n < 4096 || n >= (1LL << 31)) return 0;  // small clouds / int32 overflow: plain bisection
+    return static_cast<size_t>(guide_size(n) + 2) * sizeof(int32_t) + 256;
+}
+
 extern "C" int qb_draw(const double* d_cdf, int64_t n, const double* d_u, int64_t n_draw, int64_t* d_js,
-                       int64_t* d_overflow, void* stream) {
+                       int64_t* d_overflow, void* d_ws, size_t ws_bytes, void* stream) {
     QB_REQUIRE(d_cdf && d_u && d_js && d_overflow && n >= 1 && n_draw >= 1, QB_ERR_INVALID_ARGUMENT,
                "qb_draw: bad arguments");
     cudaStream_t st = as_stream(stream);
     QB_CUDA_CHECK(cudaMemsetAsync(d_overflow, 0, sizeof(int64_t), st));
-    draw_kernel<<<capped_grid((n_draw + 255) / 256, 8), 256, 0, st>>>(
-        d_cdf, n, d_u, n_draw, d_js, reinterpret_cast<unsigned long long*>(d_overflow));
+    const size_t need = qb_draw_workspace_bytes(n);
+    const int grid = capped_grid((n_draw + 255) / 256, 8);
+    // the guide pays for itself when there are at least about as many draws as table entries
+    if (d_ws != nullptr && need > 0 && ws_bytes >= need && n_draw * 4 >= n) {
+        const int64_t M = guide_size(n);
+        int32_t* guide = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(d_ws) + 256);
+        guide_build_kernel<<<capped_grid((M + 256) / 256, 8), 256, 0, st>>>(d_cdf, n, M, guide);
+        QB_CUDA_CHECK(cudaGetLastError());
+        draw_guided_kernel<<<grid, 256, 0, st>>>(d_cdf, n, d_u, n_draw, M, guide, d_js,
+                                                  reinterpret_cast<unsigned long long*>(d_overflow));
+    } else {
+        draw_kernel<<<grid, 256, 0, st>>>(d_cdf, n, d_u, n_draw, d_js,
+                                          reinterpret_cast<unsigned long long*>(d_overflow));
+    }
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

@@ -17,6 +17,7 @@
 // Generic d (tomography) walks its row with a per-lane rotated start so that
 // rows 128 B apart do not collide on shared-memory banks.
 // The ragged last tile (byte count not a multiple of 16) is loaded directly.
+#include <cstdlib>
 #include "qb_models.cuh"
 
 namespace qb {
@@ -103,12 +104,16 @@ __device__ __forceinline__ void publish_stats(const UpdateParams& p, double norm
 #pragma unroll
     for (int k = 0; k < 8; ++k) p.stats_out[k] = v[k];
     if (p.mirror != nullptr) {
-        volatile double* m = p.mirror;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k != QB_STAT_TAG) m[k] = v[k];
-        __threadfence_system();
-        m[QB_STAT_TAG] = p.tag;  // the host spins on this word
+        // Host mirror without a system-scope fence (a PCIe round trip on the kernel's critical path): the block is
+        // written as two 32-byte vector stores, each a single aligned PCIe write, and EACH half carries the tag —
+        // slots [3] and [6] — so the host accepts a snapshot only when both tags match (it re-reads otherwise).
+        // Layout of the mirror: {NORM, SUMSQ, NBAD, TAG | INV_NORM, NESS, TAG, SKIPPED}.
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror), "d"(v[QB_STAT_NORM]),
+                     "d"(v[QB_STAT_SUMSQ]), "d"(v[QB_STAT_NBAD]), "d"(p.tag)
+                     : "memory");
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 4), "d"(v[QB_STAT_INV_NORM]),
+                     "d"(v[QB_STAT_NESS]), "d"(p.tag), "d"(skipped)
+                     : "memory");
     }
 }
 
@@ -223,6 +228,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
     __shared__ unsigned int is_last;
 
     const int tid = threadIdx.x;
+    // Programmatic dependent launch: let the NEXT launch on this stream become resident while this one runs
+    // (its CTAs take the slots ours free and park in griddepcontrol.wait), and do not touch anything the
+    // PREVIOUS launch wrote (stats_in, w_in, the ticket) before that launch has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.guard && needs_host(p.stats_in, p.zero_weight_thresh, p.guard_resample, p.resample_below)) {
         // speculative launch whose predecessor needs the host: do nothing, say so
         if (blockIdx.x == 0 && tid == 0) publish_stats(p, p.stats_in[QB_STAT_NORM], p.stats_in[QB_STAT_SUMSQ], 0.0, 1.0);
@@ -525,9 +535,26 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
                cudaGetErrorString(cudaGetLastError()));
     const int64_t ntiles = (n + p.tile - 1) / p.tile;
     int grid = static_cast<int>(ntiles < limit ? ntiles : limit);
+    {
+        static int env_cap = -1;  // experiment knob: QB_UPD_CTAS_PER_SM caps the resident CTAs per SM
+        if (env_cap < 0) {
+            const char* e = getenv("QB_UPD_CTAS_PER_SM");
+            env_cap = e ? atoi(e) : 0;
+        }
+        if (env_cap > 0 && grid > env_cap * sm_count()) grid = env_cap * sm_count();
+    }
     if (grid > 32 * 256) grid = 32 * 256;
-    k<<<grid, UPD_THREADS, smem, as_stream(stream)>>>(p);
-    QB_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(UPD_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k, p));
     return QB_OK;
 }
 

@@ -55,10 +55,12 @@ class DeviceCloud(object):
             self.mirror_np = self.mirror.numpy()
             self._ctl = _lib.QbUpdateCtl()
             self._tag = 0
+            self._stats_view = np.zeros((QB_STAT_COUNT,))
             ws_bytes = max(self.lib.qb_update_workspace_bytes(self.n, self.d),
                            self.lib.qb_moments_workspace_bytes(self.n, self.d),
                            self.lib.qb_cdf_workspace_bytes(self.n),
-                           self.lib.qb_compact_workspace_bytes(self.n))
+                           self.lib.qb_compact_workspace_bytes(self.n),
+                           self.lib.qb_draw_workspace_bytes(self.n))
             self.ws = torch.zeros(((ws_bytes + 7) // 8,), **f64)       # zeroed once: holds the launch ticket
             self.ws_bytes = self.ws.numel() * 8
             self.moments_out = torch.empty((1 + self.d + self.d * self.d,), **f64)
@@ -73,8 +75,7 @@ class DeviceCloud(object):
         # resample scratch, allocated lazily
         self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = None
         self.launches = 0
-        self.time_updates = False          # bench: CUDA events around each fused-update launch
-        self.last_update_events = None
+        self.resample_events = None        # bench: set to [] to collect a CUDA-event pair around every resample
 
     # committed / pending views of the ping-pong buffers
     w = property(lambda self: self._w[self.cur])
@@ -135,31 +136,34 @@ class DeviceCloud(object):
         ctl.resample_below = resample_below
         ctl.guard = 1 if guard else 0
         ctl.guard_resample = 1 if guard_resample else 0
-        if self.time_updates:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
         check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep_record), int(outcome), _ptr(self.x), self.n,
                                        _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
                                        _ptr(self._stats[dst]), ctypes.byref(ctl), _ptr(self.ws), self.ws_bytes,
                                        _stream()))
-        if self.time_updates:
-            e1.record()
-            self.last_update_events = (e0, e1)
         self.launches += 1
         return self._tag
 
     def wait_stats(self, slot, tag, timeout_s=120.0):
-        """Spin on the pinned mirror of stats buffer ``slot`` until the launch ``tag`` has published it."""
+        """Spin on the pinned mirror of stats buffer ``slot`` until launch ``tag`` has published it.  The kernel
+        writes {NORM, SUMSQ, NBAD, TAG | INV_NORM, NESS, TAG, SKIPPED} as two 32-byte stores; a snapshot is
+        accepted when both tags match.  Returns an array indexed by the QB_STAT_* constants."""
         m = self.mirror_np
         base = slot * QB_STAT_COUNT
         want = float(tag)
-        if m[base + QB_STAT_TAG] != want:
-            t0 = time.perf_counter()
-            while m[base + QB_STAT_TAG] != want:
-                if time.perf_counter() - t0 > timeout_s:
-                    torch.cuda.synchronize()       # surfaces a CUDA error if the kernel died
-                    raise _lib.QbError("timed out waiting for the fused-update kernel (tag %d)" % tag)
-        return m[base:base + QB_STAT_COUNT]
+        t0 = None
+        while True:
+            a = m[base:base + 8].copy()
+            if a[3] == want and a[6] == want:
+                break
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > timeout_s:
+                torch.cuda.synchronize()           # surfaces a CUDA error if the kernel died
+                raise _lib.QbError("timed out waiting for the fused-update kernel (tag %d)" % tag)
+        out = self._stats_view
+        out[QB_STAT_NORM], out[QB_STAT_SUMSQ], out[QB_STAT_NBAD] = a[0], a[1], a[2]
+        out[QB_STAT_INV_NORM], out[QB_STAT_NESS], out[QB_STAT_TAG], out[QB_STAT_SKIPPED] = a[4], a[5], a[6], a[7]
+        return out
 
     def pending_min_weight(self, slot):
         """Smallest weight of weights buffer ``slot``, for the warning text of smc.py:417."""
@@ -216,8 +220,8 @@ class DeviceCloud(object):
 
     def draw(self, u_dev, n_new):
         check(self.lib.qb_draw(_ptr(self._cdf), self.n, _ptr(u_dev), int(n_new), _ptr(self._js),
-                               _ptr(self.counter[1:]), _stream()))
-        self.launches += 1
+                               _ptr(self.counter[1:]), _ptr(self.ws), self.ws_bytes, _stream()))
+        self.launches += 2
         return self._js
 
     def lw_move(self, mean, S, a, eps_dev, n_new, postselect, x_src=None, js=None):

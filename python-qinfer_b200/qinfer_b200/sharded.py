@@ -170,8 +170,9 @@ class _DeviceOps(object):
         m = req_in.numel()
         js = torch.empty((max(m, 1),), dtype=torch.int64, device=c.device)
         if m:
-            _lib.check(c.lib.qb_draw(_ptr(c._cdf), c.n, _ptr(req_in), m, _ptr(js), _ptr(self.overflow), _stream()))
-            c.launches += 1
+            _lib.check(c.lib.qb_draw(_ptr(c._cdf), c.n, _ptr(req_in), m, _ptr(js), _ptr(self.overflow), _ptr(c.ws),
+                                     c.ws_bytes, _stream()))
+            c.launches += 2
         return js[:m]
 
     def gather_rows(self, js):
@@ -378,6 +379,10 @@ def _make_sharded_updater_class():
                               ResamplerWarning)
             self._just_resampled = True
             self._resample_count += 1
+            ev = None
+            if self._cloud.resample_events is not None:  # bench instrumentation
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             res = self.resampler
             cloud = self._cloud
             comm = self._comm
@@ -444,6 +449,9 @@ def _make_sharded_updater_class():
                 self.model.clear_cache()
             except Exception as e:  # pragma: no cover
                 warnings.warn("Exception raised when clearing model cache: {}. Ignoring.".format(e))
+            if ev is not None:
+                ev[1].record()
+                self._cloud.resample_events.append(ev)
 
     return ShardedSMCUpdater
 

@@ -173,7 +173,7 @@ class SMCUpdater(object):
         js = torch.empty((n,), dtype=torch.int64, device=cloud.device)
         from .engine import _ptr, _stream
         _lib.check(cloud.lib.qb_draw(_ptr(cloud._cdf), cloud.n, _ptr(u), n, _ptr(js), _ptr(cloud.counter[1:]),
-                                     _stream()))
+                                     _ptr(cloud.ws), cloud.ws_bytes, _stream()))
         return cloud.x.index_select(0, js).cpu().numpy()
 
     def est_mean(self):
@@ -382,6 +382,10 @@ class SMCUpdater(object):
         self._resample_count += 1
         if self._debug_resampling:
             old_mean, old_cov = self.est_mean(), self.est_covariance_mtx()
+        ev = None
+        if self._cloud.resample_events is not None:      # bench instrumentation
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
 
         new_dist = self.resampler(self.model, self)
         if isinstance(new_dist, DeviceParticles) and new_dist.cloud is self._cloud:
@@ -403,6 +407,9 @@ class SMCUpdater(object):
             self.model.clear_cache()
         except Exception as e:  # pragma: no cover
             warnings.warn("Exception raised when clearing model cache: {}. Ignoring.".format(e))
+        if ev is not None:
+            ev[1].record()
+            self._cloud.resample_events.append(ev)
 
         if self._debug_resampling:
             import logging
