@@ -47,6 +47,8 @@ extern "C" {
 
 #define QB_MAX_D 64 /* max n_modelparams handled by the staged kernels (3-qubit tomography) */
 #define QB_MAX_RANKS 16 /* GPUs of one NVLink domain that may share a particle cloud */
+#define QB_MAX_FUSE 8   /* consecutive updates one launch can fuse (qb_fused_update_multi) */
+#define QB_MAILBOX_ROW 32 /* doubles per peer-mailbox row: 3 * QB_MAX_FUSE sums, padding, tag in the last slot */
 
 /* ---- model plugin descriptor ------------------------------------------- */
 /* Which built-in likelihood the kernels evaluate. */
@@ -85,6 +87,8 @@ typedef struct qb_expparams {
 #define QB_STAT_NESS 5      /* n_ess = norm^2 / sumsq (1 / sumsq when the |norm| < eps guard applies) */
 #define QB_STAT_TAG 6       /* caller-chosen tag of the launch that wrote this block (qb_update_ctl.tag) */
 #define QB_STAT_SKIPPED 7   /* 1 if a guarded qb_fused_update cancelled itself (see qb_update_ctl) */
+#define QB_STAT_ATTN 8      /* 1-based index of the first fused step that needs the host (clip, zero-weight policy,
+                               resample trigger), 0 if none; a guarded successor cancels itself when it is set */
 #define QB_STAT_COUNT 16
 
 /* ---- library / device --------------------------------------------------- */
@@ -119,24 +123,25 @@ size_t qb_update_workspace_bytes(int64_t n, int32_t d);
 
 /* Optional launch control.  The reference decides on the host, after every update, whether the
  * weights need clipping (smc.py:416), the zero-weight policy applies (smc.py:423-436) or a resample is
- * due (smc.py:275).  Those are rare, so the host may launch update k+1 BEFORE it has seen the result
- * of update k: with `guard` set the kernel first evaluates the same three conditions on stats_in
- * (the block update k wrote) and, if any holds, cancels itself (writes SKIPPED = 1, touches no
- * weight).  `h_mirror` is a device-accessible, 32-byte aligned pinned host block of 8 doubles that receives
- *   {NORM, SUMSQ, NBAD, TAG | INV_NORM, NESS, TAG, SKIPPED}
- * as two 32-byte stores, each carrying the tag: the host polls plain memory and accepts a snapshot when both
+ * due (smc.py:275).  Those are rare, so the host may launch the next update BEFORE it has seen the result
+ * of this one: every launch evaluates the three tests on its own sums and records the outcome in
+ * stats_out[QB_STAT_ATTN]; a launch with `guard` set first inspects stats_in and, if its predecessor needs
+ * the host (or cancelled itself), cancels itself too (SKIPPED = 1, no weight touched).
+ * `h_mirror` is a device-accessible, 32-byte aligned pinned host block of 8 doubles per fused step receiving
+ *   { S_j = sum w_j, Q_j = sum w_j^2, #bad_j, TAG | normalisation record_j, n_ess_j, TAG, attention_j + 2*skipped }
+ * as two 32-byte stores, each carrying the tag: the host polls plain memory and accepts a block when both
  * tags equal the launch's tag — no copy + synchronise per update and no system fence in the kernel. */
 typedef struct qb_update_ctl {
     double* h_mirror;          /* may be NULL */
     double tag;
     double zero_weight_thresh; /* smc.py:171-175 */
     double resample_below;     /* n_particles * resample_thresh (smc.py:275) */
-    int32_t guard;             /* 1: cancel if stats_in needs host attention */
-    int32_t guard_resample;    /* with guard: the predecessor was an update with check_for_resample */
-    /* Sharded cloud: with n_ranks > 1 the kernel all-reduces (sum w', sum w'^2, #bad) over
-     * the peers' mailboxes (qb_mailbox_create / qb_ipc_*) before publishing, so stats_out holds the GLOBAL
-     * normalisation and n_ess on every rank, bit-identical, with no NCCL call and no extra launch.  All
-     * ranks must issue the same sequence of launches with the same tags. */
+    int32_t guard;             /* 1: cancel if stats_in says the predecessor needs the host */
+    int32_t check_resample;    /* qb_fused_update only: this update is followed by an n_ess check */
+    /* Sharded cloud: with n_ranks > 1 the kernel all-reduces (sum w', sum w'^2, #bad) of every
+     * fused step over the peers' mailboxes (qb_mailbox_create / qb_ipc_*) before publishing, so stats_out
+     * holds the GLOBAL normalisation and n_ess on every rank, bit-identical, with no NCCL call and no extra
+     * launch.  All ranks must issue the same sequence of launches with the same tags. */
     int32_t n_ranks, rank;
     double* d_peer_mailbox[QB_MAX_RANKS]; /* [r] = rank r's mailbox as mapped in THIS process */
     int32_t* d_error_flag;     /* optional device int, set to 1 if a peer never answered */
@@ -154,6 +159,18 @@ int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outco
                     const double* d_stats_in, double* d_stats_out,
                     const qb_update_ctl* ctl /* may be NULL */,
                     void* d_ws, size_t ws_bytes, void* stream);
+
+/* The same launch for K = nsteps <= QB_MAX_FUSE CONSECUTIVE updates (batch_update, smc.py:459-487): the K
+ * likelihoods are applied while the particle sits in registers, so the launch still moves 8(d+2) bytes per
+ * particle.  eps / outcomes: HOST arrays of K records; bit j of resample_mask: step j is followed by an n_ess
+ * check.  Per-step sums are published (mirror, and d_step_stats = K x 8 doubles if not NULL) so the host can
+ * replay each step's record / n_ess / policy; if step j < K needs the host, re-issue the first j steps from
+ * the untouched input buffers.  Tomography models take K = 1 only. */
+int qb_fused_update_multi(const qb_model* model, const qb_expparams* eps, const int64_t* outcomes,
+                          int32_t nsteps, uint32_t resample_mask,
+                          const double* d_x, int64_t n, const double* d_w_in, double* d_w_out,
+                          const double* d_stats_in, double* d_stats_out, double* d_step_stats,
+                          const qb_update_ctl* ctl, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Plain likelihood tensor L[o][i][e] (n_o, n, n_e) — Model.likelihood
  * (abstract_model.py:443-468) for the built-in models; `eps`/`outcomes` are HOST arrays. */
@@ -219,7 +236,7 @@ int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int
 
 /* ---- sharded cloud: peer mailboxes and the resample exchange ------------------- */
 #define QB_IPC_HANDLE_BYTES 64
-/* cudaMalloc + zero a mailbox of 2 * n_ranks * 4 doubles (the only entry points that allocate). */
+/* cudaMalloc + zero a mailbox of 2 * n_ranks * QB_MAILBOX_ROW doubles (the only entry points that allocate). */
 int qb_mailbox_create(int32_t n_ranks, double** d_mailbox);
 int qb_mailbox_destroy(double* d_mailbox);
 /* CUDA IPC plumbing so that a peer PROCESS can map the mailbox (handles travel over torch.distributed). */

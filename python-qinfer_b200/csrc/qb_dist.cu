@@ -92,7 +92,7 @@ using namespace qb;
 extern "C" int qb_mailbox_create(int32_t n_ranks, double** d_mailbox) {
     QB_REQUIRE(d_mailbox && n_ranks >= 1 && n_ranks <= QB_MAX_RANKS, QB_ERR_INVALID_ARGUMENT,
                "qb_mailbox_create: bad arguments");
-    const size_t bytes = static_cast<size_t>(2) * n_ranks * 4 * sizeof(double);
+    const size_t bytes = static_cast<size_t>(2) * n_ranks * QB_MAILBOX_ROW * sizeof(double);
     void* p = nullptr;
     QB_CUDA_CHECK(cudaMalloc(&p, bytes));
     QB_CUDA_CHECK(cudaMemset(p, 0, bytes));

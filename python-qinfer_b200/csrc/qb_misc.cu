@@ -47,6 +47,7 @@ __global__ void set_uniform_kernel(double* w, int64_t n, int64_t n_global, doubl
         stats[QB_STAT_NESS] = static_cast<double>(n_global);
         stats[QB_STAT_TAG] = 0.0;
         stats[QB_STAT_SKIPPED] = 0.0;
+        stats[QB_STAT_ATTN] = 0.0;
     }
 }
 
@@ -121,6 +122,7 @@ __global__ void restat_finish_kernel(const double* partials, int nblocks, double
     stats[QB_STAT_NESS] = 1.0 / q;  // distributions.py:299-307 on the weights as they are
     stats[QB_STAT_TAG] = 0.0;
     stats[QB_STAT_SKIPPED] = 0.0;
+    stats[QB_STAT_ATTN] = 0.0;
 }
 
 // ---- plain likelihood + validity -----------------------------------------------

@@ -1,22 +1,24 @@
 // Fused Bayes-update kernel: likelihood x weight multiply x normalisation sum x
-// n_ess reduction in ONE launch (smc.py:324-386,413-453).
+// n_ess reduction in ONE launch (smc.py:324-386,413-453), for ONE update or for a
+// batch of up to QB_MAX_FUSE consecutive updates (smc.py:459-487 batch_update).
 //
-// HBM traffic per particle-update: read x (8d) + read w (8) + write w' (8)
-// = 8(d+2) bytes; the division by the normalisation (smc.py:373) is deferred
-// as the scalar stats[INV_NORM] that the NEXT pass folds into its weight load.
+// HBM traffic per launch: read x (8d) + read w (8) + write w' (8) = 8(d+2) bytes per particle,
+// whatever the number K of fused updates — the division by the normalisation (smc.py:373) is deferred
+// as the scalar stats[INV_NORM] that the NEXT launch folds into its weight load, and the K likelihoods
+// of a batch are evaluated on the particle while it sits in registers.  Per-step sums S_j = sum w_j,
+// Q_j = sum w_j^2 and bad-weight counts are reduced for every step j of the batch, so the host recovers
+// each step's normalisation record (S_j / S_{j-1}), n_ess (S_j^2 / Q_j) and policy tests exactly as if
+// the updates had been issued one by one; the weights differ from the one-by-one path only by the
+// omitted intermediate renormalisation (rounding, ~K ulp).
 //
-// Data movement: full tiles of the row-major (n, d) particle slab and of the
-// weight vector are staged global->shared with 1-D bulk TMA copies
-// (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a STAGES-deep
-// ring, so every SM keeps STAGES x 16-24 KB of loads in flight without holding
-// them in registers.  For d in {1,3,4} each thread then owns PAIRS of adjacent
-// particles: 128-bit conflict-free shared loads in, one 128-bit streaming store
-// of the two new weights out, all tile offsets compile-time immediates — the
-// instruction count per particle is what bounds this kernel once the memory
-// system is fed (ncu r1: 114 -> ~35 warp-instructions per 32 particles).
-// Generic d (tomography) walks its row with a per-lane rotated start so that
-// rows 128 B apart do not collide on shared-memory banks.
-// The ragged last tile (byte count not a multiple of 16) is loaded directly.
+// Data movement: full tiles of the row-major (n, d) particle slab and of the weight vector are staged
+// global->shared with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a
+// STAGES-deep full/empty mbarrier ring by one producer lane; 8 consumer warps read them back.  For d in
+// {1,3,4} each thread owns PAIRS of adjacent particles: 128-bit conflict-free shared loads in, one 128-bit
+// streaming store of the two new weights out.  Generic d (tomography) walks its row with a per-lane rotated
+// start so that rows 128 B apart do not collide on shared-memory banks.  The ragged last tile (byte count
+// not a multiple of 16) is read directly.  Launched with programmatic stream serialisation: the next
+// launch's CTAs become resident (2 CTAs/SM per launch leave room for it) and park in griddepcontrol.wait.
 #include <cstdlib>
 #include "qb_models.cuh"
 
@@ -25,6 +27,8 @@ namespace qb {
 constexpr int UPD_CONSUMER_WARPS = 8;
 constexpr int UPD_THREADS = (UPD_CONSUMER_WARPS + 1) * 32;  // + one TMA producer warp
 constexpr int UPD_STAGES = 3;
+constexpr int KF_MAX = QB_MAX_FUSE;
+constexpr int MBOX_ROW = QB_MAILBOX_ROW;  // doubles per mailbox row: 3 * KF_MAX sums ... tag in the last slot
 
 struct UpdateParams {
     const double* x;
@@ -32,166 +36,25 @@ struct UpdateParams {
     double* w_out;
     const double* stats_in;
     double* stats_out;
-    double* partials;        // [grid][4]
+    double* step_stats;      // [nsteps][8] device copy of the per-step blocks (may be NULL)
+    double* partials;        // [grid][3 * KF]
     unsigned int* ticket;    // last-block-done counter (self-resetting)
     int64_t n;
     int32_t tile;            // particles per tile
     int32_t d;
-    double* mirror;          // device-accessible pinned host copy of the stats block (or NULL)
+    int32_t nsteps;          // 1..KF_MAX updates fused in this launch
+    uint32_t resample_mask;  // bit j: step j is followed by an n_ess check (check_for_resample)
+    double* mirror;          // device-accessible pinned host block, nsteps x 8 doubles (or NULL)
     double tag;
     double zero_weight_thresh, resample_below;
-    int32_t guard, guard_resample;
-    int32_t n_ranks, rank;   // > 1: all-reduce the three sums over the peers' mailboxes inside this launch
+    int32_t guard, pad0;
+    int32_t n_ranks, rank;   // > 1: all-reduce the sums over the peers' mailboxes inside this launch
     double* peer_mbox[QB_MAX_RANKS];
     int32_t* error_flag;     // device int set to 1 if the peer wait timed out
     ModelView mv;
-    ExpView ev;
-    double meas[QB_MAX_D];
+    ExpView ev[KF_MAX];
+    double meas[QB_MAX_D];   // tomography (single-step launches only)
 };
-
-__device__ __forceinline__ void block_reduce3(double& s, double& q, unsigned int& bad, double* red,
-                                              unsigned int* redu) {
-    s = warp_sum(s);
-    q = warp_sum(q);
-    bad = __reduce_add_sync(0xffffffffu, bad);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) {
-        red[wid * 2 + 0] = s;
-        red[wid * 2 + 1] = q;
-        redu[wid] = bad;
-    }
-    __syncthreads();
-    if (wid == 0) {
-        const int nw = blockDim.x >> 5;
-        s = (lane < nw) ? red[lane * 2 + 0] : 0.0;
-        q = (lane < nw) ? red[lane * 2 + 1] : 0.0;
-        bad = (lane < nw) ? redu[lane] : 0u;
-        s = warp_sum(s);
-        q = warp_sum(q);
-        bad = __reduce_add_sync(0xffffffffu, bad);
-    }
-}
-
-// Does the step that produced `st` need the host before another update may run?  (negative/NaN
-// weights, smc.py:416; the zero-weight policies, smc.py:423-436; the resample trigger, smc.py:275;
-// or it was itself skipped.)  Evaluated on the device so that the NEXT update can be launched
-// speculatively and cancel itself.
-__device__ __forceinline__ bool needs_host(const double* st, double zero_thresh, int check_resample,
-                                           double resample_below) {
-    const double eps = 2.220446049250313e-16;
-    const double norm = st[QB_STAT_NORM];
-    const double total = (fabs(norm) < eps) ? norm : 1.0;  // np.sum of the normalised weights
-    bool attn = (st[QB_STAT_NBAD] > 0.0) || (total <= zero_thresh) || (st[QB_STAT_SKIPPED] != 0.0);
-    if (check_resample) attn = attn || (st[QB_STAT_NESS] < resample_below);
-    return attn;
-}
-
-__device__ __forceinline__ void publish_stats(const UpdateParams& p, double norm, double sumsq, double nbad,
-                                              double skipped) {
-    const double eps = 2.220446049250313e-16;  // np.spacing(1), smc.py:370
-    double v[QB_STAT_COUNT];
-#pragma unroll
-    for (int k = 0; k < QB_STAT_COUNT; ++k) v[k] = 0.0;
-    v[QB_STAT_NORM] = norm;
-    v[QB_STAT_SUMSQ] = sumsq;
-    v[QB_STAT_MIN] = nan("");  // computed on demand (qb_weights_min) when NBAD > 0
-    v[QB_STAT_NBAD] = nbad;
-    v[QB_STAT_INV_NORM] = (fabs(norm) < eps) ? 1.0 : 1.0 / norm;
-    // n_ess = 1 / sum(w_normalised^2); when the norm guard of smc.py:369-370 applies the weights stay as they are
-    v[QB_STAT_NESS] = (fabs(norm) < eps) ? 1.0 / sumsq : (norm * norm) / sumsq;
-    v[QB_STAT_TAG] = p.tag;
-    v[QB_STAT_SKIPPED] = skipped;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) p.stats_out[k] = v[k];
-    if (p.mirror != nullptr) {
-        // Host mirror without a system-scope fence (a PCIe round trip on the kernel's critical path): the block is
-        // written as two 32-byte vector stores, each a single aligned PCIe write, and EACH half carries the tag —
-        // slots [3] and [6] — so the host accepts a snapshot only when both tags match (it re-reads otherwise).
-        // Layout of the mirror: {NORM, SUMSQ, NBAD, TAG | INV_NORM, NESS, TAG, SKIPPED}.
-        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror), "d"(v[QB_STAT_NORM]),
-                     "d"(v[QB_STAT_SUMSQ]), "d"(v[QB_STAT_NBAD]), "d"(p.tag)
-                     : "memory");
-        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 4), "d"(v[QB_STAT_INV_NORM]),
-                     "d"(v[QB_STAT_NESS]), "d"(p.tag), "d"(skipped)
-                     : "memory");
-    }
-}
-
-// In-kernel all-reduce of (norm, sumsq, nbad) across the ranks of one NVLink domain.  Every rank owns a
-// mailbox of 2 x n_ranks x 4 doubles mapped into all peers (CUDA IPC).  Launch `tag` uses half (tag & 1):
-// lane q stores this rank's three sums into peer q's mailbox row [half][rank] and then, after a
-// system-scope fence, the tag word; it then spins on its own mailbox row [half][q] until peer q's tag
-// arrives.  The rows are summed in rank order, so every rank obtains bit-identical global sums.
-// Two halves suffice: a rank can only be one launch ahead of the slowest peer (it needs that peer's
-// previous-launch row to finish its own previous launch).
-__device__ void peer_allreduce3(const UpdateParams& p, double& s, double& q, double& bad, double* red) {
-    const int G = p.n_ranks;
-    const int half = static_cast<int>(static_cast<long long>(p.tag) & 1LL);
-    const int lane = threadIdx.x;
-    if (lane < G) {
-        volatile double* dst = p.peer_mbox[lane] + (static_cast<size_t>(half) * G + p.rank) * 4;
-        dst[0] = s;
-        dst[1] = q;
-        dst[2] = bad;
-        __threadfence_system();
-        dst[3] = p.tag;
-        volatile double* src = p.peer_mbox[p.rank] + (static_cast<size_t>(half) * G + lane) * 4;
-        const long long t0 = clock64();
-        bool ok = true;
-        while (src[3] != p.tag) {
-            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; do not hang the GPU
-                ok = false;
-                break;
-            }
-        }
-        __threadfence_system();
-        red[lane * 3 + 0] = ok ? src[0] : nan("");
-        red[lane * 3 + 1] = ok ? src[1] : nan("");
-        red[lane * 3 + 2] = ok ? src[2] : 0.0;
-        if (!ok && p.error_flag != nullptr) *p.error_flag = 1;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double ts = 0.0, tq = 0.0, tb = 0.0;
-        for (int r = 0; r < G; ++r) {
-            ts += red[r * 3 + 0];
-            tq += red[r * 3 + 1];
-            tb += red[r * 3 + 2];
-        }
-        s = ts;
-        q = tq;
-        bad = tb;
-    }
-}
-
-// Final deterministic reduction of per-block partials by the last block to finish.
-__device__ void finish_stats(const UpdateParams& p, int nblocks, double* red, unsigned int* redu, double* redp) {
-    double s = 0.0, q = 0.0, bad = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
-        s += p.partials[b * 4 + 0];
-        q += p.partials[b * 4 + 1];
-        bad += p.partials[b * 4 + 2];
-    }
-    unsigned int ubad = static_cast<unsigned int>(bad);
-    __syncthreads();
-    block_reduce3(s, q, ubad, red, redu);
-    double dbad = static_cast<double>(ubad);
-    if (p.n_ranks > 1) {
-        // broadcast the block totals held by thread 0 to the lanes that talk to the peers
-        if (threadIdx.x == 0) {
-            redp[3 * QB_MAX_RANKS + 0] = s;
-            redp[3 * QB_MAX_RANKS + 1] = q;
-            redp[3 * QB_MAX_RANKS + 2] = dbad;
-        }
-        __syncthreads();
-        s = redp[3 * QB_MAX_RANKS + 0];
-        q = redp[3 * QB_MAX_RANKS + 1];
-        dbad = redp[3 * QB_MAX_RANKS + 2];
-        __syncthreads();
-        peer_allreduce3(p, s, q, dbad, redp);
-    }
-    if (threadIdx.x == 0) publish_stats(p, s, q, dbad, 0.0);
-}
 
 struct Acc {
     double s, q;
@@ -204,14 +67,143 @@ __device__ __forceinline__ void accumulate(Acc& a, double wv) {
     a.bad += (wv >= 0.0) ? 0u : 1u;  // counts negatives and NaNs (smc.py:416)
 }
 
-// DT > 0: compile-time n_modelparams, pair processing.  DT == 0: runtime d.
+// Block reduction of KF (s, q, bad) triples into out[3*j..3*j+2] (shared memory).
+template <int KF>
+__device__ __forceinline__ void block_reduce_steps(const Acc (&a)[KF], double* red, double* out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int j = 0; j < KF; ++j) {
+        const double s = warp_sum(a[j].s);
+        const double q = warp_sum(a[j].q);
+        const unsigned int b = __reduce_add_sync(0xffffffffu, a[j].bad);
+        if (lane == 0) {
+            red[(wid * KF + j) * 3 + 0] = s;
+            red[(wid * KF + j) * 3 + 1] = q;
+            red[(wid * KF + j) * 3 + 2] = static_cast<double>(b);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 * KF) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += red[w * KF * 3 + threadIdx.x];
+        out[threadIdx.x] = v;
+    }
+    __syncthreads();
+}
+
+// Does the launch that produced `st` need the host before another update may run?  (negative/NaN
+// weights, smc.py:416; the zero-weight policies, smc.py:423-436; the resample trigger, smc.py:275;
+// or it cancelled itself.)  The producing launch evaluates those tests itself (publish) so that the NEXT
+// launch can be issued speculatively and cancel itself on one flag.
+__device__ __forceinline__ bool needs_host(const double* st) {
+    return (st[QB_STAT_ATTN] != 0.0) || (st[QB_STAT_SKIPPED] != 0.0);
+}
+
+// Publish the per-step blocks and the final stats block.  sums[3*j..] = (S_j, Q_j, nbad_j), global.
+__device__ void publish(const UpdateParams& p, const double* sums) {
+    const double skipped = 0.0;
+    const double eps = 2.220446049250313e-16;  // np.spacing(1), smc.py:370
+    const int K = p.nsteps;
+    double attn = 0.0;
+    double s_prev = 1.0;
+    double norm = 0.0, sumsq = 0.0, nbad_tot = 0.0, ness = 0.0;
+    for (int j = 0; j < K; ++j) {
+        const double S = sums[3 * j + 0], Q = sums[3 * j + 1], nb = sums[3 * j + 2];
+        // normalisation record of step j (smc.py:357): sum of (normalised previous weights) * L_j
+        const double rec = (j == 0) ? S : S / s_prev;
+        const bool degenerate = fabs(rec) < eps;      // smc.py:369-370: then the weights stay as w * L
+        const double total = degenerate ? rec : 1.0;  // np.sum of the weights the reference would hold
+        const double ne = degenerate ? 1.0 / Q : (S * S) / Q;
+        bool a = (nb > 0.0) || (total <= p.zero_weight_thresh);
+        if ((p.resample_mask >> j) & 1u) a = a || (ne < p.resample_below);
+        const double flag = (a ? 1.0 : 0.0) + 2.0 * skipped;
+        if (a && attn == 0.0) attn = static_cast<double>(j + 1);
+        if (p.step_stats != nullptr) {
+            double* o = p.step_stats + 8 * j;
+            o[0] = S;
+            o[1] = Q;
+            o[2] = nb;
+            o[3] = p.tag;
+            o[4] = rec;
+            o[5] = ne;
+            o[6] = p.tag;
+            o[7] = flag;
+        }
+        if (p.mirror != nullptr) {
+            // Host mirror without a system-scope fence: two 32-byte vector stores per step, each a single aligned
+            // PCIe write and EACH carrying the tag; the host accepts a block only when both tags match.
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j), "d"(S), "d"(Q),
+                         "d"(nb), "d"(p.tag)
+                         : "memory");
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j + 4), "d"(rec),
+                         "d"(ne), "d"(p.tag), "d"(flag)
+                         : "memory");
+        }
+        s_prev = S;
+        norm = S;
+        sumsq = Q;
+        nbad_tot += nb;
+        ness = ne;
+    }
+    double* so = p.stats_out;
+    so[QB_STAT_NORM] = norm;    // sum of the stored (unnormalised) weights after the last step
+    so[QB_STAT_SUMSQ] = sumsq;
+    so[QB_STAT_MIN] = nan("");  // computed on demand (qb_weights_min) when NBAD > 0
+    so[QB_STAT_NBAD] = nbad_tot;
+    so[QB_STAT_INV_NORM] = (fabs(norm) < eps) ? 1.0 : 1.0 / norm;
+    so[QB_STAT_NESS] = ness;
+    so[QB_STAT_TAG] = p.tag;
+    so[QB_STAT_SKIPPED] = skipped;
+    so[QB_STAT_ATTN] = attn;
+}
+
+// In-kernel all-reduce of the 3K sums across the ranks of one NVLink domain.  Every rank owns a mailbox of
+// 2 x n_ranks rows of MBOX_ROW doubles mapped into all peers (CUDA IPC).  Launch `tag` uses half (tag & 1):
+// lane q stores this rank's sums into peer q's row [half][rank] and then, after a system-scope fence, the
+// tag word; it then spins on its own row [half][q] until peer q's tag arrives.  Rows are summed in rank order,
+// so every rank obtains bit-identical global sums.  Two halves suffice: a rank can be at most one launch ahead
+// of the slowest peer (it needs that peer's previous-launch row to finish its own previous launch).
+__device__ void peer_allreduce(const UpdateParams& p, double* sums, double* scratch) {
+    const int G = p.n_ranks;
+    const int nv = 3 * p.nsteps;
+    const int half = static_cast<int>(static_cast<long long>(p.tag) & 1LL);
+    const int lane = threadIdx.x;
+    if (lane < G) {
+        volatile double* dst = p.peer_mbox[lane] + (static_cast<size_t>(half) * G + p.rank) * MBOX_ROW;
+        for (int k = 0; k < nv; ++k) dst[k] = sums[k];
+        __threadfence_system();
+        dst[MBOX_ROW - 1] = p.tag;
+        volatile double* src = p.peer_mbox[p.rank] + (static_cast<size_t>(half) * G + lane) * MBOX_ROW;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (src[MBOX_ROW - 1] != p.tag) {
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a peer died; do not hang the GPU
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        for (int k = 0; k < nv; ++k) scratch[lane * MBOX_ROW + k] = ok ? src[k] : nan("");
+        if (!ok && p.error_flag != nullptr) *p.error_flag = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        double t = 0.0;
+        for (int r = 0; r < G; ++r) t += scratch[r * MBOX_ROW + threadIdx.x];
+        sums[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+// DT > 0: compile-time n_modelparams, pair processing.  DT == 0: runtime d.  KF: 1 or KF_MAX fused updates.
 //
 // Warp-specialised: warps 0..UPD_CONSUMER_WARPS-1 compute, the last warp's lane 0 is the TMA producer.
 // full[s]  (count 1)  : producer's expect_tx + the bulk copies' complete_tx  -> consumers may read stage s
 // empty[s] (count NCW): one arrive per consumer warp                        -> producer may refill stage s
 // No CTA-wide barrier in the tile loop: warps drift freely across the ring.
-template <int KIND, bool BINOM, int DT>
-__global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __grid_constant__ UpdateParams p) {
+template <int KIND, bool BINOM, int DT, int KF>
+__global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __grid_constant__ UpdateParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TILE_CT = (DT == 1) ? 1024 : 512;  // must match choose_tile()
     constexpr int NCT = UPD_CONSUMER_WARPS * 32;     // consumer threads
@@ -222,29 +214,44 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
     const uint32_t stage_bytes = x_bytes + w_bytes;  // multiples of 128 by construction (tile % 16 == 0)
     double* meas_s = reinterpret_cast<double*>(smem_raw + 128);
     unsigned char* ring = smem_raw + 128 + QB_MAX_D * 8;
-    __shared__ double red[(UPD_THREADS / 32) * 2];
-    __shared__ unsigned int redu[UPD_THREADS / 32];
-    __shared__ double redp[3 * QB_MAX_RANKS + 3];
+    __shared__ double red[(UPD_THREADS / 32) * KF * 3];
+    __shared__ double sums[3 * KF_MAX];
+    __shared__ double peer_scratch[QB_MAX_RANKS * MBOX_ROW];
     __shared__ unsigned int is_last;
 
     const int tid = threadIdx.x;
     // Programmatic dependent launch: let the NEXT launch on this stream become resident while this one runs
-    // (its CTAs take the slots ours free and park in griddepcontrol.wait), and do not touch anything the
-    // PREVIOUS launch wrote (stats_in, w_in, the ticket) before that launch has completed and flushed.
+    // (its CTAs take free slots and park in griddepcontrol.wait), and do not touch anything the PREVIOUS
+    // launch wrote (stats_in, w_in, the ticket) before that launch has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (p.guard && needs_host(p.stats_in, p.zero_weight_thresh, p.guard_resample, p.resample_below)) {
-        // speculative launch whose predecessor needs the host: do nothing, say so
-        if (blockIdx.x == 0 && tid == 0) publish_stats(p, p.stats_in[QB_STAT_NORM], p.stats_in[QB_STAT_SUMSQ], 0.0, 1.0);
+    if (p.guard && needs_host(p.stats_in)) {
+        // Speculative launch whose predecessor needs the host: do nothing, say so.  stats_out is the block of
+        // the COMMITTED state the host may still fall back to, so only its SKIPPED word is touched (a guarded
+        // launch queued behind this one cancels on it); the host learns through the mirror.
+        if (blockIdx.x == 0 && tid == 0) {
+            p.stats_out[QB_STAT_SKIPPED] = 1.0;
+            if (p.mirror != nullptr) {
+                for (int j = 0; j < p.nsteps; ++j) {
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j), "d"(0.0),
+                                 "d"(0.0), "d"(0.0), "d"(p.tag)
+                                 : "memory");
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j + 4), "d"(0.0),
+                                 "d"(0.0), "d"(p.tag), "d"(2.0)
+                                 : "memory");
+                }
+            }
+        }
         return;
     }
-    const uint32_t bar0 = smem_u32(smem_raw);            // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
+    const uint32_t bar0 = smem_u32(smem_raw);  // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
     const uint32_t ring0 = smem_u32(ring);
     const int ntiles = static_cast<int>((p.n + tile - 1) / tile);
     const int my_tiles = (ntiles > static_cast<int>(blockIdx.x))
                              ? (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                                    static_cast<int>(gridDim.x)
                              : 0;
+    const int nsteps = (KF == 1) ? 1 : p.nsteps;
 
     if (KIND == QB_MODEL_TOMOGRAPHY) {
         for (int c = tid; c < d; c += UPD_THREADS) meas_s[c] = p.meas[c];
@@ -259,7 +266,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
     }
     __syncthreads();
 
-    Acc a0 = {0.0, 0.0, 0u}, a1 = {0.0, 0.0, 0u};
+    Acc acc[KF];
+#pragma unroll
+    for (int j = 0; j < KF; ++j) acc[j] = {0.0, 0.0, 0u};
     const int64_t tile_stride = static_cast<int64_t>(gridDim.x) * tile;
 
     if (tid >= NCT) {
@@ -286,7 +295,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
         // ===== consumer warps =====
         const double inv_norm = p.stats_in[QB_STAT_INV_NORM];
         const ModelView mv = p.mv;
-        const ExpView ev = p.ev;
         const int lane = tid & 31;
         auto meas = [&](int c) { return meas_s[c]; };
         int s = 0;
@@ -315,24 +323,34 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
                         }
                         auto row0 = [&](int c) { return xr[c]; };
                         auto row1 = [&](int c) { return xr[DT + c]; };
-                        const double L0 = model_likelihood<KIND, BINOM>(mv, ev, row0, meas, 0);
-                        const double L1 = model_likelihood<KIND, BINOM>(mv, ev, row1, meas, 0);
-                        const double w0 = (wp.x * inv_norm) * L0;  // smc.py:354 on the lazily normalised weight
-                        const double w1 = (wp.y * inv_norm) * L1;
+                        double w0 = wp.x * inv_norm;  // the lazily applied normalisation of the previous launch
+                        double w1 = wp.y * inv_norm;
+#pragma unroll
+                        for (int k = 0; k < KF; ++k) {
+                            if (KF == 1 || k < nsteps) {
+                                w0 = w0 * model_likelihood<KIND, BINOM>(mv, p.ev[k], row0, meas, 0);  // smc.py:354
+                                w1 = w1 * model_likelihood<KIND, BINOM>(mv, p.ev[k], row1, meas, 0);
+                                accumulate(acc[k], w0);
+                                accumulate(acc[k], w1);
+                            }
+                        }
                         asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(wo + 2 * j), "d"(w0),
                                      "d"(w1)
                                      : "memory");
-                        accumulate(a0, w0);
-                        accumulate(a1, w1);
                     }
                 } else {
                     for (int j = tid; j < tile; j += NCT) {
                         const double* xr = xs + static_cast<size_t>(j) * d;
                         auto row = [&](int c) { return xr[c]; };
-                        const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, lane);
-                        const double wv = (ws[j] * inv_norm) * L;
+                        double wv = ws[j] * inv_norm;
+#pragma unroll
+                        for (int k = 0; k < KF; ++k) {
+                            if (KF == 1 || k < nsteps) {
+                                wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, lane);
+                                accumulate(acc[k], wv);
+                            }
+                        }
                         stg_stream(wo + j, wv);
-                        accumulate(a0, wv);
                     }
                 }
                 __syncwarp();
@@ -342,10 +360,15 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
                 for (int j = tid; j < cnt; j += NCT) {
                     const double* xr = p.x + (first + j) * d;
                     auto row = [&](int c) { return xr[c]; };
-                    const double L = model_likelihood<KIND, BINOM>(mv, ev, row, meas, 0);
-                    const double wv = (p.w_in[first + j] * inv_norm) * L;
+                    double wv = p.w_in[first + j] * inv_norm;
+#pragma unroll
+                    for (int k = 0; k < KF; ++k) {
+                        if (KF == 1 || k < nsteps) {
+                            wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, 0);
+                            accumulate(acc[k], wv);
+                        }
+                    }
                     wo[j] = wv;
-                    accumulate(a0, wv);
                 }
             }
             if (++s == UPD_STAGES) {
@@ -355,29 +378,41 @@ __global__ void __launch_bounds__(UPD_THREADS, 4) fused_update_kernel(const __gr
         }
     }
 
-    double acc_s = a0.s + a1.s, acc_q = a0.q + a1.q;
-    unsigned int acc_bad = a0.bad + a1.bad;
-    block_reduce3(acc_s, acc_q, acc_bad, red, redu);
+    block_reduce_steps<KF>(acc, red, sums);
+    if (tid < 3 * KF) p.partials[static_cast<size_t>(blockIdx.x) * 3 * KF + tid] = sums[tid];
+    __syncthreads();
     if (tid == 0) {
-        p.partials[blockIdx.x * 4 + 0] = acc_s;
-        p.partials[blockIdx.x * 4 + 1] = acc_q;
-        p.partials[blockIdx.x * 4 + 2] = static_cast<double>(acc_bad);
         __threadfence();
         const unsigned int prev = atomicAdd(p.ticket, 1u);
         is_last = (prev == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (is_last) {
+        // deterministic final reduction of the per-block partials (fixed lane/block order)
         __threadfence();
-        finish_stats(p, gridDim.x, red, redu, redp);
-        if (tid == 0) *p.ticket = 0u;  // ready for the next launch on this stream
+        constexpr int NV = 3 * KF;
+        const int lane = tid & 31, wid = tid >> 5, nw = UPD_THREADS / 32;
+        if (tid < 3 * KF_MAX) sums[tid] = 0.0;
+        __syncthreads();
+        for (int v = wid; v < NV; v += nw) {  // one warp per value
+            double t = 0.0;
+            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) t += p.partials[static_cast<size_t>(b) * NV + v];
+            t = warp_sum(t);
+            if (lane == 0) sums[v] = t;
+        }
+        __syncthreads();
+        if (p.n_ranks > 1) peer_allreduce(p, sums, peer_scratch);
+        if (tid == 0) {
+            publish(p, sums);
+            *p.ticket = 0u;  // ready for the next launch on this stream
+        }
     }
 }
 
-// Tile size: 16-24 KB per stage; a multiple of 2 * UPD_THREADS particles for the pair kernels,
+// Tile size: 16-24 KB per stage; a multiple of 2 * consumer threads for the pair kernels,
 // of 16 particles otherwise, so every bulk copy is 128-B granular.
 static int choose_tile(int d) {
-    if (d == 1) return 1024;   // 16 KB / stage
+    if (d == 1) return 1024;           // 16 KB / stage
     if (d == 3 || d == 4) return 512;  // 16 / 20 KB
     int t = 2048 / (d + 1);
     t = (t / 16) * 16;
@@ -391,20 +426,27 @@ static size_t update_smem_bytes(int d) {
 
 typedef void (*update_kernel_t)(const UpdateParams);
 
-static update_kernel_t pick_update_kernel(const qb_model& m) {
+template <int KF>
+static update_kernel_t pick_update_kernel_k(const qb_model& m) {
     switch (m.kind) {
         case QB_MODEL_PRECESSION:
-            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true, 1>
-                              : fused_update_kernel<QB_MODEL_PRECESSION, false, 1>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true, 1, KF>
+                              : fused_update_kernel<QB_MODEL_PRECESSION, false, 1, KF>;
         case QB_MODEL_RB:
             if (m.interleaved)
-                return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 4> : fused_update_kernel<QB_MODEL_RB, false, 4>;
-            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 3> : fused_update_kernel<QB_MODEL_RB, false, 3>;
-        case QB_MODEL_TOMOGRAPHY:
-            return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true, 0>
-                              : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false, 0>;
+                return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 4, KF>
+                                  : fused_update_kernel<QB_MODEL_RB, false, 4, KF>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 3, KF>
+                              : fused_update_kernel<QB_MODEL_RB, false, 3, KF>;
     }
     return nullptr;
+}
+
+static update_kernel_t pick_update_kernel(const qb_model& m, int nsteps) {
+    if (m.kind == QB_MODEL_TOMOGRAPHY)  // per-step measurement vectors do not fit the launch parameters: K = 1
+        return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true, 0, 1>
+                          : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false, 0, 1>;
+    return (nsteps == 1) ? pick_update_kernel_k<1>(m) : pick_update_kernel_k<KF_MAX>(m);
 }
 
 int validate_model(const qb_model* m) {
@@ -429,11 +471,16 @@ int validate_model(const qb_model* m) {
 }
 
 static int update_grid_limit(update_kernel_t k, size_t smem) {
-    // the attribute call is idempotent and cheap; keeping it unconditional avoids per-device caches
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, UPD_THREADS, smem) != cudaSuccess) return -1;
     if (per_sm < 1) per_sm = 1;
+    // Two CTAs per SM per launch: leaves room for the next (programmatically dependent) launch to become
+    // resident while this one runs; measured faster than filling the SM with one launch (r1: 43.6 vs 46.6 us).
+    int cap = 2;
+    const char* e = getenv("QB_UPD_CTAS_PER_SM");  // experiment knob
+    if (e && atoi(e) > 0) cap = atoi(e);
+    if (per_sm > cap) per_sm = cap;
     return per_sm * sm_count();
 }
 
@@ -442,7 +489,7 @@ struct GridCacheEntry {
     int dev;
     int limit;
 };
-static GridCacheEntry g_grid_cache[32];
+static GridCacheEntry g_grid_cache[64];
 static int g_grid_cache_n = 0;
 
 static int cached_grid_limit(update_kernel_t k, size_t smem) {
@@ -451,7 +498,7 @@ static int cached_grid_limit(update_kernel_t k, size_t smem) {
     for (int i = 0; i < g_grid_cache_n; ++i)
         if (g_grid_cache[i].k == k && g_grid_cache[i].dev == dev) return g_grid_cache[i].limit;
     const int limit = update_grid_limit(k, smem);
-    if (limit > 0 && g_grid_cache_n < 32) g_grid_cache[g_grid_cache_n++] = {k, dev, limit};
+    if (limit > 0 && g_grid_cache_n < 64) g_grid_cache[g_grid_cache_n++] = {k, dev, limit};
     return limit;
 }
 
@@ -476,19 +523,24 @@ using namespace qb;
 extern "C" size_t qb_update_workspace_bytes(int64_t n, int32_t d) {
     (void)n;
     (void)d;
-    // per-block partials for up to 32 blocks/SM on up to 256 SMs + the ticket
-    return static_cast<size_t>(32) * 256 * 4 * sizeof(double) + 256;
+    // per-block partials (3 * QB_MAX_FUSE doubles) for up to 32 blocks/SM on up to 256 SMs + the ticket
+    return static_cast<size_t>(32) * 256 * 3 * QB_MAX_FUSE * sizeof(double) + 256;
 }
 
-extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outcome, const double* d_x,
-                               int64_t n, const double* d_w_in, double* d_w_out, const double* d_stats_in,
-                               double* d_stats_out, const qb_update_ctl* ctl, void* d_ws, size_t ws_bytes,
-                               void* stream) {
+extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* eps, const int64_t* outcomes,
+                                     int32_t nsteps, uint32_t resample_mask, const double* d_x, int64_t n,
+                                     const double* d_w_in, double* d_w_out, const double* d_stats_in,
+                                     double* d_stats_out, double* d_step_stats, const qb_update_ctl* ctl, void* d_ws,
+                                     size_t ws_bytes, void* stream) {
     int rc = validate_model(model);
     if (rc != QB_OK) return rc;
-    QB_REQUIRE(ep && d_x && d_w_in && d_w_out && d_stats_in && d_stats_out && d_ws, QB_ERR_INVALID_ARGUMENT,
-               "qb_fused_update: NULL pointer argument");
+    QB_REQUIRE(eps && outcomes && d_x && d_w_in && d_w_out && d_stats_in && d_stats_out && d_ws,
+               QB_ERR_INVALID_ARGUMENT, "qb_fused_update: NULL pointer argument");
     QB_REQUIRE(n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: n must be >= 1, got %lld", (long long)n);
+    QB_REQUIRE(nsteps >= 1 && nsteps <= QB_MAX_FUSE, QB_ERR_INVALID_ARGUMENT,
+               "qb_fused_update: 1..%d updates per launch, got %d", QB_MAX_FUSE, nsteps);
+    QB_REQUIRE(nsteps == 1 || model->kind != QB_MODEL_TOMOGRAPHY, QB_ERR_INVALID_ARGUMENT,
+               "qb_fused_update: tomography updates are not fused (one measurement vector per launch)");
     QB_REQUIRE(ws_bytes >= qb_update_workspace_bytes(n, model->d), QB_ERR_WORKSPACE,
                "qb_fused_update: workspace too small");
     QB_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w_in) & 15) == 0 &&
@@ -501,20 +553,25 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
     p.w_out = d_w_out;
     p.stats_in = d_stats_in;
     p.stats_out = d_stats_out;
+    p.step_stats = d_step_stats;
     p.ticket = reinterpret_cast<unsigned int*>(d_ws);
     p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);
     p.n = n;
     p.d = model->d;
     p.tile = choose_tile(model->d);
+    p.nsteps = nsteps;
+    p.resample_mask = resample_mask;
     p.mirror = ctl ? ctl->h_mirror : nullptr;
     p.tag = ctl ? ctl->tag : 0.0;
     p.zero_weight_thresh = ctl ? ctl->zero_weight_thresh : 0.0;
     p.resample_below = ctl ? ctl->resample_below : 0.0;
     p.guard = ctl ? ctl->guard : 0;
-    p.guard_resample = ctl ? ctl->guard_resample : 0;
+    p.pad0 = 0;
     p.n_ranks = ctl ? ctl->n_ranks : 0;
     p.rank = ctl ? ctl->rank : 0;
     p.error_flag = ctl ? ctl->d_error_flag : nullptr;
+    QB_REQUIRE(p.mirror == nullptr || (reinterpret_cast<uintptr_t>(p.mirror) & 31) == 0, QB_ERR_INVALID_ARGUMENT,
+               "qb_fused_update: the host mirror must be 32-byte aligned");
     QB_REQUIRE(p.n_ranks <= QB_MAX_RANKS, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: at most %d ranks", QB_MAX_RANKS);
     for (int r = 0; r < QB_MAX_RANKS; ++r) p.peer_mbox[r] = (ctl && r < p.n_ranks) ? ctl->d_peer_mailbox[r] : nullptr;
     if (p.n_ranks > 1) {
@@ -525,24 +582,19 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
     QB_REQUIRE(d_stats_in != d_stats_out || !p.guard, QB_ERR_INVALID_ARGUMENT,
                "qb_fused_update: a guarded update needs distinct stats_in / stats_out blocks");
     p.mv = make_model_view(*model);
-    p.ev = make_exp_view(*model, *ep, outcome);
-    for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? ep->meas[c] : 0.0;
+    for (int j = 0; j < KF_MAX; ++j) {
+        const int jj = (j < nsteps) ? j : 0;
+        p.ev[j] = make_exp_view(*model, eps[jj], outcomes[jj]);
+    }
+    for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? eps[0].meas[c] : 0.0;
 
-    update_kernel_t k = pick_update_kernel(*model);
+    update_kernel_t k = pick_update_kernel(*model, nsteps);
     const size_t smem = update_smem_bytes(model->d);
     const int limit = cached_grid_limit(k, smem);
     QB_REQUIRE(limit > 0, QB_ERR_CUDA, "qb_fused_update: occupancy query failed: %s",
                cudaGetErrorString(cudaGetLastError()));
     const int64_t ntiles = (n + p.tile - 1) / p.tile;
     int grid = static_cast<int>(ntiles < limit ? ntiles : limit);
-    {
-        static int env_cap = -1;  // experiment knob: QB_UPD_CTAS_PER_SM caps the resident CTAs per SM
-        if (env_cap < 0) {
-            const char* e = getenv("QB_UPD_CTAS_PER_SM");
-            env_cap = e ? atoi(e) : 0;
-        }
-        if (env_cap > 0 && grid > env_cap * sm_count()) grid = env_cap * sm_count();
-    }
     if (grid > 32 * 256) grid = 32 * 256;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -556,6 +608,16 @@ extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, in
     cfg.numAttrs = 1;
     QB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k, p));
     return QB_OK;
+}
+
+extern "C" int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outcome, const double* d_x,
+                               int64_t n, const double* d_w_in, double* d_w_out, const double* d_stats_in,
+                               double* d_stats_out, const qb_update_ctl* ctl, void* d_ws, size_t ws_bytes,
+                               void* stream) {
+    QB_REQUIRE(ep != nullptr, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: NULL pointer argument");
+    const uint32_t mask = (ctl && ctl->check_resample) ? 1u : 0u;
+    return qb_fused_update_multi(model, ep, &outcome, 1, mask, d_x, n, d_w_in, d_w_out, d_stats_in, d_stats_out,
+                                 nullptr, ctl, d_ws, ws_bytes, stream);
 }
 
 extern "C" int qb_weights_min(const double* d_w, int64_t n, double* d_out, void* stream) {

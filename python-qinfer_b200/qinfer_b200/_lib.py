@@ -10,7 +10,8 @@ QB_MAX_D = 64
 QB_MAX_RANKS = 16
 QB_IPC_HANDLE_BYTES = 64
 (QB_STAT_NORM, QB_STAT_SUMSQ, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_INV_NORM, QB_STAT_NESS, QB_STAT_TAG,
- QB_STAT_SKIPPED) = range(8)
+ QB_STAT_SKIPPED, QB_STAT_ATTN) = range(9)
+QB_MAX_FUSE = 8
 QB_STAT_COUNT = 16
 QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY = 1, 2, 3
 QB_SCAN_FAST, QB_SCAN_EXACT = 0, 1
@@ -31,7 +32,7 @@ class QbExpparams(ctypes.Structure):
 
 class QbUpdateCtl(ctypes.Structure):
     _fields_ = [("h_mirror", ctypes.c_void_p), ("tag", ctypes.c_double), ("zero_weight_thresh", ctypes.c_double),
-                ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("guard_resample", ctypes.c_int32),
+                ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("check_resample", ctypes.c_int32),
                 ("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32),
                 ("d_peer_mailbox", ctypes.c_void_p * QB_MAX_RANKS), ("d_error_flag", ctypes.c_void_p)]
 
@@ -62,6 +63,9 @@ SIGNATURES = {
     "qb_update_workspace_bytes": (_SZ, [_I64, _I32]),
     "qb_fused_update": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I64, _P, _I64,
                                        _P, _P, _P, _P, ctypes.POINTER(QbUpdateCtl), _P, _SZ, _P]),
+    "qb_fused_update_multi": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams),
+                                             ctypes.POINTER(_I64), _I32, ctypes.c_uint32, _P, _I64, _P, _P, _P, _P,
+                                             _P, ctypes.POINTER(QbUpdateCtl), _P, _SZ, _P]),
     "qb_likelihood": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I32,
                                      ctypes.POINTER(_I64), _I32, _P, _I64, _P, _P]),
     "qb_are_models_valid": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _P, _P]),

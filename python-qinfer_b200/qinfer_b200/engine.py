@@ -15,8 +15,10 @@ import torch
 from . import _lib
 import time
 
-from ._lib import (QB_STAT_COUNT, QB_STAT_INV_NORM, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NESS, QB_STAT_NORM,
-                   QB_STAT_SKIPPED, QB_STAT_SUMSQ, QB_STAT_TAG, check)
+from ._lib import (QB_MAX_FUSE, QB_STAT_COUNT, QB_STAT_INV_NORM, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NESS,
+                   QB_STAT_NORM, QB_STAT_SKIPPED, QB_STAT_SUMSQ, QB_STAT_TAG, check)
+
+MIRROR_SLOT = 8 * QB_MAX_FUSE      # doubles per mirror slot: one 8-double block per fused step
 
 
 def _require_cuda(device=None):
@@ -51,11 +53,12 @@ class DeviceCloud(object):
             self._stats = [torch.zeros((QB_STAT_COUNT,), **f64), torch.zeros((QB_STAT_COUNT,), **f64)]
             self.cur = 0
             # host-visible copy of each stats block, written by the kernel itself (pinned, device-accessible)
-            self.mirror = torch.zeros((2 * QB_STAT_COUNT,), dtype=torch.float64, pin_memory=True)
+            self.mirror = torch.zeros((2 * MIRROR_SLOT,), dtype=torch.float64, pin_memory=True)
             self.mirror_np = self.mirror.numpy()
             self._ctl = _lib.QbUpdateCtl()
             self._tag = 0
-            self._stats_view = np.zeros((QB_STAT_COUNT,))
+            self._eps_arr = (_lib.QbExpparams * QB_MAX_FUSE)()
+            self._out_arr = (ctypes.c_int64 * QB_MAX_FUSE)()
             ws_bytes = max(self.lib.qb_update_workspace_bytes(self.n, self.d),
                            self.lib.qb_moments_workspace_bytes(self.n, self.d),
                            self.lib.qb_cdf_workspace_bytes(self.n),
@@ -76,6 +79,7 @@ class DeviceCloud(object):
         self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = None
         self.launches = 0
         self.resample_events = None        # bench: set to [] to collect a CUDA-event pair around every resample
+        self.update_launches = 0
 
     # committed / pending views of the ping-pong buffers
     w = property(lambda self: self._w[self.cur])
@@ -122,48 +126,64 @@ class DeviceCloud(object):
         return self.stats_host.numpy()
 
     # ---- the hot kernel -------------------------------------------------------
-    def fused_update(self, ep_record, outcome, src, guard=False, guard_resample=False, zero_weight_thresh=0.0,
-                     resample_below=0.0):
-        """Launch the fused update reading weights/stats buffer ``src`` and writing buffer ``1 - src``;
-        the kernel mirrors its stats block into pinned host slot ``1 - src``.  Returns the launch tag.
-        ``guard``: speculative launch that cancels itself if the step that produced ``src`` needs the host."""
+    def fused_update(self, steps, src, guard=False, zero_weight_thresh=0.0, resample_below=0.0):
+        """Launch ONE fused kernel applying the consecutive updates ``steps`` = [(ep_record, outcome, check), ...]
+        (1..QB_MAX_FUSE of them) to weights/stats buffer ``src``, writing buffer ``1 - src``; the kernel mirrors one
+        8-double block per step into pinned host slot ``1 - src``.  Returns the launch tag.  ``guard``: speculative
+        launch that cancels itself if the launch that produced ``src`` needs the host."""
         dst = 1 - src
+        k = len(steps)
         self._tag += 1
         ctl = self._ctl
-        ctl.h_mirror = self.mirror.data_ptr() + dst * QB_STAT_COUNT * 8
+        ctl.h_mirror = self.mirror.data_ptr() + dst * MIRROR_SLOT * 8
         ctl.tag = float(self._tag)
         ctl.zero_weight_thresh = zero_weight_thresh
         ctl.resample_below = resample_below
         ctl.guard = 1 if guard else 0
-        ctl.guard_resample = 1 if guard_resample else 0
-        check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep_record), int(outcome), _ptr(self.x), self.n,
-                                       _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
-                                       _ptr(self._stats[dst]), ctypes.byref(ctl), _ptr(self.ws), self.ws_bytes,
-                                       _stream()))
+        mask = 0
+        if k == 1:
+            ep, outcome, chk = steps[0]
+            ctl.check_resample = 1 if chk else 0
+            check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep), int(outcome), _ptr(self.x), self.n,
+                                           _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
+                                           _ptr(self._stats[dst]), ctypes.byref(ctl), _ptr(self.ws), self.ws_bytes,
+                                           _stream()))
+        else:
+            eps, outs = self._eps_arr, self._out_arr
+            for j, (ep, outcome, chk) in enumerate(steps):
+                ctypes.memmove(ctypes.byref(eps, j * ctypes.sizeof(_lib.QbExpparams)), ctypes.byref(ep),
+                               ctypes.sizeof(_lib.QbExpparams))
+                outs[j] = int(outcome)
+                if chk:
+                    mask |= 1 << j
+            check(self.lib.qb_fused_update_multi(self.lib_model, eps, outs, k, mask, _ptr(self.x), self.n,
+                                                 _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
+                                                 _ptr(self._stats[dst]), None, ctypes.byref(ctl), _ptr(self.ws),
+                                                 self.ws_bytes, _stream()))
         self.launches += 1
+        self.update_launches += 1
         return self._tag
 
-    def wait_stats(self, slot, tag, timeout_s=120.0):
-        """Spin on the pinned mirror of stats buffer ``slot`` until launch ``tag`` has published it.  The kernel
-        writes {NORM, SUMSQ, NBAD, TAG | INV_NORM, NESS, TAG, SKIPPED} as two 32-byte stores; a snapshot is
-        accepted when both tags match.  Returns an array indexed by the QB_STAT_* constants."""
+    def wait_stats(self, slot, tag, nsteps=1, timeout_s=120.0):
+        """Spin on the pinned mirror of stats buffer ``slot`` until launch ``tag`` has published its ``nsteps`` blocks.
+        Each block is {S, Q, #bad, TAG | record, n_ess, TAG, attention + 2*skipped}, written as two 32-byte stores;
+        it is accepted when both tags match.  Returns an (nsteps, 8) array."""
         m = self.mirror_np
-        base = slot * QB_STAT_COUNT
+        base = slot * MIRROR_SLOT
         want = float(tag)
         t0 = None
+        last = base + 8 * (nsteps - 1)
         while True:
-            a = m[base:base + 8].copy()
-            if a[3] == want and a[6] == want:
-                break
+            a = m[base:base + 8 * nsteps].copy()
+            if a[3] == want and a[6] == want and a[last - base + 3] == want and a[last - base + 6] == want:
+                a = a.reshape(nsteps, 8)
+                if np.all(a[:, 3] == want) and np.all(a[:, 6] == want):
+                    return a
             if t0 is None:
                 t0 = time.perf_counter()
             elif time.perf_counter() - t0 > timeout_s:
                 torch.cuda.synchronize()           # surfaces a CUDA error if the kernel died
                 raise _lib.QbError("timed out waiting for the fused-update kernel (tag %d)" % tag)
-        out = self._stats_view
-        out[QB_STAT_NORM], out[QB_STAT_SUMSQ], out[QB_STAT_NBAD] = a[0], a[1], a[2]
-        out[QB_STAT_INV_NORM], out[QB_STAT_NESS], out[QB_STAT_TAG], out[QB_STAT_SKIPPED] = a[4], a[5], a[6], a[7]
-        return out
 
     def pending_min_weight(self, slot):
         """Smallest weight of weights buffer ``slot``, for the warning text of smc.py:417."""

@@ -20,7 +20,9 @@ import numpy as np
 import torch
 
 from ._exceptions import ApproximationWarning, ResamplerWarning
-from ._lib import QB_STAT_NBAD, QB_STAT_NESS, QB_STAT_NORM, QB_STAT_SKIPPED, QB_STAT_SUMSQ, QbExpparams
+import ctypes
+
+from ._lib import QB_MAX_FUSE, QB_STAT_NORM, QB_STAT_SUMSQ, QbExpparams
 from .distributions import covariance_from_moments
 from .engine import DeviceCloud
 from .models import describe_model
@@ -32,7 +34,7 @@ _EPS = np.spacing(1)
 class SMCUpdater(object):
     def __init__(self, model, n_particles, prior, resample_a=None, resampler=None, resample_thresh=0.5,
                  debug_resampling=False, track_resampling_divergence=False, zero_weight_policy='error',
-                 zero_weight_thresh=None, canonicalize=True, device=None, lazy=False):
+                 zero_weight_thresh=None, canonicalize=True, device=None, lazy=False, fuse=None):
         if track_resampling_divergence:
             raise NotImplementedError("track_resampling_divergence is outside the B200 hot path (SURVEY §2 1b)")
         self._desc = describe_model(model)        # raises UnsupportedModelError: no CPU fallback
@@ -68,10 +70,14 @@ class SMCUpdater(object):
         # warnings, zero-weight policy, resample trigger) runs when the next call needs it, and the next
         # update is launched speculatively behind it (it cancels itself on the device if the step turns out
         # to need the host).  lazy=False (default) keeps the reference's call-by-call semantics exactly.
+        # With lazy=True consecutive updates are additionally FUSED: up to ``fuse`` (default QB_MAX_FUSE = 8, 1 for
+        # tomography) buffered updates go out as one kernel launch that reads and writes the cloud once.
         self._lazy = bool(lazy)
-        self._pending = None
-        self._eps = [QbExpparams(), QbExpparams()]
-        self._ep_idx = 0
+        fuse_cap = 1 if self._desc.kind == 3 else QB_MAX_FUSE
+        self._fuse = fuse_cap if fuse is None else max(1, min(int(fuse), fuse_cap))
+        self._settling = False
+        self._queue = []            # buffered, not yet launched: (ep_record, outcome, check_for_resample)
+        self._pending = None        # launched, not yet settled: (tag, [steps])
         self.reset(n_particles)
 
     # ---- bookkeeping properties (smc.py:182-259) ----------------------------------
@@ -196,7 +202,7 @@ class SMCUpdater(object):
     def reset(self, n_particles=None, only_params=None, reset_weights=True):
         if n_particles is not None and only_params is not None:
             raise ValueError("Cannot set both n_particles and only_params.")
-        if self._cloud is not None and not getattr(self, '_in_finalize', False):
+        if self._cloud is not None:
             self._flush()
         if n_particles is None:
             n_particles = self._cloud.n
@@ -249,118 +255,176 @@ class SMCUpdater(object):
         return out[0] if len(out) == 1 else out
 
     def update(self, outcome, expparams, check_for_resample=True):
-        """smc.py:388-457.  One fused kernel launch; with ``lazy=False`` the call returns after the
-        step's bookkeeping exactly like the reference, with ``lazy=True`` it returns once the kernel is queued."""
-        cloud = self._cloud
+        """smc.py:388-457.  With ``lazy=False`` the call returns after the step's bookkeeping exactly like the
+        reference; with ``lazy=True`` it only buffers the datum (launching a fused kernel every ``fuse`` updates)."""
         self._data_record.append(outcome)
-        self._ep_idx ^= 1
-        ep = self._desc.fill_record(self._eps[self._ep_idx], expparams, 0)
-        outcome = int(outcome)
-        prev = self._pending
-        if prev is None:
-            tag = cloud.fused_update(ep, outcome, cloud.cur)
-        else:
-            # speculative: queue this update behind the pending one.  It reads the pending step's output
-            # buffers and cancels itself on the device if that step needs the host (clip, zero-weight
-            # policy, resample) — the same test the host applies when it settles the pending step next.
-            tag = cloud.fused_update(ep, outcome, 1 - cloud.cur, guard=True, guard_resample=prev[2],
-                                     zero_weight_thresh=self._zero_weight_thresh,
-                                     resample_below=self.n_particles * self.resample_thresh)
-            self._pending = None
-            plain = self._finalize(prev)                # may warn / raise / resample, like the reference
-            cloud = self._cloud
-            if not plain:                               # the speculative launch cancelled itself: redo it
-                tag = cloud.fused_update(ep, outcome, cloud.cur)
-        self._pending = (tag, outcome, bool(check_for_resample), ep)
-        self._count_calls(cloud.n)
-        self._just_resampled = False
+        self._enqueue(outcome, expparams, check_for_resample)
         if not self._lazy:
             self._flush()
+        elif len(self._queue) >= self._fuse:
+            self._launch_queue()
+
+    def _enqueue(self, outcome, expparams, check_for_resample):
+        ep = self._desc.fill_record(QbExpparams(), expparams, 0)
+        self._queue.append((ep, int(outcome), bool(check_for_resample)))
+        self._count_calls(self._cloud.n)
+        if self._pending is None and len(self._queue) == 1:
+            self._just_resampled = False         # nothing in flight: new data has arrived since the last resample
+
+    def _launch_queue(self):
+        """Launch the buffered updates, at most ``fuse`` per kernel, each launch speculatively behind the pending one."""
+        while self._queue:
+            cloud = self._cloud
+            steps, self._queue = self._queue[:self._fuse], self._queue[self._fuse:]
+            prev = self._pending
+            if prev is None:
+                tag = cloud.fused_update(steps, cloud.cur, zero_weight_thresh=self._zero_weight_thresh,
+                                         resample_below=self.n_particles * self.resample_thresh)
+                self._pending = (tag, steps)
+                continue
+            # speculative: queue this launch behind the pending one.  It reads the pending launch's output buffers
+            # and cancels itself on the device if that launch needs the host (clip, zero-weight policy, resample).
+            tag = cloud.fused_update(steps, 1 - cloud.cur, guard=True, zero_weight_thresh=self._zero_weight_thresh,
+                                     resample_below=self.n_particles * self.resample_thresh)
+            self._queue = steps + self._queue           # provisional: they only count if `prev` was plain
+            self._pending = None
+            plain = self._finalize(prev)                # may warn / raise / resample, like the reference
+            if plain:
+                self._queue = self._queue[len(steps):]
+                self._pending = (tag, steps)
+            # else: the speculative launch cancelled itself; its steps are still queued, behind whatever steps of
+            # `prev` _finalize put back
 
     def _flush(self):
-        """Settle the pending update, if any (records, warnings, zero-weight policy, resample trigger)."""
-        if self._pending is not None:
-            prev, self._pending = self._pending, None
-            self._finalize(prev)
+        """Launch and settle everything that is buffered or pending."""
+        if self._settling:          # re-entered from the step being settled (resample(), est_mean(), ...)
+            return
+        while self._queue or self._pending is not None:
+            if self._pending is not None:
+                prev, self._pending = self._pending, None
+                self._finalize(prev)
+            if self._queue:
+                self._launch_queue()
 
     def _finalize(self, pending):
-        """The host half of smc.py:413-457 for one launched update.  Returns True if the step was a plain
-        commit (no clip, no zero-weight event, no resample) — i.e. a speculative successor ran on valid input —
-        and False otherwise (the successor, if any, cancelled itself and must be re-launched)."""
-        tag, outcome, check_for_resample, ep = pending
+        """The host half of smc.py:413-457 for the updates of one launch.  Returns True if every step was a plain
+        commit; otherwise the state is brought to exactly what the reference holds after the step that needed the
+        host (re-issuing the steps before it if necessary), the remaining steps go back to the front of the queue,
+        and False is returned (a speculative successor has cancelled itself)."""
+        self._settling = True
+        try:
+            return self._finalize_locked(pending)
+        finally:
+            self._settling = False
+
+    def _finalize_locked(self, pending):
+        tag, steps = pending
         cloud = self._cloud
         slot = 1 - cloud.cur
-        st = cloud.wait_stats(slot, tag)
-        plain = True
-        if st[QB_STAT_SKIPPED] != 0.0:
-            # a speculative launch that cancelled itself although the host expected it to run (cannot happen
-            # while host and device apply the same test; kept as a safety net): redo it plainly.  Whatever
-            # was queued behind it saw SKIPPED and cancelled itself too.
-            tag = cloud.fused_update(ep, outcome, cloud.cur)
-            st = cloud.wait_stats(slot, tag)
-            plain = False
-        norm, sumsq, ness = float(st[QB_STAT_NORM]), float(st[QB_STAT_SUMSQ]), float(st[QB_STAT_NESS])
-        unnormalised = abs(norm) < _EPS                      # smc.py:369-370: then weights stay as w*L
-        total = norm if unnormalised else 1.0                # np.sum of the normalised weights
-        norm_rec = norm
+        k = len(steps)
+        blocks = cloud.wait_stats(slot, tag, k)
+        zt = self._zero_weight_thresh
+        below = self.n_particles * self.resample_thresh
+        if blocks[0][7] >= 2.0:
+            # a speculative launch that cancelled itself although the host expected it to run (cannot happen while
+            # host and device apply the same tests; kept as a safety net): run it again, plainly
+            self._queue = steps + self._queue
+            return False
+        for j in range(k):
+            S, Q, nbad, _, rec, ness, _, flag = blocks[j]
+            ep, outcome, check = steps[j]
+            self._just_resampled = False                 # smc.py:410, at the point this datum is accounted for
+            if flag == 0.0:
+                # plain step: the bookkeeping of smc.py:441-457, nothing else
+                self._normalization_record.append(float(rec))
+                self._n_ess = float(ness)
+                if self._n_ess <= self._min_n_ess:
+                    self._min_n_ess = self._n_ess
+                if check and ness <= 10:
+                    warnings.warn("Extremely small n_ess encountered ({}). Resampling is likely to fail. Consider "
+                                  "adding particles, or resampling more often.".format(ness), ApproximationWarning)
+                continue
+            # ---- step j needs the host ------------------------------------------------------------------------
+            self._queue = steps[j + 1:] + self._queue
+            unnormalised = abs(rec) < _EPS               # smc.py:369-370: then the weights stay as w*L
+            total = float(rec) if unnormalised else 1.0  # np.sum of the normalised weights
+            rejected = (nbad == 0 and total <= zt and self._zero_weight_policy in ('skip', 'error'))
+            keep = j if rejected else j + 1              # how many steps of this launch the cloud must reflect
+            if keep < k:
+                if keep > 0:
+                    t2 = cloud.fused_update(steps[:keep], cloud.cur, zero_weight_thresh=zt, resample_below=below)
+                    cloud.wait_stats(slot, t2, keep)
+            if rejected:
+                if keep > 0:
+                    cloud.commit_update()
+                    self._host_weights = None
+                if self._zero_weight_policy == 'error':
+                    raise RuntimeError("All particle weights are zero.")
+                return False                             # 'skip': smc.py:427-428
+            self._settle_step(slot, float(S), float(Q), float(nbad), float(rec), float(ness), check)
+            return False
+        cloud.commit_update()                            # smc.py:441 for the whole launch
+        self._host_weights = None
+        return True
 
-        if st[QB_STAT_NBAD] > 0:                             # smc.py:416-418
-            plain = False
+    def _settle_step(self, slot, S, Q, nbad, rec, ness, check):
+        """smc.py:416-457 for a step that needs the host; the pending buffers hold the weights after that step."""
+        cloud = self._cloud
+        unnormalised = abs(rec) < _EPS
+        total = rec if unnormalised else 1.0
+        norm_rec = rec
+        if nbad > 0:                                         # smc.py:416-418
             smallest = cloud.pending_min_weight(slot)
-            smallest = smallest if unnormalised else smallest / norm
+            smallest = smallest if unnormalised else smallest / S
             warnings.warn("Negative weights occured in particle approximation. Smallest weight observed == {}. "
                           "Clipping weights.".format(smallest), ApproximationWarning)
             st2 = cloud.clip_weights(slot)
             total = float(st2[QB_STAT_NORM])
-            norm, sumsq, unnormalised = total, float(st2[QB_STAT_SUMSQ]), True
-            ness = self._ness_from(norm, sumsq, normalised=True)
-
+            ness = self._ness_from(total, float(st2[QB_STAT_SUMSQ]), normalised=True)
         if total <= self._zero_weight_thresh:                # smc.py:423-436 (a NaN total passes, as in the reference)
-            plain = False
             policy = self._zero_weight_policy
             if policy == 'ignore':
                 pass
-            elif policy == 'skip':
-                return False
             elif policy == 'warn':
                 warnings.warn("All particle weights are zero. This will very likely fail quite badly.",
                               ApproximationWarning)
-            elif policy == 'error':
-                raise RuntimeError("All particle weights are zero.")
             elif policy == 'reset':
                 warnings.warn("All particle weights are zero. Resetting from initial prior.", ApproximationWarning)
-                self._in_finalize = True
-                try:
-                    self.reset()
-                finally:
-                    self._in_finalize = False
+                self.reset()
                 cloud = self._cloud
+            elif policy in ('skip', 'error'):                # only reachable after a clip
+                if policy == 'error':
+                    raise RuntimeError("All particle weights are zero.")
+                return
             else:
                 raise ValueError("Invalid zero-weight policy {} encountered.".format(policy))
             with np.errstate(divide='ignore', invalid='ignore'):
-                ness = self._ness_from(norm, sumsq, normalised=unnormalised)
-
+                ness = self._ness_from(S, Q, normalised=unnormalised) if nbad == 0 else ness
         cloud.commit_update()                                # smc.py:441
         self._host_weights = None
         self._normalization_record.append(norm_rec)          # smc.py:444
         self._n_ess = ness
         if self._n_ess <= self._min_n_ess:                   # smc.py:452-453
             self._min_n_ess = self._n_ess
-        if check_for_resample:
-            if self._maybe_resample():
-                plain = False
-        return plain
+        if check:
+            self._maybe_resample()
 
     def batch_update(self, outcomes, expparams, resample_interval=5):
+        """smc.py:459-487.  The reference loops ``update(check_for_resample=False)`` and calls ``_maybe_resample``
+        after every ``resample_interval``-th datum; here the same sequence is buffered and goes out as fused
+        launches (up to QB_MAX_FUSE updates each, the cloud is read and written once per launch), then settled."""
         n_exps = outcomes.shape[0]
         if expparams.shape[0] != n_exps:
             raise ValueError("The number of outcomes and experiments must match.")
         if len(expparams.shape) == 1:
             expparams = expparams[:, None]
+        self._flush()
         for idx_exp, (outcome, experiment) in enumerate(zip(iter(outcomes), iter(expparams))):
-            self.update(outcome, experiment, check_for_resample=False)
-            if (idx_exp + 1) % resample_interval == 0:
-                self._maybe_resample()
+            self._data_record.append(outcome)
+            self._enqueue(outcome, experiment, (idx_exp + 1) % resample_interval == 0)
+            if len(self._queue) >= self._fuse:
+                self._launch_queue()
+        self._flush()
 
     # ---- resampling (smc.py:263-277, 491-551) --------------------------------------------
     def _maybe_resample(self):

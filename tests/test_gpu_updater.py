@@ -243,28 +243,84 @@ def test_reset_and_setters(qb):
                           resampler=qb.LiuWestResampler())
 
 
+def _run_modes(qb, model_factory, n, x, steps, modes, seed=3):
+    """Run the same update sequence under several (lazy, fuse) modes; return the end states."""
+    out = []
+    for lazy, fuse in modes:
+        np.random.seed(seed)
+        up = qb.SMCUpdater(model_factory(), n, cases.FixedPrior(x), lazy=lazy, fuse=fuse)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for outcome, ep, chk in steps:
+                up.update(outcome, ep, check_for_resample=chk)
+        out.append(dict(rc=up.resample_count, rec=np.array(up.normalization_record), w=up.particle_weights.copy(),
+                        x=up.particle_locations.copy(), min_ess=up.min_n_ess, ess=up.n_ess,
+                        launches=up._cloud.update_launches))
+    return out
+
+
 def test_lazy_pipelining_is_bit_identical_to_eager(qb):
-    """lazy=True launches update k+1 speculatively behind update k (device-side guard); the trajectory,
+    """lazy=True, fuse=1 launches update k+1 speculatively behind update k (device-side guard); the trajectory,
     records, resample count and final cloud must equal the call-by-call (reference-semantics) run exactly."""
     n = 50000
     rs = np.random.RandomState(8)
     x = rs.random_sample((n, 1))
     ts = (9.0 / 8.0) ** np.arange(70)
     outcomes = (rs.random_sample(70) >= np.cos(ts * 0.5 / 2) ** 2).astype(int)
+    steps = [(int(outcomes[k]), ts[k:k + 1], (k % 7 != 3)) for k in range(70)]
+    a, b = _run_modes(qb, qb.SimplePrecessionModel, n, x, steps, [(False, None), (True, 1)])
+    assert a["rc"] == b["rc"] and a["rc"] >= 3
+    assert np.array_equal(a["rec"], b["rec"]) and np.array_equal(a["w"], b["w"]) and np.array_equal(a["x"], b["x"])
+    assert a["min_ess"] == b["min_ess"] and a["ess"] == b["ess"]
+
+
+@pytest.mark.parametrize("fuse", [2, 5, 8])
+def test_fused_updates_match_one_by_one(qb, fuse):
+    """K consecutive updates in one launch: same resample decisions at the same steps, records
+    and weights equal to the one-by-one path up to the omitted intermediate renormalisation (a few ulp);
+    a mid-batch resample trigger rolls the batch back to the triggering step."""
+    n = 40000
+    rs = np.random.RandomState(21)
+    x = rs.random_sample((n, 1))
+    ts = (9.0 / 8.0) ** np.arange(60)
+    outcomes = (rs.random_sample(60) >= np.cos(ts * 0.5 / 2) ** 2).astype(int)
+    steps = [(int(outcomes[k]), ts[k:k + 1], True) for k in range(60)]
+    # resampling draws from the legacy NumPy stream: identical decisions => identical streams => same clouds
+    a, b = _run_modes(qb, qb.SimplePrecessionModel, n, x, steps, [(False, None), (True, fuse)])
+    assert a["rc"] == b["rc"] and a["rc"] >= 3
+    assert b["launches"] < a["launches"]
+    np.testing.assert_allclose(b["rec"], a["rec"], rtol=1e-12)
+    np.testing.assert_allclose(b["x"], a["x"], rtol=1e-9, atol=1e-12)
+    # after several resamples the clouds differ by ~1e-13 relative (moments computed from weights a few ulp
+    # apart); cos^2(t x / 2) with t ~ 1e3 turns that into ~1e-9 on individual weights
+    np.testing.assert_allclose(b["w"], a["w"], rtol=1e-6, atol=1e-12 * a["w"].max())
+    assert b["min_ess"] == pytest.approx(a["min_ess"], rel=1e-11) and b["ess"] == pytest.approx(a["ess"], rel=1e-11)
+
+
+def test_fused_batch_update_rb(qb):
+    """batch_update(resample_interval) through fused launches vs the oracle's loop (RB o Binomial, d = 3)."""
+    import smc_oracle as o
+    n = 3000
+    inp = cases.rb_inputs(n_particles=n, n_updates=40, seed=77)
     res = []
-    for lazy in (False, True):
-        np.random.seed(3)
-        up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), lazy=lazy)
+    for ns in (qb, o):
+        model = ns.BinomialModel(ns.RandomizedBenchmarkingModel())
+        np.random.seed(1)
+        up = ns.SMCUpdater(model, n, cases.FixedPrior(inp['prior']))
+        eps = np.empty((40,), dtype=model.expparams_dtype)
+        eps['m'] = inp['ms']
+        eps['n_meas'] = inp['n_meas']
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            for k in range(70):
-                up.update(int(outcomes[k]), ts[k:k + 1], check_for_resample=(k % 7 != 3))
-        res.append((up.resample_count, np.array(up.normalization_record), up.particle_weights.copy(),
-                    up.particle_locations.copy(), up.min_n_ess, up.n_ess))
-    a, b = res
-    assert a[0] == b[0] and a[0] >= 3
-    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
-    assert a[4] == b[4] and a[5] == b[5]
+            up.batch_update(inp['counts'], eps, resample_interval=5)
+        res.append((up.resample_count, np.array([float(np.ravel(v)[0]) for v in up.normalization_record]),
+                    up.est_mean(), up.est_covariance_mtx(), up.min_n_ess))
+    (rc_g, rec_g, m_g, c_g, e_g), (rc_o, rec_o, m_o, c_o, e_o) = res
+    assert rc_g == rc_o
+    np.testing.assert_allclose(rec_g, rec_o, rtol=1e-9)
+    np.testing.assert_allclose(m_g, m_o, rtol=1e-6)
+    np.testing.assert_allclose(c_g, c_o, rtol=1e-5, atol=1e-12)
+    assert e_g == pytest.approx(e_o, rel=1e-8)
 
 
 @pytest.mark.parametrize("policy", ["skip", "error", "warn"])

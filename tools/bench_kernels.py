@@ -27,7 +27,7 @@ def timed(fn, reps=50, warm=5):
     return e0.elapsed_time(e1) / reps * 1e3   # us
 
 
-def bench_update(n, model, ep_setup, d, label):
+def bench_update(n, model, ep_setup, d, label, fuse_list=(1,)):
     desc = qb.describe_model(model)
     cloud = DeviceCloud(desc, n)
     rs = np.random.RandomState(0)
@@ -43,12 +43,16 @@ def bench_update(n, model, ep_setup, d, label):
     outcome = ep_setup(ep)
     state = {"src": 0}
 
-    def step():
-        cloud.fused_update(ep, outcome, state["src"])
-        state["src"] ^= 1
-    us = timed(step, reps=100)
-    gb = 8.0 * (d + 2) * n / (us * 1e-6) / 1e9
-    print("%-28s n=%d  %8.1f us/launch  %7.1f GB/s algorithmic  (%.1f%% of 6540)" % (label, n, us, gb, gb / 65.40))
+    for k in fuse_list:
+        steps = [(ep, outcome, False)] * k
+
+        def step():
+            cloud.fused_update(steps, state["src"])
+            state["src"] ^= 1
+        us = timed(step, reps=100)
+        gb = 8.0 * (d + 2) * n / (us * 1e-6) / 1e9
+        print("%-28s n=%d K=%d %8.1f us/launch %7.1f us/update %7.1f GB/s per launch (%.1f%% of 6540)  %.3g pu/s"
+              % (label, n, k, us, us / k, gb, gb / 65.40, n * k / (us * 1e-6)))
 
 
 def main():
@@ -58,13 +62,13 @@ def main():
         def prec(ep):
             ep.t = 17.3
             return 1
-        bench_update(n, qb.SimplePrecessionModel(), prec, 1, "update precession d=1")
+        bench_update(n, qb.SimplePrecessionModel(), prec, 1, "update precession d=1", (1, 2, 4, 8))
 
         def rbb(ep):
             ep.m = 37
             ep.n_meas = 25
             return 12
-        bench_update(n // 4, qb.BinomialModel(qb.RandomizedBenchmarkingModel()), rbb, 3, "update binomial(RB) d=3")
+        bench_update(n // 4, qb.BinomialModel(qb.RandomizedBenchmarkingModel()), rbb, 3, "update binomial(RB) d=3", (1, 8))
 
         def rb(ep):
             ep.m = 37
