@@ -198,6 +198,9 @@ size_t qb_cdf_workspace_bytes(int64_t n);
 /* d_cdf[i] = cumsum of normalised weights (resamplers.py:308). */
 int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode,
            void* d_ws, size_t ws_bytes, void* stream);
+/* Diagnostics (synchronises): *h_flag = 1 if the last QB_SCAN_EXACT call on this workspace met weights outside
+ * the parallel replay's model (negative, NaN, inf) or timed out and re-did the scan with the sequential kernel. */
+int qb_cdf_exact_fallback_flag(const void* d_ws, int64_t n, int32_t* h_flag, void* stream);
 /* d_js[i] = min(searchsorted(cdf, u[i], side='right'), n-1) (resamplers.py:318-321;
  * the clamp is distributions.py:330-333's — the reference's resampler raises
  * IndexError where the clamp acts).  *d_overflow counts clamped draws.  With a workspace of

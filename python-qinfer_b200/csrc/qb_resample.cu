@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) cdf_scan_tiles_kernel(double* ti
         tile_sums[i] = run;
         run += v;
     }
+    if (threadIdx.x == 0) tile_sums[ntiles] = total;  // ntiles + 1 entries: the exclusive prefix and the total
 }
 
 // pass 3: per-tile inclusive scan + tile offset
@@ -457,11 +458,30 @@ static int upload_consts(const double* h_mean, const double* h_S, double a, int 
 
 }  // namespace qb
 
+namespace qb {
+size_t exact_scan_workspace_bytes(int64_t n);  // qb_scan_exact.cu
+int launch_exact_scan(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, const double* tile_prefix,
+                      void* d_ws, cudaStream_t st);
+constexpr int64_t EXACT_PARALLEL_MIN = 1 << 15;  // below this the one-lane sequential replay is fast enough
+
+static size_t cdf_tiles_bytes(int64_t n) {
+    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return ((static_cast<size_t>(ntiles + 2) * sizeof(double) + 255) / 256) * 256;
+}
+}  // namespace qb
+
 using namespace qb;
 
 extern "C" size_t qb_cdf_workspace_bytes(int64_t n) {
-    const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    return static_cast<size_t>(ntiles + 1) * sizeof(double) + 256;
+    return 256 + cdf_tiles_bytes(n) + exact_scan_workspace_bytes(n);
+}
+
+extern "C" int qb_cdf_exact_fallback_flag(const void* d_ws, int64_t n, int32_t* h_flag, void* stream) {
+    QB_REQUIRE(d_ws && h_flag && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_cdf_exact_fallback_flag: bad arguments");
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(d_ws) + 256 + cdf_tiles_bytes(n);
+    QB_CUDA_CHECK(cudaMemcpyAsync(h_flag, base + 64, sizeof(int32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    QB_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));
+    return QB_OK;
 }
 
 extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode, void* d_ws,
@@ -469,12 +489,12 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
     QB_REQUIRE(d_w && d_stats && d_cdf && d_ws && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_cdf: bad arguments");
     QB_REQUIRE(ws_bytes >= qb_cdf_workspace_bytes(n), QB_ERR_WORKSPACE, "qb_cdf: workspace too small");
     cudaStream_t st = as_stream(stream);
-    if (mode == QB_SCAN_EXACT) {
+    if (mode == QB_SCAN_EXACT && n < EXACT_PARALLEL_MIN) {
         cdf_sequential_kernel<<<1, 64, 0, st>>>(d_w, d_stats, n, d_cdf);
         QB_CUDA_CHECK(cudaGetLastError());
         return QB_OK;
     }
-    QB_REQUIRE(mode == QB_SCAN_FAST, QB_ERR_INVALID_ARGUMENT, "qb_cdf: unknown mode %d", mode);
+    QB_REQUIRE(mode == QB_SCAN_FAST || mode == QB_SCAN_EXACT, QB_ERR_INVALID_ARGUMENT, "qb_cdf: unknown mode %d", mode);
     double* tiles = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);  // [0,256) is the update ticket
     const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     const int grid = capped_grid(ntiles, 8);
@@ -482,6 +502,11 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
     QB_CUDA_CHECK(cudaGetLastError());
     cdf_scan_tiles_kernel<<<1, SCAN_THREADS, 0, st>>>(tiles, ntiles);
     QB_CUDA_CHECK(cudaGetLastError());
+    if (mode == QB_SCAN_EXACT) {
+        // the approximate tile prefix predicts the binade of every segment; the exact values come from the replay scan
+        return launch_exact_scan(d_w, d_stats, n, d_cdf, tiles,
+                                 reinterpret_cast<unsigned char*>(d_ws) + 256 + cdf_tiles_bytes(n), st);
+    }
     cdf_write_kernel<<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles, d_cdf);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;

@@ -238,6 +238,12 @@ class DeviceCloud(object):
         self.launches += 1 if mode == _lib.QB_SCAN_EXACT else 3
         return self._cdf
 
+    def exact_scan_fell_back(self):
+        """Diagnostics: did the last exact scan hand over to the sequential kernel? (synchronises)"""
+        flag = ctypes.c_int32(-1)
+        check(self.lib.qb_cdf_exact_fallback_flag(_ptr(self.ws), self.n, ctypes.byref(flag), _stream()))
+        return int(flag.value)
+
     def draw(self, u_dev, n_new):
         check(self.lib.qb_draw(_ptr(self._cdf), self.n, _ptr(u_dev), int(n_new), _ptr(self._js),
                                _ptr(self.counter[1:]), _ptr(self.ws), self.ws_bytes, _stream()))

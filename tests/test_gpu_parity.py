@@ -226,6 +226,8 @@ def _draw_on_gpu(qb, w, u, scan):
     cloud.upload_weights(w)
     cloud._resample_scratch(u.shape[0])
     cdf = cloud.cdf(_lib.QB_SCAN_EXACT if scan == 'exact' else _lib.QB_SCAN_FAST)
+    if scan == 'exact' and n >= 32768:
+        _draw_on_gpu.fell_back = cloud.exact_scan_fell_back()
     cloud._u.copy_(torch.from_numpy(u))
     js = cloud.draw(cloud._u, u.shape[0])
     n_bad, overflow = cloud.read_counter()
@@ -257,6 +259,64 @@ def test_t4_exact_scan_and_draw_bit_identical(qb, name):
     want = want_cdf.searchsorted(u, side='right')
     assert overflow == int(np.sum(want >= w.shape[0]))
     assert np.array_equal(js, np.minimum(want, w.shape[0] - 1))
+
+
+def _big_weight_cases():
+    rs = np.random.RandomState(7)
+    out = {}
+    w = rs.random_sample(32768 + 5); out["random_33k"] = w / w.sum()
+    w = rs.random_sample(10 ** 6 + 3) ** 6; out["skewed_1m"] = w / w.sum()
+    w = rs.random_sample(3 * 10 ** 6); w[rs.random_sample(w.size) < 0.7] = 0.0; out["zeros_3m"] = w / w.sum()
+    out["ties_1m"] = np.full(2 ** 20, 2.0 ** -20)                    # every partial sum exact
+    w = np.full(2 ** 20 + 17, 1.0 / 3.0); out["ties_third"] = w / w.sum()   # identical weights: many exact ties
+    w = np.zeros(500000); w[400000:] = rs.random_sample(100000); out["leading_zeros"] = w / w.sum()
+    w = np.full(300000, 1e-312); w[123456] = 1.0; w[250000] = 0.5; out["denormals_and_jumps"] = w
+    w = np.exp(-0.5 * ((np.arange(10 ** 7) - 6e6) / 3e5) ** 2) + 1e-40; out["gaussian_10m"] = w / w.sum()
+    w = rs.random_sample(10 ** 7); out["random_10m"] = w / w.sum()
+    w = 2.0 ** -rs.randint(1, 60, size=200000).astype(float); out["powers_of_two"] = w / 1.0
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_big_weight_cases().keys()))
+def test_t4_parallel_exact_scan_bit_identical(qb, name):
+    """The binade-integer replay scan (n >= 32768) equals np.cumsum bit for bit, and so do the drawn indices."""
+    w = _big_weight_cases()[name]
+    rs = np.random.RandomState(len(name) + 1)
+    u = rs.random_sample(min(w.shape[0], 10 ** 6)) * min(1.0, float(np.sum(w)))
+    cdf, js, overflow = _draw_on_gpu(qb, w, u, 'exact')
+    want_cdf = np.cumsum(w)
+    nbad = int(np.sum(cdf != want_cdf))
+    assert nbad == 0, "%d of %d CDF entries differ from np.cumsum (first at %d)" % (
+        nbad, w.size, int(np.argmax(cdf != want_cdf)))
+    assert _draw_on_gpu.fell_back == 0, "the parallel replay scan handed over to the sequential kernel"
+    want = want_cdf.searchsorted(u, side='right')
+    assert np.array_equal(js, np.minimum(want, w.shape[0] - 1))
+
+
+def test_t4_exact_scan_falls_back_on_negative_weights(qb):
+    """Weights outside the replay's model (negative) are detected and the sequential kernel takes over."""
+    rs = np.random.RandomState(2)
+    w = rs.random_sample(70000) / 70000
+    w[12345] = -1e-6
+    cdf, js, _ = _draw_on_gpu(qb, w, rs.random_sample(1000) * 0.9, 'exact')
+    assert _draw_on_gpu.fell_back == 1
+    assert np.array_equal(cdf, np.cumsum(w))
+
+
+def test_t4_exact_scan_with_lazy_normalisation(qb):
+    """The scan runs on w[i] * inv_norm (the deferred normalisation), like the updater uses it."""
+    from qinfer_b200 import _lib
+    n = 400000
+    rs = np.random.RandomState(3)
+    x = rs.random_sample((n, 1))
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), resample_thresh=0.0)
+    for k in range(5):
+        up.update(k % 2, np.array([1.7 ** k]))
+    w = up.particle_weights                       # normalised weights as the host sees them (w * inv_norm)
+    cloud = up._cloud
+    cloud._resample_scratch(n)
+    cdf = cloud.cdf(_lib.QB_SCAN_EXACT).cpu().numpy()
+    assert np.array_equal(cdf, np.cumsum(w))
 
 
 def test_t4_draw_edges(qb):

@@ -96,8 +96,8 @@ def main():
             print("--- resample kernels d=%d n=%d" % (d, nn))
             print("  moments      %8.1f us" % timed(lambda: cloud.lib.qb_moments(_ptr(cloud.x), _ptr(cloud.w), _ptr(cloud.stats), nn, d, _ptr(cloud.moments_out), _ptr(cloud.ws), cloud.ws_bytes, _stream()), 20))
             print("  cdf fast     %8.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_FAST), 20))
-            if nn <= 2 * 10 ** 6:
-                print("  cdf exact    %8.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_EXACT), 3, 1))
+            print("  cdf exact    %8.1f us  (fell back: %d)" % (timed(lambda: cloud.cdf(_lib.QB_SCAN_EXACT), 10, 2),
+                                                            cloud.exact_scan_fell_back()))
             cloud.rng_uniform(cloud._u, nn, 1, 0)
             print("  rng uniform  %8.1f us" % timed(lambda: cloud.rng_uniform(cloud._u, nn, 1, 0), 20))
             print("  rng normal   %8.1f us" % timed(lambda: cloud.rng_normal(cloud._eps, nn * d, 1, 0), 20))
