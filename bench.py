@@ -237,13 +237,20 @@ def gpu_arm(args, rank, world, local_rank):
         warnings.simplefilter("ignore")
         # process warm-up (not a step of the workload): run a small cloud through updates AND resamples once so that
         # every kernel of the path is loaded (CUDA loads modules lazily at first launch) before anything is timed
+        nsmall = 65536
         if world == 1:
-            small = qb.SMCUpdater(qb.SimplePrecessionModel(), 65536, FixedPrior(prior[:65536]), lazy=True,
+            small = qb.SMCUpdater(qb.SimplePrecessionModel(), nsmall, FixedPrior(prior[:nsmall]), lazy=True,
                                   resampler=qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast'))
-            for k in range(30):
-                small.update(int(outcomes[k]), ts[k:k + 1])
-            small.est_mean()
-            del small
+        else:
+            from qinfer_b200.sharded import ShardedSMCUpdater
+            small = ShardedSMCUpdater(qb.SimplePrecessionModel(), nsmall * world, FixedPrior(prior[:nsmall]), lazy=True,
+                                      resampler=qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast'))
+        for k in range(30):
+            small.update(int(outcomes[k]), ts[k:k + 1])
+        small.est_mean()
+        if world > 1:
+            small.close()
+        del small
         # ---------------- value: state resident in HBM ----------------
         up = new_updater()
         for k in range(warm):
@@ -274,7 +281,8 @@ def gpu_arm(args, rank, world, local_rank):
         # average fused-update launch: the timed region minus the resamples (event pairs around each), over K launches.
         # Per-launch event pairs are avoided on purpose: an event between two launches breaks their programmatic
         # dependent-launch overlap.  Gaps between kernels are therefore charged to the kernel (conservative).
-        resample_ms = float(sum(a.elapsed_time(b) for a, b in up._cloud.resample_events))
+        resample_events = list(up._cloud.resample_events)
+        resample_ms = float(sum(a.elapsed_time(b) for a, b in resample_events))
         kern_ms = (elapsed_ms - resample_ms) / max(upd_launches, 1)
         posterior_mean = float(up.est_mean()[0])
 
@@ -353,7 +361,8 @@ def gpu_arm(args, rank, world, local_rank):
                          "peak_source": peak_src, "bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms,
                          "how": "(timed region - sum of event-timed resamples) / fused-update launches",
                          "update_launches": upd_launches, "updates_per_launch": steps / max(upd_launches, 1),
-                         "resample_ms_total": resample_ms},
+                         "resample_ms_total": resample_ms,
+                         "resample_ms_each": [round(a.elapsed_time(b), 3) for a, b in resample_events]},
             "clocks": clocks, "posterior_mean": posterior_mean,
         }
         if fused is not None:

@@ -58,29 +58,29 @@ struct UpdateParams {
 
 struct Acc {
     double s, q;
-    unsigned int bad;
 };
 
-__device__ __forceinline__ void accumulate(Acc& a, double wv) {
+// bit k of `bad` is set if step k produced a negative or NaN weight (smc.py:416 only asks "not all >= 0")
+__device__ __forceinline__ void accumulate(Acc& a, unsigned int& bad, int k, double wv) {
     a.s += wv;
     a.q = fma(wv, wv, a.q);
-    a.bad += (wv >= 0.0) ? 0u : 1u;  // counts negatives and NaNs (smc.py:416)
+    bad |= (wv >= 0.0) ? 0u : (1u << k);
 }
 
 // Block reduction of KF (s, q, bad) triples into out[3*j..3*j+2] (shared memory).
 template <int KF>
-__device__ __forceinline__ void block_reduce_steps(const Acc (&a)[KF], double* red, double* out) {
+__device__ __forceinline__ void block_reduce_steps(const Acc (&a)[KF], unsigned int bad, double* red, double* out) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
+    const unsigned int wbad = __reduce_or_sync(0xffffffffu, bad);
 #pragma unroll
     for (int j = 0; j < KF; ++j) {
         const double s = warp_sum(a[j].s);
         const double q = warp_sum(a[j].q);
-        const unsigned int b = __reduce_add_sync(0xffffffffu, a[j].bad);
         if (lane == 0) {
             red[(wid * KF + j) * 3 + 0] = s;
             red[(wid * KF + j) * 3 + 1] = q;
-            red[(wid * KF + j) * 3 + 2] = static_cast<double>(b);
+            red[(wid * KF + j) * 3 + 2] = ((wbad >> j) & 1u) ? 1.0 : 0.0;  // summed: > 0 iff any warp saw one
         }
     }
     __syncthreads();
@@ -203,7 +203,7 @@ __device__ void peer_allreduce(const UpdateParams& p, double* sums, double* scra
 // empty[s] (count NCW): one arrive per consumer warp                        -> producer may refill stage s
 // No CTA-wide barrier in the tile loop: warps drift freely across the ring.
 template <int KIND, bool BINOM, int DT, int KF>
-__global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __grid_constant__ UpdateParams p) {
+__global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_kernel(const __grid_constant__ UpdateParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TILE_CT = (DT == 1) ? 1024 : 512;  // must match choose_tile()
     constexpr int NCT = UPD_CONSUMER_WARPS * 32;     // consumer threads
@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __gr
     __syncthreads();
 
     Acc acc[KF];
+    unsigned int bad = 0u;
 #pragma unroll
-    for (int j = 0; j < KF; ++j) acc[j] = {0.0, 0.0, 0u};
+    for (int j = 0; j < KF; ++j) acc[j] = {0.0, 0.0};
     const int64_t tile_stride = static_cast<int64_t>(gridDim.x) * tile;
 
     if (tid >= NCT) {
@@ -330,8 +331,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __gr
                             if (KF == 1 || k < nsteps) {
                                 w0 = w0 * model_likelihood<KIND, BINOM>(mv, p.ev[k], row0, meas, 0);  // smc.py:354
                                 w1 = w1 * model_likelihood<KIND, BINOM>(mv, p.ev[k], row1, meas, 0);
-                                accumulate(acc[k], w0);
-                                accumulate(acc[k], w1);
+                                accumulate(acc[k], bad, k, w0);
+                                accumulate(acc[k], bad, k, w1);
                             }
                         }
                         asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(wo + 2 * j), "d"(w0),
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __gr
                         for (int k = 0; k < KF; ++k) {
                             if (KF == 1 || k < nsteps) {
                                 wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, lane);
-                                accumulate(acc[k], wv);
+                                accumulate(acc[k], bad, k, wv);
                             }
                         }
                         stg_stream(wo + j, wv);
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __gr
                     for (int k = 0; k < KF; ++k) {
                         if (KF == 1 || k < nsteps) {
                             wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, 0);
-                            accumulate(acc[k], wv);
+                            accumulate(acc[k], bad, k, wv);
                         }
                     }
                     wo[j] = wv;
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) fused_update_kernel(const __gr
         }
     }
 
-    block_reduce_steps<KF>(acc, red, sums);
+    block_reduce_steps<KF>(acc, bad, red, sums);
     if (tid < 3 * KF) p.partials[static_cast<size_t>(blockIdx.x) * 3 * KF + tid] = sums[tid];
     __syncthreads();
     if (tid == 0) {
@@ -470,14 +471,15 @@ int validate_model(const qb_model* m) {
     return QB_OK;
 }
 
-static int update_grid_limit(update_kernel_t k, size_t smem) {
+static int update_grid_limit(update_kernel_t k, size_t smem, int nsteps) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, UPD_THREADS, smem) != cudaSuccess) return -1;
     if (per_sm < 1) per_sm = 1;
     // Two CTAs per SM per launch: leaves room for the next (programmatically dependent) launch to become
     // resident while this one runs; measured faster than filling the SM with one launch (r1: 43.6 vs 46.6 us).
-    int cap = 2;
+    // The fused-batch variant is fp64-latency bound instead: it takes every CTA slot it can get.
+    int cap = (nsteps == 1) ? 2 : 8;
     const char* e = getenv("QB_UPD_CTAS_PER_SM");  // experiment knob
     if (e && atoi(e) > 0) cap = atoi(e);
     if (per_sm > cap) per_sm = cap;
@@ -492,12 +494,12 @@ struct GridCacheEntry {
 static GridCacheEntry g_grid_cache[64];
 static int g_grid_cache_n = 0;
 
-static int cached_grid_limit(update_kernel_t k, size_t smem) {
+static int cached_grid_limit(update_kernel_t k, size_t smem, int nsteps) {
     int dev = 0;
     cudaGetDevice(&dev);
     for (int i = 0; i < g_grid_cache_n; ++i)
         if (g_grid_cache[i].k == k && g_grid_cache[i].dev == dev) return g_grid_cache[i].limit;
-    const int limit = update_grid_limit(k, smem);
+    const int limit = update_grid_limit(k, smem, nsteps);
     if (limit > 0 && g_grid_cache_n < 64) g_grid_cache[g_grid_cache_n++] = {k, dev, limit};
     return limit;
 }
@@ -590,7 +592,7 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
 
     update_kernel_t k = pick_update_kernel(*model, nsteps);
     const size_t smem = update_smem_bytes(model->d);
-    const int limit = cached_grid_limit(k, smem);
+    const int limit = cached_grid_limit(k, smem, nsteps);
     QB_REQUIRE(limit > 0, QB_ERR_CUDA, "qb_fused_update: occupancy query failed: %s",
                cudaGetErrorString(cudaGetLastError()));
     const int64_t ntiles = (n + p.tile - 1) / p.tile;
