@@ -39,30 +39,45 @@ __global__ void __launch_bounds__(256) classify_kernel(const double* __restrict_
     if (threadIdx.x < G && hist[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(hist[threadIdx.x]));
 }
 
+// Two-level slot claiming: a block counts its draws per owner in shared memory, claims one contiguous range per
+// owner with ONE global atomic each, and hands out positions inside the range by warp ballot + per-warp offsets.
 __global__ void __launch_bounds__(256) bucket_kernel(const double* __restrict__ u, const int32_t* __restrict__ owner,
                                                      int64_t n, const __grid_constant__ BoundsArg a, int G,
                                                      unsigned long long* __restrict__ cursor,
                                                      double* __restrict__ req, int64_t* __restrict__ perm) {
-    // warp-aggregated slot claiming: one atomic per (warp, owner) instead of one per draw
-    const int lane = threadIdx.x & 31;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t nround = ((n + stride - 1) / stride) * stride;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    __shared__ unsigned int warp_cnt[8][QB_MAX_RANKS];   // per-warp count per owner, then exclusive offsets
+    __shared__ unsigned long long block_base[QB_MAX_RANKS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t per_block = static_cast<int64_t>(blockDim.x);
+    const int64_t ntiles = (n + per_block - 1) / per_block;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t i = t * per_block + threadIdx.x;
         const bool live = i < n;
         const int r = live ? owner[i] : -1;
+        unsigned int my_rank_in_warp = 0;
         for (int g = 0; g < G; ++g) {
             const unsigned int m = __ballot_sync(0xffffffffu, r == g);
-            if (m == 0) continue;
-            const int leader = __ffs(m) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[g], static_cast<unsigned long long>(__popc(m)));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (r == g) {
-                const long long pos = a.start[g] + static_cast<long long>(base) + __popc(m & ((1u << lane) - 1u));
-                req[pos] = u[i] - a.b[g];
-                perm[i] = pos;
-            }
+            if (lane == 0) warp_cnt[wid][g] = __popc(m);
+            if (r == g) my_rank_in_warp = __popc(m & ((1u << lane) - 1u));
         }
+        __syncthreads();
+        if (threadIdx.x < G) {  // exclusive scan over the 8 warps + one global atomic per owner
+            const int g = threadIdx.x;
+            unsigned int run = 0;
+            for (int w = 0; w < 8; ++w) {
+                const unsigned int c = warp_cnt[w][g];
+                warp_cnt[w][g] = run;
+                run += c;
+            }
+            block_base[g] = run ? atomicAdd(&cursor[g], static_cast<unsigned long long>(run)) : 0ULL;
+        }
+        __syncthreads();
+        if (live) {
+            const long long pos = a.start[r] + static_cast<long long>(block_base[r]) + warp_cnt[wid][r] + my_rank_in_warp;
+            req[pos] = u[i] - a.b[r];
+            perm[i] = pos;
+        }
+        __syncthreads();
     }
 }
 

@@ -79,18 +79,20 @@ class ShardComm(object):
         return t
 
     def all_gather_scalars(self, value, device):
-        """[value of rank 0, ..., value of rank G-1] as Python floats."""
+        """[value of rank 0, ..., value of rank G-1] as Python floats (one collective, one host read)."""
         mine = torch.tensor([float(value)], dtype=torch.float64, device=device)
-        out = [torch.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(out, mine, group=self.group)
-        return [float(o.item()) for o in out]
+        out = torch.empty((self.world,), dtype=torch.float64, device=device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return [float(v) for v in out.tolist()]
 
     def exchange_counts(self, send_counts, device):
-        """all-to-all of one int64 per peer: recv[r] = how many items rank r sends me."""
+        """recv[r] = how many items rank r sends me.  One all-gather of the G x G count matrix (a single
+        collective and a single host read) instead of an all-to-all."""
         send = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=device)
-        recv = torch.empty_like(send)
-        self.dist.all_to_all_single(recv, send, group=self.group)
-        return [int(c) for c in recv.tolist()]
+        mat = torch.empty((self.world * self.world,), dtype=torch.int64, device=device)
+        self.dist.all_gather_into_tensor(mat, send, group=self.group)
+        m = mat.tolist()
+        return [int(m[r * self.world + self.rank]) for r in range(self.world)]
 
     def all_to_all_v(self, send, send_counts, recv_counts, width=1):
         """Variable all-to-all of rows of ``width`` elements; ``send`` is bucketed by destination rank."""
@@ -422,15 +424,20 @@ def _make_sharded_updater_class():
                                      res._philox_offset + (goff * d + 1) // 2)
                     if first:
                         cloud.lw_move(mean, S, a, eps, n_local, res._postselect, x_src=rows2d, js=perm)
-                        cloud._js.copy_(perm)                         # the retry kernel indexes the same rows
                     else:
+                        if n_iters == 2:
+                            cloud._js.copy_(perm)                     # the retry kernel indexes the same rows
                         cloud.compact_invalid(n_local)
                         cloud.lw_retry(mean, S, a, eps, k, x_src=rows2d, own_mean=True)
-                    local_invalid, _ = cloud.read_counter()
                 first = False
                 res._philox_offset += (self._n_global * d + 1) // 2 + 1   # every rank advances in lockstep
-                tot = torch.tensor([float(local_invalid)], dtype=torch.float64, device=cloud.device)
-                comm.all_reduce_sum(tot)
+                # one collective + one host read gives every rank its own and the global invalid count
+                mine = cloud.counter[:1] if k > 0 else torch.zeros((1,), dtype=torch.int64, device=cloud.device)
+                allc = torch.empty((comm.world,), dtype=torch.int64, device=cloud.device)
+                comm.dist.all_gather_into_tensor(allc, mine, group=comm.group)
+                counts = allc.tolist()
+                local_invalid = int(counts[comm.rank])
+                tot = torch.tensor([float(sum(counts))])
                 if tot.item() == 0:
                     break
                 if n_iters >= res._maxiter:
