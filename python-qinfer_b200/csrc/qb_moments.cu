@@ -92,21 +92,34 @@ __global__ void __launch_bounds__(MOM_THREADS) moments_d16_kernel(const double* 
     const int64_t nsteps = (n + 3) / 4;
     const int64_t warp_global = static_cast<int64_t>(blockIdx.x) * NW + wid;
     const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * NW;
-    for (int64_t s = warp_global; s < nsteps; s += warp_stride) {
-        const int64_t i = s * 4 + kq;
-        double wi = 0.0, xlo = 0.0, xhi = 0.0;
-        if (i < n) {
-            wi = __ldg(w + i) * inv;
-            xlo = __ldg(x + i * D + mr);
-            xhi = __ldg(x + i * D + 8 + mr);
+    // UNROLL k-steps per iteration with all their loads issued first: one step keeps only 512 B per warp in
+    // flight, far too little to cover HBM latency (r1: 89 us -> the loads, not the DMMAs, were the limit).
+    constexpr int UNROLL = 4;
+    for (int64_t s0 = warp_global * UNROLL; s0 < nsteps; s0 += warp_stride * UNROLL) {
+        double wi[UNROLL], xlo[UNROLL], xhi[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t i = (s0 + u) * 4 + kq;
+            wi[u] = 0.0;
+            xlo[u] = 0.0;
+            xhi[u] = 0.0;
+            if (i < n) {
+                wi[u] = ldg_stream(w + i);
+                xlo[u] = ldg_stream(x + i * D + mr);
+                xhi[u] = ldg_stream(x + i * D + 8 + mr);
+            }
         }
-        const double alo = wi * xlo, ahi = wi * xhi;
-        dmma_m8n8k4(c00a, c00b, alo, xlo);
-        dmma_m8n8k4(c01a, c01b, alo, xhi);
-        dmma_m8n8k4(c11a, c11b, ahi, xhi);
-        mlo += alo;
-        mhi += ahi;
-        sw += wi;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const double wn = wi[u] * inv;
+            const double alo = wn * xlo[u], ahi = wn * xhi[u];
+            dmma_m8n8k4(c00a, c00b, alo, xlo[u]);
+            dmma_m8n8k4(c01a, c01b, alo, xhi[u]);
+            dmma_m8n8k4(c11a, c11b, ahi, xhi[u]);
+            mlo += alo;
+            mhi += ahi;
+            sw += wn;
+        }
     }
     // accumulator fragment: row = lane/4, cols = 2*(lane%4) + {0,1}
     const int r = lane >> 2, c = (lane & 3) * 2;

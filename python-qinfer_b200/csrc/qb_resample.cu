@@ -286,12 +286,23 @@ __global__ void __launch_bounds__(256) lw_move_kernel(const __grid_constant__ Lw
         const int cnt = static_cast<int>((p.n_new - first < T) ? (p.n_new - first) : T);
         if (tid == 0) block_bad = 0;
         __syncthreads();
-        // gather + shrink: mu = a * x[js] + (1-a) * mean   (resamplers.py:325)
-        for (int j = tid; j < cnt * d; j += blockDim.x) {
-            const int r = j / d, c = j - r * d;
-            const int64_t src = p.js[first + r];
-            const double xv = __ldg(p.x_old + src * d + c);
-            loc[r * ld + c] = (p.a * xv) + mshift[c];
+        // gather + shrink: mu = a * x[js] + (1-a) * mean   (resamplers.py:325); 16-byte loads when d is even
+        if ((d & 1) == 0) {
+            const int hd = d >> 1;
+            for (int j = tid; j < cnt * hd; j += blockDim.x) {
+                const int r = j / hd, c = (j - r * hd) * 2;
+                const int64_t src = p.js[first + r];
+                const double2 xv = __ldg(reinterpret_cast<const double2*>(p.x_old + src * d + c));
+                loc[r * ld + c] = (p.a * xv.x) + mshift[c];
+                loc[r * ld + c + 1] = (p.a * xv.y) + mshift[c + 1];
+            }
+        } else {
+            for (int j = tid; j < cnt * d; j += blockDim.x) {
+                const int r = j / d, c = j - r * d;
+                const int64_t src = p.js[first + r];
+                const double xv = __ldg(p.x_old + src * d + c);
+                loc[r * ld + c] = (p.a * xv) + mshift[c];
+            }
         }
         for (int j = tid; j < d * cnt; j += blockDim.x) {
             const int m = j / cnt, r = j - m * cnt;
@@ -323,6 +334,58 @@ __global__ void __launch_bounds__(256) lw_move_kernel(const __grid_constant__ Lw
         }
         __syncthreads();
         if (tid == 0 && block_bad) atomicAdd(p.n_invalid, static_cast<unsigned long long>(block_bad));
+    }
+}
+
+// d <= 4: one thread per new particle, no shared-memory staging (the row fits a sector; S and the shifted mean
+// travel as launch parameters, so no constant upload either).
+struct LwSmallParams {
+    const double* x_old;
+    const int64_t* js;
+    const double* eps;
+    double* x_new;
+    uint8_t* invalid;
+    unsigned long long* n_invalid;
+    int64_t n_new, eps_ld;
+    int32_t postselect, pad;
+    double a;
+    double S[16];
+    double ms[4];
+    ModelView mv;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) lw_move_small_kernel(const __grid_constant__ LwSmallParams p) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t nround = ((p.n_new + 31) / 32) * 32;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        const bool live = i < p.n_new;
+        bool ok = true;
+        if (live) {
+            const int64_t src = p.js[i];
+            double xv[D], ev[D], out[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) xv[c] = __ldg(p.x_old + src * D + c);
+#pragma unroll
+            for (int m = 0; m < D; ++m) ev[m] = ldg_stream(p.eps + static_cast<int64_t>(m) * p.eps_ld + i);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double z = 0.0;
+#pragma unroll
+                for (int m = 0; m < D; ++m) z = fma(p.S[c * D + m], ev[m], z);
+                out[c] = ((p.a * xv[c]) + p.ms[c]) + z;  // resamplers.py:325,332, one rounding per ufunc
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) stg_stream(p.x_new + i * D + c, out[c]);
+            if (p.postselect) {
+                auto row = [&](int c) { return out[c]; };
+                ok = model_valid(p.mv, row);
+                p.invalid[i] = ok ? 0 : 1;
+            }
+        }
+        const unsigned int bad = __ballot_sync(0xffffffffu, live && !ok);
+        if (bad && lane == 0) atomicAdd(p.n_invalid, static_cast<unsigned long long>(__popc(bad)));
     }
 }
 
@@ -551,6 +614,35 @@ extern "C" int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t 
                QB_ERR_INVALID_ARGUMENT, "qb_lw_move: NULL pointer argument");
     QB_REQUIRE(d == model->d && n_old >= 1 && n_new >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_move: bad sizes");
     cudaStream_t st = as_stream(stream);
+    if (d <= 4) {
+        LwSmallParams q;
+        q.x_old = d_x_old;
+        q.js = d_js;
+        q.eps = d_eps;
+        q.x_new = d_x_new;
+        q.invalid = d_invalid;
+        q.n_invalid = reinterpret_cast<unsigned long long*>(d_n_invalid);
+        q.n_new = n_new;
+        q.eps_ld = n_new;
+        q.postselect = postselect;
+        q.pad = 0;
+        q.a = a;
+        for (int j = 0; j < 16; ++j) q.S[j] = (j < d * d) ? h_S[j] : 0.0;
+        const double oma = 1.0 - a;
+        for (int c = 0; c < 4; ++c) q.ms[c] = (c < d) ? oma * h_mean[c] : 0.0;  // (1 - a) * mean
+        q.mv = make_model_view(*model);
+        QB_CUDA_CHECK(cudaMemsetAsync(d_n_invalid, 0, sizeof(int64_t), st));
+        if (!postselect) QB_CUDA_CHECK(cudaMemsetAsync(d_invalid, 0, static_cast<size_t>(n_new), st));
+        const int grid = capped_grid((n_new + 255) / 256, 8);
+        switch (d) {
+            case 1: lw_move_small_kernel<1><<<grid, 256, 0, st>>>(q); break;
+            case 2: lw_move_small_kernel<2><<<grid, 256, 0, st>>>(q); break;
+            case 3: lw_move_small_kernel<3><<<grid, 256, 0, st>>>(q); break;
+            default: lw_move_small_kernel<4><<<grid, 256, 0, st>>>(q); break;
+        }
+        QB_CUDA_CHECK(cudaGetLastError());
+        return QB_OK;
+    }
     LwParams p;
     rc = upload_consts(h_mean, h_S, a, d, st, &p.consts);
     if (rc != QB_OK) return rc;
@@ -580,7 +672,7 @@ extern "C" int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t 
         attr_set = true;
     }
     const int64_t ntiles = (n_new + p.tile - 1) / p.tile;
-    lw_move_kernel<<<capped_grid(ntiles, 4), 256, smem, st>>>(p);
+    lw_move_kernel<<<capped_grid(ntiles, 6), 256, smem, st>>>(p);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }
