@@ -178,6 +178,15 @@ int qb_likelihood(const qb_model* model, const qb_expparams* eps, int32_t n_e,
                   const int64_t* outcomes, int32_t n_o,
                   const double* d_x, int64_t n, double* d_L, void* stream);
 
+/* SMCUpdater.hypothetical_update (smc.py:324-386) for every (outcome, experiment) pair, on the device:
+ * d_weights[o][e][i] = (w_i L_oie) / norm_oe with the |norm| < eps -> 1 guard of smc.py:369-370, d_norms[o][e] =
+ * sum_i w_i L_oie, and optionally d_L[o][e][i] = L_oie (NULL to skip).  w_i is the normalised weight. */
+int qb_hypothetical_update(const qb_model* model, const qb_expparams* eps, int32_t n_e,
+                           const int64_t* outcomes, int32_t n_o,
+                           const double* d_x, const double* d_w, const double* d_stats, int64_t n,
+                           double* d_weights, double* d_L, double* d_norms,
+                           void* d_ws, size_t ws_bytes, void* stream);
+
 /* Model.are_models_valid (test_models.py:109-110, rb.py:149-176,
  * tomography/models.py:143-147): d_valid[i] in {0,1}. */
 int qb_are_models_valid(const qb_model* model, const double* d_x, int64_t n, uint8_t* d_valid, void* stream);

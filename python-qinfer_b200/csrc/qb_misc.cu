@@ -158,6 +158,62 @@ __global__ void __launch_bounds__(256) valid_kernel(ModelView mv, const double* 
     }
 }
 
+// ---- hypothetical update (smc.py:324-386) for one (outcome, experiment) pair ---------------------------
+struct HypParams {
+    const double* x;
+    const double* w;
+    const double* stats;
+    double* out;        // hyp weights for this pair, n contiguous doubles
+    double* L;          // likelihoods for this pair (may be NULL)
+    double* partials;   // [grid]
+    int64_t n;
+    ModelView mv;
+    ExpView ev;
+    double meas[QB_MAX_D];
+};
+
+template <int KIND, bool BINOM>
+__global__ void __launch_bounds__(256) hyp_kernel(const __grid_constant__ HypParams p) {
+    __shared__ double red[8];
+    const int d = p.mv.d;
+    const double inv = p.stats[QB_STAT_INV_NORM];
+    double s = 0.0;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+        const double* xr = p.x + i * d;
+        auto row = [&](int c) { return xr[c]; };
+        auto meas = [&](int c) { return p.meas[c]; };
+        const double L = model_likelihood<KIND, BINOM>(p.mv, p.ev, row, meas, 0);
+        const double h = (p.w[i] * inv) * L;  // weights * L (smc.py:354)
+        p.out[i] = h;
+        if (p.L != nullptr) p.L[i] = L;
+        s += h;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) s += red[k];
+        p.partials[blockIdx.x] = s;
+    }
+}
+
+__global__ void hyp_finish_kernel(const double* partials, int nblocks, double* norm_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[b];
+    *norm_out = s;  // norm_scale (smc.py:357)
+}
+
+__global__ void __launch_bounds__(256) hyp_scale_kernel(double* out, int64_t n, const double* norm) {
+    const double eps = 2.220446049250313e-16;
+    const double nv = *norm;
+    const double div = (fabs(nv) < eps) ? 1.0 : nv;  // fixed_norm_scale (smc.py:369-370)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = out[i] / div;  // smc.py:373
+}
+
 static int grid_for(int64_t n, int threads, int per_sm) {
     int64_t g = (n + threads - 1) / threads;
     const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
@@ -256,6 +312,55 @@ extern "C" int qb_likelihood(const qb_model* model, const qb_expparams* eps, int
                 QB_LAUNCH_LIK(QB_MODEL_TOMOGRAPHY)
             }
 #undef QB_LAUNCH_LIK
+            QB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    return QB_OK;
+}
+
+extern "C" int qb_hypothetical_update(const qb_model* model, const qb_expparams* eps, int32_t n_e,
+                                      const int64_t* outcomes, int32_t n_o, const double* d_x, const double* d_w,
+                                      const double* d_stats, int64_t n, double* d_weights, double* d_L,
+                                      double* d_norms, void* d_ws, size_t ws_bytes, void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(eps && outcomes && d_x && d_w && d_stats && d_weights && d_norms && d_ws && n >= 1 && n_e >= 1 &&
+                   n_o >= 1,
+               QB_ERR_INVALID_ARGUMENT, "qb_hypothetical_update: bad arguments");
+    const int grid = grid_for(n, 256, 8);
+    QB_REQUIRE(ws_bytes >= static_cast<size_t>(grid) * sizeof(double) + 256, QB_ERR_WORKSPACE,
+               "qb_hypothetical_update: workspace too small");
+    HypParams p;
+    p.x = d_x;
+    p.w = d_w;
+    p.stats = d_stats;
+    p.partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);
+    p.n = n;
+    p.mv = make_model_view(*model);
+    cudaStream_t st = as_stream(stream);
+    for (int o = 0; o < n_o; ++o) {
+        for (int e = 0; e < n_e; ++e) {
+            const int64_t pair = static_cast<int64_t>(o) * n_e + e;  // output layout (n_outcomes, n_expparams, n)
+            p.ev = make_exp_view(*model, eps[e], outcomes[o]);
+            for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? eps[e].meas[c] : 0.0;
+            p.out = d_weights + pair * n;
+            p.L = d_L ? d_L + pair * n : nullptr;
+#define QB_LAUNCH_HYP(K)                                                    \
+    if (model->binomial)                                                    \
+        hyp_kernel<K, true><<<grid, 256, 0, st>>>(p);                       \
+    else                                                                    \
+        hyp_kernel<K, false><<<grid, 256, 0, st>>>(p);
+            if (model->kind == QB_MODEL_PRECESSION) {
+                QB_LAUNCH_HYP(QB_MODEL_PRECESSION)
+            } else if (model->kind == QB_MODEL_RB) {
+                QB_LAUNCH_HYP(QB_MODEL_RB)
+            } else {
+                QB_LAUNCH_HYP(QB_MODEL_TOMOGRAPHY)
+            }
+#undef QB_LAUNCH_HYP
+            QB_CUDA_CHECK(cudaGetLastError());
+            hyp_finish_kernel<<<1, 32, 0, st>>>(p.partials, grid, d_norms + pair);
+            hyp_scale_kernel<<<grid, 256, 0, st>>>(p.out, n, d_norms + pair);
             QB_CUDA_CHECK(cudaGetLastError());
         }
     }

@@ -8,11 +8,12 @@ from .models import (BinomialModel, Model, RandomizedBenchmarkingModel, SimpleIn
                      pauli_basis)
 from .resamplers import LiuWestResampler, Resampler, sqrtm_psd
 from .smc import SMCUpdater
+from .simple_est import simple_est_prec, simple_est_rb
 
 __all__ = [
     'ApproximationWarning', 'ResamplerError', 'ResamplerWarning', 'UnsupportedModelError',
     'GinibreTomographyPrior', 'ParticleDistribution', 'PostselectedDistribution', 'UniformDistribution',
     'BinomialModel', 'Model', 'RandomizedBenchmarkingModel', 'SimpleInversionModel', 'SimplePrecessionModel',
     'TomographyBasis', 'TomographyModel', 'describe_model', 'gell_mann_basis', 'pauli_basis',
-    'LiuWestResampler', 'Resampler', 'sqrtm_psd', 'SMCUpdater',
+    'LiuWestResampler', 'Resampler', 'sqrtm_psd', 'SMCUpdater', 'simple_est_prec', 'simple_est_rb',
 ]

@@ -68,6 +68,8 @@ SIGNATURES = {
                                              _P, ctypes.POINTER(QbUpdateCtl), _P, _SZ, _P]),
     "qb_likelihood": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I32,
                                      ctypes.POINTER(_I64), _I32, _P, _I64, _P, _P]),
+    "qb_hypothetical_update": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I32,
+                                              ctypes.POINTER(_I64), _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
     "qb_are_models_valid": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _P, _P]),
     "qb_moments_workspace_bytes": (_SZ, [_I64, _I32]),
     "qb_moments": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _SZ, _P]),

@@ -207,6 +207,24 @@ class DeviceCloud(object):
         self.launches += 2
         return self.read_stats(self._stats[slot])
 
+    def hypothetical_update(self, outcomes, expparams, want_likelihood):
+        """smc.py:324-386 on the device: (weights (n_o, n_e, n), L or None, norms (n_o, n_e, 1)) as host arrays."""
+        outcomes = np.atleast_1d(np.asarray(outcomes)).astype(np.int64)
+        expparams = np.atleast_1d(np.asarray(expparams))
+        n_o, n_e = outcomes.shape[0], expparams.shape[0]
+        eps = (_lib.QbExpparams * n_e)(*[self.desc.expparams_record(expparams, e) for e in range(n_e)])
+        outs = (ctypes.c_int64 * n_o)(*[int(o) for o in outcomes])
+        f64 = dict(dtype=torch.float64, device=self.device)
+        wts = torch.empty((n_o, n_e, self.n), **f64)
+        L = torch.empty((n_o, n_e, self.n), **f64) if want_likelihood else None
+        norms = torch.empty((n_o, n_e), **f64)
+        check(self.lib.qb_hypothetical_update(self.lib_model, eps, n_e, outs, n_o, _ptr(self.x), _ptr(self.w),
+                                              _ptr(self.stats), self.n, _ptr(wts), _ptr(L) if want_likelihood else None,
+                                              _ptr(norms), _ptr(self.ws), self.ws_bytes, _stream()))
+        self.launches += 3 * n_o * n_e
+        return (wts.cpu().numpy(), L.cpu().numpy() if want_likelihood else None,
+                norms.cpu().numpy()[..., np.newaxis])
+
     # ---- moments ------------------------------------------------------------------
     def moments(self):
         """(sum w, mean (d,), second moment (d, d)) of the normalised cloud."""

@@ -233,20 +233,14 @@ class SMCUpdater(object):
             m = getattr(m, 'underlying_model', None)
 
     def hypothetical_update(self, outcomes, expparams, return_likelihood=False, return_normalization=False):
-        """smc.py:324-386 on host arrays; the likelihood tensor comes from the CUDA kernel."""
-        from .engine import device_likelihood
+        """smc.py:324-386: posterior weights of hypothetical data, shape (n_outcomes, n_expparams, n_particles),
+        computed on the device (likelihood, weight product, normalisation sum, division) and returned as host arrays."""
         self._flush()
         if not isinstance(outcomes, np.ndarray):
             outcomes = np.array([outcomes])
-        weights = self.particle_weights
         expparams = np.atleast_1d(expparams)
         self._count_calls(outcomes.shape[0] * self._cloud.n * expparams.shape[0])
-        L = device_likelihood(self._desc, self._cloud.x, outcomes, expparams).transpose([0, 2, 1])
-        hyp_weights = weights * L
-        norm_scale = np.sum(hyp_weights, axis=2)[..., np.newaxis]
-        fixed_norm_scale = norm_scale.copy()
-        fixed_norm_scale[np.abs(norm_scale) < np.spacing(1)] = 1
-        norm_weights = hyp_weights / fixed_norm_scale
+        norm_weights, L, norm_scale = self._cloud.hypothetical_update(outcomes, expparams, return_likelihood)
         out = (norm_weights,)
         if return_likelihood:
             out += (L,)

@@ -353,3 +353,59 @@ def test_lazy_mode_zero_weight_events(qb, policy):
             up.update(0, ep0, check_for_resample=False)
             w = up.particle_weights
         assert np.all(w == 0)
+
+
+def test_simple_est_prec_and_rb_match_the_oracle(qb, tmp_path):
+    """qinfer.simple_est's one-call estimators (simple_est.py:141-260) on the GPU engine vs the same recipe driven
+    through the oracle: identical legacy seed => identical prior draw, resample decisions and estimates."""
+    import smc_oracle as o
+    rs = np.random.RandomState(17)
+    # precession: rows of (counts, t, n_shots), also through a CSV file
+    ts = np.linspace(0.5, 40, 60)
+    n_shots = 30
+    counts = rs.binomial(n_shots, 1 - np.cos(ts * 0.62 / 2) ** 2)
+    table = np.column_stack([counts, ts, np.full_like(ts, n_shots)])
+    csv = tmp_path / "prec.csv"
+    np.savetxt(str(csv), table, delimiter=",", fmt=["%d", "%.17g", "%d"])
+    np.random.seed(4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean, var, extra = qb.simple_est_prec(table, freq_max=1.0, n_particles=5000, return_all=True)
+    assert extra['updater'].resample_count > 0
+    np.random.seed(4)
+    model = o.BinomialModel(o.SimplePrecessionModel(0.0))
+    ou = o.SMCUpdater(model, 5000, o.UniformDistribution([0, 1.0]))
+    eps = np.empty((60,), dtype=model.expparams_dtype)
+    eps['x'], eps['n_meas'] = ts, n_shots
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ou.batch_update(counts, eps, resample_interval=1)
+    assert extra['updater'].resample_count == ou.resample_count
+    assert mean == pytest.approx(ou.est_mean()[0], rel=1e-6)
+    assert var == pytest.approx(ou.est_covariance_mtx()[0, 0], rel=1e-5)
+    assert abs(mean - 0.62) < 0.02
+    np.random.seed(4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean2, var2 = qb.simple_est_prec(str(csv), freq_max=1.0, n_particles=5000)
+    assert mean2 == pytest.approx(mean, rel=1e-12)
+    # randomized benchmarking: rows of (counts, m, n_shots)
+    ms = np.linspace(1, 400, 50).astype(int)
+    counts = rs.binomial(25, 0.5 * 0.99 ** ms + 0.5)
+    table = np.column_stack([counts, ms, np.full_like(ms, 25)])
+    np.random.seed(9)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean, cov = qb.simple_est_rb(table, p_min=0.8, n_particles=6000)
+    np.random.seed(9)
+    model = o.BinomialModel(o.RandomizedBenchmarkingModel())
+    prior = o.PostselectedDistribution(o.UniformDistribution([[0.8, 1.0], [0, 1], [0, 1]]), model)
+    ou = o.SMCUpdater(model, 6000, prior)
+    eps = np.empty((50,), dtype=model.expparams_dtype)
+    eps['m'], eps['n_meas'] = ms, 25
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ou.batch_update(counts, eps, resample_interval=1)
+    np.testing.assert_allclose(mean, ou.est_mean(), rtol=1e-6)
+    np.testing.assert_allclose(cov, ou.est_covariance_mtx(), rtol=1e-4, atol=1e-10)
+    assert abs(mean[0] - 0.99) < 0.01
