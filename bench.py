@@ -248,6 +248,11 @@ def gpu_arm(args, rank, world, local_rank):
         for k in range(30):
             small.update(int(outcomes[k]), ts[k:k + 1])
         small.est_mean()
+        # ... and page-lock the host staging blocks the posterior read-back will recycle (torch's caching host
+        # allocator keeps them), as a long-lived process would have done on its first read
+        stage = [torch.empty((n, 1), dtype=torch.float64, pin_memory=True),
+                 torch.empty((n,), dtype=torch.float64, pin_memory=True)]
+        del stage
         if world > 1:
             small.close()
         del small
