@@ -284,6 +284,22 @@ int qb_rng_uniform(double* d_out, int64_t n, uint64_t seed, uint64_t offset, voi
 /* d_out[i] = standard normal (Box-Muller on two 53-bit uniforms). */
 int qb_rng_normal(double* d_out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
 
+/* ---- device RNG (parity mode at scale; NumPy's legacy MT19937 stream) ------ */
+/* Continue the global np.random stream the reference draws from
+ * (np.random.random, resamplers.py:319; np.random.randn, resamplers.py:332)
+ * on the device.  `h_key`/`pos` (and `has_gauss`/`cached`) are the fields of
+ * np.random.get_state(); the *_out values are what np.random.set_state() takes
+ * afterwards.  Uniforms are bit-identical to NumPy's; for normals the accepted
+ * set, the words consumed and the final state are exact and the values are
+ * within 1 ulp (device log()).  Both calls synchronise the stream (they return
+ * host state).  Workspace for n uniforms and/or m normals: */
+size_t qb_mt19937_workspace_bytes(int64_t n_uniform, int64_t n_normal);
+int qb_mt19937_uniform(const uint32_t* h_key, int32_t pos, int64_t n, double* d_out, uint32_t* h_key_out,
+                       int32_t* pos_out, void* d_ws, size_t ws_bytes, void* stream);
+int qb_mt19937_normal(const uint32_t* h_key, int32_t pos, int32_t has_gauss, double cached, int64_t m,
+                      double* d_out, uint32_t* h_key_out, int32_t* pos_out, int32_t* has_gauss_out,
+                      double* cached_out, void* d_ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

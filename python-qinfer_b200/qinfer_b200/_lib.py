@@ -96,6 +96,10 @@ SIGNATURES = {
     "qb_tomo_canonicalize": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P]),
     "qb_rng_uniform": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
     "qb_rng_normal": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
+    "qb_mt19937_workspace_bytes": (_SZ, [_I64, _I64]),
+    "qb_mt19937_uniform": (ctypes.c_int, [_P, _I32, _I64, _P, _P, ctypes.POINTER(_I32), _P, _SZ, _P]),
+    "qb_mt19937_normal": (ctypes.c_int, [_P, _I32, _I32, _F64, _I64, _P, _P, ctypes.POINTER(_I32),
+                                         ctypes.POINTER(_I32), ctypes.POINTER(_F64), _P, _SZ, _P]),
 }
 
 _lib = None

@@ -337,6 +337,43 @@ class DeviceCloud(object):
         check(self.lib.qb_rng_normal(_ptr(out), int(n), int(seed), int(offset), _stream()))
         self.launches += 1
 
+    # NumPy's legacy global MT19937 stream continued on the device (parity mode at scale): the state is read
+    # from / written back to np.random, so host draws before and after interleave exactly as in the reference.
+    def _mt_ws(self, nbytes):
+        ws = getattr(self, '_mt_workspace', None)
+        if ws is None or ws.numel() < nbytes:
+            self._mt_workspace = ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.x.device)
+        return ws
+
+    def mt19937_uniform(self, out, n):
+        kind, key, pos, has_gauss, cached = np.random.get_state()
+        if kind != 'MT19937':
+            raise _lib.QbError("np.random is not the legacy MT19937 generator")
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        key_out = np.empty(624, dtype=np.uint32)
+        pos_out = ctypes.c_int32(0)
+        nbytes = self.lib.qb_mt19937_workspace_bytes(int(n), 0)
+        ws = self._mt_ws(nbytes)
+        check(self.lib.qb_mt19937_uniform(key.ctypes.data, int(pos), int(n), _ptr(out), key_out.ctypes.data,
+                                          ctypes.byref(pos_out), _ptr(ws), ws.numel(), _stream()))
+        np.random.set_state((kind, key_out, int(pos_out.value), has_gauss, cached))
+        self.launches += 2
+
+    def mt19937_normal(self, out, m):
+        kind, key, pos, has_gauss, cached = np.random.get_state()
+        if kind != 'MT19937':
+            raise _lib.QbError("np.random is not the legacy MT19937 generator")
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        key_out = np.empty(624, dtype=np.uint32)
+        pos_out, hg_out, cached_out = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_double(0.0)
+        nbytes = self.lib.qb_mt19937_workspace_bytes(0, int(m))
+        ws = self._mt_ws(nbytes)
+        check(self.lib.qb_mt19937_normal(key.ctypes.data, int(pos), int(has_gauss), float(cached), int(m), _ptr(out),
+                                         key_out.ctypes.data, ctypes.byref(pos_out), ctypes.byref(hg_out),
+                                         ctypes.byref(cached_out), _ptr(ws), ws.numel(), _stream()))
+        np.random.set_state((kind, key_out, int(pos_out.value), int(hg_out.value), float(cached_out.value)))
+        self.launches += 6
+
 
 # ---------------------------------------------------------------------------
 # Host-array conveniences used by the Model classes (upload, run kernel, download)

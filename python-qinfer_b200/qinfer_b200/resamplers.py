@@ -13,6 +13,11 @@ Two extra, keyword-only knobs that the reference does not have:
           from the legacy global ``np.random`` stream with exactly the calls,
           shapes and order of resamplers.py:319,332 and uploads them — resample
           indices are then bit-identical to the reference under the same seed.
+          ``'mt19937'`` consumes the very same global ``np.random`` stream but
+          generates it on the device (the generator state is read from and
+          written back to ``np.random``): indices stay bit-identical, the
+          normals are within 1 ulp, and a 10^7-particle resample no longer
+          waits ~0.4 s for the host generator.  Needs the default kernel.
           ``'philox'`` generates both on the device (counter-based, seeded by
           ``seed``) for throughput.
 ``scan``  ``'exact'`` (default) reproduces ``np.cumsum``'s sequential fp64
@@ -83,11 +88,11 @@ class LiuWestResampler(Resampler):
         self._postselect = postselect
         self._zero_cov_comp = zero_cov_comp
         self._kernel = kernel
-        if rng not in ('numpy', 'philox'):
-            raise ValueError("rng must be 'numpy' or 'philox'")
+        if rng not in ('numpy', 'mt19937', 'philox'):
+            raise ValueError("rng must be 'numpy', 'mt19937' or 'philox'")
         if scan not in ('exact', 'fast'):
             raise ValueError("scan must be 'exact' or 'fast'")
-        if rng == 'philox' and kernel is not np.random.randn:
+        if rng != 'numpy' and kernel is not np.random.randn:
             raise ValueError("a custom perturbation kernel needs rng='numpy' (it is a host callable)")
         self._rng = rng
         self._scan = scan
@@ -115,6 +120,8 @@ class LiuWestResampler(Resampler):
         if self._rng == 'numpy':
             u = np.random.random((n,))                       # resamplers.py:319
             cloud._u.copy_(torch.from_numpy(u))
+        elif self._rng == 'mt19937':
+            cloud.mt19937_uniform(cloud._u, n)
         else:
             cloud.rng_uniform(cloud._u, n, self._seed, self._philox_offset)
             self._philox_offset += (n + 1) // 2
@@ -127,6 +134,8 @@ class LiuWestResampler(Resampler):
             if eps.shape != (d, k):
                 raise ValueError("resampling kernel returned shape %s, expected %s" % (eps.shape, (d, k)))
             buf.copy_(torch.from_numpy(eps.reshape(-1)))
+        elif self._rng == 'mt19937':
+            cloud.mt19937_normal(buf, d * k)                 # randn(d, k) fills row-major from the same stream
         else:
             cloud.rng_normal(buf, d * k, self._seed ^ 0x9E3779B97F4A7C15, self._philox_offset)
             self._philox_offset += (d * k + 1) // 2

@@ -555,3 +555,107 @@ def test_philox_mode_resampling_preserves_moments(qb):
     sigma = np.sqrt(c0[0, 0])
     assert abs(m1[0] - m0[0]) < 6 * sigma / np.sqrt(up.min_n_ess)
     assert abs(c1[0, 0] / c0[0, 0] - 1) < 0.05
+
+
+# ---------------------------------------------------------------------------
+# Device MT19937 (parity mode at scale): NumPy's legacy global stream continued on the GPU
+# ---------------------------------------------------------------------------
+def _mt_cloud(qb):
+    from qinfer_b200.engine import DeviceCloud
+    return DeviceCloud(qb.describe_model(qb.SimplePrecessionModel()), 16)
+
+
+def _same_state(a, b):
+    return (a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+            and (a[3] == 0 or a[4] == b[4]))
+
+
+@pytest.mark.parametrize("seed,skip,n", [(0, 0, 1), (1, 0, 5), (2, 3, 311), (3, 0, 312), (4, 1, 313), (5, 623, 10007),
+                                         (6, 17, 2 * 10 ** 6 + 1), (7, 0, 10 ** 7)])
+def test_mt19937_uniform_bit_identical_to_numpy(qb, seed, skip, n):
+    """np.random.random((n,)) (resamplers.py:319) regenerated on the device from np.random's own state: same doubles,
+    same generator state afterwards, and the host stream continues seamlessly."""
+    import torch
+    cloud = _mt_cloud(qb)
+    np.random.seed(seed)
+    if skip:
+        np.random.randint(0, 2 ** 31, size=skip)      # move the position inside the 624-word block
+    s0 = np.random.get_state()
+    want = np.random.random((n,))
+    s1 = np.random.get_state()
+    tail_want = np.random.random((7,))
+    np.random.set_state(s0)
+    out = torch.empty((n,), dtype=torch.float64, device=cloud.device)
+    cloud.mt19937_uniform(out, n)
+    got = out.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert _same_state(np.random.get_state(), s1)
+    assert np.array_equal(np.random.random((7,)), tail_want)
+
+
+@pytest.mark.parametrize("seed,pre,m", [(0, 0, 1), (1, 0, 2), (2, 1, 3), (3, 0, 10), (4, 1, 1000), (5, 0, 1001),
+                                        (6, 1, 1), (7, 1, 2), (8, 0, 10 ** 6 + 1), (9, 1, 4 * 10 ** 6)])
+def test_mt19937_normal_matches_numpy_stream(qb, seed, pre, m):
+    """np.random.randn (resamplers.py:332; legacy polar method with a cached variate): the accepted candidates, the
+    words consumed and the final state (incl. has_gauss / cached) are exact; values agree to 1 ulp of log()."""
+    import torch
+    cloud = _mt_cloud(qb)
+    np.random.seed(seed)
+    if pre:
+        np.random.randn(pre)                           # leaves a cached second variate behind when pre is odd
+    s0 = np.random.get_state()
+    want = np.random.randn(m)
+    s1 = np.random.get_state()
+    tail_want = np.random.randn(5)
+    np.random.set_state(s0)
+    out = torch.empty((m,), dtype=torch.float64, device=cloud.device)
+    cloud.mt19937_normal(out, m)
+    got = out.cpu().numpy()
+    s1_got = np.random.get_state()
+    assert s1_got[0] == s1[0] and np.array_equal(s1_got[1], s1[1]) and s1_got[2:4] == s1[2:4]
+    if s1[3]:
+        assert abs(s1_got[4] - s1[4]) <= 4 * np.spacing(abs(s1[4]))
+    ulps = np.abs(got - want) / np.spacing(np.abs(want))
+    report("mt19937_normal_max_ulp_m%d" % m, float(ulps.max()))
+    report("mt19937_normal_frac_identical_m%d" % m, float(np.mean(got == want)))
+    assert ulps.max() <= 4
+    np.testing.assert_allclose(np.random.randn(5), tail_want, rtol=1e-15)
+
+
+def test_mt19937_mode_reproduces_golden_trajectories(qb, golden):
+    """rng='mt19937' draws the same stream as rng='numpy' (the reference's), so the free-running golden
+    trajectories — resample count, records, estimates — are reproduced with the variates made on the device."""
+    class MtLiuWest(qb.LiuWestResampler):
+        def __init__(self, *a, **k):
+            k.setdefault('rng', 'mt19937')
+            super(MtLiuWest, self).__init__(*a, **k)
+
+    ns = gpu_namespace(qb)
+    ns.LiuWestResampler = MtLiuWest
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g = golden("precession_c1")
+        _check_trajectory("mt_prec_c1", cases.run_precession(ns, {k: g[k] for k in ("prior", "ts", "outcomes")}), g)
+        g = golden("rb_binomial_c3")
+        _check_trajectory("mt_rb_c3", cases.run_rb(ns, {k: g[k] for k in ("prior", "ms", "counts", "n_meas")}), g)
+        g = golden("tomography_c4")
+        _check_trajectory("mt_tomo_c4",
+                          cases.run_tomography(ns, {k: g[k] for k in ("prior", "meas", "outcomes", "true")}), g)
+
+
+def test_mt19937_mode_same_indices_as_numpy_mode_at_scale(qb):
+    """At 2e6 particles the device-generated stream picks exactly the particles the host stream picks."""
+    n = 2 * 10 ** 6
+    x = np.random.RandomState(3).random_sample((n, 1))
+    outs = []
+    for mode in ("numpy", "mt19937"):
+        up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x),
+                           resampler=qb.LiuWestResampler(a=0.98, rng=mode))
+        for k in range(10):
+            up.update(k % 2, np.array([1.4 ** k]), check_for_resample=False)
+        np.random.seed(1234)
+        up.resample()
+        outs.append((up.particle_locations.copy(), np.random.get_state()))
+    (xa, sa), (xb, sb) = outs
+    assert np.array_equal(sa[1], sb[1]) and sa[2:4] == sb[2:4]
+    np.testing.assert_allclose(xb, xa, rtol=0, atol=1e-15)

@@ -101,6 +101,9 @@ def main():
             cloud.rng_uniform(cloud._u, nn, 1, 0)
             print("  rng uniform  %8.1f us" % timed(lambda: cloud.rng_uniform(cloud._u, nn, 1, 0), 20))
             print("  rng normal   %8.1f us" % timed(lambda: cloud.rng_normal(cloud._eps, nn * d, 1, 0), 20))
+            if d == 1:
+                print("  mt19937 uniform %8.1f us" % timed(lambda: cloud.mt19937_uniform(cloud._u, nn), 3))
+                print("  mt19937 normal  %8.1f us" % timed(lambda: cloud.mt19937_normal(cloud._eps, nn * d), 3))
             print("  draw         %8.1f us" % timed(lambda: cloud.draw(cloud._u, nn), 20))
             mean = np.full(d, 0.5)
             S = np.eye(d) * 0.01
