@@ -129,6 +129,26 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def ncu_traffic(n):
+    """DRAM bytes (read + write) of ONE fused-update launch from the newest committed `ncu --set full` summary under
+    profiles/ (captured at 10^7 particles; scaled linearly to n), or (None, why)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*fused_update_K1_ncu_full.csv")), key=os.path.basename)
+    if not files:
+        return None, "no ncu --set full summary under profiles/"
+    vals = {}
+    for row in csv.reader(open(files[-1])):
+        if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(row[1], None)
+            if scale is not None:
+                vals[row[0]] = float(row[2]) * scale
+    if len(vals) != 2:
+        return None, "dram metrics missing in %s" % os.path.basename(files[-1])
+    return sum(vals.values()) * (n / 1e7), "ncu --set full, profiles/%s (captured at n=1e7, scaled by n)" % \
+        os.path.basename(files[-1])
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -364,6 +384,8 @@ def gpu_arm(args, rank, world, local_rank):
         peak, peak_src = measured_peak_gbs()
         algo_bytes = 8.0 * (1 + 2) * n                   # per launch, per GPU: 8(d+2) B/particle, d = 1
         achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(n)
+        res_each = [a.elapsed_time(b) for a, b in resample_events]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -372,14 +394,23 @@ def gpu_arm(args, rank, world, local_rank):
                     "phases": e2e_phases},
             "gpu_launches": launches, "resamples_in_timed_region": n_resamples,
             "roofline": {"bound": "hbm", "kernel": "fused_update_kernel<PRECESSION>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "peak_source": peak_src, "bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms,
                          "how": "(timed region - sum of event-timed resamples) / fused-update launches",
                          "update_launches": upd_launches, "updates_per_launch": steps / max(upd_launches, 1),
                          "resample_ms_total": resample_ms,
-                         "resample_ms_each": [round(a.elapsed_time(b), 3) for a, b in resample_events]},
+                         "resample_ms_each": [round(v, 3) for v in res_each]},
             "clocks": clocks, "posterior_mean": posterior_mean,
         }
+        if res_each:
+            # whole Liu-West resample (moments, CDF + guide, fused draw+move, weights, host sqrtm and reads):
+            # algorithmic 8(3d+5) B per resampled particle, d = 1
+            rb = 8.0 * (3 * 1 + 5) * n
+            med = float(np.median(res_each))
+            line["resample_roofline"] = {"bound": "hbm", "bytes_per_resample": rb, "median_ms": med,
+                                         "achieved": rb / (med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": rb / (med * 1e-3) / 1e9 / peak,
+                                         "note": "event-timed around resample(), host work and syncs included"}
         if fused is not None:
             line["fused_f1"] = fused
         if world == 1 and not args.no_cpu_baseline:

@@ -203,6 +203,9 @@ int qb_moments(const double* d_x, const double* d_w, const double* d_stats, int6
 /* ---- Liu-West resampler --------------------------------------------------- */
 #define QB_SCAN_FAST 0   /* parallel (re-associated) prefix sum                              */
 #define QB_SCAN_EXACT 1  /* reproduces np.cumsum's sequential fp64 rounding bit for bit      */
+#define QB_SCAN_FAST_GUIDE 2        /* QB_SCAN_FAST + the draw's guide table scattered in the same pass, for
+                                       uniforms in [0, 1) (consumed by qb_lw_draw_move / qb_lw_draw_retry)   */
+#define QB_SCAN_FAST_GUIDE_SCALED 3 /* same, for draws scaled by the slab's own total (sharded clouds)       */
 size_t qb_cdf_workspace_bytes(int64_t n);
 /* d_cdf[i] = cumsum of normalised weights (resamplers.py:308). */
 int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode,
@@ -245,6 +248,29 @@ int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int
                 uint8_t* d_invalid, int64_t* d_n_invalid,
                 int32_t own_mean /* 0: the reference's js[r] quirk; 1: js[idxs[r]] (sharded clouds) */,
                 void* stream);
+
+/* Fused first pass for the device-RNG mode, d <= 4: draw + gather + shrink + perturb + validity in ONE launch,
+ * without materialising u, js or eps.  New particle i uses uniform element i of Philox stream (seed_u, off_u)
+ * and normals eps[m][i] = element m * n_new + i of stream (seed_n, off_n) — exactly the values qb_rng_uniform /
+ * qb_rng_normal would have stored, so the result is bit-identical to qb_rng_uniform -> qb_draw -> qb_rng_normal
+ * -> qb_lw_move on the same CDF.  `d_cdf` must come from qb_cdf; with use_guide != 0 it must have been built
+ * with a QB_SCAN_FAST_GUIDE* mode on the same workspace.  scale_u != 0: draws are u * cdf[n_old-1] (a shard
+ * drawing from its own slab).  d_counters[0] = #invalid, d_counters[1] = #clamped draws. */
+int qb_lw_draw_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                    const double* d_cdf, const void* d_ws, size_t ws_bytes, int32_t use_guide,
+                    const double* h_mean, const double* h_S, double a,
+                    uint64_t seed_u, uint64_t off_u, uint64_t seed_n, uint64_t off_n, int32_t scale_u,
+                    int64_t n_new, double* d_x_new, int32_t postselect, uint8_t* d_invalid,
+                    int64_t* d_counters, void* stream);
+/* Retry pass of the fused mode over idxs[0..k): the parent index is re-drawn from uniform element r (the
+ * reference's prefix quirk, resamplers.py:372) or idxs[r] (own_mean) of stream (seed_u, off_u); fresh normals
+ * eps[m][r] = element m * k + r of stream (seed_n, off_n).  d_counters[0] = #still invalid. */
+int qb_lw_draw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                     const double* d_cdf, const void* d_ws, size_t ws_bytes, int32_t use_guide,
+                     const double* h_mean, const double* h_S, double a,
+                     uint64_t seed_u, uint64_t off_u, uint64_t seed_n, uint64_t off_n, int32_t scale_u,
+                     const int64_t* d_idxs, int64_t k, int32_t own_mean, double* d_x_new,
+                     uint8_t* d_invalid, int64_t* d_counters, void* stream);
 
 /* ---- sharded cloud: peer mailboxes and the resample exchange ------------------- */
 #define QB_IPC_HANDLE_BYTES 64

@@ -6,6 +6,7 @@
 //
 // Compiled with --fmad=false (see qb_models.cuh).
 #include "qb_models.cuh"
+#include "qb_philox.cuh"
 
 namespace qb {
 
@@ -83,14 +84,75 @@ __global__ void __launch_bounds__(SCAN_THREADS) cdf_scan_tiles_kernel(double* ti
     if (threadIdx.x == 0) tile_sums[ntiles] = total;  // ntiles + 1 entries: the exclusive prefix and the total
 }
 
-// pass 3: per-tile inclusive scan + tile offset
+// Guide table header, stored in front of a table built by cdf_write_kernel<true> (the fused draw+move kernels read it).
+struct GuideHdr {
+    double mult;   // bucket of u = floor(u * mult); a power of two, so u * mult and b / mult are exact
+    double limit;  // = M / mult: uniforms >= limit (or < 0, NaN) take the plain bisection
+    int64_t M;     // table entries 0..M; 0: no table (small clouds), plain bisection everywhere
+    int64_t pad;
+};
+
+// mult for a table of M buckets covering uniforms in [0, range): the smallest power of two 2^e >= range.
+__device__ __forceinline__ void guide_scale(double range, int64_t M, double& mult, double& limit) {
+    int e;
+    const double f = frexp(range, &e);  // range = f * 2^e, f in [1/2, 1)
+    if (f == 0.5) --e;                  // range is itself a power of two
+    mult = ldexp(static_cast<double>(M), -e);
+    limit = ldexp(1.0, e);
+}
+
+// bucket boundary of a stored CDF value: B(c) = ceil(c * mult) clamped to [0, M + 1].  Entry i owns the buckets
+// [B(cdf[i-1]), B(cdf[i])): exactly the b with cdf[i-1] <= b / mult < cdf[i], i.e. upper_bound(cdf, b / mult) = i.
+__device__ __forceinline__ int64_t guide_boundary(double c, double mult, int64_t M) {
+    const double y = ceil(c * mult);
+    if (!(y > 0.0)) return 0;  // negative or NaN
+    if (y > static_cast<double>(M)) return M + 1;
+    return static_cast<int64_t>(y);
+}
+
+constexpr int GUIDE_Q = 64;           // per-block queue of long bucket ranges (one heavy particle), filled cooperatively
+constexpr int GUIDE_SHORT_RANGE = 16;
+
+// pass 3: per-tile inclusive scan + tile offset.  The last entry of every full tile is stored as the next tile's
+// offset, so that the value a tile starts from IS the stored predecessor (needed by the guide scatter; the two
+// differ only in the rounding of the last bit).
+// GUIDE: while the CDF values sit in registers, scatter the guide table g[b] = upper_bound(cdf, b / mult) that the
+// draw kernels use to bracket the bisection (replaces a separate pass of M bisections over the finished CDF).
+template <bool GUIDE>
 __global__ void __launch_bounds__(SCAN_THREADS) cdf_write_kernel(const double* __restrict__ w,
                                                                  const double* __restrict__ stats, int64_t n,
                                                                  const double* __restrict__ tile_offsets,
-                                                                 double* __restrict__ cdf) {
+                                                                 double* __restrict__ cdf, int64_t M, int scaled,
+                                                                 GuideHdr* __restrict__ hdr,
+                                                                 int32_t* __restrict__ guide) {
     __shared__ double warp_tot[SCAN_THREADS / 32];
+    __shared__ long long warp_lastB[SCAN_THREADS / 32];
+    __shared__ long long q_lo[GUIDE_Q], q_hi[GUIDE_Q];
+    __shared__ int q_val[GUIDE_Q];
+    __shared__ int q_n;
     const double inv = stats[QB_STAT_INV_NORM];
     const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double mult = 0.0, limit = 0.0;
+    int64_t b_top = 0;
+    if (GUIDE) {
+        // range of the uniforms the table serves: [0, 1), or [0, total) for a shard that scales its draws
+        const double total_hi = tile_offsets[ntiles] * (1.0 + 9.5367431640625e-07);  // (1 + 2^-20): above cdf[n-1]
+        guide_scale(scaled ? total_hi : 1.0, M, mult, limit);
+        b_top = guide_boundary(total_hi, mult, M);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            hdr->mult = mult;
+            hdr->limit = limit;
+            hdr->M = M;
+            hdr->pad = 0;
+        }
+        if (threadIdx.x == 0) q_n = 0;
+        // buckets at or above the total hold n
+        const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+        for (int64_t b = b_top + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; b <= M; b += stride)
+            guide[b] = static_cast<int32_t>(n);
+        __syncthreads();
+    }
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t base = t * SCAN_TILE + static_cast<int64_t>(threadIdx.x) * SCAN_ITEMS;
         double v[SCAN_ITEMS];
@@ -102,12 +164,59 @@ __global__ void __launch_bounds__(SCAN_THREADS) cdf_write_kernel(const double* _
             s += v[k];
         }
         double total;
-        double run = tile_offsets[t] + block_exclusive_scan(s, warp_tot, total);
+        const double off = tile_offsets[t];
+        double run = off + block_exclusive_scan(s, warp_tot, total);
+        double c[SCAN_ITEMS];
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; ++k) {
-            const int64_t i = base + k;
             run += v[k];
-            if (i < n) cdf[i] = run;
+            c[k] = run;
+        }
+        if (threadIdx.x == SCAN_THREADS - 1 && t + 1 < ntiles) c[SCAN_ITEMS - 1] = tile_offsets[t + 1];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < n) cdf[base + k] = c[k];
+        if (GUIDE) {
+            int64_t B[SCAN_ITEMS];
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) B[k] = guide_boundary(c[k], mult, M);
+            // boundary of the stored predecessor of my first entry: previous thread's last entry (shuffle / shared),
+            // or the tile offset itself for the first thread (= the previous tile's stored last entry; 0 for tile 0)
+            long long prevB = __shfl_up_sync(0xffffffffu, static_cast<long long>(B[SCAN_ITEMS - 1]), 1);
+            if (lane == 31) warp_lastB[wid] = B[SCAN_ITEMS - 1];
+            __syncthreads();
+            if (lane == 0) prevB = (wid == 0) ? guide_boundary(off, mult, M) : warp_lastB[wid - 1];
+            int64_t lo = prevB;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                const int64_t i = base + k;
+                if (i < n) {
+                    int64_t hi = B[k];
+                    const int32_t val = static_cast<int32_t>(i);
+                    if (hi - lo > GUIDE_SHORT_RANGE) {
+                        const int slot = atomicAdd(&q_n, 1);
+                        if (slot < GUIDE_Q) {
+                            q_lo[slot] = lo;
+                            q_hi[slot] = hi;
+                            q_val[slot] = val;
+                            hi = lo;  // handed over to the block
+                        }
+                    }
+                    for (int64_t b = lo; b < hi; ++b) guide[b] = val;
+                    lo = (B[k] > lo) ? B[k] : lo;
+                    if (i == n - 1)  // between the actual total and the conservative b_top: still "past the end"
+                        for (int64_t b = lo; b < b_top; ++b) guide[b] = static_cast<int32_t>(n);
+                }
+            }
+            __syncthreads();
+            const int nq = (q_n < GUIDE_Q) ? q_n : GUIDE_Q;
+            for (int e = 0; e < nq; ++e) {
+                const int32_t val = q_val[e];
+                for (int64_t b = q_lo[e] + threadIdx.x; b < q_hi[e]; b += SCAN_THREADS) guide[b] = val;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) q_n = 0;
+            __syncthreads();
         }
     }
 }
@@ -417,6 +526,186 @@ __global__ void __launch_bounds__(256) lw_move_small_kernel(const __grid_constan
     }
 }
 
+// -----------------------------------------------------------------------------
+// Fused draw + move for the device-RNG mode (d <= 4): one pass does what rng_kernel<uniform>, draw_guided_kernel,
+// rng_kernel<normal> and lw_move_small_kernel do in four, without materialising u, js or eps: each thread
+// regenerates the Philox variates of two consecutive new particles (bit-identical to the stand-alone generators),
+// brackets the bisection with the guide table cdf_write_kernel<true> scattered, gathers the parent row, shrinks,
+// perturbs, tests validity and writes the new row.  The retry kernel regenerates the parent index the same way.
+// -----------------------------------------------------------------------------
+struct LwFusedParams {
+    const double* x_old;
+    const double* cdf;
+    const GuideHdr* hdr;     // NULL: plain bisection
+    const int32_t* guide;
+    double* x_new;
+    uint8_t* invalid;
+    unsigned long long* counters;  // [0] invalid, [1] clamped draws
+    const int64_t* idxs;           // retry only
+    int64_t n_old, n_new, k;
+    uint64_t seed_u, off_u, seed_n, off_n;
+    int32_t postselect, scale_u, own_mean, pad;
+    double a;
+    double S[16];
+    double ms[4];
+    ModelView mv;
+};
+
+struct DrawCtx {
+    const double* cdf;
+    const int32_t* guide;
+    int64_t n, M;
+    double mult, limit, scale;
+};
+
+__device__ __forceinline__ DrawCtx make_draw_ctx(const LwFusedParams& p) {
+    DrawCtx c;
+    c.cdf = p.cdf;
+    c.guide = p.guide;
+    c.n = p.n_old;
+    c.M = 0;
+    c.mult = 0.0;
+    c.limit = 0.0;
+    if (p.hdr != nullptr) {
+        c.M = p.hdr->M;
+        c.mult = p.hdr->mult;
+        c.limit = p.hdr->limit;
+    }
+    c.scale = p.scale_u ? __ldg(p.cdf + p.n_old - 1) : 1.0;
+    return c;
+}
+
+// min(upper_bound(cdf, u), n - 1); `over` counts the clamps
+__device__ __forceinline__ int64_t guided_draw(const DrawCtx& c, double u, unsigned int& over) {
+    const double ui = c.scale == 1.0 ? u : u * c.scale;
+    int64_t lo;
+    if (c.M > 0 && ui >= 0.0 && ui < c.limit) {
+        const int64_t b = static_cast<int64_t>(ui * c.mult);
+        const int2 g = *reinterpret_cast<const int2*>(c.guide + (b & ~1LL));
+        int64_t glo, ghi;
+        if (b & 1) {
+            glo = g.y;
+            ghi = __ldg(c.guide + b + 1);
+        } else {
+            glo = g.x;
+            ghi = g.y;
+        }
+        lo = upper_bound_range(c.cdf, glo, ghi, ui);
+    } else {
+        lo = upper_bound_range(c.cdf, 0, c.n, ui);
+    }
+    if (lo >= c.n) {
+        lo = c.n - 1;
+        ++over;
+    }
+    return lo;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) lw_draw_move_kernel(const __grid_constant__ LwFusedParams p) {
+    const DrawCtx dc = make_draw_ctx(p);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t npairs = (p.n_new + 1) / 2;
+    const int64_t nround = ((npairs + 31) / 32) * 32;
+    unsigned int over = 0;
+    for (int64_t pr = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pr < nround; pr += stride) {
+        const int64_t i0 = 2 * pr;
+        unsigned int nbad = 0;
+        if (i0 < p.n_new) {
+            const bool two = i0 + 1 < p.n_new;
+            double u[2];
+            philox_uniform_pair(p.seed_u, p.off_u + static_cast<uint64_t>(pr), u[0], u[1]);
+            int64_t src[2];
+            src[0] = guided_draw(dc, u[0], over);
+            src[1] = two ? guided_draw(dc, u[1], over) : src[0];
+            double xv[2][D];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int c = 0; c < D; ++c) xv[s][c] = __ldg(p.x_old + src[s] * D + c);
+            // eps[m][i] is element m * n_new + i of the normal stream (the (d, k) row-major layout of kernel(n_rvs, k))
+            double ev[2][D];
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                const int64_t f0 = static_cast<int64_t>(m) * p.n_new + i0;
+                if ((f0 & 1) == 0) {
+                    philox_normal_pair(p.seed_n, p.off_n + static_cast<uint64_t>(f0 >> 1), ev[0][m], ev[1][m]);
+                } else {
+                    ev[0][m] = philox_normal_elem(p.seed_n, p.off_n, f0);
+                    ev[1][m] = two ? philox_normal_elem(p.seed_n, p.off_n, f0 + 1) : 0.0;
+                }
+            }
+            double out[2][D];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double z = 0.0;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) z = fma(p.S[c * D + m], ev[s][m], z);
+                    out[s][c] = ((p.a * xv[s][c]) + p.ms[c]) + z;  // resamplers.py:325,332, one rounding per ufunc
+                }
+            double* dst = p.x_new + i0 * D;
+            if (D == 1 && two && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(out[0][0]),
+                             "d"(out[1][0])
+                             : "memory");
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; ++c) stg_stream(dst + c, out[0][c]);
+                if (two) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) stg_stream(dst + D + c, out[1][c]);
+                }
+            }
+            if (p.postselect) {
+                auto row0 = [&](int c) { return out[0][c]; };
+                auto row1 = [&](int c) { return out[1][c]; };
+                const bool ok0 = model_valid(p.mv, row0);
+                const bool ok1 = two ? model_valid(p.mv, row1) : true;
+                p.invalid[i0] = ok0 ? 0 : 1;
+                if (two) p.invalid[i0 + 1] = ok1 ? 0 : 1;
+                nbad = (ok0 ? 0u : 1u) + (ok1 ? 0u : 1u);
+            }
+        }
+        const unsigned int tot = __reduce_add_sync(0xffffffffu, nbad);
+        if (tot && lane == 0) atomicAdd(p.counters, static_cast<unsigned long long>(tot));
+    }
+    if (over) atomicAdd(p.counters + 1, static_cast<unsigned long long>(over));
+}
+
+// Retry of the k still-invalid particles idxs[0..k): parent = draw(u[r]) (the reference's prefix-of-the-original-means
+// quirk, resamplers.py:372) or draw(u[idxs[r]]) (own_mean), fresh normals eps[m][r] = element m * k + r of this
+// iteration's normal stream.
+template <int D>
+__global__ void __launch_bounds__(128) lw_draw_retry_kernel(const __grid_constant__ LwFusedParams p) {
+    const DrawCtx dc = make_draw_ctx(p);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    unsigned int over = 0;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.k; r += stride) {
+        const int64_t dst = p.idxs[r];
+        const int64_t slot = p.own_mean ? dst : r;
+        const int64_t src = guided_draw(dc, philox_uniform_elem(p.seed_u, p.off_u, slot), over);
+        double out[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double z = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; ++m)
+                z = fma(p.S[c * D + m], philox_normal_elem(p.seed_n, p.off_n, static_cast<int64_t>(m) * p.k + r), z);
+            out[c] = ((p.a * __ldg(p.x_old + src * D + c)) + p.ms[c]) + z;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) p.x_new[dst * D + c] = out[c];
+        auto row = [&](int c) { return out[c]; };
+        const bool ok = model_valid(p.mv, row);
+        p.invalid[dst] = ok ? 0 : 1;
+        if (!ok) atomicAdd(p.counters, 1ull);
+    }
+    (void)over;  // clamps were counted by the first pass
+}
+
 // Retry: one thread per still-invalid particle r (few of them).
 __global__ void __launch_bounds__(128) lw_retry_kernel(const __grid_constant__ LwParams p, int64_t k) {
     const int d = p.d;
@@ -563,8 +852,16 @@ static size_t cdf_tiles_bytes(int64_t n) {
 
 using namespace qb;
 
+// Workspace layout of the CDF family: [0,256) update ticket | tile sums | exact-scan scratch | guide header + table.
+static size_t guide_offset(int64_t n) {
+    return ((256 + cdf_tiles_bytes(n) + exact_scan_workspace_bytes(n) + 255) / 256) * 256;
+}
+static bool guide_wanted(int64_t n) { return n >= 4096 && n < (1LL << 31); }
+
 extern "C" size_t qb_cdf_workspace_bytes(int64_t n) {
-    return 256 + cdf_tiles_bytes(n) + exact_scan_workspace_bytes(n);
+    size_t b = guide_offset(n) + 64;
+    if (guide_wanted(n)) b += static_cast<size_t>(guide_size(n) + 2) * sizeof(int32_t);
+    return b + 256;
 }
 
 extern "C" int qb_cdf_exact_fallback_flag(const void* d_ws, int64_t n, int32_t* h_flag, void* stream) {
@@ -585,7 +882,9 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
         QB_CUDA_CHECK(cudaGetLastError());
         return QB_OK;
     }
-    QB_REQUIRE(mode == QB_SCAN_FAST || mode == QB_SCAN_EXACT, QB_ERR_INVALID_ARGUMENT, "qb_cdf: unknown mode %d", mode);
+    QB_REQUIRE(mode == QB_SCAN_FAST || mode == QB_SCAN_EXACT || mode == QB_SCAN_FAST_GUIDE ||
+                   mode == QB_SCAN_FAST_GUIDE_SCALED,
+               QB_ERR_INVALID_ARGUMENT, "qb_cdf: unknown mode %d", mode);
     double* tiles = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);  // [0,256) is the update ticket
     const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     const int grid = capped_grid(ntiles, 8);
@@ -598,7 +897,15 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
         return launch_exact_scan(d_w, d_stats, n, d_cdf, tiles,
                                  reinterpret_cast<unsigned char*>(d_ws) + 256 + cdf_tiles_bytes(n), st);
     }
-    cdf_write_kernel<<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles, d_cdf);
+    GuideHdr* hdr = reinterpret_cast<GuideHdr*>(reinterpret_cast<unsigned char*>(d_ws) + guide_offset(n));
+    int32_t* guide = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(hdr) + 64);
+    if (mode == QB_SCAN_FAST || !guide_wanted(n)) {
+        if (mode != QB_SCAN_FAST) QB_CUDA_CHECK(cudaMemsetAsync(hdr, 0, sizeof(GuideHdr), st));  // M = 0: no table
+        cdf_write_kernel<false><<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles, d_cdf, 0, 0, nullptr, nullptr);
+    } else {
+        cdf_write_kernel<true><<<grid, SCAN_THREADS, 0, st>>>(d_w, d_stats, n, tiles, d_cdf, guide_size(n),
+                                                              mode == QB_SCAN_FAST_GUIDE_SCALED ? 1 : 0, hdr, guide);
+    }
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }
@@ -759,6 +1066,104 @@ extern "C" int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t
     p.mv = make_model_view(*model);
     QB_CUDA_CHECK(cudaMemsetAsync(d_n_invalid, 0, sizeof(int64_t), st));
     lw_retry_kernel<<<capped_grid((k + 127) / 128, 8), 128, 0, st>>>(p, k);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+// ---- fused draw + move (device-RNG mode, d <= 4) ------------------------------------------------------------
+static int fill_fused(LwFusedParams& q, const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                      const double* d_cdf, const void* d_ws, size_t ws_bytes, int32_t use_guide, const double* h_mean,
+                      const double* h_S, double a, uint64_t seed_u, uint64_t off_u, uint64_t seed_n, uint64_t off_n,
+                      int32_t scale_u, double* d_x_new, uint8_t* d_invalid, int64_t* d_counters) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_x_old && d_cdf && h_mean && h_S && d_x_new && d_invalid && d_counters, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_draw_move/retry: NULL pointer argument");
+    QB_REQUIRE(d == model->d && d >= 1 && d <= 4 && n_old >= 1, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_draw_move/retry: needs 1 <= d <= 4 (larger d: qb_draw + qb_lw_move)");
+    q.x_old = d_x_old;
+    q.cdf = d_cdf;
+    q.hdr = nullptr;
+    q.guide = nullptr;
+    if (use_guide) {
+        QB_REQUIRE(d_ws && ws_bytes >= qb_cdf_workspace_bytes(n_old), QB_ERR_WORKSPACE,
+                   "qb_lw_draw_move/retry: workspace too small for the guide table");
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(d_ws) + guide_offset(n_old);
+        q.hdr = reinterpret_cast<const GuideHdr*>(base);
+        q.guide = reinterpret_cast<const int32_t*>(base + 64);
+    }
+    q.x_new = d_x_new;
+    q.invalid = d_invalid;
+    q.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    q.idxs = nullptr;
+    q.n_old = n_old;
+    q.n_new = 0;
+    q.k = 0;
+    q.seed_u = seed_u;
+    q.off_u = off_u;
+    q.seed_n = seed_n;
+    q.off_n = off_n;
+    q.postselect = 1;
+    q.scale_u = scale_u ? 1 : 0;
+    q.own_mean = 0;
+    q.pad = 0;
+    q.a = a;
+    for (int j = 0; j < 16; ++j) q.S[j] = (j < d * d) ? h_S[j] : 0.0;
+    const double oma = 1.0 - a;
+    for (int c = 0; c < 4; ++c) q.ms[c] = (c < d) ? oma * h_mean[c] : 0.0;  // (1 - a) * mean
+    q.mv = make_model_view(*model);
+    return QB_OK;
+}
+
+extern "C" int qb_lw_draw_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                               const double* d_cdf, const void* d_ws, size_t ws_bytes, int32_t use_guide,
+                               const double* h_mean, const double* h_S, double a, uint64_t seed_u, uint64_t off_u,
+                               uint64_t seed_n, uint64_t off_n, int32_t scale_u, int64_t n_new, double* d_x_new,
+                               int32_t postselect, uint8_t* d_invalid, int64_t* d_counters, void* stream) {
+    LwFusedParams q;
+    int rc = fill_fused(q, model, d_x_old, n_old, d, d_cdf, d_ws, ws_bytes, use_guide, h_mean, h_S, a, seed_u, off_u,
+                        seed_n, off_n, scale_u, d_x_new, d_invalid, d_counters);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(n_new >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_draw_move: n_new must be positive");
+    cudaStream_t st = as_stream(stream);
+    q.n_new = n_new;
+    q.postselect = postselect ? 1 : 0;
+    QB_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int64_t), st));
+    if (!postselect) QB_CUDA_CHECK(cudaMemsetAsync(d_invalid, 0, static_cast<size_t>(n_new), st));
+    const int grid = capped_grid(((n_new + 1) / 2 + 255) / 256, 8);
+    switch (d) {
+        case 1: lw_draw_move_kernel<1><<<grid, 256, 0, st>>>(q); break;
+        case 2: lw_draw_move_kernel<2><<<grid, 256, 0, st>>>(q); break;
+        case 3: lw_draw_move_kernel<3><<<grid, 256, 0, st>>>(q); break;
+        default: lw_draw_move_kernel<4><<<grid, 256, 0, st>>>(q); break;
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_draw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                                const double* d_cdf, const void* d_ws, size_t ws_bytes, int32_t use_guide,
+                                const double* h_mean, const double* h_S, double a, uint64_t seed_u, uint64_t off_u,
+                                uint64_t seed_n, uint64_t off_n, int32_t scale_u, const int64_t* d_idxs, int64_t k,
+                                int32_t own_mean, double* d_x_new, uint8_t* d_invalid, int64_t* d_counters,
+                                void* stream) {
+    LwFusedParams q;
+    int rc = fill_fused(q, model, d_x_old, n_old, d, d_cdf, d_ws, ws_bytes, use_guide, h_mean, h_S, a, seed_u, off_u,
+                        seed_n, off_n, scale_u, d_x_new, d_invalid, d_counters);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_idxs && k >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_draw_retry: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    q.idxs = d_idxs;
+    q.k = k;
+    q.own_mean = own_mean ? 1 : 0;
+    QB_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, sizeof(int64_t), st));  // the clamp count of the first pass stays
+    const int grid = capped_grid((k + 127) / 128, 8);
+    switch (d) {
+        case 1: lw_draw_retry_kernel<1><<<grid, 128, 0, st>>>(q); break;
+        case 2: lw_draw_retry_kernel<2><<<grid, 128, 0, st>>>(q); break;
+        case 3: lw_draw_retry_kernel<3><<<grid, 128, 0, st>>>(q); break;
+        default: lw_draw_retry_kernel<4><<<grid, 128, 0, st>>>(q); break;
+    }
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

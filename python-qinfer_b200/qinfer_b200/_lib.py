@@ -14,7 +14,7 @@ QB_IPC_HANDLE_BYTES = 64
 QB_MAX_FUSE = 8
 QB_STAT_COUNT = 16
 QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY = 1, 2, 3
-QB_SCAN_FAST, QB_SCAN_EXACT = 0, 1
+QB_SCAN_FAST, QB_SCAN_EXACT, QB_SCAN_FAST_GUIDE, QB_SCAN_FAST_GUIDE_SCALED = 0, 1, 2, 3
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqinfer_b200.so")
 
@@ -84,6 +84,12 @@ SIGNATURES = {
     "qb_compact_invalid": (ctypes.c_int, [_P, _I64, _P, _P, _P, _SZ, _P]),
     "qb_lw_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _I64, ctypes.POINTER(_F64),
                                    ctypes.POINTER(_F64), _F64, _P, _P, _P, _P, _I32, _P]),
+    "qb_lw_draw_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _SZ, _I32,
+                                       ctypes.POINTER(_F64), ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I32,
+                                       _I64, _P, _I32, _P, _P, _P]),
+    "qb_lw_draw_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _SZ, _I32,
+                                        ctypes.POINTER(_F64), ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I32,
+                                        _P, _I64, _I32, _P, _P, _P, _P]),
     "qb_mailbox_create": (ctypes.c_int, [_I32, ctypes.POINTER(_P)]),
     "qb_mailbox_destroy": (ctypes.c_int, [_P]),
     "qb_ipc_get_handle": (ctypes.c_int, [_P, ctypes.c_char_p]),

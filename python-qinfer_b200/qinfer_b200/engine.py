@@ -18,6 +18,7 @@ import time
 from ._lib import (QB_MAX_FUSE, QB_STAT_COUNT, QB_STAT_INV_NORM, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NESS,
                    QB_STAT_NORM, QB_STAT_SKIPPED, QB_STAT_SUMSQ, QB_STAT_TAG, check)
 
+_U64_MASK = (1 << 64) - 1
 MIRROR_SLOT = 8 * QB_MAX_FUSE      # doubles per mirror slot: one 8-double block per fused step
 
 
@@ -67,6 +68,7 @@ class DeviceCloud(object):
             self.ws = torch.zeros(((ws_bytes + 7) // 8,), **f64)       # zeroed once: holds the launch ticket
             self.ws_bytes = self.ws.numel() * 8
             self.moments_out = torch.empty((1 + self.d + self.d * self.d,), **f64)
+            self.moments_host = torch.empty((1 + self.d + self.d * self.d,), dtype=torch.float64, pin_memory=True)
             self.stats_host = torch.empty((QB_STAT_COUNT,), dtype=torch.float64, pin_memory=True)
             self.counter = torch.zeros((2,), dtype=torch.int64, device=self.device)
             self.counter_host = torch.empty((2,), dtype=torch.int64, pin_memory=True)
@@ -235,7 +237,9 @@ class DeviceCloud(object):
         check(self.lib.qb_moments(_ptr(self.x), _ptr(self.w), _ptr(self.stats), self.n, self.d,
                                   _ptr(self.moments_out), _ptr(self.ws), self.ws_bytes, _stream()))
         self.launches += 2
-        out = self.moments_out.cpu().numpy()
+        self.moments_host.copy_(self.moments_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = self.moments_host.numpy()
         d = self.d
         return out[0], out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
 
@@ -251,6 +255,14 @@ class DeviceCloud(object):
             self._invalid = torch.zeros((n_new,), dtype=torch.uint8, device=dev)
             self._idxs = torch.empty((n_new,), dtype=torch.int64, device=dev)
 
+    def _fused_scratch(self, cap):
+        """Scratch of the fused draw+move path: only the validity flags and the compacted retry list (capacity-based)."""
+        if self._invalid is None or self._invalid.numel() < cap:
+            self._invalid = torch.zeros((cap,), dtype=torch.uint8, device=self.device)
+            self._idxs = torch.empty((cap,), dtype=torch.int64, device=self.device)
+        if self._cdf is None or self._cdf.numel() != self.n:
+            self._cdf = torch.empty((self.n,), dtype=torch.float64, device=self.device)
+
     def preallocate_resample(self, n_new=None):
         """Allocate the resampling scratch and the second particle slab up front (no allocation in the loop)."""
         n_new = self.n if n_new is None else int(n_new)
@@ -258,8 +270,13 @@ class DeviceCloud(object):
         if self.x_alt is None or self.x_alt.shape[0] != n_new:
             self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
 
+    def preallocate_resample_slab(self):
+        if self.x_alt is None or self.x_alt.shape[0] != self.n:
+            self.x_alt = torch.empty((self.n, self.d), dtype=torch.float64, device=self.device)
+
     def cdf(self, mode):
-        self._resample_scratch(self.n if self._js is None else self._js.numel())
+        if self._cdf is None or self._cdf.numel() != self.n:
+            self._cdf = torch.empty((self.n,), dtype=torch.float64, device=self.device)
         check(self.lib.qb_cdf(_ptr(self.w), _ptr(self.stats), self.n, _ptr(self._cdf), int(mode), _ptr(self.ws),
                               self.ws_bytes, _stream()))
         self.launches += 1 if mode == _lib.QB_SCAN_EXACT else 3
@@ -287,6 +304,36 @@ class DeviceCloud(object):
                                   _lib.f64_array(mean), _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
                                   _ptr(eps_dev), int(n_new), _ptr(self.x_alt), int(bool(postselect)),
                                   _ptr(self._invalid), _ptr(self.counter), _stream()))
+        self.launches += 1
+
+    def lw_draw_move(self, mean, S, a, seed_u, off_u, seed_n, off_n, n_new, postselect, dst=None, scale_u=False,
+                     use_guide=True):
+        """Fused first Liu-West pass (device RNG, d <= 4): dst[i] = a * x[draw(u_i)] + (1-a) * mean + S @ eps[:, i]
+        with u and eps regenerated in the kernel from the Philox streams (seed_u, off_u) / (seed_n, off_n).
+        ``dst`` defaults to the alternate slab."""
+        if dst is None:
+            if self.x_alt is None or self.x_alt.shape[0] != n_new:
+                self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+            dst = self.x_alt
+        self._fused_scratch(n_new)
+        check(self.lib.qb_lw_draw_move(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._cdf), _ptr(self.ws),
+                                       self.ws_bytes, 1 if use_guide else 0, _lib.f64_array(mean),
+                                       _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
+                                       int(seed_u) & _U64_MASK, int(off_u) & _U64_MASK, int(seed_n) & _U64_MASK,
+                                       int(off_n) & _U64_MASK, 1 if scale_u else 0, int(n_new), _ptr(dst),
+                                       int(bool(postselect)), _ptr(self._invalid), _ptr(self.counter), _stream()))
+        self.launches += 1
+
+    def lw_draw_retry(self, mean, S, a, seed_u, off_u, seed_n, off_n, k, dst=None, scale_u=False, use_guide=True,
+                      own_mean=False):
+        dst = self.x_alt if dst is None else dst
+        check(self.lib.qb_lw_draw_retry(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._cdf), _ptr(self.ws),
+                                        self.ws_bytes, 1 if use_guide else 0, _lib.f64_array(mean),
+                                        _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
+                                        int(seed_u) & _U64_MASK, int(off_u) & _U64_MASK, int(seed_n) & _U64_MASK,
+                                        int(off_n) & _U64_MASK, 1 if scale_u else 0, _ptr(self._idxs), int(k),
+                                        1 if own_mean else 0, _ptr(dst), _ptr(self._invalid), _ptr(self.counter),
+                                        _stream()))
         self.launches += 1
 
     def read_counter(self):

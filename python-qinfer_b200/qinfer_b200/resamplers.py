@@ -38,6 +38,16 @@ from .distributions import ParticleDistribution, covariance_from_moments
 def sqrtm_psd(A, est_error=True, check_finite=True):
     """PSD matrix square root through ``scipy.linalg.eigh`` with non-positive
     eigenvalues clipped — the same host call as utils.py:593-607 (d x d, d <= 64)."""
+    A = np.asarray(A)
+    if A.shape == (1, 1) and np.isrealobj(A):
+        # eigh of a 1 x 1 matrix is (A[0,0], [[+-1]]): the same numbers without the LAPACK round trip
+        if check_finite and not np.isfinite(A[0, 0]):
+            raise ValueError("array must not contain infs or NaNs")
+        root = np.sqrt(A[0, 0]) if A[0, 0] > 0 else 0.0
+        A_sqrt = np.array([[root]], dtype=np.float64)
+        if est_error:
+            return A_sqrt, np.linalg.norm(np.dot(A_sqrt, A_sqrt) - A, 'fro')
+        return A_sqrt
     w, v = scipy.linalg.eigh(A, check_finite=check_finite)
     w[w <= 0] = 0
     np.sqrt(w, out=w)
@@ -100,6 +110,7 @@ class LiuWestResampler(Resampler):
         self._philox_offset = 0
         self.last_n_iters = 0
         self.last_overflow = 0
+        self._fused = True      # device-RNG mode: fused draw+move kernels (False: the staged launches, same result)
 
     @property
     def a(self):
@@ -141,6 +152,58 @@ class LiuWestResampler(Resampler):
             self._philox_offset += (d * k + 1) // 2
         return buf
 
+    def _staged_pass(self, cloud, mean, S, a, n_particles):
+        """CDF, uniforms, draw, normals, move as separate launches (any RNG, any d); u, js and eps live in HBM."""
+        d = cloud.d
+        cloud._resample_scratch(n_particles)
+        cloud.cdf(_lib.QB_SCAN_EXACT if self._scan == 'exact' else _lib.QB_SCAN_FAST)
+        cloud.draw(self._uniforms(cloud, n_particles), n_particles)
+        n_iters = 0
+        n_invalid = n_particles
+        first = True
+        while n_invalid and n_iters < self._maxiter:
+            n_iters += 1
+            if first:
+                eps = self._normals(cloud, d, n_particles)
+                cloud.lw_move(mean, S, a, eps, n_particles, self._postselect)
+                first = False
+            else:
+                cloud.compact_invalid(n_particles)
+                eps = self._normals(cloud, d, n_invalid)
+                cloud.lw_retry(mean, S, a, eps, n_invalid)
+            n_invalid, overflow = cloud.read_counter()
+            if n_iters == 1:
+                self.last_overflow = overflow
+        return n_iters, n_invalid
+
+    def _fused_pass(self, cloud, mean, S, a, n_particles, dst=None, scale_u=False, own_mean=False, seed=None,
+                    build_cdf=True):
+        """Device-RNG mode, d <= 4: the CDF pass also scatters the draw's guide table, and ONE kernel draws, gathers,
+        shrinks, perturbs and tests validity (u, js, eps never touch HBM).  Consumes the Philox streams exactly like
+        ``_staged_pass`` (uniforms, then normals per iteration), so both give bit-identical particles."""
+        d = cloud.d
+        seed = self._seed if seed is None else int(seed)
+        seed_u, seed_n = seed, seed ^ 0x9E3779B97F4A7C15
+        if build_cdf:
+            cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED if scale_u else _lib.QB_SCAN_FAST_GUIDE)
+        off_u = self._philox_offset
+        self._philox_offset += (n_particles + 1) // 2
+        off_n = self._philox_offset
+        self._philox_offset += (d * n_particles + 1) // 2
+        cloud.lw_draw_move(mean, S, a, seed_u, off_u, seed_n, off_n, n_particles, self._postselect, dst=dst,
+                           scale_u=scale_u)
+        n_invalid, self.last_overflow = cloud.read_counter()
+        n_iters = 1
+        while n_invalid and n_iters < self._maxiter:
+            n_iters += 1
+            cloud.compact_invalid(n_particles)
+            off_n = self._philox_offset
+            self._philox_offset += (d * n_invalid + 1) // 2
+            cloud.lw_draw_retry(mean, S, a, seed_u, off_u, seed_n, off_n, n_invalid, dst=dst, scale_u=scale_u,
+                                own_mean=own_mean)
+            n_invalid, _ = cloud.read_counter()
+        return n_iters, n_invalid
+
     # -- the call ------------------------------------------------------------------
     def __call__(self, model, particle_dist, n_particles=None, precomputed_mean=None, precomputed_cov=None):
         from .engine import DeviceCloud
@@ -177,26 +240,10 @@ class LiuWestResampler(Resampler):
         S = np.real(h * S)
 
         d = cloud.d
-        cloud._resample_scratch(n_particles)
-        cloud.cdf(_lib.QB_SCAN_EXACT if self._scan == 'exact' else _lib.QB_SCAN_FAST)
-        cloud.draw(self._uniforms(cloud, n_particles), n_particles)
-
-        n_iters = 0
-        n_invalid = n_particles
-        first = True
-        while n_invalid and n_iters < self._maxiter:
-            n_iters += 1
-            if first:
-                eps = self._normals(cloud, d, n_particles)
-                cloud.lw_move(mean, S, a, eps, n_particles, self._postselect)
-                first = False
-            else:
-                cloud.compact_invalid(n_particles)
-                eps = self._normals(cloud, d, n_invalid)
-                cloud.lw_retry(mean, S, a, eps, n_invalid)
-            n_invalid, overflow = cloud.read_counter()
-            if n_iters == 1:
-                self.last_overflow = overflow
+        if self._rng == 'philox' and self._scan == 'fast' and d <= 4 and n_particles <= cloud.n and self._fused:
+            n_iters, n_invalid = self._fused_pass(cloud, mean, S, a, n_particles)
+        else:
+            n_iters, n_invalid = self._staged_pass(cloud, mean, S, a, n_particles)
         if n_invalid:
             warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
                            "iterations.").format(n_invalid, self._maxiter), ResamplerWarning)

@@ -7,7 +7,13 @@ updater is sharded the same way, one process per GPU:
   update    each rank runs the fused kernel on its slab; the three sums it needs globally (sum w', sum w'^2,
             #bad) are all-reduced INSIDE that launch over the peers' NVLink-mapped mailboxes (qb_update.cu),
             so every rank publishes bit-identical global stats with no NCCL call and no extra launch.
-  resample  all-reduce of the 1 + d + d^2 moment sums, all-gather of the G shard totals (the global CDF is the
+  resample  d <= 4 ("split", the default): ONE all-gather of every rank's 1 + d + d^2 moment sums gives the global
+            mean/covariance AND the shard masses; every rank then draws the same multinomial split m ~ Mult(N, masses)
+            from a shared counter-based host generator, draws m[r] offspring from ITS OWN slab with the fused
+            draw+move kernel (a multinomial draw of N from the global CDF is exactly: split the count over the
+            shards, then draw within each shard), and only the surplus |m[r] - N/G| rows travel, in ONE all-to-all
+            whose counts every rank already knows (no count exchange, no index routing).
+            d > 4 ("route"): all-reduce of the moment sums, all-gather of the G shard totals (the global CDF is the
             shard CDFs offset by their exclusive prefix), then ONE request/response all-to-all: every draw is
             classified to the shard that owns its CDF range, the owner bisects its local CDF and sends the
             row back; shrink + perturb + validity run locally (NCCL through torch.distributed).
@@ -102,6 +108,19 @@ class ShardComm(object):
                                     input_split_sizes=[int(c) * width for c in send_counts], group=self.group)
         return recv
 
+    def all_gather_rows(self, row):
+        """(world, len(row)) host array of every rank's ``row`` (one collective, one host read)."""
+        out = torch.empty((self.world * row.numel(),), dtype=row.dtype, device=row.device)
+        self.dist.all_gather_into_tensor(out, row.contiguous(), group=self.group)
+        return out.cpu().numpy().reshape(self.world, row.numel())
+
+    def all_to_all_into(self, recv, send, send_counts, recv_counts, width=1):
+        """Variable all-to-all of rows of ``width`` elements straight into ``recv`` (a flat, contiguous view)."""
+        self.dist.all_to_all_single(recv, send.reshape(-1),
+                                    output_split_sizes=[int(c) * width for c in recv_counts],
+                                    input_split_sizes=[int(c) * width for c in send_counts], group=self.group)
+        return recv
+
     def all_gather_object(self, obj):
         out = [None] * self.world
         self.dist.all_gather_object(out, obj, group=self.group)
@@ -132,6 +151,64 @@ def route_resample(comm, ops, u, shard_total, width):
     rows_out = ops.gather_rows(js)
     rows = comm.all_to_all_v(rows_out, recv_counts, counts, width)
     return rows, perm, bounds
+
+
+def split_counts(rng, n_global, shard_masses):
+    """How many of the ``n_global`` offspring each shard produces: one multinomial draw over the shard masses.
+    ``rng`` is a counter-based generator seeded identically on every rank, so all ranks compute the same split
+    without communicating.  (Drawing N indices from the global CDF and counting them per shard has exactly this
+    distribution; the draws inside a shard are then i.i.d. from that shard's normalised weights.)"""
+    p = np.asarray(shard_masses, dtype=np.float64).copy()
+    p[~np.isfinite(p) | (p < 0)] = 0.0
+    if p.sum() <= 0:
+        p[:] = 1.0
+    p /= p.sum()
+    p[-1] = max(0.0, 1.0 - p[:-1].sum())         # Generator.multinomial wants sum(p[:-1]) <= 1
+    return [int(c) for c in rng.multinomial(int(n_global), p)]
+
+
+def exchange_plan(m, cap):
+    """T[r][q] = rows rank r sends to rank q so that every rank ends with cap[r] rows: surplus ranks hand their
+    extra offspring to deficit ranks, both visited in rank order (deterministic, computed by every rank)."""
+    G = len(m)
+    assert sum(m) == sum(cap)
+    T = [[0] * G for _ in range(G)]
+    need = [cap[r] - m[r] for r in range(G)]       # > 0: deficit
+    q = 0
+    for r in range(G):
+        s = m[r] - cap[r]
+        while s > 0:
+            while need[q] <= 0:
+                q += 1
+            t = min(s, need[q])
+            T[r][q] += t
+            need[q] -= t
+            s -= t
+    return T
+
+
+def split_resample(comm, ops, m, cap, width):
+    """The exchange of one "split" resample.  ``ops.slab()`` is this rank's (cap, width) destination,
+    ``ops.draw_into(dst2d)`` fills ``dst2d`` with offspring of the local slab, ``ops.alloc(rows)`` returns a
+    (rows, width) send buffer.  Returns how many rows this rank sent and received."""
+    r = comm.rank
+    keep = min(m[r], cap[r])
+    slab = ops.slab()
+    if keep:
+        ops.draw_into(slab[:keep])
+    extra = m[r] - keep
+    send = ops.alloc(extra)
+    done = 0
+    while done < extra:                                # chunks no larger than the slab (fixed scratch)
+        nc = min(cap[r], extra - done)
+        ops.draw_into(send[done:done + nc])
+        done += nc
+    T = exchange_plan(m, cap)
+    if any(any(row) for row in T):
+        recv_counts = [T[q][r] for q in range(comm.world)]
+        assert sum(recv_counts) == cap[r] - keep
+        comm.all_to_all_into(slab[keep:].reshape(-1), send, T[r], recv_counts, width)
+    return extra, cap[r] - keep
 
 
 # ---------------------------------------------------------------------------
@@ -252,7 +329,11 @@ def _make_sharded_updater_class():
         communication.
         """
 
-        def __init__(self, model, n_particles, prior, group=None, **kwargs):
+        def __init__(self, model, n_particles, prior, group=None, exchange='split', **kwargs):
+            if exchange not in ('split', 'route'):
+                raise ValueError("exchange must be 'split' or 'route'")
+            self._exchange = exchange
+            self._shard_masses = None
             self._comm = ShardComm(group)
             self._layout = ShardLayout(n_particles, self._comm.world)
             self._n_global = int(n_particles)
@@ -268,6 +349,12 @@ def _make_sharded_updater_class():
                 self.resampler = LiuWestResampler(rng='philox', scan='fast', seed=0x5EED)
             self._min_n_ess = self._n_global
             self._n_ess = float(self._n_global)
+            # "split" resample: the multinomial split is drawn by every rank from the SAME counter-based host
+            # generator (rank 0's resampler seed), the offspring from per-rank Philox streams
+            seeds = self._comm.all_gather_object(int(getattr(self.resampler, '_seed', 0x5EED)))
+            self._split_rng = np.random.Generator(np.random.Philox(key=int(seeds[0]) & ((1 << 64) - 1)))
+            self._stream_seed = (int(seeds[0]) + 0x9E3779B97F4A7C15 * (self._comm.rank + 1)) & ((1 << 64) - 1)
+            self.last_exchange = (0, 0)
             self._warm_collectives()
 
         def _warm_collectives(self):
@@ -275,6 +362,7 @@ def _make_sharded_updater_class():
             dev = self._cloud.device
             comm = self._comm
             comm.all_reduce_sum(torch.zeros((4,), dtype=torch.float64, device=dev))
+            comm.all_gather_rows(torch.zeros((4,), dtype=torch.float64, device=dev))
             comm.all_gather_scalars(0.0, dev)
             cnt = comm.exchange_counts([1] * comm.world, dev)
             comm.all_to_all_v(torch.zeros((comm.world,), dtype=torch.float64, device=dev), [1] * comm.world, cnt, 1)
@@ -349,8 +437,11 @@ def _make_sharded_updater_class():
                                             ctypes.c_void_p(cloud.ws.data_ptr()), cloud.ws_bytes,
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             cloud.launches += 2
-            self._comm.all_reduce_sum(cloud.moments_out)
-            out = cloud.moments_out.cpu().numpy()
+            rows = self._comm.all_gather_rows(cloud.moments_out)      # one collective, one host read
+            out = rows[0].copy()
+            for r in range(1, rows.shape[0]):                         # fixed rank order: identical on every rank
+                out += rows[r]
+            self._shard_masses = rows[:, 0].copy()
             d = cloud.d
             return out[0], out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
 
@@ -403,6 +494,11 @@ def _make_sharded_updater_class():
                                      "Check that n_ess is not too small.")
             S = np.real(h * S)
 
+            if d <= 4 and getattr(res, '_fused', False) and self._exchange == 'split':
+                self._split_pass(mean, S, a)
+                self._finish_resample(ev)
+                return
+
             cloud._resample_scratch(n_local)
             cdf = cloud.cdf(_lib.QB_SCAN_FAST)                       # local scan of globally normalised weights
             shard_total = float(cdf[-1].item())
@@ -446,9 +542,40 @@ def _make_sharded_updater_class():
                     break
             res.last_n_iters = n_iters
 
+            self._finish_resample(ev)
+
+        def _split_pass(self, mean, S, a):
+            """Offspring counts by a shared multinomial split, offspring drawn locally by the fused kernel, surplus
+            rows moved in one all-to-all (module docstring)."""
+            res, cloud, comm = self.resampler, self._cloud, self._comm
+            m = split_counts(self._split_rng, self._n_global, self._shard_masses)
+            cloud.preallocate_resample_slab()
+            state = {'cdf': True, 'iters': 0}
+            updater = self
+
+            class Ops(object):
+                def slab(self):
+                    return cloud.x_alt
+
+                def alloc(self, rows):
+                    return torch.empty((rows, cloud.d), dtype=torch.float64, device=cloud.device)
+
+                def draw_into(self, dst):
+                    it, bad = res._fused_pass(cloud, mean, S, a, dst.shape[0], dst=dst, scale_u=True, own_mean=True,
+                                              seed=updater._stream_seed, build_cdf=state['cdf'])
+                    state['cdf'] = False
+                    state['iters'] = max(state['iters'], it)
+                    if bad:
+                        warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                                       "iterations.").format(bad, res._maxiter), ResamplerWarning)
+
+            self.last_exchange = split_resample(comm, Ops(), m, self._layout.counts, cloud.d)
+            res.last_n_iters = state['iters']
+
+        def _finish_resample(self, ev):
+            cloud = self._cloud
             cloud.x, cloud.x_alt = cloud.x_alt, cloud.x
-            cloud.cur = cloud.cur                                     # weights buffer stays, contents reset:
-            self._set_global_uniform()
+            self._set_global_uniform()                                # weights buffer stays, contents reset
             self._host_locs = self._host_weights = None
             if self._canonicalize:
                 cloud.canonicalize()

@@ -448,6 +448,9 @@ class SMCUpdater(object):
         new_dist = self.resampler(self.model, self)
         if isinstance(new_dist, DeviceParticles) and new_dist.cloud is self._cloud:
             self._cloud.adopt_resampled(new_dist.n_particles)
+            # uniform weights 1/n: the stats block the kernel wrote is {norm 1, sumsq 1/n}; same two roundings here,
+            # without a device read
+            self._n_ess = self._ness_from(1.0, np.float64(1.0) / np.float64(new_dist.n_particles), normalised=True)
         else:                                                # a foreign resampler working on host arrays
             locs = np.asarray(new_dist.particle_locations, dtype=np.float64)
             weights = np.asarray(new_dist.particle_weights, dtype=np.float64)
@@ -455,9 +458,9 @@ class SMCUpdater(object):
                 self._rebuild_cloud(locs.shape[0])
             self._cloud.upload_locations(locs)
             self._cloud.upload_weights(weights)
+            st = self._cloud.read_stats()
+            self._n_ess = self._ness_from(st[QB_STAT_NORM], st[QB_STAT_SUMSQ], normalised=True)
         self._host_locs = self._host_weights = None
-        st = self._cloud.read_stats()
-        self._n_ess = self._ness_from(st[QB_STAT_NORM], st[QB_STAT_SUMSQ], normalised=True)
 
         if self._canonicalize:
             self._cloud.canonicalize()

@@ -659,3 +659,86 @@ def test_mt19937_mode_same_indices_as_numpy_mode_at_scale(qb):
     (xa, sa), (xb, sb) = outs
     assert np.array_equal(sa[1], sb[1]) and sa[2:4] == sb[2:4]
     np.testing.assert_allclose(xb, xa, rtol=0, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------
+# Fused draw + move (device-RNG mode): one kernel == the four staged launches, bit for bit
+# ---------------------------------------------------------------------------
+def _fused_case(qb, kind, n, seed):
+    rs = np.random.RandomState(seed)
+    if kind == "prec":
+        model, x = qb.SimplePrecessionModel(), rs.random_sample((n, 1))
+    elif kind == "prec_minfreq":          # a tenth of the offspring is invalid -> several retry rounds
+        model, x = qb.SimplePrecessionModel(min_freq=0.35), 0.35 + 0.3 * rs.random_sample((n, 1))
+    elif kind == "rb":                    # d = 3, many offspring violate A + B <= 1
+        model = qb.RandomizedBenchmarkingModel()
+        x = np.column_stack([0.8 + 0.2 * rs.random_sample(n), 0.5 * rs.random_sample(n), 0.5 * rs.random_sample(n)])
+    else:                                 # interleaved RB, d = 4
+        model = qb.RandomizedBenchmarkingModel(interleaved=True)
+        x = np.column_stack([0.9 + 0.1 * rs.random_sample(n), 0.8 + 0.2 * rs.random_sample(n),
+                             0.5 * rs.random_sample(n), 0.5 * rs.random_sample(n)])
+    w = rs.random_sample(n) ** 4
+    w[rs.randint(0, n, size=max(n // 50, 1))] = 0.0          # exact zeros: repeated CDF entries
+    if n > 10:
+        w[n // 3] = 40.0 * w.sum() / n                       # one heavy particle: a long bucket range in the guide
+    return model, x, w / w.sum()
+
+
+@pytest.mark.parametrize("kind,n,n_new", [("prec", 1000, None), ("prec", 4096, None), ("prec", 100003, None),
+                                          ("prec_minfreq", 50001, None), ("rb", 65537, None), ("rb", 30000, 29999),
+                                          ("rb_il", 20001, None), ("prec", 3000001, None), ("prec", 9, None),
+                                          ("rb", 2 ** 20, None)])
+def test_fused_draw_move_bit_identical_to_staged(qb, kind, n, n_new):
+    """qb_cdf(FAST_GUIDE) + qb_lw_draw_move / qb_lw_draw_retry against qb_cdf(FAST) + qb_rng_uniform + qb_draw +
+    qb_rng_normal + qb_lw_move / qb_compact_invalid / qb_lw_retry on the same cloud and Philox streams: identical
+    particles, identical retry rounds, identical clamp count."""
+    model, x, w = _fused_case(qb, kind, n, 17)
+    out = []
+    for fused in (False, True):
+        res = qb.LiuWestResampler(a=0.9, rng='philox', seed=1234567, scan='fast')
+        res._fused = fused
+        up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
+        up.particle_weights = w
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            new = res(model, up, n_particles=n_new)
+        out.append((new.particle_locations.copy(), res.last_n_iters, res.last_overflow, res._philox_offset))
+    (xs, it_s, ov_s, off_s), (xf, it_f, ov_f, off_f) = out
+    assert xs.shape == xf.shape == ((n if n_new is None else n_new), x.shape[1])
+    assert (it_s, ov_s, off_s) == (it_f, ov_f, off_f)
+    assert np.array_equal(xs, xf)
+    if kind in ("prec_minfreq", "rb", "rb_il"):
+        assert it_f > 1                                        # the retry kernel was exercised
+
+
+@pytest.mark.parametrize("n", [4096, 10 ** 5 + 3, 2 ** 21])
+def test_fused_resample_against_oracle_given_the_same_variates(qb, oracle, n):
+    """The fused kernel regenerates element i of the Philox streams; materialise the same streams with
+    qb_rng_uniform / qb_rng_normal, hand them to the NumPy oracle's Liu-West arithmetic, compare the particles."""
+    import torch
+    from qinfer_b200.engine import _ptr, _stream
+    model, x, w = _fused_case(qb, "prec", n, 5)
+    seed = 99
+    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=seed, scan='fast')
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
+    up.particle_weights = w
+    cloud = up._cloud
+    u = torch.empty((n,), dtype=torch.float64, device=cloud.device)
+    e = torch.empty((n,), dtype=torch.float64, device=cloud.device)
+    cloud.rng_uniform(u, n, seed, 0)
+    cloud.rng_normal(e, n, seed ^ 0x9E3779B97F4A7C15, (n + 1) // 2)
+    cdf = cloud.cdf(qb._lib.QB_SCAN_FAST).cpu().numpy().copy()
+    mean, cov = up.est_mean(), up.est_covariance_mtx()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        new = res(model, up)
+    got = new.particle_locations
+    js = np.minimum(cdf.searchsorted(u.cpu().numpy(), side='right'), n - 1)     # resamplers.py:318-321
+    S = np.real(res.h * oracle.sqrtm_psd(cov)[0])
+    mus = 0.98 * x[js] + (1 - 0.98) * mean                                      # resamplers.py:325
+    want = mus + np.dot(S, e.cpu().numpy()[None, :]).T                          # resamplers.py:332
+    valid = want[:, 0] > 0
+    assert valid.mean() > 0.99
+    assert np.array_equal(got[valid], want[valid])                              # d = 1: bit-exact by construction
+    # the scanned CDF is a valid input for the guide: non-decreasing and ending at ~1
+    assert np.all(np.diff(cdf) >= 0) and abs(cdf[-1] - 1) < 1e-12

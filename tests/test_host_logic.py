@@ -120,3 +120,19 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "smc_oracle" not in src and "import oracle" not in src, fn
+
+
+def test_sqrtm_psd_one_by_one_shortcut_equals_eigh():
+    """The 1 x 1 shortcut returns exactly what the scipy.linalg.eigh route of utils.py:593-607 returns."""
+    import scipy.linalg
+    for a in (0.0, 1e-300, 3.7e-9, 0.25, 2.0, 1e300, -1e-12):
+        A = np.array([[a]])
+        w, v = scipy.linalg.eigh(A)
+        w[w <= 0] = 0
+        np.sqrt(w, out=w)
+        want = (v * w).dot(v.conj().T)
+        want_err = np.linalg.norm(np.dot(want, want) - A, 'fro')
+        got, err = qb.sqrtm_psd(A)
+        assert got.shape == (1, 1) and got[0, 0] == want[0, 0] and err == want_err
+    with pytest.raises(ValueError):
+        qb.sqrtm_psd(np.array([[np.nan]]))

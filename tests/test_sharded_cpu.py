@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from qinfer_b200.sharded import ShardComm, ShardLayout, cdf_bounds, route_resample
+from qinfer_b200.sharded import (ShardComm, ShardLayout, cdf_bounds, exchange_plan, route_resample, split_counts,
+                                 split_resample)
 
 
 def _free_port():
@@ -123,3 +124,101 @@ def test_shard_layout():
     with pytest.raises(ValueError):
         ShardLayout(2, 3)
     assert cdf_bounds([0.25, 0.5, 0.25]) == [0.0, 0.25, 0.75, 1.0]
+
+
+# ---------------------------------------------------------------------------
+# "split" resample: shared multinomial split + local draws + one all-to-all of the surplus rows
+# ---------------------------------------------------------------------------
+def test_exchange_plan_balances_every_rank():
+    rs = np.random.RandomState(3)
+    for G in (1, 2, 3, 8):
+        cap = ShardLayout(1000 * G + 3, G).counts
+        for _ in range(20):
+            m = [int(c) for c in rs.multinomial(sum(cap), rs.dirichlet(np.ones(G) * 0.3))]
+            T = np.array(exchange_plan(m, cap))
+            assert T.shape == (G, G) and (T >= 0).all() and np.trace(T) == 0
+            sent, recv = T.sum(axis=1), T.sum(axis=0)
+            for r in range(G):
+                assert sent[r] == max(m[r] - cap[r], 0)
+                assert recv[r] == max(cap[r] - m[r], 0)
+                assert min(m[r], cap[r]) + recv[r] == cap[r]
+    assert exchange_plan([5, 5], [5, 5]) == [[0, 0], [0, 0]]
+    assert exchange_plan([10, 0, 2], [4, 4, 4]) == [[0, 4, 2], [0, 0, 0], [0, 0, 0]]
+
+
+def test_split_counts_is_a_shared_multinomial():
+    masses = [0.1, 0.0, 0.6, 0.3]
+    a = split_counts(np.random.Generator(np.random.Philox(key=7)), 10 ** 6, masses)
+    b = split_counts(np.random.Generator(np.random.Philox(key=7)), 10 ** 6, masses)
+    assert a == b and sum(a) == 10 ** 6 and a[1] == 0
+    assert all(abs(c - 1e6 * p) < 6 * np.sqrt(1e6 * p * (1 - p)) + 1 for c, p in zip(a, masses))
+    # degenerate masses fall back to an even split instead of raising
+    c = split_counts(np.random.Generator(np.random.Philox(key=1)), 1000, [float('nan'), 0.0])
+    assert sum(c) == 1000
+
+
+class SplitOps(object):
+    """CPU stand-in for the fused draw+move kernel: offspring rows are tagged (origin rank, serial number)."""
+
+    def __init__(self, rank, cap, width):
+        self.rank, self.width = rank, width
+        self._slab = torch.full((cap, width), -1.0, dtype=torch.float64)
+        self.made = 0
+
+    def slab(self):
+        return self._slab
+
+    def alloc(self, rows):
+        return torch.empty((rows, self.width), dtype=torch.float64)
+
+    def draw_into(self, dst):
+        k = dst.shape[0]
+        assert k <= self._slab.shape[0]                 # chunks never exceed the slab (fixed scratch)
+        dst[:, 0] = self.rank
+        dst[:, 1:] = torch.arange(self.made, self.made + k, dtype=torch.float64)[:, None]
+        self.made += k
+
+
+def _split_worker(rank, world, port, n_global, masses, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ShardComm()
+        layout = ShardLayout(n_global, world)
+        rng = np.random.Generator(np.random.Philox(key=99))      # same key on every rank
+        m = split_counts(rng, n_global, masses)
+        ops = SplitOps(rank, layout.counts[rank], 3)
+        sent, recv = split_resample(comm, ops, m, layout.counts, 3)
+        rows = comm.all_gather_rows(torch.tensor([float(rank), 1.0, 2.0], dtype=torch.float64))
+        np.savez(os.path.join(out_dir, "s%d.npz" % rank), slab=ops.slab().numpy(), m=np.asarray(m), made=ops.made,
+                 sent=sent, recv=recv, rows=rows)
+        comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_global,masses", [(2, 1001, [0.5, 0.5]), (3, 3000, [0.7, 0.1, 0.2]),
+                                                   (2, 400, [1.0, 0.0])])
+def test_split_resample_moves_only_the_surplus(tmp_path, world, n_global, masses):
+    port = _free_port()
+    mp.spawn(_split_worker, args=(world, port, n_global, masses, str(tmp_path)), nprocs=world, join=True)
+    layout = ShardLayout(n_global, world)
+    files = [np.load(os.path.join(str(tmp_path), "s%d.npz" % r)) for r in range(world)]
+    m = list(files[0]["m"])
+    assert sum(m) == n_global
+    seen = set()
+    for r, f in enumerate(files):
+        assert list(f["m"]) == m                              # every rank computed the same split
+        assert int(f["made"]) == m[r]                         # and drew exactly its share from its own slab
+        assert int(f["sent"]) == max(m[r] - layout.counts[r], 0)
+        assert int(f["recv"]) == max(layout.counts[r] - m[r], 0)
+        slab = f["slab"]
+        assert slab.shape == (layout.counts[r], 3) and (slab[:, 0] >= 0).all()      # full, nothing left unwritten
+        assert np.array_equal(slab[:, 1], slab[:, 2])
+        keep = min(m[r], layout.counts[r])
+        assert (slab[:keep, 0] == r).all()                    # own offspring stay in place
+        seen.update((int(o), int(k)) for o, k in slab[:, :2])
+        assert np.array_equal(f["rows"], np.array([[q, 1.0, 2.0] for q in range(world)]))
+    # the union of the slabs is exactly the set of offspring drawn: nothing lost, nothing duplicated
+    assert seen == {(r, k) for r in range(world) for k in range(m[r])}
