@@ -71,6 +71,30 @@ __device__ __forceinline__ void tma_load_1d(uint32_t smem_dst, const void* gmem_
         "l"(gmem_src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy result)
+__device__ __forceinline__ void tma_load_1d_hint(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_dst),
+        "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // ---- streaming global access ------------------------------------------------
 __device__ __forceinline__ double ldg_stream(const double* p) {
     double v;

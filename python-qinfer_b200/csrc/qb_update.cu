@@ -47,7 +47,11 @@ struct UpdateParams {
     double* mirror;          // device-accessible pinned host block, nsteps x 8 doubles (or NULL)
     double tag;
     double zero_weight_thresh, resample_below;
-    int32_t guard, pad0;
+    int32_t guard;
+    int32_t reverse;         // 1: walk the tiles from the END of the slab (zig-zag across launches, see the kernel)
+    int32_t l2hint;          // bit 0: w_in evict_first, bit 1: x evict_last, bit 2: w_out evict_last, bit 3: partition
+    int32_t pin_tiles;       // partition mode: tiles [0, pin_tiles) of x / w_in / w_out are kept in L2 (evict_last),
+                             // the rest streams through (evict_first)
     int32_t n_ranks, rank;   // > 1: all-reduce the sums over the peers' mailboxes inside this launch
     double* peer_mbox[QB_MAX_RANKS];
     int32_t* error_flag;     // device int set to 1 if the peer wait timed out
@@ -246,7 +250,8 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
     }
     const uint32_t bar0 = smem_u32(smem_raw);  // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
     const uint32_t ring0 = smem_u32(ring);
-    const int ntiles = static_cast<int>((p.n + tile - 1) / tile);
+    // the ring carries FULL tiles only; the ragged remainder (n % tile particles) is read directly by the last block
+    const int ntiles = static_cast<int>(p.n / tile);
     const int my_tiles = (ntiles > static_cast<int>(blockIdx.x))
                              ? (ntiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                                    static_cast<int>(gridDim.x)
@@ -270,22 +275,34 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
     unsigned int bad = 0u;
 #pragma unroll
     for (int j = 0; j < KF; ++j) acc[j] = {0.0, 0.0};
-    const int64_t tile_stride = static_cast<int64_t>(gridDim.x) * tile;
+    // Zig-zag: consecutive launches walk the slab in opposite directions.  One update streams 8(d+2) n bytes —
+    // twice the L2 at n = 1e7 — so a launch that restarts at tile 0 finds nothing of the previous pass; starting
+    // where the previous launch ENDED finds the tail of x and of the weights it just wrote still resident.
+    const int64_t last_tile = static_cast<int64_t>(ntiles) - 1;
+    auto tile_first = [&](int i) -> int64_t {
+        const int64_t ti = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+        return (p.reverse ? last_tile - ti : ti) * tile;
+    };
 
     if (tid >= NCT) {
         // ===== producer warp: one lane streams my tiles into the ring =====
         if (tid == NCT) {
             int s = 0;
             uint32_t phase = 0;
-            int64_t first = static_cast<int64_t>(blockIdx.x) * tile;
-            for (int i = 0; i < my_tiles; ++i, first += tile_stride) {
-                if (first + tile <= p.n) {  // full tile (the ragged last one is read directly by the consumers)
-                    mbar_wait(bar0 + 64 + 8 * s, phase ^ 1u);  // passes at once the first time round the ring
-                    const uint32_t dst = ring0 + static_cast<uint32_t>(s) * stage_bytes;
-                    mbar_expect_tx(bar0 + 8 * s, stage_bytes);
-                    tma_load_1d(dst, p.x + first * d, x_bytes, bar0 + 8 * s);
-                    tma_load_1d(dst + x_bytes, p.w_in + first, w_bytes, bar0 + 8 * s);
-                }
+            // L2 residency: w_in is dead once read (the next launch overwrites it), x and the new weights are what
+            // the next launch reads first (it walks the slab in the opposite direction)
+            uint64_t pol_w = (p.l2hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+            uint64_t pol_x = (p.l2hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+            const int64_t pin_end = static_cast<int64_t>(p.pin_tiles) * tile;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int64_t first = tile_first(i);
+                if (p.l2hint & 8) pol_w = pol_x = (first < pin_end) ? pol_keep : pol_stream;
+                mbar_wait(bar0 + 64 + 8 * s, phase ^ 1u);  // passes at once the first time round the ring
+                const uint32_t dst = ring0 + static_cast<uint32_t>(s) * stage_bytes;
+                mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+                tma_load_1d_hint(dst, p.x + first * d, x_bytes, bar0 + 8 * s, pol_x);
+                tma_load_1d_hint(dst + x_bytes, p.w_in + first, w_bytes, bar0 + 8 * s, pol_w);
                 if (++s == UPD_STAGES) {
                     s = 0;
                     phase ^= 1u;
@@ -300,10 +317,15 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         auto meas = [&](int c) { return meas_s[c]; };
         int s = 0;
         uint32_t phase = 0;
-        int64_t first = static_cast<int64_t>(blockIdx.x) * tile;
-        for (int i = 0; i < my_tiles; ++i, first += tile_stride) {
+        const bool keep_out = (p.l2hint & 4) != 0;
+        uint64_t pol_o = keep_out ? l2_policy_evict_last() : l2_policy_evict_normal();
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const int64_t pin_end = static_cast<int64_t>(p.pin_tiles) * tile;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int64_t first = tile_first(i);
+            if (p.l2hint & 8) pol_o = (first < pin_end) ? pol_keep : pol_stream;
             double* wo = p.w_out + first;
-            if (first + tile <= p.n) {
+            {
                 const unsigned char* stage = ring + static_cast<size_t>(s) * stage_bytes;
                 const double* xs = reinterpret_cast<const double*>(stage);
                 const double* ws = reinterpret_cast<const double*>(stage + x_bytes);
@@ -335,8 +357,9 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
                                 accumulate(acc[k], bad, k, w1);
                             }
                         }
-                        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(wo + 2 * j), "d"(w0),
-                                     "d"(w1)
+                        asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(
+                                         wo + 2 * j),
+                                     "d"(w0), "d"(w1), "l"(pol_o)
                                      : "memory");
                     }
                 } else {
@@ -356,25 +379,27 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar0 + 64 + 8 * s);  // this warp is done with stage s
-            } else {  // ragged last tile: straight from global memory
-                const int cnt = static_cast<int>(p.n - first);
-                for (int j = tid; j < cnt; j += NCT) {
-                    const double* xr = p.x + (first + j) * d;
-                    auto row = [&](int c) { return xr[c]; };
-                    double wv = p.w_in[first + j] * inv_norm;
-#pragma unroll
-                    for (int k = 0; k < KF; ++k) {
-                        if (KF == 1 || k < nsteps) {
-                            wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, 0);
-                            accumulate(acc[k], bad, k, wv);
-                        }
-                    }
-                    wo[j] = wv;
-                }
             }
             if (++s == UPD_STAGES) {
                 s = 0;
                 phase ^= 1u;
+            }
+        }
+        if (blockIdx.x == gridDim.x - 1) {  // ragged remainder: straight from global memory
+            const int64_t first = static_cast<int64_t>(ntiles) * tile;
+            const int cnt = static_cast<int>(p.n - first);
+            for (int j = tid; j < cnt; j += NCT) {
+                const double* xr = p.x + (first + j) * d;
+                auto row = [&](int c) { return xr[c]; };
+                double wv = p.w_in[first + j] * inv_norm;
+#pragma unroll
+                for (int k = 0; k < KF; ++k) {
+                    if (KF == 1 || k < nsteps) {
+                        wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, 0);
+                        accumulate(acc[k], bad, k, wv);
+                    }
+                }
+                p.w_out[first + j] = wv;
             }
         }
     }
@@ -568,7 +593,25 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
     p.zero_weight_thresh = ctl ? ctl->zero_weight_thresh : 0.0;
     p.resample_below = ctl ? ctl->resample_below : 0.0;
     p.guard = ctl ? ctl->guard : 0;
-    p.pad0 = 0;
+    {
+        // experiment knobs (defaults are the measured best): QB_UPD_ZIGZAG=0 disables the alternating direction,
+        // QB_UPD_L2HINT=<bits> selects the L2 eviction hints
+        static int zig = -1, hint = -1, pin_mb = 72;
+        if (zig < 0) {
+            const char* e1 = getenv("QB_UPD_ZIGZAG");
+            const char* e2 = getenv("QB_UPD_L2HINT");
+            const char* e3 = getenv("QB_UPD_PIN_MB");
+            zig = e1 ? atoi(e1) : 1;
+            hint = e2 ? atoi(e2) : 5;
+            if (e3) pin_mb = atoi(e3);
+        }
+        // the ping-pong weight buffers swap roles every launch: the direction follows which one is the source
+        p.reverse = (zig && reinterpret_cast<uintptr_t>(d_w_in) > reinterpret_cast<uintptr_t>(d_w_out)) ? 1 : 0;
+        p.l2hint = hint;
+        // partition mode: pin_mb MB of L2 shared by the head of x and of BOTH weight buffers
+        const double per_tile = static_cast<double>(choose_tile(model->d)) * 8.0 * (model->d + 2);
+        p.pin_tiles = static_cast<int32_t>(static_cast<double>(pin_mb) * 1e6 / per_tile);
+    }
     p.n_ranks = ctl ? ctl->n_ranks : 0;
     p.rank = ctl ? ctl->rank : 0;
     p.error_flag = ctl ? ctl->d_error_flag : nullptr;

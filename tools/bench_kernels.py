@@ -58,6 +58,13 @@ def bench_update(n, model, ep_setup, d, label, fuse_list=(1,)):
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 10 ** 7
+    if what == "update1":
+        def prec1(ep):
+            ep.t = 17.3
+            return 1
+        print("QB_UPD_ZIGZAG=%s QB_UPD_L2HINT=%s" % (os.environ.get("QB_UPD_ZIGZAG"), os.environ.get("QB_UPD_L2HINT")))
+        bench_update(n, qb.SimplePrecessionModel(), prec1, 1, "update precession d=1", (1, 8))
+        return
     if what in ("update", "all"):
         def prec(ep):
             ep.t = 17.3
