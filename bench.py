@@ -315,7 +315,10 @@ def gpu_arm(args, rank, world, local_rank):
         if world > 1:
             up.close()
         del up
-        host_prior = prior                               # pageable NumPy array, as a user holds it
+        # the user's host array, page-locked (the base contract times the H2D copy "from pinned host memory")
+        pinned_prior = torch.empty((n, 1), dtype=torch.float64, pin_memory=True)
+        pinned_prior.numpy()[:] = prior
+        prior = pinned_prior.numpy()
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

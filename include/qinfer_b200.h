@@ -55,7 +55,9 @@ extern "C" {
 enum qb_model_kind {
     QB_MODEL_PRECESSION = 1, /* SimpleInversionModel / SimplePrecessionModel  test_models.py:123-143,188-197 */
     QB_MODEL_RB = 2,         /* RandomizedBenchmarkingModel                   rb.py:149-195                  */
-    QB_MODEL_TOMOGRAPHY = 3  /* tomography.TomographyModel                    tomography/models.py:143-226   */
+    QB_MODEL_TOMOGRAPHY = 3, /* tomography.TomographyModel                    tomography/models.py:143-226   */
+    QB_MODEL_COIN = 4        /* CoinModel (pr0 = p; the model of the reference's risk / information-gain
+                                known-answer tests, tests/test_metrics.py)    test_models.py:262-326         */
 };
 
 typedef struct qb_model {
@@ -186,6 +188,21 @@ int qb_hypothetical_update(const qb_model* model, const qb_expparams* eps, int32
                            const double* d_x, const double* d_w, const double* d_stats, int64_t n,
                            double* d_weights, double* d_L, double* d_norms,
                            void* d_ws, size_t ws_bytes, void* stream);
+
+/* Experiment design (SMCUpdater.bayes_risk, smc.py:553-605; expected_information_gain, smc.py:607-657) for ONE
+ * experiment `ep` with outcome list `outcomes` (HOST, n_o entries = model.domain(ep).values): the likelihood of
+ * the LAST outcome is taken as 1 - sum of the others, as the reference does.  With h_oi = w_i L_oi:
+ *   d_sums[o][0]       = N_o = sum_i h_oi
+ *   d_sums[o][1+j]     = sum_i h_oi (x_ij - centre_j)          j < d
+ *   d_sums[o][1+d+j]   = sum_i h_oi (x_ij - centre_j)^2
+ *   d_kld[o] (if not NULL) = sum_i w_hyp_oi log(w_hyp_oi / w_i),  w_hyp_oi = h_oi / N_o  (smc.py:651)
+ * `h_centre` (HOST, d doubles) is any reference point (the posterior mean keeps the variance formula
+ * var = C/N - (B/N)^2 free of cancellation).  The (n_o, n) tensors of the reference never exist. */
+size_t qb_design_workspace_bytes(int64_t n, int32_t d, int32_t n_o);
+int qb_design_sums(const qb_model* model, const qb_expparams* ep, const int64_t* outcomes, int32_t n_o,
+                   const double* d_x, const double* d_w, const double* d_stats, int64_t n,
+                   const double* h_centre, double* d_sums, double* d_kld,
+                   void* d_ws, size_t ws_bytes, void* stream);
 
 /* Model.are_models_valid (test_models.py:109-110, rb.py:149-176,
  * tomography/models.py:143-147): d_valid[i] in {0,1}. */

@@ -178,6 +178,18 @@ class _ModelBase(object):
 
     is_n_outcomes_constant = True
 
+    @property
+    def Q(self):
+        # abstract_model.py:170-186: identity scale matrix unless a subclass says otherwise
+        return np.ones((self.n_modelparams,))
+
+    def domain(self, expparams):
+        # abstract_model.py:287-298
+        if expparams is None:
+            return IntegerDomain(0, 1)
+        n_o = np.broadcast_to(np.asarray(self.n_outcomes(expparams)), (np.asarray(expparams).shape[0],))
+        return [IntegerDomain(0, int(k) - 1) for k in n_o]
+
     def simulate_experiment(self, modelparams, expparams, repeat=1):
         """abstract_model.py:632-658 for constant two-outcome domains."""
         all_outcomes = np.arange(2)
@@ -189,6 +201,31 @@ class _ModelBase(object):
         if repeat == 1 and expparams.shape[0] == 1 and modelparams.shape[0] == 1:
             return outcomes[0, 0, 0]
         return outcomes
+
+
+class IntegerDomain(object):
+    """domains.py:427-560: the ``values`` of an integer outcome domain."""
+
+    def __init__(self, min=0, max=1):
+        self.min, self.max = int(min), int(max)
+
+    @property
+    def values(self):
+        return np.arange(self.min, self.max + 1, dtype=int)
+
+
+class CoinModel(_ModelBase):
+    """test_models.py:262-326: pr0 is the model parameter itself."""
+    n_modelparams = 1
+    expparams_dtype = []
+
+    def are_models_valid(self, modelparams):
+        return np.logical_and(modelparams >= 0, modelparams <= 1).all(axis=1)     # test_models.py:303-304
+
+    def likelihood(self, outcomes, modelparams, expparams):
+        self._count(outcomes, modelparams, expparams)
+        pr0 = np.tile(modelparams.flatten(), (expparams.shape[0], 1)).T           # test_models.py:323
+        return two_outcome_likelihood(outcomes, pr0)
 
 
 class SimpleInversionModel(_ModelBase):
@@ -726,6 +763,46 @@ class SMCUpdater(ParticleDistribution):
         if return_normalization:
             out += (norm_scale,)
         return out[0] if len(out) == 1 else out
+
+    def _hypothetical_posteriors(self, expparams):
+        # smc.py:576-595 / 628-647: every outcome's hypothetical weights and normalisation; the last outcome's
+        # likelihood is the complement of the others
+        os_ = self.model.domain(expparams[0, np.newaxis])[0].values
+        w_hyp, L, N = self.hypothetical_update(os_[:-1], expparams, return_normalization=True,
+                                               return_likelihood=True)
+        w_hyp_last_outcome = (1 - L.sum(axis=0)) * self.particle_weights[np.newaxis, :]
+        N = np.concatenate([N[:, :, 0], np.sum(w_hyp_last_outcome[np.newaxis, :, :], axis=2)], axis=0)
+        w_hyp_last_outcome = w_hyp_last_outcome / N[-1, :, np.newaxis]
+        w_hyp = np.concatenate([w_hyp, w_hyp_last_outcome[np.newaxis, :, :]], axis=0)
+        return w_hyp, N
+
+    def bayes_risk(self, expparams):
+        # smc.py:553-605
+        n_eps = expparams.size
+        if n_eps > 1 and not self.model.is_n_outcomes_constant:
+            risk = np.empty(n_eps)
+            for idx in range(n_eps):
+                risk[idx] = self.bayes_risk(expparams[idx, np.newaxis])[0]
+            return risk
+        w_hyp, N = self._hypothetical_posteriors(expparams)
+        mu_hyp = np.dot(w_hyp, self.particle_locations)
+        var_hyp = np.sum(
+            w_hyp * np.sum(self.model.Q * (self.particle_locations[np.newaxis, np.newaxis, :, :]
+                                           - mu_hyp[:, :, np.newaxis, :]) ** 2, axis=3),
+            axis=2)
+        return np.sum(N * var_hyp, axis=0)
+
+    def expected_information_gain(self, expparams):
+        # smc.py:607-657
+        n_eps = expparams.size
+        if n_eps > 1 and not self.model.is_n_outcomes_constant:
+            gain = np.empty(n_eps)
+            for idx in range(n_eps):
+                gain[idx] = self.expected_information_gain(expparams[idx, np.newaxis])[0]
+            return gain
+        w_hyp, N = self._hypothetical_posteriors(expparams)
+        KLD = np.sum(w_hyp * np.log(w_hyp / self.particle_weights), axis=2)
+        return np.sum(N * KLD, axis=0)
 
     def update(self, outcome, expparams, check_for_resample=True):
         # smc.py:388-457

@@ -20,7 +20,7 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "qinfer_b200", "libqinfer_b200.so")
 
 SOURCES = ["qb_misc.cu", "qb_update.cu", "qb_moments.cu", "qb_resample.cu", "qb_tomography.cu", "qb_rng.cu",
-           "qb_dist.cu", "qb_scan_exact.cu", "qb_mt19937.cu"]
+           "qb_dist.cu", "qb_scan_exact.cu", "qb_mt19937.cu", "qb_design.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

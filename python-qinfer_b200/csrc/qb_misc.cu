@@ -308,6 +308,8 @@ extern "C" int qb_likelihood(const qb_model* model, const qb_expparams* eps, int
                 QB_LAUNCH_LIK(QB_MODEL_PRECESSION)
             } else if (model->kind == QB_MODEL_RB) {
                 QB_LAUNCH_LIK(QB_MODEL_RB)
+            } else if (model->kind == QB_MODEL_COIN) {
+                QB_LAUNCH_LIK(QB_MODEL_COIN)
             } else {
                 QB_LAUNCH_LIK(QB_MODEL_TOMOGRAPHY)
             }
@@ -354,6 +356,8 @@ extern "C" int qb_hypothetical_update(const qb_model* model, const qb_expparams*
                 QB_LAUNCH_HYP(QB_MODEL_PRECESSION)
             } else if (model->kind == QB_MODEL_RB) {
                 QB_LAUNCH_HYP(QB_MODEL_RB)
+            } else if (model->kind == QB_MODEL_COIN) {
+                QB_LAUNCH_HYP(QB_MODEL_COIN)
             } else {
                 QB_LAUNCH_HYP(QB_MODEL_TOMOGRAPHY)
             }

@@ -84,6 +84,8 @@ __device__ __forceinline__ double model_pr0(const ModelView& mv, const ExpView& 
         }
         double pm = pow(p, ev.m);
         return 1.0 - (A * pm + B);
+    } else if (KIND == QB_MODEL_COIN) {
+        return row(0);  // test_models.py:323: pr0 is the coin's bias itself
     } else {
         // tomography/models.py:214-226: pr1 = clip(<meas, x>, 0, 1); pr0 = 1 - pr1
         const int d = mv.d;
@@ -168,6 +170,7 @@ __device__ __forceinline__ bool model_valid(const ModelView& mv, Row row) {
         return (0.0 <= p) && (p <= 1.0) && (0.0 <= A) && (A <= 1.0) && (0.0 <= B) && (B <= 1.0) &&
                (A + B <= 1.0) && (A * p + B <= 1.0);
     }
+    if (mv.kind == QB_MODEL_COIN) return (row(0) >= 0.0) && (row(0) <= 1.0);  // test_models.py:303-304
     return true;  // tomography/models.py:143-147
 }
 

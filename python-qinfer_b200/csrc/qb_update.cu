@@ -464,6 +464,9 @@ static update_kernel_t pick_update_kernel_k(const qb_model& m) {
                                   : fused_update_kernel<QB_MODEL_RB, false, 4, KF>;
             return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 3, KF>
                               : fused_update_kernel<QB_MODEL_RB, false, 3, KF>;
+        case QB_MODEL_COIN:
+            return m.binomial ? fused_update_kernel<QB_MODEL_COIN, true, 1, KF>
+                              : fused_update_kernel<QB_MODEL_COIN, false, 1, KF>;
     }
     return nullptr;
 }
@@ -488,6 +491,9 @@ int validate_model(const qb_model* m) {
                        "RB model needs %d model parameters, got %d", m->interleaved ? 4 : 3, m->d);
             break;
         case QB_MODEL_TOMOGRAPHY:
+            break;
+        case QB_MODEL_COIN:
+            QB_REQUIRE(m->d == 1, QB_ERR_UNSUPPORTED_MODEL, "coin model has 1 model parameter, got %d", m->d);
             break;
         default:
             set_error("unknown model kind %d (no CPU fallback exists)", m->kind);

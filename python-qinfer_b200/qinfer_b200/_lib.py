@@ -13,7 +13,7 @@ QB_IPC_HANDLE_BYTES = 64
  QB_STAT_SKIPPED, QB_STAT_ATTN) = range(9)
 QB_MAX_FUSE = 8
 QB_STAT_COUNT = 16
-QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY = 1, 2, 3
+QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY, QB_MODEL_COIN = 1, 2, 3, 4
 QB_SCAN_FAST, QB_SCAN_EXACT, QB_SCAN_FAST_GUIDE, QB_SCAN_FAST_GUIDE_SCALED = 0, 1, 2, 3
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqinfer_b200.so")
@@ -70,6 +70,9 @@ SIGNATURES = {
                                      ctypes.POINTER(_I64), _I32, _P, _I64, _P, _P]),
     "qb_hypothetical_update": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), _I32,
                                               ctypes.POINTER(_I64), _I32, _P, _P, _P, _I64, _P, _P, _P, _P, _SZ, _P]),
+    "qb_design_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "qb_design_sums": (ctypes.c_int, [ctypes.POINTER(QbModel), ctypes.POINTER(QbExpparams), ctypes.POINTER(_I64), _I32,
+                                      _P, _P, _P, _I64, ctypes.POINTER(_F64), _P, _P, _P, _SZ, _P]),
     "qb_are_models_valid": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _P, _P]),
     "qb_moments_workspace_bytes": (_SZ, [_I64, _I32]),
     "qb_moments": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _SZ, _P]),

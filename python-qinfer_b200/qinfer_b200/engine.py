@@ -79,6 +79,7 @@ class DeviceCloud(object):
             self.lib_model = ctypes.pointer(desc.c_model)
         # resample scratch, allocated lazily
         self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = None
+        self._moments_event = None
         self.launches = 0
         self.resample_events = None        # bench: set to [] to collect a CUDA-event pair around every resample
         self.update_launches = 0
@@ -231,17 +232,48 @@ class DeviceCloud(object):
         return (wts.cpu().numpy(), L.cpu().numpy() if want_likelihood else None,
                 norms.cpu().numpy()[..., np.newaxis])
 
+    def design_sums(self, expparams, idx, outcomes, centre, want_kld):
+        """qb_design_sums for experiment ``expparams[idx]``: (sums (n_o, 1 + 2d), kld (n_o,) or None) on the host."""
+        outcomes = np.atleast_1d(np.asarray(outcomes)).astype(np.int64)
+        n_o = outcomes.shape[0]
+        ep = self.desc.expparams_record(expparams, idx)
+        outs = (ctypes.c_int64 * n_o)(*[int(o) for o in outcomes])
+        need = self.lib.qb_design_workspace_bytes(self.n, self.d, n_o)
+        ws = getattr(self, '_design_ws', None)
+        if ws is None or ws.numel() * 8 < need:
+            self._design_ws = ws = torch.zeros(((need + 7) // 8,), dtype=torch.float64, device=self.device)
+        out = torch.empty((n_o * (2 + 2 * self.d),), dtype=torch.float64, device=self.device)
+        sums, kld = out[:n_o * (1 + 2 * self.d)], out[n_o * (1 + 2 * self.d):]
+        check(self.lib.qb_design_sums(self.lib_model, ctypes.byref(ep), outs, n_o, _ptr(self.x), _ptr(self.w),
+                                      _ptr(self.stats), self.n, _lib.f64_array(centre), _ptr(sums),
+                                      _ptr(kld) if want_kld else None, _ptr(ws), ws.numel() * 8, _stream()))
+        self.launches += 4 if want_kld else 2
+        host = out.cpu().numpy()
+        return (host[:n_o * (1 + 2 * self.d)].reshape(n_o, 1 + 2 * self.d).copy(),
+                host[n_o * (1 + 2 * self.d):].copy() if want_kld else None)
+
     # ---- moments ------------------------------------------------------------------
-    def moments(self):
-        """(sum w, mean (d,), second moment (d, d)) of the normalised cloud."""
+    def moments_begin(self):
+        """Launch the moment reduction and its read-back; returns at once.  Work queued after this call (e.g. the CDF
+        pass of a resample, which does not need the moments) runs while the host waits in ``moments_end``."""
         check(self.lib.qb_moments(_ptr(self.x), _ptr(self.w), _ptr(self.stats), self.n, self.d,
                                   _ptr(self.moments_out), _ptr(self.ws), self.ws_bytes, _stream()))
         self.launches += 2
         self.moments_host.copy_(self.moments_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if self._moments_event is None:
+            self._moments_event = torch.cuda.Event()
+        self._moments_event.record()
+
+    def moments_end(self):
+        self._moments_event.synchronize()
         out = self.moments_host.numpy()
         d = self.d
         return out[0], out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
+
+    def moments(self):
+        """(sum w, mean (d,), second moment (d, d)) of the normalised cloud."""
+        self.moments_begin()
+        return self.moments_end()
 
     # ---- resampling -----------------------------------------------------------------
     def _resample_scratch(self, n_new):

@@ -54,6 +54,8 @@ class ModelDescriptor(object):
             ep.t = float(expparams.flat[idx])                 # SimplePrecessionModel: bare float array
             ep.w_ = 0.0
             return ep
+        if self.kind == _lib.QB_MODEL_COIN and not self.binomial:
+            return ep                                         # CoinModel: expparams_dtype is empty
         arr = np.asarray(expparams)
         names = arr.dtype.names
         rec = arr.reshape(-1)[idx] if arr.ndim else arr[()]
@@ -79,6 +81,8 @@ class ModelDescriptor(object):
         elif self.kind == _lib.QB_MODEL_RB:
             ep.m = int(inner['m'])
             ep.reference = int(bool(inner['reference'])) if self.interleaved else 0
+        elif self.kind == _lib.QB_MODEL_COIN:
+            pass
         else:
             meas = np.asarray(inner['meas'], dtype=float).reshape(-1)
             if meas.shape[0] != self.d:
@@ -112,6 +116,8 @@ def describe_model(model):
         il = bool(getattr(inner, '_il', False))
         return ModelDescriptor(_lib.QB_MODEL_RB, 4 if il else 3, binomial=binomial, interleaved=il,
                                binomial_scalar=binomial_scalar)
+    if name == 'CoinModel':
+        return ModelDescriptor(_lib.QB_MODEL_COIN, 1, binomial=binomial, binomial_scalar=binomial_scalar)
     if name == 'TomographyModel':
         dim = int(getattr(inner, '_dim'))
         basis = np.ascontiguousarray(np.asarray(inner._basis.data, dtype=complex))
@@ -122,7 +128,7 @@ def describe_model(model):
                                binomial_scalar=binomial_scalar)
     raise UnsupportedModelError(
         "%s is not one of the model families the B200 kernels implement (SimplePrecessionModel, "
-        "SimpleInversionModel, RandomizedBenchmarkingModel, tomography.TomographyModel, optionally wrapped in "
+        "SimpleInversionModel, RandomizedBenchmarkingModel, CoinModel, tomography.TomographyModel, optionally wrapped in "
         "BinomialModel). There is no CPU fallback." % name)
 
 
@@ -152,6 +158,18 @@ class Model(object):
 
     def n_outcomes(self, expparams):
         return 2
+
+    @property
+    def Q(self):
+        """Diagonal of the quadratic-loss scale matrix (abstract_model.py:170-186): the identity by default."""
+        return np.ones((self.n_modelparams,))
+
+    def domain(self, expparams):
+        """abstract_model.py:287-298: one ``IntegerDomain(0, n_outcomes - 1)`` per experiment."""
+        if expparams is None:
+            return IntegerDomain(min=0, max=1)
+        n_o = np.broadcast_to(np.asarray(self.n_outcomes(expparams)), (_safe_shape(expparams),))
+        return [IntegerDomain(min=0, max=int(k) - 1) for k in n_o]
 
     def clear_cache(self):
         pass
@@ -184,6 +202,30 @@ class Model(object):
         if repeat == 1 and expparams.shape[0] == 1 and modelparams.shape[0] == 1:
             return outcomes[0, 0, 0]
         return outcomes
+
+
+class IntegerDomain(object):
+    """domains.py:427-560, the members the updater reads: ``values``, ``n_members``, ``min``, ``max``."""
+
+    def __init__(self, min=0, max=1):
+        self._min, self._max = int(min), int(max)
+
+    min = property(lambda self: self._min)
+    max = property(lambda self: self._max)
+    n_members = property(lambda self: self._max - self._min + 1)
+    is_finite = True
+    dtype = int
+
+    @property
+    def values(self):
+        return np.arange(self._min, self._max + 1, dtype=int)
+
+
+class CoinModel(Model):
+    """test_models.py:262-326: the model parameter is the probability of outcome 0; no experiment parameters."""
+    n_modelparams = 1
+    modelparam_names = [r'p']
+    expparams_dtype = []
 
 
 class SimpleInversionModel(Model):

@@ -217,16 +217,25 @@ class LiuWestResampler(Resampler):
             cloud.upload_locations(particle_dist.particle_locations)
             cloud.upload_weights(particle_dist.particle_weights)
 
-        if on_device and precomputed_mean is None and precomputed_cov is None:
-            _, mean, m2 = cloud.moments()                    # one pass gives both (resamplers.py:266-273)
-            cov = covariance_from_moments(mean, m2)
-        else:
-            mean = particle_dist.est_mean() if precomputed_mean is None else precomputed_mean
-            cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
         if n_particles is None:
             n_particles = (particle_dist.n_particles if self._default_n_particles is None
                            else self._default_n_particles)
         n_particles = int(n_particles)
+        fused = (self._rng == 'philox' and self._scan == 'fast' and cloud.d <= 4 and n_particles <= cloud.n
+                 and self._fused)
+        cdf_done = False
+        if on_device and precomputed_mean is None and precomputed_cov is None:
+            cloud.moments_begin()                            # one pass gives both (resamplers.py:266-273)
+            if fused:
+                # the CDF (+ guide) pass does not need the moments: queue it now, so that the device is busy while
+                # the host waits for the moments and takes the d x d matrix square root
+                cloud.cdf(_lib.QB_SCAN_FAST_GUIDE)
+                cdf_done = True
+            _, mean, m2 = cloud.moments_end()
+            cov = covariance_from_moments(mean, m2)
+        else:
+            mean = particle_dist.est_mean() if precomputed_mean is None else precomputed_mean
+            cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
 
         a, h = self._a, self._h
         if scipy.linalg.norm(cov, 'fro') == 0:
@@ -239,9 +248,8 @@ class LiuWestResampler(Resampler):
                                  "Check that n_ess is not too small.")
         S = np.real(h * S)
 
-        d = cloud.d
-        if self._rng == 'philox' and self._scan == 'fast' and d <= 4 and n_particles <= cloud.n and self._fused:
-            n_iters, n_invalid = self._fused_pass(cloud, mean, S, a, n_particles)
+        if fused:
+            n_iters, n_invalid = self._fused_pass(cloud, mean, S, a, n_particles, build_cdf=not cdf_done)
         else:
             n_iters, n_invalid = self._staged_pass(cloud, mean, S, a, n_particles)
         if n_invalid:

@@ -108,11 +108,28 @@ class ShardComm(object):
                                     input_split_sizes=[int(c) * width for c in send_counts], group=self.group)
         return recv
 
-    def all_gather_rows(self, row):
-        """(world, len(row)) host array of every rank's ``row`` (one collective, one host read)."""
+    def all_gather_rows_begin(self, row):
+        """Queue the all-gather of every rank's ``row`` and its read-back; ``all_gather_rows_end`` waits for exactly
+        that (an event), so kernels queued in between keep the device busy meanwhile."""
         out = torch.empty((self.world * row.numel(),), dtype=row.dtype, device=row.device)
         self.dist.all_gather_into_tensor(out, row.contiguous(), group=self.group)
-        return out.cpu().numpy().reshape(self.world, row.numel())
+        if out.is_cuda:
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return host, ev, row.numel(), out
+        return out, None, row.numel(), out
+
+    def all_gather_rows_end(self, handle):
+        host, ev, width, _keep = handle
+        if ev is not None:
+            ev.synchronize()
+        return host.numpy().reshape(self.world, width).copy()
+
+    def all_gather_rows(self, row):
+        """(world, len(row)) host array of every rank's ``row`` (one collective, one host read)."""
+        return self.all_gather_rows_end(self.all_gather_rows_begin(row))
 
     def all_to_all_into(self, recv, send, send_counts, recv_counts, width=1):
         """Variable all-to-all of rows of ``width`` elements straight into ``recv`` (a flat, contiguous view)."""
@@ -429,7 +446,10 @@ def _make_sharded_updater_class():
             self._restat_global()
 
         # -- global reductions ---------------------------------------------------------------
-        def _global_moments(self):
+        def _global_moments(self, overlap=None):
+            """Global (sum w, mean, second moment): local reduction, ONE all-gather, rows summed in rank order (so
+            every rank holds identical numbers).  ``overlap``: a callable that queues device work which does not
+            need the moments (the CDF pass of a resample); it runs while the collective and the host read complete."""
             cloud = self._cloud
             _lib.check(cloud.lib.qb_moments(ctypes.c_void_p(cloud.x.data_ptr()), ctypes.c_void_p(cloud.w.data_ptr()),
                                             ctypes.c_void_p(cloud.stats.data_ptr()), cloud.n, cloud.d,
@@ -437,7 +457,10 @@ def _make_sharded_updater_class():
                                             ctypes.c_void_p(cloud.ws.data_ptr()), cloud.ws_bytes,
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
             cloud.launches += 2
-            rows = self._comm.all_gather_rows(cloud.moments_out)      # one collective, one host read
+            handle = self._comm.all_gather_rows_begin(cloud.moments_out)   # one collective, one host read
+            if overlap is not None:
+                overlap()
+            rows = self._comm.all_gather_rows_end(handle)
             out = rows[0].copy()
             for r in range(1, rows.shape[0]):                         # fixed rank order: identical on every rank
                 out += rows[r]
@@ -481,7 +504,9 @@ def _make_sharded_updater_class():
             comm = self._comm
             n_local, d = cloud.n, cloud.d
 
-            _, mean, m2 = self._global_moments()
+            split = d <= 4 and getattr(res, '_fused', False) and self._exchange == 'split'
+            _, mean, m2 = self._global_moments(
+                overlap=(lambda: cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED)) if split else None)
             cov = covariance_from_moments(mean, m2)
             a, h = res._a, res._h
             if scipy.linalg.norm(cov, 'fro') == 0:
@@ -494,7 +519,7 @@ def _make_sharded_updater_class():
                                      "Check that n_ess is not too small.")
             S = np.real(h * S)
 
-            if d <= 4 and getattr(res, '_fused', False) and self._exchange == 'split':
+            if split:
                 self._split_pass(mean, S, a)
                 self._finish_resample(ev)
                 return
@@ -550,7 +575,7 @@ def _make_sharded_updater_class():
             res, cloud, comm = self.resampler, self._cloud, self._comm
             m = split_counts(self._split_rng, self._n_global, self._shard_masses)
             cloud.preallocate_resample_slab()
-            state = {'cdf': True, 'iters': 0}
+            state = {'cdf': False, 'iters': 0}            # the CDF (+ guide) was queued behind the moments
             updater = self
 
             class Ops(object):

@@ -22,7 +22,7 @@ def oracle_namespace():
         ParticleDistribution=o.ParticleDistribution,
         SimplePrecessionModel=o.SimplePrecessionModel, SimpleInversionModel=o.SimpleInversionModel,
         RandomizedBenchmarkingModel=o.RandomizedBenchmarkingModel, BinomialModel=o.BinomialModel,
-        TomographyModel=o.TomographyModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
+        CoinModel=o.CoinModel, TomographyModel=o.TomographyModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
         UniformDistribution=o.UniformDistribution, PostselectedDistribution=o.PostselectedDistribution,
         sqrtm_psd=o.sqrtm_psd)
 
@@ -38,7 +38,7 @@ def reference_namespace():
         ParticleDistribution=q.ParticleDistribution,
         SimplePrecessionModel=q.SimplePrecessionModel, SimpleInversionModel=q.SimpleInversionModel,
         RandomizedBenchmarkingModel=q.RandomizedBenchmarkingModel, BinomialModel=q.BinomialModel,
-        TomographyModel=qt.TomographyModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
+        CoinModel=q.CoinModel, TomographyModel=qt.TomographyModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
         UniformDistribution=q.UniformDistribution, PostselectedDistribution=q.PostselectedDistribution,
         sqrtm_psd=qu.sqrtm_psd)
 
@@ -319,4 +319,82 @@ def moment_vectors(ns, seed=5):
         S, err = ns.sqrtm_psd(out['mom%d_cov' % d])
         out['mom%d_S' % d] = S
         out['mom%d_Serr' % d] = np.float64(err)
+    return out
+
+
+def design_vectors(ns, seed=21):
+    """f2 vectors: SMCUpdater.bayes_risk / expected_information_gain (smc.py:553-657) on clouds with non-uniform
+    weights.  The first case is the setting of the reference's known-answer tests (tests/test_metrics.py:40-120):
+    BinomialModel(CoinModel()) with Beta(1, 3) particles and n_meas = 1..10."""
+    import warnings
+    rs = np.random.RandomState(seed)
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # (1) coin under BinomialModel, uniform weights, then the same after two data
+        n = 3000
+        x = rs.beta(1.0, 3.0, size=(n, 1))
+        model = ns.BinomialModel(ns.CoinModel())
+        up = ns.SMCUpdater(model, n, FixedPrior(x), resample_thresh=0.0)
+        ep = np.arange(1, 11, dtype=int).astype(model.expparams_dtype)
+        out['coin_x'] = x
+        out['coin_nmeas'] = np.arange(1, 11, dtype=np.int64)
+        out['coin_risk'] = np.asarray(up.bayes_risk(ep), dtype=float)
+        out['coin_ig'] = np.asarray(up.expected_information_gain(ep), dtype=float)
+        up.update(2, ep[4:5])
+        up.update(1, ep[2:3])
+        out['coin_risk_post'] = np.asarray(up.bayes_risk(ep), dtype=float)
+        out['coin_ig_post'] = np.asarray(up.expected_information_gain(ep), dtype=float)
+        # (2) precession after five updates: several evolution times in one call (n_outcomes constant)
+        n = 2500
+        x = rs.random_sample((n, 1))
+        up = ns.SMCUpdater(ns.SimplePrecessionModel(), n, FixedPrior(x), resample_thresh=0.0)
+        for k, (t, o) in enumerate(zip([1.0, 2.3, 4.1, 7.7, 12.9], [0, 1, 0, 0, 1])):
+            up.update(o, np.array([t]))
+        ts = np.array([0.5, 3.0, 11.0, 40.0, 170.0])
+        out['prec_x'] = x
+        out['prec_ts'] = ts
+        out['prec_risk'] = np.asarray(up.bayes_risk(ts), dtype=float)
+        out['prec_ig'] = np.asarray(up.expected_information_gain(ts), dtype=float)
+        # (3) randomized benchmarking, d = 3
+        n = 2000
+        x = np.column_stack([0.9 + 0.1 * rs.random_sample(n), 0.3 + 0.3 * rs.random_sample(n),
+                             0.2 + 0.2 * rs.random_sample(n)])
+        rbm = ns.RandomizedBenchmarkingModel()
+        up = ns.SMCUpdater(rbm, n, FixedPrior(x), resample_thresh=0.0)
+        ep = np.empty((3,), dtype=rbm.expparams_dtype)
+        ep['m'] = [1, 20, 150]
+        up.update(0, ep[1:2])
+        up.update(1, ep[2:3])
+        out['rb_x'] = x
+        out['rb_m'] = np.array([1, 20, 150], dtype=np.int64)
+        out['rb_risk'] = np.asarray(up.bayes_risk(ep), dtype=float)
+        out['rb_ig'] = np.asarray(up.expected_information_gain(ep), dtype=float)
+        # (4) Binomial(RB): every experiment has its own outcome count
+        bm = ns.BinomialModel(ns.RandomizedBenchmarkingModel())
+        up = ns.SMCUpdater(bm, n, FixedPrior(x), resample_thresh=0.0)
+        epb = np.empty((3,), dtype=bm.expparams_dtype)
+        epb['m'] = [5, 60, 300]
+        epb['n_meas'] = [4, 12, 25]
+        up.update(3, epb[0:1])
+        out['binrb_m'] = np.array([5, 60, 300], dtype=np.int64)
+        out['binrb_n'] = np.array([4, 12, 25], dtype=np.int64)
+        out['binrb_risk'] = np.asarray(up.bayes_risk(epb), dtype=float)
+        out['binrb_ig'] = np.asarray(up.expected_information_gain(epb), dtype=float)
+        # (5) one-qubit tomography, d = 4 (physical states: no clipping, so the likelihoods are strictly inside (0, 1))
+        basis = ns.pauli_basis(1)
+        tm = ns.TomographyModel(basis)
+        xt = ginibre_coords(rs, 1500, np.asarray(basis.data))
+        up = ns.SMCUpdater(tm, 1500, FixedPrior(xt), resample_thresh=0.0)
+        ept = np.empty((3,), dtype=tm.expparams_dtype)
+        meas = np.zeros((3, 4))
+        meas[:, 0] = np.sqrt(2) / 2
+        meas[0, 1] = meas[1, 2] = meas[2, 3] = 0.9 * np.sqrt(2) / 2
+        ept['meas'] = meas
+        up.update(0, ept[0:1])
+        up.update(1, ept[2:3])
+        out['tomo_x'] = xt
+        out['tomo_meas'] = meas
+        out['tomo_risk'] = np.asarray(up.bayes_risk(ept), dtype=float)
+        out['tomo_ig'] = np.asarray(up.expected_information_gain(ept), dtype=float)
     return out

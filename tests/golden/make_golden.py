@@ -54,6 +54,7 @@ def build(ns):
         files['likelihood_vectors'] = cases.likelihood_vectors(ns)
         files['canonicalize_vectors'] = cases.canonicalize_vectors(ns)
         files['moment_vectors'] = cases.moment_vectors(ns)
+        files['design_vectors'] = cases.design_vectors(ns)
     return files
 
 

@@ -48,7 +48,8 @@ def gpu_namespace(qb, **lw_kwargs):
         name="b200", SMCUpdater=qb.SMCUpdater, LiuWestResampler=qb.LiuWestResampler,
         ParticleDistribution=qb.ParticleDistribution, SimplePrecessionModel=qb.SimplePrecessionModel,
         SimpleInversionModel=qb.SimpleInversionModel, RandomizedBenchmarkingModel=qb.RandomizedBenchmarkingModel,
-        BinomialModel=qb.BinomialModel, TomographyModel=qb.TomographyModel, pauli_basis=qb.pauli_basis,
+        BinomialModel=qb.BinomialModel, CoinModel=qb.CoinModel, TomographyModel=qb.TomographyModel,
+        pauli_basis=qb.pauli_basis,
         gell_mann_basis=qb.gell_mann_basis, UniformDistribution=qb.UniformDistribution,
         PostselectedDistribution=qb.PostselectedDistribution, sqrtm_psd=qb.sqrtm_psd)
 
@@ -743,3 +744,65 @@ def test_fused_resample_against_oracle_given_the_same_variates(qb, oracle, n):
     # the re-associated scan ends at ~1 and is non-decreasing up to the rounding of a partial-sum boundary
     # (a zero weight next to a thread boundary may step back by an ulp; the guide scatter tolerates that)
     assert np.all(np.diff(cdf) >= -4.5e-16) and abs(cdf[-1] - 1) < 1e-12
+
+
+
+# ---------------------------------------------------------------------------
+# f2 — bayes_risk / expected_information_gain (smc.py:553-657) reduced on the device
+# ---------------------------------------------------------------------------
+def test_design_vectors_against_the_reference(qb, golden):
+    """Golden vectors of the UNMODIFIED reference (coin/binomial, precession, RB, binomial RB, tomography).  The
+    device reduces each hypothetical posterior to (N, first and second moment about the mean); tolerance 1e-10
+    relative: summation order and the shifted-moment formula differ from the reference's two-pass einsum."""
+    g = golden("design_vectors")
+    got = cases.design_vectors(gpu_namespace(qb))
+    for key in sorted(g):
+        if key.endswith(("risk", "ig", "risk_post", "ig_post")):
+            assert got[key].shape == g[key].shape, key
+            assert np.array_equal(np.isnan(got[key]), np.isnan(g[key])), key      # 0 * log 0 = NaN, as in the reference
+            ok = ~np.isnan(g[key])
+            np.testing.assert_allclose(got[key][ok], g[key][ok], rtol=1e-10, atol=0, err_msg=key)
+            report("f2_" + key + "_rel", relerr(got[key][ok], g[key][ok]))
+
+
+def test_design_known_answers_of_the_reference_tests(qb):
+    """tests/test_metrics.py:65-79 (risk, 3 decimals against the closed form) and :110-120 (BINOM_IG, 2 decimals),
+    restated with the reference's sizes: 10 000 Beta(1, 3) particles, BinomialModel(CoinModel()), n_meas = 1..10."""
+    np.random.seed(0)
+    x = np.random.beta(1.0, 3.0, size=(10000, 1))
+    model = qb.BinomialModel(qb.CoinModel())
+    up = qb.SMCUpdater(model, 10000, cases.FixedPrior(x))
+    ep = np.arange(1, 11, dtype=int).astype(model.expparams_dtype)
+    a, b = 1.0, 3.0
+    exact_risk = a * b / ((a + b) * (a + b + 1) * (a + b + ep['n_meas']))
+    np.testing.assert_almost_equal(up.bayes_risk(ep), exact_risk, decimal=3)
+    binom_ig = np.array([0.104002, 0.189223, 0.261496, 0.324283, 0.379815, 0.429613, 0.474764, 0.516069, 0.554138,
+                         0.589446])
+    np.testing.assert_almost_equal(up.expected_information_gain(ep), binom_ig, decimal=2)
+
+
+def test_coin_model_updates_match_the_oracle(qb, oracle):
+    """CoinModel (pr0 = p) through the fused update kernel, alone and under BinomialModel, vs the NumPy oracle."""
+    rs = np.random.RandomState(3)
+    x = rs.beta(2.0, 2.0, size=(5000, 1))
+    for wrap in (False, True):
+        ups = []
+        for mod in (qb, oracle):
+            m = mod.BinomialModel(mod.CoinModel()) if wrap else mod.CoinModel()
+            np.random.seed(1)
+            up = mod.SMCUpdater(m, 5000, cases.FixedPrior(x), resample_thresh=0.0)
+            if wrap:
+                ep = np.array([(7,), (3,), (12,)], dtype=m.expparams_dtype)
+                for k, o in enumerate([2, 3, 5]):
+                    up.update(o, ep[k:k + 1])
+            else:
+                ep = np.empty((1,), dtype=m.expparams_dtype)
+                for o in [0, 1, 1, 0, 1]:
+                    up.update(o, ep)
+            ups.append(up)
+        g, o = ups
+        np.testing.assert_allclose(g.particle_weights, o.particle_weights, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(g.normalization_record, np.ravel(o.normalization_record), rtol=1e-12)
+        np.testing.assert_allclose(g.est_mean(), o.est_mean(), rtol=1e-12)
+        assert np.array_equal(qb.CoinModel().are_models_valid(np.array([[-0.1], [0.0], [0.5], [1.0], [1.1]])),
+                              np.array([False, True, True, True, False]))

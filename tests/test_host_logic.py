@@ -31,10 +31,12 @@ def test_recognition_works_on_foreign_objects_with_the_reference_layout():
 
 
 def test_unsupported_model_raises_no_cpu_fallback():
-    class CoinModel(object):
+    class PoissonModel(object):
         n_modelparams = 1
     with pytest.raises(qb.UnsupportedModelError, match="no CPU fallback"):
-        qb.describe_model(CoinModel())
+        qb.describe_model(PoissonModel())
+    assert qb.describe_model(qb.CoinModel()).kind == 4          # QB_MODEL_COIN: the reference tests' risk / gain model
+    assert qb.describe_model(qb.BinomialModel(qb.CoinModel())).binomial
 
     class MyPrecession(qb.SimplePrecessionModel):      # subclasses may override likelihood: not silently accepted
         pass

@@ -108,6 +108,28 @@ def test_minfreq_case_exercises_retry_loop(golden):
     assert hit > 0
 
 
+def test_design_vectors_bit_exact(ns, golden):
+    """bayes_risk / expected_information_gain (smc.py:553-657) restated in the oracle, incl. CoinModel."""
+    g = golden("design_vectors")
+    _assert_same(cases.design_vectors(ns), g)
+
+
+def test_design_known_answers_from_the_reference_tests():
+    """tests/test_metrics.py:65-79, 110-120 on the oracle: closed-form Beta-binomial risk (3 decimals) and the
+    Mathematica BINOM_IG vector (2 decimals)."""
+    import smc_oracle as o
+    np.random.seed(0)
+    x = np.random.beta(1.0, 3.0, size=(10000, 1))
+    model = o.BinomialModel(o.CoinModel())
+    up = o.SMCUpdater(model, 10000, cases.FixedPrior(x))
+    ep = np.arange(1, 11, dtype=int).astype(model.expparams_dtype)
+    exact_risk = 3.0 / (4.0 * 5.0 * (4.0 + ep['n_meas']))
+    np.testing.assert_almost_equal(up.bayes_risk(ep), exact_risk, decimal=3)
+    binom_ig = np.array([0.104002, 0.189223, 0.261496, 0.324283, 0.379815, 0.429613, 0.474764, 0.516069, 0.554138,
+                         0.589446])
+    np.testing.assert_almost_equal(up.expected_information_gain(ep), binom_ig, decimal=2)
+
+
 def test_binomial_pmf_restatement_matches_scipy():
     import smc_oracle as o
     rs = np.random.RandomState(3)
