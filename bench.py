@@ -270,6 +270,10 @@ def gpu_arm(args, rank, world, local_rank):
         small.est_mean()
         # ... and page-lock the host staging blocks the posterior read-back will recycle (torch's caching host
         # allocator keeps them), as a long-lived process would have done on its first read
+        # (the e2e pass reads its prior from page-locked host memory, as the base contract asks; allocated first so
+        # that it does not take one of the recycled staging blocks)
+        pinned_prior = torch.empty((n, 1), dtype=torch.float64, pin_memory=True)
+        pinned_prior.numpy()[:] = prior
         stage = [torch.empty((n, 1), dtype=torch.float64, pin_memory=True),
                  torch.empty((n,), dtype=torch.float64, pin_memory=True)]
         del stage
@@ -315,10 +319,7 @@ def gpu_arm(args, rank, world, local_rank):
         if world > 1:
             up.close()
         del up
-        # the user's host array, page-locked (the base contract times the H2D copy "from pinned host memory")
-        pinned_prior = torch.empty((n, 1), dtype=torch.float64, pin_memory=True)
-        pinned_prior.numpy()[:] = prior
-        prior = pinned_prior.numpy()
+        prior = pinned_prior.numpy()                     # the user's host array, page-locked (allocated above)
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -190,8 +190,10 @@ int qb_hypothetical_update(const qb_model* model, const qb_expparams* eps, int32
                            void* d_ws, size_t ws_bytes, void* stream);
 
 /* Experiment design (SMCUpdater.bayes_risk, smc.py:553-605; expected_information_gain, smc.py:607-657) for ONE
- * experiment `ep` with outcome list `outcomes` (HOST, n_o entries = model.domain(ep).values): the likelihood of
- * the LAST outcome is taken as 1 - sum of the others, as the reference does.  With h_oi = w_i L_oi:
+ * experiment `ep` with outcome list `outcomes` (HOST, n_o entries = model.domain(ep).values).  Every outcome's
+ * likelihood is evaluated (the reference takes the last one as 1 - sum of the others, smc.py:589, which cancels
+ * to +-1e-16 under BinomialModel and then yields NaN gains); a particle of zero likelihood contributes the limit
+ * 0 to d_kld instead of 0 * log 0 = NaN.  With h_oi = w_i L_oi:
  *   d_sums[o][0]       = N_o = sum_i h_oi
  *   d_sums[o][1+j]     = sum_i h_oi (x_ij - centre_j)          j < d
  *   d_sums[o][1+d+j]   = sum_i h_oi (x_ij - centre_j)^2
@@ -320,6 +322,14 @@ int qb_gather_rows(const double* d_x, int32_t d, const int64_t* d_js, int64_t n,
  * (dim^2, dim, dim) complex128 basis tensor (interleaved re/im), dim in {2,3,4}. */
 int qb_tomo_canonicalize(double* d_x, int64_t n, int32_t dim, const double* d_basis,
                          int32_t allow_subnormalized, void* stream);
+/* Same result, for large clouds: a screening pass certifies the comfortably positive-definite particles with an
+ * LDL^H factorisation (for them canonicalize is the identity + the renormalising division) and flags the rest;
+ * the flagged ones are compacted (qb_compact_invalid) and only they go through the eigendecomposition.
+ * Scratch: d_flags (n bytes), d_idxs (n int64), d_count (one int64, stays on the device) and a workspace of
+ * qb_compact_workspace_bytes(n). */
+int qb_tomo_canonicalize_screened(double* d_x, int64_t n, int32_t dim, const double* d_basis,
+                                  int32_t allow_subnormalized, uint8_t* d_flags, int64_t* d_idxs,
+                                  int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- device RNG (throughput mode; counter-based Philox4x32-10) ------------- */
 /* d_out[i] = uniform [0,1) with 53 random bits, element i of stream (seed, offset). */

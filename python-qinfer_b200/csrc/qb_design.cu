@@ -5,13 +5,15 @@
 //   L_o,i   = Model.likelihood(os[o], x_i)            for o < n_o - 1
 //   L_last,i = 1 - sum_{o < n_o - 1} L_o,i             (smc.py:589: "the likelihood over outcomes sums to 1")
 //   N_o     = sum_i w_i L_o,i ;  w_hyp_o,i = w_i L_o,i / N_o
+// Here the last outcome's likelihood is EVALUATED like the others: for the two-outcome models that is the same
+// complement (pr1 = 1 - pr0); for BinomialModel it replaces a difference that cancels to +-1e-16 (and then feeds
+// log() a zero or negative number: the reference returns NaN there) by the pmf itself.
 // and then either the posterior variance of every outcome (risk) or its KL divergence from the prior (gain).
 // The (n_o, n) tensors w_hyp and L never exist here: pass 1 reduces, per outcome,
 //   A = sum h,  B_j = sum h (x_j - c_j),  C_j = sum h (x_j - c_j)^2        with h = w_i L_o,i
 // around a centre c (the current posterior mean, so that var = C/A - (B/A)^2 does not cancel), and pass 2, given
 // N_o = A, reduces  K = sum w_hyp log(w_hyp / w)  elementwise exactly as smc.py:651 writes it.
-// grid.y = outcome: every block row streams the cloud once (the last row evaluates all n_o - 1 likelihoods
-// per particle to form the complement).  Compiled with --fmad=false like every model kernel.
+// grid.y = outcome: every block row streams the cloud once.  Compiled with --fmad=false like every model kernel.
 #include "qb_models.cuh"
 
 namespace qb {
@@ -36,10 +38,7 @@ template <int KIND, bool BINOM>
 __device__ __forceinline__ double outcome_likelihood(const DesignParams& p, const double* xr, int o) {
     auto row = [&](int c) { return xr[c]; };
     auto meas = [&](int c) { return p.meas[c]; };
-    if (o < p.n_o - 1 || p.n_o == 1) return model_likelihood<KIND, BINOM>(p.mv, p.evs[o], row, meas, 0);
-    double acc = 0.0;  // L.sum(axis=0): outcomes added in order
-    for (int q = 0; q < p.n_o - 1; ++q) acc += model_likelihood<KIND, BINOM>(p.mv, p.evs[q], row, meas, 0);
-    return 1.0 - acc;
+    return model_likelihood<KIND, BINOM>(p.mv, p.evs[o], row, meas, 0);
 }
 
 // DMAX: compile-time bound on d for the per-thread accumulators (1, 4, 16, 64).
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(DSN_THREADS) design_sums_kernel(const __grid_c
         const double* xr = p.x + i * d;
         const double wn = p.w[i] * inv;
         const double L = outcome_likelihood<KIND, BINOM>(p, xr, o);
-        const double h = (o < p.n_o - 1 || p.n_o == 1) ? wn * L : L * wn;  // smc.py:354 / smc.py:589 operand order
+        const double h = wn * L;  // smc.py:354
         if (p.pass == 1) {
             A += h;
 #pragma unroll
@@ -78,7 +77,7 @@ __global__ void __launch_bounds__(DSN_THREADS) design_sums_kernel(const __grid_c
             }
         } else {
             const double wh = h / div;
-            A += wh * log(wh / wn);  // smc.py:651, term by term (0 * log 0 = NaN there and here)
+            if (wh > 0.0) A += wh * log(wh / wn);  // smc.py:651 term by term; a zero-likelihood particle adds its limit 0
         }
     }
     const int nv = (p.pass == 1) ? 1 + 2 * d : 1;
@@ -92,8 +91,8 @@ __global__ void __launch_bounds__(DSN_THREADS) design_sums_kernel(const __grid_c
             t = 0.0;
 #pragma unroll
             for (int c = 0; c < DMAX; ++c) {
-                if (v == 1 + c) t = B[c];
-                if (v == 1 + d + c) t = C[c];
+                if (c < d && v == 1 + c) t = B[c];
+                if (c < d && v == 1 + d + c) t = C[c];
             }
         }
         t = warp_sum(t);

@@ -103,6 +103,7 @@ SIGNATURES = {
                                        _P]),
     "qb_gather_rows": (ctypes.c_int, [_P, _I32, _P, _I64, _P, _P]),
     "qb_tomo_canonicalize": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P]),
+    "qb_tomo_canonicalize_screened": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
     "qb_rng_uniform": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
     "qb_rng_normal": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
     "qb_mt19937_workspace_bytes": (_SZ, [_I64, _I64]),

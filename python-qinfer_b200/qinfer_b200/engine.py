@@ -404,6 +404,17 @@ class DeviceCloud(object):
     def canonicalize(self):
         if self.desc.kind != _lib.QB_MODEL_TOMOGRAPHY:
             return
+        if self.n >= 4096:
+            # large clouds: LDL^H screening pass, eigendecomposition only for the particles it cannot certify
+            self._fused_scratch(self.n)
+            if getattr(self, '_canon_count', None) is None:
+                self._canon_count = torch.zeros((1,), dtype=torch.int64, device=self.device)
+            check(self.lib.qb_tomo_canonicalize_screened(_ptr(self.x), self.n, self.desc.dim, _ptr(self.basis_dev),
+                                                         int(self.desc.allow_subnormalized), _ptr(self._invalid),
+                                                         _ptr(self._idxs), _ptr(self._canon_count), _ptr(self.ws),
+                                                         self.ws_bytes, _stream()))
+            self.launches += 5
+            return
         check(self.lib.qb_tomo_canonicalize(_ptr(self.x), self.n, self.desc.dim, _ptr(self.basis_dev),
                                             int(self.desc.allow_subnormalized), _stream()))
         self.launches += 1

@@ -40,6 +40,7 @@ def c1(ns, n, n_updates, lazy):
         for k in range(n_updates):
             up.update(int(inp['outcomes'][k]), np.array([inp['ts'][k]]))
         return up.est_mean(), up.resample_count
+    run.updater = up
     return run
 
 
@@ -56,6 +57,7 @@ def c3(ns, n, n_updates, lazy):
     def run():
         up.batch_update(inp['counts'], eps, resample_interval=1)
         return up.est_mean(), up.resample_count
+    run.updater = up
     return run
 
 
@@ -76,6 +78,7 @@ def c4(ns, n, n_updates, lazy):
         for k in range(n_updates):
             up.update(int(inp['outcomes'][k]), eps[k])
         return up.est_mean(), up.resample_count
+    run.updater = up
     return run
 
 
@@ -97,7 +100,10 @@ def main():
         for label, fn, n, k, n_cpu, k_cpu, lazy in plan:
             if quick:
                 n, k = min(n, 10 ** 5), min(k, 40)
-            fn(gpu_ns, min(n, 20000), 10, lazy)()                      # warm-up: load kernels
+            warm = fn(gpu_ns, min(n, 20000), 10, lazy)                 # warm-up: load every kernel of the path,
+            warm()                                                     # including the resample's
+            warm.updater.resample()
+            warm.updater.est_mean()
             t_gpu, (mean_g, rc_g) = timed_run(fn(gpu_ns, n, k, lazy))
             t_cpu, (mean_c, rc_c) = timed_run(fn(cpu_ns, n_cpu, k_cpu, False))
             r = dict(config=label, gpu_particles=n, gpu_updates=k, gpu_seconds=t_gpu, gpu_resamples=int(rc_g),
