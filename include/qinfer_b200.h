@@ -48,7 +48,7 @@ extern "C" {
 #define QB_MAX_D 64 /* max n_modelparams handled by the staged kernels (3-qubit tomography) */
 #define QB_MAX_RANKS 16 /* GPUs of one NVLink domain that may share a particle cloud */
 #define QB_MAX_FUSE 8   /* consecutive updates one launch can fuse (qb_fused_update_multi) */
-#define QB_MAILBOX_ROW 32 /* doubles per peer-mailbox row: 3 * QB_MAX_FUSE sums, padding, tag in the last slot */
+#define QB_MAILBOX_ROW 64 /* 8-byte slots per peer-mailbox row: 2 per sum (3 * QB_MAX_FUSE sums), each {32 data bits, 32-bit flag} */
 
 /* ---- model plugin descriptor ------------------------------------------- */
 /* Which built-in likelihood the kernels evaluate. */
@@ -140,6 +140,12 @@ typedef struct qb_update_ctl {
     double resample_below;     /* n_particles * resample_thresh (smc.py:275) */
     int32_t guard;             /* 1: cancel if stats_in says the predecessor needs the host */
     int32_t check_resample;    /* qb_fused_update only: this update is followed by an n_ess check */
+    /* Chained launch: if the call issued IMMEDIATELY before this one on the same stream and workspace was the
+     * qb_fused_update[_multi] with this tag, and this call's w_in / stats_in are that call's w_out / stats_out, pass
+     * the tag here (else 0).  The kernel then depends on its predecessor through two flags in device memory (weights
+     * complete; stats published) instead of waiting for it to drain, so the predecessor's final reduction — and,
+     * for a sharded cloud, its all-reduce over NVLink — overlaps with this launch's pipeline fill. */
+    double chain_prev_tag;
     /* Sharded cloud: with n_ranks > 1 the kernel all-reduces (sum w', sum w'^2, #bad) of every
      * fused step over the peers' mailboxes (qb_mailbox_create / qb_ipc_*) before publishing, so stats_out
      * holds the GLOBAL normalisation and n_ess on every rank, bit-identical, with no NCCL call and no extra

@@ -33,7 +33,7 @@ class QbExpparams(ctypes.Structure):
 class QbUpdateCtl(ctypes.Structure):
     _fields_ = [("h_mirror", ctypes.c_void_p), ("tag", ctypes.c_double), ("zero_weight_thresh", ctypes.c_double),
                 ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("check_resample", ctypes.c_int32),
-                ("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("chain_prev_tag", ctypes.c_double), ("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32),
                 ("d_peer_mailbox", ctypes.c_void_p * QB_MAX_RANKS), ("d_error_flag", ctypes.c_void_p)]
 
 

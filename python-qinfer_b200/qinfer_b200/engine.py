@@ -80,9 +80,22 @@ class DeviceCloud(object):
         # resample scratch, allocated lazily
         self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = None
         self._moments_event = None
-        self.launches = 0
+        self._chain_tag = 0                # tag of the fused update that was the LAST thing queued for this cloud
+        self._chain_dst = -1               # ... and the weights/stats buffer it wrote
+        self._launches = 0
         self.resample_events = None        # bench: set to [] to collect a CUDA-event pair around every resample
         self.update_launches = 0
+
+    # Every entry point other than the fused update bumps ``launches`` after queueing its kernels; that also breaks
+    # the update chain (a chained update depends on its predecessor through flags, not on whatever ran in between).
+    @property
+    def launches(self):
+        return self._launches
+
+    @launches.setter
+    def launches(self, value):
+        self._launches = value
+        self._chain_tag = 0
 
     # committed / pending views of the ping-pong buffers
     w = property(lambda self: self._w[self.cur])
@@ -96,6 +109,7 @@ class DeviceCloud(object):
         if locs.shape != (self.n, self.d):
             raise ValueError("particle_locations must have shape (%d, %d), got %s" % (self.n, self.d, locs.shape))
         self.x.copy_(torch.from_numpy(locs))
+        self._chain_tag = 0
 
     def _to_host(self, t):
         """Device -> host through a pinned staging tensor.  torch's caching host allocator recycles pinned blocks, so
@@ -152,6 +166,8 @@ class DeviceCloud(object):
         ctl.zero_weight_thresh = zero_weight_thresh
         ctl.resample_below = resample_below
         ctl.guard = 1 if guard else 0
+        # chained launch: the previous thing queued for this cloud is the update whose output this one reads
+        ctl.chain_prev_tag = float(self._chain_tag) if (self._chain_tag and self._chain_dst == src) else 0.0
         mask = 0
         if k == 1:
             ep, outcome, chk = steps[0]
@@ -174,6 +190,7 @@ class DeviceCloud(object):
                                                  self.ws_bytes, _stream()))
         self.launches += 1
         self.update_launches += 1
+        self._chain_tag, self._chain_dst = self._tag, dst
         return self._tag
 
     def wait_stats(self, slot, tag, nsteps=1, timeout_s=120.0):

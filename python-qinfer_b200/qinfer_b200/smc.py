@@ -339,8 +339,10 @@ class SMCUpdater(object):
             if plain:
                 self._queue = self._queue[len(steps):]
                 self._pending = (tag, steps)
-            # else: the speculative launch cancelled itself; its steps are still queued, behind whatever steps of
-            # `prev` _finalize put back
+            else:
+                cloud._chain_tag = 0                # never chain behind a launch that cancelled itself
+            # (the speculative launch cancelled itself; its steps are still queued, behind whatever steps of
+            # `prev` _finalize put back)
 
     def _flush(self):
         """Launch and settle everything that is buffered or pending."""

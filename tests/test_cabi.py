@@ -47,7 +47,7 @@ def test_struct_layouts_match_the_header():
     _lib.load().qb_struct_sizes(sizes)                       # what the C compiler actually laid out
     assert list(sizes) == [ctypes.sizeof(_lib.QbModel), ctypes.sizeof(_lib.QbExpparams),
                            ctypes.sizeof(_lib.QbUpdateCtl)]
-    assert ctypes.sizeof(_lib.QbUpdateCtl) == 48 + 8 * _lib.QB_MAX_RANKS + 8
+    assert ctypes.sizeof(_lib.QbUpdateCtl) == 56 + 8 * _lib.QB_MAX_RANKS + 8
 
 
 def test_argument_validation_without_a_gpu():
