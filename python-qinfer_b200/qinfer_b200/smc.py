@@ -189,6 +189,31 @@ class SMCUpdater(object):
     def est_meanfn(self, fn):
         return np.einsum('i...,i...', self.particle_weights, fn(self.particle_locations))
 
+    # ---- read-side estimators (distributions.py:457-465, 557-626): host arithmetic, exactly the
+    # reference's expressions, on the read-back of the device cloud (the cloud is downloaded once and cached)
+    def est_entropy(self):
+        nz_weights = self.particle_weights[self.particle_weights > 0]
+        return -np.sum(np.log(nz_weights) * nz_weights)
+
+    def est_credible_region(self, level=0.95, return_outside=False, modelparam_slice=None):
+        s_ = np.s_[modelparam_slice] if modelparam_slice is not None else np.s_[:]
+        mps = self.particle_locations[:, s_]
+        id_sort = np.argsort(self.particle_weights)[::-1]
+        cumsum_weights = np.cumsum(self.particle_weights[id_sort])
+        id_cred = cumsum_weights <= level
+        id_cred[np.sum(id_cred)] = True
+        if return_outside:
+            return mps[id_sort][id_cred], mps[id_sort][np.logical_not(id_cred)]
+        return mps[id_sort][id_cred]
+
+    def region_est_hull(self, level=0.95, modelparam_slice=None):
+        from scipy.spatial import ConvexHull
+        points = self.est_credible_region(level=level, modelparam_slice=modelparam_slice)
+        hull = ConvexHull(points)
+        verts = hull.vertices.flatten()
+        _, first = np.unique(verts, return_index=True)          # utils.uniquify: order-preserving de-duplication
+        return points[hull.simplices], points[verts[np.sort(first)]]
+
     def est_covariance_mtx(self, corr=False):
         self._flush()
         _, mean, m2 = self._cloud.moments()

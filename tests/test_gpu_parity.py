@@ -688,7 +688,7 @@ def _fused_case(qb, kind, n, seed):
 @pytest.mark.parametrize("kind,n,n_new", [("prec", 1000, None), ("prec", 4096, None), ("prec", 100003, None),
                                           ("prec_minfreq", 50001, None), ("rb", 65537, None), ("rb", 30000, 29999),
                                           ("rb_il", 20001, None), ("prec", 3000001, None), ("prec", 9, None),
-                                          ("rb", 2 ** 20, None)])
+                                          ("rb", 2 ** 20, None), ("prec", 10 ** 7, None)])
 def test_fused_draw_move_bit_identical_to_staged(qb, kind, n, n_new):
     """qb_cdf(FAST_GUIDE) + qb_lw_draw_move / qb_lw_draw_retry against qb_cdf(FAST) + qb_rng_uniform + qb_draw +
     qb_rng_normal + qb_lw_move / qb_compact_invalid / qb_lw_retry on the same cloud and Philox streams: identical

@@ -17,6 +17,12 @@ def qb():
     return qinfer_b200
 
 
+@pytest.fixture(scope="module")
+def oracle():
+    import smc_oracle
+    return smc_oracle
+
+
 def _decimation_setup(qb, n, fraction_zero):
     """The reference drives ESS with a DecimationModel (tests/test_smc.py:55-80) that zeroes the likelihood
     of a chosen fraction of particles.  The same effect with a built-in model: 1-qubit tomography whose
@@ -409,3 +415,37 @@ def test_simple_est_prec_and_rb_match_the_oracle(qb, tmp_path):
     np.testing.assert_allclose(mean, ou.est_mean(), rtol=1e-6)
     np.testing.assert_allclose(cov, ou.est_covariance_mtx(), rtol=1e-4, atol=1e-10)
     assert abs(mean[0] - 0.99) < 0.01
+
+
+def test_read_side_estimators_match_the_oracle(qb, oracle):
+    """est_entropy / est_credible_region / est_meanfn / sample (distributions.py:320-333, 411-430, 457-465, 557-596)
+    on a weighted cloud, against the oracle's ParticleDistribution holding the same particles."""
+    rs = np.random.RandomState(8)
+    n = 3000
+    x = np.column_stack([0.9 + 0.1 * rs.random_sample(n), 0.5 * rs.random_sample(n), 0.5 * rs.random_sample(n)])
+    m_g, m_o = qb.RandomizedBenchmarkingModel(), oracle.RandomizedBenchmarkingModel()
+    up = qb.SMCUpdater(m_g, n, cases.FixedPrior(x), resample_thresh=0.0)
+    ou = oracle.SMCUpdater(m_o, n, cases.FixedPrior(x), resample_thresh=0.0)
+    ep = np.empty((2,), dtype=m_g.expparams_dtype)
+    ep['m'] = [7, 60]
+    for u in (up, ou):
+        u.update(0, ep[0:1])
+        u.update(1, ep[1:2])
+    w_o, x_o = ou.particle_weights, ou.particle_locations
+    np.testing.assert_allclose(up.particle_weights, w_o, rtol=1e-12)
+    nz = w_o[w_o > 0]
+    assert up.est_entropy() == pytest.approx(-np.sum(np.log(nz) * nz), rel=1e-12)
+    inside, outside = up.est_credible_region(level=0.9, return_outside=True, modelparam_slice=slice(0, 2))
+    order = np.argsort(w_o)[::-1]
+    k = int(np.sum(np.cumsum(w_o[order]) <= 0.9)) + 1
+    assert inside.shape == (k, 2) and outside.shape == (n - k, 2)
+    assert np.array_equal(np.sort(inside[:, 0]), np.sort(x_o[order][:k, 0]))
+    assert up.est_meanfn(lambda l: l[:, 0] ** 2) == pytest.approx(ou.est_meanfn(lambda l: l[:, 0] ** 2), rel=1e-12)
+    faces, verts = up.region_est_hull(level=0.5, modelparam_slice=slice(0, 2))
+    assert faces.shape[1:] == (2, 2) and verts.shape[1] == 2 and verts.shape[0] >= 3
+    np.random.seed(4)
+    s_g = up.sample(n=500)
+    np.random.seed(4)
+    s_o = ou.sample(n=500)
+    assert s_g.shape == (500, 3)
+    assert np.mean(np.all(s_g == s_o, axis=1)) > 0.99          # same uniforms, same CDF up to the weights' last bits
