@@ -297,6 +297,25 @@ int qb_lw_draw_retry(const qb_model* model, const double* d_x_old, int64_t n_old
                      const int64_t* d_idxs, int64_t k, int32_t own_mean, double* d_x_new,
                      uint8_t* d_invalid, int64_t* d_counters, void* stream);
 
+/* Merge draw for the device-RNG mode, d <= 4: the n_new uniforms are generated already sorted (exponential
+ * spacings E_k = -log(1 - u_k) of Philox stream (seed_e, off_e), k = 0 .. n_new, prefix-summed and normalised: exactly
+ * the order statistics of n_new i.i.d. uniforms), so the draw is a streaming merge with the CDF instead of n_new
+ * random bisections; slot k takes the k-th smallest uniform (the new particles are exchangeable), normals as in
+ * qb_lw_draw_move.  Needs n_new <= n_old and a CDF built with a QB_SCAN_FAST_GUIDE* mode on `d_ws` when use_guide
+ * != 0 (its tile scratch is reused).  d_parent_inv (n_new int32) receives the parent of every slot found invalid
+ * (input of qb_lw_merge_retry, which re-centres on the particle's own parent).  d_u_out / d_js_out (may be NULL):
+ * the sorted uniforms and every slot's parent, for tests.  d_counters as in qb_lw_draw_move. */
+int qb_lw_merge_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                     const double* d_cdf, void* d_ws, size_t ws_bytes, int32_t use_guide,
+                     const double* h_mean, const double* h_S, double a,
+                     uint64_t seed_e, uint64_t off_e, uint64_t seed_n, uint64_t off_n, int32_t scale_u,
+                     int64_t n_new, double* d_x_new, int32_t postselect, uint8_t* d_invalid,
+                     int32_t* d_parent_inv, int64_t* d_counters, double* d_u_out, int64_t* d_js_out, void* stream);
+int qb_lw_merge_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                      const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
+                      const int64_t* d_idxs, int64_t k, const int32_t* d_parent_inv, double* d_x_new,
+                      uint8_t* d_invalid, int64_t* d_counters, void* stream);
+
 /* ---- sharded cloud: peer mailboxes and the resample exchange ------------------- */
 #define QB_IPC_HANDLE_BYTES 64
 /* cudaMalloc + zero a mailbox of 2 * n_ranks * QB_MAILBOX_ROW doubles (the only entry points that allocate). */

@@ -17,7 +17,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "qinfer_b200", "libqinfer_b200.so")
+LIB = os.environ.get("QB_LIB_PATH") or os.path.join(HERE, "qinfer_b200", "libqinfer_b200.so")
+EXTRA_FLAGS = os.environ.get("QB_EXTRA_NVCC_FLAGS", "").split()        # experiment builds (A/B variants)
+if os.environ.get("QB_LIB_PATH"):
+    BUILD = os.path.join(HERE, "build_" + hashlib.sha256(LIB.encode()).hexdigest()[:8])
 
 SOURCES = ["qb_misc.cu", "qb_update.cu", "qb_moments.cu", "qb_resample.cu", "qb_tomography.cu", "qb_rng.cu",
            "qb_dist.cu", "qb_scan_exact.cu", "qb_mt19937.cu", "qb_design.cu"]
@@ -44,7 +47,7 @@ def _digest():
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -59,7 +62,7 @@ def build_library(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

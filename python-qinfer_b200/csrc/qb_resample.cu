@@ -1167,3 +1167,282 @@ extern "C" int qb_lw_draw_retry(const qb_model* model, const double* d_x_old, in
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }
+
+// =============================================================================================================
+// Merge draw (device-RNG mode, d <= 4): the uniforms are generated ALREADY SORTED, so the multinomial draw becomes
+// a streaming merge of two ascending sequences instead of n random bisections.
+//
+//   E_0 .. E_n  i.i.d. Exp(1)  (E_k = -log(1 - philox uniform k)),   S_k = E_0 + .. + E_k,   U_k = S_k / S_n
+// are distributed exactly as the order statistics of n i.i.d. U(0,1) variates (exponential spacings), and the new
+// particles of a resample are exchangeable, so slot k may take the k-th smallest uniform.  Three launches:
+//   exp_tile_sums_kernel   per-tile sums of E            (Philox + log, no memory traffic but the tile sums)
+//   cdf_scan_tiles_kernel  exclusive scan of the tile sums (shared with the CDF)
+//   lw_merge_move_kernel   per tile: regenerate E, block scan -> 8 consecutive ascending uniforms per thread;
+//                          ONE guided bisection for the thread's first uniform, then a forward walk through the
+//                          CDF (neighbouring threads walk neighbouring entries: coalesced, every sector fully
+//                          used, parents read once); gather, shrink, perturb, validity, 64-byte stores per thread.
+// The guided kernel above needs ~4 random 32-byte sectors per draw over 200 MB of tables (1.4 GB of sector traffic
+// at n = 1e7; TLB-bound at n = 1e8); this one streams the CDF and the parents once.  Offspring come out ordered by
+// parent index.  The retry pass re-centres on the particle's OWN parent (kept for the invalid slots only): the
+// reference's prefix-of-the-original-means quirk (resamplers.py:372) would pick the lowest-index parents here.
+// =============================================================================================================
+struct MergeParams {
+    LwFusedParams f;          // x_old, cdf, guide header/table, x_new, invalid, counters, seeds (seed_u/off_u = the
+                              // exponential stream), a, S, ms, model, n_old, n_new, scale_u, postselect
+    double* tiles;            // [ntiles + 1] exponential tile sums -> exclusive prefix, total last
+    int32_t* parent_inv;      // parent index of every slot found invalid (retry input); may be NULL if !postselect
+    double* u_out;            // optional: the sorted uniforms (tests)
+    int64_t* js_out;          // optional: every slot's parent (tests)
+};
+
+// the 8 exponentials of slots base .. base+7 (base even); slots beyond `last` (inclusive bound) give 0
+__device__ __forceinline__ void merge_exponentials(const LwFusedParams& f, int64_t base, int64_t last, double (&e)[SCAN_ITEMS]) {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 2; ++q) {
+        const int64_t k = base + 2 * q;
+        double a = 0.0, b = 0.0;
+        if (k <= last) {
+            philox_uniform_pair(f.seed_u, f.off_u + static_cast<uint64_t>(k >> 1), a, b);
+            a = -log(1.0 - a);  // 1 - a in (0, 1]
+            b = (k + 1 <= last) ? -log(1.0 - b) : 0.0;
+        }
+        e[2 * q] = a;
+        e[2 * q + 1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) exp_tile_sums_kernel(const __grid_constant__ LwFusedParams f,
+                                                                     double* __restrict__ tile_sums) {
+    __shared__ double warp_tot[SCAN_THREADS / 32];
+    const int64_t last = f.n_new;  // slots 0 .. n_new (n_new + 1 exponentials)
+    const int64_t ntiles = (f.n_new + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * SCAN_TILE + static_cast<int64_t>(threadIdx.x) * SCAN_ITEMS;
+        double e[SCAN_ITEMS];
+        merge_exponentials(f, base, last, e);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) s += e[k];
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int k = 0; k < SCAN_THREADS / 32; ++k) tot += warp_tot[k];
+            tile_sums[t] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(SCAN_THREADS) lw_merge_move_kernel(const __grid_constant__ MergeParams mp) {
+    __shared__ double warp_tot[SCAN_THREADS / 32];
+    const LwFusedParams& p = mp.f;
+    const DrawCtx dc = make_draw_ctx(p);
+    const int64_t n = p.n_old;
+    const int64_t last = p.n_new;
+    const int64_t ntiles = (p.n_new + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    const double inv_total = 1.0 / mp.tiles[ntiles];
+    const int lane = threadIdx.x & 31;
+    unsigned int over = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * SCAN_TILE + static_cast<int64_t>(threadIdx.x) * SCAN_ITEMS;
+        double e[SCAN_ITEMS];
+        merge_exponentials(p, base, last, e);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) s += e[k];
+        double total;
+        double run = mp.tiles[t] + block_exclusive_scan(s, warp_tot, total);
+        unsigned int nbad = 0;
+        if (base < p.n_new) {
+            // ascending uniforms of my slots (clamped below 1: S_k / S_n < 1 up to rounding)
+            double u[SCAN_ITEMS];
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                run += e[k];
+                u[k] = fmin(run * inv_total, 0.99999999999999989) * dc.scale;
+            }
+            // parent of the first slot by guided bisection, then walk forward
+            unsigned int dummy = 0;
+            DrawCtx d1 = dc;
+            d1.scale = 1.0;  // u is already scaled
+            int64_t j = guided_draw(d1, u[0], dummy);
+            int64_t par[SCAN_ITEMS];
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                if (k > 0) {
+                    while (j < n && __ldg(p.cdf + j) <= u[k]) ++j;
+                }
+                par[k] = j;
+            }
+            if (__ldg(p.cdf + j) <= u[0]) {
+                // guided_draw clamped slot 0 to n - 1 (uniform at or beyond the CDF total): so are all later slots
+#pragma unroll
+                for (int k = 0; k < SCAN_ITEMS; ++k) par[k] = n;
+            }
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                if (par[k] >= n) {
+                    par[k] = n - 1;
+                    if (base + k < p.n_new) ++over;
+                }
+            }
+            // normals, move, validity
+            double out[SCAN_ITEMS][D];
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 2; ++q) {
+                const int64_t i0 = base + 2 * q;
+                double ev[2][D];
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    const int64_t f0 = static_cast<int64_t>(m) * p.n_new + i0;
+                    if ((f0 & 1) == 0) {
+                        philox_normal_pair(p.seed_n, p.off_n + static_cast<uint64_t>(f0 >> 1), ev[0][m], ev[1][m]);
+                    } else {
+                        ev[0][m] = philox_normal_elem(p.seed_n, p.off_n, f0);
+                        ev[1][m] = philox_normal_elem(p.seed_n, p.off_n, f0 + 1);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t src = par[2 * q + h];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        double z = 0.0;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) z = fma(p.S[c * D + m], ev[h][m], z);
+                        out[2 * q + h][c] = ((p.a * __ldg(p.x_old + src * D + c)) + p.ms[c]) + z;
+                    }
+                }
+            }
+            unsigned long long flags = 0ull;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                const int64_t i = base + k;
+                if (i < p.n_new) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) stg_stream(p.x_new + i * D + c, out[k][c]);
+                    if (mp.u_out != nullptr) mp.u_out[i] = u[k];
+                    if (mp.js_out != nullptr) mp.js_out[i] = par[k];
+                    if (p.postselect) {
+                        auto row = [&](int c) { return out[k][c]; };
+                        if (!model_valid(p.mv, row)) {
+                            flags |= 1ull << (8 * k);
+                            ++nbad;
+                            mp.parent_inv[i] = static_cast<int32_t>(par[k]);
+                        }
+                    }
+                }
+            }
+            if (p.postselect) {
+                if (base + SCAN_ITEMS <= p.n_new) {
+                    *reinterpret_cast<unsigned long long*>(p.invalid + base) = flags;  // base % 8 == 0
+                } else {
+                    for (int k = 0; k < SCAN_ITEMS && base + k < p.n_new; ++k)
+                        p.invalid[base + k] = static_cast<uint8_t>((flags >> (8 * k)) & 1ull);
+                }
+            }
+        }
+        const unsigned int tot = __reduce_add_sync(0xffffffffu, nbad);
+        if (tot && lane == 0) atomicAdd(p.counters, static_cast<unsigned long long>(tot));
+    }
+    if (over) atomicAdd(p.counters + 1, static_cast<unsigned long long>(over));
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) lw_merge_retry_kernel(const __grid_constant__ MergeParams mp) {
+    const LwFusedParams& p = mp.f;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < p.k; r += stride) {
+        const int64_t dst = p.idxs[r];
+        const int64_t src = mp.parent_inv[dst];
+        double out[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double z = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; ++m)
+                z = fma(p.S[c * D + m], philox_normal_elem(p.seed_n, p.off_n, static_cast<int64_t>(m) * p.k + r), z);
+            out[c] = ((p.a * __ldg(p.x_old + src * D + c)) + p.ms[c]) + z;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) p.x_new[dst * D + c] = out[c];
+        auto row = [&](int c) { return out[c]; };
+        const bool ok = model_valid(p.mv, row);
+        p.invalid[dst] = ok ? 0 : 1;
+        if (!ok) atomicAdd(p.counters, 1ull);
+    }
+}
+
+extern "C" int qb_lw_merge_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                                const double* d_cdf, void* d_ws, size_t ws_bytes, int32_t use_guide,
+                                const double* h_mean, const double* h_S, double a, uint64_t seed_e, uint64_t off_e,
+                                uint64_t seed_n, uint64_t off_n, int32_t scale_u, int64_t n_new, double* d_x_new,
+                                int32_t postselect, uint8_t* d_invalid, int32_t* d_parent_inv, int64_t* d_counters,
+                                double* d_u_out, int64_t* d_js_out, void* stream) {
+    MergeParams mp;
+    int rc = fill_fused(mp.f, model, d_x_old, n_old, d, d_cdf, d_ws, ws_bytes, use_guide, h_mean, h_S, a, seed_e,
+                        off_e, seed_n, off_n, scale_u, d_x_new, d_invalid, d_counters);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(n_new >= 1 && n_new <= n_old, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_merge_move: needs 1 <= n_new <= n_old (the exponential tile sums reuse the CDF's tile scratch)");
+    QB_REQUIRE(d_ws && ws_bytes >= qb_cdf_workspace_bytes(n_old), QB_ERR_WORKSPACE,
+               "qb_lw_merge_move: workspace too small");
+    QB_REQUIRE(!postselect || d_parent_inv, QB_ERR_INVALID_ARGUMENT, "qb_lw_merge_move: NULL parent buffer");
+    QB_REQUIRE((reinterpret_cast<uintptr_t>(d_invalid) & 7) == 0, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_merge_move: d_invalid must be 8-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    mp.f.n_new = n_new;
+    mp.f.postselect = postselect ? 1 : 0;
+    mp.tiles = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 256);  // the CDF's tile sums are dead
+    mp.parent_inv = d_parent_inv;
+    mp.u_out = d_u_out;
+    mp.js_out = d_js_out;
+    QB_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int64_t), st));
+    if (!postselect) QB_CUDA_CHECK(cudaMemsetAsync(d_invalid, 0, static_cast<size_t>(n_new), st));
+    const int64_t ntiles = (n_new + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    const int grid = capped_grid(ntiles, 8);
+    exp_tile_sums_kernel<<<grid, SCAN_THREADS, 0, st>>>(mp.f, mp.tiles);
+    QB_CUDA_CHECK(cudaGetLastError());
+    cdf_scan_tiles_kernel<<<1, SCAN_THREADS, 0, st>>>(mp.tiles, ntiles);
+    QB_CUDA_CHECK(cudaGetLastError());
+    switch (d) {
+        case 1: lw_merge_move_kernel<1><<<grid, SCAN_THREADS, 0, st>>>(mp); break;
+        case 2: lw_merge_move_kernel<2><<<grid, SCAN_THREADS, 0, st>>>(mp); break;
+        case 3: lw_merge_move_kernel<3><<<grid, SCAN_THREADS, 0, st>>>(mp); break;
+        default: lw_merge_move_kernel<4><<<grid, SCAN_THREADS, 0, st>>>(mp); break;
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_merge_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                                 const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
+                                 const int64_t* d_idxs, int64_t k, const int32_t* d_parent_inv, double* d_x_new,
+                                 uint8_t* d_invalid, int64_t* d_counters, void* stream) {
+    MergeParams mp;
+    static const double dummy_cdf = 1.0;  // never dereferenced by the retry kernel
+    int rc = fill_fused(mp.f, model, d_x_old, n_old, d, &dummy_cdf, nullptr, 0, 0, h_mean, h_S, a, 0, 0, seed_n, off_n,
+                        0, d_x_new, d_invalid, d_counters);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_idxs && d_parent_inv && k >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_merge_retry: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    mp.f.idxs = d_idxs;
+    mp.f.k = k;
+    mp.tiles = nullptr;
+    mp.parent_inv = const_cast<int32_t*>(d_parent_inv);
+    mp.u_out = nullptr;
+    mp.js_out = nullptr;
+    QB_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, sizeof(int64_t), st));
+    const int grid = capped_grid((k + 127) / 128, 8);
+    switch (d) {
+        case 1: lw_merge_retry_kernel<1><<<grid, 128, 0, st>>>(mp); break;
+        case 2: lw_merge_retry_kernel<2><<<grid, 128, 0, st>>>(mp); break;
+        case 3: lw_merge_retry_kernel<3><<<grid, 128, 0, st>>>(mp); break;
+        default: lw_merge_retry_kernel<4><<<grid, 128, 0, st>>>(mp); break;
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}

@@ -346,7 +346,11 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         }
     };
     // Fill the ring before anything else: these copies need the predecessor's weights (acquired above), not its stats.
+#ifdef QB_VAR_OLD_PROLOGUE
+    const int npre = 0;
+#else
     const int npre = (my_tiles < UPD_STAGES) ? my_tiles : UPD_STAGES;
+#endif
     if (tid == NCT) {
         if (chained) asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy reads
         produce(0, npre);
@@ -358,7 +362,9 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
             if (seen != p.chain_prev_tag) __nanosleep(20);
         } while (seen != p.chain_prev_tag);
     }
+#ifndef QB_VAR_OLD_PROLOGUE
     __syncthreads();
+#endif
     if (p.guard && needs_host(p.stats_in)) {
         // Speculative launch whose predecessor needs the host: do nothing, say so.  stats_out is the block of
         // the COMMITTED state the host may still fall back to, so only its SKIPPED word is touched (a guarded
@@ -500,10 +506,12 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         // every block's weights are written (each fenced before its ticket): release them to a chained successor,
         // which then streams tiles while this block finishes the reduction (and the NVLink exchange)
         __threadfence();
+#ifndef QB_VAR_OLD_EPILOGUE
         if (tid == 0) {
             *p.ticket = 0u;  // no block of this launch touches it again; the successor's blocks come much later
             *reinterpret_cast<volatile double*>(p.data_tag) = p.tag;  // ordered behind the fence above
         }
+#endif
         // deterministic final reduction of the per-block partials (fixed lane/block order)
         constexpr int NV = 3 * KF;
         const int lane = tid & 31, wid = tid >> 5, nw = UPD_THREADS / 32;
@@ -517,7 +525,12 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         }
         __syncthreads();
         if (p.n_ranks > 1) peer_allreduce(p, sums, peer_scratch);
-        if (tid == 0) publish(p, sums);
+        if (tid == 0) {
+            publish(p, sums);
+#ifdef QB_VAR_OLD_EPILOGUE
+            *p.ticket = 0u;
+#endif
+        }
     }
 }
 

@@ -16,7 +16,8 @@ QB_STAT_COUNT = 16
 QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY, QB_MODEL_COIN = 1, 2, 3, 4
 QB_SCAN_FAST, QB_SCAN_EXACT, QB_SCAN_FAST_GUIDE, QB_SCAN_FAST_GUIDE_SCALED = 0, 1, 2, 3
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqinfer_b200.so")
+_LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                         "libqinfer_b200.so")
 
 
 class QbModel(ctypes.Structure):
@@ -93,6 +94,11 @@ SIGNATURES = {
     "qb_lw_draw_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _SZ, _I32,
                                         ctypes.POINTER(_F64), ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I32,
                                         _P, _I64, _I32, _P, _P, _P, _P]),
+    "qb_lw_merge_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _SZ, _I32,
+                                        ctypes.POINTER(_F64), ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I32,
+                                        _I64, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "qb_lw_merge_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, ctypes.POINTER(_F64),
+                                         ctypes.POINTER(_F64), _F64, _U64, _U64, _P, _I64, _P, _P, _P, _P, _P]),
     "qb_mailbox_create": (ctypes.c_int, [_I32, ctypes.POINTER(_P)]),
     "qb_mailbox_destroy": (ctypes.c_int, [_P]),
     "qb_ipc_get_handle": (ctypes.c_int, [_P, ctypes.c_char_p]),

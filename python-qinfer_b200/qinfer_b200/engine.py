@@ -8,6 +8,7 @@ workspaces.  Every arithmetic step is a call into ``libqinfer_b200.so``;
 nothing here computes on the CPU and nothing falls back to it.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -48,6 +49,8 @@ class DeviceCloud(object):
             f64 = dict(dtype=torch.float64, device=self.device)
             self.x = torch.empty((self.n, self.d), **f64)
             self.x_alt = None                     # allocated at the first resample
+            _pad = int(os.environ.get("QB_ALLOC_PAD", "0"))     # experiment knob: shift the weight buffers
+            self._pad_tensor = torch.empty((_pad,), dtype=torch.uint8, device=self.device) if _pad else None
             # weights and stats are ping-pong pairs: `cur` is the committed state, 1 - cur receives the
             # next update (so a rejected update leaves the committed weights intact, smc.py:423-441)
             self._w = [torch.empty((self.n,), **f64), torch.empty((self.n,), **f64)]
@@ -78,7 +81,7 @@ class DeviceCloud(object):
                 self.basis_dev = torch.from_numpy(b.copy()).to(self.device)
             self.lib_model = ctypes.pointer(desc.c_model)
         # resample scratch, allocated lazily
-        self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = None
+        self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = self._parent_inv = None
         self._moments_event = None
         self._chain_tag = 0                # tag of the fused update that was the LAST thing queued for this cloud
         self._chain_dst = -1               # ... and the weights/stats buffer it wrote
@@ -383,6 +386,35 @@ class DeviceCloud(object):
                                         int(off_n) & _U64_MASK, 1 if scale_u else 0, _ptr(self._idxs), int(k),
                                         1 if own_mean else 0, _ptr(dst), _ptr(self._invalid), _ptr(self.counter),
                                         _stream()))
+        self.launches += 1
+
+    def lw_merge_move(self, mean, S, a, seed_e, off_e, seed_n, off_n, n_new, postselect, dst=None, scale_u=False,
+                      u_out=None, js_out=None):
+        """Merge draw + move (sorted uniforms from exponential spacings, streaming merge with the CDF)."""
+        if dst is None:
+            if self.x_alt is None or self.x_alt.shape[0] != n_new:
+                self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+            dst = self.x_alt
+        self._fused_scratch(n_new)
+        if self._parent_inv is None or self._parent_inv.numel() < n_new:
+            self._parent_inv = torch.empty((n_new,), dtype=torch.int32, device=self.device)
+        check(self.lib.qb_lw_merge_move(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._cdf), _ptr(self.ws),
+                                        self.ws_bytes, 1, _lib.f64_array(mean),
+                                        _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
+                                        int(seed_e) & _U64_MASK, int(off_e) & _U64_MASK, int(seed_n) & _U64_MASK,
+                                        int(off_n) & _U64_MASK, 1 if scale_u else 0, int(n_new), _ptr(dst),
+                                        int(bool(postselect)), _ptr(self._invalid), _ptr(self._parent_inv),
+                                        _ptr(self.counter), _ptr(u_out) if u_out is not None else None,
+                                        _ptr(js_out) if js_out is not None else None, _stream()))
+        self.launches += 3
+
+    def lw_merge_retry(self, mean, S, a, seed_n, off_n, k, dst=None):
+        dst = self.x_alt if dst is None else dst
+        check(self.lib.qb_lw_merge_retry(self.lib_model, _ptr(self.x), self.n, self.d, _lib.f64_array(mean),
+                                         _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
+                                         int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, _ptr(self._idxs), int(k),
+                                         _ptr(self._parent_inv), _ptr(dst), _ptr(self._invalid), _ptr(self.counter),
+                                         _stream()))
         self.launches += 1
 
     def read_counter(self):

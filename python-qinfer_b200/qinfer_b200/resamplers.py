@@ -22,6 +22,11 @@ Two extra, keyword-only knobs that the reference does not have:
           ``seed``) for throughput.
 ``scan``  ``'exact'`` (default) reproduces ``np.cumsum``'s sequential fp64
           rounding bit for bit; ``'fast'`` is a re-associated parallel scan.
+``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'merge'`` (default): the uniforms are generated
+          already sorted (exponential spacings, a scan), so the draw streams the CDF and the parents once; the
+          new particles come out ordered by parent and a retry re-centres on the particle's own parent.
+          ``'guided'``: i.i.d. order through the guide table, bit-identical to the staged launches (incl. the
+          reference's prefix-``mus`` retry quirk).
 """
 import abc
 import warnings
@@ -86,7 +91,8 @@ class DeviceParticles(object):
 
 class LiuWestResampler(Resampler):
     def __init__(self, a=0.98, h=None, maxiter=1000, debug=False, postselect=True, zero_cov_comp=1e-10,
-                 default_n_particles=None, kernel=np.random.randn, *, rng='numpy', seed=None, scan='exact'):
+                 default_n_particles=None, kernel=np.random.randn, *, rng='numpy', seed=None, scan='exact',
+                 draw='merge'):
         self._default_n_particles = default_n_particles
         self._override_h = False
         self.a = a
@@ -104,8 +110,11 @@ class LiuWestResampler(Resampler):
             raise ValueError("scan must be 'exact' or 'fast'")
         if rng != 'numpy' and kernel is not np.random.randn:
             raise ValueError("a custom perturbation kernel needs rng='numpy' (it is a host callable)")
+        if draw not in ('merge', 'guided'):
+            raise ValueError("draw must be 'merge' or 'guided'")
         self._rng = rng
         self._scan = scan
+        self._draw = draw       # device-RNG mode only: sorted uniforms + streaming merge, or i.i.d. order + guide table
         self._seed = int(seed) if seed is not None else 0x5EED
         self._philox_offset = 0
         self.last_n_iters = 0
@@ -186,12 +195,18 @@ class LiuWestResampler(Resampler):
         seed_u, seed_n = seed, seed ^ 0x9E3779B97F4A7C15
         if build_cdf:
             cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED if scale_u else _lib.QB_SCAN_FAST_GUIDE)
+        merge = self._draw == 'merge'
         off_u = self._philox_offset
-        self._philox_offset += (n_particles + 1) // 2
+        self._philox_offset += (n_particles + 2) // 2 if merge else (n_particles + 1) // 2
         off_n = self._philox_offset
         self._philox_offset += (d * n_particles + 1) // 2
-        cloud.lw_draw_move(mean, S, a, seed_u, off_u, seed_n, off_n, n_particles, self._postselect, dst=dst,
-                           scale_u=scale_u)
+        if merge:
+            # sorted uniforms (n + 1 exponential spacings of the uniform stream) + streaming merge with the CDF
+            cloud.lw_merge_move(mean, S, a, seed_u, off_u, seed_n, off_n, n_particles, self._postselect, dst=dst,
+                                scale_u=scale_u)
+        else:
+            cloud.lw_draw_move(mean, S, a, seed_u, off_u, seed_n, off_n, n_particles, self._postselect, dst=dst,
+                               scale_u=scale_u)
         n_invalid, self.last_overflow = cloud.read_counter()
         n_iters = 1
         while n_invalid and n_iters < self._maxiter:
@@ -199,8 +214,11 @@ class LiuWestResampler(Resampler):
             cloud.compact_invalid(n_particles)
             off_n = self._philox_offset
             self._philox_offset += (d * n_invalid + 1) // 2
-            cloud.lw_draw_retry(mean, S, a, seed_u, off_u, seed_n, off_n, n_invalid, dst=dst, scale_u=scale_u,
-                                own_mean=own_mean)
+            if merge:
+                cloud.lw_merge_retry(mean, S, a, seed_n, off_n, n_invalid, dst=dst)
+            else:
+                cloud.lw_draw_retry(mean, S, a, seed_u, off_u, seed_n, off_n, n_invalid, dst=dst, scale_u=scale_u,
+                                    own_mean=own_mean)
             n_invalid, _ = cloud.read_counter()
         return n_iters, n_invalid
 

@@ -696,7 +696,7 @@ def test_fused_draw_move_bit_identical_to_staged(qb, kind, n, n_new):
     model, x, w = _fused_case(qb, kind, n, 17)
     out = []
     for fused in (False, True):
-        res = qb.LiuWestResampler(a=0.9, rng='philox', seed=1234567, scan='fast')
+        res = qb.LiuWestResampler(a=0.9, rng='philox', seed=1234567, scan='fast', draw='guided')
         res._fused = fused
         up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
         up.particle_weights = w
@@ -720,7 +720,7 @@ def test_fused_resample_against_oracle_given_the_same_variates(qb, oracle, n):
     from qinfer_b200.engine import _ptr, _stream
     model, x, w = _fused_case(qb, "prec", n, 5)
     seed = 99
-    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=seed, scan='fast')
+    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=seed, scan='fast', draw='guided')
     up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
     up.particle_weights = w
     cloud = up._cloud
@@ -808,3 +808,79 @@ def test_coin_model_updates_match_the_oracle(qb, oracle):
         np.testing.assert_allclose(g.est_mean(), o.est_mean(), rtol=1e-12)
         assert np.array_equal(qb.CoinModel().are_models_valid(np.array([[-0.1], [0.0], [0.5], [1.0], [1.1]])),
                               np.array([False, True, True, True, False]))
+
+
+
+# ---------------------------------------------------------------------------
+# Merge draw: sorted uniforms from exponential spacings + streaming merge with the CDF
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n", [("prec", 9), ("prec", 1000), ("prec", 4096), ("prec", 100003), ("rb", 65537),
+                                    ("rb_il", 20001), ("prec", 2 ** 21), ("prec", 10 ** 7)])
+def test_merge_draw_parents_and_particles_are_exact(qb, oracle, kind, n):
+    """qb_lw_merge_move with its debug outputs: the uniforms are ascending, in [0, 1) and uniformly spread; every
+    slot's parent is exactly min(searchsorted(cdf, u, 'right'), n - 1) on the device's own CDF (the forward walk
+    equals the bisection); and the new particle is a * x[parent] + (1 - a) * mean + S @ eps with eps from the
+    normal stream, bit for bit (resamplers.py:318-332 arithmetic)."""
+    import torch
+    model, x, w = _fused_case(qb, kind, n, 23)
+    d = x.shape[1]
+    seed = 4242
+    res = qb.LiuWestResampler(a=0.95, rng='philox', seed=seed, scan='fast')
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
+    up.particle_weights = w
+    cloud = up._cloud
+    mean, cov = up.est_mean(), up.est_covariance_mtx()
+    S = np.real(res.h * oracle.sqrtm_psd(cov)[0])
+    cdf = cloud.cdf(qb._lib.QB_SCAN_FAST_GUIDE).cpu().numpy().copy()
+    u_out = torch.empty((n,), dtype=torch.float64, device=cloud.device)
+    js_out = torch.empty((n,), dtype=torch.int64, device=cloud.device)
+    off_e, off_n = 0, (n + 2) // 2
+    seed_n = seed ^ 0x9E3779B97F4A7C15
+    cloud.lw_merge_move(mean, S, 0.95, seed, off_e, seed_n, off_n, n, True, u_out=u_out, js_out=js_out)
+    n_invalid, overflow = cloud.read_counter()
+    u, js, got = u_out.cpu().numpy(), js_out.cpu().numpy(), cloud.x_alt.cpu().numpy().copy()
+    assert np.all(np.diff(u) >= 0) and u[0] >= 0 and u[-1] < 1
+    if n >= 1000:                                      # order statistics of n uniforms: KS distance ~ 1/sqrt(n)
+        assert np.max(np.abs(u - (np.arange(n) + 0.5) / n)) < 4.0 / np.sqrt(n)
+    want_js = np.minimum(cdf.searchsorted(u, side='right'), n - 1)
+    assert np.array_equal(js, want_js)
+    assert overflow == int(np.sum(cdf.searchsorted(u, side='right') >= n))
+    eps = torch.empty((d * n,), dtype=torch.float64, device=cloud.device)
+    cloud.rng_normal(eps, d * n, seed_n, off_n)
+    e = eps.cpu().numpy().reshape(d, n)
+    want = (0.95 * x[js] + (1 - 0.95) * mean)
+    if d == 1:
+        want = want + np.dot(S, e).T                    # one product, one sum: bit-exact
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want + np.dot(S, e).T, rtol=1e-13, atol=1e-15)
+    valid = model.are_models_valid(got)
+    flags = cloud._invalid[:n].cpu().numpy().astype(bool)
+    assert np.array_equal(flags, ~valid) and n_invalid == int(np.sum(~valid))
+    if n_invalid:
+        par = cloud._parent_inv[:n].cpu().numpy()
+        assert np.array_equal(par[flags], js[flags])
+
+
+@pytest.mark.parametrize("kind,n", [("prec_minfreq", 50001), ("rb", 2 ** 18)])
+def test_merge_mode_resample_through_the_plugin(qb, kind, n):
+    """LiuWestResampler(rng='philox', scan='fast') (draw='merge' is its default) through the resampler call:
+    retries leave only valid particles, mean and covariance are preserved as Liu-West promises."""
+    model, x, w = _fused_case(qb, kind, n, 31)
+    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast')
+    assert res._draw == 'merge'
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
+    up.particle_weights = w
+    m0, c0 = up.est_mean(), up.est_covariance_mtx()
+    ess0 = up.n_ess
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        up.resample()
+    assert res.last_n_iters > 1
+    locs = up.particle_locations
+    assert model.are_models_valid(locs).all()
+    m1, c1 = up.est_mean(), up.est_covariance_mtx()
+    sig = np.sqrt(np.diag(c0))
+    assert np.all(np.abs(m1 - m0) < 6 * sig / np.sqrt(ess0) + 0.02 * sig)     # postselection shifts the mean a little
+    assert np.all(np.abs(np.diag(c1) / np.diag(c0) - 1) < 0.15)
+    assert np.all(up.particle_weights == 1.0 / n)

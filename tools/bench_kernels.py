@@ -39,6 +39,7 @@ def bench_update(n, model, ep_setup, d, label, fuse_list=(1,)):
         x = rs.random_sample((n, d)) / d
     cloud.upload_locations(x)
     cloud.set_uniform_weights()
+    print("  x %#x  w0 %#x  w1 %#x" % (cloud.x.data_ptr(), cloud._w[0].data_ptr(), cloud._w[1].data_ptr()))
     ep = _lib.QbExpparams()
     outcome = ep_setup(ep)
     state = {"src": 0}
@@ -62,7 +63,8 @@ def main():
         def prec1(ep):
             ep.t = 17.3
             return 1
-        print("QB_UPD_ZIGZAG=%s QB_UPD_L2HINT=%s" % (os.environ.get("QB_UPD_ZIGZAG"), os.environ.get("QB_UPD_L2HINT")))
+        print("QB_UPD_ZIGZAG=%s QB_UPD_L2HINT=%s QB_ALLOC_PAD=%s" % (os.environ.get("QB_UPD_ZIGZAG"),
+              os.environ.get("QB_UPD_L2HINT"), os.environ.get("QB_ALLOC_PAD")))
         bench_update(n, qb.SimplePrecessionModel(), prec1, 1, "update precession d=1", (1, 8))
         return
     if what in ("update", "all"):
@@ -117,6 +119,12 @@ def main():
             print("  lw_move      %8.1f us" % timed(lambda: cloud.lw_move(mean, S, 0.98, cloud._eps, nn, True), 20))
             if d == 16:
                 print("  canonicalize %8.1f us" % timed(lambda: cloud.canonicalize(), 10))
+            if d <= 4:
+                print("  cdf fast+guide %6.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_FAST_GUIDE), 20))
+                print("  fused draw+move (guided) %8.1f us" % timed(
+                    lambda: cloud.lw_draw_move(mean, S, 0.98, 1, 0, 2, 0, nn, True), 20))
+                print("  merge draw+move (sorted) %8.1f us  (3 launches)" % timed(
+                    lambda: cloud.lw_merge_move(mean, S, 0.98, 1, 0, 2, 0, nn, True), 20))
 
 
 if __name__ == "__main__":
