@@ -1264,27 +1264,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) lw_merge_move_kernel(const __gri
                 run += e[k];
                 u[k] = fmin(run * inv_total, 0.99999999999999989) * dc.scale;
             }
-            // parent of the first slot by guided bisection, then walk forward
+            // parent of the first slot by guided bisection; the parents of the other slots lie a few entries further
+            // on: fetch a window of the CDF with independent loads (one memory round trip instead of a chain of
+            // dependent ones) and count, per slot, the entries at or below its uniform; walk on only past the window
             unsigned int dummy = 0;
             DrawCtx d1 = dc;
             d1.scale = 1.0;  // u is already scaled
-            int64_t j = guided_draw(d1, u[0], dummy);
-            int64_t par[SCAN_ITEMS];
+            const int64_t j0 = guided_draw(d1, u[0], dummy);
+            const bool clamped0 = __ldg(p.cdf + j0) <= u[0];  // uniform at or beyond the CDF total (then all are)
+            constexpr int WIN = 16;
+            double cw[WIN];
 #pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) {
-                if (k > 0) {
+            for (int i = 0; i < WIN; ++i) cw[i] = (j0 + i < n) ? __ldg(p.cdf + j0 + i) : INFINITY;
+            int64_t par[SCAN_ITEMS];
+            par[0] = j0;
+#pragma unroll
+            for (int k = 1; k < SCAN_ITEMS; ++k) {
+                int cnt = 0;
+#pragma unroll
+                for (int i = 0; i < WIN; ++i) cnt += (cw[i] <= u[k]) ? 1 : 0;
+                int64_t j = j0 + cnt;
+                if (cnt == WIN) {
                     while (j < n && __ldg(p.cdf + j) <= u[k]) ++j;
                 }
                 par[k] = j;
             }
-            if (__ldg(p.cdf + j) <= u[0]) {
-                // guided_draw clamped slot 0 to n - 1 (uniform at or beyond the CDF total): so are all later slots
-#pragma unroll
-                for (int k = 0; k < SCAN_ITEMS; ++k) par[k] = n;
-            }
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
-                if (par[k] >= n) {
+                if (clamped0 || par[k] >= n) {
                     par[k] = n - 1;
                     if (base + k < p.n_new) ++over;
                 }

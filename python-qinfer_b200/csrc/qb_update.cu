@@ -246,7 +246,11 @@ __device__ void peer_allreduce(const UpdateParams& p, double* sums, double* scra
 // full[s]  (count 1)  : producer's expect_tx + the bulk copies' complete_tx  -> consumers may read stage s
 // empty[s] (count NCW): one arrive per consumer warp                        -> producer may refill stage s
 // No CTA-wide barrier in the tile loop: warps drift freely across the ring.
-template <int KIND, bool BINOM, int DT, int KF>
+// CHAIN: compiled for clouds whose launches may be chained (sharded clouds): flag-based dependency on the
+// predecessor, ring prefetch before the stats wait, early release of the weights.  CHAIN = false is the plain
+// programmatic-dependent-launch kernel (one GPU: measured 1.5 us/launch faster than running the chain-capable
+// code un-chained).
+template <int KIND, bool BINOM, int DT, int KF, bool CHAIN>
 __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_kernel(const __grid_constant__ UpdateParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TILE_CT = (DT == 1) ? 1024 : 512;  // must match choose_tile()
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
     //            sharded, publish).  This launch acquires data_tag, starts streaming tiles, and only then waits
     //            for the stats tag: the predecessor's tail and the NVLink exchange hide behind the pipeline fill.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const bool chained = p.chain_prev_tag != 0.0;
+    const bool chained = CHAIN && p.chain_prev_tag != 0.0;
     if (!chained) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
     } else if (tid == 0) {
@@ -283,6 +287,27 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
             asm volatile("ld.acquire.gpu.global.f64 %0, [%1];" : "=d"(seen) : "l"(p.data_tag) : "memory");
             if (seen != p.chain_prev_tag) __nanosleep(20);
         } while (seen != p.chain_prev_tag);
+    }
+    if constexpr (!CHAIN) {
+        if (p.guard && needs_host(p.stats_in)) {
+            // Speculative launch whose predecessor needs the host: do nothing, say so.  stats_out is the block of
+            // the COMMITTED state the host may still fall back to, so only its SKIPPED word is touched (a guarded
+            // launch queued behind this one cancels on it); the host learns through the mirror.
+            if (blockIdx.x == 0 && tid == 0) {
+                p.stats_out[QB_STAT_SKIPPED] = 1.0;
+                if (p.mirror != nullptr) {
+                    for (int j = 0; j < p.nsteps; ++j) {
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j), "d"(0.0),
+                                     "d"(0.0), "d"(0.0), "d"(p.tag)
+                                     : "memory");
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j + 4),
+                                     "d"(0.0), "d"(0.0), "d"(p.tag), "d"(2.0)
+                                     : "memory");
+                    }
+                }
+            }
+            return;
+        }
     }
 
     const uint32_t bar0 = smem_u32(smem_raw);  // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
@@ -321,86 +346,109 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         return (p.reverse ? last_tile - ti : ti) * tile;
     };
 
-    // ===== producer state (lane 0 of the last warp streams my tiles into the ring) =====
-    int prod_s = 0;
-    uint32_t prod_phase = 0;
-    // L2 residency: w_in is dead once read (the next launch overwrites it), x and the new weights are what
-    // the next launch reads first (it walks the slab in the opposite direction)
-    uint64_t pol_w = (p.l2hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
-    uint64_t pol_x = (p.l2hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-    const int64_t pin_end = static_cast<int64_t>(p.pin_tiles) * tile;
-    auto produce = [&](int i_from, int i_to) {
-        for (int i = i_from; i < i_to; ++i) {
-            const int64_t first = tile_first(i);
-            if (p.l2hint & 8) pol_w = pol_x = (first < pin_end) ? pol_keep : pol_stream;
-            mbar_wait(bar0 + 64 + 8 * prod_s, prod_phase ^ 1u);  // passes at once the first time round the ring
-            const uint32_t dst = ring0 + static_cast<uint32_t>(prod_s) * stage_bytes;
-            mbar_expect_tx(bar0 + 8 * prod_s, stage_bytes);
-            tma_load_1d_hint(dst, p.x + first * d, x_bytes, bar0 + 8 * prod_s, pol_x);
-            tma_load_1d_hint(dst + x_bytes, p.w_in + first, w_bytes, bar0 + 8 * prod_s, pol_w);
-            if (++prod_s == UPD_STAGES) {
-                prod_s = 0;
-                prod_phase ^= 1u;
+    if constexpr (CHAIN) {
+        // ===== producer state (lane 0 of the last warp streams my tiles into the ring) =====
+        int prod_s = 0;
+        uint32_t prod_phase = 0;
+        // L2 residency: w_in is dead once read (the next launch overwrites it), x and the new weights are what
+        // the next launch reads first (it walks the slab in the opposite direction)
+        uint64_t pol_w = (p.l2hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+        uint64_t pol_x = (p.l2hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+        const int64_t pin_end = static_cast<int64_t>(p.pin_tiles) * tile;
+        auto produce = [&](int i_from, int i_to) {
+            for (int i = i_from; i < i_to; ++i) {
+                const int64_t first = tile_first(i);
+                if (p.l2hint & 8) pol_w = pol_x = (first < pin_end) ? pol_keep : pol_stream;
+                mbar_wait(bar0 + 64 + 8 * prod_s, prod_phase ^ 1u);  // passes at once the first time round the ring
+                const uint32_t dst = ring0 + static_cast<uint32_t>(prod_s) * stage_bytes;
+                mbar_expect_tx(bar0 + 8 * prod_s, stage_bytes);
+                tma_load_1d_hint(dst, p.x + first * d, x_bytes, bar0 + 8 * prod_s, pol_x);
+                tma_load_1d_hint(dst + x_bytes, p.w_in + first, w_bytes, bar0 + 8 * prod_s, pol_w);
+                if (++prod_s == UPD_STAGES) {
+                    prod_s = 0;
+                    prod_phase ^= 1u;
+                }
             }
+        };
+        // Fill the ring before anything else: these copies need the predecessor's weights (acquired above), not its stats.
+        const int npre = (my_tiles < UPD_STAGES) ? my_tiles : UPD_STAGES;
+        if (tid == NCT) {
+            if (chained) asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy reads
+            produce(0, npre);
         }
-    };
-    // Fill the ring before anything else: these copies need the predecessor's weights (acquired above), not its stats.
-#ifdef QB_VAR_OLD_PROLOGUE
-    const int npre = 0;
-#else
-    const int npre = (my_tiles < UPD_STAGES) ? my_tiles : UPD_STAGES;
-#endif
-    if (tid == NCT) {
-        if (chained) asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy reads
-        produce(0, npre);
-    }
-    if (chained && tid == 0) {  // now the predecessor's stats block (its last block is still reducing / exchanging)
-        double seen;
-        do {
-            asm volatile("ld.acquire.gpu.global.f64 %0, [%1];" : "=d"(seen) : "l"(p.stats_in + QB_STAT_TAG) : "memory");
-            if (seen != p.chain_prev_tag) __nanosleep(20);
-        } while (seen != p.chain_prev_tag);
-    }
-#ifndef QB_VAR_OLD_PROLOGUE
-    __syncthreads();
-#endif
-    if (p.guard && needs_host(p.stats_in)) {
-        // Speculative launch whose predecessor needs the host: do nothing, say so.  stats_out is the block of
-        // the COMMITTED state the host may still fall back to, so only its SKIPPED word is touched (a guarded
-        // launch queued behind this one cancels on it); the host learns through the mirror.
-        if (tid == 0) {
-            for (int s = 0; s < npre; ++s) mbar_wait(bar0 + 8 * s, 0u);  // let the prefetched copies land before exit
-            if (blockIdx.x == 0) {
-                p.stats_out[QB_STAT_SKIPPED] = 1.0;
-                __threadfence();
-                *reinterpret_cast<volatile double*>(p.stats_out + QB_STAT_TAG) = p.tag;
-                if (p.mirror != nullptr) {
-                    for (int j = 0; j < p.nsteps; ++j) {
-                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j), "d"(0.0),
-                                     "d"(0.0), "d"(0.0), "d"(p.tag)
-                                     : "memory");
-                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j + 4),
-                                     "d"(0.0), "d"(0.0), "d"(p.tag), "d"(2.0)
-                                     : "memory");
-                    }
-                }
-                // a chained successor of THIS launch must not wait for weights that will never come
-                if (p.data_tag != nullptr) {
-                    __threadfence();
-                    *reinterpret_cast<volatile double*>(p.data_tag) = p.tag;
-                }
-            }
+        if (chained && tid == 0) {  // now the predecessor's stats block (its last block is still reducing / exchanging)
+            double seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.f64 %0, [%1];" : "=d"(seen) : "l"(p.stats_in + QB_STAT_TAG) : "memory");
+                if (seen != p.chain_prev_tag) __nanosleep(20);
+            } while (seen != p.chain_prev_tag);
         }
         __syncthreads();
-        return;
+        if (p.guard && needs_host(p.stats_in)) {
+            // Speculative launch whose predecessor needs the host: do nothing, say so.  stats_out is the block of
+            // the COMMITTED state the host may still fall back to, so only its SKIPPED word is touched (a guarded
+            // launch queued behind this one cancels on it); the host learns through the mirror.
+            if (tid == 0) {
+                for (int s = 0; s < npre; ++s) mbar_wait(bar0 + 8 * s, 0u);  // let the prefetched copies land before exit
+                if (blockIdx.x == 0) {
+                    p.stats_out[QB_STAT_SKIPPED] = 1.0;
+                    __threadfence();
+                    *reinterpret_cast<volatile double*>(p.stats_out + QB_STAT_TAG) = p.tag;
+                    if (p.mirror != nullptr) {
+                        for (int j = 0; j < p.nsteps; ++j) {
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j), "d"(0.0),
+                                         "d"(0.0), "d"(0.0), "d"(p.tag)
+                                         : "memory");
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror + 8 * j + 4),
+                                         "d"(0.0), "d"(0.0), "d"(p.tag), "d"(2.0)
+                                         : "memory");
+                        }
+                    }
+                    // a chained successor of THIS launch must not wait for weights that will never come
+                    if (p.data_tag != nullptr) {
+                        __threadfence();
+                        *reinterpret_cast<volatile double*>(p.data_tag) = p.tag;
+                    }
+                }
+            }
+            __syncthreads();
+            return;
+        }
+
+        if (tid == NCT) produce(npre, my_tiles);   // the producer lane does the rest of its job here
     }
 
     if (tid >= NCT) {
-        if (tid == NCT) produce(npre, my_tiles);
+        if constexpr (!CHAIN) {
+            // ===== producer warp: one lane streams my tiles into the ring =====
+            if (tid == NCT) {
+                int s = 0;
+                uint32_t phase = 0;
+                // L2 residency: w_in is dead once read (the next launch overwrites it), x and the new weights are
+                // what the next launch reads first (it walks the slab in the opposite direction)
+                uint64_t pol_w = (p.l2hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+                uint64_t pol_x = (p.l2hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+                const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+                const int64_t pin_end = static_cast<int64_t>(p.pin_tiles) * tile;
+                for (int i = 0; i < my_tiles; ++i) {
+                    const int64_t first = tile_first(i);
+                    if (p.l2hint & 8) pol_w = pol_x = (first < pin_end) ? pol_keep : pol_stream;
+                    mbar_wait(bar0 + 64 + 8 * s, phase ^ 1u);  // passes at once the first time round the ring
+                    const uint32_t dst = ring0 + static_cast<uint32_t>(s) * stage_bytes;
+                    mbar_expect_tx(bar0 + 8 * s, stage_bytes);
+                    tma_load_1d_hint(dst, p.x + first * d, x_bytes, bar0 + 8 * s, pol_x);
+                    tma_load_1d_hint(dst + x_bytes, p.w_in + first, w_bytes, bar0 + 8 * s, pol_w);
+                    if (++s == UPD_STAGES) {
+                        s = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
     } else {
         // ===== consumer warps =====
-        const double inv_norm = __ldcg(p.stats_in + QB_STAT_INV_NORM);
+        const double inv_norm = CHAIN ? __ldcg(p.stats_in + QB_STAT_INV_NORM) : p.stats_in[QB_STAT_INV_NORM];
         const ModelView mv = p.mv;
         const int lane = tid & 31;
         auto meas = [&](int c) { return meas_s[c]; };
@@ -480,7 +528,7 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
             for (int j = tid; j < cnt; j += NCT) {
                 const double* xr = p.x + (first + j) * d;
                 auto row = [&](int c) { return xr[c]; };
-                double wv = __ldcg(p.w_in + first + j) * inv_norm;
+                double wv = (CHAIN ? __ldcg(p.w_in + first + j) : p.w_in[first + j]) * inv_norm;
 #pragma unroll
                 for (int k = 0; k < KF; ++k) {
                     if (KF == 1 || k < nsteps) {
@@ -488,7 +536,10 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
                         accumulate(acc[k], bad, k, wv);
                     }
                 }
-                __stcg(p.w_out + first + j, wv);
+                if (CHAIN)
+                    __stcg(p.w_out + first + j, wv);
+                else
+                    p.w_out[first + j] = wv;
             }
         }
     }
@@ -506,12 +557,10 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         // every block's weights are written (each fenced before its ticket): release them to a chained successor,
         // which then streams tiles while this block finishes the reduction (and the NVLink exchange)
         __threadfence();
-#ifndef QB_VAR_OLD_EPILOGUE
-        if (tid == 0) {
+        if (CHAIN && tid == 0) {
             *p.ticket = 0u;  // no block of this launch touches it again; the successor's blocks come much later
             *reinterpret_cast<volatile double*>(p.data_tag) = p.tag;  // ordered behind the fence above
         }
-#endif
         // deterministic final reduction of the per-block partials (fixed lane/block order)
         constexpr int NV = 3 * KF;
         const int lane = tid & 31, wid = tid >> 5, nw = UPD_THREADS / 32;
@@ -519,7 +568,10 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         __syncthreads();
         for (int v = wid; v < NV; v += nw) {  // one warp per value
             double t = 0.0;
-            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) t += __ldcg(p.partials + static_cast<size_t>(b) * NV + v);
+            for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) {
+                const double* pp = p.partials + static_cast<size_t>(b) * NV + v;
+                t += CHAIN ? __ldcg(pp) : *pp;
+            }
             t = warp_sum(t);
             if (lane == 0) sums[v] = t;
         }
@@ -527,9 +579,7 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         if (p.n_ranks > 1) peer_allreduce(p, sums, peer_scratch);
         if (tid == 0) {
             publish(p, sums);
-#ifdef QB_VAR_OLD_EPILOGUE
-            *p.ticket = 0u;
-#endif
+            if (!CHAIN) *p.ticket = 0u;  // ready for the next launch on this stream
         }
     }
 }
@@ -551,30 +601,35 @@ static size_t update_smem_bytes(int d) {
 
 typedef void (*update_kernel_t)(const UpdateParams);
 
-template <int KF>
+template <int KF, bool CH>
 static update_kernel_t pick_update_kernel_k(const qb_model& m) {
     switch (m.kind) {
         case QB_MODEL_PRECESSION:
-            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true, 1, KF>
-                              : fused_update_kernel<QB_MODEL_PRECESSION, false, 1, KF>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true, 1, KF, CH>
+                              : fused_update_kernel<QB_MODEL_PRECESSION, false, 1, KF, CH>;
         case QB_MODEL_RB:
             if (m.interleaved)
-                return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 4, KF>
-                                  : fused_update_kernel<QB_MODEL_RB, false, 4, KF>;
-            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 3, KF>
-                              : fused_update_kernel<QB_MODEL_RB, false, 3, KF>;
+                return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 4, KF, CH>
+                                  : fused_update_kernel<QB_MODEL_RB, false, 4, KF, CH>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 3, KF, CH>
+                              : fused_update_kernel<QB_MODEL_RB, false, 3, KF, CH>;
         case QB_MODEL_COIN:
-            return m.binomial ? fused_update_kernel<QB_MODEL_COIN, true, 1, KF>
-                              : fused_update_kernel<QB_MODEL_COIN, false, 1, KF>;
+            return m.binomial ? fused_update_kernel<QB_MODEL_COIN, true, 1, KF, CH>
+                              : fused_update_kernel<QB_MODEL_COIN, false, 1, KF, CH>;
     }
     return nullptr;
 }
 
-static update_kernel_t pick_update_kernel(const qb_model& m, int nsteps) {
+template <bool CH>
+static update_kernel_t pick_update_kernel_c(const qb_model& m, int nsteps) {
     if (m.kind == QB_MODEL_TOMOGRAPHY)  // per-step measurement vectors do not fit the launch parameters: K = 1
-        return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true, 0, 1>
-                          : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false, 0, 1>;
-    return (nsteps == 1) ? pick_update_kernel_k<1>(m) : pick_update_kernel_k<KF_MAX>(m);
+        return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true, 0, 1, CH>
+                          : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false, 0, 1, CH>;
+    return (nsteps == 1) ? pick_update_kernel_k<1, CH>(m) : pick_update_kernel_k<KF_MAX, CH>(m);
+}
+
+static update_kernel_t pick_update_kernel(const qb_model& m, int nsteps, bool chain) {
+    return chain ? pick_update_kernel_c<true>(m, nsteps) : pick_update_kernel_c<false>(m, nsteps);
 }
 
 int validate_model(const qb_model* m) {
@@ -752,7 +807,7 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
     }
     for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? eps[0].meas[c] : 0.0;
 
-    update_kernel_t k = pick_update_kernel(*model, nsteps);
+    update_kernel_t k = pick_update_kernel(*model, nsteps, p.chain_capable != 0);
     const size_t smem = update_smem_bytes(model->d);
     const int limit = cached_grid_limit(k, smem, nsteps);
     QB_REQUIRE(limit > 0, QB_ERR_CUDA, "qb_fused_update: occupancy query failed: %s",
