@@ -321,6 +321,8 @@ class DeviceCloud(object):
         self._resample_scratch(n_new)
         if self.x_alt is None or self.x_alt.shape[0] != n_new:
             self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+        if self._parent_inv is None or self._parent_inv.numel() < n_new:
+            self._parent_inv = torch.empty((n_new,), dtype=torch.int32, device=self.device)
 
     def preallocate_resample_slab(self):
         if self.x_alt is None or self.x_alt.shape[0] != self.n:

@@ -22,13 +22,14 @@ Two extra, keyword-only knobs that the reference does not have:
           ``seed``) for throughput.
 ``scan``  ``'exact'`` (default) reproduces ``np.cumsum``'s sequential fp64
           rounding bit for bit; ``'fast'`` is a re-associated parallel scan.
-``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'merge'`` (default): the uniforms are generated
-          already sorted (exponential spacings, a scan), so the draw streams the CDF and the parents once; the
-          new particles come out ordered by parent and a retry re-centres on the particle's own parent.
-          ``'guided'``: i.i.d. order through the guide table, bit-identical to the staged launches (incl. the
-          reference's prefix-``mus`` retry quirk).
+``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'guided'`` (default): i.i.d. order through the
+          guide table, bit-identical to the staged launches (incl. the reference's prefix-``mus`` retry quirk).
+          ``'merge'``: the uniforms are generated already sorted (exponential spacings, a scan), so the draw streams
+          the CDF and the parents once instead of bisecting at random; the new particles come out ordered by
+          parent and a retry re-centres on the particle's own parent.
 """
 import abc
+import os
 import warnings
 
 import numpy as np
@@ -92,7 +93,7 @@ class DeviceParticles(object):
 class LiuWestResampler(Resampler):
     def __init__(self, a=0.98, h=None, maxiter=1000, debug=False, postselect=True, zero_cov_comp=1e-10,
                  default_n_particles=None, kernel=np.random.randn, *, rng='numpy', seed=None, scan='exact',
-                 draw='merge'):
+                 draw=None):
         self._default_n_particles = default_n_particles
         self._override_h = False
         self.a = a
@@ -110,6 +111,8 @@ class LiuWestResampler(Resampler):
             raise ValueError("scan must be 'exact' or 'fast'")
         if rng != 'numpy' and kernel is not np.random.randn:
             raise ValueError("a custom perturbation kernel needs rng='numpy' (it is a host callable)")
+        if draw is None:
+            draw = os.environ.get("QB_DRAW", "guided")      # (environment override: A/B runs of the bench)
         if draw not in ('merge', 'guided'):
             raise ValueError("draw must be 'merge' or 'guided'")
         self._rng = rng

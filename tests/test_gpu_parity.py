@@ -864,10 +864,10 @@ def test_merge_draw_parents_and_particles_are_exact(qb, oracle, kind, n):
 
 @pytest.mark.parametrize("kind,n", [("prec_minfreq", 50001), ("rb", 2 ** 18)])
 def test_merge_mode_resample_through_the_plugin(qb, kind, n):
-    """LiuWestResampler(rng='philox', scan='fast') (draw='merge' is its default) through the resampler call:
-    retries leave only valid particles, mean and covariance are preserved as Liu-West promises."""
+    """LiuWestResampler(rng='philox', scan='fast', draw='merge') through the resampler call: retries leave only
+    valid particles, mean and covariance are preserved as Liu-West promises."""
     model, x, w = _fused_case(qb, kind, n, 31)
-    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast')
+    res = qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast', draw='merge')
     assert res._draw == 'merge'
     up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
     up.particle_weights = w

@@ -67,6 +67,21 @@ def main():
               os.environ.get("QB_UPD_L2HINT"), os.environ.get("QB_ALLOC_PAD")))
         bench_update(n, qb.SimplePrecessionModel(), prec1, 1, "update precession d=1", (1, 8))
         return
+    if what == "resample1":
+        model = qb.SimplePrecessionModel()
+        cloud = DeviceCloud(qb.describe_model(model), n)
+        rs = np.random.RandomState(0)
+        cloud.upload_locations(rs.random_sample((n, 1)) * 0.2 + 0.4)
+        w = rs.random_sample(n) ** 4
+        cloud.upload_weights(w / w.sum())
+        mean, S = np.full(1, 0.5), np.eye(1) * 0.01
+        print("--- device-RNG resample kernels d=1 n=%d" % n)
+        print("  moments                  %8.1f us" % timed(lambda: cloud.lib.qb_moments(_ptr(cloud.x), _ptr(cloud.w), _ptr(cloud.stats), n, 1, _ptr(cloud.moments_out), _ptr(cloud.ws), cloud.ws_bytes, _stream()), 10))
+        print("  cdf fast                 %8.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_FAST), 10))
+        print("  cdf fast+guide           %8.1f us" % timed(lambda: cloud.cdf(_lib.QB_SCAN_FAST_GUIDE), 10))
+        print("  fused draw+move (guided) %8.1f us" % timed(lambda: cloud.lw_draw_move(mean, S, 0.98, 1, 0, 2, 0, n, True), 10))
+        print("  merge draw+move (sorted) %8.1f us  (3 launches)" % timed(lambda: cloud.lw_merge_move(mean, S, 0.98, 1, 0, 2, 0, n, True), 10))
+        return
     if what in ("update", "all"):
         def prec(ep):
             ep.t = 17.3
