@@ -83,11 +83,23 @@ class DeviceCloud(object):
         # resample scratch, allocated lazily
         self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = self._parent_inv = None
         self._moments_event = None
+        # one control block per destination slot: the constant fields are written once
+        self._ctls = [_lib.QbUpdateCtl(), _lib.QbUpdateCtl()]
+        self._ctl_key = None
+        self._refresh_ptrs()
         self._chain_tag = 0                # tag of the fused update that was the LAST thing queued for this cloud
         self._chain_dst = -1               # ... and the weights/stats buffer it wrote
         self._launches = 0
         self.resample_events = None        # bench: set to [] to collect a CUDA-event pair around every resample
         self.update_launches = 0
+
+    def _refresh_ptrs(self):
+        """Raw pointers of the buffers the hot loop passes on every launch (re-derived whenever a buffer is swapped)."""
+        self._px = _ptr(self.x)
+        self._pw = [_ptr(self._w[0]), _ptr(self._w[1])]
+        self._pstats = [_ptr(self._stats[0]), _ptr(self._stats[1])]
+        self._pws = _ptr(self.ws)
+        self._px_id = self.x.data_ptr()
 
     # Every entry point other than the fused update bumps ``launches`` after queueing its kernels; that also breaks
     # the update chain (a chained update depends on its predecessor through flags, not on whatever ran in between).
@@ -163,23 +175,30 @@ class DeviceCloud(object):
         dst = 1 - src
         k = len(steps)
         self._tag += 1
-        ctl = self._ctl
-        ctl.h_mirror = self.mirror.data_ptr() + dst * MIRROR_SLOT * 8
+        if self.x.data_ptr() != self._px_id or self._pw[0].value != self._w[0].data_ptr():
+            self._refresh_ptrs()                       # a resample swapped the slabs (or re-sized the weights)
+        key = (zero_weight_thresh, resample_below, self._ctl.n_ranks)
+        if key != self._ctl_key:                       # constants of the two per-slot control blocks
+            for slot, c in enumerate(self._ctls):
+                ctypes.memmove(ctypes.byref(c), ctypes.byref(self._ctl), ctypes.sizeof(_lib.QbUpdateCtl))
+                c.h_mirror = self.mirror.data_ptr() + slot * MIRROR_SLOT * 8
+                c.zero_weight_thresh = zero_weight_thresh
+                c.resample_below = resample_below
+            self._ctl_key = key
+        ctl = self._ctls[dst]
         ctl.tag = float(self._tag)
-        ctl.zero_weight_thresh = zero_weight_thresh
-        ctl.resample_below = resample_below
         ctl.guard = 1 if guard else 0
         # chained launch: the previous thing queued for this cloud is the update whose output this one reads
         ctl.chain_prev_tag = float(self._chain_tag) if (self._chain_tag and self._chain_dst == src) else 0.0
-        mask = 0
+        stream = _stream()
         if k == 1:
             ep, outcome, chk = steps[0]
             ctl.check_resample = 1 if chk else 0
-            check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep), int(outcome), _ptr(self.x), self.n,
-                                           _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
-                                           _ptr(self._stats[dst]), ctypes.byref(ctl), _ptr(self.ws), self.ws_bytes,
-                                           _stream()))
+            check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep), int(outcome), self._px, self.n,
+                                           self._pw[src], self._pw[dst], self._pstats[src], self._pstats[dst],
+                                           ctypes.byref(ctl), self._pws, self.ws_bytes, stream))
         else:
+            mask = 0
             eps, outs = self._eps_arr, self._out_arr
             for j, (ep, outcome, chk) in enumerate(steps):
                 ctypes.memmove(ctypes.byref(eps, j * ctypes.sizeof(_lib.QbExpparams)), ctypes.byref(ep),
@@ -187,10 +206,9 @@ class DeviceCloud(object):
                 outs[j] = int(outcome)
                 if chk:
                     mask |= 1 << j
-            check(self.lib.qb_fused_update_multi(self.lib_model, eps, outs, k, mask, _ptr(self.x), self.n,
-                                                 _ptr(self._w[src]), _ptr(self._w[dst]), _ptr(self._stats[src]),
-                                                 _ptr(self._stats[dst]), None, ctypes.byref(ctl), _ptr(self.ws),
-                                                 self.ws_bytes, _stream()))
+            check(self.lib.qb_fused_update_multi(self.lib_model, eps, outs, k, mask, self._px, self.n,
+                                                 self._pw[src], self._pw[dst], self._pstats[src], self._pstats[dst],
+                                                 None, ctypes.byref(ctl), self._pws, self.ws_bytes, stream))
         self.launches += 1
         self.update_launches += 1
         self._chain_tag, self._chain_dst = self._tag, dst
@@ -203,6 +221,17 @@ class DeviceCloud(object):
         m = self.mirror_np
         base = slot * MIRROR_SLOT
         want = float(tag)
+        if nsteps == 1:                         # the common case: two scalar reads per poll
+            i3, i6 = base + 3, base + 6
+            spins = 0
+            while True:
+                if m[i3] == want and m[i6] == want:
+                    a = m[base:base + 8].copy()
+                    if a[3] == want and a[6] == want:
+                        return a.reshape(1, 8)
+                spins += 1
+                if spins > 20000:
+                    break                       # fall through to the timed loop below
         t0 = None
         last = base + 8 * (nsteps - 1)
         while True:

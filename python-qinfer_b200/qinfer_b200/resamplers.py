@@ -22,11 +22,12 @@ Two extra, keyword-only knobs that the reference does not have:
           ``seed``) for throughput.
 ``scan``  ``'exact'`` (default) reproduces ``np.cumsum``'s sequential fp64
           rounding bit for bit; ``'fast'`` is a re-associated parallel scan.
-``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'guided'`` (default): i.i.d. order through the
-          guide table, bit-identical to the staged launches (incl. the reference's prefix-``mus`` retry quirk).
-          ``'merge'``: the uniforms are generated already sorted (exponential spacings, a scan), so the draw streams
-          the CDF and the parents once instead of bisecting at random; the new particles come out ordered by
-          parent and a retry re-centres on the particle's own parent.
+``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'guided'``: i.i.d. order through the guide table,
+          bit-identical to the staged launches (incl. the reference's prefix-``mus`` retry quirk).  ``'merge'``: the
+          uniforms are generated already sorted (exponential spacings, a scan), so the draw streams the CDF and
+          the parents once instead of bisecting at random; the new particles come out ordered by parent and a
+          retry re-centres on the particle's own parent.  ``'auto'`` (default): guided below 3.2e7 particles per
+          cloud, merge above (measured cross-over between 1e7 and 1e8).
 """
 import abc
 import os
@@ -39,6 +40,9 @@ import torch
 from . import _lib
 from ._exceptions import ResamplerError, ResamplerWarning
 from .distributions import ParticleDistribution, covariance_from_moments
+
+
+MERGE_DRAW_MIN_PARTICLES = 32 * 1000 * 1000
 
 
 def sqrtm_psd(A, est_error=True, check_finite=True):
@@ -112,9 +116,9 @@ class LiuWestResampler(Resampler):
         if rng != 'numpy' and kernel is not np.random.randn:
             raise ValueError("a custom perturbation kernel needs rng='numpy' (it is a host callable)")
         if draw is None:
-            draw = os.environ.get("QB_DRAW", "guided")      # (environment override: A/B runs of the bench)
-        if draw not in ('merge', 'guided'):
-            raise ValueError("draw must be 'merge' or 'guided'")
+            draw = os.environ.get("QB_DRAW", "auto")        # (environment override: A/B runs of the bench)
+        if draw not in ('auto', 'merge', 'guided'):
+            raise ValueError("draw must be 'auto', 'merge' or 'guided'")
         self._rng = rng
         self._scan = scan
         self._draw = draw       # device-RNG mode only: sorted uniforms + streaming merge, or i.i.d. order + guide table
@@ -198,7 +202,9 @@ class LiuWestResampler(Resampler):
         seed_u, seed_n = seed, seed ^ 0x9E3779B97F4A7C15
         if build_cdf:
             cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED if scale_u else _lib.QB_SCAN_FAST_GUIDE)
-        merge = self._draw == 'merge'
+        # measured (B200, d = 1): guided 310 us vs merge 331 us at n = 1e7, 6.9 ms vs 3.1 ms at n = 1e8 (the guided
+        # draw's random sectors run out of TLB reach / L2 there); 'auto' switches in between
+        merge = self._draw == 'merge' or (self._draw == 'auto' and cloud.n >= MERGE_DRAW_MIN_PARTICLES)
         off_u = self._philox_offset
         self._philox_offset += (n_particles + 2) // 2 if merge else (n_particles + 1) // 2
         off_n = self._philox_offset

@@ -76,6 +76,7 @@ class SMCUpdater(object):
         fuse_cap = 1 if self._desc.kind == 3 else QB_MAX_FUSE
         self._fuse = fuse_cap if fuse is None else max(1, min(int(fuse), fuse_cap))
         self._settling = False
+        self._counted = None        # models of the chain that keep a call count
         self._queue = []            # buffered, not yet launched: (ep_record, outcome, check_for_resample)
         self._pending = None        # launched, not yet settled: (tag, [steps])
         self.reset(n_particles)
@@ -251,11 +252,16 @@ class SMCUpdater(object):
 
     # ---- updates (smc.py:324-487) --------------------------------------------------------
     def _count_calls(self, n):
-        m = self.model
-        while m is not None:
-            if hasattr(m, '_call_count'):
-                m._call_count += n
-            m = getattr(m, 'underlying_model', None)
+        chain = self._counted
+        if chain is None:
+            chain, m = [], self.model
+            while m is not None:
+                if hasattr(m, '_call_count'):
+                    chain.append(m)
+                m = getattr(m, 'underlying_model', None)
+            self._counted = chain
+        for m in chain:
+            m._call_count += n
 
     def hypothetical_update(self, outcomes, expparams, return_likelihood=False, return_normalization=False):
         """smc.py:324-386: posterior weights of hypothetical data, shape (n_outcomes, n_expparams, n_particles),
