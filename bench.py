@@ -218,7 +218,7 @@ def workload_config(n_per_gpu, world):
                         "LiuWest a=0.98, resample_thresh 0.5" % (n_per_gpu, world),
             "particles_per_gpu": n_per_gpu, "n_modelparams": 1,
             "l2_policy": "inputs larger than L2: each update streams 240 MB (x, w in, w out) through a 126 MB L2",
-            "resampler": "rng=philox (device), scan=fast", "updater": "lazy=True (speculative launch pipelining)"}
+            "resampler": "rng=philox (device), scan=fast, draw=auto (guided below 3.2e7 particles, merge above)", "updater": "lazy=True (speculative launch pipelining)"}
 
 
 # ---------------------------------------------------------------------------
