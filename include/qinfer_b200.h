@@ -66,6 +66,8 @@ typedef struct qb_model {
     int32_t binomial;     /* 1: wrapped in BinomialModel (derived_models.py:222-360) */
     int32_t interleaved;  /* RB only: `_il` (rb.py:114-115) */
     double min_freq;      /* precession only: `_min_freq` (test_models.py:78-80,109-110) */
+    double likelihood_power; /* MLEModel (derived_models.py:681-703): every likelihood is raised to this power
+                                after the (binomial) model evaluated it; 0 or 1 = plain model */
 } qb_model;
 
 /* One experiment record (one element of the `expparams` array handed to

@@ -281,6 +281,36 @@ class RandomizedBenchmarkingModel(_ModelBase):
         return two_outcome_likelihood(outcomes, rb_pr0(modelparams, expparams['m'], self._il, ref))
 
 
+class MLEModel(_ModelBase):
+    """derived_models.py:681-703 — every likelihood of the underlying model raised to ``likelihood_power``."""
+
+    def __init__(self, underlying_model, likelihood_power):
+        super(MLEModel, self).__init__()
+        self._underlying_model = underlying_model
+        self._pow = likelihood_power
+
+    underlying_model = property(lambda self: self._underlying_model)
+    n_modelparams = property(lambda self: self._underlying_model.n_modelparams)
+    expparams_dtype = property(lambda self: self._underlying_model.expparams_dtype)
+    is_n_outcomes_constant = property(lambda self: self._underlying_model.is_n_outcomes_constant)
+
+    def n_outcomes(self, expparams):
+        return self._underlying_model.n_outcomes(expparams)
+
+    def are_models_valid(self, modelparams):
+        return self._underlying_model.are_models_valid(modelparams)
+
+    def canonicalize(self, modelparams):
+        return self._underlying_model.canonicalize(modelparams)
+
+    def update_timestep(self, modelparams, expparams):
+        return self._underlying_model.update_timestep(modelparams, expparams)
+
+    def likelihood(self, outcomes, modelparams, expparams):
+        L = self._underlying_model.likelihood(outcomes, modelparams, expparams)      # derived_models.py:701-703
+        return L ** self._pow
+
+
 class BinomialModel(_ModelBase):
     """derived_models.py:222-360 — n_meas iid shots of a two-outcome model."""
 

@@ -25,6 +25,7 @@ struct ExpView {
 struct ModelView {
     int32_t kind, d, binomial, interleaved;
     double min_freq;
+    double like_pow;   // MLEModel: L ** like_pow (1 = plain)
 };
 
 __host__ inline ExpView make_exp_view(const qb_model& m, const qb_expparams& ep, int64_t outcome) {
@@ -52,6 +53,7 @@ __host__ inline ModelView make_model_view(const qb_model& m) {
     v.binomial = m.binomial;
     v.interleaved = m.interleaved;
     v.min_freq = m.min_freq;
+    v.like_pow = (m.likelihood_power == 0.0) ? 1.0 : m.likelihood_power;
     return v;
 }
 
@@ -135,8 +137,8 @@ __device__ __forceinline__ void model_pr01(const ModelView& mv, const ExpView& e
 }
 
 template <int KIND, bool BINOM, typename Row, typename Meas>
-__device__ __forceinline__ double model_likelihood(const ModelView& mv, const ExpView& ev, Row row, Meas meas,
-                                                   int rot) {
+__device__ __forceinline__ double model_likelihood_plain(const ModelView& mv, const ExpView& ev, Row row, Meas meas,
+                                                         int rot) {
     if (KIND == QB_MODEL_PRECESSION && !BINOM) {
         // two-outcome precession: one select between sin^2(r) and 1 - sin^2(r)
         const double dw = row(0) - ev.w_;
@@ -152,6 +154,18 @@ __device__ __forceinline__ double model_likelihood(const ModelView& mv, const Ex
     // amplifies the last bit of a small pr1, so the binomial path keeps the reference's rounding sequence
     if (BINOM) return binom_pmf(ev, 1.0 - pr0);
     return ev.outcome0 ? pr0 : pr1;
+}
+
+// The likelihood the updater sees: the (binomial) model's, raised to MLEModel's power when one is set
+// (derived_models.py:701-703: `L ** self._pow`, one pow() per element like NumPy's).  pow() stays out of line so
+// that the plain models' inner loops keep their registers and instruction footprint.
+static __device__ __noinline__ double likelihood_pow(double L, double g) { return pow(L, g); }
+
+template <int KIND, bool BINOM, typename Row, typename Meas>
+__device__ __forceinline__ double model_likelihood(const ModelView& mv, const ExpView& ev, Row row, Meas meas,
+                                                   int rot) {
+    const double L = model_likelihood_plain<KIND, BINOM>(mv, ev, row, meas, rot);
+    return (mv.like_pow == 1.0) ? L : likelihood_pow(L, mv.like_pow);
 }
 
 // Model.are_models_valid for one particle.

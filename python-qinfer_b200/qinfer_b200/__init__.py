@@ -3,7 +3,7 @@ SMCUpdater / Model / Resampler plugin surface (hot path only)."""
 from ._exceptions import ApproximationWarning, ResamplerError, ResamplerWarning, UnsupportedModelError
 from .distributions import (GinibreTomographyPrior, ParticleDistribution, PostselectedDistribution,
                             UniformDistribution)
-from .models import (BinomialModel, CoinModel, IntegerDomain, Model, RandomizedBenchmarkingModel, SimpleInversionModel,
+from .models import (BinomialModel, CoinModel, IntegerDomain, MLEModel, Model, RandomizedBenchmarkingModel, SimpleInversionModel,
                      SimplePrecessionModel, TomographyBasis, TomographyModel, describe_model, gell_mann_basis,
                      pauli_basis)
 from .resamplers import LiuWestResampler, Resampler, sqrtm_psd
@@ -13,7 +13,7 @@ from .simple_est import simple_est_prec, simple_est_rb
 __all__ = [
     'ApproximationWarning', 'ResamplerError', 'ResamplerWarning', 'UnsupportedModelError',
     'GinibreTomographyPrior', 'ParticleDistribution', 'PostselectedDistribution', 'UniformDistribution',
-    'BinomialModel', 'CoinModel', 'IntegerDomain', 'Model', 'RandomizedBenchmarkingModel', 'SimpleInversionModel', 'SimplePrecessionModel',
+    'BinomialModel', 'CoinModel', 'IntegerDomain', 'MLEModel', 'Model', 'RandomizedBenchmarkingModel', 'SimpleInversionModel', 'SimplePrecessionModel',
     'TomographyBasis', 'TomographyModel', 'describe_model', 'gell_mann_basis', 'pauli_basis',
     'LiuWestResampler', 'Resampler', 'sqrtm_psd', 'SMCUpdater', 'simple_est_prec', 'simple_est_rb',
 ]

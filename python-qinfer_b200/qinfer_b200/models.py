@@ -25,7 +25,8 @@ class ModelDescriptor(object):
     """What the kernels need to know about a model instance."""
 
     def __init__(self, kind, d, binomial=False, interleaved=False, min_freq=0.0,
-                 scalar_expparam=False, binomial_scalar=False, dim=0, basis=None, allow_subnormalized=False):
+                 scalar_expparam=False, binomial_scalar=False, dim=0, basis=None, allow_subnormalized=False,
+                 likelihood_power=1.0):
         self.kind = kind
         self.d = int(d)
         self.binomial = bool(binomial)
@@ -36,8 +37,10 @@ class ModelDescriptor(object):
         self.dim = int(dim)
         self.basis = basis
         self.allow_subnormalized = bool(allow_subnormalized)
+        self.likelihood_power = float(likelihood_power)
         self.c_model = _lib.QbModel(kind=kind, d=self.d, binomial=int(self.binomial),
-                                    interleaved=int(self.interleaved), min_freq=self.min_freq)
+                                    interleaved=int(self.interleaved), min_freq=self.min_freq,
+                                    likelihood_power=self.likelihood_power)
 
     @property
     def needs_canonicalize(self):
@@ -102,6 +105,10 @@ def describe_model(model):
     binomial = False
     binomial_scalar = False
     inner = model
+    power = 1.0
+    if _name(model) == 'MLEModel':            # derived_models.py:681-703: L ** likelihood_power, outermost decorator
+        power = float(getattr(model, '_pow'))
+        model = inner = model.underlying_model
     if _name(model) == 'BinomialModel':
         binomial = True
         binomial_scalar = bool(getattr(model, '_expparams_scalar'))
@@ -111,13 +118,13 @@ def describe_model(model):
         return ModelDescriptor(_lib.QB_MODEL_PRECESSION, 1, binomial=binomial,
                                min_freq=getattr(inner, '_min_freq', 0.0),
                                scalar_expparam=(name == 'SimplePrecessionModel'),
-                               binomial_scalar=binomial_scalar)
+                               binomial_scalar=binomial_scalar, likelihood_power=power)
     if name == 'RandomizedBenchmarkingModel':
         il = bool(getattr(inner, '_il', False))
         return ModelDescriptor(_lib.QB_MODEL_RB, 4 if il else 3, binomial=binomial, interleaved=il,
-                               binomial_scalar=binomial_scalar)
+                               binomial_scalar=binomial_scalar, likelihood_power=power)
     if name == 'CoinModel':
-        return ModelDescriptor(_lib.QB_MODEL_COIN, 1, binomial=binomial, binomial_scalar=binomial_scalar)
+        return ModelDescriptor(_lib.QB_MODEL_COIN, 1, binomial=binomial, binomial_scalar=binomial_scalar, likelihood_power=power)
     if name == 'TomographyModel':
         dim = int(getattr(inner, '_dim'))
         basis = np.ascontiguousarray(np.asarray(inner._basis.data, dtype=complex))
@@ -125,7 +132,7 @@ def describe_model(model):
             raise UnsupportedModelError("TomographyModel with dim=%d exceeds QB_MAX_D" % dim)
         return ModelDescriptor(_lib.QB_MODEL_TOMOGRAPHY, dim ** 2, binomial=binomial, dim=dim, basis=basis,
                                allow_subnormalized=getattr(inner, '_allow_subnormalied', False),
-                               binomial_scalar=binomial_scalar)
+                               binomial_scalar=binomial_scalar, likelihood_power=power)
     raise UnsupportedModelError(
         "%s is not one of the model families the B200 kernels implement (SimplePrecessionModel, "
         "SimpleInversionModel, RandomizedBenchmarkingModel, CoinModel, tomography.TomographyModel, optionally wrapped in "
@@ -265,6 +272,46 @@ class RandomizedBenchmarkingModel(Model):
     @property
     def expparams_dtype(self):
         return [('m', 'uint')] + ([('reference', bool)] if self._il else [])
+
+
+class MLEModel(Model):
+    """derived_models.py:681-703: amplifies the Bayes update by raising every likelihood of the underlying model to
+    ``likelihood_power`` (the fictional posterior of [JDD08] whose mean approximates the MLE)."""
+
+    def __init__(self, underlying_model, likelihood_power):
+        super(MLEModel, self).__init__()
+        self._underlying_model = underlying_model
+        self._pow = likelihood_power
+
+    underlying_model = property(lambda self: self._underlying_model)
+    decorated_model = property(lambda self: self._underlying_model)
+    base_model = property(lambda self: getattr(self._underlying_model, 'base_model', self._underlying_model))
+    n_modelparams = property(lambda self: self._underlying_model.n_modelparams)
+    modelparam_names = property(lambda self: self._underlying_model.modelparam_names)
+    expparams_dtype = property(lambda self: self._underlying_model.expparams_dtype)
+    is_n_outcomes_constant = property(lambda self: self._underlying_model.is_n_outcomes_constant)
+    Q = property(lambda self: self._underlying_model.Q)
+
+    def n_outcomes(self, expparams):
+        return self._underlying_model.n_outcomes(expparams)
+
+    def domain(self, expparams):
+        return self._underlying_model.domain(expparams)
+
+    def are_models_valid(self, modelparams):
+        return self._underlying_model.are_models_valid(modelparams)
+
+    def canonicalize(self, modelparams):
+        return self._underlying_model.canonicalize(modelparams)
+
+    def clear_cache(self):
+        self._underlying_model.clear_cache()
+
+    def update_timestep(self, modelparams, expparams):
+        return self._underlying_model.update_timestep(modelparams, expparams)
+
+    def simulate_experiment(self, modelparams, expparams, repeat=1):
+        return self._underlying_model.simulate_experiment(modelparams, expparams, repeat)
 
 
 class BinomialModel(Model):

@@ -22,7 +22,7 @@ def oracle_namespace():
         ParticleDistribution=o.ParticleDistribution,
         SimplePrecessionModel=o.SimplePrecessionModel, SimpleInversionModel=o.SimpleInversionModel,
         RandomizedBenchmarkingModel=o.RandomizedBenchmarkingModel, BinomialModel=o.BinomialModel,
-        CoinModel=o.CoinModel, TomographyModel=o.TomographyModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
+        CoinModel=o.CoinModel, MLEModel=o.MLEModel, TomographyModel=o.TomographyModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
         UniformDistribution=o.UniformDistribution, PostselectedDistribution=o.PostselectedDistribution,
         sqrtm_psd=o.sqrtm_psd)
 
@@ -38,7 +38,7 @@ def reference_namespace():
         ParticleDistribution=q.ParticleDistribution,
         SimplePrecessionModel=q.SimplePrecessionModel, SimpleInversionModel=q.SimpleInversionModel,
         RandomizedBenchmarkingModel=q.RandomizedBenchmarkingModel, BinomialModel=q.BinomialModel,
-        CoinModel=q.CoinModel, TomographyModel=qt.TomographyModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
+        CoinModel=q.CoinModel, MLEModel=q.MLEModel, TomographyModel=qt.TomographyModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
         UniformDistribution=q.UniformDistribution, PostselectedDistribution=q.PostselectedDistribution,
         sqrtm_psd=qu.sqrtm_psd)
 
@@ -397,4 +397,36 @@ def design_vectors(ns, seed=21):
         out['tomo_meas'] = meas
         out['tomo_risk'] = np.asarray(up.bayes_risk(ept), dtype=float)
         out['tomo_ig'] = np.asarray(up.expected_information_gain(ept), dtype=float)
+    return out
+
+
+def mle_vectors(ns, seed=41):
+    """f4 vectors: MLEModel (derived_models.py:681-703) — likelihoods raised to a power, alone and over BinomialModel,
+    and a short update trajectory without resampling."""
+    import warnings
+    rs = np.random.RandomState(seed)
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x = np.concatenate([rs.random_sample(197), [0.0, 1.0, 0.5]])[:, None]
+        ts = np.array([0.0, 1.0, 7.3, (9 / 8.) ** 40])
+        m = ns.MLEModel(ns.SimplePrecessionModel(), 3.5)
+        out['prec_x'], out['prec_t'] = x, ts
+        out['prec_L'] = m.likelihood(np.array([0, 1]), x, ts)
+        xr = rs.random_sample((200, 3)) * np.array([0.3, 0.5, 0.5]) + np.array([0.7, 0.0, 0.0])
+        bm = ns.MLEModel(ns.BinomialModel(ns.RandomizedBenchmarkingModel()), 0.5)
+        epb = np.empty((2,), dtype=bm.expparams_dtype)
+        epb['m'] = [3, 120]
+        epb['n_meas'] = [20, 20]
+        out['binrb_x'] = xr
+        out['binrb_L'] = bm.likelihood(np.array([0, 7, 20]), xr, epb)
+        n = 1500
+        prior = rs.random_sample((n, 1))
+        up = ns.SMCUpdater(ns.MLEModel(ns.SimplePrecessionModel(), 2.0), n, FixedPrior(prior), resample_thresh=0.0)
+        for t, o in zip([0.7, 1.9, 3.3, 6.1, 9.9, 14.2], [0, 1, 0, 0, 1, 0]):
+            up.update(o, np.array([t]))
+        out['traj_prior'] = prior
+        out['traj_w'] = np.array(up.particle_weights)
+        out['traj_norm'] = np.array([float(np.ravel(v)[0]) for v in up.normalization_record])
+        out['traj_mean'] = np.asarray(up.est_mean(), dtype=float)
     return out

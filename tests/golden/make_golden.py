@@ -55,6 +55,7 @@ def build(ns):
         files['canonicalize_vectors'] = cases.canonicalize_vectors(ns)
         files['moment_vectors'] = cases.moment_vectors(ns)
         files['design_vectors'] = cases.design_vectors(ns)
+        files['mle_vectors'] = cases.mle_vectors(ns)
     return files
 
 

@@ -48,7 +48,8 @@ def gpu_namespace(qb, **lw_kwargs):
         name="b200", SMCUpdater=qb.SMCUpdater, LiuWestResampler=qb.LiuWestResampler,
         ParticleDistribution=qb.ParticleDistribution, SimplePrecessionModel=qb.SimplePrecessionModel,
         SimpleInversionModel=qb.SimpleInversionModel, RandomizedBenchmarkingModel=qb.RandomizedBenchmarkingModel,
-        BinomialModel=qb.BinomialModel, CoinModel=qb.CoinModel, TomographyModel=qb.TomographyModel,
+        BinomialModel=qb.BinomialModel, CoinModel=qb.CoinModel, MLEModel=qb.MLEModel,
+        TomographyModel=qb.TomographyModel,
         pauli_basis=qb.pauli_basis,
         gell_mann_basis=qb.gell_mann_basis, UniformDistribution=qb.UniformDistribution,
         PostselectedDistribution=qb.PostselectedDistribution, sqrtm_psd=qb.sqrtm_psd)
@@ -884,3 +885,23 @@ def test_merge_mode_resample_through_the_plugin(qb, kind, n):
     assert np.all(np.abs(m1 - m0) < 6 * sig / np.sqrt(ess0) + 0.02 * sig)     # postselection shifts the mean a little
     assert np.all(np.abs(np.diag(c1) / np.diag(c0) - 1) < 0.15)
     assert np.all(up.particle_weights == 1.0 / n)
+
+
+
+# ---------------------------------------------------------------------------
+# f4 — MLEModel: the likelihood raised to a power inside every kernel that evaluates it
+# ---------------------------------------------------------------------------
+def test_mle_model_against_the_reference(qb, golden):
+    """derived_models.py:681-703 through qb_likelihood and the fused update (golden vectors of the reference).
+    pow() is within an ulp of glibc's; 1e-12 relative with the absolute floors of T1."""
+    g = golden("mle_vectors")
+    got = cases.mle_vectors(gpu_namespace(qb))
+    np.testing.assert_allclose(got["prec_L"], g["prec_L"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(got["binrb_L"], g["binrb_L"], rtol=5e-12, atol=1e-300)
+    np.testing.assert_allclose(got["traj_norm"], g["traj_norm"], rtol=1e-12)
+    np.testing.assert_allclose(got["traj_w"], g["traj_w"], rtol=1e-11, atol=1e-15 * g["traj_w"].max())
+    np.testing.assert_allclose(got["traj_mean"], g["traj_mean"], rtol=1e-12)
+    report("f4_mle_traj_w_rel", relerr(got["traj_w"], g["traj_w"], floor=1e-15 * g["traj_w"].max()))
+    # the power is part of the model descriptor: plain models are untouched
+    assert qb.describe_model(qb.MLEModel(qb.SimplePrecessionModel(), 2.0)).likelihood_power == 2.0
+    assert qb.describe_model(qb.SimplePrecessionModel()).likelihood_power == 1.0

@@ -19,6 +19,9 @@ def test_describe_builtin_models():
     d = qb.describe_model(qb.TomographyModel(qb.pauli_basis(2)))
     assert (d.kind, d.d, d.dim) == (_lib.QB_MODEL_TOMOGRAPHY, 16, 4)
     assert d.basis.shape == (16, 4, 4)
+    d = qb.describe_model(qb.MLEModel(qb.BinomialModel(qb.RandomizedBenchmarkingModel()), 2.5))
+    assert (d.kind, d.binomial, d.likelihood_power, d.c_model.likelihood_power) == (_lib.QB_MODEL_RB, True, 2.5, 2.5)
+    assert qb.describe_model(qb.SimplePrecessionModel()).c_model.likelihood_power == 1.0
 
 
 def test_recognition_works_on_foreign_objects_with_the_reference_layout():

@@ -114,6 +114,11 @@ def test_design_vectors_bit_exact(ns, golden):
     _assert_same(cases.design_vectors(ns), g)
 
 
+def test_mle_vectors_bit_exact(ns, golden):
+    """MLEModel (derived_models.py:681-703) restated in the oracle."""
+    _assert_same(cases.mle_vectors(ns), golden("mle_vectors"))
+
+
 def test_design_known_answers_from_the_reference_tests():
     """tests/test_metrics.py:65-79, 110-120 on the oracle: closed-form Beta-binomial risk (3 decimals) and the
     Mathematica BINOM_IG vector (2 decimals)."""
