@@ -175,7 +175,7 @@ int qb_fused_update(const qb_model* model, const qb_expparams* ep, int64_t outco
  * particle.  eps / outcomes: HOST arrays of K records; bit j of resample_mask: step j is followed by an n_ess
  * check.  Per-step sums are published (mirror, and d_step_stats = K x 8 doubles if not NULL) so the host can
  * replay each step's record / n_ess / policy; if step j < K needs the host, re-issue the first j steps from
- * the untouched input buffers.  Tomography models take K = 1 only. */
+ * the untouched input buffers.  Tomography models and models with a likelihood power take K = 1 only. */
 int qb_fused_update_multi(const qb_model* model, const qb_expparams* eps, const int64_t* outcomes,
                           int32_t nsteps, uint32_t resample_mask,
                           const double* d_x, int64_t n, const double* d_w_in, double* d_w_out,

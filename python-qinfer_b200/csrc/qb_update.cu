@@ -240,6 +240,16 @@ __device__ void peer_allreduce(const UpdateParams& p, double* sums, double* scra
     __syncthreads();
 }
 
+// MLEModel's power is applied by the one-update kernels only (fused launches keep the plain likelihood and their
+// register budget; the host does not fuse updates of a model with a power, like tomography).
+template <int KIND, bool BINOM, int KF, typename Row, typename Meas>
+__device__ __forceinline__ double update_likelihood(const ModelView& mv, const ExpView& ev, Row row, Meas meas, int rot) {
+    if constexpr (KF == 1)
+        return model_likelihood<KIND, BINOM>(mv, ev, row, meas, rot);
+    else
+        return model_likelihood_plain<KIND, BINOM>(mv, ev, row, meas, rot);
+}
+
 // DT > 0: compile-time n_modelparams, pair processing.  DT == 0: runtime d.  KF: 1 or KF_MAX fused updates.
 //
 // Warp-specialised: warps 0..UPD_CONSUMER_WARPS-1 compute, the last warp's lane 0 is the TMA producer.
@@ -488,8 +498,8 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
 #pragma unroll
                         for (int k = 0; k < KF; ++k) {
                             if (KF == 1 || k < nsteps) {
-                                w0 = w0 * model_likelihood<KIND, BINOM>(mv, p.ev[k], row0, meas, 0);  // smc.py:354
-                                w1 = w1 * model_likelihood<KIND, BINOM>(mv, p.ev[k], row1, meas, 0);
+                                w0 = w0 * update_likelihood<KIND, BINOM, KF>(mv, p.ev[k], row0, meas, 0);  // smc.py:354
+                                w1 = w1 * update_likelihood<KIND, BINOM, KF>(mv, p.ev[k], row1, meas, 0);
                                 accumulate(acc[k], bad, k, w0);
                                 accumulate(acc[k], bad, k, w1);
                             }
@@ -507,7 +517,7 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
 #pragma unroll
                         for (int k = 0; k < KF; ++k) {
                             if (KF == 1 || k < nsteps) {
-                                wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, lane);
+                                wv = wv * update_likelihood<KIND, BINOM, KF>(mv, p.ev[k], row, meas, lane);
                                 accumulate(acc[k], bad, k, wv);
                             }
                         }
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
 #pragma unroll
                 for (int k = 0; k < KF; ++k) {
                     if (KF == 1 || k < nsteps) {
-                        wv = wv * model_likelihood<KIND, BINOM>(mv, p.ev[k], row, meas, 0);
+                        wv = wv * update_likelihood<KIND, BINOM, KF>(mv, p.ev[k], row, meas, 0);
                         accumulate(acc[k], bad, k, wv);
                     }
                 }
@@ -728,6 +738,8 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
                "qb_fused_update: 1..%d updates per launch, got %d", QB_MAX_FUSE, nsteps);
     QB_REQUIRE(nsteps == 1 || model->kind != QB_MODEL_TOMOGRAPHY, QB_ERR_INVALID_ARGUMENT,
                "qb_fused_update: tomography updates are not fused (one measurement vector per launch)");
+    QB_REQUIRE(nsteps == 1 || model->likelihood_power == 0.0 || model->likelihood_power == 1.0, QB_ERR_INVALID_ARGUMENT,
+               "qb_fused_update: updates of a model with a likelihood power (MLEModel) are not fused");
     QB_REQUIRE(ws_bytes >= qb_update_workspace_bytes(n, model->d), QB_ERR_WORKSPACE,
                "qb_fused_update: workspace too small");
     QB_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w_in) & 15) == 0 &&

@@ -73,7 +73,7 @@ class SMCUpdater(object):
         # With lazy=True consecutive updates are additionally FUSED: up to ``fuse`` (default QB_MAX_FUSE = 8, 1 for
         # tomography) buffered updates go out as one kernel launch that reads and writes the cloud once.
         self._lazy = bool(lazy)
-        fuse_cap = 1 if self._desc.kind == 3 else QB_MAX_FUSE
+        fuse_cap = 1 if (self._desc.kind == 3 or self._desc.likelihood_power != 1.0) else QB_MAX_FUSE
         self._fuse = fuse_cap if fuse is None else max(1, min(int(fuse), fuse_cap))
         self._settling = False
         self._counted = None        # models of the chain that keep a call count
