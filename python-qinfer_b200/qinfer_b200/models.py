@@ -136,7 +136,7 @@ def describe_model(model):
     raise UnsupportedModelError(
         "%s is not one of the model families the B200 kernels implement (SimplePrecessionModel, "
         "SimpleInversionModel, RandomizedBenchmarkingModel, CoinModel, tomography.TomographyModel, optionally wrapped in "
-        "BinomialModel). There is no CPU fallback." % name)
+        "BinomialModel and/or MLEModel). There is no CPU fallback." % name)
 
 
 # ---------------------------------------------------------------------------
