@@ -20,8 +20,6 @@ import numpy as np
 import torch
 
 from ._exceptions import ApproximationWarning, ResamplerWarning
-import ctypes
-
 from ._lib import QB_MAX_FUSE, QB_STAT_NORM, QB_STAT_SUMSQ, QbExpparams
 from .distributions import covariance_from_moments
 from .engine import DeviceCloud

@@ -138,3 +138,24 @@ class FakeCloud(object):
         st[NORM], st[SUMSQ], st[MIN], st[NBAD], st[INV_NORM] = np.sum(w), np.sum(w * w), np.min(w), 0.0, 1.0
         st[NESS] = 1.0 / st[SUMSQ]
         return st.copy()
+
+    # ---- experiment design (csrc/qb_design.cu restated) ------------------------------------------------
+    def design_sums(self, expparams, idx, outcomes, centre, want_kld):
+        ep = self.desc.expparams_record(expparams, idx)
+        wn = self.download_weights()
+        dx = self.x - np.asarray(centre)[None, :]
+        n_o = len(outcomes)
+        sums, kld = np.zeros((n_o, 1 + 2 * self.d)), np.zeros(n_o)
+        pr0 = np.cos(ep.t * (self.x[:, 0] - ep.w_) / 2) ** 2
+        for o, outcome in enumerate(outcomes):
+            h = wn * (pr0 if outcome == 0 else 1 - pr0)
+            sums[o, 0] = np.sum(h)
+            sums[o, 1:1 + self.d] = h @ dx
+            sums[o, 1 + self.d:] = h @ dx ** 2
+            if want_kld:
+                div = 1.0 if (o < n_o - 1 and abs(sums[o, 0]) < EPS) else sums[o, 0]
+                wh = h / div
+                pos = wh > 0
+                kld[o] = np.sum(wh[pos] * np.log(wh[pos] / wn[pos]))
+        self.launches += 2
+        return sums, (kld if want_kld else None)

@@ -130,3 +130,16 @@ def test_properties_settle_pending_work():
     assert len(got.normalization_record) == 5                             # reading a record flushes
     assert not got._queue and got._pending is None
     assert got.data_record == [int(o) for o in inp['outcomes'][:5]]
+
+
+def test_risk_and_information_gain_host_algebra():
+    """SMCUpdater.bayes_risk / expected_information_gain (smc.py:553-657): the host recombines the per-outcome
+    reductions (normalisation, first and second moment about the mean, KL sums) into the reference's numbers."""
+    inp, ref, got = _pair(700, 9, False, None, resample_thresh=0.0)
+    for k in range(6):
+        for u in (ref, got):
+            u.update(int(inp['outcomes'][k]), np.array([inp['ts'][k]]))
+    ts = np.array([0.4, 2.0, 9.0, 33.0])
+    np.testing.assert_allclose(got.bayes_risk(ts), ref.bayes_risk(ts), rtol=1e-10)
+    np.testing.assert_allclose(got.expected_information_gain(ts), ref.expected_information_gain(ts), rtol=1e-10)
+    assert got.risk(2.0).shape == (1,)
