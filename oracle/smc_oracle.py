@@ -311,6 +311,110 @@ class MLEModel(_ModelBase):
         return L ** self._pow
 
 
+class RandomWalkModel(_ModelBase):
+    """derived_models.py:705-741 — after every update each particle takes a step drawn from ``step_distribution``."""
+
+    def __init__(self, underlying_model, step_distribution):
+        super(RandomWalkModel, self).__init__()
+        self._underlying_model = underlying_model
+        self._step_dist = step_distribution
+        if underlying_model.n_modelparams != step_distribution.n_rvs:
+            raise TypeError("Step distribution does not match model dimension.")
+
+    underlying_model = property(lambda self: self._underlying_model)
+    n_modelparams = property(lambda self: self._underlying_model.n_modelparams)
+    expparams_dtype = property(lambda self: self._underlying_model.expparams_dtype)
+
+    def are_models_valid(self, modelparams):
+        return self._underlying_model.are_models_valid(modelparams)
+
+    def likelihood(self, outcomes, modelparams, expparams):
+        return self._underlying_model.likelihood(outcomes, modelparams, expparams)
+
+    def update_timestep(self, modelparams, expparams):
+        # derived_models.py:733-741: one step per (particle, experiment), independent of the experiment
+        steps = self._step_dist.sample(n=modelparams.shape[0] * expparams.shape[0])
+        steps = steps.reshape((modelparams.shape[0], expparams.shape[0], self.n_modelparams))
+        steps = steps.transpose((0, 2, 1))
+        return modelparams[:, :, np.newaxis] + steps
+
+
+class NormalStepDistribution(object):
+    """distributions.py MultivariateNormalDistribution restricted to what RandomWalkModel needs: zero-mean steps
+    ``np.random.multivariate_normal(mean, cov, n)`` (distributions.py:1016-1017)."""
+
+    def __init__(self, mean, cov):
+        self._mean, self._cov = np.asarray(mean, dtype=float), np.asarray(cov, dtype=float)
+        self.n_rvs = self._mean.shape[0]
+
+    def sample(self, n=1):
+        return np.random.multivariate_normal(self._mean, self._cov, n)
+
+
+class GaussianRandomWalkModel(_ModelBase):
+    """derived_models.py:743-963, diagonal covariance without a model transformation: every update adds zero-mean
+    Gaussian steps to the parameters ``random_walk_idxs``; the step scales are fixed (``fixed_covariance``, the
+    diagonal) or learned (one extra model parameter sigma per walking parameter, valid iff >= 0)."""
+
+    def __init__(self, underlying_model, random_walk_idxs='all', fixed_covariance=None, scale_mult=None):
+        super(GaussianRandomWalkModel, self).__init__()
+        self._underlying_model = underlying_model
+        n_u = underlying_model.n_modelparams
+        self._rw_idxs = np.s_[:n_u] if isinstance(random_walk_idxs, str) and random_walk_idxs == 'all' \
+            else random_walk_idxs
+        explicit = np.arange(n_u)[self._rw_idxs]
+        if explicit.size == 0:
+            raise IndexError('At least one model parameter must take a random walk.')
+        self._n_rw = len(explicit)
+        if fixed_covariance is None:                                   # derived_models.py:811-818
+            self._has_fixed_covariance = False
+            self._srw_idxs = (n_u + np.arange(self._n_rw)).astype(int)
+            self._n_mps = n_u + self._n_rw
+        else:                                                          # derived_models.py:834-842
+            self._has_fixed_covariance = True
+            fixed_covariance = np.asarray(fixed_covariance, dtype=float)
+            if fixed_covariance.ndim != 1 or fixed_covariance.size != self._n_rw:
+                raise ValueError('fixed_covariance must be the diagonal, one entry per walking parameter')
+            self._fixed_scale = np.sqrt(fixed_covariance)
+            self._n_mps = n_u
+        if scale_mult is None:                                         # derived_models.py:859-864
+            self._scale_mult_fcn = (lambda expparams: 1)
+        elif isinstance(scale_mult, str):
+            self._scale_mult_fcn = lambda x: x[scale_mult]
+        else:
+            self._scale_mult_fcn = scale_mult
+
+    underlying_model = property(lambda self: self._underlying_model)
+    n_modelparams = property(lambda self: self._n_mps)
+    expparams_dtype = property(lambda self: self._underlying_model.expparams_dtype)
+    is_n_outcomes_constant = False
+
+    def are_models_valid(self, modelparams):
+        # derived_models.py:883-892
+        n_u = self._underlying_model.n_modelparams
+        ud_valid = self._underlying_model.are_models_valid(modelparams[..., :n_u])
+        if self._has_fixed_covariance:
+            return ud_valid
+        pos_std = np.greater_equal(modelparams[..., self._srw_idxs], 0).all(axis=-1)
+        return np.logical_and(ud_valid, pos_std)
+
+    def likelihood(self, outcomes, modelparams, expparams):
+        # derived_models.py:894-896
+        return self._underlying_model.likelihood(
+            outcomes, modelparams[..., :self._underlying_model.n_modelparams], expparams)
+
+    def update_timestep(self, modelparams, expparams):
+        # derived_models.py:921-963 (diagonal branch, no transformation)
+        n_mps, n_eps = modelparams.shape[0], expparams.shape[0]
+        scale = self._fixed_scale if self._has_fixed_covariance else modelparams[:, self._srw_idxs]
+        steps = scale * np.random.normal(size=(n_eps, n_mps, self._n_rw))
+        steps = steps.transpose((1, 2, 0))
+        steps = self._scale_mult_fcn(expparams) * steps
+        new_mps = np.repeat(modelparams[:, :, np.newaxis], n_eps, axis=2)
+        new_mps[:, self._rw_idxs, :] += steps
+        return new_mps
+
+
 class BinomialModel(_ModelBase):
     """derived_models.py:222-360 — n_meas iid shots of a two-outcome model."""
 

@@ -22,7 +22,9 @@ def oracle_namespace():
         ParticleDistribution=o.ParticleDistribution,
         SimplePrecessionModel=o.SimplePrecessionModel, SimpleInversionModel=o.SimpleInversionModel,
         RandomizedBenchmarkingModel=o.RandomizedBenchmarkingModel, BinomialModel=o.BinomialModel,
-        CoinModel=o.CoinModel, MLEModel=o.MLEModel, TomographyModel=o.TomographyModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
+        CoinModel=o.CoinModel, MLEModel=o.MLEModel, TomographyModel=o.TomographyModel,
+        RandomWalkModel=o.RandomWalkModel, GaussianRandomWalkModel=o.GaussianRandomWalkModel,
+        NormalStepDistribution=o.NormalStepDistribution, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
         UniformDistribution=o.UniformDistribution, PostselectedDistribution=o.PostselectedDistribution,
         sqrtm_psd=o.sqrtm_psd)
 
@@ -38,7 +40,9 @@ def reference_namespace():
         ParticleDistribution=q.ParticleDistribution,
         SimplePrecessionModel=q.SimplePrecessionModel, SimpleInversionModel=q.SimpleInversionModel,
         RandomizedBenchmarkingModel=q.RandomizedBenchmarkingModel, BinomialModel=q.BinomialModel,
-        CoinModel=q.CoinModel, MLEModel=q.MLEModel, TomographyModel=qt.TomographyModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
+        CoinModel=q.CoinModel, MLEModel=q.MLEModel, TomographyModel=qt.TomographyModel,
+        RandomWalkModel=q.RandomWalkModel, GaussianRandomWalkModel=q.GaussianRandomWalkModel,
+        NormalStepDistribution=q.MultivariateNormalDistribution, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
         UniformDistribution=q.UniformDistribution, PostselectedDistribution=q.PostselectedDistribution,
         sqrtm_psd=qu.sqrtm_psd)
 
@@ -429,4 +433,41 @@ def mle_vectors(ns, seed=41):
         out['traj_w'] = np.array(up.particle_weights)
         out['traj_norm'] = np.array([float(np.ravel(v)[0]) for v in up.normalization_record])
         out['traj_mean'] = np.asarray(up.est_mean(), dtype=float)
+    return out
+
+
+def random_walk_vectors(ns, seed=53):
+    """f4 groundwork: the time-dependent decorators (derived_models.py:705-963).  Their update_timestep draws from the
+    global NumPy stream, so each trajectory runs under a fixed legacy seed; resampling included."""
+    import warnings
+    rs = np.random.RandomState(seed)
+    out = {}
+    n = 1200
+    prior = rs.random_sample((n, 1))
+    ts = exp_sparse_times(30)
+    outcomes = (rs.random_sample(30) >= np.cos(ts * 0.45 / 2) ** 2).astype(int)
+    out['prior'], out['ts'], out['outcomes'] = prior, ts, outcomes
+
+    def run(model, prior_arr):
+        np.random.seed(7)
+        up = ns.SMCUpdater(model, prior_arr.shape[0], FixedPrior(prior_arr))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for t, o in zip(ts, outcomes):
+                up.update(int(o), np.array([t]))
+        return (np.array(up.particle_locations), np.array(up.particle_weights),
+                np.array([float(np.ravel(v)[0]) for v in up.normalization_record]), np.int64(up.resample_count))
+
+    # (1) RandomWalkModel with a fixed normal step distribution
+    m = ns.RandomWalkModel(ns.SimplePrecessionModel(), ns.NormalStepDistribution(np.zeros(1), np.array([[1e-6]])))
+    out['rw_x'], out['rw_w'], out['rw_norm'], out['rw_rc'] = run(m, prior)
+    # (2) GaussianRandomWalkModel, fixed diagonal covariance
+    m = ns.GaussianRandomWalkModel(ns.SimplePrecessionModel(), fixed_covariance=np.array([4e-6]))
+    out['grw_fixed_x'], out['grw_fixed_w'], out['grw_fixed_norm'], out['grw_fixed_rc'] = run(m, prior)
+    # (3) GaussianRandomWalkModel, learned step scale: one extra model parameter sigma >= 0
+    prior2 = np.column_stack([prior[:, 0], 2e-3 * rs.random_sample(n)])
+    out['prior2'] = prior2
+    m = ns.GaussianRandomWalkModel(ns.SimplePrecessionModel())
+    out['grw_learn_x'], out['grw_learn_w'], out['grw_learn_norm'], out['grw_learn_rc'] = run(m, prior2)
+    out['grw_learn_valid'] = m.are_models_valid(np.array([[0.5, 0.0], [0.5, -1e-9], [-0.1, 1e-3]]))
     return out

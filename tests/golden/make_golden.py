@@ -56,6 +56,7 @@ def build(ns):
         files['moment_vectors'] = cases.moment_vectors(ns)
         files['design_vectors'] = cases.design_vectors(ns)
         files['mle_vectors'] = cases.mle_vectors(ns)
+        files['random_walk_vectors'] = cases.random_walk_vectors(ns)
     return files
 
 

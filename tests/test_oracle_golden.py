@@ -119,6 +119,13 @@ def test_mle_vectors_bit_exact(ns, golden):
     _assert_same(cases.mle_vectors(ns), golden("mle_vectors"))
 
 
+def test_random_walk_vectors_bit_exact(ns, golden):
+    """RandomWalkModel / GaussianRandomWalkModel (derived_models.py:705-963, diagonal covariance) restated in the
+    oracle: whole trajectories incl. resampling under a fixed legacy seed.  (Pins the oracle for SURVEY §8 f4; the
+    device side of update_timestep is not built yet.)"""
+    _assert_same(cases.random_walk_vectors(ns), golden("random_walk_vectors"))
+
+
 def test_design_known_answers_from_the_reference_tests():
     """tests/test_metrics.py:65-79, 110-120 on the oracle: closed-form Beta-binomial risk (3 decimals) and the
     Mathematica BINOM_IG vector (2 decimals)."""
