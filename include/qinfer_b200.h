@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define QB_ABI_VERSION 1
+#define QB_ABI_VERSION 2 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes */
 
 #define QB_OK 0
 #define QB_ERR_INVALID_ARGUMENT (-1)

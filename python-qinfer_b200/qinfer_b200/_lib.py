@@ -6,6 +6,7 @@ fails this module raises, loudly.
 import ctypes
 import os
 
+QB_ABI_VERSION = 2
 QB_MAX_D = 64
 QB_MAX_RANKS = 16
 QB_IPC_HANDLE_BYTES = 64
@@ -140,8 +141,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError if the .so does not export what the header declares
         fn.restype = res
         fn.argtypes = args
-    if lib.qb_abi_version() != 1:
-        raise QbError("libqinfer_b200.so ABI version %d, expected 1" % lib.qb_abi_version())
+    if lib.qb_abi_version() != QB_ABI_VERSION:
+        raise QbError("libqinfer_b200.so ABI version %d, expected %d" % (lib.qb_abi_version(), QB_ABI_VERSION))
     sizes = (ctypes.c_int32 * 3)()
     lib.qb_struct_sizes(sizes)
     if list(sizes) != [ctypes.sizeof(QbModel), ctypes.sizeof(QbExpparams), ctypes.sizeof(QbUpdateCtl)]:
