@@ -193,7 +193,7 @@ class LiuWestResampler(Resampler):
         return n_iters, n_invalid
 
     def _fused_pass(self, cloud, mean, S, a, n_particles, dst=None, scale_u=False, own_mean=False, seed=None,
-                    build_cdf=True):
+                    build_cdf=True, auto_merge=True):
         """Device-RNG mode, d <= 4: the CDF pass also scatters the draw's guide table, and ONE kernel draws, gathers,
         shrinks, perturbs and tests validity (u, js, eps never touch HBM).  Consumes the Philox streams exactly like
         ``_staged_pass`` (uniforms, then normals per iteration), so both give bit-identical particles."""
@@ -204,7 +204,7 @@ class LiuWestResampler(Resampler):
             cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED if scale_u else _lib.QB_SCAN_FAST_GUIDE)
         # measured (B200, d = 1): guided 310 us vs merge 331 us at n = 1e7, 6.9 ms vs 3.1 ms at n = 1e8 (the guided
         # draw's random sectors run out of TLB reach / L2 there); 'auto' switches in between
-        merge = self._draw == 'merge' or (self._draw == 'auto' and cloud.n >= MERGE_DRAW_MIN_PARTICLES)
+        merge = self._draw == 'merge' or (self._draw == 'auto' and auto_merge and cloud.n >= MERGE_DRAW_MIN_PARTICLES)
         off_u = self._philox_offset
         self._philox_offset += (n_particles + 2) // 2 if merge else (n_particles + 1) // 2
         off_n = self._philox_offset

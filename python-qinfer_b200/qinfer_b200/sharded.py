@@ -586,8 +586,10 @@ def _make_sharded_updater_class():
                     return torch.empty((rows, cloud.d), dtype=torch.float64, device=cloud.device)
 
                 def draw_into(self, dst):
+                    # ('auto' stays with the guided draw here: the merge draw on a scaled slab CDF is selected
+                    # only when asked for explicitly)
                     it, bad = res._fused_pass(cloud, mean, S, a, dst.shape[0], dst=dst, scale_u=True, own_mean=True,
-                                              seed=updater._stream_seed, build_cdf=state['cdf'])
+                                              seed=updater._stream_seed, build_cdf=state['cdf'], auto_merge=False)
                     state['cdf'] = False
                     state['iters'] = max(state['iters'], it)
                     if bad:
