@@ -8,7 +8,8 @@ through it and has no CPU fallback.
 
 What this is: a NumPy restatement of the reference's algorithm
 (QInfer/python-qinfer @ 8170c84, paths relative to /root/reference/src/qinfer)
-for exactly the functions SURVEY.md §8(a) lists.  Every function cites the
+for exactly the functions SURVEY.md §8(a) lists, plus the "next" rows built so far (§8 f2: bayes_risk /
+expected_information_gain with CoinModel; f4: MLEModel, RandomWalkModel, GaussianRandomWalkModel).  Every function cites the
 reference lines it follows and performs the same floating-point operations in
 the same order on the same array shapes, so that under an identical legacy
 ``np.random`` seed it reproduces the reference bit for bit.
@@ -21,7 +22,8 @@ against those vectors bit-exactly (weights, resample indices, locations,
 moments) on every CPU test run.  The reference itself holds no golden vectors
 for this path; its behavioural tests (tests/test_smc.py:109-137,
 tests/test_precession_model.py:86-110, tests/test_distributions.py:652-706,
-tests/test_utils.py:132-152) are restated in ``tests/test_reference_behaviour.py``.
+tests/test_utils.py:132-152, tests/test_metrics.py:40-120) are restated in ``tests/test_gpu_updater.py``,
+``tests/test_host_logic.py`` and ``tests/test_oracle_golden.py``.
 
 Third-party arithmetic the reference delegates (not under /root/reference):
   * ``scipy.stats.binom(n, p).pmf(k)`` (utils.py:106-111), SciPy un-pinned by
