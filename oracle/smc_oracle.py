@@ -9,7 +9,7 @@ through it and has no CPU fallback.
 What this is: a NumPy restatement of the reference's algorithm
 (QInfer/python-qinfer @ 8170c84, paths relative to /root/reference/src/qinfer)
 for exactly the functions SURVEY.md §8(a) lists, plus the "next" rows built so far (§8 f2: bayes_risk /
-expected_information_gain with CoinModel; f4: MLEModel, RandomWalkModel, GaussianRandomWalkModel).  Every function cites the
+expected_information_gain with CoinModel; f4: MLEModel, PoisonedModel, RandomWalkModel, GaussianRandomWalkModel).  Every function cites the
 reference lines it follows and performs the same floating-point operations in
 the same order on the same array shapes, so that under an identical legacy
 ``np.random`` seed it reproduces the reference bit for bit.
@@ -311,6 +311,45 @@ class MLEModel(_ModelBase):
     def likelihood(self, outcomes, modelparams, expparams):
         L = self._underlying_model.likelihood(outcomes, modelparams, expparams)      # derived_models.py:701-703
         return L ** self._pow
+
+
+def binom_est_error(p, N, hedge=float(0)):
+    # utils.py:683-688
+    return np.sqrt(p * (1 - p) / (N + 2 * hedge + 1))
+
+
+class PoisonedModel(_ModelBase):
+    """derived_models.py:148-220 — the underlying likelihood plus clipped Gaussian noise that mimics the sampling
+    error of adaptive (ALE: fixed tolerance) or fixed-sample (MLE: hedged binomial standard error) likelihood
+    estimation."""
+
+    def __init__(self, underlying_model, tol=None, n_samples=None, hedge=None):
+        super(PoisonedModel, self).__init__()
+        self._underlying_model = underlying_model
+        if (tol is None) == (n_samples is None):
+            raise ValueError("Exactly one of tol and n_samples must be specified")
+        self._ale = tol is not None
+        self._tol = tol
+        self._n_samples = n_samples
+        self._hedge = hedge if hedge is not None else 0.0
+
+    underlying_model = property(lambda self: self._underlying_model)
+    n_modelparams = property(lambda self: self._underlying_model.n_modelparams)
+    expparams_dtype = property(lambda self: self._underlying_model.expparams_dtype)
+
+    def are_models_valid(self, modelparams):
+        return self._underlying_model.are_models_valid(modelparams)
+
+    def likelihood(self, outcomes, modelparams, expparams):
+        # derived_models.py:188-204
+        L = self._underlying_model.likelihood(outcomes, modelparams, expparams)
+        epsilon = np.random.normal(size=L.shape)
+        if self._ale:
+            epsilon *= self._tol
+        else:
+            epsilon *= binom_est_error(p=L, N=self._n_samples, hedge=self._hedge)
+        np.clip(L + epsilon, 0, 1, out=L)
+        return L
 
 
 class RandomWalkModel(_ModelBase):

@@ -24,7 +24,7 @@ def oracle_namespace():
         RandomizedBenchmarkingModel=o.RandomizedBenchmarkingModel, BinomialModel=o.BinomialModel,
         CoinModel=o.CoinModel, MLEModel=o.MLEModel, TomographyModel=o.TomographyModel,
         RandomWalkModel=o.RandomWalkModel, GaussianRandomWalkModel=o.GaussianRandomWalkModel,
-        NormalStepDistribution=o.NormalStepDistribution, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
+        NormalStepDistribution=o.NormalStepDistribution, PoisonedModel=o.PoisonedModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
         UniformDistribution=o.UniformDistribution, PostselectedDistribution=o.PostselectedDistribution,
         sqrtm_psd=o.sqrtm_psd)
 
@@ -42,7 +42,7 @@ def reference_namespace():
         RandomizedBenchmarkingModel=q.RandomizedBenchmarkingModel, BinomialModel=q.BinomialModel,
         CoinModel=q.CoinModel, MLEModel=q.MLEModel, TomographyModel=qt.TomographyModel,
         RandomWalkModel=q.RandomWalkModel, GaussianRandomWalkModel=q.GaussianRandomWalkModel,
-        NormalStepDistribution=q.MultivariateNormalDistribution, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
+        NormalStepDistribution=q.MultivariateNormalDistribution, PoisonedModel=q.PoisonedModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
         UniformDistribution=q.UniformDistribution, PostselectedDistribution=q.PostselectedDistribution,
         sqrtm_psd=qu.sqrtm_psd)
 
@@ -470,4 +470,9 @@ def random_walk_vectors(ns, seed=53):
     m = ns.GaussianRandomWalkModel(ns.SimplePrecessionModel())
     out['grw_learn_x'], out['grw_learn_w'], out['grw_learn_norm'], out['grw_learn_rc'] = run(m, prior2)
     out['grw_learn_valid'] = m.are_models_valid(np.array([[0.5, 0.0], [0.5, -1e-9], [-0.1, 1e-3]]))
+    # (4) PoisonedModel: ALE (fixed tolerance) and MLE (hedged binomial standard error) noise on the likelihood
+    m = ns.PoisonedModel(ns.SimplePrecessionModel(), tol=0.01)
+    out['ale_x'], out['ale_w'], out['ale_norm'], out['ale_rc'] = run(m, prior)
+    m = ns.PoisonedModel(ns.SimplePrecessionModel(), n_samples=200, hedge=0.5)
+    out['mle_x'], out['mle_w'], out['mle_norm'], out['mle_rc'] = run(m, prior)
     return out
