@@ -25,6 +25,7 @@ qinfer/perf_testing.py:250-251 (only ``update`` is timed; prior sampling is not)
 bounded particle sample (stated in the output), and prints the same JSON line.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -295,6 +296,8 @@ def gpu_arm(args, rank, world, local_rank):
             sampler.start()
             time.sleep(0.35)                             # let nvidia-smi take its first samples
         barrier()
+        gc.collect()
+        gc.disable()                                     # no collector pauses inside the timed regions (host hygiene)
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         for k in range(warm, warm + steps):
@@ -374,6 +377,7 @@ def gpu_arm(args, rank, world, local_rank):
         h2d = (n * 8 + 64 * steps) / steps               # prior upload amortised + per-step experiment record
         d2h = (2 * n * 8 + 8) / steps + 16 * 8           # posterior read-back amortised + per-step stats block
 
+    gc.enable()
     if dist is not None:
         t = torch.tensor([elapsed_ms, e2e_ms, kern_ms, resample_ms], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
