@@ -322,7 +322,8 @@ def gpu_arm(args, rank, world, local_rank):
         if world > 1:
             up.close()
         del up, cloud                                    # (a live reference would keep ~1 GB of device buffers
-        torch.cuda.synchronize()                         #  allocated and make the e2e pass cudaMalloc its own)
+        gc.collect()                                     #  allocated and make the e2e pass cudaMalloc its own)
+        torch.cuda.synchronize()
         prior = pinned_prior.numpy()                     # the user's host array, page-locked (allocated above)
         barrier()
         t0 = time.perf_counter()
