@@ -266,8 +266,9 @@ def gpu_arm(args, rank, world, local_rank):
             from qinfer_b200.sharded import ShardedSMCUpdater
             small = ShardedSMCUpdater(qb.SimplePrecessionModel(), nsmall * world, FixedPrior(prior[:nsmall]), lazy=True,
                                       resampler=qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast'))
+        wts_, wout_ = make_data(30, seed=7)              # its own data: independent of --steps/--warmup
         for k in range(30):
-            small.update(int(outcomes[k]), ts[k:k + 1])
+            small.update(int(wout_[k]), wts_[k:k + 1])
         small.est_mean()
         # ... and page-lock the host staging blocks the posterior read-back will recycle (torch's caching host
         # allocator keeps them), as a long-lived process would have done on its first read
