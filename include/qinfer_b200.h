@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define QB_ABI_VERSION 2 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes */
+#define QB_ABI_VERSION 3 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes; 3: qb_lw_binned_* */
 
 #define QB_OK 0
 #define QB_ERR_INVALID_ARGUMENT (-1)
@@ -317,6 +317,69 @@ int qb_lw_merge_retry(const qb_model* model, const double* d_x_old, int64_t n_ol
                       const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
                       const int64_t* d_idxs, int64_t k, const int32_t* d_parent_inv, double* d_x_new,
                       uint8_t* d_invalid, int64_t* d_counters, void* stream);
+
+/* Binned multinomial resample for the device-RNG mode, d <= 4 (the default draw of LiuWestResampler(rng='philox',
+ * scan='fast')): resamplers.py:266-273 (moments), :308-321 (multinomial draw), :325-372 (shrink, perturb,
+ * postselection) and :390-392 (weights 1/n) in three streaming launches, no global CDF, no stored uniforms or
+ * indices (csrc/qb_binned.cu describes the factorisation: multinomial counts per bin of 2048 particles, then i.i.d.
+ * draws inside each bin from a shared-memory CDF).  The offspring multiset has exactly the reference's law; the
+ * slot ORDER differs (grouped by parent bin).
+ *   qb_lw_binned_prepare  one pass over (w, x): bin sums -> bin-level CDF, weighted moments into d_moments_out
+ *                         (1 + d + d*d doubles, layout of qb_moments; may be NULL) and into the pinned, device-mapped
+ *                         host block h_mirror (32 doubles, [31] = tag, written last; may be NULL); then the multinomial
+ *                         counts of n_new draws (Philox stream (seed_u, off_u), elements 0..n_new-1), their output
+ *                         offsets and the segment list.
+ *   qb_lw_binned_move     slot i draws inside its bin with uniform element i of (seed_v, off_v), normals
+ *                         eps[m][i] = element m * n_new + i of (seed_n, off_n).  Slots >= split go to
+ *                         d_x_new2[(i - split)] when d_x_new2 != NULL (a shard's surplus rows).  d_w_new != NULL:
+ *                         also stores the new weights 1/n_global and their stats block d_stats_new.  Invalid slots
+ *                         are appended to d_list (n_new int64: slot | parent << 32); h_mirror (8 doubles, 32-byte
+ *                         aligned, device-accessible: pinned host or device memory) receives {#invalid, #clamped,
+ *                         #drawn, tag}.  retry_rounds > 0 (with postselect) queues qb_lw_binned_retry right behind it
+ *                         (rounds = retry_rounds, stream offset off_n + round_stride), reporting into h_mirror[4..8).
+ *                         d_js_out (may be NULL): the parent of every slot (tests).
+ *   qb_lw_binned_retry    up to `rounds` fresh perturbations per still-invalid list entry in ONE launch (round j: normals
+ *                         element m * n_new + slot of (seed_n, off_n + j * round_stride)), re-centred on the slot's
+ *                         own parent, stopping at the first valid one; resolved entries become -1.  The list length is
+ *                         read on the device (a counter in the workspace), so the call may be queued right behind the
+ *                         move.  h_mirror (4 doubles) receives {#still invalid, most rounds used, list length, tag}.
+ * Workspace: qb_lw_binned_workspace_bytes(n_old, n_new), ZERO-INITIALISED once, private to these three calls. */
+size_t qb_lw_binned_workspace_bytes(int64_t n_old, int64_t n_new);
+/* qb_lw_binned_prepare = qb_lw_binned_sums (pass 1) + qb_lw_binned_count (pass 2).  A sharded cloud calls them
+ * separately: the shard masses of pass 1 decide how many offspring n_new this slab produces. */
+int qb_lw_binned_sums(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old, int32_t d,
+                      double* d_moments_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
+int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, void* d_ws, size_t ws_bytes,
+                       void* stream);
+int qb_lw_binned_prepare(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old, int32_t d,
+                         int64_t n_new, uint64_t seed_u, uint64_t off_u, double* d_moments_out, double* h_mirror,
+                         double tag, void* d_ws, size_t ws_bytes, void* stream);
+int qb_lw_binned_move(const qb_model* model, const double* d_x_old, const double* d_w, const double* d_stats,
+                      int64_t n_old, int32_t d, const double* h_mean, const double* h_S, double a,
+                      uint64_t seed_v, uint64_t off_v, uint64_t seed_n, uint64_t off_n, int64_t n_new,
+                      double* d_x_new, int64_t split, double* d_x_new2, double* d_w_new, int64_t n_global,
+                      double* d_stats_new, int32_t postselect, int32_t retry_rounds, int64_t* d_list,
+                      int64_t* d_js_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
+int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                       const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
+                       uint64_t round_stride, int32_t rounds, int64_t n_new, double* d_x_new, int64_t split,
+                       double* d_x_new2, int64_t* d_list, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                       void* stream);
+
+/* The whole resample queued by ONE call, with no host decision in between: pass 1 additionally derives the Liu-West
+ * constants on the device — cov = E[xx^T] - mu mu^T (distributions.py:388-389), a zero Frobenius norm replaced by
+ * zero_cov_comp * I (resamplers.py:288-293), S = h * sqrtm_psd(cov) (utils.py:593-607: symmetric eigendecomposition,
+ * here cyclic Jacobi; eigenvalues <= 0 clipped), (1 - a) * mean — and pass 3 reads them from the workspace.
+ * h_mirror: 40 doubles, 32-byte aligned, device-accessible: [0, 1+d+d*d) the moments, [29] covariance flag (0 fine,
+ * 1 zero norm replaced, 2 not finite), [30] || S0 S0 - cov ||_F, [31] = tag once pass 1 has published; [32, 36) the
+ * move's {#invalid, #clamped, #drawn, tag}; [36, 40) the queued retry's {#still invalid, rounds used, list length, tag}.
+ * The host checks the flags and raises the reference's warnings / ResamplerError after the fact. */
+int qb_lw_binned_resample(const qb_model* model, const double* d_x, const double* d_w, const double* d_stats,
+                          int64_t n_old, int32_t d, int64_t n_new, double a, double h, double zero_cov_comp,
+                          uint64_t seed, uint64_t off_u, uint64_t off_v, uint64_t seed_n, uint64_t off_n,
+                          double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
+                          int32_t postselect, int32_t retry_rounds, int64_t* d_list, double* d_moments_out,
+                          double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---- sharded cloud: peer mailboxes and the resample exchange ------------------- */
 #define QB_IPC_HANDLE_BYTES 64

@@ -1,0 +1,1126 @@
+// "Binned" multinomial Liu-West resample for the device-RNG mode, d <= 4 (SURVEY §8 a12-a17;
+// distributions.py:337-399, resamplers.py:308-372).
+//
+// The reference draws n i.i.d. uniforms and bisects the global CDF for each (resamplers.py:319-321): n random
+// probes into a table far larger than any cache.  A multinomial draw factorises exactly:
+//
+//     counts per BIN of 2048 consecutive particles  ~  Multinomial(n_new; bin masses)
+//     given its count m_t, the offspring of bin t are m_t i.i.d. draws from the bin's own normalised weights
+//
+// and the new particles of a resample are exchangeable, so bin t's offspring may occupy the contiguous output
+// slots [offs[t], offs[t] + m_t).  Every pass then streams:
+//
+//   binned_sums_kernel   one read of (w, x): per-bin weight sums AND the weighted moments (Sum w, Sum w x,
+//                        Sum w x x^T) of distributions.py:337-399; the last block turns the bin sums into the
+//                        bin-level CDF `bounds` and publishes the moments (device buffer + pinned host mirror).
+//   binned_count_kernel  no HBM traffic: n_new Philox uniforms are located in `bounds` (shared memory) and
+//                        histogrammed -> the multinomial counts; the last block scans them into output offsets
+//                        and cuts every bin's output range into segments of <= SEG slots.
+//                        (Runs while the host takes the d x d matrix square root of the covariance.)
+//   binned_move_kernel   per segment: the bin's weights and rows are loaded ONCE, coalesced, into shared memory,
+//                        scanned there into the bin-local CDF, and every output slot of the segment draws a fresh
+//                        uniform, bisects the shared-memory CDF (no global probe), takes its parent row from
+//                        shared memory, shrinks (resamplers.py:325), perturbs (:332), tests validity (:345-357) and
+//                        stores its row and its new weight 1/n (:390-392) with coalesced streaming stores.
+//                        Invalid slots are appended to a list (slot, parent) for binned_retry_kernel.
+//
+// HBM traffic per resampled particle: 8(d+1) [sums+moments] + 8(d+1) [bin load] + 8d + 8 [row + weight out]
+// = 8(3d+3) B (48 B for d = 1) against SURVEY §8d's 8(3d+5): the global CDF, the uniforms, the indices and the
+// guide table of the other draw paths never exist.  The random probes happen in shared memory.
+//
+// Statistical contract: the offspring multiset has exactly the law of the reference's (n i.i.d. draws from the
+// normalised weights); slot order differs (ordered by parent bin), which the resampler's result does not depend
+// on (uniform weights, exchangeable particles).  Philox streams: (seed_u, off_u) element i < n_new locates draw i's
+// bin; (seed_v, off_v) element i positions slot i inside its bin; normals as in qb_lw_draw_move.  A retry
+// re-centres the slot on its own parent with normals indexed by SLOT (deterministic whatever the list order).
+//
+// Compiled with --fmad=false (one rounding per reference ufunc in the move; explicit fma() in the reductions).
+#include "qb_models.cuh"
+#include "qb_philox.cuh"
+
+namespace qb {
+
+constexpr int BIN = 2048;                         // particles per bin
+constexpr int BIN_LOG2 = 11;
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_ITEMS = BIN / BIN_THREADS;      // 8 consecutive particles per thread
+constexpr int SEG = 2 * BIN;                      // output slots per segment (mean offspring per bin: BIN)
+constexpr int COUNT_THREADS = 1024;
+constexpr int BIN_MAX_GRID = 4096;                // partials rows reserved in the workspace
+constexpr int MOM_MAX = 1 + 4 + 10;               // packed moment outputs for d <= 4
+
+struct BinLayout {
+    size_t bounds, counts, offs, segs, partials, total;
+    int64_t T, max_segs;
+};
+
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+static BinLayout bin_layout(int64_t n_old, int64_t n_new) {
+    BinLayout L;
+    L.T = (n_old + BIN - 1) / BIN;
+    L.max_segs = L.T + n_new / SEG + 2;
+    L.bounds = 512;                                              // [0,512): tickets, nseg, counters (byte 64), Liu-West constants (byte 128)
+    L.counts = L.bounds + align256(static_cast<size_t>(L.T + 1) * 8);
+    L.offs = L.counts + align256(static_cast<size_t>(L.T + 2) * 4);
+    L.partials = L.offs + align256(static_cast<size_t>(L.T + 1) * 8);
+    L.segs = L.partials + align256(static_cast<size_t>(BIN_MAX_GRID) * MOM_MAX * 8);  // last: only its size depends on n_new
+    L.total = L.segs + align256(static_cast<size_t>(L.max_segs) * 8);
+    return L;
+}
+
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// Exclusive block scan of one value per thread (warp shuffles + one shared array of NW entries); `total` = block sum.
+template <typename V, int NW>
+__device__ __forceinline__ V block_excl_scan(V v, V* warp_tot, V& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    V inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const V t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    V base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const V t = warp_tot[k];
+        if (k < wid) base += t;
+        tot += t;
+    }
+    total = tot;
+    __syncthreads();
+    return base + (inc - v);
+}
+
+// =============================================================================================================
+// pass 1: bin sums + moments
+// =============================================================================================================
+struct BinSumsParams {
+    const double* x;
+    const double* w;
+    const double* stats;
+    int64_t n;
+    int32_t T, pad;
+    double* bounds;          // [T + 1]: bin sums, then (last block) their exclusive prefix; bounds[T] = total
+    unsigned int* counts;    // [T + 2]: zeroed here for pass 2
+    double* partials;        // [grid][NOUT]
+    double* moments_out;     // device, 1 + d + d*d (may be NULL)
+    double* mirror;          // pinned host, 32 doubles: values, [29] covariance flags, [30] sqrtm error, tag at [31]
+    double tag;
+    unsigned int* ticket;
+    double* consts;          // != NULL: the last block also derives the Liu-West constants S (16) and (1-a) mean (4)
+    double a, h, zero_cov_comp;
+};
+
+// Liu-West constants on the device (d <= 4), restating resamplers.py:266-305 + utils.py:593-607 for one thread:
+//   cov = E[x x^T] - mu mu^T (distributions.py:388-389); zero Frobenius norm -> zero_cov_comp * I (flag 1);
+//   S = h * sqrtm_psd(cov): symmetric eigendecomposition (cyclic Jacobi), eigenvalues <= 0 clipped, V sqrt(w) V^T;
+//   err = || S0 S0 - cov ||_F (the host raises ResamplerError when it is not finite; flag 2: cov itself not finite).
+// For d = 1 the arithmetic is the host path's, operation for operation (product, difference, sqrt, product).
+template <int D>
+__device__ void liu_west_consts(const double* out /* 1 + D + D*D moments */, double a, double h, double zero_cov_comp,
+                                double* consts /* S[16], ms[4] */, double& flags, double& err) {
+    double mean[D], cov[D][D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) mean[m] = out[1 + m];
+    bool finite = true;
+    double fro2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < D; ++m)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            cov[m][c] = out[1 + D + m * D + c] - mean[m] * mean[c];
+            finite = finite && isfinite(cov[m][c]);
+            fro2 += cov[m][c] * cov[m][c];
+        }
+    flags = finite ? 0.0 : 2.0;
+    if (finite && fro2 == 0.0) {
+        flags = 1.0;
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int c = 0; c < D; ++c) cov[m][c] = (m == c) ? zero_cov_comp : 0.0;
+    }
+    double S0[D][D];
+    if (D == 1) {
+        S0[0][0] = (cov[0][0] > 0.0) ? sqrt(cov[0][0]) : 0.0;
+    } else {
+        double A[D][D], V[D][D];
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                A[m][c] = cov[m][c];
+                V[m][c] = (m == c) ? 1.0 : 0.0;
+            }
+        for (int sweep = 0; sweep < 24; ++sweep) {
+            double off = 0.0;
+#pragma unroll
+            for (int p_ = 0; p_ < D; ++p_)
+#pragma unroll
+                for (int q_ = p_ + 1; q_ < D; ++q_) off += A[p_][q_] * A[p_][q_];
+            if (!(off > 0.0)) break;
+#pragma unroll
+            for (int p_ = 0; p_ < D; ++p_)
+#pragma unroll
+                for (int q_ = p_ + 1; q_ < D; ++q_) {
+                    const double apq = A[p_][q_];
+                    if (apq == 0.0) continue;
+                    const double theta = (A[q_][q_] - A[p_][p_]) / (2.0 * apq);
+                    const double t = ((theta >= 0.0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {   // A <- A J
+                        const double akp = A[k][p_], akq = A[k][q_];
+                        A[k][p_] = cs * akp - sn * akq;
+                        A[k][q_] = sn * akp + cs * akq;
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {   // A <- J^T A
+                        const double apk = A[p_][k], aqk = A[q_][k];
+                        A[p_][k] = cs * apk - sn * aqk;
+                        A[q_][k] = sn * apk + cs * aqk;
+                    }
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {   // V <- V J
+                        const double vkp = V[k][p_], vkq = V[k][q_];
+                        V[k][p_] = cs * vkp - sn * vkq;
+                        V[k][q_] = sn * vkp + cs * vkq;
+                    }
+                    A[p_][q_] = 0.0;
+                    A[q_][p_] = 0.0;
+                }
+        }
+        double rt[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) rt[k] = (A[k][k] > 0.0) ? sqrt(A[k][k]) : 0.0;   // w[w <= 0] = 0; sqrt(w)
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) v = fma(V[m][k] * rt[k], V[c][k], v);
+                S0[m][c] = v;
+            }
+    }
+    double e2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < D; ++m)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) v = fma(S0[m][k], S0[k][c], v);
+            const double df = v - cov[m][c];
+            e2 += df * df;
+        }
+    err = (D == 1) ? fabs(S0[0][0] * S0[0][0] - cov[0][0]) : sqrt(e2);
+    for (int j = 0; j < 16; ++j) consts[j] = 0.0;
+#pragma unroll
+    for (int m = 0; m < D; ++m)
+#pragma unroll
+        for (int c = 0; c < D; ++c) consts[m * D + c] = h * S0[m][c];
+    const double oma = 1.0 - a;
+    for (int c = 0; c < 4; ++c) consts[16 + c] = (c < D) ? oma * mean[c] : 0.0;   // (1 - a) * mean
+}
+
+template <int D>
+__global__ void __launch_bounds__(BIN_THREADS) binned_sums_kernel(const __grid_constant__ BinSumsParams p) {
+    constexpr int NOUT = 1 + D + D * (D + 1) / 2;
+    constexpr int NW = BIN_THREADS / 32;
+    constexpr int CHUNK = 32 * BIN_ITEMS;            // particles one warp covers per step (8 per lane)
+    constexpr int NCHUNK = BIN / CHUNK;              // 8 steps per bin
+    __shared__ double mred[NW * NOUT];
+    __shared__ double scan_tot[NW];
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double inv = p.stats[QB_STAT_INV_NORM];
+    double acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = 0.0;
+    // One WARP per bin: no block-wide barrier in the streaming loop, every warp keeps its own loads in flight.
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * NW + wid;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * NW;
+    for (int64_t t = gw; t < p.T; t += nwarps) {
+        double s = 0.0;
+#pragma unroll (D <= 2 ? 4 : 2)
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            const int64_t base = t * BIN + static_cast<int64_t>(ch) * CHUNK + static_cast<int64_t>(lane) * BIN_ITEMS;
+            double wv[BIN_ITEMS], xv[BIN_ITEMS * D];
+            if (base + BIN_ITEMS <= p.n) {
+#pragma unroll
+                for (int k = 0; k < BIN_ITEMS / 2; ++k) {
+                    const double2 t2 = ldg_stream2(p.w + base + 2 * k);
+                    wv[2 * k] = t2.x;
+                    wv[2 * k + 1] = t2.y;
+                }
+#pragma unroll
+                for (int k = 0; k < BIN_ITEMS * D / 2; ++k) {
+                    const double2 t2 = ldg_stream2(p.x + base * D + 2 * k);
+                    xv[2 * k] = t2.x;
+                    xv[2 * k + 1] = t2.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < BIN_ITEMS; ++k) {
+                    const bool in = base + k < p.n;
+                    wv[k] = in ? p.w[base + k] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) xv[k * D + c] = in ? p.x[(base + k) * D + c] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BIN_ITEMS; ++k) {
+                const double wi = wv[k] * inv;
+                s += wi;
+                acc[0] += wi;
+                int o = 1 + D;
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    const double wx = wi * xv[k * D + m];
+                    acc[1 + m] += wx;
+#pragma unroll
+                    for (int c = m; c < D; ++c) {
+                        acc[o] = fma(wx, xv[k * D + c], acc[o]);
+                        ++o;
+                    }
+                }
+            }
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            p.bounds[t] = s;
+            p.counts[t] = 0u;
+        }
+    }
+    // moment partials of this block (fixed order)
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) mred[wid * NOUT + k] = v;
+    }
+    __syncthreads();
+    if (tid < NOUT) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) v += mred[k * NOUT + tid];
+        p.partials[static_cast<size_t>(blockIdx.x) * NOUT + tid] = v;
+    }
+    __threadfence();   // every warp's bin sums (lane 0) and the partials, before this block's ticket
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- last block: bin sums -> exclusive prefix (the bin-level CDF) ----
+    const int T = p.T;
+    const int per = (T + BIN_THREADS - 1) / BIN_THREADS;
+    const int lo = tid * per, hi = (lo + per < T) ? lo + per : T;
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) s += __ldcg(p.bounds + i);
+    double total;
+    double run = block_excl_scan<double, NW>(s, scan_tot, total);
+    for (int i = lo; i < hi; ++i) {
+        const double v = __ldcg(p.bounds + i);
+        p.bounds[i] = run;
+        run += v;
+    }
+    if (tid == 0) {
+        p.bounds[T] = total;
+        p.counts[T] = 0u;
+        p.counts[T + 1] = 0u;
+    }
+    // ---- moments: one warp per output, lanes stride over the blocks' partials (fixed order) ----
+    __shared__ double fin[NOUT];
+    for (int o = wid; o < NOUT; o += NW) {
+        double v = 0.0;
+        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) v += __ldcg(p.partials + static_cast<size_t>(b) * NOUT + o);
+        v = warp_sum(v);
+        if (lane == 0) fin[o] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double out[1 + D + D * D];
+        out[0] = fin[0];
+#pragma unroll
+        for (int m = 0; m < D; ++m) out[1 + m] = fin[1 + m];
+        int o = 1 + D;
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int c = m; c < D; ++c) {
+                out[1 + D + m * D + c] = fin[o];
+                out[1 + D + c * D + m] = fin[o];
+                ++o;
+            }
+        if (p.moments_out != nullptr)
+            for (int k = 0; k < 1 + D + D * D; ++k) p.moments_out[k] = out[k];
+        double flags = 0.0, err = 0.0;
+        if (p.consts != nullptr) liu_west_consts<D>(out, p.a, p.h, p.zero_cov_comp, p.consts, flags, err);
+        if (p.mirror != nullptr) {
+            for (int k = 0; k < 1 + D + D * D; ++k) p.mirror[k] = out[k];
+            p.mirror[29] = flags;
+            p.mirror[30] = err;
+            __threadfence_system();
+            *reinterpret_cast<volatile double*>(p.mirror + 31) = p.tag;
+        }
+        *p.ticket = 0u;
+    }
+}
+
+// =============================================================================================================
+// pass 2: multinomial counts per bin (histogram of n_new uniforms over the bin-level CDF), offsets, segments
+// =============================================================================================================
+struct BinCountParams {
+    const double* bounds;
+    unsigned int* counts;    // [T + 2]
+    int64_t* offs;           // [T + 1]
+    uint2* segs;             // [max_segs]: (bin, chunk)
+    unsigned int* ticket;
+    unsigned int* nseg;
+    int64_t n_new;
+    int32_t T, max_segs;
+    uint64_t seed_u, off_u;
+};
+
+// bin of v: the t in [0, T) with bounds[t] <= v < bounds[t+1] (clamped).  Starts from the proportional guess
+// (bin masses are nearly equal for a well-mixed cloud: 1-3 probes), gallops, then bisects: O(log T) whatever the
+// weights look like.
+template <typename Tab>
+__device__ __forceinline__ int locate_bin(Tab tab, int T, double v, double guess_scale) {
+    int g = static_cast<int>(v * guess_scale);
+    g = (g < 0) ? 0 : ((g > T - 1) ? T - 1 : g);
+    int lo, hi;  // invariant: (lo == 0 or tab(lo) <= v) and (hi == T or tab(hi) > v), lo < hi
+    if (tab(g) <= v) {
+        lo = g;
+        hi = g + 1;
+        int step = 1;
+        while (hi < T && tab(hi) <= v) {
+            lo = hi;
+            hi = (hi + step < T) ? hi + step : T;
+            step <<= 1;
+        }
+    } else {
+        hi = g;
+        lo = g - 1;
+        int step = 1;
+        while (lo > 0 && tab(lo) > v) {
+            hi = lo;
+            lo = (lo - step > 0) ? lo - step : 0;
+            step <<= 1;
+        }
+        if (lo < 0) lo = 0;
+        if (hi <= lo) hi = lo + 1;
+    }
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (tab(mid) <= v)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(COUNT_THREADS) binned_count_kernel(const __grid_constant__ BinCountParams p) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    __shared__ long long scan_a[COUNT_THREADS / 32], scan_b[COUNT_THREADS / 32];
+    __shared__ unsigned int is_last;
+    const int T = p.T, tid = threadIdx.x;
+    double* bounds_s = reinterpret_cast<double*>(bsm);                          // [T + 1]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(bounds_s + (T + 2));   // [T + 2] (8-byte aligned, even length)
+    const int Tpad = (T + 2) & ~1;
+    if (SMEM) {
+        for (int i = tid; i <= T; i += COUNT_THREADS) bounds_s[i] = p.bounds[i];
+        for (int i = tid; i < Tpad; i += COUNT_THREADS) hist[i] = 0u;
+        __syncthreads();
+    }
+    const double total = SMEM ? bounds_s[T] : p.bounds[T];
+    const double guess_scale = static_cast<double>(T) / total;
+    auto tab_s = [&](int i) { return bounds_s[i]; };
+    auto tab_g = [&](int i) { return __ldg(p.bounds + i); };
+    const int64_t npairs = (p.n_new + 1) / 2;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * COUNT_THREADS;
+    constexpr int NP = 4;  // Philox counters per thread and iteration: 8 independent searches in flight
+    for (int64_t pr0 = static_cast<int64_t>(blockIdx.x) * COUNT_THREADS + tid; pr0 < npairs; pr0 += NP * stride) {
+        double v[2 * NP];
+        bool live[2 * NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int64_t pr = pr0 + q * stride;
+            double u0 = 0.0, u1 = 0.0;
+            if (pr < npairs) philox_uniform_pair(p.seed_u, p.off_u + static_cast<uint64_t>(pr), u0, u1);
+            v[2 * q] = u0 * total;
+            v[2 * q + 1] = u1 * total;
+            live[2 * q] = pr < npairs;
+            live[2 * q + 1] = pr < npairs && 2 * pr + 1 < p.n_new;
+        }
+        int b[2 * NP];
+#pragma unroll
+        for (int q = 0; q < 2 * NP; ++q)
+            b[q] = SMEM ? locate_bin(tab_s, T, v[q], guess_scale) : locate_bin(tab_g, T, v[q], guess_scale);
+#pragma unroll
+        for (int q = 0; q < 2 * NP; ++q)
+            if (live[q]) {
+                if (SMEM)
+                    atomicAdd(hist + b[q], 1u);
+                else
+                    atomicAdd(p.counts + b[q], 1u);
+            }
+    }
+    if (SMEM) {
+        __syncthreads();
+        // two 32-bit counts per 64-bit atomic (no carry: every count < n_new < 2^31)
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.counts);
+        for (int i = tid; i < Tpad / 2; i += COUNT_THREADS) {
+            const unsigned long long v = static_cast<unsigned long long>(hist[2 * i]) |
+                                         (static_cast<unsigned long long>(hist[2 * i + 1]) << 32);
+            if (v) atomicAdd(dst + i, v);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- last block: counts -> output offsets; every bin's output range cut into segments of <= SEG slots ----
+    const int per = (T + COUNT_THREADS - 1) / COUNT_THREADS;
+    const int lo = tid * per, hi = (lo + per < T) ? lo + per : T;
+    long long m_sum = 0, s_sum = 0;
+    for (int i = lo; i < hi; ++i) {
+        const long long m = static_cast<long long>(__ldcg(p.counts + i));
+        m_sum += m;
+        s_sum += (m + SEG - 1) / SEG;
+    }
+    long long m_tot, s_tot;
+    long long m_run = block_excl_scan<long long, COUNT_THREADS / 32>(m_sum, scan_a, m_tot);
+    long long s_run = block_excl_scan<long long, COUNT_THREADS / 32>(s_sum, scan_b, s_tot);
+    for (int i = lo; i < hi; ++i) {
+        const long long m = static_cast<long long>(__ldcg(p.counts + i));
+        p.offs[i] = m_run;
+        m_run += m;
+        const long long ns = (m + SEG - 1) / SEG;
+        for (long long c = 0; c < ns; ++c)
+            if (s_run + c < p.max_segs) p.segs[s_run + c] = make_uint2(static_cast<unsigned int>(i), static_cast<unsigned int>(c));
+        s_run += ns;
+    }
+    if (tid == 0) {
+        p.offs[T] = m_tot;
+        *p.nseg = static_cast<unsigned int>(s_tot < p.max_segs ? s_tot : p.max_segs);
+        // the move / retry kernels' counters: [0] invalid slots (list length), [1] clamped draws, [2] still invalid
+        // after a retry launch, [3] most rounds used
+        unsigned long long* ctr = reinterpret_cast<unsigned long long*>(p.ticket - 1 + 16);
+        ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0ull;
+        *p.ticket = 0u;
+    }
+}
+
+// =============================================================================================================
+// pass 3: per segment, bin-local CDF in shared memory, draw + gather + shrink + perturb + validity + weights
+// =============================================================================================================
+struct BinMoveParams {
+    const double* x_old;
+    const double* w;
+    const double* stats;
+    const int64_t* offs;
+    const uint2* segs;
+    const unsigned int* nseg;
+    double* x_new;
+    double* x_new2;          // slots >= split are stored at x_new2[(slot - split)] (sharded: surplus rows); may be NULL
+    int64_t split;
+    double* w_new;           // may be NULL
+    double w_value;
+    double* stats_new;       // may be NULL: stats block of the uniform weights
+    double n_global;
+    long long* list;         // invalid slots: slot | parent << 32 (postselect only)
+    unsigned long long* counters;  // [0] invalid, [1] clamped draws
+    int64_t* js_out;         // optional: global parent index of every slot (tests)
+    double* mirror;          // pinned host: {invalid, clamped, drawn, tag} (may be NULL)
+    double tag;
+    unsigned int* ticket;
+    int64_t n_old, n_new;
+    uint64_t round_stride;   // retry: Philox counters between the normal streams of consecutive rounds
+    int32_t T, postselect, rounds, pad0;
+    uint64_t seed_v, off_v, seed_n, off_n;
+    double a;
+    double S[16];
+    double ms[4];
+    const double* consts;    // != NULL: S and (1-a) mean come from the workspace (derived on the device by pass 1)
+    ModelView mv;
+};
+
+// the Liu-West constants of this launch: launch parameters (host-derived) or the workspace (device-derived)
+template <int D>
+__device__ __forceinline__ void load_consts(const BinMoveParams& p, double (&S)[D * D], double (&ms)[D]) {
+    if (p.consts != nullptr) {
+#pragma unroll
+        for (int j = 0; j < D * D; ++j) S[j] = __ldcg(p.consts + j);
+#pragma unroll
+        for (int c = 0; c < D; ++c) ms[c] = __ldcg(p.consts + 16 + c);
+    } else {
+#pragma unroll
+        for (int j = 0; j < D * D; ++j) S[j] = p.S[j];
+#pragma unroll
+        for (int c = 0; c < D; ++c) ms[c] = p.ms[c];
+    }
+}
+
+template <int D>
+__device__ __forceinline__ double* slot_ptr(const BinMoveParams& p, int64_t i) {
+    return (p.x_new2 != nullptr && i >= p.split) ? p.x_new2 + (i - p.split) * D : p.x_new + i * D;
+}
+
+// normals eps[m] of slot pair (i0, i0 + 1), i0 even: element m * n_new + i of stream (seed_n, off_n)
+template <int D>
+__device__ __forceinline__ void slot_normals(const BinMoveParams& p, int64_t i0, bool need0, bool need1,
+                                             double (&ev)[2][D]) {
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        const int64_t f0 = static_cast<int64_t>(m) * p.n_new + i0;
+        if ((f0 & 1) == 0) {
+            philox_normal_pair(p.seed_n, p.off_n + static_cast<uint64_t>(f0 >> 1), ev[0][m], ev[1][m]);
+        } else {
+            ev[0][m] = need0 ? philox_normal_elem(p.seed_n, p.off_n, f0) : 0.0;
+            ev[1][m] = need1 ? philox_normal_elem(p.seed_n, p.off_n, f0 + 1) : 0.0;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(BIN_THREADS, (D <= 2) ? 3 : 2) binned_move_kernel(const __grid_constant__ BinMoveParams p) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    constexpr int NW = BIN_THREADS / 32;
+    double* cdf_s = reinterpret_cast<double*>(msm);        // [BIN]
+    double* x_s = cdf_s + BIN;                             // [BIN * D]
+    __shared__ double scan_tot[NW];
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double inv = p.stats[QB_STAT_INV_NORM];
+    const unsigned int nseg = *p.nseg;
+    unsigned int n_clamped = 0;
+    double Sl[D * D], msl[D];
+    load_consts<D>(p, Sl, msl);
+    if (blockIdx.x == 0 && tid == 0 && p.stats_new != nullptr) {
+        // resamplers.py:390-392: weights 1/n; the stats block of set_uniform_kernel
+        double* st = p.stats_new;
+        st[QB_STAT_NORM] = 1.0;
+        st[QB_STAT_SUMSQ] = p.w_value;
+        st[QB_STAT_MIN] = p.w_value;
+        st[QB_STAT_NBAD] = 0.0;
+        st[QB_STAT_INV_NORM] = 1.0;
+        st[QB_STAT_NESS] = p.n_global;
+        st[QB_STAT_TAG] = 0.0;
+        st[QB_STAT_SKIPPED] = 0.0;
+        st[QB_STAT_ATTN] = 0.0;
+    }
+    for (unsigned int s = blockIdx.x; s < nseg; s += gridDim.x) {
+        const uint2 sg = p.segs[s];
+        const int64_t bin = sg.x;
+        const int64_t first = bin * BIN;
+        const int cnt = static_cast<int>((p.n_old - first < BIN) ? (p.n_old - first) : BIN);
+        const int64_t o_bin = p.offs[bin];
+        const int64_t o_begin = o_bin + static_cast<int64_t>(sg.y) * SEG;
+        int64_t o_end = p.offs[bin + 1];
+        if (o_end > o_begin + SEG) o_end = o_begin + SEG;
+        // ---- load the bin, scan the weights into the bin-local CDF ----
+        const int j0 = tid * BIN_ITEMS;
+        double wv[BIN_ITEMS];
+        if (cnt == BIN) {
+#pragma unroll
+            for (int k = 0; k < BIN_ITEMS / 2; ++k) {
+                const double2 t2 = *reinterpret_cast<const double2*>(p.w + first + j0 + 2 * k);
+                wv[2 * k] = t2.x * inv;
+                wv[2 * k + 1] = t2.y * inv;
+            }
+#pragma unroll
+            for (int k = 0; k < BIN_ITEMS * D / 2; ++k) {
+                const double2 t2 = *reinterpret_cast<const double2*>(p.x_old + (first + j0) * D + 2 * k);
+                *reinterpret_cast<double2*>(x_s + j0 * D + 2 * k) = t2;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < BIN_ITEMS; ++k) {
+                const bool in = j0 + k < cnt;
+                wv[k] = in ? p.w[first + j0 + k] * inv : 0.0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) x_s[(j0 + k) * D + c] = in ? p.x_old[(first + j0 + k) * D + c] : 0.0;
+            }
+        }
+        double ts = 0.0;
+#pragma unroll
+        for (int k = 0; k < BIN_ITEMS; ++k) ts += wv[k];
+        double total;
+        double run = block_excl_scan<double, NW>(ts, scan_tot, total);
+        // The bin-local CDF goes to shared memory in EYTZINGER (breadth-first) order: node k of the implicit search
+        // tree over cdf[0 .. BIN-2] sits at eyt[k], children at 2k and 2k+1.  The probes of one tree level are
+        // contiguous, so the upper levels (few distinct nodes per warp) are conflict-free — in sorted order they sit
+        // 2^j entries apart, i.e. in ONE bank.  (Entry BIN-1, the bin total, is never needed: v < total.)
+#pragma unroll
+        for (int k = 0; k < BIN_ITEMS; ++k) {
+            run += wv[k];
+            const unsigned int r = static_cast<unsigned int>(j0 + k) + 1u;   // 1-based sorted rank
+            if (r < static_cast<unsigned int>(BIN)) {
+                const int tz = __ffs(r) - 1;
+                cdf_s[(1u << (BIN_LOG2 - 1 - tz)) + (r >> (tz + 1))] = run;
+            } else {
+                cdf_s[0] = run;                                               // slot 0 is no tree node: keeps the total
+            }
+        }
+        __syncthreads();
+        const double top = cdf_s[0];
+        // ---- the segment's output slots: NP Philox counters (2 slots each) per thread and round ----
+        constexpr int NP = 4;
+        const int64_t base_even = o_begin & ~1LL;
+        for (int64_t ib = base_even + 2 * tid; ib < o_end; ib += 2 * NP * BIN_THREADS) {
+            double v[2 * NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int64_t i0 = ib + static_cast<int64_t>(q) * 2 * BIN_THREADS;
+                double u0 = 0.0, u1 = 0.0;
+                if (i0 < o_end) philox_uniform_pair(p.seed_v, p.off_v + static_cast<uint64_t>(i0 >> 1), u0, u1);
+                v[2 * q] = u0 * top;
+                v[2 * q + 1] = u1 * top;
+            }
+            // branch-free descent, the 2 NP searches interleaved: k <- 2k + (eyt[k] <= v); rank = k - BIN = number
+            // of entries <= v = first index with cdf > v (side='right', resamplers.py:321)
+            unsigned int kk[2 * NP];
+#pragma unroll
+            for (int q = 0; q < 2 * NP; ++q) kk[q] = 1u;
+#pragma unroll
+            for (int lvl = 0; lvl < BIN_LOG2; ++lvl) {
+#pragma unroll
+                for (int q = 0; q < 2 * NP; ++q) kk[q] = 2u * kk[q] + ((cdf_s[kk[q]] <= v[q]) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int64_t i0 = ib + static_cast<int64_t>(q) * 2 * BIN_THREADS;
+                if (i0 >= o_end) continue;
+                const bool need0 = i0 >= o_begin, need1 = i0 + 1 < o_end;
+                int par[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int lo = static_cast<int>(kk[2 * q + h]) - BIN;
+                    if (lo >= cnt) {                                          // distributions.py:330-333's clamp
+                        lo = cnt - 1;
+                        if (h == 0 ? need0 : need1) ++n_clamped;
+                    }
+                    par[h] = lo;
+                }
+                double ev[2][D];
+                slot_normals<D>(p, i0, need0, need1, ev);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!(h == 0 ? need0 : need1)) continue;
+                    const int64_t i = i0 + h;
+                    double out[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        double z = 0.0;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) z = fma(Sl[c * D + m], ev[h][m], z);
+                        out[c] = ((p.a * x_s[par[h] * D + c]) + msl[c]) + z;  // resamplers.py:325,332, one rounding per ufunc
+                    }
+                    double* dst = slot_ptr<D>(p, i);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) stg_stream(dst + c, out[c]);
+                    if (p.w_new != nullptr) stg_stream(p.w_new + i, p.w_value);
+                    if (p.js_out != nullptr) p.js_out[i] = first + par[h];
+                    if (p.postselect) {
+                        auto row = [&](int c) { return out[c]; };
+                        if (!model_valid(p.mv, row)) {
+                            const unsigned long long pos = atomicAdd(p.counters, 1ull);
+                            p.list[pos] = static_cast<long long>(i) | (static_cast<long long>(first + par[h]) << 32);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();  // the next segment overwrites the shared-memory bin
+    }
+    n_clamped = __reduce_add_sync(0xffffffffu, n_clamped);
+    if (n_clamped && lane == 0) atomicAdd(p.counters + 1, static_cast<unsigned long long>(n_clamped));
+    if (p.mirror == nullptr) return;
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+        if (is_last) {
+            __threadfence();
+            const double bad = static_cast<double>(__ldcg(p.counters));
+            const double clamped = static_cast<double>(__ldcg(p.counters + 1));
+            const double drawn = static_cast<double>(p.offs[p.T]);
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror), "d"(bad), "d"(clamped), "d"(drawn),
+                         "d"(p.tag)
+                         : "memory");
+            *p.ticket = 0u;
+        }
+    }
+}
+
+// Retry over the entries of the invalid list (resamplers.py:327-372).  Every entry takes up to `rounds` fresh
+// perturbations in THIS launch — round j uses normals eps[m] = element m * n_new + slot of stream
+// (seed_n, off_n + j * round_stride) — and stops at the first valid one; an entry whose slot became valid is marked
+// resolved (-1).  The list length is read from the device (counters[0], written by the move kernel), so the host
+// queues this launch right behind the move without a round trip; with no invalid slot it exits at once.
+// counters[2] = entries still invalid, counters[3] = most rounds any entry used.
+template <int D>
+__global__ void __launch_bounds__(128) binned_retry_kernel(const __grid_constant__ BinMoveParams p) {
+    __shared__ unsigned int is_last;
+    const int64_t k0 = static_cast<int64_t>(*reinterpret_cast<const volatile unsigned long long*>(p.counters));
+    double Sl[D * D], msl[D];
+    load_consts<D>(p, Sl, msl);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < k0; r += stride) {
+        const long long e = p.list[r];
+        if (e < 0) continue;
+        const int64_t slot = e & 0xffffffffLL, parent = e >> 32;
+        double mu[D], out[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) mu[c] = (p.a * __ldg(p.x_old + parent * D + c)) + msl[c];
+        bool ok = false;
+        int used = 0;
+        for (int j = 0; j < p.rounds && !ok; ++j) {
+            const uint64_t off = p.off_n + static_cast<uint64_t>(j) * p.round_stride;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double z = 0.0;
+#pragma unroll
+                for (int m = 0; m < D; ++m)
+                    z = fma(Sl[c * D + m], philox_normal_elem(p.seed_n, off, static_cast<int64_t>(m) * p.n_new + slot), z);
+                out[c] = mu[c] + z;
+            }
+            auto row = [&](int c) { return out[c]; };
+            ok = model_valid(p.mv, row);
+            used = j + 1;
+        }
+        double* dst = slot_ptr<D>(p, slot);
+#pragma unroll
+        for (int c = 0; c < D; ++c) dst[c] = out[c];
+        if (ok)
+            p.list[r] = -1;
+        else
+            atomicAdd(p.counters + 2, 1ull);
+        atomicMax(p.counters + 3, static_cast<unsigned long long>(used));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+        if (is_last) {
+            __threadfence();
+            const double bad = static_cast<double>(__ldcg(p.counters + 2));
+            const double used = static_cast<double>(__ldcg(p.counters + 3));
+            const double listed = static_cast<double>(__ldcg(p.counters));
+            if (p.mirror != nullptr) asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.mirror), "d"(bad), "d"(used), "d"(listed),
+                         "d"(p.tag)
+                         : "memory");
+            p.counters[2] = 0ull;   // ready for the next retry launch
+            p.counters[3] = 0ull;
+            *p.ticket = 0u;
+        }
+    }
+}
+
+int validate_model(const qb_model* m);
+
+static int bin_grid(int64_t want, int per_sm) {
+    int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
+    if (cap > BIN_MAX_GRID) cap = BIN_MAX_GRID;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
+}  // namespace qb
+
+using namespace qb;
+
+extern "C" size_t qb_lw_binned_workspace_bytes(int64_t n_old, int64_t n_new) {
+    if (n_old < 1 || n_new < 1) return 0;
+    return bin_layout(n_old, n_new).total;
+}
+
+static int launch_sums(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old, int32_t d,
+                       double* d_moments_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream,
+                       bool device_consts, double a, double h, double zero_cov_comp) {
+    QB_REQUIRE(d_x && d_w && d_stats && d_ws, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_sums: NULL pointer argument");
+    QB_REQUIRE(d >= 1 && d <= 4, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_sums: needs 1 <= d <= 4, got %d", d);
+    QB_REQUIRE(n_old >= 1 && n_old < (1LL << 31), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_sums: particle count must lie in [1, 2^31)");
+    QB_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0,
+               QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_sums: x and w must be 16-byte aligned");
+    const BinLayout L = bin_layout(n_old, 1);
+    QB_REQUIRE(ws_bytes >= L.total, QB_ERR_WORKSPACE, "qb_lw_binned_sums: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    unsigned int* hdr = reinterpret_cast<unsigned int*>(ws);
+    BinSumsParams sp;
+    sp.x = d_x;
+    sp.w = d_w;
+    sp.stats = d_stats;
+    sp.n = n_old;
+    sp.T = static_cast<int32_t>(L.T);
+    sp.pad = 0;
+    sp.bounds = reinterpret_cast<double*>(ws + L.bounds);
+    sp.counts = reinterpret_cast<unsigned int*>(ws + L.counts);
+    sp.partials = reinterpret_cast<double*>(ws + L.partials);
+    sp.moments_out = d_moments_out;
+    sp.mirror = h_mirror;
+    sp.tag = tag;
+    sp.ticket = hdr + 0;
+    sp.consts = device_consts ? reinterpret_cast<double*>(ws + 128) : nullptr;
+    sp.a = a;
+    sp.h = h;
+    sp.zero_cov_comp = zero_cov_comp;
+    const int g1 = bin_grid((L.T + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32), (d <= 2) ? 4 : 2);
+    switch (d) {
+        case 1: binned_sums_kernel<1><<<g1, BIN_THREADS, 0, st>>>(sp); break;
+        case 2: binned_sums_kernel<2><<<g1, BIN_THREADS, 0, st>>>(sp); break;
+        case 3: binned_sums_kernel<3><<<g1, BIN_THREADS, 0, st>>>(sp); break;
+        default: binned_sums_kernel<4><<<g1, BIN_THREADS, 0, st>>>(sp); break;
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_binned_sums(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old, int32_t d,
+                                 double* d_moments_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                                 void* stream) {
+    return launch_sums(d_x, d_w, d_stats, n_old, d, d_moments_out, h_mirror, tag, d_ws, ws_bytes, stream, false, 0.0,
+                       0.0, 0.0);
+}
+
+extern "C" int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, void* d_ws,
+                                  size_t ws_bytes, void* stream) {
+    QB_REQUIRE(d_ws, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_count: NULL workspace");
+    QB_REQUIRE(n_old >= 1 && n_new >= 1 && n_old < (1LL << 31) && n_new < (1LL << 31), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_count: particle counts must lie in [1, 2^31)");
+    const BinLayout L = bin_layout(n_old, n_new);
+    QB_REQUIRE(ws_bytes >= L.total, QB_ERR_WORKSPACE, "qb_lw_binned_count: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    unsigned int* hdr = reinterpret_cast<unsigned int*>(ws);
+    BinCountParams cp;
+    cp.bounds = reinterpret_cast<const double*>(ws + L.bounds);
+    cp.counts = reinterpret_cast<unsigned int*>(ws + L.counts);
+    cp.offs = reinterpret_cast<int64_t*>(ws + L.offs);
+    cp.segs = reinterpret_cast<uint2*>(ws + L.segs);
+    cp.ticket = hdr + 1;
+    cp.nseg = hdr + 3;
+    cp.n_new = n_new;
+    cp.T = static_cast<int32_t>(L.T);
+    cp.max_segs = static_cast<int32_t>(L.max_segs);
+    cp.seed_u = seed_u;
+    cp.off_u = off_u;
+    const size_t smem = static_cast<size_t>(L.T + 2) * 8 + static_cast<size_t>((L.T + 2) & ~1LL) * 4 + 16;
+    const int64_t npairs = (n_new + 1) / 2;
+    if (smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            QB_CUDA_CHECK(cudaFuncSetAttribute(binned_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               200 * 1024));
+            attr_set = true;
+        }
+        const int g2 = bin_grid((npairs + COUNT_THREADS * 4 - 1) / (COUNT_THREADS * 4), 1);
+        binned_count_kernel<true><<<g2, COUNT_THREADS, smem, st>>>(cp);
+    } else {
+        binned_count_kernel<false><<<bin_grid((npairs + COUNT_THREADS - 1) / COUNT_THREADS, 2), COUNT_THREADS, 0, st>>>(cp);
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_binned_prepare(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old,
+                                    int32_t d, int64_t n_new, uint64_t seed_u, uint64_t off_u, double* d_moments_out,
+                                    double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream) {
+    QB_REQUIRE(n_new >= 1 && n_new < (1LL << 31), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_prepare: n_new must lie in [1, 2^31)");
+    QB_REQUIRE(n_old >= 1 && ws_bytes >= bin_layout(n_old, n_new).total, QB_ERR_WORKSPACE,
+               "qb_lw_binned_prepare: workspace too small");
+    int rc = qb_lw_binned_sums(d_x, d_w, d_stats, n_old, d, d_moments_out, h_mirror, tag, d_ws, ws_bytes, stream);
+    if (rc != QB_OK) return rc;
+    return qb_lw_binned_count(n_old, n_new, seed_u, off_u, d_ws, ws_bytes, stream);
+}
+
+static int fill_move(BinMoveParams& q, const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                     const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n, int64_t n_new,
+                     double* d_x_new, int64_t split, double* d_x_new2, int64_t* d_list,
+                     double* h_mirror, double tag, void* d_ws, size_t ws_bytes, const BinLayout& L) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE((h_mean == nullptr) == (h_S == nullptr), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_move/retry: pass both h_mean and h_S, or neither (constants derived by qb_lw_binned_resample)");
+    QB_REQUIRE(d_x_old && d_x_new && d_ws, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_move/retry: NULL pointer argument");
+    QB_REQUIRE(d == model->d && d >= 1 && d <= 4, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_move/retry: needs 1 <= d <= 4");
+    QB_REQUIRE(n_old >= 1 && n_new >= 1 && n_old < (1LL << 31) && n_new < (1LL << 31), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_move/retry: particle counts must lie in [1, 2^31)");
+    QB_REQUIRE(ws_bytes >= L.total, QB_ERR_WORKSPACE, "qb_lw_binned_move/retry: workspace too small");
+    QB_REQUIRE(h_mirror == nullptr || (reinterpret_cast<uintptr_t>(h_mirror) & 31) == 0, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_move/retry: the host mirror must be 32-byte aligned");
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+    unsigned int* hdr = reinterpret_cast<unsigned int*>(ws);
+    q.x_old = d_x_old;
+    q.w = nullptr;
+    q.stats = nullptr;
+    q.offs = reinterpret_cast<const int64_t*>(ws + L.offs);
+    q.segs = reinterpret_cast<const uint2*>(ws + L.segs);
+    q.nseg = hdr + 3;
+    q.x_new = d_x_new;
+    q.x_new2 = d_x_new2;
+    q.split = split;
+    q.w_new = nullptr;
+    q.w_value = 0.0;
+    q.stats_new = nullptr;
+    q.n_global = 0.0;
+    q.list = reinterpret_cast<long long*>(d_list);
+    q.counters = reinterpret_cast<unsigned long long*>(ws + 64);
+    q.js_out = nullptr;
+    q.mirror = h_mirror;
+    q.tag = tag;
+    q.ticket = hdr + 2;
+    q.n_old = n_old;
+    q.n_new = n_new;
+    q.round_stride = 0;
+    q.rounds = 1;
+    q.pad0 = 0;
+    q.T = static_cast<int32_t>(L.T);
+    q.postselect = 1;
+    q.seed_v = 0;
+    q.off_v = 0;
+    q.seed_n = seed_n;
+    q.off_n = off_n;
+    q.a = a;
+    const double oma = 1.0 - a;
+    for (int j = 0; j < 16; ++j) q.S[j] = (h_S != nullptr && j < d * d) ? h_S[j] : 0.0;
+    for (int c = 0; c < 4; ++c) q.ms[c] = (h_mean != nullptr && c < d) ? oma * h_mean[c] : 0.0;  // (1 - a) * mean
+    q.consts = (h_mean == nullptr) ? reinterpret_cast<const double*>(ws + 128) : nullptr;
+    q.mv = make_model_view(*model);
+    return QB_OK;
+}
+
+typedef void (*bin_kernel_t)(const BinMoveParams);
+
+static int launch_retry(const BinMoveParams& q, int d, cudaStream_t st) {
+    static const bin_kernel_t kernels[4] = {binned_retry_kernel<1>, binned_retry_kernel<2>, binned_retry_kernel<3>,
+                                            binned_retry_kernel<4>};
+    const int grid = bin_grid(1 << 20, 4);   // the list length is only known on the device: grid-stride
+    kernels[d - 1]<<<grid, 128, 0, st>>>(q);
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_binned_move(const qb_model* model, const double* d_x_old, const double* d_w,
+                                 const double* d_stats, int64_t n_old, int32_t d, const double* h_mean,
+                                 const double* h_S, double a, uint64_t seed_v, uint64_t off_v, uint64_t seed_n,
+                                 uint64_t off_n, int64_t n_new, double* d_x_new, int64_t split, double* d_x_new2,
+                                 double* d_w_new, int64_t n_global, double* d_stats_new, int32_t postselect,
+                                 int32_t retry_rounds, int64_t* d_list, int64_t* d_js_out, double* h_mirror,
+                                 double tag, void* d_ws, size_t ws_bytes, void* stream) {
+    BinMoveParams q;
+    const BinLayout L = bin_layout(n_old < 1 ? 1 : n_old, n_new < 1 ? 1 : n_new);
+    int rc = fill_move(q, model, d_x_old, n_old, d, h_mean, h_S, a, seed_n, off_n, n_new, d_x_new, split, d_x_new2,
+                       d_list, h_mirror, tag, d_ws, ws_bytes, L);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_w && d_stats, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_move: NULL weights");
+    QB_REQUIRE(!postselect || d_list, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_move: NULL invalid list");
+    QB_REQUIRE(d_w_new == nullptr || n_global >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_move: bad n_global");
+    QB_REQUIRE(retry_rounds >= 0, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_move: negative retry_rounds");
+    QB_REQUIRE((reinterpret_cast<uintptr_t>(d_x_old) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0,
+               QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_move: x_old and w must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    q.w = d_w;
+    q.stats = d_stats;
+    q.w_new = d_w_new;
+    q.w_value = (n_global >= 1) ? 1.0 / static_cast<double>(n_global) : 0.0;
+    q.stats_new = d_stats_new;
+    q.n_global = static_cast<double>(n_global);
+    q.js_out = d_js_out;
+    q.postselect = postselect ? 1 : 0;
+    q.seed_v = seed_v;
+    q.off_v = off_v;
+    const size_t smem = static_cast<size_t>(BIN) * (1 + d) * sizeof(double);
+    static const bin_kernel_t kernels[4] = {binned_move_kernel<1>, binned_move_kernel<2>, binned_move_kernel<3>,
+                                            binned_move_kernel<4>};
+    static int per_sm_cache[4] = {0, 0, 0, 0};
+    if (per_sm_cache[d - 1] == 0) {
+        QB_CUDA_CHECK(cudaFuncSetAttribute(kernels[d - 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        int occ = 0;
+        QB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernels[d - 1], BIN_THREADS, smem));
+        per_sm_cache[d - 1] = occ < 1 ? 1 : occ;
+    }
+    const int grid = bin_grid(L.max_segs, per_sm_cache[d - 1]);
+    kernels[d - 1]<<<grid, BIN_THREADS, smem, st>>>(q);
+    QB_CUDA_CHECK(cudaGetLastError());
+    if (postselect && retry_rounds > 0) {
+        // the retry launch reads the list length on the device: queue it now, no host round trip in between
+        q.rounds = retry_rounds;
+        q.round_stride = static_cast<uint64_t>((static_cast<int64_t>(d) * n_new + 1) / 2);
+        q.off_n = off_n + q.round_stride;
+        q.mirror = (h_mirror != nullptr) ? h_mirror + 4 : nullptr;
+        return launch_retry(q, d, st);
+    }
+    return QB_OK;
+}
+
+extern "C" int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
+                                  const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
+                                  uint64_t round_stride, int32_t rounds, int64_t n_new, double* d_x_new, int64_t split,
+                                  double* d_x_new2, int64_t* d_list, double* h_mirror, double tag, void* d_ws,
+                                  size_t ws_bytes, void* stream) {
+    BinMoveParams q;
+    const BinLayout L = bin_layout(n_old < 1 ? 1 : n_old, n_new < 1 ? 1 : n_new);
+    int rc = fill_move(q, model, d_x_old, n_old, d, h_mean, h_S, a, seed_n, off_n, n_new, d_x_new, split, d_x_new2,
+                       d_list, h_mirror, tag, d_ws, ws_bytes, L);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_list && rounds >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_retry: bad arguments");
+    q.rounds = rounds;
+    q.round_stride = round_stride;
+    return launch_retry(q, d, as_stream(stream));
+}
+
+// The whole device-RNG resample queued by ONE call: pass 1 (sums, moments, Liu-West constants derived on the
+// device), pass 2 (counts), pass 3 (move, reading the constants from the workspace) and the first retry launch.
+extern "C" int qb_lw_binned_resample(const qb_model* model, const double* d_x, const double* d_w, const double* d_stats,
+                                     int64_t n_old, int32_t d, int64_t n_new, double a, double h, double zero_cov_comp,
+                                     uint64_t seed, uint64_t off_u, uint64_t off_v, uint64_t seed_n, uint64_t off_n,
+                                     double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
+                                     int32_t postselect, int32_t retry_rounds, int64_t* d_list, double* d_moments_out,
+                                     double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(n_new >= 1 && n_new < (1LL << 31) && n_old >= 1, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_resample: particle counts must lie in [1, 2^31)");
+    QB_REQUIRE(d == model->d, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_resample: d does not match the model");
+    QB_REQUIRE(h_mirror != nullptr && (reinterpret_cast<uintptr_t>(h_mirror) & 31) == 0, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_resample: needs a 32-byte aligned, device-accessible result block of 40 doubles");
+    QB_REQUIRE(ws_bytes >= bin_layout(n_old, n_new).total, QB_ERR_WORKSPACE,
+               "qb_lw_binned_resample: workspace too small");
+    rc = launch_sums(d_x, d_w, d_stats, n_old, d, d_moments_out, h_mirror, tag, d_ws, ws_bytes, stream, true, a, h,
+                     zero_cov_comp);
+    if (rc != QB_OK) return rc;
+    rc = qb_lw_binned_count(n_old, n_new, seed, off_u, d_ws, ws_bytes, stream);
+    if (rc != QB_OK) return rc;
+    return qb_lw_binned_move(model, d_x, d_w, d_stats, n_old, d, nullptr, nullptr, a, seed, off_v, seed_n, off_n, n_new,
+                             d_x_new, n_new, nullptr, d_w_new, n_global, d_stats_new, postselect, retry_rounds, d_list,
+                             nullptr, h_mirror + 32, tag, d_ws, ws_bytes, stream);
+}

@@ -73,7 +73,7 @@ class DeviceCloud(object):
             self.moments_out = torch.empty((1 + self.d + self.d * self.d,), **f64)
             self.moments_host = torch.empty((1 + self.d + self.d * self.d,), dtype=torch.float64, pin_memory=True)
             self.stats_host = torch.empty((QB_STAT_COUNT,), dtype=torch.float64, pin_memory=True)
-            self.counter = torch.zeros((2,), dtype=torch.int64, device=self.device)
+            self.counter = torch.zeros((4,), dtype=torch.int64, device=self.device)
             self.counter_host = torch.empty((2,), dtype=torch.int64, pin_memory=True)
             self.basis_dev = None
             if desc.basis is not None:
@@ -83,6 +83,13 @@ class DeviceCloud(object):
         # resample scratch, allocated lazily
         self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = self._parent_inv = None
         self._moments_event = None
+        # binned resample (qb_lw_binned_*): private zeroed workspace, invalid-slot list and a pinned mirror the
+        # kernels write their results into (moments: 32 doubles; counters: 4 doubles), allocated at first use
+        self._bin_ws = None
+        self._bin_cap = (0, 0)
+        self._bin_list = None
+        self._bin_mirror = None
+        self._bin_tag = 0
         # one control block per destination slot: the constant fields are written once
         self._ctls = [_lib.QbUpdateCtl(), _lib.QbUpdateCtl()]
         self._ctl_key = None
@@ -448,8 +455,200 @@ class DeviceCloud(object):
                                          _stream()))
         self.launches += 1
 
+    # ---- binned resample (device RNG, d <= 4): csrc/qb_binned.cu ------------------------------------------------
+    def binned_supported(self, n_new):
+        return self.d <= 4 and self.n < (1 << 31) and 1 <= int(n_new) < (1 << 31)
+
+    def _binned_scratch(self, n_new):
+        if self._bin_ws is None or self._bin_cap[0] != self.n or self._bin_cap[1] < n_new:
+            cap_new = max(int(n_new), self.n)
+            nbytes = self.lib.qb_lw_binned_workspace_bytes(self.n, cap_new)
+            self._bin_ws = torch.zeros(((nbytes + 7) // 8,), dtype=torch.float64, device=self.device)
+            self._bin_cap = (self.n, cap_new)
+            self._bin_list = torch.empty((cap_new,), dtype=torch.int64, device=self.device)
+        if self._bin_mirror is None:
+            self._bin_mirror = torch.zeros((64,), dtype=torch.float64, pin_memory=True)
+            self._bin_mirror_np = self._bin_mirror.numpy()
+
+    def preallocate_binned(self, n_new=None):
+        self._binned_scratch(self.n if n_new is None else int(n_new))
+        self.preallocate_resample_slab()
+
+    def binned_prepare(self, n_new, seed_u, off_u):
+        """Queue pass 1 + 2 of the binned resample: bin sums, moments (device buffer + pinned mirror) and the
+        multinomial counts of ``n_new`` draws.  Returns the tag ``binned_moments_wait`` polls for."""
+        self._binned_scratch(n_new)
+        self._bin_tag += 1
+        check(self.lib.qb_lw_binned_prepare(self.x.data_ptr(), self.w.data_ptr(), self.stats.data_ptr(), self.n,
+                                            self.d, int(n_new), int(seed_u) & _U64_MASK, int(off_u) & _U64_MASK,
+                                            self.moments_out.data_ptr(), self._bin_mirror.data_ptr(),
+                                            float(self._bin_tag), self._bin_ws.data_ptr(), self._bin_ws.numel() * 8,
+                                            _stream()))
+        self.launches += 2
+        return self._bin_tag
+
+    def binned_resample(self, n_new, a, h, zero_cov_comp, seed, off_u, off_v, seed_n, off_n, postselect,
+                        retry_rounds, fuse_weights, n_global=None):
+        """The whole binned resample queued by one call (moments, Liu-West constants on the device, counts, move,
+        first retry launch).  Returns the tag; poll ``binned_moments_wait`` / ``binned_flags`` for the host-side checks
+        and ``binned_counters_wait`` / ``binned_retry_wait(queued=True)`` for the result."""
+        n_new = int(n_new)
+        self._binned_scratch(n_new)
+        if self.x_alt is None or self.x_alt.shape[0] != n_new:
+            self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+        self._bin_tag += 1
+        tag = self._bin_tag
+        rounds = int(retry_rounds) if (retry_rounds and postselect) else 0
+        check(self.lib.qb_lw_binned_resample(
+            self.lib_model, self.x.data_ptr(), self.w.data_ptr(), self.stats.data_ptr(), self.n, self.d, n_new,
+            float(a), float(h), float(zero_cov_comp), int(seed) & _U64_MASK, int(off_u) & _U64_MASK,
+            int(off_v) & _U64_MASK, int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, self.x_alt.data_ptr(),
+            self.w_alt.data_ptr() if fuse_weights else None, n_new if n_global is None else int(n_global),
+            self.stats_alt.data_ptr() if fuse_weights else None, 1 if postselect else 0, rounds,
+            self._bin_list.data_ptr(), self.moments_out.data_ptr(), self._bin_mirror.data_ptr(), float(tag),
+            self._bin_ws.data_ptr(), self._bin_ws.numel() * 8, _stream()))
+        self.launches += 4 if rounds else 3
+        return tag
+
+    def binned_flags(self):
+        """(covariance flag, sqrtm error) published with the moments of the last ``binned_resample``."""
+        return int(self._bin_mirror_np[29]), float(self._bin_mirror_np[30])
+
+    def binned_sums(self):
+        """Pass 1 alone (sharded clouds: the shard masses decide this slab's offspring count)."""
+        self._binned_scratch(self.n)
+        self._bin_tag += 1
+        check(self.lib.qb_lw_binned_sums(_ptr(self.x), _ptr(self.w), _ptr(self.stats), self.n, self.d,
+                                         _ptr(self.moments_out), ctypes.c_void_p(self._bin_mirror.data_ptr()),
+                                         float(self._bin_tag), _ptr(self._bin_ws), self._bin_ws.numel() * 8,
+                                         _stream()))
+        self.launches += 1
+        return self._bin_tag
+
+    def binned_count(self, n_new, seed_u, off_u):
+        """Pass 2 alone: multinomial counts of ``n_new`` draws over the bins of the last ``binned_sums``."""
+        if self._bin_cap[1] < n_new:
+            raise _lib.QbError("binned_count: call binned_reserve(n_new) before binned_sums")
+        check(self.lib.qb_lw_binned_count(self.n, int(n_new), int(seed_u) & _U64_MASK, int(off_u) & _U64_MASK,
+                                          _ptr(self._bin_ws), self._bin_ws.numel() * 8, _stream()))
+        self.launches += 1
+
+    def _spin(self, index, tag, what, timeout_s=120.0):
+        m = self._bin_mirror_np
+        want = float(tag)
+        spins, t0 = 0, None
+        while m[index] != want:
+            spins += 1
+            if spins > 20000:
+                if t0 is None:
+                    t0 = time.perf_counter()
+                elif time.perf_counter() - t0 > timeout_s:
+                    torch.cuda.synchronize()
+                    raise _lib.QbError("timed out waiting for %s (tag %d)" % (what, tag))
+
+    def binned_moments_wait(self, tag):
+        """(sum w, mean (d,), second moment (d, d)) published by ``binned_prepare``'s first kernel."""
+        self._spin(31, tag, "the binned resample's moments")
+        d = self.d
+        out = self._bin_mirror_np[:1 + d + d * d].copy()
+        return out[0], out[1:1 + d], out[1 + d:].reshape(d, d)
+
+    def _bin_consts(self, mean, S):
+        """mean (d,) and S (d, d) as the ctypes arrays the C ABI takes (allocated once, refilled)."""
+        if getattr(self, '_bin_mean_c', None) is None:
+            self._bin_mean_c = (ctypes.c_double * 4)()
+            self._bin_S_c = (ctypes.c_double * 16)()
+        if mean is None:                 # constants derived on the device (binned_resample)
+            return None, None
+        d = self.d
+        mc, sc = self._bin_mean_c, self._bin_S_c
+        if d == 1:
+            mc[0] = float(mean[0])
+            sc[0] = float(S[0][0]) if not isinstance(S, float) else S
+        else:
+            flat = np.asarray(S, dtype=np.float64).reshape(-1)
+            for c in range(d):
+                mc[c] = float(mean[c])
+            for j in range(d * d):
+                sc[j] = float(flat[j])
+        return mc, sc
+
+    def binned_move(self, mean, S, a, seed_v, off_v, seed_n, off_n, n_new, postselect, dst=None, split=None,
+                    dst2=None, fuse_weights=False, n_global=None, js_out=None, retry_rounds=0):
+        """Pass 3: every output slot draws inside its bin, moves and is tested; with ``fuse_weights`` the new uniform
+        weights and their stats block go to the alternate weight buffer in the same launch.  ``retry_rounds`` > 0
+        (postselection only) queues the retry kernel right behind it: up to that many fresh perturbations per invalid
+        slot, round j drawing from the normal stream at ``off_n + (j + 1) * stride``, stride = (d n_new + 1) // 2.
+        Returns the tag(s) ``binned_counters_wait`` / ``binned_retry_wait`` poll for."""
+        if dst is None:
+            if self.x_alt is None or self.x_alt.shape[0] != n_new:
+                self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+            dst = self.x_alt
+        self._bin_tag += 1
+        tag = self._bin_tag
+        n_new = int(n_new)
+        n_global = n_new if n_global is None else int(n_global)
+        w_new = self.w_alt.data_ptr() if fuse_weights else None
+        st_new = self.stats_alt.data_ptr() if fuse_weights else None
+        mc, sc = self._bin_consts(mean, S)
+        stream = _stream()
+        mirror = self._bin_mirror.data_ptr()
+        lib, model, d = self.lib, self.lib_model, self.d
+        x, split = self.x.data_ptr(), int(n_new if split is None else split)
+        dst_p, dst2_p = dst.data_ptr(), (dst2.data_ptr() if dst2 is not None else None)
+        rounds = int(retry_rounds) if (retry_rounds and postselect) else 0
+        check(lib.qb_lw_binned_move(model, x, self.w.data_ptr(), self.stats.data_ptr(), self.n, d, mc, sc, float(a),
+                                    int(seed_v) & _U64_MASK, int(off_v) & _U64_MASK, int(seed_n) & _U64_MASK,
+                                    int(off_n) & _U64_MASK, n_new, dst_p, split, dst2_p, w_new, n_global, st_new,
+                                    1 if postselect else 0, rounds, self._bin_list.data_ptr(),
+                                    js_out.data_ptr() if js_out is not None else None, mirror + 32 * 8, float(tag),
+                                    self._bin_ws.data_ptr(), self._bin_ws.numel() * 8, stream))
+        self.launches += 2 if rounds else 1
+        return (tag, tag) if rounds else tag
+
+    def binned_retry(self, mean, S, a, seed_n, off_n, n_new, rounds=1, dst=None, split=None, dst2=None):
+        """Up to ``rounds`` more perturbations per still-invalid slot of the last move (round j: normal stream at
+        ``off_n + j * stride``)."""
+        dst = self.x_alt if dst is None else dst
+        self._bin_tag += 1
+        mc, sc = self._bin_consts(mean, S)
+        n_new = int(n_new)
+        stride = (self.d * n_new + 1) // 2
+        check(self.lib.qb_lw_binned_retry(self.lib_model, self.x.data_ptr(), self.n, self.d, mc, sc, float(a),
+                                          int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, stride, int(rounds), n_new,
+                                          dst.data_ptr(), int(n_new if split is None else split),
+                                          dst2.data_ptr() if dst2 is not None else None, self._bin_list.data_ptr(),
+                                          self._bin_mirror.data_ptr() + 40 * 8,
+                                          float(self._bin_tag), self._bin_ws.data_ptr(), self._bin_ws.numel() * 8,
+                                          _stream()))
+        self.launches += 1
+        return self._bin_tag
+
+    def binned_counters_wait(self, tag):
+        """(#invalid, #clamped draws, #drawn) of the move launch ``tag`` (from the pinned mirror)."""
+        self._spin(32 + 3, tag, "the binned resample's move kernel")
+        m = self._bin_mirror_np
+        return int(m[32]), int(m[33]), int(m[34])
+
+    def binned_retry_wait(self, tag, queued=False):
+        """(#still invalid, most rounds used, list length) of a retry launch: ``queued`` = the one ``binned_move`` queued
+        behind itself (it reports next to the move's block, under the move's tag)."""
+        base = 36 if queued else 40
+        self._spin(base + 3, tag, "the binned resample's retry kernel")
+        m = self._bin_mirror_np
+        return int(m[base]), int(m[base + 1]), int(m[base + 2])
+
+    def adopt_binned(self, n_new, weights_fused):
+        """Make the slab the binned move wrote current.  With fused weights the alternate weight/stats buffers already
+        hold 1/n and its stats block: flip the ping-pong index instead of launching the fill kernel."""
+        if n_new != self.n or not weights_fused:
+            return self.adopt_resampled(n_new)
+        self.x, self.x_alt = self.x_alt, self.x
+        self.cur = 1 - self.cur
+        self._chain_tag = 0
+
     def read_counter(self):
-        self.counter_host.copy_(self.counter, non_blocking=True)
+        self.counter_host.copy_(self.counter[:2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return int(self.counter_host[0]), int(self.counter_host[1])
 

@@ -22,12 +22,15 @@ Two extra, keyword-only knobs that the reference does not have:
           ``seed``) for throughput.
 ``scan``  ``'exact'`` (default) reproduces ``np.cumsum``'s sequential fp64
           rounding bit for bit; ``'fast'`` is a re-associated parallel scan.
-``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'guided'``: i.i.d. order through the guide table,
+``draw``  device-RNG mode with ``scan='fast'`` and d <= 4 only.  ``'binned'``: the multinomial draw factorised into
+          counts per bin of 2048 particles + i.i.d. draws inside each bin from a shared-memory CDF; moments, counts,
+          draw, move and the new weights in three streaming launches (csrc/qb_binned.cu); same law as the
+          reference's draw, offspring grouped by parent bin, a retry re-centres on the particle's own parent.
+          ``'guided'``: i.i.d. order through the guide table,
           bit-identical to the staged launches (incl. the reference's prefix-``mus`` retry quirk).  ``'merge'``: the
           uniforms are generated already sorted (exponential spacings, a scan), so the draw streams the CDF and
           the parents once instead of bisecting at random; the new particles come out ordered by parent and a
-          retry re-centres on the particle's own parent.  ``'auto'`` (default): guided below 3.2e7 particles per
-          cloud, merge above (measured cross-over between 1e7 and 1e8).
+          retry re-centres on the particle's own parent.  ``'auto'`` (default): binned.
 """
 import abc
 import os
@@ -38,7 +41,7 @@ import scipy.linalg
 import torch
 
 from . import _lib
-from ._exceptions import ResamplerError, ResamplerWarning
+from ._exceptions import ApproximationWarning, ResamplerError, ResamplerWarning
 from .distributions import ParticleDistribution, covariance_from_moments
 
 
@@ -56,7 +59,7 @@ def sqrtm_psd(A, est_error=True, check_finite=True):
         root = np.sqrt(A[0, 0]) if A[0, 0] > 0 else 0.0
         A_sqrt = np.array([[root]], dtype=np.float64)
         if est_error:
-            return A_sqrt, np.linalg.norm(np.dot(A_sqrt, A_sqrt) - A, 'fro')
+            return A_sqrt, abs(root * root - A[0, 0])        # the Frobenius norm of a 1 x 1 matrix
         return A_sqrt
     w, v = scipy.linalg.eigh(A, check_finite=check_finite)
     w[w <= 0] = 0
@@ -65,6 +68,17 @@ def sqrtm_psd(A, est_error=True, check_finite=True):
     if est_error:
         return A_sqrt, np.linalg.norm(np.dot(A_sqrt, A_sqrt) - A, 'fro')
     return A_sqrt
+
+
+def _cov_1x1(mean, second_moment):
+    """``covariance_from_moments`` for one model parameter: the same product, difference and tests as
+    distributions.py:388-397 without the array machinery (the eigenvalue of a 1 x 1 matrix is its entry)."""
+    c = second_moment[0, 0] - mean[0] * mean[0]
+    assert np.isfinite(c)
+    if not c >= 0:
+        warnings.warn('Numerical error in covariance estimation causing positive semidefinite violation.',
+                      ApproximationWarning)
+    return np.array([[c]])
 
 
 class Resampler(abc.ABC):
@@ -77,9 +91,10 @@ class DeviceParticles(object):
     """What the device path of a resampler returns: the new particles are already
     in the cloud's alternate slab; host arrays are produced only on request."""
 
-    def __init__(self, cloud, n_particles):
+    def __init__(self, cloud, n_particles, weights_fused=False):
         self.cloud = cloud
         self.n_particles = int(n_particles)
+        self.weights_fused = bool(weights_fused)   # the alternate weight buffer already holds 1/n and its stats
 
     @property
     def particle_weights(self):
@@ -117,8 +132,8 @@ class LiuWestResampler(Resampler):
             raise ValueError("a custom perturbation kernel needs rng='numpy' (it is a host callable)")
         if draw is None:
             draw = os.environ.get("QB_DRAW", "auto")        # (environment override: A/B runs of the bench)
-        if draw not in ('auto', 'merge', 'guided'):
-            raise ValueError("draw must be 'auto', 'merge' or 'guided'")
+        if draw not in ('auto', 'binned', 'merge', 'guided'):
+            raise ValueError("draw must be 'auto', 'binned', 'merge' or 'guided'")
         self._rng = rng
         self._scan = scan
         self._draw = draw       # device-RNG mode only: sorted uniforms + streaming merge, or i.i.d. order + guide table
@@ -231,6 +246,97 @@ class LiuWestResampler(Resampler):
             n_invalid, _ = cloud.read_counter()
         return n_iters, n_invalid
 
+    def _binned_offsets(self, n_particles):
+        """Philox stream positions of one binned resample: bin-locating uniforms, in-bin uniforms, then normals."""
+        off_u = self._philox_offset
+        off_v = off_u + (n_particles + 1) // 2
+        self._philox_offset = off_v + (n_particles + 1) // 2
+        return off_u, off_v
+
+    RETRY_ROUNDS = 8        # perturbations per invalid particle and retry launch (binned draw)
+
+    def _binned_plan(self, d, n_particles):
+        """Philox positions of the move's normals and of the queued retry rounds; advances the stream."""
+        stride = (d * n_particles + 1) // 2
+        off_n = self._philox_offset
+        self._philox_offset += stride
+        rounds = 0
+        if self._postselect and self._maxiter > 1:
+            rounds = max(1, min(self.RETRY_ROUNDS, self._maxiter - 1))
+            self._philox_offset += rounds * stride
+        return stride, off_n, rounds
+
+    def _binned_finish(self, cloud, tag, rounds, stride, mean, S, a, n_particles, seed_n, dst=None, split=None,
+                       dst2=None):
+        """Wait for the move (and the retry launch queued behind it), then run the rest of the postselection loop of
+        resamplers.py:327-372 if anything is still invalid (rare: 8 rounds have already run on the device)."""
+        if rounds:
+            n_invalid, used, listed = cloud.binned_retry_wait(tag, queued=True)
+            _, self.last_overflow, drawn = cloud.binned_counters_wait(tag)
+            n_iters = 1 + (used if listed else 0)
+        else:
+            n_invalid, self.last_overflow, drawn = cloud.binned_counters_wait(tag)
+            n_iters = 1
+            if not self._postselect:
+                n_invalid = 0
+        if drawn != n_particles:
+            raise _lib.QbError("binned resample drew %d offspring, expected %d" % (drawn, n_particles))
+        while n_invalid and n_iters < self._maxiter:
+            more = min(self.RETRY_ROUNDS, self._maxiter - n_iters)
+            off_n = self._philox_offset
+            self._philox_offset += more * stride
+            t2 = cloud.binned_retry(mean, S, a, seed_n, off_n, n_particles, more, dst=dst, split=split, dst2=dst2)
+            n_invalid, used, _ = cloud.binned_retry_wait(t2)
+            n_iters += used if n_invalid == 0 else more
+        return n_iters, n_invalid
+
+    def _binned_move(self, cloud, mean, S, a, n_particles, off_v, seed=None, fuse_weights=False, n_global=None,
+                     dst=None, split=None, dst2=None):
+        """Pass 3 of the binned resample with host-supplied constants (precomputed moments, sharded clouds) + the
+        postselection loop.  The first retry launch is queued behind the move without a host round trip."""
+        seed = self._seed if seed is None else int(seed)
+        seed_n = seed ^ 0x9E3779B97F4A7C15
+        stride, off_n, rounds = self._binned_plan(cloud.d, n_particles)
+        tags = cloud.binned_move(mean, S, a, seed, off_v, seed_n, off_n, n_particles, self._postselect, dst=dst,
+                                 split=split, dst2=dst2, fuse_weights=fuse_weights, n_global=n_global,
+                                 retry_rounds=rounds)
+        tag = tags[0] if rounds else tags
+        return self._binned_finish(cloud, tag, rounds, stride, mean, S, a, n_particles, seed_n, dst=dst, split=split,
+                                   dst2=dst2)
+
+    def _binned_device(self, cloud, n_particles, fuse_weights):
+        """The whole binned resample with NO host decision between its launches: the Liu-West constants (covariance,
+        zero-norm replacement, matrix square root, shifted mean) are derived by the first kernel's last block.  The
+        host reads the moments when they are published and performs the reference's CHECKS (finite assert and PSD
+        warning of distributions.py:388-397, zero-norm warning of resamplers.py:288-293, ResamplerError of :296-299)
+        while the device is already drawing."""
+        d = cloud.d
+        seed, seed_n = self._seed, self._seed ^ 0x9E3779B97F4A7C15
+        off_u, off_v = self._binned_offsets(n_particles)
+        stride, off_n, rounds = self._binned_plan(d, n_particles)
+        tag = cloud.binned_resample(n_particles, self._a, self._h, self._zero_cov_comp, seed, off_u, off_v, seed_n,
+                                    off_n, self._postselect, rounds, fuse_weights)
+        _, mean, m2 = cloud.binned_moments_wait(tag)
+        flag, s_err = cloud.binned_flags()
+        _cov_1x1(mean, m2) if d == 1 else covariance_from_moments(mean, m2)
+        if flag == 1:
+            warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
+                          "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
+        if not np.isfinite(s_err):
+            raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
+                                 "Check that n_ess is not too small.")
+        return self._binned_finish(cloud, tag, rounds, stride, None, None, self._a, n_particles, seed_n)
+
+    def _binned_return(self, cloud, on_device, n_particles, n_iters, n_invalid, weights_fused):
+        if n_invalid:
+            warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                           "iterations.").format(n_invalid, self._maxiter), ResamplerWarning)
+        self.last_n_iters = n_iters
+        if on_device:
+            return DeviceParticles(cloud, n_particles, weights_fused)
+        return ParticleDistribution(particle_locations=cloud.x_alt.cpu().numpy(),
+                                    particle_weights=np.ones((n_particles,)) / n_particles)
+
     # -- the call ------------------------------------------------------------------
     def __call__(self, model, particle_dist, n_particles=None, precomputed_mean=None, precomputed_cov=None):
         from .engine import DeviceCloud
@@ -248,10 +354,26 @@ class LiuWestResampler(Resampler):
             n_particles = (particle_dist.n_particles if self._default_n_particles is None
                            else self._default_n_particles)
         n_particles = int(n_particles)
-        fused = (self._rng == 'philox' and self._scan == 'fast' and cloud.d <= 4 and n_particles <= cloud.n
-                 and self._fused)
+        device_rng = self._rng == 'philox' and self._scan == 'fast' and self._fused
+        binned = device_rng and self._draw in ('auto', 'binned') and cloud.binned_supported(n_particles)
+        fused = device_rng and not binned and cloud.d <= 4 and n_particles <= cloud.n
         cdf_done = False
-        if on_device and precomputed_mean is None and precomputed_cov is None:
+        if binned and precomputed_mean is None and precomputed_cov is None:
+            weights_fused = on_device and n_particles == cloud.n
+            n_iters, n_invalid = self._binned_device(cloud, n_particles, weights_fused)
+            return self._binned_return(cloud, on_device, n_particles, n_iters, n_invalid, weights_fused)
+        if binned:
+            # precomputed moments: pass 1 + 2 are queued at once, the host takes the matrix square root of the given
+            # covariance while they run
+            off_u, off_v = self._binned_offsets(n_particles)
+            tag = cloud.binned_prepare(n_particles, self._seed, off_u)
+            if precomputed_mean is None and precomputed_cov is None:
+                _, mean, m2 = cloud.binned_moments_wait(tag)
+                cov = _cov_1x1(mean, m2) if cloud.d == 1 else covariance_from_moments(mean, m2)
+            else:
+                mean = particle_dist.est_mean() if precomputed_mean is None else precomputed_mean
+                cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
+        elif on_device and precomputed_mean is None and precomputed_cov is None:
             cloud.moments_begin()                            # one pass gives both (resamplers.py:266-273)
             if fused:
                 # the CDF (+ guide) pass does not need the moments: queue it now, so that the device is busy while
@@ -265,7 +387,7 @@ class LiuWestResampler(Resampler):
             cov = particle_dist.est_covariance_mtx() if precomputed_cov is None else precomputed_cov
 
         a, h = self._a, self._h
-        if scipy.linalg.norm(cov, 'fro') == 0:
+        if (cov[0, 0] == 0) if cov.shape == (1, 1) else (scipy.linalg.norm(cov, 'fro') == 0):
             warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
                           "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
             cov = self._zero_cov_comp * np.eye(cov.shape[0])
@@ -275,7 +397,11 @@ class LiuWestResampler(Resampler):
                                  "Check that n_ess is not too small.")
         S = np.real(h * S)
 
-        if fused:
+        weights_fused = False
+        if binned:
+            weights_fused = on_device and n_particles == cloud.n
+            n_iters, n_invalid = self._binned_move(cloud, mean, S, a, n_particles, off_v, fuse_weights=weights_fused)
+        elif fused:
             n_iters, n_invalid = self._fused_pass(cloud, mean, S, a, n_particles, build_cdf=not cdf_done)
         else:
             n_iters, n_invalid = self._staged_pass(cloud, mean, S, a, n_particles)
@@ -285,6 +411,6 @@ class LiuWestResampler(Resampler):
         self.last_n_iters = n_iters
 
         if on_device:
-            return DeviceParticles(cloud, n_particles)
+            return DeviceParticles(cloud, n_particles, weights_fused)
         return ParticleDistribution(particle_locations=cloud.x_alt.cpu().numpy(),
                                     particle_weights=np.ones((n_particles,)) / n_particles)

@@ -531,7 +531,7 @@ class SMCUpdater(object):
 
         new_dist = self.resampler(self.model, self)
         if isinstance(new_dist, DeviceParticles) and new_dist.cloud is self._cloud:
-            self._cloud.adopt_resampled(new_dist.n_particles)
+            self._cloud.adopt_binned(new_dist.n_particles, getattr(new_dist, 'weights_fused', False))
             # uniform weights 1/n: the stats block the kernel wrote is {norm 1, sumsq 1/n}; same two roundings here,
             # without a device read
             self._n_ess = self._ness_from(1.0, np.float64(1.0) / np.float64(new_dist.n_particles), normalised=True)

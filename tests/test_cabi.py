@@ -35,7 +35,7 @@ def test_binding_covers_every_declared_symbol_and_loads():
     from qinfer_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared_symbols()
     lib = _lib.load()
-    assert lib.qb_abi_version() == _lib.QB_ABI_VERSION == 2
+    assert lib.qb_abi_version() == _lib.QB_ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header():
