@@ -222,7 +222,7 @@ __device__ void liu_west_consts(const double* out /* 1 + D + D*D moments */, dou
             const double df = v - cov[m][c];
             e2 += df * df;
         }
-    err = (D == 1) ? fabs(S0[0][0] * S0[0][0] - cov[0][0]) : sqrt(e2);
+    err = sqrt(e2);   // (overflows to inf where np.linalg.norm's x.dot(x) does: the reference then raises)
     for (int j = 0; j < 16; ++j) consts[j] = 0.0;
 #pragma unroll
     for (int m = 0; m < D; ++m)

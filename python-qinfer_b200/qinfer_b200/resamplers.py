@@ -59,7 +59,7 @@ def sqrtm_psd(A, est_error=True, check_finite=True):
         root = np.sqrt(A[0, 0]) if A[0, 0] > 0 else 0.0
         A_sqrt = np.array([[root]], dtype=np.float64)
         if est_error:
-            return A_sqrt, abs(root * root - A[0, 0])        # the Frobenius norm of a 1 x 1 matrix
+            return A_sqrt, np.linalg.norm(np.dot(A_sqrt, A_sqrt) - A, 'fro')
         return A_sqrt
     w, v = scipy.linalg.eigh(A, check_finite=check_finite)
     w[w <= 0] = 0
