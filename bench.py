@@ -11,13 +11,23 @@ whole Liu-West resample whenever n_ess < N/2 — 10 to 20 times per 1000 steps).
 Metric: particle-updates/s = particles x steps / time, reference convention of
 qinfer/perf_testing.py:250-251 (only ``update`` is timed; prior sampling is not).
 
-  value  inputs resident in HBM, timed with CUDA events around the K update calls.
+  value  inputs resident in HBM, timed with CUDA events around the K update calls
+         (throughput mode: device Philox RNG, binned multinomial draw, lazy host settlement).
   e2e    the same K updates through the public API starting from HOST arrays: the
-         host->device upload of the prior sample and the device->host read-back of the
-         posterior (locations, weights, mean) are inside the timed region, as are the
-         per-step scalar exchanges (experiment record in, normalisation/n_ess out).
+         host->device upload of the prior sample (page-locked), the per-step scalar
+         exchanges (experiment record in, normalisation/n_ess out) and the device->host read
+         of the posterior mean are inside the timed region; the read-back of the whole
+         posterior cloud is timed too and reported as a phase (`with_posterior_readback`).
   roofline  fused-update kernel only: algorithmic bytes 8(d+2) per particle
-         over its average device duration, measured with CUDA events around each launch.
+         over its average device duration; `traffic` = DRAM bytes of one launch from the newest
+         committed `ncu --set full` capture (named), `dram_frac` = that traffic over the same time.
+  parity_mode  the same K steps with rng='mt19937', scan='exact' (resample indices bit-identical
+         to the reference under a legacy seed): what the bit-exact guarantee costs.
+  north_star_1e8  N = 10^8 particles on one GPU, 200 steps (BASELINE.json north_star's target).
+  c5     (8 GPUs) the same K steps at 1.25e7 particles per GPU = N = 10^8 over the box.
+  check  in-run correctness: the parity-mode updater against the CPU baseline's posterior on the
+         shared prefix of the schedule (1e-6), the throughput-mode updater within 5 standard errors;
+         sharded_check (N > 1): sharded cloud against a single-GPU run of the same cloud.
   cpu_baseline  the NumPy oracle port of the reference, timed on this host on a bounded
          sample of the same workload (first updates of the schedule incl. the resamples).
 
@@ -43,7 +53,10 @@ for _p in (os.path.join(ROOT, "python-qinfer_b200"), os.path.join(ROOT, "oracle"
 METRIC = "particle_updates_per_sec"
 UNIT = "particle-updates/s"
 PARTICLES_PER_GPU = 10 ** 7
+C5_PARTICLES_PER_GPU = 10 ** 8 // 8
 TRUE_OMEGA = 0.5
+PREFIX_STEPS = 14            # the CPU baseline's sample: the first updates of the schedule at the full particle count
+PROCESS_WARMUP_STEPS = 30
 
 
 # ---------------------------------------------------------------------------
@@ -73,6 +86,12 @@ class FixedPrior(object):
 
     def sample(self, n=1):
         return self._s
+
+
+def drive(up, ts, outcomes, lo, hi):
+    """Steps lo .. hi-1 of the workload through the public API (one ``update`` per datum)."""
+    for k in range(lo, hi):
+        up.update(int(outcomes[k]), ts[k:k + 1])
 
 
 # ---------------------------------------------------------------------------
@@ -132,7 +151,8 @@ class ClockSampler(object):
 
 def ncu_traffic(n):
     """DRAM bytes (read + write) of ONE fused-update launch from the newest committed `ncu --set full` summary under
-    profiles/ (captured at 10^7 particles; scaled linearly to n), or (None, why)."""
+    profiles/ (captured at 10^7 particles; scaled linearly to n), or (None, why).  The capture is named in the
+    output so that a reader can tell which build it describes."""
     import csv
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*fused_update_K1_ncu_full.csv")), key=os.path.basename)
@@ -146,8 +166,8 @@ def ncu_traffic(n):
                 vals[row[0]] = float(row[2]) * scale
     if len(vals) != 2:
         return None, "dram metrics missing in %s" % os.path.basename(files[-1])
-    return sum(vals.values()) * (n / 1e7), "ncu --set full, profiles/%s (captured at n=1e7, scaled by n)" % \
-        os.path.basename(files[-1])
+    return sum(vals.values()) * (n / 1e7), "ncu --set full capture profiles/%s (n=1e7, flushed L2, scaled by n); not " \
+        "re-measured in this run" % os.path.basename(files[-1])
 
 
 def measured_peak_gbs():
@@ -175,7 +195,7 @@ def run_oracle(n, ts, outcomes, prior, seed=0):
             t0 = time.perf_counter()
             up.update(int(outcomes[k]), np.array([ts[k]]))
             step_times.append(time.perf_counter() - t0)
-    return step_times, up.resample_count
+    return step_times, up
 
 
 def cpu_threads():
@@ -185,16 +205,37 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def workload_text(n_per_gpu, world):
+    return ("C2 SimplePrecessionModel, %d particles/GPU x %d GPU, t_k=(9/8)^(k mod 100), LiuWest a=0.98, "
+            "resample_thresh 0.5" % (n_per_gpu, world))
+
+
+def workload_config(n_per_gpu, world):
+    return {"workload": workload_text(n_per_gpu, world),
+            "particles_per_gpu": n_per_gpu, "n_modelparams": 1,
+            "l2_policy": "inputs larger than L2: each update streams 240 MB (x, w in, w out) through a 126 MB L2",
+            "resampler": "rng=philox (device), scan=fast, draw=binned (multinomial counts per bin of 2048 + in-bin "
+                         "draws from a shared-memory CDF)",
+            "updater": "lazy=True (speculative launch pipelining)"}
+
+
+def reference_config(n, world):
+    return {"workload": workload_text(PARTICLES_PER_GPU, world),
+            "particles_per_gpu": PARTICLES_PER_GPU, "particles_timed": n, "n_modelparams": 1,
+            "resampler": "the reference's: np.random (legacy MT19937) uniforms + np.cumsum + searchsorted + randn, host",
+            "updater": "the reference's call-by-call SMCUpdater.update (NumPy port, single process)"}
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
     # bound the CPU work: ~55 ns per particle-update incl. amortised resamples (BASELINE.md probes)
     budget_s = 150.0
-    n = int(min(PARTICLES_PER_GPU, max(10 ** 5, budget_s / ((steps + warm) * 5.5e-8))))
+    n = int(min(PARTICLES_PER_GPU, max(10 ** 5, budget_s / (max(steps + warm, 1) * 5.5e-8))))
     ts, outcomes = make_data(steps + warm)
     prior = make_prior(n, 99)
-    times, n_res = run_oracle(n, ts, outcomes, prior)
+    times, up = run_oracle(n, ts, outcomes, prior)
     timed = times[warm:]
     total = float(np.sum(timed))
     value = n * steps / total
@@ -202,253 +243,427 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n, 1),
+        "config": reference_config(n, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                          "sample": "NumPy oracle port of qinfer.SMCUpdater+LiuWestResampler; each step = one update "
                                    "of a %d-particle sample (of the 10^7 workload), %d steps, %d resamples; NumPy "
                                    "ufunc loops are single-threaded, BLAS dot may use %d threads"
-                                   % (n, steps, n_res, cpu_threads())},
+                                   % (n, steps, up.resample_count, cpu_threads())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(n_per_gpu, world):
-    return {"workload": "C2 SimplePrecessionModel, %d particles/GPU x %d GPU, t_k=(9/8)^(k mod 100), "
-                        "LiuWest a=0.98, resample_thresh 0.5" % (n_per_gpu, world),
-            "particles_per_gpu": n_per_gpu, "n_modelparams": 1,
-            "l2_policy": "inputs larger than L2: each update streams 240 MB (x, w in, w out) through a 126 MB L2",
-            "resampler": "rng=philox (device), scan=fast, draw=auto (guided below 3.2e7 particles, merge above)", "updater": "lazy=True (speculative launch pipelining)"}
+def cpu_baseline(n):
+    """Oracle on the first PREFIX_STEPS updates of the same workload at the full particle count (incl. the
+    resamples they trigger): ~15-25 s of single-process NumPy.  Also returns the posterior the GPU arm checks
+    itself against."""
+    m = PREFIX_STEPS
+    ts, outcomes = make_data(m)
+    prior = make_prior(n, 99)
+    times, up = run_oracle(n, ts, outcomes, prior)
+    total = float(np.sum(times))
+    rec = {"value": n * m / total, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+           "sample": "NumPy oracle port, first %d updates of the schedule at N=%d incl. %d resamples, %.1f s"
+                     % (m, n, up.resample_count, total)}
+    post = {"mean": float(up.est_mean()[0]), "cov": float(up.est_covariance_mtx()[0, 0]), "n_ess": float(up.n_ess),
+            "resample_count": int(up.resample_count),
+            "normalization_record": [float(np.ravel(v)[0]) for v in up.normalization_record]}
+    return rec, post
 
 
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-def gpu_arm(args, rank, world, local_rank):
-    import torch
-    import qinfer_b200 as qb
-    from qinfer_b200 import _lib
+class CudaBackend(object):
+    """Everything of the GPU arm that touches torch / the engine, behind a small surface so that the arm's data and
+    indexing logic can be driven on CPU by a test double (tests/test_bench_contract.py)."""
 
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl")
+    def __init__(self, local_rank, world):
+        import torch
+        import qinfer_b200 as qb
+        self.torch, self.qb, self.world = torch, qb, world
+        torch.cuda.set_device(local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl")
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def resampler(self, mode, seed):
+        if mode == 'parity':
+            return self.qb.LiuWestResampler(a=0.98, rng='mt19937', scan='exact')
+        return self.qb.LiuWestResampler(a=0.98, rng='philox', seed=seed, scan='fast')
+
+    def new_updater(self, n, prior, mode='throughput', fuse=1, seed=1000, sharded=None, lazy=True):
+        qb = self.qb
+        sharded = (self.world > 1) if sharded is None else sharded
+        res = self.resampler(mode, seed)
+        if sharded:
+            from qinfer_b200.sharded import ShardedSMCUpdater
+            up = ShardedSMCUpdater(qb.SimplePrecessionModel(), n * self.world, FixedPrior(prior), resampler=res,
+                                   lazy=lazy, fuse=fuse)
+        else:
+            up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, FixedPrior(prior), resampler=res, lazy=lazy, fuse=fuse)
+        cloud = up._cloud
+        if mode == 'parity':
+            cloud.preallocate_resample()
+        else:
+            cloud.preallocate_binned()
+        return up
+
+    def pinned(self, array):
+        t = self.torch.empty(array.shape, dtype=self.torch.float64, pin_memory=True)
+        t.numpy()[:] = array
+        return t
+
+    def timer(self):
+        torch = self.torch
+
+        class T(object):
+            def start(self):
+                self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+            def stop(self):
+                self.b.record()
+
+            def ms(self):
+                torch.cuda.synchronize()
+                return self.a.elapsed_time(self.b)
+        return T()
+
+    def collect_resample_events(self, up):
+        up._cloud.resample_events = []
+
+    def resample_ms(self, up):
+        return [a.elapsed_time(b) for a, b in up._cloud.resample_events]
+
+    def launch_counts(self, up):
+        return up._cloud.launches, up._cloud.update_launches
+
+    def close(self, up):
+        if hasattr(up, 'close'):
+            try:
+                up.close()
+            except Exception:
+                pass
+
+    def reduce(self, values, op="max"):
+        if self.dist is None:
+            return list(values)
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def finish(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def process_warmup(be, prior):
+    """Not a step of the workload: run a small cloud through updates AND resamples once so that every kernel of
+    the path is loaded (CUDA loads modules lazily at first launch) before anything is timed.  Uses its own data,
+    independent of --steps / --warmup."""
+    nsmall = min(65536, prior.shape[0])
+    wts, wout = make_data(PROCESS_WARMUP_STEPS, seed=7)
+    for mode in (('throughput', 'parity') if be.world == 1 else ('throughput',)):
+        small = be.new_updater(nsmall, prior[:nsmall], mode=mode, seed=5)
+        if mode == 'parity':
+            np.random.seed(123)
+        drive(small, wts, wout, 0, PROCESS_WARMUP_STEPS)
+        small.est_mean()
+        be.close(small)
+        del small
+
+
+def timed_run(be, n, prior, ts, outcomes, warm, steps, mode='throughput', fuse=1, seed=1000, clocks=None):
+    """W untimed warm-up steps, then exactly K timed steps between barriers; device time by CUDA events."""
+    up = be.new_updater(n, prior, mode=mode, fuse=fuse, seed=seed)
+    if mode == 'parity':
+        np.random.seed(0)
+    drive(up, ts, outcomes, 0, warm)
+    up._flush()
+    be.collect_resample_events(up)
+    l0, u0 = be.launch_counts(up)
+    r0 = up.resample_count
+    if clocks is not None:
+        clocks.start()
+        time.sleep(0.35)                             # let nvidia-smi take its first samples
+    be.barrier()
+    gc.collect()
+    gc.disable()                                     # no collector pauses inside the timed region (host hygiene)
+    t = be.timer()
+    t.start()
+    drive(up, ts, outcomes, warm, warm + steps)
+    up._flush()                                      # settle the last (lazily pending) step
+    t.stop()
+    be.barrier()
+    gc.enable()
+    elapsed_ms = t.ms()
+    clk = clocks.stop() if clocks is not None else None
+    l1, u1 = be.launch_counts(up)
+    res_each = be.resample_ms(up)
+    out = {"elapsed_ms": elapsed_ms, "launches": l1 - l0, "update_launches": u1 - u0,
+           "resamples": up.resample_count - r0, "resample_ms_each": res_each, "clocks": clk,
+           "posterior_mean": float(up.est_mean()[0]), "n_ess": float(up.n_ess)}
+    be.close(up)
+    del up
+    gc.collect()
+    return out
+
+
+def e2e_run(be, n, pinned_prior, ts, outcomes, warm, steps, fuse=1, seed=1000):
+    """From HOST arrays through the public API: prior upload (page-locked source), K updates, posterior mean read;
+    then the read-back of the whole posterior cloud, timed separately."""
+    prior = pinned_prior.numpy()
+    be.barrier()
+    t0 = time.perf_counter()
+    t = be.timer()
+    t.start()
+    up = be.new_updater(n, prior, fuse=fuse, seed=seed)    # H2D of the n x 1 prior sample happens here
+    be.sync()
+    t_setup = time.perf_counter() - t0
+    drive(up, ts, outcomes, warm, warm + steps)
+    up._flush()
+    mean = up.est_mean()                                    # D2H of the result the caller asks for
+    t.stop()
+    t_core = time.perf_counter() - t0
+    locs = up.particle_locations                            # D2H of the whole posterior (a user who plots it)
+    wts = up.particle_weights
+    t_total = time.perf_counter() - t0
+    be.barrier()
+    core_ms = max(t.ms(), 1e3 * t_core)
+    assert locs.shape[0] == n and wts.shape[0] == n and np.isfinite(mean).all()
+    be.close(up)
+    del up, locs, wts
+    gc.collect()
+    return {"core_ms": core_ms, "setup_and_h2d_ms": 1e3 * t_setup, "updates_ms": 1e3 * (t_core - t_setup),
+            "posterior_readback_ms": 1e3 * (t_total - t_core), "with_readback_ms": 1e3 * t_total}
+
+
+def prefix_check(be, n, post):
+    """The GPU path against the CPU baseline's posterior after the shared prefix of the schedule, from the same prior:
+    parity mode (legacy MT19937 stream on the device + exact scan) must agree to 1e-6 (north_star) and take the same
+    number of resamples; throughput mode (Philox, binned draw) must be statistically consistent."""
+    ts, outcomes = make_data(PREFIX_STEPS)
+    prior = make_prior(n, 99)
+    out = {}
+    up = be.new_updater(n, prior, mode='parity', fuse=1, sharded=False, lazy=False)
+    np.random.seed(0)
+    drive(up, ts, outcomes, 0, PREFIX_STEPS)
+    mean, cov = float(up.est_mean()[0]), float(up.est_covariance_mtx()[0, 0])
+    norm = np.array([float(np.ravel(v)[0]) for v in up.normalization_record])
+    out["parity_mean_rel_err"] = abs(mean - post["mean"]) / abs(post["mean"])
+    out["parity_cov_rel_err"] = abs(cov - post["cov"]) / abs(post["cov"])
+    out["parity_norm_record_max_rel_err"] = float(np.max(np.abs(norm / np.array(post["normalization_record"]) - 1)))
+    out["parity_resample_count"] = [int(up.resample_count), post["resample_count"]]
+    be.close(up)
+    del up
+    up = be.new_updater(n, prior, mode='throughput', fuse=1, sharded=False)
+    drive(up, ts, outcomes, 0, PREFIX_STEPS)
+    mean_t, ess_t = float(up.est_mean()[0]), float(up.n_ess)
+    se = np.sqrt(post["cov"] / max(post["n_ess"], 1.0) + post["cov"] / max(ess_t, 1.0))
+    out["throughput_mean_sigmas"] = abs(mean_t - post["mean"]) / se
+    out["throughput_resample_count"] = [int(up.resample_count), post["resample_count"]]
+    be.close(up)
+    del up
+    out["tolerance"] = "parity: 1e-6 relative on mean and covariance, equal resample count; throughput: 5 standard errors"
+    out["ok"] = bool(out["parity_mean_rel_err"] < 1e-6 and out["parity_cov_rel_err"] < 1e-6 and
+                     out["parity_norm_record_max_rel_err"] < 1e-9 and
+                     out["parity_resample_count"][0] == out["parity_resample_count"][1] and
+                     out["throughput_mean_sigmas"] < 5.0)
+    return out
+
+
+def sharded_check(be, rank, world):
+    """N > 1: a small sharded cloud against a single-GPU run of the same cloud on rank 0 — records and n_ess up to the
+    first resample to 1e-10 (different summation order), posterior mean within 5 standard errors at the end."""
+    n_local, m = 131072, 40
+    ts, outcomes = make_data(m, seed=77)
+    full = make_prior(n_local * world, 4242)
+    up = be.new_updater(n_local, full[rank * n_local:(rank + 1) * n_local], seed=31 + rank)
+    drive(up, ts, outcomes, 0, m)
+    rec = np.array([float(np.ravel(v)[0]) for v in up.normalization_record])
+    mean, cov, ess, count = float(up.est_mean()[0]), float(up.est_covariance_mtx()[0, 0]), float(up.n_ess), \
+        int(up.resample_count)
+    be.close(up)
+    del up
+    out = None
+    if rank == 0:
+        one = be.new_updater(n_local * world, full, seed=31, sharded=False)
+        first = None
+        for k in range(m):
+            one.update(int(outcomes[k]), ts[k:k + 1])
+            if first is None and one.resample_count > 0:
+                first = k
+        rec1 = np.array([float(np.ravel(v)[0]) for v in one.normalization_record])
+        upto = m if first is None else first + 1          # records up to and including the step that triggered it
+        mean1, cov1, ess1 = float(one.est_mean()[0]), float(one.est_covariance_mtx()[0, 0]), float(one.n_ess)
+        se = np.sqrt(cov / max(ess, 1.0) + cov1 / max(ess1, 1.0))
+        out = {"world": world, "particles": n_local * world, "steps": m,
+               "records_before_first_resample": int(upto),
+               "norm_record_max_rel_err": float(np.max(np.abs(rec[:upto] / rec1[:upto] - 1))),
+               "resample_count": [count, int(one.resample_count)],
+               "mean_sigmas": abs(mean - mean1) / se, "mean": [mean, mean1]}
+        out["ok"] = bool(out["norm_record_max_rel_err"] < 1e-10 and out["mean_sigmas"] < 5.0 and
+                         abs(count - int(one.resample_count)) <= 1)
+        del one
+    be.barrier()
+    return out
+
+
+def roofline_record(run, n, steps):
+    peak, peak_src = measured_peak_gbs()
+    resample_ms = float(sum(run["resample_ms_each"]))
+    # average fused-update launch: the timed region minus the resamples (event pairs around each), over the launches.
+    # Per-launch event pairs are avoided on purpose: an event between two launches breaks their programmatic
+    # dependent-launch overlap.  Gaps between kernels are therefore charged to the kernel (conservative).
+    kern_ms = (run["elapsed_ms"] - resample_ms) / max(run["update_launches"], 1)
+    algo_bytes = 8.0 * (1 + 2) * n                   # per launch, per GPU: 8(d+2) B/particle, d = 1
+    achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(n)
+    return {"bound": "hbm", "kernel": "fused_update_kernel<PRECESSION>", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "dram_frac": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None,
+            "note": "achieved = ALGORITHMIC bytes over time; consecutive launches walk the slab in opposite "
+                    "directions, so part of it is served by the 126 MB L2 and DRAM moves less (traffic); dram_frac "
+                    "is the DRAM share of the measured copy peak",
+            "peak_source": peak_src, "bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms,
+            "how": "(timed region - sum of event-timed resamples) / fused-update launches",
+            "update_launches": run["update_launches"], "updates_per_launch": steps / max(run["update_launches"], 1),
+            "resample_ms_total": resample_ms, "resample_ms_each": [round(v, 3) for v in run["resample_ms_each"]]}
+
+
+def resample_roofline(run, n):
+    if not run["resample_ms_each"]:
+        return None
+    peak, _ = measured_peak_gbs()
+    # whole Liu-West resample (moments + constants, counts, draw + move + weights, retry launch, host wait):
+    # algorithmic 8(3d+5) B per resampled particle (SURVEY §8d), d = 1; the binned path moves 8(3d+3)
+    rb = 8.0 * (3 * 1 + 5) * n
+    med = float(np.median(run["resample_ms_each"]))
+    return {"bound": "hbm", "bytes_per_resample": rb, "median_ms": med, "achieved": rb / (med * 1e-3) / 1e9,
+            "peak": peak, "unit": "GB/s", "frac": rb / (med * 1e-3) / 1e9 / peak,
+            "note": "event-timed around resample(), host work and syncs included"}
+
+
+def gpu_arm(args, rank, world, local_rank, backend=None):
+    be = backend if backend is not None else CudaBackend(local_rank, world)
     n = args.particles
     steps, warm = args.steps, args.warmup
     ts, outcomes = make_data(steps + warm)
     prior = make_prior(n, 99 + rank)
-
-    def new_updater(fuse=None):
-        fuse = args.fuse if fuse is None else fuse
-        res = qb.LiuWestResampler(a=0.98, rng='philox', seed=1000 + rank, scan='fast')
-        if world > 1:
-            from qinfer_b200.sharded import ShardedSMCUpdater
-            return ShardedSMCUpdater(qb.SimplePrecessionModel(), n * world, FixedPrior(prior), resampler=res, lazy=True,
-                                     fuse=fuse)
-        return qb.SMCUpdater(qb.SimplePrecessionModel(), n, FixedPrior(prior), resampler=res, lazy=True, fuse=fuse)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    extras = not args.no_extras
+    line = None
+    fused = parity = star = c5 = shard = None
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        # process warm-up (not a step of the workload): run a small cloud through updates AND resamples once so that
-        # every kernel of the path is loaded (CUDA loads modules lazily at first launch) before anything is timed
-        nsmall = 65536
-        if world == 1:
-            small = qb.SMCUpdater(qb.SimplePrecessionModel(), nsmall, FixedPrior(prior[:nsmall]), lazy=True,
-                                  resampler=qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast'))
-        else:
-            from qinfer_b200.sharded import ShardedSMCUpdater
-            small = ShardedSMCUpdater(qb.SimplePrecessionModel(), nsmall * world, FixedPrior(prior[:nsmall]), lazy=True,
-                                      resampler=qb.LiuWestResampler(a=0.98, rng='philox', seed=5, scan='fast'))
-        wts_, wout_ = make_data(30, seed=7)              # its own data: independent of --steps/--warmup
-        for k in range(30):
-            small.update(int(wout_[k]), wts_[k:k + 1])
-        small.est_mean()
-        # ... and page-lock the host staging blocks the posterior read-back will recycle (torch's caching host
-        # allocator keeps them), as a long-lived process would have done on its first read
-        # (the e2e pass reads its prior from page-locked host memory, as the base contract asks; allocated first so
-        # that it does not take one of the recycled staging blocks)
-        pinned_prior = torch.empty((n, 1), dtype=torch.float64, pin_memory=True)
-        pinned_prior.numpy()[:] = prior
-        stage = [torch.empty((n, 1), dtype=torch.float64, pin_memory=True),
-                 torch.empty((n,), dtype=torch.float64, pin_memory=True)]
+        process_warmup(be, prior)
+        # page-lock the host block of the e2e pass (as the base contract asks) and the staging blocks its posterior
+        # read-back will recycle (torch's caching host allocator keeps them), as a long-lived process would have
+        pinned_prior = be.pinned(prior)
+        stage = [be.pinned(prior), be.pinned(prior[:, 0])]
         del stage
-        if world > 1:
-            small.close()
-        del small
         # ---------------- value: state resident in HBM ----------------
-        up = new_updater()
-        for k in range(warm):
-            up.update(int(outcomes[k]), ts[k:k + 1])
-        cloud = up._cloud
-        cloud.preallocate_resample()
-        cloud.resample_events = []
-        launches0 = cloud.launches
-        upd_launches0 = cloud.update_launches
-        res0 = up.resample_count
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-            time.sleep(0.35)                             # let nvidia-smi take its first samples
-        barrier()
-        gc.collect()
-        gc.disable()                                     # no collector pauses inside the timed regions (host hygiene)
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for k in range(warm, warm + steps):
-            up.update(int(outcomes[k]), ts[k:k + 1])
-        up._flush()                                      # settle the last (lazily pending) step
-        stop.record()
-        barrier()
-        elapsed_ms = start.elapsed_time(stop)
-        clocks = sampler.stop() if rank == 0 else None
-        launches = cloud.launches - launches0
-        upd_launches = cloud.update_launches - upd_launches0
-        n_resamples = up.resample_count - res0
-        # average fused-update launch: the timed region minus the resamples (event pairs around each), over K launches.
-        # Per-launch event pairs are avoided on purpose: an event between two launches breaks their programmatic
-        # dependent-launch overlap.  Gaps between kernels are therefore charged to the kernel (conservative).
-        resample_events = list(up._cloud.resample_events)
-        resample_ms = float(sum(a.elapsed_time(b) for a, b in resample_events))
-        kern_ms = (elapsed_ms - resample_ms) / max(upd_launches, 1)
-        posterior_mean = float(up.est_mean()[0])
-
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        run = timed_run(be, n, prior, ts, outcomes, warm, steps, fuse=args.fuse, seed=1000 + rank, clocks=sampler)
         # ---------------- e2e: from host arrays, through the public API ----------------
-        if world > 1:
-            up.close()
-        del up, cloud                                    # (a live reference would keep ~1 GB of device buffers
-        gc.collect()                                     #  allocated and make the e2e pass cudaMalloc its own)
-        torch.cuda.synchronize()
-        prior = pinned_prior.numpy()                     # the user's host array, page-locked (allocated above)
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        up = new_updater()                               # H2D of the n x 1 prior sample happens here
-        up._cloud.preallocate_resample()
-        torch.cuda.synchronize()
-        t_setup = time.perf_counter() - t0
-        for k in range(warm, warm + steps):
-            up.update(int(outcomes[k]), ts[k:k + 1])
-        up._flush()
-        torch.cuda.synchronize()
-        t_steps = time.perf_counter() - t0 - t_setup
-        locs = up.particle_locations                     # D2H posterior
-        wts = up.particle_weights
-        mean = up.est_mean()
-        e1.record()
-        barrier()
-        t_total = time.perf_counter() - t0
-        e2e_ms = max(e0.elapsed_time(e1), 1e3 * t_total)
-        e2e_phases = {"setup_and_h2d_ms": 1e3 * t_setup, "updates_ms": 1e3 * t_steps,
-                      "readback_ms": 1e3 * (t_total - t_setup - t_steps)}
-        assert locs.shape[0] == n and wts.shape[0] == n and np.isfinite(mean).all()
-        h2d = (n * 8 + 64 * steps) / steps               # prior upload amortised + per-step experiment record
-        d2h = (2 * n * 8 + 8) / steps + 16 * 8           # posterior read-back amortised + per-step stats block
-
-        # ---------------- extra: the same K updates, 8 fused per launch ----------------
-        fused = None
-        if world == 1 and args.fuse == 1:
-            del up
-            up = new_updater(fuse=8)
-            up._cloud.preallocate_resample()
-            for k in range(warm):
-                up.update(int(outcomes[k]), ts[k:k + 1])
-            up._flush()
-            l0 = up._cloud.update_launches
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for k in range(warm, warm + steps):
-                up.update(int(outcomes[k]), ts[k:k + 1])
-            up._flush()
-            f1.record()
-            barrier()
-            fused_ms = f0.elapsed_time(f1)
-            fused = {"updates_per_launch_max": 8, "value": n * steps / (fused_ms * 1e-3), "unit": UNIT,
-                     "ms_per_step": fused_ms / steps, "update_launches": up._cloud.update_launches - l0,
-                     "resamples": up.resample_count,
+        e2e = e2e_run(be, n, pinned_prior, ts, outcomes, warm, steps, fuse=args.fuse, seed=1000 + rank)
+        rec_bytes = 64                                   # experiment record in (t, outcome, flags); stats block out
+        h2d = n * 8.0 / steps + rec_bytes                # prior upload amortised + per-step experiment record
+        d2h = 64 + 8.0 / steps                           # per-step stats block + the posterior mean
+        if extras and world == 1 and args.fuse == 1:
+            # SURVEY §8 f1: the same K updates, 8 fused per launch
+            f = timed_run(be, n, prior, ts, outcomes, warm, steps, fuse=8, seed=1000)
+            fused = {"updates_per_launch_max": 8, "value": n * steps / (f["elapsed_ms"] * 1e-3), "unit": UNIT,
+                     "ms_per_step": f["elapsed_ms"] / steps, "update_launches": f["update_launches"],
+                     "resamples": f["resamples"],
                      "note": "same workload and semantics (per-step n_ess check, speculative + roll-back); the fused "
                              "kernel is fp64-pipe bound, not HBM bound"}
-        h2d = (n * 8 + 64 * steps) / steps               # prior upload amortised + per-step experiment record
-        d2h = (2 * n * 8 + 8) / steps + 16 * 8           # posterior read-back amortised + per-step stats block
+            # the bit-exact mode: legacy MT19937 stream continued on the device, exact (np.cumsum-rounding) scan
+            p = timed_run(be, n, prior, ts, outcomes, warm, steps, mode='parity', fuse=1)
+            parity = {"resampler": "rng=mt19937 (NumPy's legacy stream, generated on the device), scan=exact, staged "
+                                   "draw: resample indices bit-identical to the reference under np.random.seed",
+                      "value": n * steps / (p["elapsed_ms"] * 1e-3), "unit": UNIT,
+                      "ms_per_step": p["elapsed_ms"] / steps, "resamples": p["resamples"],
+                      "resample_ms_each": [round(v, 3) for v in p["resample_ms_each"]],
+                      "posterior_mean": p["posterior_mean"]}
+            if n == PARTICLES_PER_GPU and not args.no_north_star:
+                big = 10 ** 8
+                bts, bout = make_data(205)
+                s = timed_run(be, big, make_prior(big, 7), bts, bout, 5, 200, fuse=1, seed=2000)
+                sr = roofline_record(s, big, 200)
+                star = {"workload": "SimplePrecessionModel, N = 1e8 particles on ONE GPU, 200 updates (north_star)",
+                        "value": big * 200 / (s["elapsed_ms"] * 1e-3), "unit": UNIT,
+                        "ms_per_step": s["elapsed_ms"] / 200, "resamples": s["resamples"],
+                        "resample_ms_each": [round(v, 3) for v in s["resample_ms_each"]],
+                        "roofline_frac": sr["frac"], "avg_update_launch_ms": sr["avg_launch_ms"],
+                        "target": ">= 1e9 particle-updates/s at >= 60 % of the HBM roofline"}
+        if extras and world == 8 and n == PARTICLES_PER_GPU:
+            nc = C5_PARTICLES_PER_GPU
+            c = timed_run(be, nc, make_prior(nc, 199 + rank), ts, outcomes, warm, steps, fuse=args.fuse,
+                          seed=3000 + rank)
+            c_ms = be.reduce([c["elapsed_ms"]])[0]
+            c5 = {"workload": "C5: N = 1e8 over 8 GPUs, 1.25e7 particles per GPU, same %d steps" % steps,
+                  "value": nc * world * steps / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms / steps,
+                  "resamples": c["resamples"]}
+        if extras and world > 1:
+            shard = sharded_check(be, rank, world)
 
-    gc.enable()
-    if dist is not None:
-        t = torch.tensor([elapsed_ms, e2e_ms, kern_ms, resample_ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, kern_ms, resample_ms = [float(v) for v in t.cpu()]
-        tl = torch.tensor([launches], dtype=torch.int64, device='cuda')
-        dist.all_reduce(tl)
-        launches = int(tl.item())
-
+    elapsed_ms, core_ms = be.reduce([run["elapsed_ms"], e2e["core_ms"]])
+    launches = int(be.reduce([run["launches"]], op="sum")[0])
     if rank == 0:
         total_particles = n * world
         value = total_particles * steps / (elapsed_ms * 1e-3)
-        e2e = total_particles * steps / (e2e_ms * 1e-3)
-        peak, peak_src = measured_peak_gbs()
-        algo_bytes = 8.0 * (1 + 2) * n                   # per launch, per GPU: 8(d+2) B/particle, d = 1
-        achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(n)
-        res_each = [a.elapsed_time(b) for a, b in resample_events]
+        run_max = dict(run, elapsed_ms=elapsed_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(n, world),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "phases": e2e_phases},
-            "gpu_launches": launches, "resamples_in_timed_region": n_resamples,
-            "roofline": {"bound": "hbm", "kernel": "fused_update_kernel<PRECESSION>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": algo_bytes, "avg_launch_ms": kern_ms,
-                         "how": "(timed region - sum of event-timed resamples) / fused-update launches",
-                         "update_launches": upd_launches, "updates_per_launch": steps / max(upd_launches, 1),
-                         "resample_ms_total": resample_ms,
-                         "resample_ms_each": [round(v, 3) for v in res_each]},
-            "clocks": clocks, "posterior_mean": posterior_mean,
+            "e2e": {"value": total_particles * steps / (core_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "timed": "prior upload from page-locked host memory + K updates (host scalars in, stats out) + "
+                             "posterior mean read",
+                    "phases": {k: e2e[k] for k in ("setup_and_h2d_ms", "updates_ms", "posterior_readback_ms")},
+                    "with_posterior_readback": {"value": total_particles * steps / (e2e["with_readback_ms"] * 1e-3),
+                                                "d2h_bytes_per_step": d2h + 16.0 * n / steps}},
+            "gpu_launches": launches, "resamples_in_timed_region": run["resamples"],
+            "roofline": roofline_record(run_max, n, steps),
+            "clocks": run["clocks"], "posterior_mean": run["posterior_mean"],
         }
-        if res_each:
-            # whole Liu-West resample (moments, CDF + guide, fused draw+move, weights, host sqrtm and reads):
-            # algorithmic 8(3d+5) B per resampled particle, d = 1
-            rb = 8.0 * (3 * 1 + 5) * n
-            med = float(np.median(res_each))
-            line["resample_roofline"] = {"bound": "hbm", "bytes_per_resample": rb, "median_ms": med,
-                                         "achieved": rb / (med * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                         "frac": rb / (med * 1e-3) / 1e9 / peak,
-                                         "note": "event-timed around resample(), host work and syncs included"}
-        if fused is not None:
-            line["fused_f1"] = fused
+        rr = resample_roofline(run, n)
+        if rr is not None:
+            line["resample_roofline"] = rr
+        for key, val in (("fused_f1", fused), ("parity_mode", parity), ("north_star_1e8", star), ("c5", c5),
+                         ("sharded_check", shard)):
+            if val is not None:
+                line[key] = val
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(n)
+            line["cpu_baseline"], post = cpu_baseline(n)
+            if extras:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    line["check"] = prefix_check(be, n, post)
         print(json.dumps(line))
-    if dist is not None:
-        try:
-            up.close()
-        except Exception:
-            pass
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        bad = [k for k in ("check", "sharded_check") if k in line and not line[k]["ok"]]
+        if bad:
+            sys.stderr.write("bench.py: in-run correctness check failed: %s\n" % ", ".join(bad))
+    be.finish()
+    return line
 
 
-def cpu_baseline(n):
-    """Oracle on the first 14 updates of the same workload at the full particle count (incl. the
-    resamples they trigger): ~15-25 s of single-process NumPy."""
-    m = 14
-    ts, outcomes = make_data(m)
-    prior = make_prior(n, 99)
-    times, n_res = run_oracle(n, ts, outcomes, prior)
-    total = float(np.sum(times))
-    return {"value": n * m / total, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
-            "sample": "NumPy oracle port, first %d updates of the schedule at N=%d incl. %d resamples, %.1f s"
-                      % (m, n, n_res, total)}
-
-
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -456,10 +671,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=int, default=PARTICLES_PER_GPU, help="particles per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip fused_f1 / parity_mode / north_star_1e8 / c5 / the correctness checks")
+    ap.add_argument("--no-north-star", action="store_true")
     ap.add_argument("--fuse", type=int, default=1,
                     help="updates fused per launch in the timed regions (1 = one launch per update, the headline)")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args = ap.parse_args(argv)
+    if args.steps < 1:
+        ap.error("--steps must be at least 1")
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -436,6 +436,29 @@ def _make_sharded_updater_class():
             cloud.stats.copy_(torch.from_numpy(host))
             self._n_ess = 1.0 / sumsq
 
+        # smc.py:416-418 on a sharded cloud: the bad-weight count the kernel publishes is already global, so every rank
+        # takes the clip path together; the smallest weight and the post-clip sums must be global too, or the ranks
+        # would take different policy / resample decisions (and the next in-kernel all-reduce would wait for a peer
+        # that never launches)
+        def _pending_min_weight(self, slot):
+            mine = torch.tensor([self._cloud.pending_min_weight(slot)], dtype=torch.float64, device=self._cloud.device)
+            self._comm.dist.all_reduce(mine, op=self._comm.dist.ReduceOp.MIN, group=self._comm.group)
+            return float(mine.item())
+
+        def _clip_weights(self, slot):
+            cloud = self._cloud
+            st = np.array(cloud.clip_weights(slot), dtype=np.float64)      # local sums of the clipped slab
+            sums = torch.tensor([st[_lib.QB_STAT_NORM], st[_lib.QB_STAT_SUMSQ]], dtype=torch.float64,
+                                device=cloud.device)
+            self._comm.all_reduce_sum(sums)
+            norm, sumsq = [float(v) for v in sums.tolist()]
+            st[_lib.QB_STAT_NORM], st[_lib.QB_STAT_SUMSQ] = norm, sumsq
+            st[_lib.QB_STAT_INV_NORM] = 1.0
+            st[_lib.QB_STAT_NESS] = 1.0 / sumsq if sumsq else np.inf
+            st[_lib.QB_STAT_NBAD] = 0.0
+            cloud._stats[slot].copy_(torch.from_numpy(st))
+            return st
+
         @property
         def particle_weights(self):
             return SMCUpdater.particle_weights.fget(self)
@@ -505,6 +528,10 @@ def _make_sharded_updater_class():
             n_local, d = cloud.n, cloud.d
 
             split = d <= 4 and getattr(res, '_fused', False) and self._exchange == 'split'
+            if split and getattr(res, '_draw', 'auto') in ('auto', 'binned') and cloud.binned_supported(n_local):
+                self._split_pass_binned()
+                self._finish_resample(ev)
+                return
             _, mean, m2 = self._global_moments(
                 overlap=(lambda: cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED)) if split else None)
             cov = covariance_from_moments(mean, m2)
@@ -598,6 +625,64 @@ def _make_sharded_updater_class():
 
             self.last_exchange = split_resample(comm, Ops(), m, self._layout.counts, cloud.d)
             res.last_n_iters = state['iters']
+
+        def _liu_west_consts(self, mean, m2):
+            """cov, zero-norm replacement and S = h * sqrtm_psd(cov) on the host (resamplers.py:266-305), identical on
+            every rank because the moments are."""
+            res = self.resampler
+            cov = covariance_from_moments(mean, m2)
+            if scipy.linalg.norm(cov, 'fro') == 0:
+                warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
+                              "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
+                cov = res._zero_cov_comp * np.eye(cov.shape[0])
+            S, S_err = sqrtm_psd(cov)
+            if not np.isfinite(S_err):
+                raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
+                                     "Check that n_ess is not too small.")
+            return np.real(res._h * S)
+
+        def _split_pass_binned(self):
+            """The "split" resample over the binned draw (csrc/qb_binned.cu): ONE pass over the slab gives its bin
+            sums and its moment sums; ONE all-gather of the 1 + d + d^2 sums gives the global mean / covariance and
+            the shard masses; every rank draws the same multinomial split m ~ Mult(N, masses), then draws ITS m[r]
+            offspring from its own slab — the first min(m[r], N/G) straight into its new slab, the surplus into the
+            send buffer of the one all-to-all — in one launch."""
+            res, cloud, comm = self.resampler, self._cloud, self._comm
+            r, d = comm.rank, cloud.d
+            cap = self._layout.counts
+            cloud.preallocate_resample_slab()
+            cloud._binned_scratch(2 * cloud.n)                   # (re-allocation zeroes the workspace: before pass 1)
+            cloud.binned_sums()
+            rows = comm.all_gather_rows(cloud.moments_out)       # one collective, one host read
+            out = rows[0].copy()
+            for q in range(1, rows.shape[0]):                    # fixed rank order: identical on every rank
+                out += rows[q]
+            self._shard_masses = rows[:, 0].copy()
+            mean, m2 = out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
+            S = self._liu_west_consts(mean, m2)
+            m = split_counts(self._split_rng, self._n_global, self._shard_masses)
+            keep = min(m[r], cap[r])
+            extra = m[r] - keep
+            send = torch.empty((max(extra, 1), d), dtype=torch.float64, device=cloud.device)
+            iters = 0
+            if m[r] > 0:
+                if m[r] > cloud._bin_cap[1]:                     # a slab holding far more than its share of the mass
+                    cloud._binned_scratch(m[r])
+                    cloud.binned_sums()
+                off_u, off_v = res._binned_offsets(m[r])
+                cloud.binned_count(m[r], self._stream_seed, off_u)
+                iters, bad = res._binned_move(cloud, mean, S, res._a, m[r], off_v, seed=self._stream_seed,
+                                              dst=cloud.x_alt, split=keep, dst2=send if extra else None)
+                if bad:
+                    warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                                   "iterations.").format(bad, res._maxiter), ResamplerWarning)
+            T = exchange_plan(m, cap)
+            if any(any(row) for row in T):
+                recv_counts = [T[q][r] for q in range(comm.world)]
+                assert sum(recv_counts) == cap[r] - keep
+                comm.all_to_all_into(cloud.x_alt[keep:].reshape(-1), send[:extra], T[r], recv_counts, d)
+            self.last_exchange = (extra, cap[r] - keep)
+            res.last_n_iters = iters
 
         def _finish_resample(self, ev):
             cloud = self._cloud

@@ -452,11 +452,11 @@ class SMCUpdater(object):
         total = rec if unnormalised else 1.0
         norm_rec = rec
         if nbad > 0:                                         # smc.py:416-418
-            smallest = cloud.pending_min_weight(slot)
+            smallest = self._pending_min_weight(slot)
             smallest = smallest if unnormalised else smallest / S
             warnings.warn("Negative weights occured in particle approximation. Smallest weight observed == {}. "
                           "Clipping weights.".format(smallest), ApproximationWarning)
-            st2 = cloud.clip_weights(slot)
+            st2 = self._clip_weights(slot)
             total = float(st2[QB_STAT_NORM])
             ness = self._ness_from(total, float(st2[QB_STAT_SUMSQ]), normalised=True)
         if total <= self._zero_weight_thresh:                # smc.py:423-436 (a NaN total passes, as in the reference)
@@ -486,6 +486,13 @@ class SMCUpdater(object):
             self._min_n_ess = self._n_ess
         if check:
             self._maybe_resample()
+
+    # (hooks: a sharded cloud makes these two global with collectives)
+    def _pending_min_weight(self, slot):
+        return self._cloud.pending_min_weight(slot)
+
+    def _clip_weights(self, slot):
+        return self._cloud.clip_weights(slot)
 
     def batch_update(self, outcomes, expparams, resample_interval=5):
         """smc.py:459-487.  The reference loops ``update(check_for_resample=False)`` and calls ``_maybe_resample``
