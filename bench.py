@@ -116,6 +116,21 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout_s=8.0):
+        """Block until nvidia-smi has written its first line: its start-up (NVML initialisation of every GPU of the
+        box, hundreds of ms on an 8-GPU node) must not overlap the timed region — it stalls kernel launches."""
+        if self.proc is None:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    time.sleep(0.05)
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -376,8 +391,12 @@ def process_warmup(be, prior):
     independent of --steps / --warmup."""
     nsmall = min(65536, prior.shape[0])
     wts, wout = make_data(PROCESS_WARMUP_STEPS, seed=7)
-    for mode in (('throughput', 'parity') if be.world == 1 else ('throughput',)):
-        small = be.new_updater(nsmall, prior[:nsmall], mode=mode, seed=5)
+    # a small cloud in both modes (module loading), then a throw-away cloud of the workload's size in the timed mode:
+    # the allocator, the pinned staging blocks and (sharded) NCCL's channels for these message sizes exist before
+    # the timed updater is built
+    plan = [(nsmall, 'throughput')] + ([(nsmall, 'parity')] if be.world == 1 else []) + [(prior.shape[0], 'throughput')]
+    for nsz, mode in plan:
+        small = be.new_updater(nsz, prior[:nsz], mode=mode, seed=5)
         if mode == 'parity':
             np.random.seed(123)
         drive(small, wts, wout, 0, PROCESS_WARMUP_STEPS)
@@ -398,7 +417,7 @@ def timed_run(be, n, prior, ts, outcomes, warm, steps, mode='throughput', fuse=1
     r0 = up.resample_count
     if clocks is not None:
         clocks.start()
-        time.sleep(0.35)                             # let nvidia-smi take its first samples
+        clocks.wait_first_sample()                   # nvidia-smi's start-up stays outside the timed region
     be.barrier()
     gc.collect()
     gc.disable()                                     # no collector pauses inside the timed region (host hygiene)
@@ -443,7 +462,8 @@ def e2e_run(be, n, pinned_prior, ts, outcomes, warm, steps, fuse=1, seed=1000):
     t_total = time.perf_counter() - t0
     be.barrier()
     core_ms = max(t.ms(), 1e3 * t_core)
-    assert locs.shape[0] == n and wts.shape[0] == n and np.isfinite(mean).all()
+    # (a sharded cloud's slab floats around n after a resample)
+    assert locs.shape[0] == wts.shape[0] and abs(locs.shape[0] - n) <= 0.05 * n + 4096 and np.isfinite(mean).all()
     be.close(up)
     del up, locs, wts
     gc.collect()

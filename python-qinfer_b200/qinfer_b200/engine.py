@@ -39,21 +39,27 @@ def _stream():
 
 
 class DeviceCloud(object):
-    def __init__(self, desc, n, device=None):
+    def __init__(self, desc, n, device=None, capacity=None):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.desc = desc
         self.n = int(n)
         self.d = int(desc.d)
+        # ``capacity`` >= n particles are allocated; the cloud may then change its size up to that bound without
+        # touching the allocator (a resample into another particle count; the floating slabs of a sharded cloud)
+        self.capacity = max(self.n, int(capacity or 0))
         with torch.cuda.device(self.device):
             f64 = dict(dtype=torch.float64, device=self.device)
-            self.x = torch.empty((self.n, self.d), **f64)
-            self.x_alt = None                     # allocated at the first resample
+            self._x_back = torch.empty((self.capacity, self.d), **f64)
+            self._x_alt_back = None               # allocated at the first resample
+            self.x = self._x_back[:self.n]
+            self.x_alt = None
             _pad = int(os.environ.get("QB_ALLOC_PAD", "0"))     # experiment knob: shift the weight buffers
             self._pad_tensor = torch.empty((_pad,), dtype=torch.uint8, device=self.device) if _pad else None
             # weights and stats are ping-pong pairs: `cur` is the committed state, 1 - cur receives the
             # next update (so a rejected update leaves the committed weights intact, smc.py:423-441)
-            self._w = [torch.empty((self.n,), **f64), torch.empty((self.n,), **f64)]
+            self._w_back = [torch.empty((self.capacity,), **f64), torch.empty((self.capacity,), **f64)]
+            self._w = [b[:self.n] for b in self._w_back]
             self._stats = [torch.zeros((QB_STAT_COUNT,), **f64), torch.zeros((QB_STAT_COUNT,), **f64)]
             self.cur = 0
             # host-visible copy of each stats block, written by the kernel itself (pinned, device-accessible)
@@ -63,13 +69,7 @@ class DeviceCloud(object):
             self._tag = 0
             self._eps_arr = (_lib.QbExpparams * QB_MAX_FUSE)()
             self._out_arr = (ctypes.c_int64 * QB_MAX_FUSE)()
-            ws_bytes = max(self.lib.qb_update_workspace_bytes(self.n, self.d),
-                           self.lib.qb_moments_workspace_bytes(self.n, self.d),
-                           self.lib.qb_cdf_workspace_bytes(self.n),
-                           self.lib.qb_compact_workspace_bytes(self.n),
-                           self.lib.qb_draw_workspace_bytes(self.n))
-            self.ws = torch.zeros(((ws_bytes + 7) // 8,), **f64)       # zeroed once: holds the launch ticket
-            self.ws_bytes = self.ws.numel() * 8
+            self._alloc_workspace()
             self.moments_out = torch.empty((1 + self.d + self.d * self.d,), **f64)
             self.moments_host = torch.empty((1 + self.d + self.d * self.d,), dtype=torch.float64, pin_memory=True)
             self.stats_host = torch.empty((QB_STAT_COUNT,), dtype=torch.float64, pin_memory=True)
@@ -99,6 +99,27 @@ class DeviceCloud(object):
         self._launches = 0
         self.resample_events = None        # bench: set to [] to collect a CUDA-event pair around every resample
         self.update_launches = 0
+
+    def _alloc_workspace(self):
+        cap = self.capacity
+        ws_bytes = max(self.lib.qb_update_workspace_bytes(cap, self.d),
+                       self.lib.qb_moments_workspace_bytes(cap, self.d),
+                       self.lib.qb_cdf_workspace_bytes(cap),
+                       self.lib.qb_compact_workspace_bytes(cap),
+                       self.lib.qb_draw_workspace_bytes(cap))
+        self.ws = torch.zeros(((ws_bytes + 7) // 8,), dtype=torch.float64, device=self.device)   # zeroed once: holds the launch ticket
+        self.ws_bytes = self.ws.numel() * 8
+
+    def _alt_slab(self, n_new):
+        """The alternate particle slab as an (n_new, d) view of its backing buffer (grown only when too small)."""
+        n_new = int(n_new)
+        if self._x_alt_back is None or self._x_alt_back.shape[0] < n_new:
+            self._x_alt_back = torch.empty((max(n_new, self.capacity), self.d), dtype=torch.float64,
+                                           device=self.device)
+            self.x_alt = None
+        if self.x_alt is None or self.x_alt.shape[0] != n_new:
+            self.x_alt = self._x_alt_back[:n_new]
+        return self.x_alt
 
     def _refresh_ptrs(self):
         """Raw pointers of the buffers the hot loop passes on every launch (re-derived whenever a buffer is swapped)."""
@@ -355,14 +376,12 @@ class DeviceCloud(object):
         """Allocate the resampling scratch and the second particle slab up front (no allocation in the loop)."""
         n_new = self.n if n_new is None else int(n_new)
         self._resample_scratch(n_new)
-        if self.x_alt is None or self.x_alt.shape[0] != n_new:
-            self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+        self._alt_slab(n_new)
         if self._parent_inv is None or self._parent_inv.numel() < n_new:
             self._parent_inv = torch.empty((n_new,), dtype=torch.int32, device=self.device)
 
     def preallocate_resample_slab(self):
-        if self.x_alt is None or self.x_alt.shape[0] != self.n:
-            self.x_alt = torch.empty((self.n, self.d), dtype=torch.float64, device=self.device)
+        self._alt_slab(self.n)
 
     def cdf(self, mode):
         if self._cdf is None or self._cdf.numel() != self.n:
@@ -386,8 +405,7 @@ class DeviceCloud(object):
 
     def lw_move(self, mean, S, a, eps_dev, n_new, postselect, x_src=None, js=None):
         """x_alt[i] = a * x_src[js[i]] + (1-a) * mean + S @ eps[:, i] (x_src defaults to the current slab)."""
-        if self.x_alt is None or self.x_alt.shape[0] != n_new:
-            self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+        self._alt_slab(n_new)
         src = self.x if x_src is None else x_src
         js = self._js if js is None else js
         check(self.lib.qb_lw_move(self.lib_model, _ptr(src), src.shape[0], self.d, _ptr(js),
@@ -402,8 +420,7 @@ class DeviceCloud(object):
         with u and eps regenerated in the kernel from the Philox streams (seed_u, off_u) / (seed_n, off_n).
         ``dst`` defaults to the alternate slab."""
         if dst is None:
-            if self.x_alt is None or self.x_alt.shape[0] != n_new:
-                self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+            self._alt_slab(n_new)
             dst = self.x_alt
         self._fused_scratch(n_new)
         check(self.lib.qb_lw_draw_move(self.lib_model, _ptr(self.x), self.n, self.d, _ptr(self._cdf), _ptr(self.ws),
@@ -430,8 +447,7 @@ class DeviceCloud(object):
                       u_out=None, js_out=None):
         """Merge draw + move (sorted uniforms from exponential spacings, streaming merge with the CDF)."""
         if dst is None:
-            if self.x_alt is None or self.x_alt.shape[0] != n_new:
-                self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+            self._alt_slab(n_new)
             dst = self.x_alt
         self._fused_scratch(n_new)
         if self._parent_inv is None or self._parent_inv.numel() < n_new:
@@ -460,11 +476,12 @@ class DeviceCloud(object):
         return self.d <= 4 and self.n < (1 << 31) and 1 <= int(n_new) < (1 << 31)
 
     def _binned_scratch(self, n_new):
-        if self._bin_ws is None or self._bin_cap[0] != self.n or self._bin_cap[1] < n_new:
-            cap_new = max(int(n_new), self.n)
-            nbytes = self.lib.qb_lw_binned_workspace_bytes(self.n, cap_new)
+        """Workspace and invalid list for a cloud of up to ``capacity`` particles resampled into up to ``n_new``."""
+        if self._bin_ws is None or self._bin_cap[0] < self.capacity or self._bin_cap[1] < n_new:
+            cap_new = max(int(n_new), self.capacity, self._bin_cap[1])
+            nbytes = self.lib.qb_lw_binned_workspace_bytes(self.capacity, cap_new)
             self._bin_ws = torch.zeros(((nbytes + 7) // 8,), dtype=torch.float64, device=self.device)
-            self._bin_cap = (self.n, cap_new)
+            self._bin_cap = (self.capacity, cap_new)
             self._bin_list = torch.empty((cap_new,), dtype=torch.int64, device=self.device)
         if self._bin_mirror is None:
             self._bin_mirror = torch.zeros((64,), dtype=torch.float64, pin_memory=True)
@@ -494,8 +511,7 @@ class DeviceCloud(object):
         and ``binned_counters_wait`` / ``binned_retry_wait(queued=True)`` for the result."""
         n_new = int(n_new)
         self._binned_scratch(n_new)
-        if self.x_alt is None or self.x_alt.shape[0] != n_new:
-            self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+        self._alt_slab(n_new)
         self._bin_tag += 1
         tag = self._bin_tag
         rounds = int(retry_rounds) if (retry_rounds and postselect) else 0
@@ -581,8 +597,7 @@ class DeviceCloud(object):
         slot, round j drawing from the normal stream at ``off_n + (j + 1) * stride``, stride = (d n_new + 1) // 2.
         Returns the tag(s) ``binned_counters_wait`` / ``binned_retry_wait`` poll for."""
         if dst is None:
-            if self.x_alt is None or self.x_alt.shape[0] != n_new:
-                self.x_alt = torch.empty((n_new, self.d), dtype=torch.float64, device=self.device)
+            self._alt_slab(n_new)
             dst = self.x_alt
         self._bin_tag += 1
         tag = self._bin_tag
@@ -638,12 +653,12 @@ class DeviceCloud(object):
         m = self._bin_mirror_np
         return int(m[base]), int(m[base + 1]), int(m[base + 2])
 
-    def adopt_binned(self, n_new, weights_fused):
+    def adopt_binned(self, n_new, weights_fused, n_global=None):
         """Make the slab the binned move wrote current.  With fused weights the alternate weight/stats buffers already
         hold 1/n and its stats block: flip the ping-pong index instead of launching the fill kernel."""
-        if n_new != self.n or not weights_fused:
-            return self.adopt_resampled(n_new)
-        self.x, self.x_alt = self.x_alt, self.x
+        if not weights_fused:
+            return self.adopt_resampled(n_new, n_global)
+        self._swap_slabs(n_new)
         self.cur = 1 - self.cur
         self._chain_tag = 0
 
@@ -666,19 +681,42 @@ class DeviceCloud(object):
                                    1 if own_mean else 0, _stream()))
         self.launches += 1
 
-    def adopt_resampled(self, n_new):
-        """Make the freshly written slab current; weights become uniform."""
-        if n_new != self.n:
-            self.n = int(n_new)
+    def _swap_slabs(self, n_new):
+        """The alternate slab (holding ``n_new`` new particles) becomes current; every per-particle buffer follows the
+        new particle count.  Within ``capacity`` nothing is allocated; beyond it the weight buffers and the
+        workspaces are rebuilt for the new size (a resampler asked for more particles, resamplers.py:86-88)."""
+        n_new = int(n_new)
+        self._x_back, self._x_alt_back = self._x_alt_back, self._x_back
+        if n_new > self.capacity or n_new > self._w_back[0].numel():
+            self.capacity = n_new
             f64 = dict(dtype=torch.float64, device=self.device)
-            self._w = [torch.empty((self.n,), **f64), torch.empty((self.n,), **f64)]
-            old_x = self.x
-            self.x = self.x_alt
-            self.x_alt = None
-            del old_x
-        else:
-            self.x, self.x_alt = self.x_alt, self.x
-        self.set_uniform_weights()
+            self._w_back = [torch.empty((n_new,), **f64), torch.empty((n_new,), **f64)]
+            self._alloc_workspace()
+            self._bin_ws = None
+            self._cdf = self._js = self._u = self._eps = self._invalid = self._idxs = self._parent_inv = None
+            if self._x_alt_back is not None and self._x_alt_back.shape[0] < n_new:
+                self._x_alt_back = None
+        self.n = n_new
+        self.x = self._x_back[:n_new]
+        self.x_alt = self._x_alt_back[:n_new] if self._x_alt_back is not None else None
+        self._w = [b[:n_new] for b in self._w_back]
+        self._chain_tag = 0
+
+    def resize(self, n_new):
+        """Change the particle count within ``capacity`` without touching the data (the caller refills the slab)."""
+        n_new = int(n_new)
+        if n_new > self.capacity:
+            raise _lib.QbError("resize(%d) beyond the cloud's capacity %d" % (n_new, self.capacity))
+        self.n = n_new
+        self.x = self._x_back[:n_new]
+        self.x_alt = None
+        self._w = [b[:n_new] for b in self._w_back]
+        self._chain_tag = 0
+
+    def adopt_resampled(self, n_new, n_global=None):
+        """Make the freshly written slab current; weights become uniform."""
+        self._swap_slabs(n_new)
+        self.set_uniform_weights(n_global)
 
     def canonicalize(self):
         if self.desc.kind != _lib.QB_MODEL_TOMOGRAPHY:

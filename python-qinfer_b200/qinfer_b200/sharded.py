@@ -57,6 +57,14 @@ class ShardLayout(object):
     def count(self, rank):
         return self.counts[rank]
 
+    def set_counts(self, counts):
+        """Floating slabs: after a resample every rank keeps the offspring it drew (counts sum to n_global)."""
+        assert sum(counts) == self.n_global and len(counts) == self.world
+        self.counts = [int(c) for c in counts]
+        self.offsets = [0]
+        for c in self.counts:
+            self.offsets.append(self.offsets[-1] + c)
+
     def owner_of_index(self, global_index):
         return int(np.searchsorted(self.offsets, global_index, side='right') - 1)
 
@@ -334,7 +342,7 @@ class PeerMailboxes(object):
 def _make_sharded_updater_class():
     from .smc import SMCUpdater
     from .distributions import covariance_from_moments
-    from .resamplers import sqrtm_psd
+    from .resamplers import sqrtm_psd, _cov_1x1
 
     class ShardedSMCUpdater(SMCUpdater):
         """``SMCUpdater`` whose cloud is sharded over the ranks of the default process group.
@@ -353,6 +361,7 @@ def _make_sharded_updater_class():
             self._shard_masses = None
             self._comm = ShardComm(group)
             self._layout = ShardLayout(n_particles, self._comm.world)
+            self._base_counts = list(self._layout.counts)      # the balanced split; slabs float around it
             self._n_global = int(n_particles)
             self._mail = None
             self._ops = None
@@ -386,6 +395,15 @@ def _make_sharded_updater_class():
             torch.cuda.synchronize()
 
         # -- plumbing ----------------------------------------------------------------------
+        SLAB_SLACK = 0.03       # floating slabs: capacity = balanced size * (1 + slack) (at least + 4096)
+
+        @classmethod
+        def _slab_capacity(cls, n):
+            return int(n) + max(4096, int(cls.SLAB_SLACK * n))
+
+        def _cloud_capacity(self, n):
+            return self._slab_capacity(n)
+
         def _rebuild_cloud(self, n):
             super(ShardedSMCUpdater, self)._rebuild_cloud(n)
             if self._comm.world > 1:
@@ -411,7 +429,14 @@ def _make_sharded_updater_class():
         def reset(self, n_particles=None, only_params=None, reset_weights=True):
             if self._cloud is not None and n_particles not in (None, self._cloud.n, self._n_global):
                 raise ValueError("changing the particle count of a sharded cloud is not supported")
-            local = self._layout.count(self._comm.rank)
+            local = self._base_counts[self._comm.rank]
+            if self._cloud is not None and self._cloud.n != local:
+                if only_params is not None:
+                    raise ValueError("reset(only_params=...) after the slabs of a sharded cloud have floated is not "
+                                     "supported")
+                self._flush()
+                self._cloud.resize(local)                # back to the balanced split: the prior refills every slab
+                self._layout.set_counts(self._base_counts)
             super(ShardedSMCUpdater, self).reset(local if self._cloud is None else None, only_params, reset_weights)
             if reset_weights:
                 self._set_global_uniform()               # w = 1 / N_global on every slab
@@ -529,8 +554,8 @@ def _make_sharded_updater_class():
 
             split = d <= 4 and getattr(res, '_fused', False) and self._exchange == 'split'
             if split and getattr(res, '_draw', 'auto') in ('auto', 'binned') and cloud.binned_supported(n_local):
-                self._split_pass_binned()
-                self._finish_resample(ev)
+                floated = self._split_pass_binned()
+                self._finish_resample(ev, weights_fused=floated)
                 return
             _, mean, m2 = self._global_moments(
                 overlap=(lambda: cloud.cdf(_lib.QB_SCAN_FAST_GUIDE_SCALED)) if split else None)
@@ -630,8 +655,8 @@ def _make_sharded_updater_class():
             """cov, zero-norm replacement and S = h * sqrtm_psd(cov) on the host (resamplers.py:266-305), identical on
             every rank because the moments are."""
             res = self.resampler
-            cov = covariance_from_moments(mean, m2)
-            if scipy.linalg.norm(cov, 'fro') == 0:
+            cov = _cov_1x1(mean, m2) if mean.shape[0] == 1 else covariance_from_moments(mean, m2)
+            if (cov[0, 0] == 0) if cov.shape == (1, 1) else (scipy.linalg.norm(cov, 'fro') == 0):
                 warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
                               "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
                 cov = res._zero_cov_comp * np.eye(cov.shape[0])
@@ -649,9 +674,7 @@ def _make_sharded_updater_class():
             send buffer of the one all-to-all — in one launch."""
             res, cloud, comm = self.resampler, self._cloud, self._comm
             r, d = comm.rank, cloud.d
-            cap = self._layout.counts
-            cloud.preallocate_resample_slab()
-            cloud._binned_scratch(2 * cloud.n)                   # (re-allocation zeroes the workspace: before pass 1)
+            cloud._binned_scratch(cloud.capacity)                # (re-allocation zeroes the workspace: before pass 1)
             cloud.binned_sums()
             rows = comm.all_gather_rows(cloud.moments_out)       # one collective, one host read
             out = rows[0].copy()
@@ -659,8 +682,28 @@ def _make_sharded_updater_class():
                 out += rows[q]
             self._shard_masses = rows[:, 0].copy()
             mean, m2 = out[1:1 + d].copy(), out[1 + d:].reshape(d, d).copy()
-            S = self._liu_west_consts(mean, m2)
             m = split_counts(self._split_rng, self._n_global, self._shard_masses)
+            caps = [self._slab_capacity(c) for c in self._base_counts]
+            if all(1 <= m[q] <= caps[q] for q in range(comm.world)):
+                # FLOATING SLABS: every rank keeps exactly the offspring it drew — no row leaves its GPU, and the new
+                # weights 1/N are written by the same launch.  Slab sizes then drift around the balanced split by
+                # ~sqrt(N/G) per resample; the exchange below runs only when one outgrows its capacity.
+                cloud._alt_slab(m[r])
+                off_u, off_v = res._binned_offsets(m[r])
+                cloud.binned_count(m[r], self._stream_seed, off_u)   # (runs while the host takes the square root)
+                S = self._liu_west_consts(mean, m2)
+                iters, bad = res._binned_move(cloud, mean, S, res._a, m[r], off_v, seed=self._stream_seed,
+                                              fuse_weights=True, n_global=self._n_global, dst=cloud.x_alt)
+                if bad:
+                    warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                                   "iterations.").format(bad, res._maxiter), ResamplerWarning)
+                self._layout.set_counts(m)
+                self.last_exchange = (0, 0)
+                res.last_n_iters = iters
+                return True
+            S = self._liu_west_consts(mean, m2)
+            cap = self._base_counts                              # rebalance: everybody back to the balanced split
+            cloud._alt_slab(cap[r])
             keep = min(m[r], cap[r])
             extra = m[r] - keep
             send = torch.empty((max(extra, 1), d), dtype=torch.float64, device=cloud.device)
@@ -681,13 +724,21 @@ def _make_sharded_updater_class():
                 recv_counts = [T[q][r] for q in range(comm.world)]
                 assert sum(recv_counts) == cap[r] - keep
                 comm.all_to_all_into(cloud.x_alt[keep:].reshape(-1), send[:extra], T[r], recv_counts, d)
+            self._layout.set_counts(cap)
             self.last_exchange = (extra, cap[r] - keep)
             res.last_n_iters = iters
+            return False
 
-        def _finish_resample(self, ev):
+        def _finish_resample(self, ev, weights_fused=False):
             cloud = self._cloud
-            cloud.x, cloud.x_alt = cloud.x_alt, cloud.x
-            self._set_global_uniform()                                # weights buffer stays, contents reset
+            n_new = self._layout.count(self._comm.rank)
+            if weights_fused:                                         # the move wrote 1/N and the global stats block
+                cloud.adopt_binned(n_new, True)
+                self._n_ess = float(self._n_global)
+                self._host_weights = None
+            else:
+                cloud._swap_slabs(n_new)
+                self._set_global_uniform()                            # weights buffer stays, contents reset
             self._host_locs = self._host_weights = None
             if self._canonicalize:
                 cloud.canonicalize()

@@ -155,9 +155,13 @@ class SMCUpdater(object):
 
     def _rebuild_cloud(self, n):
         launches = self._cloud.launches if self._cloud is not None else 0
-        self._cloud = DeviceCloud(self._desc, n, self._device)
+        self._cloud = DeviceCloud(self._desc, n, self._device, capacity=self._cloud_capacity(n))
         self._cloud.launches = launches
         self._host_locs = self._host_weights = None
+
+    def _cloud_capacity(self, n):
+        """Particles to allocate for a cloud of ``n`` (a sharded cloud adds slack for its floating slabs)."""
+        return n
 
     @staticmethod
     def _ness_from(norm, sumsq, normalised=False):

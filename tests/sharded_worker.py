@@ -86,7 +86,17 @@ def main():
             w = up.particle_weights
             check(np.all(w == 1.0 / n_global), "weights not uniform")
             locs = up.particle_locations
-            check(locs.shape == (hi - lo, 1) and np.all(locs > 0), "invalid locations")
+            check(locs.shape == (up.n_local, 1) and w.shape == (up.n_local,) and np.all(locs > 0), "invalid locations")
+            # floating slabs: every rank keeps the offspring it drew; the sizes sum to the global count and stay
+            # within the slack around the balanced split
+            cnt = torch.tensor([up.n_local], dtype=torch.int64, device='cuda')
+            dist.all_reduce(cnt)
+            check(int(cnt.item()) == n_global, "slab sizes sum to %d" % int(cnt.item()))
+            check(abs(up.n_local - (hi - lo)) <= max(4096, 0.03 * (hi - lo)), "slab drifted to %d" % up.n_local)
+            check(up.last_exchange == (0, 0), "rows travelled %r" % (up.last_exchange,))
+            # ... and the updater keeps working on the resized slab
+            up.update(int(outcomes[6]), ts[6:7])
+            check(np.isfinite(up.n_ess) and up.n_ess <= n_global, "update after a floated resample")
             up.close()
         # (c) a free-running sharded trajectory lands on the same posterior as the oracle (statistically)
         import smc_oracle as oracle
