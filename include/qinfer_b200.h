@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define QB_ABI_VERSION 3 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes; 3: qb_lw_binned_* */
+#define QB_ABI_VERSION 3 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes; 3: qb_lw_binned_*,
+                            qb_model.d_extra / extra_rule, qb_walk_step, qb_poison_likelihood, qb_tomo_canonicalize*_ld */
 
 #define QB_OK 0
 #define QB_ERR_INVALID_ARGUMENT (-1)
@@ -68,6 +69,11 @@ typedef struct qb_model {
     double min_freq;      /* precession only: `_min_freq` (test_models.py:78-80,109-110) */
     double likelihood_power; /* MLEModel (derived_models.py:681-703): every likelihood is raised to this power
                                 after the (binomial) model evaluated it; 0 or 1 = plain model */
+    int32_t d_extra;      /* trailing model parameters the likelihood ignores (d counts them): the learned step scales
+                             of GaussianRandomWalkModel (derived_models.py:811-818, 894-896), the diffusion rate of
+                             DiffusiveTomographyModel (tomography/models.py:229-256) */
+    int32_t extra_rule;   /* their validity (are_models_valid): 0 none, 1 all >= 0 (derived_models.py:883-892),
+                             2 the last one > 0 (tomography/models.py:245-249) */
 } qb_model;
 
 /* One experiment record (one element of the `expparams` array handed to
@@ -420,6 +426,38 @@ int qb_tomo_canonicalize(double* d_x, int64_t n, int32_t dim, const double* d_ba
 int qb_tomo_canonicalize_screened(double* d_x, int64_t n, int32_t dim, const double* d_basis,
                                   int32_t allow_subnormalized, uint8_t* d_flags, int64_t* d_idxs,
                                   int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Same two calls for particles stored with a row pitch of `ld` >= dim^2 doubles (DiffusiveTomographyModel keeps its
+ * diffusion rate behind the dim^2 state parameters, tomography/models.py:251-255: only the first dim^2 entries of a
+ * row are canonicalised, the rest passes through). */
+int qb_tomo_canonicalize_ld(double* d_x, int64_t n, int32_t dim, int32_t ld, const double* d_basis,
+                            int32_t allow_subnormalized, void* stream);
+int qb_tomo_canonicalize_screened_ld(double* d_x, int64_t n, int32_t dim, int32_t ld, const double* d_basis,
+                                     int32_t allow_subnormalized, uint8_t* d_flags, int64_t* d_idxs,
+                                     int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- time-dependent and noisy decorators ------------------------------------------------------- */
+/* Model.update_timestep for the random-walk decorators, in place after an update has been committed (smc.py:447-449).
+ * For each particle i and each of the n_rw walking parameters c (HOST arrays of n_rw entries):
+ *   QB_WALK_ADD      x[i][idx[c]] += (mult * z[i][zcol[c]])                        z holds the steps themselves
+ *                    (RandomWalkModel, derived_models.py:733-741, steps drawn by the model's own distribution)
+ *   QB_WALK_FIXED    x[i][idx[c]] += (mult * (scale[c] * z[i][zcol[c]]))           fixed diagonal covariance
+ *                    (GaussianRandomWalkModel, derived_models.py:925-929,944-962)
+ *   QB_WALK_LEARNED  x[i][idx[c]] += (mult * ((x[i][sidx[c]] * pre) * z[i][zcol[c]]))   per-particle scale: learned
+ *                    sigma (derived_models.py:926, pre = 1) or DiffusiveTomographyModel's eps * sqrt(t)
+ *                    (tomography/models.py:261-266, pre = sqrt(t), mult = 1)
+ * with one rounding per reference ufunc.  `d_z` is (n, kz) row-major standard normals (or steps). */
+#define QB_WALK_ADD 0
+#define QB_WALK_FIXED 1
+#define QB_WALK_LEARNED 2
+int qb_walk_step(double* d_x, int64_t n, int32_t d, int32_t n_rw, const int32_t* h_idx, const int32_t* h_zcol,
+                 int32_t mode, const double* h_scale, const int32_t* h_sidx, double pre, double mult,
+                 const double* d_z, int32_t kz, void* stream);
+/* PoisonedModel.likelihood's noise (derived_models.py:188-204) on a likelihood vector, in place:
+ *   L[i] = clip(L[i] + z[i] * sigma_i, 0, 1),  sigma_i = tol (mode 0, ALE) or
+ *   sqrt(L[i] * (1 - L[i]) / denom) (mode 1, MLE: binom_est_error, utils.py:683-688, denom = N + 2 hedge + 1). */
+int qb_poison_likelihood(double* d_L, int64_t n, const double* d_z, int32_t mode, double tol, double denom,
+                         void* stream);
 
 /* ---- device RNG (throughput mode; counter-based Philox4x32-10) ------------- */
 /* d_out[i] = uniform [0,1) with 53 random bits, element i of stream (seed, offset). */

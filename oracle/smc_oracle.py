@@ -608,6 +608,45 @@ class TomographyModel(_ModelBase):
         return two_outcome_likelihood(outcomes, 1 - tomography_pr1(modelparams, expparams['meas']))
 
 
+class DiffusiveTomographyModel(TomographyModel):
+    """tomography/models.py:228-272 — one extra model parameter eps > 0 (diffusion scale) and one extra experiment
+    field ``t``; every update ends with a Gaussian step of scale eps * sqrt(t) on the state parameters 1 .. d^2 - 1
+    followed by re-canonicalisation."""
+
+    @property
+    def n_modelparams(self):
+        return self._dim ** 2 + 1
+
+    @property
+    def expparams_dtype(self):
+        return [('meas', float, self._dim ** 2), ('t', float)]
+
+    def are_models_valid(self, modelparams):
+        # tomography/models.py:245-249
+        return np.logical_and(np.ones((modelparams.shape[0],), dtype=bool), modelparams[:, -1] > 0)
+
+    def canonicalize(self, modelparams):
+        # tomography/models.py:251-255
+        return np.concatenate([
+            super(DiffusiveTomographyModel, self).canonicalize(modelparams[:, :-1]),
+            modelparams[:, -1, None]
+        ], axis=1)
+
+    def likelihood(self, outcomes, modelparams, expparams):
+        # tomography/models.py:256-257
+        return super(DiffusiveTomographyModel, self).likelihood(outcomes, modelparams[:, :-1], expparams)
+
+    def update_timestep(self, modelparams, expparams):
+        # tomography/models.py:259-272
+        eps = (modelparams[:, -1, None] * np.sqrt(expparams['t']))[:, :, None]
+        steps = eps * np.random.randn(*modelparams[:, None, :].shape)
+        steps[:, :, [0, -1]] = 0
+        raw_modelparams = modelparams[:, None, :] + steps
+        for idx_experiment in range(len(expparams)):
+            raw_modelparams[:, idx_experiment, :] = self.canonicalize(raw_modelparams[:, idx_experiment, :])
+        return raw_modelparams.transpose((0, 2, 1))
+
+
 # ---------------------------------------------------------------------------
 # Priors used by the benchmark configurations (host side, SURVEY §8c/d)
 # ---------------------------------------------------------------------------

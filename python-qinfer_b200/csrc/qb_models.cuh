@@ -26,6 +26,7 @@ struct ModelView {
     int32_t kind, d, binomial, interleaved;
     double min_freq;
     double like_pow;   // MLEModel: L ** like_pow (1 = plain)
+    int32_t d_extra, extra_rule;  // trailing parameters the likelihood ignores, and their validity rule
 };
 
 __host__ inline ExpView make_exp_view(const qb_model& m, const qb_expparams& ep, int64_t outcome) {
@@ -54,6 +55,8 @@ __host__ inline ModelView make_model_view(const qb_model& m) {
     v.interleaved = m.interleaved;
     v.min_freq = m.min_freq;
     v.like_pow = (m.likelihood_power == 0.0) ? 1.0 : m.likelihood_power;
+    v.d_extra = m.d_extra;
+    v.extra_rule = m.extra_rule;
     return v;
 }
 
@@ -170,7 +173,22 @@ __device__ __forceinline__ double model_likelihood(const ModelView& mv, const Ex
 
 // Model.are_models_valid for one particle.
 template <typename Row>
+__device__ __forceinline__ bool model_valid_base(const ModelView& mv, Row row);
+
+// ... including the trailing parameters of a decorator (learned random-walk scales, diffusion rate)
+template <typename Row>
 __device__ __forceinline__ bool model_valid(const ModelView& mv, Row row) {
+    bool ok = model_valid_base(mv, row);
+    if (mv.extra_rule == 1) {          // derived_models.py:883-892: every learned step scale >= 0
+        for (int c = mv.d - mv.d_extra; c < mv.d; ++c) ok = ok && (row(c) >= 0.0);
+    } else if (mv.extra_rule == 2) {   // tomography/models.py:245-249: diffusion rate > 0
+        ok = ok && (row(mv.d - 1) > 0.0);
+    }
+    return ok;
+}
+
+template <typename Row>
+__device__ __forceinline__ bool model_valid_base(const ModelView& mv, Row row) {
     if (mv.kind == QB_MODEL_PRECESSION) {
         return row(0) > mv.min_freq;  // test_models.py:109-110
     } else if (mv.kind == QB_MODEL_RB) {

@@ -57,7 +57,7 @@ __device__ __forceinline__ void build_rho(const double* xv, const double* bs, cp
 // otherwise it is flagged for the Jacobi kernel below (which decides exactly as before).  One coalesced pass
 // over the slab, no local-memory traffic.
 template <int DIM>
-__global__ void __launch_bounds__(TOMO_THREADS) tomo_screen_kernel(double* __restrict__ x, int64_t n,
+__global__ void __launch_bounds__(TOMO_THREADS) tomo_screen_kernel(double* __restrict__ x, int64_t n, int ld,
                                                                    const double* __restrict__ basis, int allow_subnorm,
                                                                    uint8_t* __restrict__ flags) {
     constexpr int D2 = DIM * DIM;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(TOMO_THREADS) tomo_screen_kernel(double* __res
         asm volatile("" ::: "memory");
         double xv[D2];
 #pragma unroll
-        for (int a = 0; a < D2; ++a) xv[a] = x[i * D2 + a];
+        for (int a = 0; a < D2; ++a) xv[a] = x[i * ld + a];
         cplx A[DIM][DIM];
         build_rho<DIM>(xv, bs, A);
         double dmax = 0.0;
@@ -101,14 +101,14 @@ __global__ void __launch_bounds__(TOMO_THREADS) tomo_screen_kernel(double* __res
         if (pd && !allow_subnorm) {
             const double norm = xv[0] * sqrt_dim;
 #pragma unroll
-            for (int a = 0; a < D2; ++a) x[i * D2 + a] = xv[a] / norm;
+            for (int a = 0; a < D2; ++a) x[i * ld + a] = xv[a] / norm;
         }
     }
 }
 
 // idxs == NULL: every particle; otherwise the particles idxs[0 .. *count) left over by the screening pass.
 template <int DIM>
-__global__ void __launch_bounds__(TOMO_THREADS) tomo_canonicalize_kernel(double* __restrict__ x, int64_t n,
+__global__ void __launch_bounds__(TOMO_THREADS) tomo_canonicalize_kernel(double* __restrict__ x, int64_t n, int ld,
                                                                          const double* __restrict__ basis,
                                                                          int allow_subnorm,
                                                                          const int64_t* __restrict__ idxs,
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(TOMO_THREADS) tomo_canonicalize_kernel(double*
         asm volatile("" ::: "memory");  // keep the basis in shared memory (see tomo_screen_kernel)
         double xv[D2];
 #pragma unroll
-        for (int a = 0; a < D2; ++a) xv[a] = x[i * D2 + a];
+        for (int a = 0; a < D2; ++a) xv[a] = x[i * ld + a];
 
         cplx A[DIM][DIM], V[DIM][DIM];
         build_rho<DIM>(xv, bs, A);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TOMO_THREADS) tomo_canonicalize_kernel(double*
         }
         if (!all_nonneg || !allow_subnorm) {
 #pragma unroll
-            for (int a = 0; a < D2; ++a) x[i * D2 + a] = xv[a];
+            for (int a = 0; a < D2; ++a) x[i * ld + a] = xv[a];
         }
     }
 }
@@ -248,17 +248,22 @@ static int tomo_grid(int64_t n) {
 
 extern "C" int qb_tomo_canonicalize(double* d_x, int64_t n, int32_t dim, const double* d_basis,
                                     int32_t allow_subnormalized, void* stream) {
-    QB_REQUIRE(d_x && d_basis && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_tomo_canonicalize: bad arguments");
+    return qb_tomo_canonicalize_ld(d_x, n, dim, dim * dim, d_basis, allow_subnormalized, stream);
+}
+
+extern "C" int qb_tomo_canonicalize_ld(double* d_x, int64_t n, int32_t dim, int32_t ld, const double* d_basis,
+                                       int32_t allow_subnormalized, void* stream) {
+    QB_REQUIRE(d_x && d_basis && n >= 1 && ld >= dim * dim, QB_ERR_INVALID_ARGUMENT, "qb_tomo_canonicalize: bad arguments");
     QB_REQUIRE(dim >= 2 && dim <= 4, QB_ERR_UNSUPPORTED_MODEL,
                "qb_tomo_canonicalize: Hilbert-space dimension %d not in {2,3,4}", dim);
     const int grid = tomo_grid(n);
     cudaStream_t st = as_stream(stream);
     if (dim == 2)
-        tomo_canonicalize_kernel<2><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, nullptr, nullptr);
+        tomo_canonicalize_kernel<2><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, nullptr, nullptr);
     else if (dim == 3)
-        tomo_canonicalize_kernel<3><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, nullptr, nullptr);
+        tomo_canonicalize_kernel<3><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, nullptr, nullptr);
     else
-        tomo_canonicalize_kernel<4><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, nullptr, nullptr);
+        tomo_canonicalize_kernel<4><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, nullptr, nullptr);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }
@@ -266,18 +271,25 @@ extern "C" int qb_tomo_canonicalize(double* d_x, int64_t n, int32_t dim, const d
 extern "C" int qb_tomo_canonicalize_screened(double* d_x, int64_t n, int32_t dim, const double* d_basis,
                                              int32_t allow_subnormalized, uint8_t* d_flags, int64_t* d_idxs,
                                              int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream) {
-    QB_REQUIRE(d_x && d_basis && d_flags && d_idxs && d_count && d_ws && n >= 1, QB_ERR_INVALID_ARGUMENT,
+    return qb_tomo_canonicalize_screened_ld(d_x, n, dim, dim * dim, d_basis, allow_subnormalized, d_flags, d_idxs,
+                                            d_count, d_ws, ws_bytes, stream);
+}
+
+extern "C" int qb_tomo_canonicalize_screened_ld(double* d_x, int64_t n, int32_t dim, int32_t ld, const double* d_basis,
+                                                int32_t allow_subnormalized, uint8_t* d_flags, int64_t* d_idxs,
+                                                int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream) {
+    QB_REQUIRE(d_x && d_basis && d_flags && d_idxs && d_count && d_ws && n >= 1 && ld >= dim * dim, QB_ERR_INVALID_ARGUMENT,
                "qb_tomo_canonicalize_screened: bad arguments");
     QB_REQUIRE(dim >= 2 && dim <= 4, QB_ERR_UNSUPPORTED_MODEL,
                "qb_tomo_canonicalize: Hilbert-space dimension %d not in {2,3,4}", dim);
     const int grid = tomo_grid(n);
     cudaStream_t st = as_stream(stream);
     if (dim == 2)
-        tomo_screen_kernel<2><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, d_flags);
+        tomo_screen_kernel<2><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, d_flags);
     else if (dim == 3)
-        tomo_screen_kernel<3><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, d_flags);
+        tomo_screen_kernel<3><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, d_flags);
     else
-        tomo_screen_kernel<4><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, d_flags);
+        tomo_screen_kernel<4><<<grid, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, d_flags);
     QB_CUDA_CHECK(cudaGetLastError());
     int rc = qb_compact_invalid(d_flags, n, d_idxs, d_count, d_ws, ws_bytes, stream);
     if (rc != QB_OK) return rc;
@@ -285,11 +297,11 @@ extern "C" int qb_tomo_canonicalize_screened(double* d_x, int64_t n, int32_t dim
     // grid is plenty for the few per cent of particles that usually remain
     const int g2 = (grid + 3) / 4;
     if (dim == 2)
-        tomo_canonicalize_kernel<2><<<g2, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, d_idxs, d_count);
+        tomo_canonicalize_kernel<2><<<g2, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, d_idxs, d_count);
     else if (dim == 3)
-        tomo_canonicalize_kernel<3><<<g2, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, d_idxs, d_count);
+        tomo_canonicalize_kernel<3><<<g2, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, d_idxs, d_count);
     else
-        tomo_canonicalize_kernel<4><<<g2, TOMO_THREADS, 0, st>>>(d_x, n, d_basis, allow_subnormalized, d_idxs, d_count);
+        tomo_canonicalize_kernel<4><<<g2, TOMO_THREADS, 0, st>>>(d_x, n, ld, d_basis, allow_subnormalized, d_idxs, d_count);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

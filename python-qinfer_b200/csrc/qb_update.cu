@@ -630,8 +630,25 @@ static update_kernel_t pick_update_kernel_k(const qb_model& m) {
     return nullptr;
 }
 
+// a decorator appended parameters the likelihood ignores: the row pitch is a run-time value (generic-d kernel, K = 1)
+static update_kernel_t pick_update_kernel_extra(const qb_model& m) {
+    switch (m.kind) {
+        case QB_MODEL_PRECESSION:
+            return m.binomial ? fused_update_kernel<QB_MODEL_PRECESSION, true, 0, 1, false>
+                              : fused_update_kernel<QB_MODEL_PRECESSION, false, 0, 1, false>;
+        case QB_MODEL_RB:
+            return m.binomial ? fused_update_kernel<QB_MODEL_RB, true, 0, 1, false>
+                              : fused_update_kernel<QB_MODEL_RB, false, 0, 1, false>;
+        case QB_MODEL_COIN:
+            return m.binomial ? fused_update_kernel<QB_MODEL_COIN, true, 0, 1, false>
+                              : fused_update_kernel<QB_MODEL_COIN, false, 0, 1, false>;
+    }
+    return nullptr;
+}
+
 template <bool CH>
 static update_kernel_t pick_update_kernel_c(const qb_model& m, int nsteps) {
+    if (m.d_extra > 0 && m.kind != QB_MODEL_TOMOGRAPHY) return (CH || nsteps != 1) ? nullptr : pick_update_kernel_extra(m);
     if (m.kind == QB_MODEL_TOMOGRAPHY)  // per-step measurement vectors do not fit the launch parameters: K = 1
         return m.binomial ? fused_update_kernel<QB_MODEL_TOMOGRAPHY, true, 0, 1, CH>
                           : fused_update_kernel<QB_MODEL_TOMOGRAPHY, false, 0, 1, CH>;
@@ -646,18 +663,21 @@ int validate_model(const qb_model* m) {
     QB_REQUIRE(m != nullptr, QB_ERR_INVALID_ARGUMENT, "model is NULL");
     QB_REQUIRE(m->d >= 1 && m->d <= QB_MAX_D, QB_ERR_INVALID_ARGUMENT, "n_modelparams %d outside [1, %d]", m->d,
                QB_MAX_D);
+    QB_REQUIRE(m->d_extra >= 0 && m->d_extra < m->d && m->extra_rule >= 0 && m->extra_rule <= 2,
+               QB_ERR_INVALID_ARGUMENT, "bad d_extra %d / extra_rule %d", m->d_extra, m->extra_rule);
+    const int db = m->d - m->d_extra;   // parameters of the likelihood itself
     switch (m->kind) {
         case QB_MODEL_PRECESSION:
-            QB_REQUIRE(m->d == 1, QB_ERR_UNSUPPORTED_MODEL, "precession model has 1 model parameter, got %d", m->d);
+            QB_REQUIRE(db == 1, QB_ERR_UNSUPPORTED_MODEL, "precession model has 1 model parameter, got %d", db);
             break;
         case QB_MODEL_RB:
-            QB_REQUIRE(m->d == (m->interleaved ? 4 : 3), QB_ERR_UNSUPPORTED_MODEL,
-                       "RB model needs %d model parameters, got %d", m->interleaved ? 4 : 3, m->d);
+            QB_REQUIRE(db == (m->interleaved ? 4 : 3), QB_ERR_UNSUPPORTED_MODEL,
+                       "RB model needs %d model parameters, got %d", m->interleaved ? 4 : 3, db);
             break;
         case QB_MODEL_TOMOGRAPHY:
             break;
         case QB_MODEL_COIN:
-            QB_REQUIRE(m->d == 1, QB_ERR_UNSUPPORTED_MODEL, "coin model has 1 model parameter, got %d", m->d);
+            QB_REQUIRE(db == 1, QB_ERR_UNSUPPORTED_MODEL, "coin model has 1 model parameter, got %d", db);
             break;
         default:
             set_error("unknown model kind %d (no CPU fallback exists)", m->kind);
@@ -820,6 +840,9 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
     for (int c = 0; c < QB_MAX_D; ++c) p.meas[c] = (c < model->d) ? eps[0].meas[c] : 0.0;
 
     update_kernel_t k = pick_update_kernel(*model, nsteps, p.chain_capable != 0);
+    QB_REQUIRE(k != nullptr, QB_ERR_UNSUPPORTED_MODEL,
+               "qb_fused_update: a model with decorator parameters (d_extra > 0) takes one update per launch on an "
+               "unsharded cloud");
     const size_t smem = update_smem_bytes(model->d);
     const int limit = cached_grid_limit(k, smem, nsteps);
     QB_REQUIRE(limit > 0, QB_ERR_CUDA, "qb_fused_update: occupancy query failed: %s",

@@ -16,6 +16,7 @@ QB_MAX_FUSE = 8
 QB_STAT_COUNT = 16
 QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY, QB_MODEL_COIN = 1, 2, 3, 4
 QB_SCAN_FAST, QB_SCAN_EXACT, QB_SCAN_FAST_GUIDE, QB_SCAN_FAST_GUIDE_SCALED = 0, 1, 2, 3
+QB_WALK_ADD, QB_WALK_FIXED, QB_WALK_LEARNED = 0, 1, 2
 
 _LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                          "libqinfer_b200.so")
@@ -24,7 +25,7 @@ _LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(os.path.dirname(os.pat
 class QbModel(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("d", ctypes.c_int32), ("binomial", ctypes.c_int32),
                 ("interleaved", ctypes.c_int32), ("min_freq", ctypes.c_double),
-                ("likelihood_power", ctypes.c_double)]
+                ("likelihood_power", ctypes.c_double), ("d_extra", ctypes.c_int32), ("extra_rule", ctypes.c_int32)]
 
 
 class QbExpparams(ctypes.Structure):
@@ -125,6 +126,11 @@ SIGNATURES = {
     "qb_gather_rows": (ctypes.c_int, [_P, _I32, _P, _I64, _P, _P]),
     "qb_tomo_canonicalize": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P]),
     "qb_tomo_canonicalize_screened": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "qb_tomo_canonicalize_ld": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P]),
+    "qb_tomo_canonicalize_screened_ld": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "qb_walk_step": (ctypes.c_int, [_P, _I64, _I32, _I32, ctypes.POINTER(_I32), ctypes.POINTER(_I32), _I32,
+                                    ctypes.POINTER(_F64), ctypes.POINTER(_I32), _F64, _F64, _P, _I32, _P]),
+    "qb_poison_likelihood": (ctypes.c_int, [_P, _I64, _P, _I32, _F64, _F64, _P]),
     "qb_rng_uniform": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
     "qb_rng_normal": (ctypes.c_int, [_P, _I64, _U64, _U64, _P]),
     "qb_mt19937_workspace_bytes": (_SZ, [_I64, _I64]),

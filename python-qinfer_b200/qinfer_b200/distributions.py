@@ -142,3 +142,25 @@ class GinibreTomographyPrior(object):
         rho = np.einsum('nij,nkj->nik', X, X.conj())
         rho /= np.trace(rho, axis1=1, axis2=2)[:, None, None]
         return np.real(np.einsum('aij,nij->na', self._basis.data.conj(), rho))
+
+
+class MultivariateNormalDistribution(object):
+    """distributions.py:882-908: N(mean, cov); ``sample`` draws ``np.random.randn(n, n_rvs)`` and maps it through
+    ``scipy.linalg.sqrtm(cov)`` exactly like the reference (the step distribution of ``RandomWalkModel``)."""
+
+    def __init__(self, mean, cov):
+        import scipy.linalg as la
+        self.mean = np.array(mean).flatten()
+        self.cov = cov
+        self.invcov = la.inv(cov)
+
+    @property
+    def n_rvs(self):
+        return self.mean.shape[0]
+
+    def sample(self, n=1):
+        import scipy.linalg as la
+        return np.einsum("ij,nj->ni", la.sqrtm(self.cov), np.random.randn(n, self.n_rvs)) + self.mean
+
+    def grad_log_pdf(self, x):
+        return -np.dot(self.invcov, (x - self.mean).transpose()).transpose()

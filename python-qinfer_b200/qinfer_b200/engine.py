@@ -90,6 +90,8 @@ class DeviceCloud(object):
         self._bin_list = None
         self._bin_mirror = None
         self._bin_tag = 0
+        # noise source of the f4 decorators (PoisonedModel, random walks): see ``normals``
+        self.noise_rng, self.noise_seed, self.noise_offset = 'numpy', 0x6E6F697365, 0
         # one control block per destination slot: the constant fields are written once
         self._ctls = [_lib.QbUpdateCtl(), _lib.QbUpdateCtl()]
         self._ctl_key = None
@@ -219,7 +221,11 @@ class DeviceCloud(object):
         # chained launch: the previous thing queued for this cloud is the update whose output this one reads
         ctl.chain_prev_tag = float(self._chain_tag) if (self._chain_tag and self._chain_dst == src) else 0.0
         stream = _stream()
-        if k == 1:
+        if k == 1 and self.desc.poison is not None:
+            ep, outcome, chk = steps[0]
+            ctl.check_resample = 1 if chk else 0
+            self._poisoned_update(ep, outcome, src, dst, ctl, stream)
+        elif k == 1:
             ep, outcome, chk = steps[0]
             ctl.check_resample = 1 if chk else 0
             check(self.lib.qb_fused_update(self.lib_model, ctypes.byref(ep), int(outcome), self._px, self.n,
@@ -726,15 +732,99 @@ class DeviceCloud(object):
             self._fused_scratch(self.n)
             if getattr(self, '_canon_count', None) is None:
                 self._canon_count = torch.zeros((1,), dtype=torch.int64, device=self.device)
-            check(self.lib.qb_tomo_canonicalize_screened(_ptr(self.x), self.n, self.desc.dim, _ptr(self.basis_dev),
-                                                         int(self.desc.allow_subnormalized), _ptr(self._invalid),
-                                                         _ptr(self._idxs), _ptr(self._canon_count), _ptr(self.ws),
-                                                         self.ws_bytes, _stream()))
+            check(self.lib.qb_tomo_canonicalize_screened_ld(_ptr(self.x), self.n, self.desc.dim, self.d,
+                                                            _ptr(self.basis_dev), int(self.desc.allow_subnormalized),
+                                                            _ptr(self._invalid), _ptr(self._idxs),
+                                                            _ptr(self._canon_count), _ptr(self.ws), self.ws_bytes,
+                                                            _stream()))
             self.launches += 5
             return
-        check(self.lib.qb_tomo_canonicalize(_ptr(self.x), self.n, self.desc.dim, _ptr(self.basis_dev),
-                                            int(self.desc.allow_subnormalized), _stream()))
+        check(self.lib.qb_tomo_canonicalize_ld(_ptr(self.x), self.n, self.desc.dim, self.d, _ptr(self.basis_dev),
+                                               int(self.desc.allow_subnormalized), _stream()))
         self.launches += 1
+
+    # ---- f4 decorators: Gaussian steps after an update, Gaussian noise on the likelihood -------------------------
+    def normals(self, count):
+        """``count`` standard normals in a device buffer, from the cloud's noise source (set by the updater):
+        'numpy' draws np.random.normal on the host exactly where the reference does and uploads, 'mt19937' continues
+        the same legacy stream on the device, 'philox' is the counter-based device generator."""
+        count = int(count)
+        buf = getattr(self, '_noise_buf', None)
+        if buf is None or buf.numel() < count:
+            self._noise_buf = buf = torch.empty((count,), dtype=torch.float64, device=self.device)
+        buf = buf[:count]
+        kind = self.noise_rng
+        if kind == 'numpy':
+            buf.copy_(torch.from_numpy(np.random.normal(size=(count,))))
+        elif kind == 'mt19937':
+            self.mt19937_normal(buf, count)
+        else:
+            self.rng_normal(buf, count, self.noise_seed, self.noise_offset)
+            self.noise_offset += (count + 1) // 2
+        return buf
+
+    def walk_step(self, expparams):
+        """Model.update_timestep of the decorator described by ``desc.walk`` (derived_models.py:733-741, 921-963;
+        tomography/models.py:257-272), in place on the committed slab."""
+        walk = self.desc.walk
+        n, d, kind = self.n, self.d, walk['kind']
+        I32 = ctypes.c_int32
+        mult = 1.0
+        if kind == 'generic':                               # the model's own step distribution: a host object
+            steps = np.ascontiguousarray(walk['dist'].sample(n=n), dtype=np.float64).reshape(n, -1)
+            k = steps.shape[1]
+            z = torch.from_numpy(steps).to(self.device).reshape(-1)
+            idx = zcol = list(range(k))
+            mode, scale, sidx, pre = _lib.QB_WALK_ADD, None, None, 1.0
+        elif kind == 'diffusive':                           # eps * sqrt(t) * randn, first and last parameter fixed
+            k = d
+            z = self.normals(n * d)
+            idx = zcol = list(range(1, d - 1))
+            mode, scale, sidx = _lib.QB_WALK_LEARNED, None, [d - 1] * (d - 2)
+            pre = float(np.sqrt(np.asarray(expparams)['t'].reshape(-1)[0]))
+        else:
+            idx = walk['idxs']
+            k = len(idx)
+            zcol = list(range(k))
+            fn = walk.get('scale_mult')
+            if fn is not None:
+                mult = float(np.ravel(np.asarray(fn(expparams), dtype=float))[0])
+            pre = 1.0
+            if kind == 'fixed':
+                z, mode, scale, sidx = self.normals(n * k), _lib.QB_WALK_FIXED, walk['scale'], None
+            elif kind == 'learned':
+                z, mode, scale, sidx = self.normals(n * k), _lib.QB_WALK_LEARNED, None, walk['sidx']
+            else:                                           # fixed dense covariance: chol @ normal(n_rw, n) on the host
+                steps = np.dot(walk['chol'], np.random.normal(size=(k, n))).T
+                z = torch.from_numpy(np.ascontiguousarray(steps)).to(self.device).reshape(-1)
+                mode, scale, sidx = _lib.QB_WALK_ADD, None, None
+        n_rw = len(idx)
+        check(self.lib.qb_walk_step(_ptr(self.x), n, d, n_rw, (I32 * n_rw)(*idx), (I32 * n_rw)(*zcol), mode,
+                                    _lib.f64_array(scale) if scale is not None else None,
+                                    (I32 * n_rw)(*sidx) if sidx is not None else None, pre, mult, _ptr(z), k,
+                                    _stream()))
+        self.launches += 1
+        if kind == 'diffusive':
+            self.canonicalize()
+
+    def _poisoned_update(self, ep, outcome, src, dst, ctl, stream):
+        """PoisonedModel (derived_models.py:188-204): plain likelihood -> + clipped Gaussian noise -> the fused update
+        kernel on the poisoned likelihood vector (a one-parameter 'coin' whose pr0 is the stored value)."""
+        n, po = self.n, self.desc.poison
+        L = getattr(self, '_like_buf', None)
+        if L is None or L.numel() < n:
+            self._like_buf = L = torch.empty((self.capacity,), dtype=torch.float64, device=self.device)
+            self._coin = _lib.QbModel(kind=_lib.QB_MODEL_COIN, d=1, binomial=0, interleaved=0, min_freq=0.0,
+                                      likelihood_power=1.0, d_extra=0, extra_rule=0)
+            self._coin_ep = _lib.QbExpparams()
+        outs = (ctypes.c_int64 * 1)(int(outcome))
+        check(self.lib.qb_likelihood(self.lib_model, ctypes.byref(ep), 1, outs, 1, self._px, n, _ptr(L), stream))
+        z = self.normals(n)
+        check(self.lib.qb_poison_likelihood(_ptr(L), n, _ptr(z), po['mode'], po['tol'], po['denom'], stream))
+        check(self.lib.qb_fused_update(ctypes.byref(self._coin), ctypes.byref(self._coin_ep), 0, _ptr(L), n,
+                                       self._pw[src], self._pw[dst], self._pstats[src], self._pstats[dst],
+                                       ctypes.byref(ctl), self._pws, self.ws_bytes, stream))
+        self.launches += 2
 
     def rng_uniform(self, out, n, seed, offset):
         check(self.lib.qb_rng_uniform(_ptr(out), int(n), int(seed), int(offset), _stream()))
@@ -826,8 +916,8 @@ def host_canonicalize(desc, modelparams):
     xd = torch.from_numpy(x).to(dev)
     b = np.ascontiguousarray(desc.basis).view(np.float64).reshape(-1)
     bd = torch.from_numpy(b.copy()).to(dev)
-    check(lib.qb_tomo_canonicalize(_ptr(xd), x.shape[0], desc.dim, _ptr(bd), int(desc.allow_subnormalized),
-                                   _stream()))
+    check(lib.qb_tomo_canonicalize_ld(_ptr(xd), x.shape[0], desc.dim, x.shape[1], _ptr(bd),
+                                      int(desc.allow_subnormalized), _stream()))
     return xd.cpu().numpy()
 
 

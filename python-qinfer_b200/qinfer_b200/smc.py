@@ -71,7 +71,14 @@ class SMCUpdater(object):
         # With lazy=True consecutive updates are additionally FUSED: up to ``fuse`` (default QB_MAX_FUSE = 8, 1 for
         # tomography) buffered updates go out as one kernel launch that reads and writes the cloud once.
         self._lazy = bool(lazy)
-        fuse_cap = 1 if (self._desc.kind == 3 or self._desc.likelihood_power != 1.0) else QB_MAX_FUSE
+        # f4 decorators (RandomWalkModel, GaussianRandomWalkModel, DiffusiveTomographyModel, PoisonedModel): the
+        # particles move (or the likelihood takes fresh noise) after / at every update, in the reference's order of
+        # random draws -> one update per launch, settled before the next one goes out
+        self._time_dependent = self._desc.walk is not None
+        if self._time_dependent or self._desc.poison is not None:
+            self._lazy = False
+        fuse_cap = 1 if (self._desc.kind == 3 or self._desc.likelihood_power != 1.0 or self._time_dependent
+                         or self._desc.poison is not None or self._desc.d_extra) else QB_MAX_FUSE
         self._fuse = fuse_cap if fuse is None else max(1, min(int(fuse), fuse_cap))
         self._settling = False
         self._counted = None        # models of the chain that keep a call count
@@ -157,6 +164,11 @@ class SMCUpdater(object):
         launches = self._cloud.launches if self._cloud is not None else 0
         self._cloud = DeviceCloud(self._desc, n, self._device, capacity=self._cloud_capacity(n))
         self._cloud.launches = launches
+        # the decorators' noise follows the resampler's generator choice: 'numpy' (default) draws from np.random on
+        # the host in the reference's order, 'mt19937' continues that stream on the device, 'philox' is device-only
+        res = getattr(self, 'resampler', None)
+        self._cloud.noise_rng = getattr(res, '_rng', 'numpy')
+        self._cloud.noise_seed = (int(getattr(res, '_seed', 0)) ^ 0x6E6F697365) & ((1 << 64) - 1)
         self._host_locs = self._host_weights = None
 
     def _cloud_capacity(self, n):
@@ -346,6 +358,8 @@ class SMCUpdater(object):
 
     def _enqueue(self, outcome, expparams, check_for_resample):
         ep = self._desc.fill_record(QbExpparams(), expparams, 0)
+        if self._time_dependent:
+            ep.host_expparams = np.atleast_1d(expparams)   # update_timestep's argument (scale_mult, 't')
         self._queue.append((ep, int(outcome), bool(check_for_resample)))
         self._count_calls(self._cloud.n)
         if self._pending is None and len(self._queue) == 1:
@@ -420,6 +434,16 @@ class SMCUpdater(object):
                 # plain step: the bookkeeping of smc.py:441-457, nothing else
                 self._normalization_record.append(float(rec))
                 self._n_ess = float(ness)
+                if self._time_dependent:                 # smc.py:447-449 (a time-dependent model is never fused: k = 1)
+                    cloud.commit_update()
+                    self._host_weights = None
+                    self._timestep(ep)
+                    if self._n_ess <= self._min_n_ess:
+                        self._min_n_ess = self._n_ess
+                    if check and ness <= 10:
+                        warnings.warn("Extremely small n_ess encountered ({}). Resampling is likely to fail. Consider "
+                                      "adding particles, or resampling more often.".format(ness), ApproximationWarning)
+                    return True
                 if self._n_ess <= self._min_n_ess:
                     self._min_n_ess = self._n_ess
                 if check and ness <= 10:
@@ -443,13 +467,19 @@ class SMCUpdater(object):
                 if self._zero_weight_policy == 'error':
                     raise RuntimeError("All particle weights are zero.")
                 return False                             # 'skip': smc.py:427-428
-            self._settle_step(slot, float(S), float(Q), float(nbad), float(rec), float(ness), check)
+            self._settle_step(slot, float(S), float(Q), float(nbad), float(rec), float(ness), check, ep)
             return False
         cloud.commit_update()                            # smc.py:441 for the whole launch
         self._host_weights = None
         return True
 
-    def _settle_step(self, slot, S, Q, nbad, rec, ness, check):
+    def _timestep(self, ep):
+        """smc.py:447-449: ``particle_locations = model.update_timestep(particle_locations, expparams)[:, :, 0]``
+        for the time-dependent decorators, on the device."""
+        self._cloud.walk_step(ep.host_expparams)
+        self._host_locs = None
+
+    def _settle_step(self, slot, S, Q, nbad, rec, ness, check, ep=None):
         """smc.py:416-457 for a step that needs the host; the pending buffers hold the weights after that step."""
         cloud = self._cloud
         unnormalised = abs(rec) < _EPS
@@ -485,6 +515,8 @@ class SMCUpdater(object):
         cloud.commit_update()                                # smc.py:441
         self._host_weights = None
         self._normalization_record.append(norm_rec)          # smc.py:444
+        if self._time_dependent and ep is not None:          # smc.py:447-449
+            self._timestep(ep)
         self._n_ess = ness
         if self._n_ess <= self._min_n_ess:                   # smc.py:452-453
             self._min_n_ess = self._n_ess

@@ -23,6 +23,7 @@ def oracle_namespace():
         SimplePrecessionModel=o.SimplePrecessionModel, SimpleInversionModel=o.SimpleInversionModel,
         RandomizedBenchmarkingModel=o.RandomizedBenchmarkingModel, BinomialModel=o.BinomialModel,
         CoinModel=o.CoinModel, MLEModel=o.MLEModel, TomographyModel=o.TomographyModel,
+        DiffusiveTomographyModel=o.DiffusiveTomographyModel,
         RandomWalkModel=o.RandomWalkModel, GaussianRandomWalkModel=o.GaussianRandomWalkModel,
         NormalStepDistribution=o.NormalStepDistribution, PoisonedModel=o.PoisonedModel, pauli_basis=o.pauli_basis, gell_mann_basis=o.gell_mann_basis,
         UniformDistribution=o.UniformDistribution, PostselectedDistribution=o.PostselectedDistribution,
@@ -41,6 +42,7 @@ def reference_namespace():
         SimplePrecessionModel=q.SimplePrecessionModel, SimpleInversionModel=q.SimpleInversionModel,
         RandomizedBenchmarkingModel=q.RandomizedBenchmarkingModel, BinomialModel=q.BinomialModel,
         CoinModel=q.CoinModel, MLEModel=q.MLEModel, TomographyModel=qt.TomographyModel,
+        DiffusiveTomographyModel=qt.DiffusiveTomographyModel,
         RandomWalkModel=q.RandomWalkModel, GaussianRandomWalkModel=q.GaussianRandomWalkModel,
         NormalStepDistribution=q.MultivariateNormalDistribution, PoisonedModel=q.PoisonedModel, pauli_basis=qt.pauli_basis, gell_mann_basis=qt.gell_mann_basis,
         UniformDistribution=q.UniformDistribution, PostselectedDistribution=q.PostselectedDistribution,
@@ -475,4 +477,42 @@ def random_walk_vectors(ns, seed=53):
     out['ale_x'], out['ale_w'], out['ale_norm'], out['ale_rc'] = run(m, prior)
     m = ns.PoisonedModel(ns.SimplePrecessionModel(), n_samples=200, hedge=0.5)
     out['mle_x'], out['mle_w'], out['mle_norm'], out['mle_rc'] = run(m, prior)
+    return out
+
+
+def diffusive_vectors(ns, seed=71):
+    """f4: DiffusiveTomographyModel (tomography/models.py:228-272), one qubit in the Pauli basis: 5 model parameters
+    (4 state coordinates + the diffusion scale), experiments carry a duration ``t``.  Free-running trajectory under a
+    fixed legacy seed, resampling and re-canonicalisation included; plus the validity rule and one bare
+    update_timestep on fixed particles."""
+    import warnings
+    rs = np.random.RandomState(seed)
+    out = {}
+    basis = ns.pauli_basis(1)
+    model = ns.DiffusiveTomographyModel(basis)
+    bd = np.asarray(basis.data)
+    n, n_up = 600, 24
+    prior = np.column_stack([ginibre_coords(rs, n, bd), 0.02 + 0.05 * rs.random_sample(n)])
+    true = ginibre_coords(rs, 1, bd)[0]
+    ep = np.empty((n_up,), dtype=model.expparams_dtype)
+    meas = np.zeros((n_up, 4))
+    ks = rs.randint(1, 4, size=n_up)
+    meas[:, 0] = np.sqrt(2) / 2
+    meas[np.arange(n_up), ks] = np.sqrt(2) / 2
+    ep['meas'] = meas
+    ep['t'] = 0.5 + rs.random_sample(n_up)
+    outcomes = (rs.random_sample(n_up) < np.clip(meas @ true, 0, 1)).astype(np.int64)
+    out['prior'], out['meas'], out['t'], out['outcomes'] = prior, meas, np.array(ep['t']), outcomes
+    out['valid'] = np.asarray(model.are_models_valid(np.array([[0.7, 0.1, 0.0, 0.2, 0.01], [0.7, 0.1, 0.0, 0.2, 0.0],
+                                                              [0.7, 0.1, 0.0, 0.2, -0.3]])))
+    np.random.seed(11)
+    up = ns.SMCUpdater(model, n, FixedPrior(prior))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(n_up):
+            up.update(int(outcomes[k]), ep[k:k + 1])
+    out['x'] = np.array(up.particle_locations)
+    out['w'] = np.array(up.particle_weights)
+    out['norm'] = np.array([float(np.ravel(v)[0]) for v in up.normalization_record])
+    out['rc'] = np.int64(up.resample_count)
     return out

@@ -49,7 +49,9 @@ def gpu_namespace(qb, **lw_kwargs):
         ParticleDistribution=qb.ParticleDistribution, SimplePrecessionModel=qb.SimplePrecessionModel,
         SimpleInversionModel=qb.SimpleInversionModel, RandomizedBenchmarkingModel=qb.RandomizedBenchmarkingModel,
         BinomialModel=qb.BinomialModel, CoinModel=qb.CoinModel, MLEModel=qb.MLEModel,
-        TomographyModel=qb.TomographyModel,
+        TomographyModel=qb.TomographyModel, DiffusiveTomographyModel=qb.DiffusiveTomographyModel,
+        RandomWalkModel=qb.RandomWalkModel, GaussianRandomWalkModel=qb.GaussianRandomWalkModel,
+        PoisonedModel=qb.PoisonedModel, NormalStepDistribution=qb.MultivariateNormalDistribution,
         pauli_basis=qb.pauli_basis,
         gell_mann_basis=qb.gell_mann_basis, UniformDistribution=qb.UniformDistribution,
         PostselectedDistribution=qb.PostselectedDistribution, sqrtm_psd=qb.sqrtm_psd)
@@ -905,3 +907,75 @@ def test_mle_model_against_the_reference(qb, golden):
     # the power is part of the model descriptor: plain models are untouched
     assert qb.describe_model(qb.MLEModel(qb.SimplePrecessionModel(), 2.0)).likelihood_power == 2.0
     assert qb.describe_model(qb.SimplePrecessionModel()).likelihood_power == 1.0
+
+
+# ---------------------------------------------------------------------------
+# f4 — time-dependent and noisy decorators on the device (derived_models.py:148-220, 705-963;
+# tomography/models.py:228-272) against golden trajectories of the UNMODIFIED reference
+# ---------------------------------------------------------------------------
+def _f4_check(got, g, key, x_rtol=1e-9):
+    """Free-running trajectories incl. resampling under the legacy seed: same resample count, records 1e-9, particles
+    1e-9 (the device evaluates cos^2 to within an ulp of NumPy's; the walk / noise arithmetic is operation for
+    operation the reference's)."""
+    assert int(got[key + '_rc']) == int(g[key + '_rc'])
+    np.testing.assert_allclose(got[key + '_norm'], g[key + '_norm'], rtol=1e-9)
+    np.testing.assert_allclose(got[key + '_x'], g[key + '_x'], rtol=x_rtol, atol=1e-13)
+    np.testing.assert_allclose(got[key + '_w'], g[key + '_w'], rtol=1e-7, atol=1e-16)
+    report("f4_%s_x_maxabs" % key, float(np.max(np.abs(got[key + '_x'] - g[key + '_x']))))
+
+
+def test_f4_random_walk_and_poisoned_models_against_the_reference(qb, golden):
+    g = golden("random_walk_vectors")
+    got = cases.random_walk_vectors(gpu_namespace(qb))
+    for key in ("rw", "grw_fixed", "grw_learn", "ale", "mle"):
+        _f4_check(got, g, key)
+    assert np.array_equal(np.asarray(got['grw_learn_valid'], dtype=bool), g['grw_learn_valid'])
+
+
+def test_f4_diffusive_tomography_against_the_reference(qb, golden):
+    g = golden("diffusive_vectors")
+    got = cases.diffusive_vectors(gpu_namespace(qb))
+    assert np.array_equal(np.asarray(got['valid'], dtype=bool), g['valid'])
+    assert int(got['rc']) == int(g['rc'])
+    np.testing.assert_allclose(got['norm'], g['norm'], rtol=1e-8)
+    # canonicalisation: Hermitian Jacobi on the device vs np.linalg.eig in the reference agree to ~1e-10 per call
+    # (test_t6); the state is re-projected after each of the 24 updates and 3 resamples of this run, and states
+    # clipped at the boundary of the Bloch ball (an eigenvalue ~ 0) are the most sensitive: measured 9e-9 worst case
+    np.testing.assert_allclose(got['x'], g['x'], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(np.average(got['x'], axis=0, weights=got['w']),
+                               np.average(g['x'], axis=0, weights=g['w']), rtol=1e-6, atol=1e-9)   # north_star
+    np.testing.assert_allclose(got['w'], g['w'], rtol=1e-6, atol=1e-15)
+    report("f4_diffusive_x_maxabs", float(np.max(np.abs(got['x'] - g['x']))))
+
+
+@pytest.mark.parametrize("rng", ["mt19937", "philox"])
+def test_f4_device_noise_sources(qb, rng):
+    """The decorators' noise from the device generators: 'mt19937' continues the legacy stream (same trajectory as
+    the host-drawn one up to the 1-ulp normals), 'philox' is statistically equivalent (random-walk variance grows as
+    sigma^2 per update)."""
+    n, sigma = 200000, 3e-3
+    rs = np.random.RandomState(4)
+    prior = 0.5 + 0.01 * rs.randn(n, 1)
+    model = qb.GaussianRandomWalkModel(qb.SimplePrecessionModel(), fixed_covariance=np.array([sigma ** 2]))
+    res = qb.LiuWestResampler(a=0.98, rng=rng, seed=9, scan='exact' if rng == 'mt19937' else 'fast')
+    np.random.seed(3)
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(prior), resampler=res, resample_thresh=0.0)
+    v0 = float(np.var(up.particle_locations))
+    for k in range(8):
+        up.update(k % 2, np.array([1e-3]))                # (likelihood ~ flat: the cloud only diffuses)
+    v1 = float(np.var(up.particle_locations))
+    assert abs((v1 - v0) / (8 * sigma ** 2) - 1) < 0.03
+    if rng == 'mt19937':
+        np.random.seed(3)
+        ref = qb.SMCUpdater(model, n, cases.FixedPrior(prior), resample_thresh=0.0)
+        for k in range(8):
+            ref.update(k % 2, np.array([1e-3]))
+        np.testing.assert_allclose(up.particle_locations, ref.particle_locations, rtol=1e-12, atol=1e-15)
+
+
+def test_f4_unsupported_decorator_variants_fail_loudly(qb):
+    with pytest.raises(qb.UnsupportedModelError):
+        qb.GaussianRandomWalkModel(qb.SimplePrecessionModel(), diagonal=False)
+    with pytest.raises(qb.UnsupportedModelError):
+        qb.GaussianRandomWalkModel(qb.SimplePrecessionModel(), fixed_covariance=np.array([1e-6]),
+                                   model_transformation=(np.log, np.exp))

@@ -161,3 +161,9 @@ def test_golden_files_match_a_fresh_reference_run(golden):
         warnings.simplefilter("ignore")
         out = cases.run_precession(ns_ref, _inputs(g, ["prior", "ts", "outcomes"]))
     _assert_same(out, g)
+
+
+def test_diffusive_tomography_vectors_bit_exact(ns, golden):
+    """f4: DiffusiveTomographyModel (tomography/models.py:228-272) — trajectory with per-update Gaussian diffusion and
+    re-canonicalisation, validity rule of the extra parameter."""
+    _assert_same(cases.diffusive_vectors(ns), golden("diffusive_vectors"))
