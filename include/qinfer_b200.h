@@ -345,8 +345,12 @@ int qb_lw_merge_retry(const qb_model* model, const double* d_x_old, int64_t n_ol
  *                         (rounds = retry_rounds, stream offset off_n + round_stride), reporting into h_mirror[4..8).
  *                         d_js_out (may be NULL): the parent of every slot (tests).
  *   qb_lw_binned_retry    up to `rounds` fresh perturbations per still-invalid list entry in ONE launch (round j: normals
- *                         element m * n_new + slot of (seed_n, off_n + j * round_stride)), re-centred on the slot's
- *                         own parent, stopping at the first valid one; resolved entries become -1.  The list length is
+ *                         element m * n_new + slot of (seed_n, off_n + j * round_stride)), stopping at the first valid
+ *                         one; resolved entries become -1.  Re-centred on the slot's own parent (own_mean != 0), or —
+ *                         the reference's law: resamplers.py:372 re-slices `mus = mus[:k]`, so the r-th still-invalid
+ *                         particle is re-centred on the r-th ORIGINAL draw, an i.i.d. draw from the weighted cloud —
+ *                         on the parent of a uniformly random slot (d_parents: the n_new int32 parent indices the move
+ *                         stored; uniform element `slot` of stream (seed_v, off_n + j * round_stride)), fresh each round.  The list length is
  *                         read on the device (a counter in the workspace), so the call may be queued right behind the
  *                         move.  h_mirror (4 doubles) receives {#still invalid, most rounds used, list length, tag}.
  * Workspace: qb_lw_binned_workspace_bytes(n_old, n_new), ZERO-INITIALISED once, private to these three calls. */
@@ -364,13 +368,14 @@ int qb_lw_binned_move(const qb_model* model, const double* d_x_old, const double
                       int64_t n_old, int32_t d, const double* h_mean, const double* h_S, double a,
                       uint64_t seed_v, uint64_t off_v, uint64_t seed_n, uint64_t off_n, int64_t n_new,
                       double* d_x_new, int64_t split, double* d_x_new2, double* d_w_new, int64_t n_global,
-                      double* d_stats_new, int32_t postselect, int32_t retry_rounds, int64_t* d_list,
-                      int64_t* d_js_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
+                      double* d_stats_new, int32_t postselect, int32_t retry_rounds, int32_t own_mean, int64_t* d_list,
+                      int32_t* d_parents, int64_t* d_js_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                      void* stream);
 int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
                        const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
-                       uint64_t round_stride, int32_t rounds, int64_t n_new, double* d_x_new, int64_t split,
-                       double* d_x_new2, int64_t* d_list, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
-                       void* stream);
+                       uint64_t round_stride, int32_t rounds, int32_t own_mean, uint64_t seed_v, int64_t n_new,
+                       double* d_x_new, int64_t split, double* d_x_new2, int64_t* d_list, const int32_t* d_parents,
+                       double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
 
 /* The whole resample queued by ONE call, with no host decision in between: pass 1 additionally derives the Liu-West
  * constants on the device — cov = E[xx^T] - mu mu^T (distributions.py:388-389), a zero Frobenius norm replaced by
@@ -384,8 +389,9 @@ int qb_lw_binned_resample(const qb_model* model, const double* d_x, const double
                           int64_t n_old, int32_t d, int64_t n_new, double a, double h, double zero_cov_comp,
                           uint64_t seed, uint64_t off_u, uint64_t off_v, uint64_t seed_n, uint64_t off_n,
                           double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
-                          int32_t postselect, int32_t retry_rounds, int64_t* d_list, double* d_moments_out,
-                          double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
+                          int32_t postselect, int32_t retry_rounds, int32_t own_mean, int64_t* d_list,
+                          int32_t* d_parents, double* d_moments_out, double* h_mirror, double tag, void* d_ws,
+                          size_t ws_bytes, void* stream);
 
 /* ---- sharded cloud: peer mailboxes and the resample exchange ------------------- */
 #define QB_IPC_HANDLE_BYTES 64

@@ -552,6 +552,9 @@ struct BinMoveParams {
     long long* list;         // invalid slots: slot | parent << 32 (postselect only)
     unsigned long long* counters;  // [0] invalid, [1] clamped draws
     int64_t* js_out;         // optional: global parent index of every slot (tests)
+    int32_t* parents;        // global parent index of every slot (postselect): a uniformly random slot's parent is an
+                             // i.i.d. draw from the weighted cloud — what the reference's retry re-centres on
+    int32_t own_mean, pad1;  // retry: 1 = the slot's own parent, 0 = the reference's law (resamplers.py:372, below)
     double* mirror;          // pinned host: {invalid, clamped, drawn, tag} (may be NULL)
     double tag;
     unsigned int* ticket;
@@ -742,6 +745,7 @@ __global__ void __launch_bounds__(BIN_THREADS, (D <= 2) ? 3 : 2) binned_move_ker
                     for (int c = 0; c < D; ++c) stg_stream(dst + c, out[c]);
                     if (p.w_new != nullptr) stg_stream(p.w_new + i, p.w_value);
                     if (p.js_out != nullptr) p.js_out[i] = first + par[h];
+                    if (p.parents != nullptr) p.parents[i] = static_cast<int32_t>(first + par[h]);
                     if (p.postselect) {
                         auto row = [&](int c) { return out[c]; };
                         if (!model_valid(p.mv, row)) {
@@ -791,14 +795,25 @@ __global__ void __launch_bounds__(128) binned_retry_kernel(const __grid_constant
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < k0; r += stride) {
         const long long e = p.list[r];
         if (e < 0) continue;
-        const int64_t slot = e & 0xffffffffLL, parent = e >> 32;
+        const int64_t slot = e & 0xffffffffLL;
+        int64_t parent = e >> 32;
         double mu[D], out[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) mu[c] = (p.a * __ldg(p.x_old + parent * D + c)) + msl[c];
         bool ok = false;
         int used = 0;
         for (int j = 0; j < p.rounds && !ok; ++j) {
             const uint64_t off = p.off_n + static_cast<uint64_t>(j) * p.round_stride;
+            if (!p.own_mean && p.parents != nullptr) {
+                // The reference re-centres the r-th still-invalid particle on mus[r], the shrunk mean of the r-th
+                // ORIGINAL draw (resamplers.py:372 re-slices `mus = mus[:k]`): an i.i.d. draw from the weighted
+                // cloud, unrelated to the particle's own parent, and a different one every iteration as the invalid
+                // set shrinks.  Same law here: the parent of a uniformly random slot, fresh every round.
+                const double u = philox_uniform_elem(p.seed_v, off, slot);
+                int64_t sl = static_cast<int64_t>(u * static_cast<double>(p.n_new));
+                if (sl >= p.n_new) sl = p.n_new - 1;
+                parent = p.parents[sl];
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) mu[c] = (p.a * __ldg(p.x_old + parent * D + c)) + msl[c];
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double z = 0.0;
@@ -995,6 +1010,9 @@ static int fill_move(BinMoveParams& q, const qb_model* model, const double* d_x_
     q.list = reinterpret_cast<long long*>(d_list);
     q.counters = reinterpret_cast<unsigned long long*>(ws + 64);
     q.js_out = nullptr;
+    q.parents = nullptr;
+    q.own_mean = 1;
+    q.pad1 = 0;
     q.mirror = h_mirror;
     q.tag = tag;
     q.ticket = hdr + 2;
@@ -1034,8 +1052,9 @@ extern "C" int qb_lw_binned_move(const qb_model* model, const double* d_x_old, c
                                  const double* h_S, double a, uint64_t seed_v, uint64_t off_v, uint64_t seed_n,
                                  uint64_t off_n, int64_t n_new, double* d_x_new, int64_t split, double* d_x_new2,
                                  double* d_w_new, int64_t n_global, double* d_stats_new, int32_t postselect,
-                                 int32_t retry_rounds, int64_t* d_list, int64_t* d_js_out, double* h_mirror,
-                                 double tag, void* d_ws, size_t ws_bytes, void* stream) {
+                                 int32_t retry_rounds, int32_t own_mean, int64_t* d_list, int32_t* d_parents,
+                                 int64_t* d_js_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                                 void* stream) {
     BinMoveParams q;
     const BinLayout L = bin_layout(n_old < 1 ? 1 : n_old, n_new < 1 ? 1 : n_new);
     int rc = fill_move(q, model, d_x_old, n_old, d, h_mean, h_S, a, seed_n, off_n, n_new, d_x_new, split, d_x_new2,
@@ -1055,6 +1074,8 @@ extern "C" int qb_lw_binned_move(const qb_model* model, const double* d_x_old, c
     q.stats_new = d_stats_new;
     q.n_global = static_cast<double>(n_global);
     q.js_out = d_js_out;
+    q.parents = postselect ? d_parents : nullptr;
+    q.own_mean = (own_mean || d_parents == nullptr) ? 1 : 0;
     q.postselect = postselect ? 1 : 0;
     q.seed_v = seed_v;
     q.off_v = off_v;
@@ -1084,9 +1105,10 @@ extern "C" int qb_lw_binned_move(const qb_model* model, const double* d_x_old, c
 
 extern "C" int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
                                   const double* h_mean, const double* h_S, double a, uint64_t seed_n, uint64_t off_n,
-                                  uint64_t round_stride, int32_t rounds, int64_t n_new, double* d_x_new, int64_t split,
-                                  double* d_x_new2, int64_t* d_list, double* h_mirror, double tag, void* d_ws,
-                                  size_t ws_bytes, void* stream) {
+                                  uint64_t round_stride, int32_t rounds, int32_t own_mean, uint64_t seed_v, int64_t n_new,
+                                  double* d_x_new, int64_t split, double* d_x_new2, int64_t* d_list,
+                                  const int32_t* d_parents, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                                  void* stream) {
     BinMoveParams q;
     const BinLayout L = bin_layout(n_old < 1 ? 1 : n_old, n_new < 1 ? 1 : n_new);
     int rc = fill_move(q, model, d_x_old, n_old, d, h_mean, h_S, a, seed_n, off_n, n_new, d_x_new, split, d_x_new2,
@@ -1095,6 +1117,9 @@ extern "C" int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, 
     QB_REQUIRE(d_list && rounds >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_retry: bad arguments");
     q.rounds = rounds;
     q.round_stride = round_stride;
+    q.parents = const_cast<int32_t*>(d_parents);
+    q.own_mean = (own_mean || d_parents == nullptr) ? 1 : 0;
+    q.seed_v = seed_v;
     return launch_retry(q, d, as_stream(stream));
 }
 
@@ -1104,8 +1129,9 @@ extern "C" int qb_lw_binned_resample(const qb_model* model, const double* d_x, c
                                      int64_t n_old, int32_t d, int64_t n_new, double a, double h, double zero_cov_comp,
                                      uint64_t seed, uint64_t off_u, uint64_t off_v, uint64_t seed_n, uint64_t off_n,
                                      double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
-                                     int32_t postselect, int32_t retry_rounds, int64_t* d_list, double* d_moments_out,
-                                     double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream) {
+                                     int32_t postselect, int32_t retry_rounds, int32_t own_mean, int64_t* d_list,
+                                     int32_t* d_parents, double* d_moments_out, double* h_mirror, double tag,
+                                     void* d_ws, size_t ws_bytes, void* stream) {
     int rc = validate_model(model);
     if (rc != QB_OK) return rc;
     QB_REQUIRE(n_new >= 1 && n_new < (1LL << 31) && n_old >= 1, QB_ERR_INVALID_ARGUMENT,
@@ -1121,6 +1147,6 @@ extern "C" int qb_lw_binned_resample(const qb_model* model, const double* d_x, c
     rc = qb_lw_binned_count(n_old, n_new, seed, off_u, d_ws, ws_bytes, stream);
     if (rc != QB_OK) return rc;
     return qb_lw_binned_move(model, d_x, d_w, d_stats, n_old, d, nullptr, nullptr, a, seed, off_v, seed_n, off_n, n_new,
-                             d_x_new, n_new, nullptr, d_w_new, n_global, d_stats_new, postselect, retry_rounds, d_list,
-                             nullptr, h_mirror + 32, tag, d_ws, ws_bytes, stream);
+                             d_x_new, n_new, nullptr, d_w_new, n_global, d_stats_new, postselect, retry_rounds, own_mean,
+                             d_list, d_parents, nullptr, h_mirror + 32, tag, d_ws, ws_bytes, stream);
 }

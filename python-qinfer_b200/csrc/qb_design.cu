@@ -7,7 +7,8 @@
 //   N_o     = sum_i w_i L_o,i ;  w_hyp_o,i = w_i L_o,i / N_o
 // Here the last outcome's likelihood is EVALUATED like the others: for the two-outcome models that is the same
 // complement (pr1 = 1 - pr0); for BinomialModel it replaces a difference that cancels to +-1e-16 (and then feeds
-// log() a zero or negative number: the reference returns NaN there) by the pmf itself.
+// log() a zero or negative number: the reference returns NaN there) by the pmf itself.  Under MLEModel (a likelihood
+// power != 1) the likelihoods do not sum to one, so there the reference's complement is formed as written.
 // and then either the posterior variance of every outcome (risk) or its KL divergence from the prior (gain).
 // The (n_o, n) tensors w_hyp and L never exist here: pass 1 reduces, per outcome,
 //   A = sum h,  B_j = sum h (x_j - c_j),  C_j = sum h (x_j - c_j)^2        with h = w_i L_o,i
@@ -38,6 +39,13 @@ template <int KIND, bool BINOM>
 __device__ __forceinline__ double outcome_likelihood(const DesignParams& p, const double* xr, int o) {
     auto row = [&](int c) { return xr[c]; };
     auto meas = [&](int c) { return p.meas[c]; };
+    if (p.mv.like_pow != 1.0 && o == p.n_o - 1 && p.n_o > 1) {
+        // MLEModel: the powered likelihoods no longer sum to one, and the reference DEFINES the last outcome's as
+        // 1 - sum of the others (smc.py:589) — sin^4 versus 1 - cos^4: evaluating it would silently change the risk
+        double s = 0.0;
+        for (int q = 0; q < p.n_o - 1; ++q) s += model_likelihood<KIND, BINOM>(p.mv, p.evs[q], row, meas, 0);
+        return 1.0 - s;
+    }
     return model_likelihood<KIND, BINOM>(p.mv, p.evs[o], row, meas, 0);
 }
 

@@ -108,13 +108,13 @@ SIGNATURES = {
     "qb_lw_binned_prepare": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I64, _U64, _U64, _P, _P, _F64, _P, _SZ, _P]),
     "qb_lw_binned_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _P, _P, _I64, _I32, ctypes.POINTER(_F64),
                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I64, _P, _I64, _P, _P,
-                                         _I64, _P, _I32, _I32, _P, _P, _P, _F64, _P, _SZ, _P]),
+                                         _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _F64, _P, _SZ, _P]),
     "qb_lw_binned_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, ctypes.POINTER(_F64),
-                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _I32, _I64, _P, _I64, _P, _P,
-                                          _P, _F64, _P, _SZ, _P]),
+                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _I32, _I32, _U64, _I64, _P,
+                                          _I64, _P, _P, _P, _P, _F64, _P, _SZ, _P]),
     "qb_lw_binned_resample": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _P, _P, _I64, _I32, _I64, _F64, _F64, _F64,
-                                             _U64, _U64, _U64, _U64, _U64, _P, _P, _I64, _P, _I32, _I32, _P, _P, _P,
-                                             _F64, _P, _SZ, _P]),
+                                             _U64, _U64, _U64, _U64, _U64, _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P,
+                                             _P, _P, _F64, _P, _SZ, _P]),
     "qb_mailbox_create": (ctypes.c_int, [_I32, ctypes.POINTER(_P)]),
     "qb_mailbox_destroy": (ctypes.c_int, [_P]),
     "qb_ipc_get_handle": (ctypes.c_int, [_P, ctypes.c_char_p]),

@@ -489,6 +489,7 @@ class DeviceCloud(object):
             self._bin_ws = torch.zeros(((nbytes + 7) // 8,), dtype=torch.float64, device=self.device)
             self._bin_cap = (self.capacity, cap_new)
             self._bin_list = torch.empty((cap_new,), dtype=torch.int64, device=self.device)
+            self._bin_parents = torch.empty((cap_new,), dtype=torch.int32, device=self.device)
         if self._bin_mirror is None:
             self._bin_mirror = torch.zeros((64,), dtype=torch.float64, pin_memory=True)
             self._bin_mirror_np = self._bin_mirror.numpy()
@@ -511,7 +512,7 @@ class DeviceCloud(object):
         return self._bin_tag
 
     def binned_resample(self, n_new, a, h, zero_cov_comp, seed, off_u, off_v, seed_n, off_n, postselect,
-                        retry_rounds, fuse_weights, n_global=None):
+                        retry_rounds, fuse_weights, n_global=None, own_mean=False):
         """The whole binned resample queued by one call (moments, Liu-West constants on the device, counts, move,
         first retry launch).  Returns the tag; poll ``binned_moments_wait`` / ``binned_flags`` for the host-side checks
         and ``binned_counters_wait`` / ``binned_retry_wait(queued=True)`` for the result."""
@@ -527,7 +528,8 @@ class DeviceCloud(object):
             int(off_v) & _U64_MASK, int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, self.x_alt.data_ptr(),
             self.w_alt.data_ptr() if fuse_weights else None, n_new if n_global is None else int(n_global),
             self.stats_alt.data_ptr() if fuse_weights else None, 1 if postselect else 0, rounds,
-            self._bin_list.data_ptr(), self.moments_out.data_ptr(), self._bin_mirror.data_ptr(), float(tag),
+            1 if own_mean else 0, self._bin_list.data_ptr(), self._bin_parents.data_ptr(),
+            self.moments_out.data_ptr(), self._bin_mirror.data_ptr(), float(tag),
             self._bin_ws.data_ptr(), self._bin_ws.numel() * 8, _stream()))
         self.launches += 4 if rounds else 3
         return tag
@@ -596,7 +598,7 @@ class DeviceCloud(object):
         return mc, sc
 
     def binned_move(self, mean, S, a, seed_v, off_v, seed_n, off_n, n_new, postselect, dst=None, split=None,
-                    dst2=None, fuse_weights=False, n_global=None, js_out=None, retry_rounds=0):
+                    dst2=None, fuse_weights=False, n_global=None, js_out=None, retry_rounds=0, own_mean=False):
         """Pass 3: every output slot draws inside its bin, moves and is tested; with ``fuse_weights`` the new uniform
         weights and their stats block go to the alternate weight buffer in the same launch.  ``retry_rounds`` > 0
         (postselection only) queues the retry kernel right behind it: up to that many fresh perturbations per invalid
@@ -621,13 +623,15 @@ class DeviceCloud(object):
         check(lib.qb_lw_binned_move(model, x, self.w.data_ptr(), self.stats.data_ptr(), self.n, d, mc, sc, float(a),
                                     int(seed_v) & _U64_MASK, int(off_v) & _U64_MASK, int(seed_n) & _U64_MASK,
                                     int(off_n) & _U64_MASK, n_new, dst_p, split, dst2_p, w_new, n_global, st_new,
-                                    1 if postselect else 0, rounds, self._bin_list.data_ptr(),
+                                    1 if postselect else 0, rounds, 1 if own_mean else 0,
+                                    self._bin_list.data_ptr(), self._bin_parents.data_ptr(),
                                     js_out.data_ptr() if js_out is not None else None, mirror + 32 * 8, float(tag),
                                     self._bin_ws.data_ptr(), self._bin_ws.numel() * 8, stream))
         self.launches += 2 if rounds else 1
         return (tag, tag) if rounds else tag
 
-    def binned_retry(self, mean, S, a, seed_n, off_n, n_new, rounds=1, dst=None, split=None, dst2=None):
+    def binned_retry(self, mean, S, a, seed_n, off_n, n_new, rounds=1, dst=None, split=None, dst2=None,
+                     own_mean=False, seed_v=0):
         """Up to ``rounds`` more perturbations per still-invalid slot of the last move (round j: normal stream at
         ``off_n + j * stride``)."""
         dst = self.x_alt if dst is None else dst
@@ -636,10 +640,11 @@ class DeviceCloud(object):
         n_new = int(n_new)
         stride = (self.d * n_new + 1) // 2
         check(self.lib.qb_lw_binned_retry(self.lib_model, self.x.data_ptr(), self.n, self.d, mc, sc, float(a),
-                                          int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, stride, int(rounds), n_new,
+                                          int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, stride, int(rounds),
+                                          1 if own_mean else 0, int(seed_v) & _U64_MASK, n_new,
                                           dst.data_ptr(), int(n_new if split is None else split),
                                           dst2.data_ptr() if dst2 is not None else None, self._bin_list.data_ptr(),
-                                          self._bin_mirror.data_ptr() + 40 * 8,
+                                          self._bin_parents.data_ptr(), self._bin_mirror.data_ptr() + 40 * 8,
                                           float(self._bin_tag), self._bin_ws.data_ptr(), self._bin_ws.numel() * 8,
                                           _stream()))
         self.launches += 1

@@ -142,6 +142,10 @@ class LiuWestResampler(Resampler):
         self.last_n_iters = 0
         self.last_overflow = 0
         self._fused = True      # device-RNG mode: fused draw+move kernels (False: the staged launches, same result)
+        # binned draw, postselection retry: False (default) re-centres a still-invalid particle on an i.i.d. draw from
+        # the weighted cloud — the LAW of the reference's loop, whose `mus = mus[:k]` (resamplers.py:372) pairs the
+        # r-th invalid particle with the r-th original draw; True keeps the particle's own parent (textbook Liu-West)
+        self._own_mean = False
 
     @property
     def a(self):
@@ -267,7 +271,7 @@ class LiuWestResampler(Resampler):
         return stride, off_n, rounds
 
     def _binned_finish(self, cloud, tag, rounds, stride, mean, S, a, n_particles, seed_n, dst=None, split=None,
-                       dst2=None):
+                       dst2=None, seed_v=0):
         """Wait for the move (and the retry launch queued behind it), then run the rest of the postselection loop of
         resamplers.py:327-372 if anything is still invalid (rare: 8 rounds have already run on the device)."""
         if rounds:
@@ -285,7 +289,8 @@ class LiuWestResampler(Resampler):
             more = min(self.RETRY_ROUNDS, self._maxiter - n_iters)
             off_n = self._philox_offset
             self._philox_offset += more * stride
-            t2 = cloud.binned_retry(mean, S, a, seed_n, off_n, n_particles, more, dst=dst, split=split, dst2=dst2)
+            t2 = cloud.binned_retry(mean, S, a, seed_n, off_n, n_particles, more, dst=dst, split=split, dst2=dst2,
+                                    own_mean=self._own_mean, seed_v=seed_v)
             n_invalid, used, _ = cloud.binned_retry_wait(t2)
             n_iters += used if n_invalid == 0 else more
         return n_iters, n_invalid
@@ -299,10 +304,10 @@ class LiuWestResampler(Resampler):
         stride, off_n, rounds = self._binned_plan(cloud.d, n_particles)
         tags = cloud.binned_move(mean, S, a, seed, off_v, seed_n, off_n, n_particles, self._postselect, dst=dst,
                                  split=split, dst2=dst2, fuse_weights=fuse_weights, n_global=n_global,
-                                 retry_rounds=rounds)
+                                 retry_rounds=rounds, own_mean=self._own_mean)
         tag = tags[0] if rounds else tags
         return self._binned_finish(cloud, tag, rounds, stride, mean, S, a, n_particles, seed_n, dst=dst, split=split,
-                                   dst2=dst2)
+                                   dst2=dst2, seed_v=seed)
 
     def _binned_device(self, cloud, n_particles, fuse_weights):
         """The whole binned resample with NO host decision between its launches: the Liu-West constants (covariance,
@@ -315,7 +320,7 @@ class LiuWestResampler(Resampler):
         off_u, off_v = self._binned_offsets(n_particles)
         stride, off_n, rounds = self._binned_plan(d, n_particles)
         tag = cloud.binned_resample(n_particles, self._a, self._h, self._zero_cov_comp, seed, off_u, off_v, seed_n,
-                                    off_n, self._postselect, rounds, fuse_weights)
+                                    off_n, self._postselect, rounds, fuse_weights, own_mean=self._own_mean)
         _, mean, m2 = cloud.binned_moments_wait(tag)
         flag, s_err = cloud.binned_flags()
         _cov_1x1(mean, m2) if d == 1 else covariance_from_moments(mean, m2)
@@ -325,7 +330,7 @@ class LiuWestResampler(Resampler):
         if not np.isfinite(s_err):
             raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
                                  "Check that n_ess is not too small.")
-        return self._binned_finish(cloud, tag, rounds, stride, None, None, self._a, n_particles, seed_n)
+        return self._binned_finish(cloud, tag, rounds, stride, None, None, self._a, n_particles, seed_n, seed_v=seed)
 
     def _binned_return(self, cloud, on_device, n_particles, n_iters, n_invalid, weights_fused):
         if n_invalid:

@@ -516,3 +516,24 @@ def diffusive_vectors(ns, seed=71):
     out['norm'] = np.array([float(np.ravel(v)[0]) for v in up.normalization_record])
     out['rc'] = np.int64(up.resample_count)
     return out
+
+
+def mle_design_vectors(ns, seed=29):
+    """bayes_risk / expected_information_gain under MLEModel (smc.py:584-591 with derived_models.py:701-703): the last
+    outcome's hypothetical likelihood is 1 - sum of the others' POWERED likelihoods."""
+    import warnings
+    rs = np.random.RandomState(seed)
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n = 2000
+        x = rs.random_sample((n, 1))
+        for tag, gamma in (("g2", 2.0), ("g05", 0.5)):
+            up = ns.SMCUpdater(ns.MLEModel(ns.SimplePrecessionModel(), gamma), n, FixedPrior(x), resample_thresh=0.0)
+            for t, o in zip([1.0, 2.3, 4.1], [0, 1, 0]):
+                up.update(o, np.array([t]))
+            ts = np.array([0.5, 3.0, 11.0, 40.0])
+            out[tag + '_risk'] = np.asarray(up.bayes_risk(ts), dtype=float)
+            out[tag + '_ig'] = np.asarray(up.expected_information_gain(ts), dtype=float)
+        out['x'] = x
+    return out

@@ -58,6 +58,7 @@ def build(ns):
         files['mle_vectors'] = cases.mle_vectors(ns)
         files['random_walk_vectors'] = cases.random_walk_vectors(ns)
         files['diffusive_vectors'] = cases.diffusive_vectors(ns)
+        files['mle_design_vectors'] = cases.mle_design_vectors(ns)
     return files
 
 

@@ -163,16 +163,20 @@ def test_binned_passes_are_exact(qb, oracle, kind, n, n_new, wkind):
         assert st[0] == 1.0 and st[1] == 1.0 / n and st[4] == 1.0 and st[5] == float(n) and st[8] == 0.0
     if kind in ("prec_minfreq", "rb", "rb_il"):
         assert n_invalid > 0
-        # one retry round: every listed slot is recomputed from ITS parent with normals indexed by slot
+        # one retry round: every listed slot is re-centred on the parent of a uniformly random slot (the law of the
+        # reference's mus[:k] re-slicing, resamplers.py:372) with normals indexed by slot
         off_r = off_n + (d * n_new + 1) // 2
-        tag = cloud.binned_retry(mean, S, a, seed ^ GOLD, off_r, n_new, 1)
+        tag = cloud.binned_retry(mean, S, a, seed ^ GOLD, off_r, n_new, 1, seed_v=seed)
         left, used, listed = cloud.binned_retry_wait(tag)
         assert used == 1 and listed == n_invalid
         torch.cuda.synchronize()
         got2 = cloud.x_alt.cpu().numpy()
         e2 = _stream(cloud, d * n_new, seed ^ GOLD, off_r, normal=True).reshape(d, n_new)
         slots = np.nonzero(bad)[0]
-        want2 = a * x[js[slots]] + (1 - a) * mean + np.dot(S, e2[:, slots]).T
+        uq = _stream(cloud, n_new, seed, off_r)
+        donor = np.minimum((uq[slots] * n_new).astype(np.int64), n_new - 1)
+        assert np.array_equal(cloud._bin_parents[:n_new].cpu().numpy(), js)
+        want2 = a * x[js[donor]] + (1 - a) * mean + np.dot(S, e2[:, slots]).T
         np.testing.assert_allclose(got2[slots], want2, rtol=1e-13, atol=1e-15)
         assert np.array_equal(got2[~bad], got[~bad])
         still = ~np.asarray(model.are_models_valid(got2[slots]), dtype=bool)
@@ -338,3 +342,33 @@ def test_binned_zero_covariance_warns_and_uses_the_small_covariance(qb):
     locs = up.particle_locations
     assert abs(locs.mean() - 0.5) < 1e-4
     assert abs(locs.std() / (res.h * 1e-3) - 1) < 0.05                      # S = h * sqrt(1e-6)
+
+
+def test_binned_retry_own_parent_variant(qb, oracle):
+    """own_mean=True: a still-invalid particle is retried around ITS OWN parent (textbook Liu-West)."""
+    import torch
+    model, x, w = _fused_case(qb, "prec_minfreq", 50001, 23)
+    n, seed, a = 50001, 4242, 0.95
+    res = qb.LiuWestResampler(a=a, rng='philox', seed=seed, scan='fast')
+    up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
+    up.particle_weights = w
+    cloud = up._cloud
+    tag = cloud.binned_prepare(n, seed, 0)
+    _, mean, m2 = cloud.binned_moments_wait(tag)
+    S = np.real(res.h * oracle.sqrtm_psd(m2 - np.outer(mean, mean))[0])
+    js_out = torch.empty((n,), dtype=torch.int64, device=cloud.device)
+    off_n = 2 * ((n + 1) // 2)
+    tag = cloud.binned_move(mean, S, a, seed, (n + 1) // 2, seed ^ GOLD, off_n, n, True, js_out=js_out)
+    n_invalid = cloud.binned_counters_wait(tag)[0]
+    torch.cuda.synchronize()
+    got = cloud.x_alt.cpu().numpy().copy()
+    bad = ~np.asarray(model.are_models_valid(got), dtype=bool)
+    assert n_invalid == bad.sum() > 0
+    off_r = off_n + (n + 1) // 2
+    tag = cloud.binned_retry(mean, S, a, seed ^ GOLD, off_r, n, 1, own_mean=True)
+    cloud.binned_retry_wait(tag)
+    torch.cuda.synchronize()
+    e2 = _stream(cloud, n, seed ^ GOLD, off_r, normal=True)
+    slots = np.nonzero(bad)[0]
+    want = a * x[js_out.cpu().numpy()[slots]] + (1 - a) * mean + (S[0, 0] * e2[slots])[:, None]
+    assert np.array_equal(cloud.x_alt.cpu().numpy()[slots], want)

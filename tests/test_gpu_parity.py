@@ -979,3 +979,14 @@ def test_f4_unsupported_decorator_variants_fail_loudly(qb):
     with pytest.raises(qb.UnsupportedModelError):
         qb.GaussianRandomWalkModel(qb.SimplePrecessionModel(), fixed_covariance=np.array([1e-6]),
                                    model_transformation=(np.log, np.exp))
+
+
+def test_design_under_mle_model_follows_the_reference_complement(qb, golden):
+    """with a likelihood power the device must form the last outcome as 1 - sum(others ** gamma) like
+    smc.py:589, not evaluate L_last ** gamma."""
+    g = golden("mle_design_vectors")
+    got = cases.mle_design_vectors(gpu_namespace(qb))
+    for key in ("g2_risk", "g2_ig", "g05_risk", "g05_ig"):
+        ok = np.isfinite(g[key])
+        assert ok.any()
+        np.testing.assert_allclose(got[key][ok], g[key][ok], rtol=1e-9, err_msg=key)

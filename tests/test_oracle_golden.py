@@ -167,3 +167,8 @@ def test_diffusive_tomography_vectors_bit_exact(ns, golden):
     """f4: DiffusiveTomographyModel (tomography/models.py:228-272) — trajectory with per-update Gaussian diffusion and
     re-canonicalisation, validity rule of the extra parameter."""
     _assert_same(cases.diffusive_vectors(ns), golden("diffusive_vectors"))
+
+
+def test_mle_design_vectors_bit_exact(ns, golden):
+    """Risk and information gain under MLEModel: the last outcome as 1 - sum of the powered others (smc.py:589)."""
+    _assert_same(cases.mle_design_vectors(ns), golden("mle_design_vectors"))
