@@ -38,7 +38,8 @@ extern "C" {
 #endif
 
 #define QB_ABI_VERSION 3 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes; 3: qb_lw_binned_*,
-                            qb_model.d_extra / extra_rule, qb_walk_step, qb_poison_likelihood, qb_tomo_canonicalize*_ld */
+                            qb_model.d_extra / extra_rule, qb_walk_step, qb_poison_likelihood, qb_tomo_canonicalize*_ld,
+                            qb_weights_entropy, qb_weight_mass_hist, qb_weights_select */
 
 #define QB_OK 0
 #define QB_ERR_INVALID_ARGUMENT (-1)
@@ -441,6 +442,23 @@ int qb_tomo_canonicalize_ld(double* d_x, int64_t n, int32_t dim, int32_t ld, con
 int qb_tomo_canonicalize_screened_ld(double* d_x, int64_t n, int32_t dim, int32_t ld, const double* d_basis,
                                      int32_t allow_subnormalized, uint8_t* d_flags, int64_t* d_idxs,
                                      int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- read-side estimators ------------------------------------------------------------------------ */
+/* ParticleDistribution.est_entropy (distributions.py:457-465): *d_out = -sum over w_i > 0 of w_i log w_i (w normalised).
+ * Workspace: qb_readside_workspace_bytes(). */
+size_t qb_readside_workspace_bytes(void);
+int qb_weights_entropy(const double* d_w, const double* d_stats, int64_t n, double* d_out, void* d_ws, size_t ws_bytes,
+                       void* stream);
+/* est_credible_region (distributions.py:558-614) by radix SELECTION instead of a sort: one pass histograms the
+ * normalised weights whose bit pattern above (shift + nbits) equals `prefix` by their nbits-wide digit at `shift`
+ * (nbits <= 11): d_mass[b] = their weight mass, d_count[b] = how many (2048 entries each, zeroed by the call).
+ * Non-negative doubles order like their patterns; weights <= 0 or NaN are skipped (they carry no mass). */
+int qb_weight_mass_hist(const double* d_w, const double* d_stats, int64_t n, int32_t shift, int32_t nbits,
+                        uint64_t prefix, double* d_mass, uint64_t* d_count, void* stream);
+/* d_flags[i] = 1 iff the pattern of the normalised weight i is > tau_bits (mode 0) or == tau_bits (mode 1); input of
+ * qb_compact_invalid, whose index list + qb_gather_rows bring only the region's members to the host. */
+int qb_weights_select(const double* d_w, const double* d_stats, int64_t n, uint64_t tau_bits, int32_t mode,
+                      uint8_t* d_flags, void* stream);
 
 /* ---- time-dependent and noisy decorators ------------------------------------------------------- */
 /* Model.update_timestep for the random-walk decorators, in place after an update has been committed (smc.py:447-449).

@@ -23,7 +23,7 @@ if os.environ.get("QB_LIB_PATH"):
     BUILD = os.path.join(HERE, "build_" + hashlib.sha256(LIB.encode()).hexdigest()[:8])
 
 SOURCES = ["qb_misc.cu", "qb_update.cu", "qb_moments.cu", "qb_resample.cu", "qb_tomography.cu", "qb_rng.cu",
-           "qb_dist.cu", "qb_scan_exact.cu", "qb_mt19937.cu", "qb_design.cu", "qb_binned.cu", "qb_walk.cu"]
+           "qb_dist.cu", "qb_scan_exact.cu", "qb_mt19937.cu", "qb_design.cu", "qb_binned.cu", "qb_walk.cu", "qb_readside.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -128,6 +128,10 @@ SIGNATURES = {
     "qb_tomo_canonicalize_screened": (ctypes.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
     "qb_tomo_canonicalize_ld": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P]),
     "qb_tomo_canonicalize_screened_ld": (ctypes.c_int, [_P, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "qb_readside_workspace_bytes": (_SZ, []),
+    "qb_weights_entropy": (ctypes.c_int, [_P, _P, _I64, _P, _P, _SZ, _P]),
+    "qb_weight_mass_hist": (ctypes.c_int, [_P, _P, _I64, _I32, _I32, _U64, _P, _P, _P]),
+    "qb_weights_select": (ctypes.c_int, [_P, _P, _I64, _U64, _I32, _P, _P]),
     "qb_walk_step": (ctypes.c_int, [_P, _I64, _I32, _I32, ctypes.POINTER(_I32), ctypes.POINTER(_I32), _I32,
                                     ctypes.POINTER(_F64), ctypes.POINTER(_I32), _F64, _F64, _P, _I32, _P]),
     "qb_poison_likelihood": (ctypes.c_int, [_P, _I64, _P, _I32, _F64, _F64, _P]),

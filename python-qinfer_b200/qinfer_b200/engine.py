@@ -748,6 +748,108 @@ class DeviceCloud(object):
                                                int(self.desc.allow_subnormalized), _stream()))
         self.launches += 1
 
+    # ---- read-side estimators on the device -------------------------------------------------------
+    def _readside_ws(self):
+        ws = getattr(self, '_rs_ws', None)
+        if ws is None:
+            nbytes = self.lib.qb_readside_workspace_bytes()
+            self._rs_ws = ws = torch.zeros(((nbytes + 7) // 8,), dtype=torch.float64, device=self.device)
+            self._rs_mass = torch.zeros((2048,), dtype=torch.float64, device=self.device)
+            self._rs_count = torch.zeros((2048,), dtype=torch.int64, device=self.device)
+            self._rs_out = torch.zeros((1,), dtype=torch.float64, device=self.device)
+        return ws
+
+    def entropy(self):
+        """-sum_{w > 0} w log w of the normalised weights (distributions.py:457-465); 8 bytes come back."""
+        ws = self._readside_ws()
+        check(self.lib.qb_weights_entropy(_ptr(self.w), _ptr(self.stats), self.n, _ptr(self._rs_out), _ptr(ws),
+                                          ws.numel() * 8, _stream()))
+        self.launches += 2
+        return float(self._rs_out.cpu().numpy()[0])
+
+    def credible_members(self, level):
+        """Indices (device int64 tensor) of the K heaviest particles, K = 1 + #{k : cumsum of the descending weights
+        <= level} (distributions.py:583-592), found by radix selection on the weights' bit patterns — no sort, and
+        only 6 x 32 KB of histograms travel to the host.  Equal weights at the threshold are taken lowest index
+        first (the reference's order among ties is that of an unstable argsort)."""
+        self._readside_ws()
+        n = self.n
+        prefix, mass_above, count_above = 0, 0.0, 0
+        last = None
+        for shift, nb in ((53, 11), (42, 11), (31, 11), (20, 11), (9, 11), (0, 9)):
+            check(self.lib.qb_weight_mass_hist(_ptr(self.w), _ptr(self.stats), n, shift, nb, prefix,
+                                               _ptr(self._rs_mass), _ptr(self._rs_count), _stream()))
+            self.launches += 1
+            nbk = 1 << nb
+            mass = self._rs_mass.cpu().numpy()[:nbk][::-1]           # from the heaviest bucket down
+            count = self._rs_count.cpu().numpy()[:nbk][::-1]
+            incl = mass_above + np.cumsum(mass)
+            over = np.nonzero((incl > level) & (count > 0))[0]
+            if over.size == 0:
+                # every cumulative weight is <= level: the reference indexes one past the end (distributions.py:591)
+                raise IndexError("index %d is out of bounds for axis 0 with size %d" % (n, n))
+            j = int(over[0])
+            mass_above += float(np.sum(mass[:j]))
+            count_above += int(np.sum(count[:j]))
+            prefix = (prefix << nb) | (nbk - 1 - j)
+            last = (float(mass[j]), int(count[j]))
+        tau = prefix
+        v = float(np.array([tau], dtype=np.uint64).view(np.float64)[0])
+        c_eq = last[1]
+        # how many of the c_eq particles weighing exactly tau still fit under `level`: the reference's np.cumsum adds
+        # them one by one, so do the same (from the mass above them) instead of multiplying
+        k_est = int(np.floor((level - mass_above) / v)) if v > 0 else 0
+        m = int(min(c_eq, max(k_est, 0) + 8))
+        run = np.cumsum(np.concatenate([[mass_above], np.full(m, v)]))[1:]
+        k_in = int(np.sum(run <= level))
+        take = min(k_in + 1, c_eq)
+        # members: everything heavier than tau, plus `take` of the particles that weigh exactly tau
+        flags = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        cnt = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        parts = []
+        for mode, want in ((0, count_above), (1, take)):
+            if want == 0:
+                continue
+            idx = torch.empty((n,), dtype=torch.int64, device=self.device)
+            check(self.lib.qb_weights_select(_ptr(self.w), _ptr(self.stats), n, tau, mode, _ptr(flags), _stream()))
+            check(self.lib.qb_compact_invalid(_ptr(flags), n, _ptr(idx), _ptr(cnt), _ptr(self.ws), self.ws_bytes,
+                                              _stream()))
+            self.launches += 4
+            parts.append(idx[:want])
+        return torch.cat(parts) if len(parts) > 1 else parts[0]
+
+    def gather_members(self, idx):
+        """(locations (k, d), normalised weights (k,)) of the particles ``idx`` as host arrays: 8 k (d + 1) bytes."""
+        k = idx.numel()
+        rows = torch.empty((k, self.d), dtype=torch.float64, device=self.device)
+        wts = torch.empty((k,), dtype=torch.float64, device=self.device)
+        check(self.lib.qb_gather_rows(_ptr(self.x), self.d, _ptr(idx), k, _ptr(rows), _stream()))
+        check(self.lib.qb_gather_rows(_ptr(self.w), 1, _ptr(idx), k, _ptr(wts), _stream()))
+        self.launches += 2
+        inv = float(self.read_stats()[QB_STAT_INV_NORM])
+        self.last_d2h_bytes = 8 * k * (self.d + 1)
+        return self._to_host(rows), self._to_host(wts) * inv
+
+    def weighted_mean_of(self, values):
+        """sum_i w_i values[i, :] for an (n, k) float64 device tensor (est_meanfn, distributions.py:411-430), through
+        the moment kernel, k <= 64 columns per launch; 8 k bytes come back."""
+        n, k = values.shape
+        out = np.empty((k,))
+        for c0 in range(0, k, _lib.QB_MAX_D):
+            c1 = min(k, c0 + _lib.QB_MAX_D)
+            blk = values[:, c0:c1].contiguous()
+            kk = c1 - c0
+            need = self.lib.qb_moments_workspace_bytes(n, kk)
+            ws = getattr(self, '_meanfn_ws', None)
+            if ws is None or ws.numel() * 8 < need:
+                self._meanfn_ws = ws = torch.zeros(((need + 7) // 8,), dtype=torch.float64, device=self.device)
+            res = torch.empty((1 + kk + kk * kk,), dtype=torch.float64, device=self.device)
+            check(self.lib.qb_moments(_ptr(blk), _ptr(self.w), _ptr(self.stats), n, kk, _ptr(res), _ptr(ws),
+                                      ws.numel() * 8, _stream()))
+            self.launches += 2
+            out[c0:c1] = res[1:1 + kk].cpu().numpy()
+        return out
+
     # ---- f4 decorators: Gaussian steps after an update, Gaussian noise on the likelihood -------------------------
     def normals(self, count):
         """``count`` standard normals in a device buffer, from the cloud's noise source (set by the updater):

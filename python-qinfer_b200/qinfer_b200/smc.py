@@ -202,24 +202,47 @@ class SMCUpdater(object):
         return self._cloud.moments()[1]
 
     def est_meanfn(self, fn):
+        """distributions.py:411-430: sum_i w_i fn(x_i).  ``fn`` is first offered the DEVICE tensor of particle
+        locations: a function written with arithmetic operators / torch-compatible calls (``lambda x: x ** 2``) is
+        evaluated and reduced on the GPU and only its mean comes back.  A function that needs NumPy arrays raises on
+        the device tensor and is applied to the downloaded cloud as in the reference."""
+        self._flush()
+        cloud = self._cloud
+        try:
+            vals = fn(cloud.x)
+            on_device = isinstance(vals, torch.Tensor) and vals.is_cuda and vals.shape[0] == cloud.n
+        except Exception:
+            on_device = False
+        if on_device:
+            vals = vals.to(torch.float64)
+            shape = tuple(vals.shape[1:])
+            return cloud.weighted_mean_of(vals.reshape(cloud.n, -1)).reshape(shape)
         return np.einsum('i...,i...', self.particle_weights, fn(self.particle_locations))
 
-    # ---- read-side estimators (distributions.py:457-465, 557-626): host arithmetic, exactly the
-    # reference's expressions, on the read-back of the device cloud (the cloud is downloaded once and cached)
+    # ---- read-side estimators (distributions.py:457-465, 557-626; SURVEY §8 f3) on the device: the cloud is not
+    # downloaded; what travels is proportional to the answer
     def est_entropy(self):
-        nz_weights = self.particle_weights[self.particle_weights > 0]
-        return -np.sum(np.log(nz_weights) * nz_weights)
+        self._flush()
+        return self._cloud.entropy()
 
     def est_credible_region(self, level=0.95, return_outside=False, modelparam_slice=None):
+        """distributions.py:558-614: the particles of highest weight whose cumulative weight reaches ``level``, sorted
+        by weight (descending).  The members are selected on the device (radix selection of the threshold weight,
+        ordered compaction) and only they are downloaded; ``return_outside=True`` needs every particle and takes the
+        host route."""
+        self._flush()
         s_ = np.s_[modelparam_slice] if modelparam_slice is not None else np.s_[:]
-        mps = self.particle_locations[:, s_]
-        id_sort = np.argsort(self.particle_weights)[::-1]
-        cumsum_weights = np.cumsum(self.particle_weights[id_sort])
-        id_cred = cumsum_weights <= level
-        id_cred[np.sum(id_cred)] = True
         if return_outside:
+            mps = self.particle_locations[:, s_]
+            id_sort = np.argsort(self.particle_weights)[::-1]
+            cumsum_weights = np.cumsum(self.particle_weights[id_sort])
+            id_cred = cumsum_weights <= level
+            id_cred[np.sum(id_cred)] = True
             return mps[id_sort][id_cred], mps[id_sort][np.logical_not(id_cred)]
-        return mps[id_sort][id_cred]
+        idx = self._cloud.credible_members(level)
+        locs, wts = self._cloud.gather_members(idx)
+        order = np.argsort(-wts, kind='stable')
+        return locs[order][:, s_]
 
     def region_est_hull(self, level=0.95, modelparam_slice=None):
         from scipy.spatial import ConvexHull

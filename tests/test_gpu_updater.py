@@ -449,3 +449,65 @@ def test_read_side_estimators_match_the_oracle(qb, oracle):
     s_o = ou.sample(n=500)
     assert s_g.shape == (500, 3)
     assert np.mean(np.all(s_g == s_o, axis=1)) > 0.99          # same uniforms, same CDF up to the weights' last bits
+
+
+@pytest.mark.parametrize("n,level", [(3000, 0.9), (10 ** 6, 0.95), (10 ** 6, 0.5), (200001, 0.999)])
+def test_f3_credible_region_on_the_device(qb, oracle, n, level):
+    """est_credible_region (distributions.py:558-614) by radix selection + compaction on the device: the same member
+    set as the reference's argsort + cumsum, sorted by weight, and only the members are downloaded (D2H bytes
+    proportional to the region, not to the cloud)."""
+    rs = np.random.RandomState(12)
+    x = rs.random_sample((n, 1))
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x), resample_thresh=0.0)
+    for t, o in zip([1.1, 2.7, 6.3, 11.9, 23.0], [0, 1, 0, 0, 1]):
+        up.update(o, np.array([t]))
+    w = up.particle_weights
+    order = np.argsort(w)[::-1]
+    k = int(np.sum(np.cumsum(w[order]) <= level)) + 1
+    region = up.est_credible_region(level=level)
+    assert region.shape == (k, 1)
+    assert up._cloud.last_d2h_bytes == 8 * k * 2 and k < n
+    want = x[order][:k]
+    wk = w[order][k - 1]
+    assert np.sum(w == wk) == 1                      # (distinct weights at the boundary: the member set is unique)
+    assert np.array_equal(np.sort(region[:, 0]), np.sort(want[:, 0]))
+    # sorted by weight, heaviest first: compare where the weights are distinct
+    distinct = np.concatenate([[True], np.diff(w[order][:k]) != 0]) & np.concatenate([np.diff(w[order][:k]) != 0, [True]])
+    assert np.array_equal(region[distinct], want[distinct])
+    # slicing and the uniform-weights tie case (every weight equal: any K of them, lowest index first)
+    up2 = qb.SMCUpdater(qb.RandomizedBenchmarkingModel(), 5000, cases.FixedPrior(rs.random_sample((5000, 3))))
+    reg = up2.est_credible_region(level=0.25, modelparam_slice=slice(1, 3))
+    assert reg.shape == (int(np.sum(np.cumsum(np.full(5000, 1 / 5000)) <= 0.25)) + 1, 2)
+    with pytest.raises(IndexError):
+        up2.est_credible_region(level=1.5)
+
+
+def test_f3_meanfn_and_entropy_on_the_device(qb, oracle):
+    """est_meanfn (distributions.py:411-430): a function written with operators is evaluated on the device tensor and
+    reduced there (moment kernel); a NumPy-only function falls back to the reference's host expression; est_entropy
+    (distributions.py:457-465) is a device reduction."""
+    import torch
+    rs = np.random.RandomState(3)
+    n = 400000
+    x = np.column_stack([0.9 + 0.1 * rs.random_sample(n), 0.5 * rs.random_sample(n), 0.5 * rs.random_sample(n)])
+    up = qb.SMCUpdater(qb.RandomizedBenchmarkingModel(), n, cases.FixedPrior(x), resample_thresh=0.0)
+    ep = np.empty((2,), dtype=up.model.expparams_dtype)
+    ep['m'] = [7, 60]
+    up.update(0, ep[0:1])
+    up.update(1, ep[1:2])
+    w = up.particle_weights
+    calls = []
+
+    def poly(l):
+        calls.append(type(l))
+        return l ** 2 + 3.0 * l
+
+    got = up.est_meanfn(poly)
+    assert calls == [torch.Tensor]                                   # evaluated on the device tensor only
+    np.testing.assert_allclose(got, np.einsum('i,ij->j', w, x ** 2 + 3.0 * x), rtol=1e-12)
+    got1 = up.est_meanfn(lambda l: l[:, 0] * l[:, 2])
+    assert np.shape(got1) == () and got1 == pytest.approx(float(np.dot(w, x[:, 0] * x[:, 2])), rel=1e-12)
+    host = up.est_meanfn(lambda l: np.sin(np.asarray(l)[:, 1]))      # needs NumPy: the reference's host route
+    assert host == pytest.approx(float(np.dot(w, np.sin(x[:, 1]))), rel=1e-12)
+    nz = w[w > 0]
+    assert up.est_entropy() == pytest.approx(-np.sum(np.log(nz) * nz), rel=1e-11)
