@@ -261,10 +261,14 @@ int qb_draw(const double* d_cdf, int64_t n, const double* d_u, int64_t n_draw,
  * With postselect != 0, d_invalid[i] = !are_models_valid(x_new[i]) and
  * *d_n_invalid is their count.  h_mean (d) and h_S (d*d, row-major, already
  * scaled by h) are HOST arrays. */
+/* d_ws: a device buffer of qb_lw_move_workspace_bytes(d) bytes owned by the caller (one per cloud / stream) that
+ * receives S and (1-a) mean for the generic-d kernels; qb_lw_move ignores it for d <= 4 (may be NULL there). */
+size_t qb_lw_move_workspace_bytes(int32_t d);
 int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
                const int64_t* d_js, const double* h_mean, const double* h_S, double a,
                const double* d_eps, int64_t n_new, double* d_x_new,
-               int32_t postselect, uint8_t* d_invalid, int64_t* d_n_invalid, void* stream);
+               int32_t postselect, uint8_t* d_invalid, int64_t* d_n_invalid, void* d_ws, size_t ws_bytes,
+               void* stream);
 size_t qb_compact_workspace_bytes(int64_t n);
 /* Ordered compaction: d_idxs_out = ascending indices i with d_invalid[i] != 0
  * (np.nonzero, resamplers.py:365-367); *d_count = how many. */
@@ -281,7 +285,7 @@ int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int
                 const double* d_eps, double* d_x_new,
                 uint8_t* d_invalid, int64_t* d_n_invalid,
                 int32_t own_mean /* 0: the reference's js[r] quirk; 1: js[idxs[r]] (sharded clouds) */,
-                void* stream);
+                void* d_ws, size_t ws_bytes, void* stream);
 
 /* Fused first pass for the device-RNG mode, d <= 4: draw + gather + shrink + perturb + validity in ONE launch,
  * without materialising u, js or eps.  New particle i uses uniform element i of Philox stream (seed_u, off_u)

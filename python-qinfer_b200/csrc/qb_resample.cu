@@ -763,15 +763,38 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(const uint8_
     }
 }
 
-__global__ void compact_scan_kernel(unsigned long long* tile_counts, int64_t ntiles, int64_t* total) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    unsigned long long run = 0;
-    for (int64_t t = 0; t < ntiles; ++t) {
+// exclusive scan of the tile counts by one block: sequential chunks per thread + a block scan of the chunk sums
+// (the counts are 64-bit integers: any association order gives the same result)
+__global__ void __launch_bounds__(CMP_THREADS) compact_scan_kernel(unsigned long long* tile_counts, int64_t ntiles,
+                                                                   int64_t* total) {
+    __shared__ unsigned long long wsum[CMP_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t per = (ntiles + CMP_THREADS - 1) / CMP_THREADS;
+    const int64_t lo = static_cast<int64_t>(threadIdx.x) * per;
+    const int64_t hi = (lo + per < ntiles) ? lo + per : ntiles;
+    unsigned long long s = 0;
+    for (int64_t t = lo; t < hi; ++t) s += tile_counts[t];
+    unsigned long long inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < CMP_THREADS / 32; ++k) {
+        if (k < wid) base += wsum[k];
+        tot += wsum[k];
+    }
+    unsigned long long run = base + (inc - s);
+    for (int64_t t = lo; t < hi; ++t) {
         const unsigned long long c = tile_counts[t];
         tile_counts[t] = run;
         run += c;
     }
-    *total = static_cast<int64_t>(run);
+    if (threadIdx.x == 0) *total = static_cast<int64_t>(tot);
 }
 
 __global__ void __launch_bounds__(CMP_THREADS) compact_write_kernel(const uint8_t* __restrict__ flags, int64_t n,
@@ -813,26 +836,18 @@ static int capped_grid(int64_t want, int per_sm) {
 
 int validate_model(const qb_model* m);
 
-// S (d*d) and (1-a)*mean (d) live in a small device buffer owned by the library
-// (one per stream would be needed for concurrent resamples; the reference path is
-// single-threaded, SURVEY §8b "Threading").
-static double* g_consts = nullptr;
-static int g_consts_dev = -1;
-
-static int upload_consts(const double* h_mean, const double* h_S, double a, int d, cudaStream_t st,
-                         const double** out) {
-    int dev = 0;
-    QB_CUDA_CHECK(cudaGetDevice(&dev));
-    if (g_consts == nullptr || g_consts_dev != dev) {
-        QB_CUDA_CHECK(cudaMalloc(&g_consts, (QB_MAX_D * QB_MAX_D + QB_MAX_D) * sizeof(double)));
-        g_consts_dev = dev;
-    }
+// S (d*d) and (1-a)*mean (d) of the generic-d kernels live in a CALLER-owned device buffer of
+// qb_lw_move_workspace_bytes(d) bytes (one per cloud: two updaters on two streams do not share anything)
+static int upload_consts(const double* h_mean, const double* h_S, double a, int d, cudaStream_t st, void* d_ws,
+                         size_t ws_bytes, const double** out) {
+    QB_REQUIRE(d_ws != nullptr && ws_bytes >= static_cast<size_t>(d) * (d + 1) * sizeof(double), QB_ERR_WORKSPACE,
+               "qb_lw_move/retry: n_modelparams > 4 needs a workspace of qb_lw_move_workspace_bytes(d) bytes");
     static thread_local double host[QB_MAX_D * QB_MAX_D + QB_MAX_D];
     for (int j = 0; j < d * d; ++j) host[j] = h_S[j];
     const double oma = 1.0 - a;
     for (int c = 0; c < d; ++c) host[d * d + c] = oma * h_mean[c];  // (1 - a) * mean
-    QB_CUDA_CHECK(cudaMemcpyAsync(g_consts, host, (d * d + d) * sizeof(double), cudaMemcpyHostToDevice, st));
-    *out = g_consts;
+    QB_CUDA_CHECK(cudaMemcpyAsync(d_ws, host, (d * d + d) * sizeof(double), cudaMemcpyHostToDevice, st));
+    *out = reinterpret_cast<const double*>(d_ws);
     return QB_OK;
 }
 
@@ -942,7 +957,7 @@ extern "C" int qb_draw(const double* d_cdf, int64_t n, const double* d_u, int64_
 extern "C" int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d, const int64_t* d_js,
                           const double* h_mean, const double* h_S, double a, const double* d_eps, int64_t n_new,
                           double* d_x_new, int32_t postselect, uint8_t* d_invalid, int64_t* d_n_invalid,
-                          void* stream) {
+                          void* d_ws, size_t ws_bytes, void* stream) {
     int rc = validate_model(model);
     if (rc != QB_OK) return rc;
     QB_REQUIRE(d_x_old && d_js && h_mean && h_S && d_eps && d_x_new && d_invalid && d_n_invalid,
@@ -979,7 +994,7 @@ extern "C" int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t 
         return QB_OK;
     }
     LwParams p;
-    rc = upload_consts(h_mean, h_S, a, d, st, &p.consts);
+    rc = upload_consts(h_mean, h_S, a, d, st, d_ws, ws_bytes, &p.consts);
     if (rc != QB_OK) return rc;
     p.x_old = d_x_old;
     p.js = d_js;
@@ -1012,6 +1027,10 @@ extern "C" int qb_lw_move(const qb_model* model, const double* d_x_old, int64_t 
     return QB_OK;
 }
 
+extern "C" size_t qb_lw_move_workspace_bytes(int32_t d) {
+    return static_cast<size_t>(d) * (d + 1) * sizeof(double);
+}
+
 extern "C" size_t qb_compact_workspace_bytes(int64_t n) {
     const int64_t ntiles = (n + CMP_TILE - 1) / CMP_TILE;
     return static_cast<size_t>(ntiles + 1) * sizeof(unsigned long long) + 256;
@@ -1028,7 +1047,7 @@ extern "C" int qb_compact_invalid(const uint8_t* d_invalid, int64_t n, int64_t* 
     const int grid = capped_grid(ntiles, 8);
     compact_count_kernel<<<grid, CMP_THREADS, 0, st>>>(d_invalid, n, tiles);
     QB_CUDA_CHECK(cudaGetLastError());
-    compact_scan_kernel<<<1, 32, 0, st>>>(tiles, ntiles, d_count);
+    compact_scan_kernel<<<1, CMP_THREADS, 0, st>>>(tiles, ntiles, d_count);
     QB_CUDA_CHECK(cudaGetLastError());
     compact_write_kernel<<<grid, CMP_THREADS, 0, st>>>(d_invalid, n, tiles, d_idxs_out);
     QB_CUDA_CHECK(cudaGetLastError());
@@ -1038,7 +1057,7 @@ extern "C" int qb_compact_invalid(const uint8_t* d_invalid, int64_t n, int64_t* 
 extern "C" int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d, const int64_t* d_js,
                            const int64_t* d_idxs, int64_t k, const double* h_mean, const double* h_S, double a,
                            const double* d_eps, double* d_x_new, uint8_t* d_invalid, int64_t* d_n_invalid,
-                           int32_t own_mean, void* stream) {
+                           int32_t own_mean, void* d_ws, size_t ws_bytes, void* stream) {
     int rc = validate_model(model);
     if (rc != QB_OK) return rc;
     QB_REQUIRE(d_x_old && d_js && d_idxs && h_mean && h_S && d_eps && d_x_new && d_invalid && d_n_invalid,
@@ -1046,7 +1065,7 @@ extern "C" int qb_lw_retry(const qb_model* model, const double* d_x_old, int64_t
     QB_REQUIRE(d == model->d && n_old >= 1 && k >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_retry: bad sizes");
     cudaStream_t st = as_stream(stream);
     LwParams p;
-    rc = upload_consts(h_mean, h_S, a, d, st, &p.consts);
+    rc = upload_consts(h_mean, h_S, a, d, st, d_ws, ws_bytes, &p.consts);
     if (rc != QB_OK) return rc;
     p.x_old = d_x_old;
     p.js = d_js;

@@ -85,12 +85,13 @@ SIGNATURES = {
     "qb_cdf_exact_fallback_flag": (ctypes.c_int, [_P, _I64, ctypes.POINTER(_I32), _P]),
     "qb_draw_workspace_bytes": (_SZ, [_I64]),
     "qb_draw": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "qb_lw_move_workspace_bytes": (_SZ, [_I32]),
     "qb_lw_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, ctypes.POINTER(_F64),
-                                  ctypes.POINTER(_F64), _F64, _P, _I64, _P, _I32, _P, _P, _P]),
+                                  ctypes.POINTER(_F64), _F64, _P, _I64, _P, _I32, _P, _P, _P, _SZ, _P]),
     "qb_compact_workspace_bytes": (_SZ, [_I64]),
     "qb_compact_invalid": (ctypes.c_int, [_P, _I64, _P, _P, _P, _SZ, _P]),
     "qb_lw_retry": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _I64, ctypes.POINTER(_F64),
-                                   ctypes.POINTER(_F64), _F64, _P, _P, _P, _P, _I32, _P]),
+                                   ctypes.POINTER(_F64), _F64, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
     "qb_lw_draw_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _I64, _I32, _P, _P, _SZ, _I32,
                                        ctypes.POINTER(_F64), ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I32,
                                        _I64, _P, _I32, _P, _P, _P]),

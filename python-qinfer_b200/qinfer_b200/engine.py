@@ -409,6 +409,14 @@ class DeviceCloud(object):
         self.launches += 2
         return self._js
 
+    def _lw_consts(self):
+        """This cloud's device buffer for S and (1 - a) mean of the staged Liu-West kernels (caller-owned)."""
+        buf = getattr(self, '_lw_consts_buf', None)
+        if buf is None:
+            nbytes = self.lib.qb_lw_move_workspace_bytes(self.d)
+            self._lw_consts_buf = buf = torch.empty(((nbytes + 7) // 8,), dtype=torch.float64, device=self.device)
+        return buf
+
     def lw_move(self, mean, S, a, eps_dev, n_new, postselect, x_src=None, js=None):
         """x_alt[i] = a * x_src[js[i]] + (1-a) * mean + S @ eps[:, i] (x_src defaults to the current slab)."""
         self._alt_slab(n_new)
@@ -417,7 +425,8 @@ class DeviceCloud(object):
         check(self.lib.qb_lw_move(self.lib_model, _ptr(src), src.shape[0], self.d, _ptr(js),
                                   _lib.f64_array(mean), _lib.f64_array(np.asarray(S).reshape(-1)), float(a),
                                   _ptr(eps_dev), int(n_new), _ptr(self.x_alt), int(bool(postselect)),
-                                  _ptr(self._invalid), _ptr(self.counter), _stream()))
+                                  _ptr(self._invalid), _ptr(self.counter), _ptr(self._lw_consts()),
+                                  self._lw_consts().numel() * 8, _stream()))
         self.launches += 1
 
     def lw_draw_move(self, mean, S, a, seed_u, off_u, seed_n, off_n, n_new, postselect, dst=None, scale_u=False,
@@ -689,7 +698,8 @@ class DeviceCloud(object):
                                    _ptr(self._idxs), int(k), _lib.f64_array(mean),
                                    _lib.f64_array(np.asarray(S).reshape(-1)), float(a), _ptr(eps_dev),
                                    _ptr(self.x_alt), _ptr(self._invalid), _ptr(self.counter),
-                                   1 if own_mean else 0, _stream()))
+                                   1 if own_mean else 0, _ptr(self._lw_consts()), self._lw_consts().numel() * 8,
+                                   _stream()))
         self.launches += 1
 
     def _swap_slabs(self, n_new):

@@ -91,6 +91,8 @@ def main():
     cpu_ns = cases.oracle_namespace()
     plan = [
         ("C1 SimplePrecession N=1e3 x 100 updates (default LW, numpy RNG, exact scan)", c1, 1000, 100, 1000, 100, False),
+        ("C1 as above with lazy=True (updates buffered and fused 8 per launch: the small-cloud path)", c1, 1000, 100, 1000,
+         100, True),
         ("C3 Binomial(RB) N=1e6 x 201 updates, batch_update(resample_interval=1)", c3, 10 ** 6, 201, 10 ** 5, 40, True),
         ("C4 Tomography 2 qubits (d=16) N=1e6 x 200 updates, canonicalize", c4, 10 ** 6, 200, 2000, 40, True),
     ]
