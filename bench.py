@@ -90,6 +90,14 @@ class FixedPrior(object):
 
 def drive(up, ts, outcomes, lo, hi):
     """Steps lo .. hi-1 of the workload through the public API (one ``update`` per datum)."""
+    if os.environ.get("QB_BENCH_TRACE") and hi - lo <= 64:       # diagnostics: host time after every call
+        t0 = time.perf_counter()
+        stamps = []
+        for k in range(lo, hi):
+            up.update(int(outcomes[k]), ts[k:k + 1])
+            stamps.append(int((time.perf_counter() - t0) * 1e6))
+        sys.stderr.write("[trace rank %s] steps %d..%d host us: %s\n" % (os.environ.get("RANK", "0"), lo, hi, stamps))
+        return
     for k in range(lo, hi):
         up.update(int(outcomes[k]), ts[k:k + 1])
 
@@ -102,6 +110,8 @@ class ClockSampler(object):
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    PERIOD_MS = 200     # the profiling recipe's period: a faster poll holds the driver lock often enough to delay launches
+
     def __init__(self, gpu_index):
         self.path = "/tmp/qb_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
         self.proc = None
@@ -111,7 +121,7 @@ class ClockSampler(object):
         try:
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -334,6 +344,30 @@ class CudaBackend(object):
             cloud.preallocate_resample()
         else:
             cloud.preallocate_binned()
+        if os.environ.get("QB_BENCH_TRACE"):                 # diagnostics: host time of every stage of a resample
+            stages = []
+
+            def wrap(obj, name):
+                fn = getattr(obj, name, None)
+                if fn is None:
+                    return
+
+                def inner(*a, **k):
+                    t_a = time.perf_counter()
+                    r = fn(*a, **k)
+                    stages.append("%s %d" % (name, (time.perf_counter() - t_a) * 1e6))
+                    if name in ("adopt_binned", "_finish_resample"):
+                        sys.stderr.write("[trace rank %s] resample stages (us): %s\n"
+                                         % (os.environ.get("RANK", "0"), ", ".join(stages)))
+                        del stages[:]
+                    return r
+                setattr(obj, name, inner)
+            for nm in ("binned_sums", "binned_count", "binned_move", "binned_resample", "binned_moments_wait",
+                       "binned_retry_wait", "binned_counters_wait", "_alt_slab", "adopt_binned"):
+                wrap(cloud, nm)
+            if sharded:
+                wrap(up._comm, "all_gather_rows")
+                wrap(up, "_liu_west_consts")
         return up
 
     def pinned(self, array):
@@ -418,9 +452,9 @@ def timed_run(be, n, prior, ts, outcomes, warm, steps, mode='throughput', fuse=1
     if clocks is not None:
         clocks.start()
         clocks.wait_first_sample()                   # nvidia-smi's start-up stays outside the timed region
+    gc.collect()                                     # (before the barrier: a collection takes milliseconds and would
+    gc.disable()                                     #  skew the ranks' entry into the timed region)
     be.barrier()
-    gc.collect()
-    gc.disable()                                     # no collector pauses inside the timed region (host hygiene)
     t = be.timer()
     t.start()
     drive(up, ts, outcomes, warm, warm + steps)
@@ -445,6 +479,7 @@ def e2e_run(be, n, pinned_prior, ts, outcomes, warm, steps, fuse=1, seed=1000):
     """From HOST arrays through the public API: prior upload (page-locked source), K updates, posterior mean read;
     then the read-back of the whole posterior cloud, timed separately."""
     prior = pinned_prior.numpy()
+    gc.collect()
     be.barrier()
     t0 = time.perf_counter()
     t = be.timer()
@@ -595,7 +630,7 @@ def gpu_arm(args, rank, world, local_rank, backend=None):
         stage = [be.pinned(prior), be.pinned(prior[:, 0])]
         del stage
         # ---------------- value: state resident in HBM ----------------
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("QB_BENCH_NO_CLOCKS")) else None
         run = timed_run(be, n, prior, ts, outcomes, warm, steps, fuse=args.fuse, seed=1000 + rank, clocks=sampler)
         # ---------------- e2e: from host arrays, through the public API ----------------
         e2e = e2e_run(be, n, pinned_prior, ts, outcomes, warm, steps, fuse=args.fuse, seed=1000 + rank)

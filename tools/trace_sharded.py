@@ -20,6 +20,16 @@ for rep in range(2):
     up._flush()
     be.barrier()
     marks = []
+    stages = []
+    def wrap(obj, name):
+        fn = getattr(obj, name)
+        def inner(*a, **k):
+            t_a = time.perf_counter(); r = fn(*a, **k); stages.append((name, t_a, time.perf_counter())); return r
+        setattr(obj, name, inner)
+    for nm in ("binned_sums", "binned_count", "binned_move", "binned_retry_wait", "binned_counters_wait", "adopt_binned", "_alt_slab"):
+        wrap(up._cloud, nm)
+    wrap(up._comm, "all_gather_rows")
+    wrap(up, "_liu_west_consts")
     orig_resample = up.resample
     def traced():
         t0 = time.perf_counter(); orig_resample(); marks.append(("resample", t0, time.perf_counter()))
@@ -36,6 +46,7 @@ for rep in range(2):
     if rank == 0:
         print("rep", rep, "per-step host stamps (us):", " ".join("%.0f" % (s * 1e6) for s in stamps), "flush %.0f sync %.0f" % (tf * 1e6, te * 1e6))
         print("   resamples:", [(round((a - t0) * 1e6), round((b - t0) * 1e6)) for _, a, b in marks])
+        print("   stages:", " ".join("%s %d-%d" % (nm, (a - t0) * 1e6, (b - t0) * 1e6) for nm, a, b in stages))
     be.close(up)
     del up
 be.finish()
