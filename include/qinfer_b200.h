@@ -75,6 +75,13 @@ typedef struct qb_model {
                              DiffusiveTomographyModel (tomography/models.py:229-256) */
     int32_t extra_rule;   /* their validity (are_models_valid): 0 none, 1 all >= 0 (derived_models.py:883-892),
                              2 the last one > 0 (tomography/models.py:245-249) */
+    int32_t fast_math;    /* 0 (default): the reference's operation sequence — pow() for p ** m (rb.py:193), SciPy's
+                             exp(logC + k log p + (n-k) log1p(-p)) for the binomial pmf (utils.py:106-111).
+                             1: integer powers by squaring — p ** m (m is an unsigned integer in the reference) and, for
+                             n_meas <= 56, C(n,k) p^k (1-p)^(n-k) with the exact binomial coefficient: no pow / log /
+                             exp per particle.  Relative deviation from the strict path <= 1e-13 (each of the <= 2 log2
+                             multiplications rounds once); north_star's 1e-6 on mean / covariance is unaffected. */
+    int32_t reserved0;
 } qb_model;
 
 /* One experiment record (one element of the `expparams` array handed to

@@ -19,7 +19,9 @@ struct ExpView {
     double n_meas, k;  // BinomialModel: shots and observed count
     double logc;       // lgamma(n+1) - lgamma(k+1) - lgamma(n-k+1), hoisted per update
     int32_t k_in_range; // 0 <= k <= n
-    int32_t pad;
+    int32_t fast_binom; // fast_math: n_meas small enough for C(n,k) p^k (1-p)^(n-k) by integer powers
+    double binc;       // fast_math: the binomial coefficient C(n, k) (exact below 2^53)
+    uint32_t m_int, k_int, nk_int, pad;   // fast_math: the integer exponents
 };
 
 struct ModelView {
@@ -27,6 +29,7 @@ struct ModelView {
     double min_freq;
     double like_pow;   // MLEModel: L ** like_pow (1 = plain)
     int32_t d_extra, extra_rule;  // trailing parameters the likelihood ignores, and their validity rule
+    int32_t fast_math, pad0;      // integer powers instead of pow / log / exp (qb_model.fast_math)
 };
 
 __host__ inline ExpView make_exp_view(const qb_model& m, const qb_expparams& ep, int64_t outcome) {
@@ -44,7 +47,33 @@ __host__ inline ExpView make_exp_view(const qb_model& m, const qb_expparams& ep,
         v.logc = lgamma(v.n_meas + 1.0) - lgamma(v.k + 1.0) - lgamma(v.n_meas - v.k + 1.0);
     }
     v.pad = 0;
+    v.fast_binom = 0;
+    v.binc = 1.0;
+    v.m_int = static_cast<uint32_t>(static_cast<uint64_t>(ep.m));
+    v.k_int = v.nk_int = 0;
+    if (m.fast_math && m.binomial && v.k_in_range && ep.n_meas <= 56) {
+        // C(n, k) by the multiplicative formula in extended precision: exact integers below 2^53 for n <= 56
+        const int64_t k = (outcome < ep.n_meas - outcome) ? outcome : ep.n_meas - outcome;
+        long double c = 1.0L;
+        for (int64_t i = 1; i <= k; ++i) c = c * static_cast<long double>(ep.n_meas - k + i) / static_cast<long double>(i);
+        v.binc = static_cast<double>(roundl(c));
+        v.k_int = static_cast<uint32_t>(outcome);
+        v.nk_int = static_cast<uint32_t>(ep.n_meas - outcome);
+        v.fast_binom = 1;
+    }
     return v;
+}
+
+// x ** e for an unsigned integer exponent by squaring: <= 2 log2(e) multiplications, each rounding once.  The exponent is
+// uniform over the launch, so the loop does not diverge.
+__device__ __forceinline__ double ipow(double x, uint32_t e) {
+    double r = 1.0;
+    while (e) {
+        if (e & 1u) r *= x;
+        e >>= 1;
+        if (e) x *= x;
+    }
+    return r;
 }
 
 __host__ inline ModelView make_model_view(const qb_model& m) {
@@ -57,6 +86,8 @@ __host__ inline ModelView make_model_view(const qb_model& m) {
     v.like_pow = (m.likelihood_power == 0.0) ? 1.0 : m.likelihood_power;
     v.d_extra = m.d_extra;
     v.extra_rule = m.extra_rule;
+    v.fast_math = m.fast_math;
+    v.pad0 = 0;
     return v;
 }
 
@@ -87,7 +118,7 @@ __device__ __forceinline__ double model_pr0(const ModelView& mv, const ExpView& 
             A = row(1);
             B = row(2);
         }
-        double pm = pow(p, ev.m);
+        double pm = mv.fast_math ? ipow(p, ev.m_int) : pow(p, ev.m);
         return 1.0 - (A * pm + B);
     } else if (KIND == QB_MODEL_COIN) {
         return row(0);  // test_models.py:323: pr0 is the coin's bias itself
@@ -109,6 +140,7 @@ __device__ __forceinline__ double model_pr0(const ModelView& mv, const ExpView& 
 // exp(logC + xlogy(k, p) + xlog1py(n - k, -p)).
 __device__ __forceinline__ double binom_pmf(const ExpView& ev, double p) {
     if (!ev.k_in_range) return 0.0;
+    if (ev.fast_binom) return (ev.binc * ipow(p, ev.k_int)) * ipow(1.0 - p, ev.nk_int);
     double t1 = (ev.k == 0.0) ? 0.0 : ev.k * log(p);
     double nk = ev.n_meas - ev.k;
     double t2 = (nk == 0.0) ? 0.0 : nk * log1p(-p);

@@ -25,7 +25,8 @@ _LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(os.path.dirname(os.pat
 class QbModel(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("d", ctypes.c_int32), ("binomial", ctypes.c_int32),
                 ("interleaved", ctypes.c_int32), ("min_freq", ctypes.c_double),
-                ("likelihood_power", ctypes.c_double), ("d_extra", ctypes.c_int32), ("extra_rule", ctypes.c_int32)]
+                ("likelihood_power", ctypes.c_double), ("d_extra", ctypes.c_int32), ("extra_rule", ctypes.c_int32),
+                ("fast_math", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
 
 
 class QbExpparams(ctypes.Structure):

@@ -32,10 +32,13 @@ _EPS = np.spacing(1)
 class SMCUpdater(object):
     def __init__(self, model, n_particles, prior, resample_a=None, resampler=None, resample_thresh=0.5,
                  debug_resampling=False, track_resampling_divergence=False, zero_weight_policy='error',
-                 zero_weight_thresh=None, canonicalize=True, device=None, lazy=False, fuse=None):
+                 zero_weight_thresh=None, canonicalize=True, device=None, lazy=False, fuse=None, fast_math=False):
         if track_resampling_divergence:
             raise NotImplementedError("track_resampling_divergence is outside the B200 hot path (SURVEY §2 1b)")
         self._desc = describe_model(model)        # raises UnsupportedModelError: no CPU fallback
+        # fast_math=True: integer powers by squaring instead of pow / log / exp in the RB and binomial likelihoods
+        # (relative deviation <= 1e-13 from the reference's operation sequence; the default keeps that sequence)
+        self._desc.c_model.fast_math = 1 if fast_math else 0
         self._device = device
         self._cloud = None
         self._resample_count = 0

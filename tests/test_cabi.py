@@ -40,7 +40,7 @@ def test_binding_covers_every_declared_symbol_and_loads():
 
 def test_struct_layouts_match_the_header():
     from qinfer_b200 import _lib
-    assert ctypes.sizeof(_lib.QbModel) == 40          # + d_extra, extra_rule (ABI 3)
+    assert ctypes.sizeof(_lib.QbModel) == 48          # + d_extra, extra_rule, fast_math, reserved (ABI 3)
     assert ctypes.sizeof(_lib.QbExpparams) == 8 + 8 + 8 + 4 + 4 + 8 + 8 * _lib.QB_MAX_D
     assert _lib.QbExpparams.meas.offset == 40
     sizes = (ctypes.c_int32 * 3)()

@@ -990,3 +990,38 @@ def test_design_under_mle_model_follows_the_reference_complement(qb, golden):
         ok = np.isfinite(g[key])
         assert ok.any()
         np.testing.assert_allclose(got[key][ok], g[key][ok], rtol=1e-9, err_msg=key)
+
+
+@pytest.mark.parametrize("binomial", [False, True])
+def test_fast_math_likelihoods_within_1e12_of_the_strict_path(qb, binomial):
+    """SMCUpdater(fast_math=True): p ** m and the binomial pmf by integer powers (qb_model.fast_math) against the
+    reference's operation sequence (pow, exp(logC + k log p + (n-k) log1p(-p))): weights within 2e-13 relative per update,
+    records and n_ess likewise, over sequence lengths up to 800 and every count k of n_meas = 25."""
+    rs = np.random.RandomState(6)
+    n = 200000
+    x = np.column_stack([0.8 + 0.2 * rs.random_sample(n), 0.5 * rs.random_sample(n), 0.5 * rs.random_sample(n)])
+    model = qb.RandomizedBenchmarkingModel()
+    if binomial:
+        model = qb.BinomialModel(model)
+    eps = np.empty((26,), dtype=model.expparams_dtype)
+    eps['m'] = np.linspace(1, 800, 26).astype(int)
+    if binomial:
+        eps['n_meas'] = 25
+    outs = {}
+    for fast in (False, True):
+        up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resample_thresh=0.0, fast_math=fast)
+        ws = []
+        for k in range(26):
+            up.update(k if binomial else k % 2, eps[k:k + 1])
+            if k in (0, 5, 25):
+                ws.append(up.particle_weights.copy())
+        outs[fast] = (ws, np.array(up.normalization_record), up.n_ess)
+    (w0, r0, e0), (w1, r1, e1) = outs[False], outs[True]
+    for a, b in zip(w0, w1):
+        rel = np.abs(b - a) / np.maximum(np.abs(a), 1e-300)
+        worst = int(np.argmax(rel))
+        # (<= 2e-13 per update — the strict path's exp() of an argument near -100 is the noisier side — over 26 updates)
+        assert rel[worst] <= 26 * 2e-13, (rel[worst], a[worst], b[worst], x[worst])
+    np.testing.assert_allclose(r1, r0, rtol=1e-12)
+    assert abs(e1 - e0) <= 1e-11 * e0
+    report("fast_math_%s_weights_rel" % ("binom" if binomial else "rb"), relerr(w1[-1], w0[-1], floor=1e-300))

@@ -44,10 +44,12 @@ def c1(ns, n, n_updates, lazy):
     return run
 
 
-def c3(ns, n, n_updates, lazy):
+def c3(ns, n, n_updates, lazy, fast_math=False):
     inp = cases.rb_inputs(n_particles=n, n_updates=n_updates)
     model = ns.BinomialModel(ns.RandomizedBenchmarkingModel())
     kw = dict(lazy=True, resampler=ns.LiuWestResampler(a=0.98, rng='philox', scan='fast', seed=1)) if lazy else {}
+    if fast_math:
+        kw['fast_math'] = True
     np.random.seed(0)
     up = ns.SMCUpdater(model, n, cases.FixedPrior(inp['prior']), **kw)
     eps = np.empty((n_updates,), dtype=model.expparams_dtype)
@@ -94,6 +96,8 @@ def main():
         ("C1 as above with lazy=True (updates buffered and fused 8 per launch: the small-cloud path)", c1, 1000, 100, 1000,
          100, True),
         ("C3 Binomial(RB) N=1e6 x 201 updates, batch_update(resample_interval=1)", c3, 10 ** 6, 201, 10 ** 5, 40, True),
+        ("C3 as above with fast_math=True (integer powers instead of pow / log / exp)",
+         lambda ns, n, k, lazy: c3(ns, n, k, lazy, fast_math=(ns is gpu_ns)), 10 ** 6, 201, 10 ** 5, 40, True),
         ("C4 Tomography 2 qubits (d=16) N=1e6 x 200 updates, canonicalize", c4, 10 ** 6, 200, 2000, 40, True),
     ]
     results = []
@@ -106,6 +110,7 @@ def main():
             warm()                                                     # including the resample's
             warm.updater.resample()
             warm.updater.est_mean()
+            fn(gpu_ns, n, min(k, 30), lazy)()                          # ... and the allocator / pinned blocks at full size
             t_gpu, (mean_g, rc_g) = timed_run(fn(gpu_ns, n, k, lazy))
             t_cpu, (mean_c, rc_c) = timed_run(fn(cpu_ns, n_cpu, k_cpu, False))
             r = dict(config=label, gpu_particles=n, gpu_updates=k, gpu_seconds=t_gpu, gpu_resamples=int(rc_g),

@@ -27,8 +27,9 @@ def timed(fn, reps=50, warm=5):
     return e0.elapsed_time(e1) / reps * 1e3   # us
 
 
-def bench_update(n, model, ep_setup, d, label, fuse_list=(1,)):
+def bench_update(n, model, ep_setup, d, label, fuse_list=(1,), fast_math=False):
     desc = qb.describe_model(model)
+    desc.c_model.fast_math = 1 if fast_math else 0
     cloud = DeviceCloud(desc, n)
     rs = np.random.RandomState(0)
     if d == 1:
@@ -93,11 +94,14 @@ def main():
             ep.n_meas = 25
             return 12
         bench_update(n // 4, qb.BinomialModel(qb.RandomizedBenchmarkingModel()), rbb, 3, "update binomial(RB) d=3", (1, 8))
+        bench_update(n // 4, qb.BinomialModel(qb.RandomizedBenchmarkingModel()), rbb, 3,
+                     "update binomial(RB) fast_math", (1, 8), fast_math=True)
 
         def rb(ep):
             ep.m = 37
             return 1
         bench_update(n // 4, qb.RandomizedBenchmarkingModel(), rb, 3, "update RB d=3")
+        bench_update(n // 4, qb.RandomizedBenchmarkingModel(), rb, 3, "update RB d=3 fast_math", fast_math=True)
 
         def tomo(ep):
             for c in range(16):
