@@ -35,6 +35,7 @@
 // re-centres the slot on its own parent with normals indexed by SLOT (deterministic whatever the list order).
 //
 // Compiled with --fmad=false (one rounding per reference ufunc in the move; explicit fma() in the reductions).
+#include <cstdlib>
 #include "qb_models.cuh"
 #include "qb_philox.cuh"
 
@@ -232,6 +233,94 @@ __device__ void liu_west_consts(const double* out /* 1 + D + D*D moments */, dou
     for (int c = 0; c < 4; ++c) consts[16 + c] = (c < D) ? oma * mean[c] : 0.0;   // (1 - a) * mean
 }
 
+// Tail of pass 1, shared by both kernels: per-block moment partials, last-block-done ticket, and in the last block the
+// bin-level CDF, the finished moments, the Liu-West constants and the host mirror.  NW = warps of the block.
+template <int D, int NW>
+__device__ __forceinline__ void sums_finish(const BinSumsParams& p, const double (&acc)[1 + D + D * (D + 1) / 2],
+                                            double* mred, double* scan_tot, unsigned int* is_last_p) {
+    constexpr int NOUT = 1 + D + D * (D + 1) / 2;
+    constexpr int NTHREADS = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned int& is_last = *is_last_p;
+    // moment partials of this block (fixed order)
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) mred[wid * NOUT + k] = v;
+    }
+    __syncthreads();
+    if (tid < NOUT) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) v += mred[k * NOUT + tid];
+        p.partials[static_cast<size_t>(blockIdx.x) * NOUT + tid] = v;
+    }
+    __threadfence();   // every warp's bin sums (lane 0) and the partials, before this block's ticket
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(p.ticket, 1u);
+        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- last block: bin sums -> exclusive prefix (the bin-level CDF) ----
+    const int T = p.T;
+    const int per = (T + NTHREADS - 1) / NTHREADS;
+    const int lo = tid * per, hi = (lo + per < T) ? lo + per : T;
+    double s = 0.0;
+    for (int i = lo; i < hi; ++i) s += __ldcg(p.bounds + i);
+    double total;
+    double run = block_excl_scan<double, NW>(s, scan_tot, total);
+    for (int i = lo; i < hi; ++i) {
+        const double v = __ldcg(p.bounds + i);
+        p.bounds[i] = run;
+        run += v;
+    }
+    if (tid == 0) {
+        p.bounds[T] = total;
+        p.counts[T] = 0u;
+        p.counts[T + 1] = 0u;
+    }
+    // ---- moments: one warp per output, lanes stride over the blocks' partials (fixed order) ----
+    __shared__ double fin[NOUT];
+    for (int o = wid; o < NOUT; o += NW) {
+        double v = 0.0;
+        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) v += __ldcg(p.partials + static_cast<size_t>(b) * NOUT + o);
+        v = warp_sum(v);
+        if (lane == 0) fin[o] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double out[1 + D + D * D];
+        out[0] = fin[0];
+#pragma unroll
+        for (int m = 0; m < D; ++m) out[1 + m] = fin[1 + m];
+        int o = 1 + D;
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int c = m; c < D; ++c) {
+                out[1 + D + m * D + c] = fin[o];
+                out[1 + D + c * D + m] = fin[o];
+                ++o;
+            }
+        if (p.moments_out != nullptr)
+            for (int k = 0; k < 1 + D + D * D; ++k) p.moments_out[k] = out[k];
+        double flags = 0.0, err = 0.0;
+        if (p.consts != nullptr) liu_west_consts<D>(out, p.a, p.h, p.zero_cov_comp, p.consts, flags, err);
+        if (p.mirror != nullptr) {
+            for (int k = 0; k < 1 + D + D * D; ++k) p.mirror[k] = out[k];
+            p.mirror[29] = flags;
+            p.mirror[30] = err;
+            __threadfence_system();
+            *reinterpret_cast<volatile double*>(p.mirror + 31) = p.tag;
+        }
+        *p.ticket = 0u;
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(BIN_THREADS) binned_sums_kernel(const __grid_constant__ BinSumsParams p) {
     constexpr int NOUT = 1 + D + D * (D + 1) / 2;
@@ -301,83 +390,164 @@ __global__ void __launch_bounds__(BIN_THREADS) binned_sums_kernel(const __grid_c
             p.counts[t] = 0u;
         }
     }
-    // moment partials of this block (fixed order)
-#pragma unroll
-    for (int k = 0; k < NOUT; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) mred[wid * NOUT + k] = v;
-    }
-    __syncthreads();
-    if (tid < NOUT) {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < NW; ++k) v += mred[k * NOUT + tid];
-        p.partials[static_cast<size_t>(blockIdx.x) * NOUT + tid] = v;
-    }
-    __threadfence();   // every warp's bin sums (lane 0) and the partials, before this block's ticket
-    __syncthreads();
+    sums_finish<D, NW>(p, acc, mred, scan_tot, &is_last);
+}
+
+// Pass 1, streaming variant: whole bins (w: 16 KB, x: 16 D KB) are staged global -> shared with 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) through a STAGES-deep full/empty mbarrier ring by one producer
+// lane, like the fused update kernel; 8 consumer warps read 128-bit conflict-free shared loads of particle PAIRS.
+// Each consumer warp owns a fixed 256-particle eighth of every bin; the eighth sums meet in shared memory and the
+// last warp to arrive adds them in warp order (deterministic) and writes the bin sum.  The ragged last bin (n not a
+// multiple of 2048) is read directly by block 0.
+constexpr int SUMS_CONSUMERS = 8;
+constexpr int SUMS_THREADS = (SUMS_CONSUMERS + 1) * 32;
+
+template <int D, int STAGES>
+__global__ void __launch_bounds__(SUMS_THREADS) binned_sums_tma_kernel(const __grid_constant__ BinSumsParams p) {
+    constexpr int NOUT = 1 + D + D * (D + 1) / 2;
+    constexpr int NW = SUMS_THREADS / 32;
+    constexpr uint32_t W_BYTES = BIN * 8u, X_BYTES = BIN * D * 8u, STAGE_BYTES = W_BYTES + X_BYTES;
+    extern __shared__ __align__(128) unsigned char ssm[];
+    __shared__ double mred[NW * NOUT];
+    __shared__ double scan_tot[NW];
+    __shared__ double eighth[STAGES][SUMS_CONSUMERS];
+    __shared__ unsigned int arrived[STAGES];
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t bar0 = smem_u32(ssm);          // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
+    unsigned char* ring = ssm + 128;
+    const uint32_t ring0 = smem_u32(ring);
+    const int64_t full_bins = p.n / BIN;
+    const int my_bins = (full_bins > static_cast<int64_t>(blockIdx.x))
+                            ? static_cast<int>((full_bins - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     if (tid == 0) {
-        __threadfence();
-        const unsigned int prev = atomicAdd(p.ticket, 1u);
-        is_last = (prev == gridDim.x - 1) ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // ---- last block: bin sums -> exclusive prefix (the bin-level CDF) ----
-    const int T = p.T;
-    const int per = (T + BIN_THREADS - 1) / BIN_THREADS;
-    const int lo = tid * per, hi = (lo + per < T) ? lo + per : T;
-    double s = 0.0;
-    for (int i = lo; i < hi; ++i) s += __ldcg(p.bounds + i);
-    double total;
-    double run = block_excl_scan<double, NW>(s, scan_tot, total);
-    for (int i = lo; i < hi; ++i) {
-        const double v = __ldcg(p.bounds + i);
-        p.bounds[i] = run;
-        run += v;
-    }
-    if (tid == 0) {
-        p.bounds[T] = total;
-        p.counts[T] = 0u;
-        p.counts[T + 1] = 0u;
-    }
-    // ---- moments: one warp per output, lanes stride over the blocks' partials (fixed order) ----
-    __shared__ double fin[NOUT];
-    for (int o = wid; o < NOUT; o += NW) {
-        double v = 0.0;
-        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) v += __ldcg(p.partials + static_cast<size_t>(b) * NOUT + o);
-        v = warp_sum(v);
-        if (lane == 0) fin[o] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double out[1 + D + D * D];
-        out[0] = fin[0];
 #pragma unroll
-        for (int m = 0; m < D; ++m) out[1 + m] = fin[1 + m];
-        int o = 1 + D;
-#pragma unroll
-        for (int m = 0; m < D; ++m)
-#pragma unroll
-            for (int c = m; c < D; ++c) {
-                out[1 + D + m * D + c] = fin[o];
-                out[1 + D + c * D + m] = fin[o];
-                ++o;
-            }
-        if (p.moments_out != nullptr)
-            for (int k = 0; k < 1 + D + D * D; ++k) p.moments_out[k] = out[k];
-        double flags = 0.0, err = 0.0;
-        if (p.consts != nullptr) liu_west_consts<D>(out, p.a, p.h, p.zero_cov_comp, p.consts, flags, err);
-        if (p.mirror != nullptr) {
-            for (int k = 0; k < 1 + D + D * D; ++k) p.mirror[k] = out[k];
-            p.mirror[29] = flags;
-            p.mirror[30] = err;
-            __threadfence_system();
-            *reinterpret_cast<volatile double*>(p.mirror + 31) = p.tag;
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);
+            mbar_init(bar0 + 64 + 8 * s, SUMS_CONSUMERS);
+            arrived[s] = 0u;
         }
-        *p.ticket = 0u;
+        mbar_fence_init();
     }
+    __syncthreads();
+    double acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = 0.0;
+    const double inv = p.stats[QB_STAT_INV_NORM];
+
+    if (wid == SUMS_CONSUMERS) {
+        if (lane == 0) {   // ===== producer lane =====
+            const uint64_t pol = l2_policy_evict_first();
+            int s = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < my_bins; ++i) {
+                const int64_t first = (static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x) * BIN;
+                mbar_wait(bar0 + 64 + 8 * s, phase ^ 1u);   // passes at once the first time round the ring
+                const uint32_t dst = ring0 + static_cast<uint32_t>(s) * STAGE_BYTES;
+                mbar_expect_tx(bar0 + 8 * s, STAGE_BYTES);
+                tma_load_1d_hint(dst, p.x + first * D, X_BYTES, bar0 + 8 * s, pol);
+                tma_load_1d_hint(dst + X_BYTES, p.w + first, W_BYTES, bar0 + 8 * s, pol);
+                if (++s == STAGES) {
+                    s = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== consumer warps =====
+        int s = 0;
+        uint32_t phase = 0;
+        for (int i = 0; i < my_bins; ++i) {
+            const int64_t t = static_cast<int64_t>(blockIdx.x) + static_cast<int64_t>(i) * gridDim.x;
+            const double* xs = reinterpret_cast<const double*>(ring + static_cast<size_t>(s) * STAGE_BYTES);
+            const double* ws = reinterpret_cast<const double*>(ring + static_cast<size_t>(s) * STAGE_BYTES + X_BYTES);
+            mbar_wait(bar0 + 8 * s, phase);
+            double sub = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = 256 * wid + 64 * k + 2 * lane;       // my pair of this quarter of the warp's eighth
+                const double2 wp = *reinterpret_cast<const double2*>(ws + j);
+                double xr[2 * D];
+#pragma unroll
+                for (int v = 0; v < D; ++v) {
+                    const double2 t2 = *reinterpret_cast<const double2*>(xs + static_cast<size_t>(j) * D + 2 * v);
+                    xr[2 * v] = t2.x;
+                    xr[2 * v + 1] = t2.y;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double wi = (h == 0 ? wp.x : wp.y) * inv;
+                    sub += wi;
+                    acc[0] += wi;
+                    int o = 1 + D;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) {
+                        const double wx = wi * xr[h * D + m];
+                        acc[1 + m] += wx;
+#pragma unroll
+                        for (int c = m; c < D; ++c) {
+                            acc[o] = fma(wx, xr[h * D + c], acc[o]);
+                            ++o;
+                        }
+                    }
+                }
+            }
+            sub = warp_sum(sub);
+            if (lane == 0) {
+                eighth[s][wid] = sub;
+                __threadfence_block();
+                if (atomicAdd(&arrived[s], 1u) == SUMS_CONSUMERS - 1) {     // last warp of this bin: fixed-order sum
+                    __threadfence_block();
+                    double tot = 0.0;
+#pragma unroll
+                    for (int q = 0; q < SUMS_CONSUMERS; ++q) tot += *reinterpret_cast<volatile double*>(&eighth[s][q]);
+                    p.bounds[t] = tot;
+                    p.counts[t] = 0u;
+                    arrived[s] = 0u;
+                }
+                mbar_arrive(bar0 + 64 + 8 * s);   // only now may the producer refill stage s (and eighth[s] be reused)
+            }
+            __syncwarp();
+            if (++s == STAGES) {
+                s = 0;
+                phase ^= 1u;
+            }
+        }
+    }
+    __syncthreads();
+    // ragged last bin: straight from global memory, by block 0 (its sum is written before the ticket below)
+    if (blockIdx.x == 0 && full_bins < p.T) {
+        const int64_t first = full_bins * BIN;
+        const int cnt = static_cast<int>(p.n - first);
+        double sub = 0.0;
+        for (int j = tid; j < cnt; j += SUMS_THREADS) {
+            const double wi = p.w[first + j] * inv;
+            sub += wi;
+            acc[0] += wi;
+            int o = 1 + D;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                const double wx = wi * p.x[(first + j) * D + m];
+                acc[1 + m] += wx;
+#pragma unroll
+                for (int c = m; c < D; ++c) {
+                    acc[o] = fma(wx, p.x[(first + j) * D + c], acc[o]);
+                    ++o;
+                }
+            }
+        }
+        sub = warp_sum(sub);
+        if (lane == 0) scan_tot[wid] = sub;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int q = 0; q < NW; ++q) tot += scan_tot[q];
+            p.bounds[full_bins] = tot;
+            p.counts[full_bins] = 0u;
+        }
+        __syncthreads();
+    }
+    sums_finish<D, NW>(p, acc, mred, scan_tot, &is_last);
 }
 
 // =============================================================================================================
@@ -906,6 +1076,30 @@ static int launch_sums(const double* d_x, const double* d_w, const double* d_sta
     sp.a = a;
     sp.h = h;
     sp.zero_cov_comp = zero_cov_comp;
+    static int tma_mode = -1;
+    if (tma_mode < 0) {
+        const char* e = getenv("QB_BINNED_SUMS_TMA");   // experiment knob: 0 = the register-streaming kernel
+        tma_mode = e ? atoi(e) : 1;
+    }
+    const int64_t full_bins = n_old / BIN;
+    if (tma_mode && full_bins >= 1) {
+        typedef void (*sums_kernel_t)(const BinSumsParams);
+        static const sums_kernel_t kernels[4] = {binned_sums_tma_kernel<1, 3>, binned_sums_tma_kernel<2, 3>,
+                                                 binned_sums_tma_kernel<3, 2>, binned_sums_tma_kernel<4, 2>};
+        static const int stages[4] = {3, 3, 2, 2};
+        static int per_sm[4] = {0, 0, 0, 0};
+        const size_t smem = 128 + static_cast<size_t>(stages[d - 1]) * BIN * (d + 1) * 8;
+        if (per_sm[d - 1] == 0) {
+            QB_CUDA_CHECK(cudaFuncSetAttribute(kernels[d - 1], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            int occ = 0;
+            QB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernels[d - 1], SUMS_THREADS, smem));
+            per_sm[d - 1] = occ < 1 ? 1 : occ;
+        }
+        const int g1 = bin_grid(full_bins, per_sm[d - 1]);
+        kernels[d - 1]<<<g1, SUMS_THREADS, smem, st>>>(sp);
+        QB_CUDA_CHECK(cudaGetLastError());
+        return QB_OK;
+    }
     const int g1 = bin_grid((L.T + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32), (d <= 2) ? 4 : 2);
     switch (d) {
         case 1: binned_sums_kernel<1><<<g1, BIN_THREADS, 0, st>>>(sp); break;

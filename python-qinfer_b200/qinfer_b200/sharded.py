@@ -381,6 +381,7 @@ def _make_sharded_updater_class():
             self._split_rng = np.random.Generator(np.random.Philox(key=int(seeds[0]) & ((1 << 64) - 1)))
             self._stream_seed = (int(seeds[0]) + 0x9E3779B97F4A7C15 * (self._comm.rank + 1)) & ((1 << 64) - 1)
             self.last_exchange = (0, 0)
+            self._sample_calls = 0
             self._warm_collectives()
 
         def _warm_collectives(self):
@@ -530,10 +531,66 @@ def _make_sharded_updater_class():
             return cov
 
         def sample(self, n=1):
-            raise NotImplementedError("sample() on a sharded cloud is outside the hot path")
+            """distributions.py:320-333 on the sharded cloud (collective: every rank calls it and receives the SAME
+            ``n`` samples).  A weighted draw of n particles = split n over the shards by their masses (one shared
+            multinomial, like the resample), draw inside each slab, gather the rows."""
+            self._flush()
+            cloud, comm = self._cloud, self._comm
+            masses = comm.all_gather_scalars(self._local_mass(), cloud.device)
+            m = split_counts(self._split_rng, int(n), masses)
+            mine = np.empty((0, cloud.d))
+            if m[comm.rank] > 0:
+                cloud._resample_scratch(cloud.n if cloud._js is None else cloud._js.numel())
+                cloud.cdf(_lib.QB_SCAN_FAST)
+                total = float(cloud._cdf[-1].item())
+                rng = np.random.Generator(np.random.Philox(key=(self._stream_seed + self._sample_calls) & ((1 << 64) - 1)))
+                u = torch.from_numpy(rng.random(m[comm.rank]) * total).to(cloud.device)
+                js = torch.empty((m[comm.rank],), dtype=torch.int64, device=cloud.device)
+                _lib.check(cloud.lib.qb_draw(ctypes.c_void_p(cloud._cdf.data_ptr()), cloud.n,
+                                             ctypes.c_void_p(u.data_ptr()), m[comm.rank],
+                                             ctypes.c_void_p(js.data_ptr()),
+                                             ctypes.c_void_p(cloud.counter[1:].data_ptr()),
+                                             ctypes.c_void_p(cloud.ws.data_ptr()), cloud.ws_bytes,
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                cloud.launches += 2
+                mine = cloud.x.index_select(0, js).cpu().numpy()
+            self._sample_calls += 1
+            parts = comm.all_gather_object(mine)
+            return np.concatenate([p_ for p_ in parts if p_.shape[0]], axis=0)
 
-        def hypothetical_update(self, *a, **k):
-            raise NotImplementedError("hypothetical_update() on a sharded cloud is outside the hot path")
+        def _local_mass(self):
+            """Sum of this slab's globally normalised weights."""
+            cloud = self._cloud
+            _lib.check(cloud.lib.qb_moments(ctypes.c_void_p(cloud.x.data_ptr()), ctypes.c_void_p(cloud.w.data_ptr()),
+                                            ctypes.c_void_p(cloud.stats.data_ptr()), cloud.n, cloud.d,
+                                            ctypes.c_void_p(cloud.moments_out.data_ptr()),
+                                            ctypes.c_void_p(cloud.ws.data_ptr()), cloud.ws_bytes,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            cloud.launches += 2
+            return float(cloud.moments_out[0].item())
+
+        def hypothetical_update(self, outcomes, expparams, return_likelihood=False, return_normalization=False):
+            """smc.py:324-386 on the sharded cloud (collective): this rank's slab of the hypothetical weights,
+            normalised by the GLOBAL sums (one all-reduce of the n_outcomes x n_expparams normalisations)."""
+            self._flush()
+            if not isinstance(outcomes, np.ndarray):
+                outcomes = np.array([outcomes])
+            expparams = np.atleast_1d(expparams)
+            self._count_calls(outcomes.shape[0] * self._cloud.n * expparams.shape[0])
+            w_loc, L, norm_loc = self._cloud.hypothetical_update(outcomes, expparams, return_likelihood)
+            eps_ = np.spacing(1)
+            div_loc = np.where(np.abs(norm_loc) < eps_, 1.0, norm_loc)           # what the kernel divided by
+            sums = torch.from_numpy(np.ascontiguousarray(norm_loc.reshape(-1))).to(self._cloud.device)
+            self._comm.all_reduce_sum(sums)
+            norm = sums.cpu().numpy().reshape(norm_loc.shape)
+            div = np.where(np.abs(norm) < eps_, 1.0, norm)                       # smc.py:369-370 on the global sums
+            weights = w_loc * (div_loc / div)
+            out = (weights,)
+            if return_likelihood:
+                out += (L,)
+            if return_normalization:
+                out += (norm,)
+            return out[0] if len(out) == 1 else out
 
         # -- resampling -------------------------------------------------------------------------
         def resample(self):

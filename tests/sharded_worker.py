@@ -70,6 +70,22 @@ def main():
                 up.particle_weights
                 up.est_mean()
                 up.est_covariance_mtx()
+            # hypothetical_update: this slab of the globally normalised hypothetical weights; sample: the same draws
+            # everywhere, distributed like the weights
+            hyp, hn = up.hypothetical_update(np.array([0, 1]), ts[7:9], return_normalization=True)
+            check(hyp.shape == (2, 2, up.n_local) and hn.shape == (2, 2, 1), "hypothetical shapes")
+            if ref is not None:
+                rh, rn = ref.hypothetical_update(np.array([0, 1]), ts[7:9], return_normalization=True)
+                check(np.allclose(hn, rn, rtol=1e-11), "hypothetical normalisation")
+                check(np.allclose(hyp, rh[:, :, lo:hi], rtol=1e-10, atol=1e-300), "hypothetical weights")
+            smp = up.sample(20000)
+            check(smp.shape == (20000, 1), "sample shape %r" % (smp.shape,))
+            sm_t = torch.tensor([float(smp.sum())], dtype=torch.float64, device='cuda')
+            g2 = [torch.empty_like(sm_t) for _ in range(world)]
+            dist.all_gather(g2, sm_t)
+            check(all(torch.equal(g2[0], q) for q in g2), "ranks drew different samples")
+            mu, sd = up.est_mean()[0], np.sqrt(up.est_covariance_mtx()[0, 0])
+            check(abs(smp.mean() - mu) < 6 * sd / np.sqrt(20000), "sample mean %r vs %r" % (smp.mean(), mu))
             # all ranks hold identical global numbers
             t = torch.tensor([up.n_ess, up.normalization_record[-1]], dtype=torch.float64, device='cuda')
             g = [torch.empty_like(t) for _ in range(world)]
