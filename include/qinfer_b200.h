@@ -371,11 +371,22 @@ size_t qb_lw_binned_workspace_bytes(int64_t n_old, int64_t n_new);
  * separately: the shard masses of pass 1 decide how many offspring n_new this slab produces. */
 int qb_lw_binned_sums(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old, int32_t d,
                       double* d_moments_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
-int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, void* d_ws, size_t ws_bytes,
-                       void* stream);
+/* How pass 2 obtains the multinomial counts: QB_COUNT_HISTOGRAM locates n_new Philox uniforms (elements 0..n_new-1 of
+ * (seed_u, off_u)) in the bin-level CDF held in shared memory; QB_COUNT_TREE splits n_new down a binary tree over the
+ * bins with one exact Binomial variate per node (inversion / BTPE, Philox counters off_u + 32 k of node k) — <= 2T
+ * variates whatever n_new.  Same law (Multinomial(n_new; bin masses)); both are pure functions of (weights, seed,
+ * offset).  QB_COUNT_AUTO (default of the Python host): the histogram while its tables fit in shared memory
+ * (n_old <= 3.4e7), the tree beyond. */
+#define QB_COUNT_AUTO 0
+#define QB_COUNT_HISTOGRAM 1
+#define QB_COUNT_TREE 2
+int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, int32_t mode, void* d_ws,
+                       size_t ws_bytes, void* stream);
+/* The tree's sampler on its own (tests): d_out[i] ~ Binomial(n, p), i < count, from counters off + 32 i of stream seed. */
+int qb_binomial_sample(int64_t n, double p, int64_t count, uint64_t seed, uint64_t off, int64_t* d_out, void* stream);
 int qb_lw_binned_prepare(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old, int32_t d,
-                         int64_t n_new, uint64_t seed_u, uint64_t off_u, double* d_moments_out, double* h_mirror,
-                         double tag, void* d_ws, size_t ws_bytes, void* stream);
+                         int64_t n_new, uint64_t seed_u, uint64_t off_u, int32_t count_mode, double* d_moments_out,
+                         double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream);
 int qb_lw_binned_move(const qb_model* model, const double* d_x_old, const double* d_w, const double* d_stats,
                       int64_t n_old, int32_t d, const double* h_mean, const double* h_S, double a,
                       uint64_t seed_v, uint64_t off_v, uint64_t seed_n, uint64_t off_n, int64_t n_new,
@@ -399,8 +410,8 @@ int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, int64_t n_o
  * The host checks the flags and raises the reference's warnings / ResamplerError after the fact. */
 int qb_lw_binned_resample(const qb_model* model, const double* d_x, const double* d_w, const double* d_stats,
                           int64_t n_old, int32_t d, int64_t n_new, double a, double h, double zero_cov_comp,
-                          uint64_t seed, uint64_t off_u, uint64_t off_v, uint64_t seed_n, uint64_t off_n,
-                          double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
+                          uint64_t seed, uint64_t off_u, int32_t count_mode, uint64_t off_v, uint64_t seed_n,
+                          uint64_t off_n, double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
                           int32_t postselect, int32_t retry_rounds, int32_t own_mean, int64_t* d_list,
                           int32_t* d_parents, double* d_moments_out, double* h_mirror, double tag, void* d_ws,
                           size_t ws_bytes, void* stream);

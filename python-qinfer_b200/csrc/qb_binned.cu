@@ -51,8 +51,8 @@ constexpr int BIN_MAX_GRID = 4096;                // partials rows reserved in t
 constexpr int MOM_MAX = 1 + 4 + 10;               // packed moment outputs for d <= 4
 
 struct BinLayout {
-    size_t bounds, counts, offs, segs, partials, total;
-    int64_t T, max_segs;
+    size_t bounds, counts, offs, segs, partials, heap, total;
+    int64_t T, max_segs, P;
 };
 
 static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
@@ -65,7 +65,10 @@ static BinLayout bin_layout(int64_t n_old, int64_t n_new) {
     L.counts = L.bounds + align256(static_cast<size_t>(L.T + 1) * 8);
     L.offs = L.counts + align256(static_cast<size_t>(L.T + 2) * 4);
     L.partials = L.offs + align256(static_cast<size_t>(L.T + 1) * 8);
-    L.segs = L.partials + align256(static_cast<size_t>(BIN_MAX_GRID) * MOM_MAX * 8);  // last: only its size depends on n_new
+    L.P = 1;
+    while (L.P < L.T) L.P *= 2;                                  // leaves of the binomial-splitting tree over the bins
+    L.heap = L.partials + align256(static_cast<size_t>(BIN_MAX_GRID) * MOM_MAX * 8);
+    L.segs = L.heap + align256(static_cast<size_t>(2 * L.P) * 4);  // last: only its size depends on n_new
     L.total = L.segs + align256(static_cast<size_t>(L.max_segs) * 8);
     return L;
 }
@@ -702,6 +705,236 @@ __global__ void __launch_bounds__(COUNT_THREADS) binned_count_kernel(const __gri
     }
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// pass 2, default: the same multinomial counts WITHOUT touching n_new uniforms.  A multinomial over the bins factorises
+// over a binary tree: the root holds n_new; a node holding c offspring hands Binomial(c, mass(left) / mass(node)) to
+// its left child and the rest to the right one; the leaves (bins) then hold exactly Multinomial(n_new; bin masses).
+// One binomial variate per tree node (<= 2T of them) replaces n_new uniform draws + searches + atomics: 60 us -> ~15 us
+// at n = 1e7 and 1.3 ms -> ~0.05 ms at n = 1e8, where the histogram's tables no longer fit in shared memory.
+// The binomial sampler is exact (inversion for small means, BTPE rejection [Kachitvichyanukul & Schmeiser 1988] with
+// its Stirling squeeze otherwise — the algorithm NumPy's legacy generator uses), driven by counter-based Philox
+// uniforms: node k consumes counters off_u + 32 k .. of stream seed_u, so the counts are a pure function of
+// (weights, seed, offset).  One CTA walks the tree level by level.
+// -------------------------------------------------------------------------------------------------------------
+struct NodeRng {
+    uint64_t seed, ctr;
+    double spare;
+    int have;
+    __device__ __forceinline__ double next() {
+        if (have) {
+            have = 0;
+            return spare;
+        }
+        double a, b;
+        philox_uniform_pair(seed, ctr++, a, b);
+        spare = b;
+        have = 1;
+        return a;
+    }
+};
+
+__device__ long long binomial_inversion(NodeRng& g, long long n, double p) {   // p <= 1/2, n p < 30
+    const double q = 1.0 - p, qn = exp(static_cast<double>(n) * log(q)), np = static_cast<double>(n) * p;
+    const double bd = np + 10.0 * sqrt(np * q + 1.0);
+    const long long bound = (static_cast<double>(n) < bd) ? n : static_cast<long long>(bd);
+    long long X = 0;
+    double px = qn, U = g.next();
+    while (U > px) {
+        ++X;
+        if (X > bound) {
+            X = 0;
+            px = qn;
+            U = g.next();
+        } else {
+            U -= px;
+            px = ((static_cast<double>(n - X + 1)) * p * px) / (static_cast<double>(X) * q);
+        }
+    }
+    return X;
+}
+
+__device__ __forceinline__ double stirling_tail(double v, double v2) {
+    return (13680.0 - (462.0 - (132.0 - (99.0 - 140.0 / v2) / v2) / v2) / v2) / v / 166320.0;
+}
+
+__device__ long long binomial_btpe(NodeRng& g, long long n_, double p) {        // p <= 1/2, n p >= 30
+    const double n = static_cast<double>(n_);
+    const double r = p, q = 1.0 - r, fm = n * r + r;
+    const double m = floor(fm);
+    const double p1 = floor(2.195 * sqrt(n * r * q) - 4.6 * q) + 0.5;
+    const double xm = m + 0.5, xl = xm - p1, xr = xm + p1;
+    const double c = 0.134 + 20.5 / (15.3 + m);
+    double a = (fm - xl) / (fm - xl * r);
+    const double laml = a * (1.0 + a / 2.0);
+    a = (xr - fm) / (xr * q);
+    const double lamr = a * (1.0 + a / 2.0);
+    const double p2 = p1 * (1.0 + 2.0 * c), p3 = p2 + c / laml, p4 = p3 + c / lamr;
+    const double nrq = n * r * q;
+    double y;
+    for (;;) {
+        const double u = g.next() * p4;
+        double v = g.next();
+        if (u <= p1) {                                   // triangular centre: accept at once
+            y = floor(xm - p1 * v + u);
+            break;
+        }
+        if (u <= p2) {                                   // parallelograms
+            const double x = xl + (u - p1) / c;
+            v = v * c + 1.0 - fabs(m - x + 0.5) / p1;
+            if (v > 1.0) continue;
+            y = floor(x);
+        } else if (u <= p3) {                            // left exponential tail
+            y = floor(xl + log(v) / laml);
+            if (y < 0.0 || v == 0.0) continue;
+            v = v * (u - p2) * laml;
+        } else {                                         // right exponential tail
+            y = floor(xr - log(v) / lamr);
+            if (y > n || v == 0.0) continue;
+            v = v * (u - p3) * lamr;
+        }
+        const double k = fabs(y - m);
+        if (!(k > 20.0 && k < nrq / 2.0 - 1.0)) {        // explicit evaluation of f(y) / f(m)
+            const double s = r / q, aa = s * (n + 1.0);
+            double F = 1.0;
+            if (m < y) {
+                for (double i = m + 1.0; i <= y; i += 1.0) F *= (aa / i - s);
+            } else if (m > y) {
+                for (double i = y + 1.0; i <= m; i += 1.0) F /= (aa / i - s);
+            }
+            if (v > F) continue;
+            break;
+        }
+        // squeezing with the Stirling series
+        const double rho = (k / nrq) * ((k * (k / 3.0 + 0.625) + 0.16666666666666666) / nrq + 0.5);
+        const double t = -k * k / (2.0 * nrq);
+        const double A = log(v);
+        if (A < t - rho) break;
+        if (A > t + rho) continue;
+        const double x1 = y + 1.0, f1 = m + 1.0, z = n + 1.0 - m, w = n - y + 1.0;
+        const double bound = xm * log(f1 / x1) + (n - m + 0.5) * log(z / w) + (y - m) * log(w * r / (x1 * q)) +
+                             stirling_tail(f1, f1 * f1) + stirling_tail(z, z * z) + stirling_tail(x1, x1 * x1) +
+                             stirling_tail(w, w * w);
+        if (A > bound) continue;
+        break;
+    }
+    return static_cast<long long>(y);
+}
+
+// X ~ Binomial(n, p), exact
+__device__ long long binomial_sample(uint64_t seed, uint64_t ctr, long long n, double p) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    NodeRng g = {seed, ctr, 0.0, 0};
+    const double r = (p <= 0.5) ? p : 1.0 - p;
+    const long long y = (static_cast<double>(n) * r < 30.0) ? binomial_inversion(g, n, r) : binomial_btpe(g, n, r);
+    return (p <= 0.5) ? y : n - y;
+}
+
+__global__ void __launch_bounds__(256) binomial_test_kernel(uint64_t seed, uint64_t off, long long n, double p,
+                                                            int64_t count, long long* __restrict__ out) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+        out[i] = binomial_sample(seed, off + 32ull * static_cast<uint64_t>(i), n, p);
+}
+
+struct TreeParams {
+    BinCountParams c;
+    unsigned int* heap;   // [2P]: node k (1-based, children 2k and 2k+1) holds its offspring count; leaves at P + t
+    int32_t P, levels;
+};
+
+// one node of the splitting tree: hand Binomial(c, mass(left) / mass(node)) to the left child
+__device__ __forceinline__ void split_node(const TreeParams& tp, int k, int lo, int span) {
+    const BinCountParams& p = tp.c;
+    const int T = p.T;
+    const long long c = static_cast<long long>(tp.heap[k]);
+    const int mid = lo + span / 2, hi = lo + span;
+    long long left = 0;
+    if (c > 0) {
+        if (mid >= T) {
+            left = c;                                   // the right half lies beyond the last bin
+        } else {
+            const double b_lo = p.bounds[lo], b_mid = p.bounds[mid], b_hi = p.bounds[(hi < T) ? hi : T];
+            const double mass = b_hi - b_lo;
+            const double ql = (mass > 0.0) ? (b_mid - b_lo) / mass : 1.0;
+            left = binomial_sample(p.seed_u, p.off_u + 32ull * static_cast<uint64_t>(k), c,
+                                   (ql < 0.0) ? 0.0 : ((ql > 1.0) ? 1.0 : ql));
+        }
+    }
+    tp.heap[2 * k] = static_cast<unsigned int>(left);
+    tp.heap[2 * k + 1] = static_cast<unsigned int>(c - left);
+}
+
+// leaf counts -> output offsets; every bin's output range cut into segments of <= SEG slots (one CTA)
+__device__ void tree_leaf_scan(const TreeParams& tp, long long* scan_a, long long* scan_b) {
+    const BinCountParams& p = tp.c;
+    const int T = p.T, tid = threadIdx.x;
+    const unsigned int* leaf = tp.heap + tp.P;
+    const int per = (T + COUNT_THREADS - 1) / COUNT_THREADS;
+    const int lo = tid * per, hi = (lo + per < T) ? lo + per : T;
+    long long m_sum = 0, s_sum = 0;
+    for (int i = lo; i < hi; ++i) {
+        const long long m = static_cast<long long>(__ldcg(leaf + i));
+        m_sum += m;
+        s_sum += (m + SEG - 1) / SEG;
+    }
+    long long m_tot, s_tot;
+    long long m_run = block_excl_scan<long long, COUNT_THREADS / 32>(m_sum, scan_a, m_tot);
+    long long s_run = block_excl_scan<long long, COUNT_THREADS / 32>(s_sum, scan_b, s_tot);
+    for (int i = lo; i < hi; ++i) {
+        const long long m = static_cast<long long>(__ldcg(leaf + i));
+        p.counts[i] = static_cast<unsigned int>(m);
+        p.offs[i] = m_run;
+        m_run += m;
+        const long long ns = (m + SEG - 1) / SEG;
+        for (long long c = 0; c < ns; ++c)
+            if (s_run + c < p.max_segs) p.segs[s_run + c] = make_uint2(static_cast<unsigned int>(i), static_cast<unsigned int>(c));
+        s_run += ns;
+    }
+    if (tid == 0) {
+        p.offs[T] = m_tot;
+        *p.nseg = static_cast<unsigned int>(s_tot < p.max_segs ? s_tot : p.max_segs);
+        unsigned long long* ctr = reinterpret_cast<unsigned long long*>(p.ticket - 1 + 16);
+        ctr[0] = ctr[1] = ctr[2] = ctr[3] = 0ull;
+    }
+}
+
+// levels [0, top) of the tree by one CTA (the upper levels have few nodes: their cost is the dependency chain); when
+// that is the whole tree, the leaf scan follows in the same launch
+__global__ void __launch_bounds__(COUNT_THREADS) binned_tree_count_kernel(const __grid_constant__ TreeParams tp, int top) {
+    __shared__ long long scan_a[COUNT_THREADS / 32], scan_b[COUNT_THREADS / 32];
+    const int P = tp.P, tid = threadIdx.x;
+    if (tid == 0) tp.heap[1] = static_cast<unsigned int>(tp.c.n_new);
+    __syncthreads();
+    for (int lvl = 0; lvl < top; ++lvl) {
+        const int nodes = 1 << lvl;
+        const int span = P >> lvl;                              // leaves under a node of this level
+        for (int i = tid; i < nodes; i += COUNT_THREADS) split_node(tp, nodes + i, i * span, span);
+        __syncthreads();
+    }
+    if (top == tp.levels) tree_leaf_scan(tp, scan_a, scan_b);
+}
+
+// levels [top, levels): one CTA per node of level `top`, each finishing its own subtree
+__global__ void __launch_bounds__(64) binned_subtree_kernel(const __grid_constant__ TreeParams tp, int top) {
+    const int P = tp.P;
+    const int root = blockIdx.x;                                // index within level `top`
+    for (int lvl = top; lvl < tp.levels; ++lvl) {
+        const int rel = 1 << (lvl - top);                       // nodes of this level under my root
+        const int span = P >> lvl;
+        for (int j = threadIdx.x; j < rel; j += blockDim.x) {
+            const int i = root * rel + j;
+            split_node(tp, (1 << lvl) + i, i * span, span);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(COUNT_THREADS) binned_leaf_scan_kernel(const __grid_constant__ TreeParams tp) {
+    __shared__ long long scan_a[COUNT_THREADS / 32], scan_b[COUNT_THREADS / 32];
+    tree_leaf_scan(tp, scan_a, scan_b);
+}
+
 // =============================================================================================================
 // pass 3: per segment, bin-local CDF in shared memory, draw + gather + shrink + perturb + validity + weights
 // =============================================================================================================
@@ -1118,8 +1351,17 @@ extern "C" int qb_lw_binned_sums(const double* d_x, const double* d_w, const dou
                        0.0, 0.0);
 }
 
-extern "C" int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, void* d_ws,
-                                  size_t ws_bytes, void* stream) {
+extern "C" int qb_binomial_sample(int64_t n, double p, int64_t count, uint64_t seed, uint64_t off, int64_t* d_out,
+                                  void* stream) {
+    QB_REQUIRE(d_out && count >= 1 && n >= 0, QB_ERR_INVALID_ARGUMENT, "qb_binomial_sample: bad arguments");
+    binomial_test_kernel<<<bin_grid((count + 255) / 256, 8), 256, 0, as_stream(stream)>>>(
+        seed, off, static_cast<long long>(n), p, count, reinterpret_cast<long long*>(d_out));
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
+extern "C" int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, int32_t mode,
+                                  void* d_ws, size_t ws_bytes, void* stream) {
     QB_REQUIRE(d_ws, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_count: NULL workspace");
     QB_REQUIRE(n_old >= 1 && n_new >= 1 && n_old < (1LL << 31) && n_new < (1LL << 31), QB_ERR_INVALID_ARGUMENT,
                "qb_lw_binned_count: particle counts must lie in [1, 2^31)");
@@ -1140,7 +1382,31 @@ extern "C" int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u,
     cp.max_segs = static_cast<int32_t>(L.max_segs);
     cp.seed_u = seed_u;
     cp.off_u = off_u;
+    QB_REQUIRE(mode == QB_COUNT_AUTO || mode == QB_COUNT_TREE || mode == QB_COUNT_HISTOGRAM, QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_binned_count: unknown mode %d", mode);
     const size_t smem = static_cast<size_t>(L.T + 2) * 8 + static_cast<size_t>((L.T + 2) & ~1LL) * 4 + 16;
+    // measured (B200): while the histogram's tables fit in shared memory it costs ~6 ns per 1000 draws (61 us at
+    // n_new = 1e7) and the tree ~10 us per level (143 us for the 13 levels of 1e7 / 2048 bins); beyond that (n > 3.4e7)
+    // the histogram falls back to global tables and atomics (1.35 ms at 1e8) and the tree wins
+    if (mode == QB_COUNT_AUTO) mode = (smem <= 200 * 1024 && n_new >= 4 * L.T) ? QB_COUNT_HISTOGRAM : QB_COUNT_TREE;
+    if (mode == QB_COUNT_TREE) {
+        TreeParams tp;
+        tp.c = cp;
+        tp.heap = reinterpret_cast<unsigned int*>(ws + L.heap);
+        tp.P = static_cast<int32_t>(L.P);
+        tp.levels = 0;
+        while ((1LL << tp.levels) < L.P) ++tp.levels;
+        const int top = (tp.levels <= 11) ? tp.levels : 10;
+        binned_tree_count_kernel<<<1, COUNT_THREADS, 0, st>>>(tp, top);
+        QB_CUDA_CHECK(cudaGetLastError());
+        if (top < tp.levels) {
+            binned_subtree_kernel<<<1 << top, 64, 0, st>>>(tp, top);
+            QB_CUDA_CHECK(cudaGetLastError());
+            binned_leaf_scan_kernel<<<1, COUNT_THREADS, 0, st>>>(tp);
+            QB_CUDA_CHECK(cudaGetLastError());
+        }
+        return QB_OK;
+    }
     const int64_t npairs = (n_new + 1) / 2;
     if (smem <= 200 * 1024) {
         static bool attr_set = false;
@@ -1159,15 +1425,16 @@ extern "C" int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u,
 }
 
 extern "C" int qb_lw_binned_prepare(const double* d_x, const double* d_w, const double* d_stats, int64_t n_old,
-                                    int32_t d, int64_t n_new, uint64_t seed_u, uint64_t off_u, double* d_moments_out,
-                                    double* h_mirror, double tag, void* d_ws, size_t ws_bytes, void* stream) {
+                                    int32_t d, int64_t n_new, uint64_t seed_u, uint64_t off_u, int32_t count_mode,
+                                    double* d_moments_out, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                                    void* stream) {
     QB_REQUIRE(n_new >= 1 && n_new < (1LL << 31), QB_ERR_INVALID_ARGUMENT,
                "qb_lw_binned_prepare: n_new must lie in [1, 2^31)");
     QB_REQUIRE(n_old >= 1 && ws_bytes >= bin_layout(n_old, n_new).total, QB_ERR_WORKSPACE,
                "qb_lw_binned_prepare: workspace too small");
     int rc = qb_lw_binned_sums(d_x, d_w, d_stats, n_old, d, d_moments_out, h_mirror, tag, d_ws, ws_bytes, stream);
     if (rc != QB_OK) return rc;
-    return qb_lw_binned_count(n_old, n_new, seed_u, off_u, d_ws, ws_bytes, stream);
+    return qb_lw_binned_count(n_old, n_new, seed_u, off_u, count_mode, d_ws, ws_bytes, stream);
 }
 
 static int fill_move(BinMoveParams& q, const qb_model* model, const double* d_x_old, int64_t n_old, int32_t d,
@@ -1321,8 +1588,8 @@ extern "C" int qb_lw_binned_retry(const qb_model* model, const double* d_x_old, 
 // device), pass 2 (counts), pass 3 (move, reading the constants from the workspace) and the first retry launch.
 extern "C" int qb_lw_binned_resample(const qb_model* model, const double* d_x, const double* d_w, const double* d_stats,
                                      int64_t n_old, int32_t d, int64_t n_new, double a, double h, double zero_cov_comp,
-                                     uint64_t seed, uint64_t off_u, uint64_t off_v, uint64_t seed_n, uint64_t off_n,
-                                     double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
+                                     uint64_t seed, uint64_t off_u, int32_t count_mode, uint64_t off_v, uint64_t seed_n,
+                                     uint64_t off_n, double* d_x_new, double* d_w_new, int64_t n_global, double* d_stats_new,
                                      int32_t postselect, int32_t retry_rounds, int32_t own_mean, int64_t* d_list,
                                      int32_t* d_parents, double* d_moments_out, double* h_mirror, double tag,
                                      void* d_ws, size_t ws_bytes, void* stream) {
@@ -1338,7 +1605,7 @@ extern "C" int qb_lw_binned_resample(const qb_model* model, const double* d_x, c
     rc = launch_sums(d_x, d_w, d_stats, n_old, d, d_moments_out, h_mirror, tag, d_ws, ws_bytes, stream, true, a, h,
                      zero_cov_comp);
     if (rc != QB_OK) return rc;
-    rc = qb_lw_binned_count(n_old, n_new, seed, off_u, d_ws, ws_bytes, stream);
+    rc = qb_lw_binned_count(n_old, n_new, seed, off_u, count_mode, d_ws, ws_bytes, stream);
     if (rc != QB_OK) return rc;
     return qb_lw_binned_move(model, d_x, d_w, d_stats, n_old, d, nullptr, nullptr, a, seed, off_v, seed_n, off_n, n_new,
                              d_x_new, n_new, nullptr, d_w_new, n_global, d_stats_new, postselect, retry_rounds, own_mean,

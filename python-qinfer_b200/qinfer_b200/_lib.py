@@ -17,6 +17,7 @@ QB_STAT_COUNT = 16
 QB_MODEL_PRECESSION, QB_MODEL_RB, QB_MODEL_TOMOGRAPHY, QB_MODEL_COIN = 1, 2, 3, 4
 QB_SCAN_FAST, QB_SCAN_EXACT, QB_SCAN_FAST_GUIDE, QB_SCAN_FAST_GUIDE_SCALED = 0, 1, 2, 3
 QB_WALK_ADD, QB_WALK_FIXED, QB_WALK_LEARNED = 0, 1, 2
+QB_COUNT_AUTO, QB_COUNT_HISTOGRAM, QB_COUNT_TREE = 0, 1, 2
 
 _LIB_PATH = os.environ.get("QB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)),
                                                          "libqinfer_b200.so")
@@ -106,8 +107,10 @@ SIGNATURES = {
                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _P, _I64, _P, _P, _P, _P, _P]),
     "qb_lw_binned_workspace_bytes": (_SZ, [_I64, _I64]),
     "qb_lw_binned_sums": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _F64, _P, _SZ, _P]),
-    "qb_lw_binned_count": (ctypes.c_int, [_I64, _I64, _U64, _U64, _P, _SZ, _P]),
-    "qb_lw_binned_prepare": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I64, _U64, _U64, _P, _P, _F64, _P, _SZ, _P]),
+    "qb_lw_binned_count": (ctypes.c_int, [_I64, _I64, _U64, _U64, _I32, _P, _SZ, _P]),
+    "qb_binomial_sample": (ctypes.c_int, [_I64, _F64, _I64, _U64, _U64, _P, _P]),
+    "qb_lw_binned_prepare": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I64, _U64, _U64, _I32, _P, _P, _F64, _P, _SZ,
+                                            _P]),
     "qb_lw_binned_move": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _P, _P, _I64, _I32, ctypes.POINTER(_F64),
                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _U64, _I64, _P, _I64, _P, _P,
                                          _I64, _P, _I32, _I32, _I32, _P, _P, _P, _P, _F64, _P, _SZ, _P]),
@@ -115,8 +118,8 @@ SIGNATURES = {
                                           ctypes.POINTER(_F64), _F64, _U64, _U64, _U64, _I32, _I32, _U64, _I64, _P,
                                           _I64, _P, _P, _P, _P, _F64, _P, _SZ, _P]),
     "qb_lw_binned_resample": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _P, _P, _I64, _I32, _I64, _F64, _F64, _F64,
-                                             _U64, _U64, _U64, _U64, _U64, _P, _P, _I64, _P, _I32, _I32, _I32, _P, _P,
-                                             _P, _P, _F64, _P, _SZ, _P]),
+                                             _U64, _U64, _I32, _U64, _U64, _U64, _P, _P, _I64, _P, _I32, _I32, _I32,
+                                             _P, _P, _P, _P, _F64, _P, _SZ, _P]),
     "qb_mailbox_create": (ctypes.c_int, [_I32, ctypes.POINTER(_P)]),
     "qb_mailbox_destroy": (ctypes.c_int, [_P]),
     "qb_ipc_get_handle": (ctypes.c_int, [_P, ctypes.c_char_p]),

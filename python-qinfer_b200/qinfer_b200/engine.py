@@ -90,6 +90,7 @@ class DeviceCloud(object):
         self._bin_list = None
         self._bin_mirror = None
         self._bin_tag = 0
+        self.count_mode = int(os.environ.get('QB_BINNED_COUNT', _lib.QB_COUNT_AUTO))   # pass 2: auto | histogram | binomial tree
         # noise source of the f4 decorators (PoisonedModel, random walks): see ``normals``
         self.noise_rng, self.noise_seed, self.noise_offset = 'numpy', 0x6E6F697365, 0
         # one control block per destination slot: the constant fields are written once
@@ -514,7 +515,7 @@ class DeviceCloud(object):
         self._bin_tag += 1
         check(self.lib.qb_lw_binned_prepare(self.x.data_ptr(), self.w.data_ptr(), self.stats.data_ptr(), self.n,
                                             self.d, int(n_new), int(seed_u) & _U64_MASK, int(off_u) & _U64_MASK,
-                                            self.moments_out.data_ptr(), self._bin_mirror.data_ptr(),
+                                            self.count_mode, self.moments_out.data_ptr(), self._bin_mirror.data_ptr(),
                                             float(self._bin_tag), self._bin_ws.data_ptr(), self._bin_ws.numel() * 8,
                                             _stream()))
         self.launches += 2
@@ -534,7 +535,7 @@ class DeviceCloud(object):
         check(self.lib.qb_lw_binned_resample(
             self.lib_model, self.x.data_ptr(), self.w.data_ptr(), self.stats.data_ptr(), self.n, self.d, n_new,
             float(a), float(h), float(zero_cov_comp), int(seed) & _U64_MASK, int(off_u) & _U64_MASK,
-            int(off_v) & _U64_MASK, int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, self.x_alt.data_ptr(),
+            self.count_mode, int(off_v) & _U64_MASK, int(seed_n) & _U64_MASK, int(off_n) & _U64_MASK, self.x_alt.data_ptr(),
             self.w_alt.data_ptr() if fuse_weights else None, n_new if n_global is None else int(n_global),
             self.stats_alt.data_ptr() if fuse_weights else None, 1 if postselect else 0, rounds,
             1 if own_mean else 0, self._bin_list.data_ptr(), self._bin_parents.data_ptr(),
@@ -563,7 +564,7 @@ class DeviceCloud(object):
         if self._bin_cap[1] < n_new:
             raise _lib.QbError("binned_count: call binned_reserve(n_new) before binned_sums")
         check(self.lib.qb_lw_binned_count(self.n, int(n_new), int(seed_u) & _U64_MASK, int(off_u) & _U64_MASK,
-                                          _ptr(self._bin_ws), self._bin_ws.numel() * 8, _stream()))
+                                          self.count_mode, _ptr(self._bin_ws), self._bin_ws.numel() * 8, _stream()))
         self.launches += 1
 
     def _spin(self, index, tag, what, timeout_s=120.0):

@@ -45,6 +45,8 @@ def _align256(b):
 
 def _read_ws(cloud):
     """bounds (T+1), counts (T), offs (T+1), nseg from the binned workspace (layout of bin_layout(), qb_binned.cu)."""
+    import torch
+    torch.cuda.synchronize()
     T = (cloud.n + BIN - 1) // BIN
     raw = cloud._bin_ws.cpu().numpy().view(np.uint8)
     o_bounds = 512
@@ -95,6 +97,7 @@ def test_binned_passes_are_exact(qb, oracle, kind, n, n_new, wkind):
     up = qb.SMCUpdater(model, n, cases.FixedPrior(x), resampler=res)
     up.particle_weights = w
     cloud = up._cloud
+    cloud.count_mode = qb._lib.QB_COUNT_HISTOGRAM          # (the counts are then checked against the uniforms themselves)
     off_u, off_v, off_n = 3, 3 + (n_new + 1) // 2, 3 + 2 * ((n_new + 1) // 2)
 
     # ---- pass 1 + 2 -------------------------------------------------------------------------------------------
@@ -372,3 +375,79 @@ def test_binned_retry_own_parent_variant(qb, oracle):
     slots = np.nonzero(bad)[0]
     want = a * x[js_out.cpu().numpy()[slots]] + (1 - a) * mean + (S[0, 0] * e2[slots])[:, None]
     assert np.array_equal(cloud.x_alt.cpu().numpy()[slots], want)
+
+
+@pytest.mark.parametrize("n,p", [(5, 0.3), (40, 0.5), (1000, 0.01), (1000, 0.2), (10 ** 7, 0.5), (10 ** 7, 1e-6),
+                                 (10 ** 7, 1.0 - 3e-6), (12345678, 0.0372), (2 ** 31 - 1, 0.37), (3000, 0.9871)])
+def test_device_binomial_sampler_is_exact(qb, n, p):
+    """The sampler behind the binomial-tree counts (inversion below a mean of 30, BTPE above) against
+    scipy.stats.binom: Pearson chi-square of 4e5 variates over the outcomes with an expected count >= 10 (tails
+    pooled), within 5 sigma of its degrees of freedom; mean and variance within 5 standard errors."""
+    import scipy.stats
+    import torch
+    from qinfer_b200.engine import _ptr, _stream
+    lib = qb._lib.load()
+    count = 400000
+    out = torch.empty((count,), dtype=torch.int64, device='cuda')
+    qb._lib.check(lib.qb_binomial_sample(n, p, count, 77, 1000, _ptr(out), _stream()))
+    v = out.cpu().numpy()
+    assert v.min() >= 0 and v.max() <= n
+    mean, var = n * p, n * p * (1 - p)
+    assert abs(v.mean() - mean) < 5 * np.sqrt(var / count) + 1e-12
+    assert abs(v.var() - var) < 5 * var * np.sqrt(2.0 / count + (1 / max(var, 1e-300) - 6 / n) / count) + 1e-12
+    lo, hi = int(max(0, np.floor(mean - 8 * np.sqrt(var) - 10))), int(min(n, np.ceil(mean + 8 * np.sqrt(var) + 10)))
+    ks = np.arange(lo, hi + 1)
+    expect = count * scipy.stats.binom.pmf(ks, n, p)
+    got = np.bincount(np.clip(v - lo, 0, hi - lo), minlength=ks.size).astype(float)
+    big = expect >= 10
+    chi2 = float(np.sum((got[big] - expect[big]) ** 2 / expect[big]))
+    dof = int(big.sum())
+    rest_e, rest_g = count - expect[big].sum(), count - got[big].sum()
+    if rest_e > 10:
+        chi2 += (rest_g - rest_e) ** 2 / rest_e
+        dof += 1
+    assert abs(chi2 - (dof - 1)) < 5 * np.sqrt(2 * dof) + 5, (chi2, dof)
+
+
+@pytest.mark.parametrize("wkind,n,n_new", [("rand", 6 * BIN + 5, 3 * 10 ** 6), ("sorted", 100003, 250001),
+                                           ("zero_bins", 6 * BIN + 5, 40000), ("rand", 10 ** 7, 10 ** 7),
+                                           ("rand", 9, 1000), ("rand", 2 ** 23 + 77, 2 ** 23 + 77)])
+def test_tree_counts_are_multinomial_in_the_bin_masses(qb, wkind, n, n_new):
+    """QB_COUNT_TREE: the bin counts sum to n_new exactly, bins of zero mass get nothing, and over 12 independent
+    seeds the counts are consistent with Multinomial(n_new; bin masses) (pooled Pearson chi-square, 5 sigma)."""
+    rs = np.random.RandomState(2)
+    x = rs.random_sample((n, 1))
+    w = _weights(wkind, n, rs)
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x))
+    up.particle_weights = w
+    cloud = up._cloud
+    cloud.count_mode = qb._lib.QB_COUNT_TREE
+    T = (n + BIN - 1) // BIN
+    pad = np.zeros(T * BIN)
+    pad[:n] = w
+    mass = pad.reshape(T, BIN).sum(axis=1)
+    chi2 = dof = 0.0
+    for seed in range(12):
+        tag = cloud.binned_prepare(n_new, 1000 + seed, 5 * seed)
+        cloud.binned_moments_wait(tag)
+        import torch
+        torch.cuda.synchronize()
+        _, bounds, counts, offs, nseg = _read_ws(cloud)
+        assert counts.sum() == n_new and offs[T] == n_new
+        assert np.array_equal(offs, np.concatenate([[0], np.cumsum(counts)]))
+        assert np.all(counts[mass == 0] == 0)
+        assert nseg == int(np.sum((counts + SEG - 1) // SEG))
+        e = n_new * mass
+        big = e >= 10
+        if big.sum() > 1:
+            chi2 += float(np.sum((counts[big] - e[big]) ** 2 / e[big]))
+            dof += big.sum() - (1 if big.all() else 0)
+    if dof > 0:
+        assert abs(chi2 - dof) < 5 * np.sqrt(2 * dof) + 5, (chi2, dof)
+    # different seeds give different counts, the same seed the same
+    tag = cloud.binned_prepare(n_new, 1000, 0)
+    cloud.binned_moments_wait(tag)
+    c0 = _read_ws(cloud)[2]
+    tag = cloud.binned_prepare(n_new, 1000, 0)
+    cloud.binned_moments_wait(tag)
+    assert np.array_equal(_read_ws(cloud)[2], c0)
