@@ -1502,7 +1502,7 @@ typedef void (*bin_kernel_t)(const BinMoveParams);
 static int launch_retry(const BinMoveParams& q, int d, cudaStream_t st) {
     static const bin_kernel_t kernels[4] = {binned_retry_kernel<1>, binned_retry_kernel<2>, binned_retry_kernel<3>,
                                             binned_retry_kernel<4>};
-    const int grid = bin_grid(1 << 20, 4);   // the list length is only known on the device: grid-stride
+    const int grid = bin_grid(1 << 20, 1);   // the list length is only known on the device: grid-stride (one CTA per SM)
     kernels[d - 1]<<<grid, 128, 0, st>>>(q);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
