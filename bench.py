@@ -428,7 +428,9 @@ def process_warmup(be, prior):
     # a small cloud in both modes (module loading), then a throw-away cloud of the workload's size in the timed mode:
     # the allocator, the pinned staging blocks and (sharded) NCCL's channels for these message sizes exist before
     # the timed updater is built
-    plan = [(nsmall, 'throughput')] + ([(nsmall, 'parity')] if be.world == 1 else []) + [(prior.shape[0], 'throughput')]
+    plan = [(nsmall, 'throughput')] + ([(nsmall, 'parity')] if be.world == 1 else []) + [(prior.shape[0], 'throughput')] \
+        + ([(prior.shape[0], 'parity')] if be.world == 1 else [])    # (the device MT19937 path's first call at a new size
+                                                                     #  costs ~0.1 s once per process)
     for nsz, mode in plan:
         small = be.new_updater(nsz, prior[:nsz], mode=mode, seed=5)
         if mode == 'parity':
