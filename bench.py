@@ -370,6 +370,13 @@ class CudaBackend(object):
                 wrap(up, "_liu_west_consts")
         return up
 
+    def parity_js(self, up):
+        """Global parent indices of the last parity-mode resample (this rank's slab of them when sharded)."""
+        js = getattr(up, "last_parity_js", None)
+        if js is None:
+            js = up._cloud._js
+        return None if js is None else js.cpu().numpy()
+
     def pinned(self, array):
         t = self.torch.empty(array.shape, dtype=self.torch.float64, pin_memory=True)
         t.numpy()[:] = array
@@ -576,6 +583,31 @@ def sharded_check(be, rank, world):
                          abs(count - int(one.resample_count)) <= 1)
         del one
     be.barrier()
+    # parity mode on the sharded cloud: legacy MT19937 stream + the exact scan chained across the slabs;
+    # the global resample indices must equal the single-GPU parity run's
+    if hasattr(be, "parity_js"):
+        np.random.seed(99)                                 # the same legacy state on every rank
+        up = be.new_updater(n_local, full[rank * n_local:(rank + 1) * n_local], mode='parity', lazy=False)
+        drive(up, ts, outcomes, 0, m)
+        js, count_p, mean_p = be.parity_js(up), int(up.resample_count), float(up.est_mean()[0])
+        be.close(up)
+        del up
+        if rank == 0:
+            np.random.seed(99)
+            one = be.new_updater(n_local * world, full, mode='parity', sharded=False, lazy=False)
+            drive(one, ts, outcomes, 0, m)
+            js1 = be.parity_js(one)[:n_local]
+            mean1 = float(one.est_mean()[0])
+            par = {"resample_count": [count_p, int(one.resample_count)],
+                   "last_resample_js_equal_frac": float(np.mean(js == js1)) if js is not None else None,
+                   "mean_rel_err": abs(mean_p - mean1) / abs(mean1)}
+            par["ok"] = bool(count_p == int(one.resample_count) and count_p > 0 and par["mean_rel_err"] < 1e-6 and
+                             par["last_resample_js_equal_frac"] is not None and
+                             par["last_resample_js_equal_frac"] >= 0.999)
+            out["parity_mode"] = par
+            out["ok"] = bool(out["ok"] and par["ok"])
+            del one
+        be.barrier()
     return out
 
 

@@ -251,6 +251,12 @@ size_t qb_cdf_workspace_bytes(int64_t n);
 /* d_cdf[i] = cumsum of normalised weights (resamplers.py:308). */
 int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode,
            void* d_ws, size_t ws_bytes, void* stream);
+/* QB_SCAN_EXACT continued across slabs (SURVEY §8e "Parity mode": the sequential-CDF chain crosses shards): the
+ * running sum starts at *d_carry_in (a DEVICE double: the last CDF entry of the slab before this one; 0 for the first
+ * slab) instead of at 0, so that the concatenation of the slabs' outputs is np.cumsum of the concatenated weights
+ * (resamplers.py:308) bit for bit.  Same workspace as qb_cdf. */
+int qb_cdf_chained(const double* d_w, const double* d_stats, int64_t n, double* d_cdf,
+                   const double* d_carry_in, void* d_ws, size_t ws_bytes, void* stream);
 /* Diagnostics (synchronises): *h_flag = 1 if the last QB_SCAN_EXACT call on this workspace met weights outside
  * the parallel replay's model (negative, NaN, inf) or timed out and re-did the scan with the sequential kernel. */
 int qb_cdf_exact_fallback_flag(const void* d_ws, int64_t n, int32_t* h_flag, void* stream);

@@ -227,11 +227,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) cdf_write_kernel(const double* _
 constexpr int SEQ_CHUNK = 2048;
 __global__ void __launch_bounds__(64) cdf_sequential_kernel(const double* __restrict__ w,
                                                             const double* __restrict__ stats, int64_t n,
-                                                            double* __restrict__ cdf) {
+                                                            double* __restrict__ cdf,
+                                                            const double* __restrict__ carry) {
     __shared__ double buf[3][SEQ_CHUNK];
     const double inv = stats[QB_STAT_INV_NORM];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double run = 0.0;
+    double run = carry ? *carry : 0.0;  // (chained scan: the running rounded sum of the slabs before this one)
     const int64_t nchunks = (n + SEQ_CHUNK - 1) / SEQ_CHUNK;
     for (int64_t c = 0; c < nchunks + 2; ++c) {
         if (wid == 1) {
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(64) cdf_sequential_kernel(const double* __rest
             const int64_t first = (c - 1) * SEQ_CHUNK;
             const int cnt = static_cast<int>((n - first < SEQ_CHUNK) ? (n - first) : SEQ_CHUNK);
             int j = 0;
-            if (c == 1) {  // cumsum's first element is w[0] itself
+            if (c == 1 && !carry) {  // cumsum's first element is w[0] itself
                 run = b[0];
                 j = 1;
             }
@@ -856,7 +857,7 @@ static int upload_consts(const double* h_mean, const double* h_S, double a, int 
 namespace qb {
 size_t exact_scan_workspace_bytes(int64_t n);  // qb_scan_exact.cu
 int launch_exact_scan(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, const double* tile_prefix,
-                      void* d_ws, cudaStream_t st);
+                      const double* d_carry, void* d_ws, cudaStream_t st);
 constexpr int64_t EXACT_PARALLEL_MIN = 1 << 15;  // below this the one-lane sequential replay is fast enough
 
 static size_t cdf_tiles_bytes(int64_t n) {
@@ -887,13 +888,13 @@ extern "C" int qb_cdf_exact_fallback_flag(const void* d_ws, int64_t n, int32_t* 
     return QB_OK;
 }
 
-extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode, void* d_ws,
-                      size_t ws_bytes, void* stream) {
+static int cdf_impl(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode,
+                    const double* d_carry, void* d_ws, size_t ws_bytes, void* stream) {
     QB_REQUIRE(d_w && d_stats && d_cdf && d_ws && n >= 1, QB_ERR_INVALID_ARGUMENT, "qb_cdf: bad arguments");
     QB_REQUIRE(ws_bytes >= qb_cdf_workspace_bytes(n), QB_ERR_WORKSPACE, "qb_cdf: workspace too small");
     cudaStream_t st = as_stream(stream);
     if (mode == QB_SCAN_EXACT && n < EXACT_PARALLEL_MIN) {
-        cdf_sequential_kernel<<<1, 64, 0, st>>>(d_w, d_stats, n, d_cdf);
+        cdf_sequential_kernel<<<1, 64, 0, st>>>(d_w, d_stats, n, d_cdf, d_carry);
         QB_CUDA_CHECK(cudaGetLastError());
         return QB_OK;
     }
@@ -909,7 +910,7 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
     QB_CUDA_CHECK(cudaGetLastError());
     if (mode == QB_SCAN_EXACT) {
         // the approximate tile prefix predicts the binade of every segment; the exact values come from the replay scan
-        return launch_exact_scan(d_w, d_stats, n, d_cdf, tiles,
+        return launch_exact_scan(d_w, d_stats, n, d_cdf, tiles, d_carry,
                                  reinterpret_cast<unsigned char*>(d_ws) + 256 + cdf_tiles_bytes(n), st);
     }
     GuideHdr* hdr = reinterpret_cast<GuideHdr*>(reinterpret_cast<unsigned char*>(d_ws) + guide_offset(n));
@@ -923,6 +924,17 @@ extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, doubl
     }
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
+}
+
+extern "C" int qb_cdf(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, int32_t mode, void* d_ws,
+                      size_t ws_bytes, void* stream) {
+    return cdf_impl(d_w, d_stats, n, d_cdf, mode, nullptr, d_ws, ws_bytes, stream);
+}
+
+extern "C" int qb_cdf_chained(const double* d_w, const double* d_stats, int64_t n, double* d_cdf,
+                              const double* d_carry_in, void* d_ws, size_t ws_bytes, void* stream) {
+    QB_REQUIRE(d_carry_in, QB_ERR_INVALID_ARGUMENT, "qb_cdf_chained: d_carry_in is NULL");
+    return cdf_impl(d_w, d_stats, n, d_cdf, QB_SCAN_EXACT, d_carry_in, d_ws, ws_bytes, stream);
 }
 
 extern "C" size_t qb_draw_workspace_bytes(int64_t n) {

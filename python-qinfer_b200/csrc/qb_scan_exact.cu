@@ -121,6 +121,7 @@ struct ExParams {
     const double* w;
     const double* stats;
     const double* tile_prefix;  // approximate exclusive prefix every SCAN tile (2048 weights), ntiles + 1 entries
+    const double* carry;        // NULL, or the exact running sum this scan continues from (a slab of a sharded cloud)
     double* cdf;
     ExDesc* desc;
     unsigned int* ticket;
@@ -256,8 +257,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_scan_kernel(const __grid_
     if (tid == 0) {
         const int64_t t0 = seg_first / 2048;
         const int64_t t1 = (seg_first + seg_cnt64 + 2047) / 2048;
-        const double lo = p.tile_prefix[t0] * (1.0 - 1e-11);
-        const double hi = p.tile_prefix[t1] * (1.0 + 1e-11);
+        const double base = p.carry ? *p.carry : 0.0;
+        const double lo = (base + p.tile_prefix[t0]) * (1.0 - 1e-11);
+        const double hi = (base + p.tile_prefix[t1]) * (1.0 + 1e-11);
         int mode = EX_HARD, e = 0;
         if (c > 0 && lo > 0.0 && hi < 1.0e300 && binade_of(lo) == binade_of(hi)) {
             mode = EX_PLAIN;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_scan_kernel(const __grid_
 
     // ---- B: look-back for the exact start value ----
     if (tid == 0) {
-        double v = 0.0;
+        double v = p.carry ? *p.carry : 0.0;
         if (c > 0) {
             int j = c - 1;
             // walk back to the nearest exact VALUE, skipping over PLAIN aggregates
@@ -437,12 +439,13 @@ __global__ void __launch_bounds__(EX_THREADS, 1) exact_scan_kernel(const __grid_
 
 // the sequential kernel, run only if the parallel one met a weight outside its model (negative, NaN, inf)
 __global__ void exact_scan_fallback_kernel(const double* __restrict__ w, const double* __restrict__ stats, int64_t n,
-                                           double* __restrict__ cdf, const int* __restrict__ fallback) {
+                                           double* __restrict__ cdf, const int* __restrict__ fallback,
+                                           const double* __restrict__ carry) {
     if (*fallback == 0 || threadIdx.x != 0 || blockIdx.x != 0) return;
     const double inv = stats[QB_STAT_INV_NORM];
-    double run = 0.0;
+    double run = carry ? *carry : 0.0;
     for (int64_t i = 0; i < n; ++i) {
-        run = (i == 0) ? w[0] * inv : run + w[i] * inv;
+        run = (i == 0 && !carry) ? w[0] * inv : run + w[i] * inv;
         cdf[i] = run;
     }
 }
@@ -454,7 +457,7 @@ size_t exact_scan_workspace_bytes(int64_t n) {
 
 // `tile_prefix`: ntiles + 1 approximate exclusive prefix values (tile = 2048 weights), already on the device.
 int launch_exact_scan(const double* d_w, const double* d_stats, int64_t n, double* d_cdf, const double* tile_prefix,
-                      void* d_ws, cudaStream_t st) {
+                      const double* d_carry, void* d_ws, cudaStream_t st) {
     const int sms = sm_count();
     int64_t chunk = (n + static_cast<int64_t>(sms) * EX_THREADS - 1) / (static_cast<int64_t>(sms) * EX_THREADS);
     chunk = ((chunk + 3) / 4) * 4;
@@ -467,6 +470,7 @@ int launch_exact_scan(const double* d_w, const double* d_stats, int64_t n, doubl
     p.w = d_w;
     p.stats = d_stats;
     p.tile_prefix = tile_prefix;
+    p.carry = d_carry;
     p.cdf = d_cdf;
     p.ticket = reinterpret_cast<unsigned int*>(base);
     p.fallback = reinterpret_cast<int*>(base + 64);
@@ -478,7 +482,7 @@ int launch_exact_scan(const double* d_w, const double* d_stats, int64_t n, doubl
     QB_CUDA_CHECK(cudaMemsetAsync(base, 0, 256 + sizeof(ExDesc) * ncta, st));
     exact_scan_kernel<<<ncta, EX_THREADS, 0, st>>>(p);
     QB_CUDA_CHECK(cudaGetLastError());
-    exact_scan_fallback_kernel<<<1, 32, 0, st>>>(d_w, d_stats, n, d_cdf, p.fallback);
+    exact_scan_fallback_kernel<<<1, 32, 0, st>>>(d_w, d_stats, n, d_cdf, p.fallback, d_carry);
     QB_CUDA_CHECK(cudaGetLastError());
     return QB_OK;
 }

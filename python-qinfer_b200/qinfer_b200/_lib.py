@@ -84,6 +84,7 @@ SIGNATURES = {
     "qb_moments": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _SZ, _P]),
     "qb_cdf_workspace_bytes": (_SZ, [_I64]),
     "qb_cdf": (ctypes.c_int, [_P, _P, _I64, _P, _I32, _P, _SZ, _P]),
+    "qb_cdf_chained": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "qb_cdf_exact_fallback_flag": (ctypes.c_int, [_P, _I64, ctypes.POINTER(_I32), _P]),
     "qb_draw_workspace_bytes": (_SZ, [_I64]),
     "qb_draw": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _SZ, _P]),

@@ -390,9 +390,18 @@ class DeviceCloud(object):
     def preallocate_resample_slab(self):
         self._alt_slab(self.n)
 
-    def cdf(self, mode):
+    def cdf(self, mode, carry=None):
+        """``carry``: a one-element device tensor holding the exact running sum of the slabs before this one (the
+        chained exact scan of a sharded cloud's parity mode)."""
         if self._cdf is None or self._cdf.numel() != self.n:
             self._cdf = torch.empty((self.n,), dtype=torch.float64, device=self.device)
+        if carry is not None:
+            if mode != _lib.QB_SCAN_EXACT:
+                raise ValueError("a carried-in running sum needs the exact scan")
+            check(self.lib.qb_cdf_chained(_ptr(self.w), _ptr(self.stats), self.n, _ptr(self._cdf), _ptr(carry),
+                                          _ptr(self.ws), self.ws_bytes, _stream()))
+            self.launches += 1
+            return self._cdf
         check(self.lib.qb_cdf(_ptr(self.w), _ptr(self.stats), self.n, _ptr(self._cdf), int(mode), _ptr(self.ws),
                               self.ws_bytes, _stream()))
         self.launches += 1 if mode == _lib.QB_SCAN_EXACT else 3
@@ -693,9 +702,10 @@ class DeviceCloud(object):
                                           _ptr(self.ws), self.ws_bytes, _stream()))
         self.launches += 3
 
-    def lw_retry(self, mean, S, a, eps_dev, k, x_src=None, own_mean=False):
+    def lw_retry(self, mean, S, a, eps_dev, k, x_src=None, own_mean=False, js=None):
         src = self.x if x_src is None else x_src
-        check(self.lib.qb_lw_retry(self.lib_model, _ptr(src), src.shape[0], self.d, _ptr(self._js),
+        check(self.lib.qb_lw_retry(self.lib_model, _ptr(src), src.shape[0], self.d,
+                                   _ptr(self._js if js is None else js),
                                    _ptr(self._idxs), int(k), _lib.f64_array(mean),
                                    _lib.f64_array(np.asarray(S).reshape(-1)), float(a), _ptr(eps_dev),
                                    _ptr(self.x_alt), _ptr(self._invalid), _ptr(self.counter),

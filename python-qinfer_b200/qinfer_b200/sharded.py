@@ -21,10 +21,17 @@ updater is sharded the same way, one process per GPU:
 ``ShardComm`` is the only place that touches torch.distributed, and the routing of a resample is written against
 a small ``ops`` interface so that it runs unchanged on CPU tensors under gloo (tests/test_sharded_cpu.py).
 
-Deviations from the single-GPU path, both documented in DESIGN.md: the CDF is the re-associated (fast) scan, so
-resample indices are not bit-identical to the single-process reference; and the postselection retry re-centres a
-particle on its OWN shrunk mean instead of replicating the reference's prefix-slice quirk (resamplers.py:372),
-which would need a second exchange.
+  parity    ``LiuWestResampler(rng='numpy' | 'mt19937')`` (SURVEY §8e "Parity mode"): the global resample indices
+            equal the single-process reference's.  The exact scan is CHAINED across the slabs — rank r continues the
+            sequential fp64 sum from the last CDF entry of rank r - 1 (one double, point to point) — the slab CDFs
+            and slabs are all-gathered, every rank generates the same legacy stream (a sequential generator cannot be
+            sharded) and keeps the variates of its own global slots, and the postselection retry follows the
+            reference's ``mus[:k]`` prefix (resamplers.py:372) in GLOBAL invalid order (``parity_resample`` below).
+
+Deviations of the throughput mode from the single-GPU path, both documented in DESIGN.md: the CDF is the
+re-associated (fast) scan, so resample indices are not bit-identical to the single-process reference; and the
+postselection retry re-centres a particle on its OWN shrunk mean instead of replicating the reference's prefix-slice
+quirk (resamplers.py:372), which would need a second exchange.
 """
 import ctypes
 import warnings
@@ -146,6 +153,38 @@ class ShardComm(object):
                                     input_split_sizes=[int(c) * width for c in send_counts], group=self.group)
         return recv
 
+    def _global_rank(self, r):
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def recv_prev(self, t):
+        """Point to point: receive ``t`` from rank - 1 (the carried-in running sum of a chained scan)."""
+        self.dist.recv(t, src=self._global_rank(self.rank - 1), group=self.group)
+        return t
+
+    def send_next(self, t):
+        self.dist.send(t.contiguous(), dst=self._global_rank(self.rank + 1), group=self.group)
+
+    def all_gather_ragged(self, t, counts, width=1):
+        """Concatenation over the ranks of slabs of counts[r] rows of ``width`` elements (flat tensors)."""
+        counts = [int(c) for c in counts]
+        cap = max(counts) * width
+        mine = t.reshape(-1)
+        if mine.numel() != cap:
+            pad = torch.zeros((cap,), dtype=t.dtype, device=t.device)
+            pad[:mine.numel()] = mine
+            mine = pad
+        out = torch.empty((self.world * cap,), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, mine.contiguous(), group=self.group)
+        if all(c * width == cap for c in counts):
+            return out
+        return torch.cat([out[q * cap:q * cap + counts[q] * width] for q in range(self.world)])
+
+    def all_gather_ints(self, value, device):
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        out = torch.empty((self.world,), dtype=torch.int64, device=device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return [int(v) for v in out.tolist()]
+
     def all_gather_object(self, obj):
         out = [None] * self.world
         self.dist.all_gather_object(out, obj, group=self.group)
@@ -239,6 +278,123 @@ def split_resample(comm, ops, m, cap, width):
 # ---------------------------------------------------------------------------
 # device ops + sharded updater
 # ---------------------------------------------------------------------------
+def _columns(eps, d, k_total, first, k):
+    """Columns [first, first + k) of a flat (d, k_total) row-major block, as a flat (d, k) block."""
+    if d == 1 or k == k_total:
+        return eps[first:first + k] if d == 1 else eps
+    return eps.reshape(d, k_total)[:, first:first + k].contiguous().reshape(-1)
+
+
+def parity_resample(comm, ops, layout, d, postselect, maxiter):
+    """Liu-West resample of a sharded cloud with the reference's GLOBAL indices (resamplers.py:308-372).
+
+    ``ops`` supplies the kernels (CUDA engine, or NumPy in tests/test_sharded_cpu.py):
+      scan(carry) -> this slab's piece of np.cumsum(w_global), continued from the one-element tensor ``carry``
+      slab() -> (n_local, d) locations;  zeros(n) -> float64 tensor
+      uniforms(n) / normals(d, k) -> the next n / d*k variates of the legacy stream (identical on every rank)
+      draw(cdf, u) -> min(searchsorted(cdf, u, 'right'), len(cdf) - 1)
+      move(x_all, js, eps) -> writes the new slab, returns this rank's invalid count
+      retry(x_all, js_prefix, eps, k) -> re-perturbs the k invalid rows (ascending slot order) around
+                                         a x_all[js_prefix[r]] + (1 - a) mean, returns the new invalid count
+    Returns (n_iters, n_invalid_global, js of this slab)."""
+    r, world = comm.rank, comm.world
+    counts, first = layout.counts, layout.offsets[comm.rank]
+    n_local, n_global = counts[r], layout.n_global
+    # the sequential-CDF chain crosses the shards: one double travels rank to rank
+    carry = ops.zeros(1)
+    if r > 0:
+        comm.recv_prev(carry)
+    cdf = ops.scan(carry)
+    if r < world - 1:
+        comm.send_next(cdf[n_local - 1:n_local])
+    cdf_all = comm.all_gather_ragged(cdf, counts, 1)
+    x_all = comm.all_gather_ragged(ops.slab(), counts, d).reshape(n_global, d)
+    u_all = ops.uniforms(n_global)                                   # resamplers.py:319
+    js = ops.draw(cdf_all, u_all[first:first + n_local])             # the global js of this rank's slots
+    eps = ops.normals(d, n_global)                                   # kernel(n_rvs, n) — one global block
+    k_local = ops.move(x_all, js, _columns(eps, d, n_global, first, n_local))
+    n_iters = 1
+    while True:
+        ks = comm.all_gather_ints(k_local if postselect else 0, cdf.device)
+        k_global = sum(ks)
+        if k_global == 0 or n_iters >= maxiter:
+            return n_iters, k_global, js
+        n_iters += 1
+        # `mus = mus[:k]` (resamplers.py:372): the q-th still-invalid particle IN GLOBAL ORDER is re-centred on the
+        # q-th original draw; its parent index is recomputed here from the shared uniform stream
+        q0 = sum(ks[:r])
+        eps = ops.normals(d, k_global)                               # every rank consumes the whole block
+        if k_local:
+            js_prefix = ops.draw(cdf_all, u_all[q0:q0 + k_local])
+            k_local = ops.retry(x_all, js_prefix, _columns(eps, d, k_global, q0, k_local), k_local)
+
+
+class _ParityOps(object):
+    """``parity_resample``'s kernels on the CUDA engine."""
+
+    def __init__(self, cloud, resampler, mean, S):
+        self.cloud, self.res, self.mean, self.S = cloud, resampler, mean, S
+        cloud._resample_scratch(cloud.n)
+        self._bufs = {}
+
+    def _buf(self, name, n, dtype=torch.float64):
+        b = self._bufs.get(name)
+        if b is None or b.numel() < n:
+            self._bufs[name] = b = torch.empty((int(n),), dtype=dtype, device=self.cloud.device)
+        return b[:n]
+
+    def zeros(self, n):
+        return torch.zeros((n,), dtype=torch.float64, device=self.cloud.device)
+
+    def slab(self):
+        return self.cloud.x
+
+    def scan(self, carry):
+        return self.cloud.cdf(_lib.QB_SCAN_EXACT, carry=carry)
+
+    def uniforms(self, n):
+        out = self._buf('u', n)
+        if self.res._rng == 'numpy':
+            out.copy_(torch.from_numpy(np.random.random((n,))))
+        else:
+            self.cloud.mt19937_uniform(out, n)
+        return out
+
+    def normals(self, d, k):
+        out = self._buf('eps', d * k)
+        if self.res._rng == 'numpy':
+            eps = np.ascontiguousarray(self.res._kernel(d, k), dtype=np.float64)
+            if eps.shape != (d, k):
+                raise ValueError("resampling kernel returned shape %s, expected %s" % (eps.shape, (d, k)))
+            out.copy_(torch.from_numpy(eps.reshape(-1)))
+        else:
+            self.cloud.mt19937_normal(out, d * k)
+        return out
+
+    def draw(self, cdf, u):
+        cloud = self.cloud
+        js = torch.empty((u.numel(),), dtype=torch.int64, device=cloud.device)
+        nbytes = cloud.lib.qb_draw_workspace_bytes(cdf.numel())
+        ws = self._buf('draw_ws', max(nbytes, 8), torch.uint8)
+        _lib.check(cloud.lib.qb_draw(ctypes.c_void_p(cdf.data_ptr()), cdf.numel(), ctypes.c_void_p(u.data_ptr()),
+                                     u.numel(), ctypes.c_void_p(js.data_ptr()),
+                                     ctypes.c_void_p(cloud.counter[1:].data_ptr()),
+                                     ctypes.c_void_p(ws.data_ptr()) if nbytes else None, nbytes,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        cloud.launches += 2
+        return js
+
+    def move(self, x_all, js, eps):
+        res = self.res
+        self.cloud.lw_move(self.mean, self.S, res._a, eps, self.cloud.n, res._postselect, x_src=x_all, js=js)
+        return self.cloud.read_counter()[0] if res._postselect else 0
+
+    def retry(self, x_all, js_prefix, eps, k):
+        self.cloud.compact_invalid(self.cloud.n)
+        self.cloud.lw_retry(self.mean, self.S, self.res._a, eps, k, x_src=x_all, js=js_prefix)
+        return self.cloud.read_counter()[0]
+
+
 class _DeviceOps(object):
     def __init__(self, cloud, world):
         self.cloud = cloud
@@ -366,9 +522,9 @@ def _make_sharded_updater_class():
             self._mail = None
             self._ops = None
             resampler = kwargs.get('resampler')
-            if resampler is not None and getattr(resampler, '_rng', 'philox') != 'philox':
-                raise ValueError("a sharded cloud needs LiuWestResampler(rng='philox'): the legacy NumPy stream "
-                                 "is a single sequential generator")
+            # (rng='numpy' / 'mt19937': the parity mode — every rank must hold the same np.random state, e.g.
+            # np.random.seed(s) on every rank, because every rank generates the whole legacy stream)
+            self.last_parity_js = None
             super(ShardedSMCUpdater, self).__init__(model, self._layout.count(self._comm.rank), prior, **kwargs)
             if resampler is None:
                 from .resamplers import LiuWestResampler
@@ -609,6 +765,10 @@ def _make_sharded_updater_class():
             comm = self._comm
             n_local, d = cloud.n, cloud.d
 
+            if getattr(res, '_rng', 'philox') != 'philox':
+                self._parity_pass()
+                self._finish_resample(ev)
+                return
             split = d <= 4 and getattr(res, '_fused', False) and self._exchange == 'split'
             if split and getattr(res, '_draw', 'auto') in ('auto', 'binned') and cloud.binned_supported(n_local):
                 floated = self._split_pass_binned()
@@ -677,6 +837,22 @@ def _make_sharded_updater_class():
             res.last_n_iters = n_iters
 
             self._finish_resample(ev)
+
+        def _parity_pass(self):
+            """Parity mode: global moments, then ``parity_resample`` (chained exact scan, shared legacy stream)."""
+            res, cloud = self.resampler, self._cloud
+            if self._layout.counts != self._base_counts:
+                raise _lib.QbError("parity-mode resample on floated slabs (mix of resamplers on one sharded cloud)")
+            _, mean, m2 = self._global_moments()
+            S = self._liu_west_consts(mean, m2)
+            ops = _ParityOps(cloud, res, mean, S)
+            n_iters, bad, js = parity_resample(self._comm, ops, self._layout, cloud.d, res._postselect, res._maxiter)
+            if bad:
+                warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                               "iterations.").format(bad, res._maxiter), ResamplerWarning)
+            res.last_n_iters = n_iters
+            self.last_parity_js = js                 # global parent index of every slot of this slab (diagnostics)
+            self.last_exchange = (0, 0)
 
         def _split_pass(self, mean, S, a):
             """Offspring counts by a shared multinomial split, offspring drawn locally by the fused kernel, surplus

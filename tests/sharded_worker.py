@@ -45,6 +45,14 @@ def main():
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        import smc_oracle as oracle
+        np.random.seed(0)
+        ou = oracle.SMCUpdater(oracle.SimplePrecessionModel(), n_global, Fixed(x), resample_thresh=0.0)
+        for k in range(6):
+            ou.update(int(outcomes[k]), np.array([ts[k]]))
+        ou.resample()
+        om1, oc1 = ou.est_mean(), ou.est_covariance_mtx()
+        del ou
         for lazy in (False, True):
             res = qb.LiuWestResampler(rng='philox', scan='fast', seed=11)
             up = ShardedSMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x[lo:hi]), resampler=res, lazy=lazy,
@@ -97,8 +105,10 @@ def main():
             up.resample()
             m1, c1 = up.est_mean(), up.est_covariance_mtx()
             check(abs(up.n_ess - n_global) < 1e-6 * n_global, "n_ess after resample %r" % up.n_ess)
-            check(abs(m1[0] - m0[0]) < 8 * np.sqrt(c0[0, 0] / ess0), "mean moved %r -> %r" % (m0, m1))
-            check(abs(c1[0, 0] / c0[0, 0] - 1) < 0.1, "cov moved %r -> %r" % (c0, c1))
+            # (offspring below 0 are invalid; the reference's retry re-centres them on an independent draw
+            # (resamplers.py:372), which moves ~3 % of the mass away from 0: the oracle's resample is the yardstick)
+            check(abs(m1[0] - om1[0]) < 8 * np.sqrt(c0[0, 0] / ess0), "mean moved %r -> %r (oracle %r)" % (m0, m1, om1))
+            check(abs(c1[0, 0] / oc1[0, 0] - 1) < 0.05, "cov moved %r -> %r (oracle %r)" % (c0, c1, oc1))
             w = up.particle_weights
             check(np.all(w == 1.0 / n_global), "weights not uniform")
             locs = up.particle_locations
@@ -115,7 +125,6 @@ def main():
             check(np.isfinite(up.n_ess) and up.n_ess <= n_global, "update after a floated resample")
             up.close()
         # (c) a free-running sharded trajectory lands on the same posterior as the oracle (statistically)
-        import smc_oracle as oracle
         res = qb.LiuWestResampler(rng='philox', scan='fast', seed=3)
         up = ShardedSMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x[lo:hi]), resampler=res, lazy=True)
         for k in range(40):
@@ -131,6 +140,72 @@ def main():
             check(nres >= 3, "too few resamples %d" % nres)
             check(abs(mean[0] - om[0]) < 6 * np.sqrt(oc[0, 0]), "posterior mean %r vs oracle %r" % (mean, om))
             check(0.3 < cov[0, 0] / oc[0, 0] < 3.0, "posterior cov %r vs oracle %r" % (cov, oc))
+        # (d) PARITY MODE: legacy MT19937 stream continued on the device + the exact scan chained across
+        # the slabs -> the global resample indices equal the single-GPU engine's and the reference algorithm's
+        # (np.cumsum(w).searchsorted(np.random.random(n), 'right')) bit for bit, retry quirk included
+        rs = np.random.RandomState(17)
+        problems = []
+        n1 = 200003                                                         # slabs >= 32768: the parallel replay scan
+        problems.append((qb.SimplePrecessionModel(min_freq=0.35), 0.3 + 0.4 * rs.random_sample((n1, 1))))
+        n3 = 50001                                                          # small slabs: the one-lane kernel
+        problems.append((qb.RandomizedBenchmarkingModel(),
+                         np.column_stack([0.9 + 0.1 * rs.random_sample(n3), 0.6 * rs.random_sample(n3),
+                                          0.4 * rs.random_sample(n3)])))
+        for model, xs in problems:
+            n_par = xs.shape[0]
+            lay = ShardLayout(n_par, world)
+            plo, phi = lay.offsets[rank], lay.offsets[rank + 1]
+            w = rs.random_sample(n_par) ** 4
+            w[rs.randint(0, n_par, n_par // 7)] = 0.0
+            w /= w.sum()
+            np.random.seed(4242)                                            # the same legacy state on every rank
+            up = ShardedSMCUpdater(model, n_par, Fixed(xs[plo:phi]),
+                                   resampler=qb.LiuWestResampler(a=0.9, rng='mt19937', scan='exact'))
+            up.particle_weights = w[plo:phi]
+            up.resample()
+            js = up.last_parity_js.cpu().numpy()
+            locs, iters = up.particle_locations, up.resampler.last_n_iters
+            after = np.random.random()
+            check(np.all(up.particle_weights == 1.0 / n_par), "parity: weights not uniform")
+            want = np.cumsum(w).searchsorted(np.random.RandomState(4242).random_sample(n_par), side='right')
+            check(np.array_equal(js, want[plo:phi]), "parity: js differ from np.cumsum/searchsorted in %d slots"
+                  % int(np.sum(js != want[plo:phi])))
+            check(iters > 2, "parity: the retry loop did not run (%d iterations)" % iters)
+            check(bool(np.all(np.asarray(model.are_models_valid(locs)))), "parity: invalid particles left")
+            up.close()
+            if rank == 0:
+                np.random.seed(4242)
+                ref = qb.SMCUpdater(model, n_par, Fixed(xs),
+                                    resampler=qb.LiuWestResampler(a=0.9, rng='mt19937', scan='exact'))
+                ref.particle_weights = w
+                ref.resample()
+                check(np.array_equal(ref._cloud._js.cpu().numpy()[plo:phi], js), "parity: js differ from single GPU")
+                check(ref.resampler.last_n_iters == iters, "parity: %d iterations vs %d on one GPU"
+                      % (iters, ref.resampler.last_n_iters))
+                check(np.random.random() == after, "parity: legacy stream position differs from single GPU")
+                # (locations: same js, same variates; the global mean / covariance are reduced in another order)
+                check(np.allclose(locs, ref.particle_locations[plo:phi], rtol=1e-12, atol=1e-14),
+                      "parity: locations differ from single GPU by %r"
+                      % float(np.max(np.abs(locs - ref.particle_locations[plo:phi]))))
+        # ... and free-running: the sharded parity trajectory follows the single-GPU parity trajectory
+        np.random.seed(7)
+        up = ShardedSMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x[lo:hi]),
+                               resampler=qb.LiuWestResampler(rng='mt19937', scan='exact'))
+        for k in range(25):
+            up.update(int(outcomes[k]), ts[k:k + 1])
+        mean, cov, nres = up.est_mean(), up.est_covariance_mtx(), up.resample_count
+        up.close()
+        if rank == 0:
+            np.random.seed(7)
+            ref = qb.SMCUpdater(qb.SimplePrecessionModel(), n_global, Fixed(x),
+                                resampler=qb.LiuWestResampler(rng='mt19937', scan='exact'))
+            for k in range(25):
+                ref.update(int(outcomes[k]), ts[k:k + 1])
+            check(nres == ref.resample_count and nres >= 3, "parity trajectory: %d resamples vs %d"
+                  % (nres, ref.resample_count))
+            check(abs(mean[0] - ref.est_mean()[0]) <= 1e-9 * abs(mean[0]), "parity trajectory: mean %r vs %r"
+                  % (mean, ref.est_mean()))
+            check(abs(cov[0, 0] / ref.est_covariance_mtx()[0, 0] - 1) <= 1e-7, "parity trajectory: covariance")
     flag = torch.tensor([len(fails)], dtype=torch.int64, device='cuda')
     dist.all_reduce(flag)
     for f in fails:

@@ -297,6 +297,37 @@ def test_t4_parallel_exact_scan_bit_identical(qb, name):
     assert np.array_equal(js, np.minimum(want, w.shape[0] - 1))
 
 
+@pytest.mark.parametrize("name", ["skewed_1m", "zeros_3m", "leading_zeros", "denormals_and_jumps", "powers_of_two",
+                                  "ties_third", "random_33k"])
+def test_t4_chained_exact_scan_equals_cumsum_of_the_concatenation(qb, name):
+    """qb_cdf_chained (SURVEY §8e parity mode): slabs scanned one after the other, each continuing the running fp64
+    sum from the last CDF entry of the slab before it, concatenate to np.cumsum of the whole weight vector bit for
+    bit — through the parallel replay scan (slabs >= 32768) and the one-lane kernel (small slabs) alike."""
+    import torch
+    from qinfer_b200 import _lib
+    from qinfer_b200.engine import DeviceCloud
+    w = _big_weight_cases()[name]
+    n = w.shape[0]
+    cuts = [0, int(0.37 * n) + 1, int(0.37 * n) + 1 + 1000, int(0.8 * n) + 3, n]      # uneven, one small slab
+    desc = qb.describe_model(qb.SimplePrecessionModel())
+    carry = torch.zeros((1,), dtype=torch.float64, device="cuda")
+    pieces = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        cloud = DeviceCloud(desc, hi - lo)
+        cloud.upload_locations(np.zeros((hi - lo, 1)))
+        cloud.upload_weights(w[lo:hi])
+        cloud.stats[_lib.QB_STAT_INV_NORM] = 1.0             # slab weights are normalised GLOBALLY already
+        cdf = cloud.cdf(_lib.QB_SCAN_EXACT, carry=carry)
+        if hi - lo >= 32768:
+            assert cloud.exact_scan_fell_back() == 0
+        pieces.append(cdf.cpu().numpy())
+        carry = cdf[-1:].clone()
+    got, want = np.concatenate(pieces), np.cumsum(w)
+    nbad = int(np.sum(got != want))
+    assert nbad == 0, "%d of %d chained CDF entries differ from np.cumsum (first at %d)" % (
+        nbad, n, int(np.argmax(got != want)))
+
+
 def test_t4_exact_scan_falls_back_on_negative_weights(qb):
     """Weights outside the replay's model (negative) are detected and the sequential kernel takes over."""
     rs = np.random.RandomState(2)

@@ -10,8 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from qinfer_b200.sharded import (ShardComm, ShardLayout, cdf_bounds, exchange_plan, route_resample, split_counts,
-                                 split_resample)
+from qinfer_b200.sharded import (ShardComm, ShardLayout, cdf_bounds, exchange_plan, parity_resample, route_resample,
+                                 split_counts, split_resample)
 
 
 def _free_port():
@@ -222,3 +222,118 @@ def test_split_resample_moves_only_the_surplus(tmp_path, world, n_global, masses
         assert np.array_equal(f["rows"], np.array([[q, 1.0, 2.0] for q in range(world)]))
     # the union of the slabs is exactly the set of offspring drawn: nothing lost, nothing duplicated
     assert seen == {(r, k) for r in range(world) for k in range(m[r])}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parity mode: chained sequential scan + shared legacy stream + the reference's `mus[:k]` prefix in global
+# invalid order.  NumPy stands in for the kernels; the ORACLE's LiuWestResampler on the whole cloud is the truth.
+# ---------------------------------------------------------------------------------------------------------------------
+class NumpyParityOps(object):
+    def __init__(self, model, x_local, w_local, mean, S, a):
+        self.model, self.x, self.w, self.mean, self.S, self.a = model, x_local, w_local, mean, S, a
+        self.new = None
+        self.invalid = None
+
+    def zeros(self, n):
+        return torch.zeros((n,), dtype=torch.float64)
+
+    def slab(self):
+        return torch.from_numpy(self.x)
+
+    def scan(self, carry):
+        run = float(carry[0])
+        out = np.empty_like(self.w)
+        for i, wi in enumerate(self.w):               # the sequential fp64 chain, continued from the previous slab
+            run = run + wi
+            out[i] = run
+        return torch.from_numpy(out)
+
+    def uniforms(self, n):
+        return torch.from_numpy(np.random.random((n,)))
+
+    def normals(self, d, k):
+        return torch.from_numpy(np.random.randn(d, k).reshape(-1))
+
+    def draw(self, cdf, u):
+        c = cdf.numpy()
+        return torch.from_numpy(np.minimum(c.searchsorted(u.numpy(), side='right'), c.size - 1).astype(np.int64))
+
+    def _perturb(self, x_all, js, eps):
+        d = self.x.shape[1]
+        mus = self.a * x_all.numpy()[js.numpy(), :] + (1 - self.a) * self.mean
+        return mus + np.dot(self.S, eps.numpy().reshape(d, -1)).T
+
+    def move(self, x_all, js, eps):
+        self.new = self._perturb(x_all, js, eps)
+        self.invalid = np.logical_not(self.model.are_models_valid(self.new))
+        return int(self.invalid.sum())
+
+    def retry(self, x_all, js_prefix, eps, k):
+        idxs = np.nonzero(self.invalid)[0]
+        assert idxs.size == k
+        self.new[idxs] = self._perturb(x_all, js_prefix, eps)
+        self.invalid[idxs] = np.logical_not(self.model.are_models_valid(self.new[idxs]))
+        return int(self.invalid.sum())
+
+
+def _parity_problem(n_global, d, seed):
+    import smc_oracle as oracle
+    rs = np.random.RandomState(seed)
+    if d == 1:
+        model = oracle.SimplePrecessionModel(min_freq=0.35)            # a third of the perturbed cloud is invalid
+        x = 0.3 + 0.4 * rs.random_sample((n_global, 1))
+    else:
+        model = oracle.RandomizedBenchmarkingModel()                   # p, A, B in [0, 1], A + B <= 1
+        x = np.column_stack([0.9 + 0.1 * rs.random_sample(n_global), 0.6 * rs.random_sample(n_global),
+                             0.4 * rs.random_sample(n_global)])
+    w = rs.random_sample(n_global) ** 4
+    w[rs.randint(0, n_global, n_global // 7)] = 0.0
+    w /= w.sum()
+    return oracle, model, x, w
+
+
+def _parity_worker(rank, world, port, n_global, d, out_dir):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        oracle, model, x, w = _parity_problem(n_global, d, 321)
+        comm = ShardComm()
+        layout = ShardLayout(n_global, world)
+        lo, hi = layout.offsets[rank], layout.offsets[rank + 1]
+        a, h = 0.9, np.sqrt(1 - 0.9 ** 2)
+        whole = oracle.ParticleDistribution(particle_locations=x, particle_weights=w)
+        mean = whole.est_mean()
+        S = np.real(h * oracle.sqrtm_psd(whole.est_covariance_mtx())[0])
+        np.random.seed(77)                                              # the same legacy stream on every rank
+        ops = NumpyParityOps(model, x[lo:hi].copy(), w[lo:hi].copy(), mean, S, a)
+        n_iters, bad, js = parity_resample(comm, ops, layout, d, True, 1000)
+        np.savez(os.path.join(out_dir, "p%d.npz" % rank), new=ops.new, js=js.numpy(), n_iters=n_iters, bad=bad,
+                 next_u=np.random.random())
+        comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_global,d", [(2, 3001, 1), (3, 2000, 3)])
+def test_parity_resample_equals_the_single_process_reference_algorithm(tmp_path, world, n_global, d):
+    port = _free_port()
+    mp.spawn(_parity_worker, args=(world, port, n_global, d, str(tmp_path)), nprocs=world, join=True)
+    oracle, model, x, w = _parity_problem(n_global, d, 321)
+    np.random.seed(77)
+    dist_ = oracle.ParticleDistribution(particle_locations=x, particle_weights=w)
+    res = oracle.LiuWestResampler(a=0.9)
+    want = res(model, dist_).particle_locations
+    next_u = np.random.random()
+    js_want = np.cumsum(w).searchsorted(np.random.RandomState(77).random_sample(n_global), side='right')
+    parts = [np.load(os.path.join(str(tmp_path), "p%d.npz" % r)) for r in range(world)]
+    got = np.concatenate([f["new"] for f in parts], axis=0)
+    assert np.array_equal(np.concatenate([f["js"] for f in parts]), js_want)        # global indices, bit for bit
+    assert all(int(f["n_iters"]) > 2 and int(f["bad"]) == 0 for f in parts)         # the retry loop really ran
+    assert all(float(f["next_u"]) == next_u for f in parts)                         # streams consumed in lockstep
+    if d == 1:
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
