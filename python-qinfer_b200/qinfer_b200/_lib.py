@@ -188,3 +188,26 @@ def check(rc):
 
 def f64_array(values):
     return (ctypes.c_double * len(values))(*[float(v) for v in values])
+
+
+# ---- NVTX ranges (SURVEY §5 tracing): QB_NVTX=1 wraps the host entry points in named ranges (visible in nsys / ncu
+# timelines); unset, the functions are left untouched — no cost on the hot path ------------------------------------
+NVTX = os.environ.get("QB_NVTX", "0") == "1"
+
+
+def nvtx_range(name):
+    def deco(fn):
+        if not NVTX:
+            return fn
+        import functools
+        import torch
+
+        @functools.wraps(fn)
+        def inner(*args, **kwargs):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return inner
+    return deco

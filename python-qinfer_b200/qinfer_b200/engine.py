@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._lib import nvtx_range
 import time
 
 from ._lib import (QB_MAX_FUSE, QB_STAT_COUNT, QB_STAT_INV_NORM, QB_STAT_MIN, QB_STAT_NBAD, QB_STAT_NESS,
@@ -198,6 +199,7 @@ class DeviceCloud(object):
         return self.stats_host.numpy()
 
     # ---- the hot kernel -------------------------------------------------------
+    @nvtx_range('qb.cloud.fused_update')
     def fused_update(self, steps, src, guard=False, zero_weight_thresh=0.0, resample_below=0.0):
         """Launch ONE fused kernel applying the consecutive updates ``steps`` = [(ep_record, outcome, check), ...]
         (1..QB_MAX_FUSE of them) to weights/stats buffer ``src``, writing buffer ``1 - src``; the kernel mirrors one
@@ -249,6 +251,7 @@ class DeviceCloud(object):
         self._chain_tag, self._chain_dst = self._tag, dst
         return self._tag
 
+    @nvtx_range('qb.cloud.wait_stats')
     def wait_stats(self, slot, tag, nsteps=1, timeout_s=120.0):
         """Spin on the pinned mirror of stats buffer ``slot`` until launch ``tag`` has published its ``nsteps`` blocks.
         Each block is {S, Q, #bad, TAG | record, n_ess, TAG, attention + 2*skipped}, written as two 32-byte stores;
@@ -530,6 +533,7 @@ class DeviceCloud(object):
         self.launches += 2
         return self._bin_tag
 
+    @nvtx_range('qb.cloud.binned_resample')
     def binned_resample(self, n_new, a, h, zero_cov_comp, seed, off_u, off_v, seed_n, off_n, postselect,
                         retry_rounds, fuse_weights, n_global=None, own_mean=False):
         """The whole binned resample queued by one call (moments, Liu-West constants on the device, counts, move,
@@ -675,6 +679,7 @@ class DeviceCloud(object):
         m = self._bin_mirror_np
         return int(m[32]), int(m[33]), int(m[34])
 
+    @nvtx_range('qb.cloud.binned_retry_wait')
     def binned_retry_wait(self, tag, queued=False):
         """(#still invalid, most rounds used, list length) of a retry launch: ``queued`` = the one ``binned_move`` queued
         behind itself (it reports next to the move's block, under the move's tag)."""
@@ -750,6 +755,7 @@ class DeviceCloud(object):
         self._swap_slabs(n_new)
         self.set_uniform_weights(n_global)
 
+    @nvtx_range('qb.cloud.canonicalize')
     def canonicalize(self):
         if self.desc.kind != _lib.QB_MODEL_TOMOGRAPHY:
             return

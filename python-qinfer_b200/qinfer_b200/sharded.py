@@ -41,6 +41,7 @@ import scipy.linalg
 import torch
 
 from . import _lib
+from ._lib import nvtx_range
 from ._exceptions import ResamplerError, ResamplerWarning
 
 
@@ -651,6 +652,7 @@ def _make_sharded_updater_class():
             self._restat_global()
 
         # -- global reductions ---------------------------------------------------------------
+        @nvtx_range('qb.sharded.global_moments')
         def _global_moments(self, overlap=None):
             """Global (sum w, mean, second moment): local reduction, ONE all-gather, rows summed in rank order (so
             every rank holds identical numbers).  ``overlap``: a callable that queues device work which does not
@@ -749,6 +751,7 @@ def _make_sharded_updater_class():
             return out[0] if len(out) == 1 else out
 
         # -- resampling -------------------------------------------------------------------------
+        @nvtx_range('qb.sharded.resample')
         def resample(self):
             self._flush()
             if self._just_resampled:
@@ -838,6 +841,7 @@ def _make_sharded_updater_class():
 
             self._finish_resample(ev)
 
+        @nvtx_range('qb.sharded.parity_pass')
         def _parity_pass(self):
             """Parity mode: global moments, then ``parity_resample`` (chained exact scan, shared legacy stream)."""
             res, cloud = self.resampler, self._cloud
@@ -899,6 +903,7 @@ def _make_sharded_updater_class():
                                      "Check that n_ess is not too small.")
             return np.real(res._h * S)
 
+        @nvtx_range('qb.sharded.split_pass_binned')
         def _split_pass_binned(self):
             """The "split" resample over the binned draw (csrc/qb_binned.cu): ONE pass over the slab gives its bin
             sums and its moment sums; ONE all-gather of the 1 + d + d^2 sums gives the global mean / covariance and

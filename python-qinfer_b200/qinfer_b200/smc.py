@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from ._exceptions import ApproximationWarning, ResamplerWarning
-from ._lib import QB_MAX_FUSE, QB_STAT_NORM, QB_STAT_SUMSQ, QbExpparams
+from ._lib import QB_MAX_FUSE, QB_STAT_NORM, QB_STAT_SUMSQ, QbExpparams, nvtx_range
 from .distributions import covariance_from_moments
 from .engine import DeviceCloud
 from .models import describe_model
@@ -303,6 +303,7 @@ class SMCUpdater(object):
         for m in chain:
             m._call_count += n
 
+    @nvtx_range('qb.hypothetical_update')
     def hypothetical_update(self, outcomes, expparams, return_likelihood=False, return_normalization=False):
         """smc.py:324-386: posterior weights of hypothetical data, shape (n_outcomes, n_expparams, n_particles),
         computed on the device (likelihood, weight product, normalisation sum, division) and returned as host arrays."""
@@ -372,6 +373,7 @@ class SMCUpdater(object):
     def risk(self, x0):
         return self.bayes_risk(np.array([(x0,)], dtype=self.model.expparams_dtype))
 
+    @nvtx_range('qb.update')
     def update(self, outcome, expparams, check_for_resample=True):
         """smc.py:388-457.  With ``lazy=False`` the call returns after the step's bookkeeping exactly like the
         reference; with ``lazy=True`` it only buffers the datum (launching a fused kernel every ``fuse`` updates)."""
@@ -417,6 +419,7 @@ class SMCUpdater(object):
             # (the speculative launch cancelled itself; its steps are still queued, behind whatever steps of
             # `prev` _finalize put back)
 
+    @nvtx_range('qb.flush')
     def _flush(self):
         """Launch and settle everything that is buffered or pending."""
         if self._settling:          # re-entered from the step being settled (resample(), est_mean(), ...)
@@ -556,6 +559,7 @@ class SMCUpdater(object):
     def _clip_weights(self, slot):
         return self._cloud.clip_weights(slot)
 
+    @nvtx_range('qb.batch_update')
     def batch_update(self, outcomes, expparams, resample_interval=5):
         """smc.py:459-487.  The reference loops ``update(check_for_resample=False)`` and calls ``_maybe_resample``
         after every ``resample_interval``-th datum; here the same sequence is buffered and goes out as fused
@@ -585,6 +589,7 @@ class SMCUpdater(object):
             return True
         return False
 
+    @nvtx_range('qb.resample')
     def resample(self):
         self._flush()
         if self._just_resampled:

@@ -141,3 +141,19 @@ def test_sqrtm_psd_one_by_one_shortcut_equals_eigh():
         assert got.shape == (1, 1) and got[0, 0] == want[0, 0] and err == want_err
     with pytest.raises(ValueError):
         qb.sqrtm_psd(np.array([[np.nan]]))
+
+
+def test_nvtx_ranges_are_opt_in():
+    """QB_NVTX=1 wraps the host entry points in NVTX ranges; unset, the functions are untouched (no hot-path cost)."""
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); import qinfer_b200 as qb; from qinfer_b200.engine import DeviceCloud; "
+            "print(int(hasattr(qb.SMCUpdater.update, '__wrapped__')), int(hasattr(qb.SMCUpdater.resample, '__wrapped__')),"
+            " int(hasattr(DeviceCloud.fused_update, '__wrapped__')))") % os.path.join(ROOT, "python-qinfer_b200")
+    for flag, want in (("1", "1 1 1"), ("0", "0 0 0")):
+        env = dict(os.environ, QB_NVTX=flag)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert out.stdout.strip().splitlines()[-1] == want
