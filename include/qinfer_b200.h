@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define QB_ABI_VERSION 3 /* 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes; 3: qb_lw_binned_*,
+#define QB_ABI_VERSION 4 /* 4: qb_update_ctl.h_shard_norms, qb_cdf_chained, qb_lw_binned_shard_consts; 2: qb_model.likelihood_power, qb_update_ctl.chain_prev_tag, flagged-word mailboxes; 3: qb_lw_binned_*,
                             qb_model.d_extra / extra_rule, qb_walk_step, qb_poison_likelihood, qb_tomo_canonicalize*_ld,
                             qb_weights_entropy, qb_weight_mass_hist, qb_weights_select */
 
@@ -169,6 +169,10 @@ typedef struct qb_update_ctl {
     int32_t n_ranks, rank;
     double* d_peer_mailbox[QB_MAX_RANKS]; /* [r] = rank r's mailbox as mapped in THIS process */
     int32_t* d_error_flag;     /* optional device int, set to 1 if a peer never answered */
+    /* Optional, n_ranks > 1: device-accessible pinned host block of QB_MAX_RANKS + 1 doubles.  The launch stores every
+     * rank's own sum w' of its LAST fused step in [0, n_ranks) — the shard masses a following resample splits its
+     * offspring by, known without another pass or collective — and then the launch tag in [QB_MAX_RANKS]. */
+    double* h_shard_norms;
 } qb_update_ctl;
 /* One launch: w_out[i] = (w_in[i] * stats_in[INV_NORM]) * L(outcome | x_i; ep)
  * fused with the block+warp reductions for sum, sum of squares, min and the
@@ -386,6 +390,15 @@ int qb_lw_binned_sums(const double* d_x, const double* d_w, const double* d_stat
 #define QB_COUNT_AUTO 0
 #define QB_COUNT_HISTOGRAM 1
 #define QB_COUNT_TREE 2
+/* Sharded cloud, between pass 1 and pass 3: `d_rows` holds n_ranks rows of 1 + d + d*d moment sums (the
+ * all-gathered `d_moments_out` of every rank's qb_lw_binned_sums, globally normalised weights).  One thread sums them
+ * in rank order — bit-identical on every rank — and derives the Liu-West constants exactly like
+ * qb_lw_binned_resample's first kernel (same workspace slot: a following qb_lw_binned_move / _retry with h_mean = h_S =
+ * NULL uses them).  h_mirror (may be NULL): [0 ..) the global moments, [29] covariance flag, [30] sqrtm error,
+ * [31] tag, as qb_lw_binned_resample publishes them. */
+int qb_lw_binned_shard_consts(const double* d_rows, int32_t n_ranks, int32_t d, double a, double h,
+                              double zero_cov_comp, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                              void* stream);
 int qb_lw_binned_count(int64_t n_old, int64_t n_new, uint64_t seed_u, uint64_t off_u, int32_t mode, void* d_ws,
                        size_t ws_bytes, void* stream);
 /* The tree's sampler on its own (tests): d_out[i] ~ Binomial(n, p), i < count, from counters off + 32 i of stream seed. */

@@ -1351,6 +1351,45 @@ extern "C" int qb_lw_binned_sums(const double* d_x, const double* d_w, const dou
                        0.0, 0.0);
 }
 
+// Sharded cloud: global moments = rows summed in rank order, then the same constants the single-GPU pass 1 derives.
+template <int D>
+__global__ void shard_consts_kernel(const double* __restrict__ rows, int n_ranks, double a, double h,
+                                    double zero_cov_comp, double* __restrict__ consts, double* mirror, double tag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    constexpr int NM = 1 + D + D * D;
+    double out[NM];
+    for (int k = 0; k < NM; ++k) out[k] = rows[k];
+    for (int r = 1; r < n_ranks; ++r)
+        for (int k = 0; k < NM; ++k) out[k] += rows[r * NM + k];
+    double flags = 0.0, err = 0.0;
+    liu_west_consts<D>(out, a, h, zero_cov_comp, consts, flags, err);
+    if (mirror != nullptr) {
+        for (int k = 0; k < NM; ++k) mirror[k] = out[k];
+        mirror[29] = flags;
+        mirror[30] = err;
+        __threadfence_system();
+        *reinterpret_cast<volatile double*>(mirror + 31) = tag;
+    }
+}
+
+extern "C" int qb_lw_binned_shard_consts(const double* d_rows, int32_t n_ranks, int32_t d, double a, double h,
+                                         double zero_cov_comp, double* h_mirror, double tag, void* d_ws, size_t ws_bytes,
+                                         void* stream) {
+    QB_REQUIRE(d_rows && d_ws && n_ranks >= 1, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_shard_consts: bad arguments");
+    QB_REQUIRE(d >= 1 && d <= 4, QB_ERR_INVALID_ARGUMENT, "qb_lw_binned_shard_consts: needs 1 <= d <= 4, got %d", d);
+    QB_REQUIRE(ws_bytes >= 512, QB_ERR_WORKSPACE, "qb_lw_binned_shard_consts: workspace too small");
+    double* consts = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_ws) + 128);
+    cudaStream_t st = as_stream(stream);
+    switch (d) {
+        case 1: shard_consts_kernel<1><<<1, 32, 0, st>>>(d_rows, n_ranks, a, h, zero_cov_comp, consts, h_mirror, tag); break;
+        case 2: shard_consts_kernel<2><<<1, 32, 0, st>>>(d_rows, n_ranks, a, h, zero_cov_comp, consts, h_mirror, tag); break;
+        case 3: shard_consts_kernel<3><<<1, 32, 0, st>>>(d_rows, n_ranks, a, h, zero_cov_comp, consts, h_mirror, tag); break;
+        default: shard_consts_kernel<4><<<1, 32, 0, st>>>(d_rows, n_ranks, a, h, zero_cov_comp, consts, h_mirror, tag); break;
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}
+
 extern "C" int qb_binomial_sample(int64_t n, double p, int64_t count, uint64_t seed, uint64_t off, int64_t* d_out,
                                   void* stream) {
     QB_REQUIRE(d_out && count >= 1 && n >= 0, QB_ERR_INVALID_ARGUMENT, "qb_binomial_sample: bad arguments");

@@ -59,6 +59,7 @@ struct UpdateParams {
     int32_t n_ranks, rank;   // > 1: all-reduce the sums over the peers' mailboxes inside this launch
     double* peer_mbox[QB_MAX_RANKS];
     int32_t* error_flag;     // device int set to 1 if the peer wait timed out
+    double* shard_norms;     // pinned host block (or NULL): every rank's own sum w' of the last step + the tag
     ModelView mv;
     ExpView ev[KF_MAX];
     double meas[QB_MAX_D];   // tomography (single-step launches only)
@@ -237,7 +238,16 @@ __device__ void peer_allreduce(const UpdateParams& p, double* sums, double* scra
         }
         sums[threadIdx.x] = any_bad ? nan("") : t;
     }
+    if (p.shard_norms != nullptr && threadIdx.x < G) {
+        // the shard masses a following resample splits its offspring by: rank r's own sum w' of the last fused step
+        const int k = 3 * (p.nsteps - 1);
+        const unsigned int lo = scr[threadIdx.x * nw + 2 * k], hi = scr[threadIdx.x * nw + 2 * k + 1];
+        p.shard_norms[threadIdx.x] = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+        __threadfence_system();
+    }
     __syncthreads();
+    if (p.shard_norms != nullptr && threadIdx.x == 0)
+        *reinterpret_cast<volatile double*>(p.shard_norms + QB_MAX_RANKS) = any_bad ? -1.0 : p.tag;
 }
 
 // MLEModel's power is applied by the one-update kernels only (fused launches keep the plain likelihood and their
@@ -821,6 +831,7 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
     p.n_ranks = ctl ? ctl->n_ranks : 0;
     p.rank = ctl ? ctl->rank : 0;
     p.error_flag = ctl ? ctl->d_error_flag : nullptr;
+    p.shard_norms = (ctl && ctl->n_ranks > 1) ? ctl->h_shard_norms : nullptr;
     QB_REQUIRE(p.mirror == nullptr || (reinterpret_cast<uintptr_t>(p.mirror) & 31) == 0, QB_ERR_INVALID_ARGUMENT,
                "qb_fused_update: the host mirror must be 32-byte aligned");
     QB_REQUIRE(p.n_ranks <= QB_MAX_RANKS, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: at most %d ranks", QB_MAX_RANKS);

@@ -6,7 +6,7 @@ fails this module raises, loudly.
 import ctypes
 import os
 
-QB_ABI_VERSION = 3
+QB_ABI_VERSION = 4
 QB_MAX_D = 64
 QB_MAX_RANKS = 16
 QB_IPC_HANDLE_BYTES = 64
@@ -40,7 +40,8 @@ class QbUpdateCtl(ctypes.Structure):
     _fields_ = [("h_mirror", ctypes.c_void_p), ("tag", ctypes.c_double), ("zero_weight_thresh", ctypes.c_double),
                 ("resample_below", ctypes.c_double), ("guard", ctypes.c_int32), ("check_resample", ctypes.c_int32),
                 ("chain_prev_tag", ctypes.c_double), ("n_ranks", ctypes.c_int32), ("rank", ctypes.c_int32),
-                ("d_peer_mailbox", ctypes.c_void_p * QB_MAX_RANKS), ("d_error_flag", ctypes.c_void_p)]
+                ("d_peer_mailbox", ctypes.c_void_p * QB_MAX_RANKS), ("d_error_flag", ctypes.c_void_p),
+                ("h_shard_norms", ctypes.c_void_p)]
 
 
 class QbError(RuntimeError):
@@ -108,6 +109,7 @@ SIGNATURES = {
                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _P, _I64, _P, _P, _P, _P, _P]),
     "qb_lw_binned_workspace_bytes": (_SZ, [_I64, _I64]),
     "qb_lw_binned_sums": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _F64, _P, _SZ, _P]),
+    "qb_lw_binned_shard_consts": (ctypes.c_int, [_P, _I32, _I32, _F64, _F64, _F64, _P, _F64, _P, _SZ, _P]),
     "qb_lw_binned_count": (ctypes.c_int, [_I64, _I64, _U64, _U64, _I32, _P, _SZ, _P]),
     "qb_binomial_sample": (ctypes.c_int, [_I64, _F64, _I64, _U64, _U64, _P, _P]),
     "qb_lw_binned_prepare": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _I64, _U64, _U64, _I32, _P, _P, _F64, _P, _SZ,

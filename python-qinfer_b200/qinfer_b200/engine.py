@@ -97,6 +97,8 @@ class DeviceCloud(object):
         # one control block per destination slot: the constant fields are written once
         self._ctls = [_lib.QbUpdateCtl(), _lib.QbUpdateCtl()]
         self._ctl_key = None
+        self._shard_norms = None           # sharded clouds: pinned [2 slots][QB_MAX_RANKS + 1] per-rank sums + tag
+        self._slot_tag = [0, 0]            # tag of the update launch whose output weights buffer [slot] still holds
         self._refresh_ptrs()
         self._chain_tag = 0                # tag of the fused update that was the LAST thing queued for this cloud
         self._chain_dst = -1               # ... and the weights/stats buffer it wrote
@@ -175,6 +177,7 @@ class DeviceCloud(object):
         if w.shape != (self.n,):
             raise ValueError("particle_weights must have shape (%d,), got %s" % (self.n, w.shape))
         self.w.copy_(torch.from_numpy(w))
+        self._slot_tag = [0, 0]
         check(self.lib.qb_weights_restat(_ptr(self.w), self.n, _ptr(self.stats), _ptr(self.ws), self.ws_bytes,
                                          _stream()))
         self.launches += 2
@@ -190,6 +193,7 @@ class DeviceCloud(object):
         n_global = self.n if n_global is None else int(n_global)
         check(self.lib.qb_weights_set_uniform_global(_ptr(self.w), self.n, n_global, _ptr(self.stats), _stream()))
         self.launches += 1
+        self._slot_tag = [0, 0]
 
     def read_stats(self, which=None):
         """Blocking read of a stats block (norm, sumsq, min, nbad, inv_norm, n_ess)."""
@@ -215,6 +219,8 @@ class DeviceCloud(object):
             for slot, c in enumerate(self._ctls):
                 ctypes.memmove(ctypes.byref(c), ctypes.byref(self._ctl), ctypes.sizeof(_lib.QbUpdateCtl))
                 c.h_mirror = self.mirror.data_ptr() + slot * MIRROR_SLOT * 8
+                c.h_shard_norms = (self._shard_norms.data_ptr() + slot * (_lib.QB_MAX_RANKS + 1) * 8
+                                   if self._shard_norms is not None else None)
                 c.zero_weight_thresh = zero_weight_thresh
                 c.resample_below = resample_below
             self._ctl_key = key
@@ -249,7 +255,26 @@ class DeviceCloud(object):
         self.launches += 1
         self.update_launches += 1
         self._chain_tag, self._chain_dst = self._tag, dst
+        self._slot_tag[dst] = self._tag
         return self._tag
+
+    def enable_shard_norms(self):
+        """Sharded clouds: every update launch also publishes each rank's own sum w' (the shard masses)."""
+        if self._shard_norms is None:
+            self._shard_norms = torch.zeros((2 * (_lib.QB_MAX_RANKS + 1),), dtype=torch.float64, pin_memory=True)
+            self._shard_norms_np = self._shard_norms.numpy()
+            self._ctl_key = None
+
+    def shard_masses(self, n_ranks):
+        """Per-rank sums of the committed weights buffer as the update launch that wrote it published them (identical
+        on every rank), or None when the buffer has been written by anything else since."""
+        tag = self._slot_tag[self.cur]
+        if self._shard_norms is None or not tag:
+            return None
+        row = self._shard_norms_np[self.cur * (_lib.QB_MAX_RANKS + 1):(self.cur + 1) * (_lib.QB_MAX_RANKS + 1)]
+        if row[_lib.QB_MAX_RANKS] != float(tag):
+            return None
+        return row[:n_ranks].copy()
 
     @nvtx_range('qb.cloud.wait_stats')
     def wait_stats(self, slot, tag, nsteps=1, timeout_s=120.0):
@@ -298,6 +323,7 @@ class DeviceCloud(object):
         """smc.py:416-418 on weights buffer ``slot`` (normalise, clip to [0,1], re-derive its stats)."""
         check(self.lib.qb_weights_clip(_ptr(self._w[slot]), self.n, _ptr(self._stats[slot]), _ptr(self.ws),
                                        self.ws_bytes, _stream()))
+        self._slot_tag = [0, 0]
         self.launches += 2
         return self.read_stats(self._stats[slot])
 
@@ -561,14 +587,27 @@ class DeviceCloud(object):
         """(covariance flag, sqrtm error) published with the moments of the last ``binned_resample``."""
         return int(self._bin_mirror_np[29]), float(self._bin_mirror_np[30])
 
-    def binned_sums(self):
+    def binned_sums(self, mirror=True):
         """Pass 1 alone (sharded clouds: the shard masses decide this slab's offspring count)."""
         self._binned_scratch(self.n)
         self._bin_tag += 1
         check(self.lib.qb_lw_binned_sums(_ptr(self.x), _ptr(self.w), _ptr(self.stats), self.n, self.d,
-                                         _ptr(self.moments_out), ctypes.c_void_p(self._bin_mirror.data_ptr()),
+                                         _ptr(self.moments_out),
+                                         ctypes.c_void_p(self._bin_mirror.data_ptr()) if mirror else None,
                                          float(self._bin_tag), _ptr(self._bin_ws), self._bin_ws.numel() * 8,
                                          _stream()))
+        self.launches += 1
+        return self._bin_tag
+
+    def binned_shard_consts(self, rows, n_ranks, a, h, zero_cov_comp):
+        """Sharded clouds: global moments (``rows`` = the all-gathered moment sums, device) and the Liu-West constants
+        derived on the device; a following ``binned_move(None, None, ...)`` uses them.  Returns the tag
+        ``binned_moments_wait`` / ``binned_flags`` poll for."""
+        self._bin_tag += 1
+        check(self.lib.qb_lw_binned_shard_consts(_ptr(rows), int(n_ranks), self.d, float(a), float(h),
+                                                 float(zero_cov_comp), ctypes.c_void_p(self._bin_mirror.data_ptr()),
+                                                 float(self._bin_tag), _ptr(self._bin_ws), self._bin_ws.numel() * 8,
+                                                 _stream()))
         self.launches += 1
         return self._bin_tag
 
@@ -696,6 +735,7 @@ class DeviceCloud(object):
         self._swap_slabs(n_new)
         self.cur = 1 - self.cur
         self._chain_tag = 0
+        self._slot_tag = [0, 0]
 
     def read_counter(self):
         self.counter_host.copy_(self.counter[:2], non_blocking=True)
@@ -749,6 +789,7 @@ class DeviceCloud(object):
         self.x_alt = None
         self._w = [b[:n_new] for b in self._w_back]
         self._chain_tag = 0
+        self._slot_tag = [0, 0]
 
     def adopt_resampled(self, n_new, n_global=None):
         """Make the freshly written slab current; weights become uniform."""

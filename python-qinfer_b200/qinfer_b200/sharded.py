@@ -568,6 +568,7 @@ def _make_sharded_updater_class():
                 if self._mail is None:
                     self._mail = PeerMailboxes(self._comm)
                 self._mail.install(self._cloud._ctl)
+                self._cloud.enable_shard_norms()      # every update publishes the shard masses a resample splits by
             self._ops = _DeviceOps(self._cloud, self._comm.world)
 
         def close(self):
@@ -913,6 +914,11 @@ def _make_sharded_updater_class():
             res, cloud, comm = self.resampler, self._cloud, self._comm
             r, d = comm.rank, cloud.d
             cloud._binned_scratch(cloud.capacity)                # (re-allocation zeroes the workspace: before pass 1)
+            masses = cloud.shard_masses(comm.world) if comm.world > 1 else None
+            if masses is not None:
+                cloud.binned_sums(mirror=False)                  # (pass 1 needs nothing from the host: queue it first)
+                if self._queued_split_pass(masses):
+                    return True
             cloud.binned_sums()
             rows = comm.all_gather_rows(cloud.moments_out)       # one collective, one host read
             out = rows[0].copy()
@@ -966,6 +972,58 @@ def _make_sharded_updater_class():
             self.last_exchange = (extra, cap[r] - keep)
             res.last_n_iters = iters
             return False
+
+        def _queued_split_pass(self, masses):
+            """The floating-slab resample with NO host round trip between its launches.  The shard masses came with the
+            last update's in-kernel all-reduce (every rank's own sum w', identical on every rank), so the split m is
+            drawn BEFORE anything is queued; then pass 1, the all-gather of the moment sums (device to device), the
+            kernel that sums them in rank order and derives the Liu-West constants, the counts, the move and the first
+            retry launch go out back to back (pass 1 has been queued by the caller) and the host waits once — its checks (finite / PSD / zero-norm warnings)
+            read the published global moments while the device is already drawing.  False: the split does not fit
+            the slabs' capacities (the caller then runs the exchange path; the shared generator has advanced on every
+            rank alike)."""
+            res, cloud, comm = self.resampler, self._cloud, self._comm
+            r, d = comm.rank, cloud.d
+            m = split_counts(self._split_rng, self._n_global, masses)
+            caps = [self._slab_capacity(c) for c in self._base_counts]
+            if not all(1 <= m[q] <= caps[q] for q in range(comm.world)):
+                return False
+            cloud._alt_slab(m[r])
+            width = 1 + d + d * d
+            rows = getattr(self, '_moment_rows', None)
+            if rows is None or rows.numel() != comm.world * width:
+                rows = self._moment_rows = torch.empty((comm.world * width,), dtype=torch.float64, device=cloud.device)
+            comm.dist.all_gather_into_tensor(rows, cloud.moments_out[:width], group=comm.group)
+            tag = cloud.binned_shard_consts(rows, comm.world, res._a, res._h, res._zero_cov_comp)
+            off_u, off_v = res._binned_offsets(m[r])
+            cloud.binned_count(m[r], self._stream_seed, off_u)
+            seed = self._stream_seed
+            seed_n = seed ^ 0x9E3779B97F4A7C15
+            stride, off_n, rounds = res._binned_plan(d, m[r])
+            tags = cloud.binned_move(None, None, res._a, seed, off_v, seed_n, off_n, m[r], res._postselect,
+                                     dst=cloud.x_alt, fuse_weights=True, n_global=self._n_global,
+                                     retry_rounds=rounds, own_mean=res._own_mean)
+            mtag = tags[0] if rounds else tags
+            # the reference's checks on the global moments (distributions.py:388-397, resamplers.py:288-299)
+            _, mean, m2 = cloud.binned_moments_wait(tag)
+            flag, s_err = cloud.binned_flags()
+            _cov_1x1(mean, m2) if d == 1 else covariance_from_moments(mean, m2)
+            if flag == 1:
+                warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
+                              "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
+            if not np.isfinite(s_err):
+                raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
+                                     "Check that n_ess is not too small.")
+            iters, bad = res._binned_finish(cloud, mtag, rounds, stride, None, None, res._a, m[r], seed_n,
+                                            dst=cloud.x_alt, seed_v=seed)
+            if bad:
+                warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
+                               "iterations.").format(bad, res._maxiter), ResamplerWarning)
+            self._shard_masses = np.asarray(masses, dtype=np.float64)
+            self._layout.set_counts(m)
+            self.last_exchange = (0, 0)
+            res.last_n_iters = iters
+            return True
 
         def _finish_resample(self, ev, weights_fused=False):
             cloud = self._cloud

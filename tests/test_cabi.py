@@ -35,7 +35,7 @@ def test_binding_covers_every_declared_symbol_and_loads():
     from qinfer_b200 import _lib
     assert sorted(_lib.SIGNATURES) == _declared_symbols()
     lib = _lib.load()
-    assert lib.qb_abi_version() == _lib.QB_ABI_VERSION == 3
+    assert lib.qb_abi_version() == _lib.QB_ABI_VERSION == 4
 
 
 def test_struct_layouts_match_the_header():
@@ -47,7 +47,7 @@ def test_struct_layouts_match_the_header():
     _lib.load().qb_struct_sizes(sizes)                       # what the C compiler actually laid out
     assert list(sizes) == [ctypes.sizeof(_lib.QbModel), ctypes.sizeof(_lib.QbExpparams),
                            ctypes.sizeof(_lib.QbUpdateCtl)]
-    assert ctypes.sizeof(_lib.QbUpdateCtl) == 56 + 8 * _lib.QB_MAX_RANKS + 8
+    assert ctypes.sizeof(_lib.QbUpdateCtl) == 56 + 8 * _lib.QB_MAX_RANKS + 8 + 8     # + h_shard_norms (ABI 4)
 
 
 def test_argument_validation_without_a_gpu():
