@@ -501,6 +501,25 @@ int qb_weight_mass_hist(const double* d_w, const double* d_stats, int64_t n, int
 int qb_weights_select(const double* d_w, const double* d_stats, int64_t n, uint64_t tau_bits, int32_t mode,
                       uint8_t* d_flags, void* stream);
 
+/* ---- small clouds, parity mode: the first Liu-West pass in ONE single-CTA launch --------------------------------- */
+/* For n_old <= QB_SMALL_MAX, d <= 4 (the reference's own CPU-sized runs, BASELINE config C1, are launch-latency bound
+ * on a GPU).  One CTA: moments -> covariance / zero-norm replacement / matrix square root (as qb_lw_binned_resample's
+ * pass 1) -> np.cumsum of the normalised weights, sequential fp64 (resamplers.py:308) -> d_js[i] =
+ * min(searchsorted(cdf, d_u[i], 'right'), n_old - 1) (resamplers.py:318-321) -> x_new[i] = a x[js[i]] + (1 - a) mean +
+ * S eps[:, i] (resamplers.py:325-332; d_eps is (d, n_new) row-major) -> d_invalid flags, d_counters[0] = their count,
+ * d_counters[1] = clamped draws -> optionally the uniform weights 1 / n_new and their stats block.  d_u / d_eps are the
+ * HOST-drawn legacy variates (np.random), uploaded by the caller.  The retry iterations use qb_compact_invalid +
+ * qb_lw_retry on the same buffers.  h_mirror (pinned, 64 doubles, 32-byte aligned): [0..) moments, [29] covariance
+ * flag, [30] sqrtm error, [31] tag | [32] invalid, [33] clamped, [34] n_new, [35] tag | [40..56) S (times h),
+ * [56..60) (1 - a) mean. */
+#define QB_SMALL_MAX 4096
+int qb_lw_small_resample(const qb_model* model, const double* d_x, const double* d_w, const double* d_stats,
+                         int64_t n_old, int32_t d, double a, double h, double zero_cov_comp,
+                         const double* d_u, const double* d_eps, int64_t n_new, double* d_x_new,
+                         int64_t* d_js, uint8_t* d_invalid, int64_t* d_counters, double* d_w_new /* may be NULL */,
+                         double* d_stats_new /* may be NULL */, int32_t postselect, double* d_moments_out /* may be NULL */,
+                         double* h_mirror, double tag, void* stream);
+
 /* ---- time-dependent and noisy decorators ------------------------------------------------------- */
 /* Model.update_timestep for the random-walk decorators, in place after an update has been committed (smc.py:447-449).
  * For each particle i and each of the n_rw walking parameters c (HOST arrays of n_rw entries):

@@ -1650,3 +1650,245 @@ extern "C" int qb_lw_binned_resample(const qb_model* model, const double* d_x, c
                              d_x_new, n_new, nullptr, d_w_new, n_global, d_stats_new, postselect, retry_rounds, own_mean,
                              d_list, d_parents, nullptr, h_mirror + 32, tag, d_ws, ws_bytes, stream);
 }
+
+// =====================================================================================================================
+// Small clouds (n <= QB_SMALL_MAX), parity mode: the WHOLE first Liu-West pass in ONE single-CTA launch.
+// A cloud of 10^3 particles (the reference's own CPU-sized runs, BASELINE config C1) is launch-latency bound: the
+// staged parity path costs ~15 launches and 3 host round trips per resample.  Here one CTA holds the weights in shared
+// memory and does, in order: moments (block reduction) -> covariance, zero-norm replacement, matrix square root
+// (liu_west_consts, as pass 1 of the binned resample) -> np.cumsum of the normalised weights by ONE lane, strictly
+// sequential fp64 (resamplers.py:308) -> js = min(searchsorted(cdf, u, 'right'), n - 1) for the HOST-drawn uniforms
+// (resamplers.py:318-321; the legacy np.random stream stays on the host, where it is cheapest at this size) ->
+// mu = a x[js] + (1 - a) mean, x' = mu + S eps for the host-drawn normals (resamplers.py:325-332, the arithmetic of
+// lw_move_small_kernel) -> validity flags and their count -> uniform weights + their stats block.  The retry
+// iterations (rare) go through the staged kernels, which find js, the flags and the count where they expect them.
+// =====================================================================================================================
+constexpr int SMALL_MAX = QB_SMALL_MAX;
+constexpr int SMALL_THREADS = 1024;
+
+struct SmallParams {
+    const double* x;
+    const double* w;
+    const double* stats;
+    const double* u;        // n_new uniforms
+    const double* eps;      // (d, n_new) row-major normals
+    double* x_new;
+    int64_t* js;
+    uint8_t* invalid;
+    unsigned long long* counters;   // [0] invalid, [1] clamped draws
+    double* w_new;          // may be NULL
+    double* stats_new;      // may be NULL
+    double* moments_out;    // may be NULL (device copy of the moments)
+    double* mirror;         // pinned: [0..) moments, [29] flag, [30] err, [31] tag | [32] invalid, [33] clamped, [34] n_new,
+                            // [35] tag | [40..56) S (scaled by h), [56..60) (1 - a) mean
+    double tag;
+    int32_t n_old, n_new, postselect, pad;
+    double a, h, zero_cov_comp;
+    ModelView mv;
+};
+
+template <int D>
+__global__ void __launch_bounds__(SMALL_THREADS) lw_small_resample_kernel(const __grid_constant__ SmallParams p) {
+    constexpr int NOUT = 1 + D + D * (D + 1) / 2;
+    constexpr int NW = SMALL_THREADS / 32;
+    __shared__ double cdf[SMALL_MAX];
+    __shared__ double red[NW * NOUT];
+    __shared__ double consts[20];
+    __shared__ unsigned int s_bad, s_over;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = p.n_old;
+    const double inv = p.stats[QB_STAT_INV_NORM];
+    if (tid == 0) {
+        s_bad = 0u;
+        s_over = 0u;
+    }
+    // ---- normalised weights into shared memory + moment sums ----
+    double acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = 0.0;
+    for (int i = tid; i < n; i += SMALL_THREADS) {
+        const double wv = p.w[i] * inv;
+        cdf[i] = wv;
+        double xv[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) xv[c] = p.x[static_cast<size_t>(i) * D + c];
+        acc[0] += wv;
+        int o = 1 + D;
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            const double wx = wv * xv[m];
+            acc[1 + m] += wx;
+#pragma unroll
+            for (int c = m; c < D; ++c) acc[o++] += wx * xv[c];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) red[wid * NOUT + k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // finished moments (fixed order) and the Liu-West constants
+        double out[1 + D + D * D];
+        double fin[NOUT];
+        for (int k = 0; k < NOUT; ++k) {
+            double v = 0.0;
+            for (int q = 0; q < NW; ++q) v += red[q * NOUT + k];
+            fin[k] = v;
+        }
+        out[0] = fin[0];
+#pragma unroll
+        for (int m = 0; m < D; ++m) out[1 + m] = fin[1 + m];
+        int o = 1 + D;
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+#pragma unroll
+            for (int c = m; c < D; ++c) {
+                out[1 + D + m * D + c] = fin[o];
+                out[1 + D + c * D + m] = fin[o];
+                ++o;
+            }
+        double flags = 0.0, err = 0.0;
+        liu_west_consts<D>(out, p.a, p.h, p.zero_cov_comp, consts, flags, err);
+        if (p.moments_out != nullptr)
+            for (int k = 0; k < 1 + D + D * D; ++k) p.moments_out[k] = out[k];
+        for (int k = 0; k < 1 + D + D * D; ++k) p.mirror[k] = out[k];
+        for (int k = 0; k < 20; ++k) p.mirror[40 + k] = consts[k];
+        p.mirror[29] = flags;
+        p.mirror[30] = err;
+        __threadfence_system();
+        *reinterpret_cast<volatile double*>(p.mirror + 31) = p.tag;   // the host starts its checks now
+    } else if (tid == 32) {
+        // np.cumsum, one lane, in place (the other warps wait at the barrier)
+        double run = cdf[0];
+        for (int i = 1; i < n; ++i) {
+            run = run + cdf[i];
+            cdf[i] = run;
+        }
+    }
+    __syncthreads();
+    double S[D * D], ms[D];
+#pragma unroll
+    for (int j = 0; j < D * D; ++j) S[j] = consts[j];
+#pragma unroll
+    for (int c = 0; c < D; ++c) ms[c] = consts[16 + c];
+    // ---- draw + move + validity ----
+    const int n_new = p.n_new;
+    const int nround = ((n_new + 31) / 32) * 32;
+    const double w_value = 1.0 / static_cast<double>(n_new);
+    for (int i = tid; i < nround; i += SMALL_THREADS) {
+        const bool live = i < n_new;
+        bool ok = true, over = false;
+        if (live) {
+            const double u = p.u[i];
+            int lo = 0, hi = n;
+            while (lo < hi) {                       // searchsorted(..., side='right')
+                const int mid = (lo + hi) >> 1;
+                if (u < cdf[mid]) hi = mid; else lo = mid + 1;
+            }
+            if (lo >= n) {
+                lo = n - 1;
+                over = true;
+            }
+            p.js[i] = lo;
+            double xv[D], ev[D], out[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) xv[c] = p.x[static_cast<size_t>(lo) * D + c];
+#pragma unroll
+            for (int m = 0; m < D; ++m) ev[m] = p.eps[static_cast<size_t>(m) * n_new + i];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double z = 0.0;
+#pragma unroll
+                for (int m = 0; m < D; ++m) z = fma(S[c * D + m], ev[m], z);
+                out[c] = ((p.a * xv[c]) + ms[c]) + z;   // resamplers.py:325,332, one rounding per ufunc
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) p.x_new[static_cast<size_t>(i) * D + c] = out[c];
+            if (p.postselect) {
+                auto row = [&](int c) { return out[c]; };
+                ok = model_valid(p.mv, row);
+            }
+            p.invalid[i] = ok ? 0 : 1;
+            if (p.w_new != nullptr) p.w_new[i] = w_value;
+        }
+        const unsigned int bad = __ballot_sync(0xffffffffu, live && !ok);
+        const unsigned int ovr = __ballot_sync(0xffffffffu, live && over);
+        if (lane == 0) {
+            if (bad) atomicAdd(&s_bad, static_cast<unsigned int>(__popc(bad)));
+            if (ovr) atomicAdd(&s_over, static_cast<unsigned int>(__popc(ovr)));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        p.counters[0] = s_bad;
+        p.counters[1] = s_over;
+        if (p.stats_new != nullptr) {     // resamplers.py:390-392: weights 1/n; the stats block of set_uniform_kernel
+            double* st = p.stats_new;
+            st[QB_STAT_NORM] = 1.0;
+            st[QB_STAT_SUMSQ] = w_value;
+            st[QB_STAT_MIN] = w_value;
+            st[QB_STAT_NBAD] = 0.0;
+            st[QB_STAT_INV_NORM] = 1.0;
+            st[QB_STAT_NESS] = static_cast<double>(n_new);
+            st[QB_STAT_TAG] = 0.0;
+            st[QB_STAT_SKIPPED] = 0.0;
+            st[QB_STAT_ATTN] = 0.0;
+        }
+        p.mirror[32] = static_cast<double>(s_bad);
+        p.mirror[33] = static_cast<double>(s_over);
+        p.mirror[34] = static_cast<double>(n_new);
+        __threadfence_system();
+        *reinterpret_cast<volatile double*>(p.mirror + 35) = p.tag;
+    }
+}
+
+extern "C" int qb_lw_small_resample(const qb_model* model, const double* d_x, const double* d_w, const double* d_stats,
+                                    int64_t n_old, int32_t d, double a, double h, double zero_cov_comp,
+                                    const double* d_u, const double* d_eps, int64_t n_new, double* d_x_new,
+                                    int64_t* d_js, uint8_t* d_invalid, int64_t* d_counters, double* d_w_new,
+                                    double* d_stats_new, int32_t postselect, double* d_moments_out, double* h_mirror,
+                                    double tag, void* stream) {
+    int rc = validate_model(model);
+    if (rc != QB_OK) return rc;
+    QB_REQUIRE(d_x && d_w && d_stats && d_u && d_eps && d_x_new && d_js && d_invalid && d_counters && h_mirror,
+               QB_ERR_INVALID_ARGUMENT, "qb_lw_small_resample: NULL pointer argument");
+    QB_REQUIRE(d == model->d && d >= 1 && d <= 4, QB_ERR_INVALID_ARGUMENT, "qb_lw_small_resample: needs 1 <= d <= 4");
+    QB_REQUIRE(n_old >= 1 && n_old <= SMALL_MAX && n_new >= 1 && n_new < (1LL << 30), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_small_resample: needs 1 <= n_old <= %d (got %lld)", SMALL_MAX, static_cast<long long>(n_old));
+    QB_REQUIRE((d_w_new == nullptr) == (d_stats_new == nullptr), QB_ERR_INVALID_ARGUMENT,
+               "qb_lw_small_resample: pass both d_w_new and d_stats_new, or neither");
+    SmallParams p;
+    p.x = d_x;
+    p.w = d_w;
+    p.stats = d_stats;
+    p.u = d_u;
+    p.eps = d_eps;
+    p.x_new = d_x_new;
+    p.js = d_js;
+    p.invalid = d_invalid;
+    p.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    p.w_new = d_w_new;
+    p.stats_new = d_stats_new;
+    p.moments_out = d_moments_out;
+    p.mirror = h_mirror;
+    p.tag = tag;
+    p.n_old = static_cast<int32_t>(n_old);
+    p.n_new = static_cast<int32_t>(n_new);
+    p.postselect = postselect ? 1 : 0;
+    p.pad = 0;
+    p.a = a;
+    p.h = h;
+    p.zero_cov_comp = zero_cov_comp;
+    p.mv = make_model_view(*model);
+    cudaStream_t st = as_stream(stream);
+    switch (d) {
+        case 1: lw_small_resample_kernel<1><<<1, SMALL_THREADS, 0, st>>>(p); break;
+        case 2: lw_small_resample_kernel<2><<<1, SMALL_THREADS, 0, st>>>(p); break;
+        case 3: lw_small_resample_kernel<3><<<1, SMALL_THREADS, 0, st>>>(p); break;
+        default: lw_small_resample_kernel<4><<<1, SMALL_THREADS, 0, st>>>(p); break;
+    }
+    QB_CUDA_CHECK(cudaGetLastError());
+    return QB_OK;
+}

@@ -7,6 +7,7 @@ import ctypes
 import os
 
 QB_ABI_VERSION = 4
+QB_SMALL_MAX = 4096
 QB_MAX_D = 64
 QB_MAX_RANKS = 16
 QB_IPC_HANDLE_BYTES = 64
@@ -109,6 +110,8 @@ SIGNATURES = {
                                          ctypes.POINTER(_F64), _F64, _U64, _U64, _P, _I64, _P, _P, _P, _P, _P]),
     "qb_lw_binned_workspace_bytes": (_SZ, [_I64, _I64]),
     "qb_lw_binned_sums": (ctypes.c_int, [_P, _P, _P, _I64, _I32, _P, _P, _F64, _P, _SZ, _P]),
+    "qb_lw_small_resample": (ctypes.c_int, [ctypes.POINTER(QbModel), _P, _P, _P, _I64, _I32, _F64, _F64, _F64, _P, _P, _I64,
+                                            _P, _P, _P, _P, _P, _P, _I32, _P, _P, _F64, _P]),
     "qb_lw_binned_shard_consts": (ctypes.c_int, [_P, _I32, _I32, _F64, _F64, _F64, _P, _F64, _P, _SZ, _P]),
     "qb_lw_binned_count": (ctypes.c_int, [_I64, _I64, _U64, _U64, _I32, _P, _SZ, _P]),
     "qb_binomial_sample": (ctypes.c_int, [_I64, _F64, _I64, _U64, _U64, _P, _P]),

@@ -583,6 +583,48 @@ class DeviceCloud(object):
         self.launches += 4 if rounds else 3
         return tag
 
+    # ---- small clouds, parity mode: one single-CTA launch --------------------------------------------------------
+    def small_supported(self, n_new):
+        return self.d <= 4 and self.n <= _lib.QB_SMALL_MAX and n_new <= 4 * _lib.QB_SMALL_MAX
+
+    def small_resample(self, u, eps, n_new, a, h, zero_cov_comp, postselect, fuse_weights):
+        """Queue the whole first Liu-West pass of a small cloud (csrc/qb_binned.cu, lw_small_resample_kernel) on the
+        HOST-drawn variates ``u`` (n_new,) and ``eps`` (d, n_new): ONE pinned staging copy, ONE launch.  Returns the
+        tag ``binned_moments_wait`` / ``binned_flags`` / ``binned_counters_wait`` poll for; ``small_consts`` then
+        gives the constants the device used (for the staged retry kernels)."""
+        n_new, d = int(n_new), self.d
+        self._resample_scratch(n_new)
+        self._alt_slab(n_new)
+        if self._bin_mirror is None:
+            self._bin_mirror = torch.zeros((64,), dtype=torch.float64, pin_memory=True)
+            self._bin_mirror_np = self._bin_mirror.numpy()
+        stage = getattr(self, '_small_stage', None)
+        if stage is None or stage.numel() < (1 + d) * n_new:
+            self._small_stage = stage = torch.empty(((1 + d) * n_new,), dtype=torch.float64, pin_memory=True)
+            self._small_stage_np = stage.numpy()
+            self._small_dev = torch.empty(((1 + d) * n_new,), dtype=torch.float64, device=self.device)
+        sn = self._small_stage_np
+        sn[:n_new] = u
+        sn[n_new:(1 + d) * n_new] = eps.reshape(-1)
+        dev = self._small_dev
+        dev[:(1 + d) * n_new].copy_(stage[:(1 + d) * n_new], non_blocking=True)
+        self._bin_tag += 1
+        tag = self._bin_tag
+        base = dev.data_ptr()
+        check(self.lib.qb_lw_small_resample(
+            self.lib_model, self.x.data_ptr(), self.w.data_ptr(), self.stats.data_ptr(), self.n, d, float(a), float(h),
+            float(zero_cov_comp), base, base + 8 * n_new, n_new, self.x_alt.data_ptr(), self._js.data_ptr(),
+            self._invalid.data_ptr(), self.counter.data_ptr(), self.w_alt.data_ptr() if fuse_weights else None,
+            self.stats_alt.data_ptr() if fuse_weights else None, 1 if postselect else 0, self.moments_out.data_ptr(),
+            self._bin_mirror.data_ptr(), float(tag), _stream()))
+        self.launches += 1
+        return tag
+
+    def small_consts(self):
+        """(S (d, d) scaled by h) the last ``small_resample`` derived on the device (valid after its moments tag)."""
+        d = self.d
+        return self._bin_mirror_np[40:40 + d * d].reshape(d, d).copy()
+
     def binned_flags(self):
         """(covariance flag, sqrtm error) published with the moments of the last ``binned_resample``."""
         return int(self._bin_mirror_np[29]), float(self._bin_mirror_np[30])

@@ -146,6 +146,7 @@ class LiuWestResampler(Resampler):
         # the weighted cloud — the LAW of the reference's loop, whose `mus = mus[:k]` (resamplers.py:372) pairs the
         # r-th invalid particle with the r-th original draw; True keeps the particle's own parent (textbook Liu-West)
         self._own_mean = False
+        self._small = True      # parity mode: clouds of <= QB_SMALL_MAX particles resample in one single-CTA launch
 
     @property
     def a(self):
@@ -332,6 +333,41 @@ class LiuWestResampler(Resampler):
                                  "Check that n_ess is not too small.")
         return self._binned_finish(cloud, tag, rounds, stride, None, None, self._a, n_particles, seed_n, seed_v=seed)
 
+    def _small_pass(self, cloud, n_particles, fuse_weights):
+        """Parity mode on a small cloud (<= QB_SMALL_MAX particles, d <= 4): the legacy variates are drawn HERE, by
+        np.random itself, in the reference's order (uniforms, resamplers.py:319, then kernel(n_rvs, n), :332), and ONE
+        single-CTA launch does moments, constants, np.cumsum, searchsorted, shrink + perturb and the validity test.
+        The host performs the reference's checks on the published moments; the retry iterations (rare) run through
+        the staged kernels."""
+        d = cloud.d
+        u = np.random.random((n_particles,))
+        eps = np.ascontiguousarray(self._kernel(d, n_particles), dtype=np.float64)
+        if eps.shape != (d, n_particles):
+            raise ValueError("resampling kernel returned shape %s, expected %s" % (eps.shape, (d, n_particles)))
+        tag = cloud.small_resample(u, eps, n_particles, self._a, self._h, self._zero_cov_comp, self._postselect,
+                                   fuse_weights)
+        _, mean, m2 = cloud.binned_moments_wait(tag)
+        flag, s_err = cloud.binned_flags()
+        _cov_1x1(mean, m2) if d == 1 else covariance_from_moments(mean, m2)          # (finite assert, PSD warning)
+        if flag == 1:
+            warnings.warn("Covariance has zero norm; adding in small covariance in resampler. "
+                          "Consider increasing n_particles to improve covariance estimates.", ResamplerWarning)
+        if not np.isfinite(s_err):
+            raise ResamplerError("Infinite error in computing the square root of the covariance matrix. "
+                                 "Check that n_ess is not too small.")
+        S = cloud.small_consts()
+        n_invalid, self.last_overflow, _ = cloud.binned_counters_wait(tag)
+        n_iters = 1
+        if not self._postselect:
+            n_invalid = 0
+        while n_invalid and n_iters < self._maxiter:
+            n_iters += 1
+            cloud.compact_invalid(n_particles)
+            k_eps = self._normals(cloud, d, n_invalid)
+            cloud.lw_retry(mean, S, self._a, k_eps, n_invalid)
+            n_invalid, _ = cloud.read_counter()
+        return n_iters, n_invalid
+
     def _binned_return(self, cloud, on_device, n_particles, n_iters, n_invalid, weights_fused):
         if n_invalid:
             warnings.warn(("Liu-West resampling failed to find valid models for {} particles within {} "
@@ -363,6 +399,12 @@ class LiuWestResampler(Resampler):
         binned = device_rng and self._draw in ('auto', 'binned') and cloud.binned_supported(n_particles)
         fused = device_rng and not binned and cloud.d <= 4 and n_particles <= cloud.n
         cdf_done = False
+        small = (self._small and self._rng in ('numpy', 'mt19937') and self._scan == 'exact'
+                 and precomputed_mean is None and precomputed_cov is None and cloud.small_supported(n_particles))
+        if small:
+            weights_fused = on_device and n_particles == cloud.n
+            n_iters, n_invalid = self._small_pass(cloud, n_particles, weights_fused)
+            return self._binned_return(cloud, on_device, n_particles, n_iters, n_invalid, weights_fused)
         if binned and precomputed_mean is None and precomputed_cov is None:
             weights_fused = on_device and n_particles == cloud.n
             n_iters, n_invalid = self._binned_device(cloud, n_particles, weights_fused)

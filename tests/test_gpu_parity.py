@@ -439,6 +439,71 @@ def test_t5_liu_west_events_tomography(qb, golden):
                                               0.98))
 
 
+@pytest.mark.parametrize("kind,n", [("precession", 1000), ("precession", 4096), ("rb", 3000)])
+def test_t5_small_cloud_single_launch_resample_equals_the_oracle(qb, kind, n):
+    """Parity mode on a small cloud (qb_lw_small_resample: ONE single-CTA launch on host-drawn np.random variates):
+    resample indices bit-identical to the oracle's (np.cumsum + searchsorted), locations 1e-12, the same number of
+    retry iterations, and the legacy stream left at the same position; and identical to the staged launches."""
+    import smc_oracle as oracle
+    rs = np.random.RandomState(n)
+    if kind == "precession":
+        gm, om = qb.SimplePrecessionModel(min_freq=0.35), oracle.SimplePrecessionModel(min_freq=0.35)
+        x = 0.3 + 0.4 * rs.random_sample((n, 1))
+    else:
+        gm, om = qb.RandomizedBenchmarkingModel(), oracle.RandomizedBenchmarkingModel()
+        x = np.column_stack([0.9 + 0.1 * rs.random_sample(n), 0.6 * rs.random_sample(n), 0.4 * rs.random_sample(n)])
+    w = rs.random_sample(n) ** 4
+    w[rs.randint(0, n, n // 7)] = 0.0
+    w /= w.sum()
+    np.random.seed(31)
+    ores = oracle.LiuWestResampler(a=0.9)
+    ores.record = True
+    want = ores(om, oracle.ParticleDistribution(particle_locations=x, particle_weights=w)).particle_locations
+    want_next = np.random.random()
+    results = {}
+    for small in (True, False):
+        np.random.seed(31)
+        res = qb.LiuWestResampler(a=0.9, rng='numpy', scan='exact')
+        res._small = small
+        up = qb.SMCUpdater(gm, n, cases.FixedPrior(x), resampler=res)
+        up.particle_weights = w
+        launches0 = up._cloud.launches
+        up.resample()
+        results[small] = (up._cloud._js.cpu().numpy().copy(), up.particle_locations.copy(), res.last_n_iters,
+                          np.random.random(), up._cloud.launches - launches0, up.particle_weights.copy())
+    js, locs, iters, nxt, launches, wts = results[True]
+    assert np.array_equal(js, ores.trace["js"])
+    assert iters == ores.trace["n_iters"] and iters > 2                     # the retry loop ran, equally long
+    assert nxt == want_next
+    np.testing.assert_allclose(locs, want, rtol=1e-12, atol=1e-14)
+    assert np.all(np.asarray(gm.are_models_valid(locs)))
+    assert np.all(wts == 1.0 / n)
+    js2, locs2, iters2, nxt2, launches2, _ = results[False]
+    assert np.array_equal(js, js2) and iters == iters2 and nxt == nxt2
+    np.testing.assert_allclose(locs, locs2, rtol=1e-12, atol=1e-14)
+    assert launches < launches2                                             # fewer launches than the staged path
+    report("t5_small_%s_%d_locs_rel" % (kind, n), relerr(locs, want))
+
+
+def test_t5_small_cloud_zero_covariance_warns_like_the_reference(qb):
+    import warnings as _w
+    n = 512
+    x = np.full((n, 1), 0.5)
+    np.random.seed(3)
+    up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(x),
+                       resampler=qb.LiuWestResampler(rng='numpy', scan='exact'))
+    with _w.catch_warnings(record=True) as rec:
+        _w.simplefilter("always")
+        up.resample()
+    assert any("zero norm" in str(r.message) for r in rec)
+    np.random.seed(3)
+    np.random.random((n,))
+    eps = np.random.randn(1, n)
+    h = np.sqrt(1 - 0.98 ** 2)
+    want = (0.98 * 0.5 + (1 - 0.98) * 0.5) + (h * np.sqrt(1e-10)) * eps[0]
+    np.testing.assert_allclose(up.particle_locations[:, 0], want, rtol=1e-13)
+
+
 # ---------------------------------------------------------------------------
 # T6 — tomography canonicalize vs TomographyModel.canonicalize (golden)
 # ---------------------------------------------------------------------------
