@@ -169,9 +169,11 @@ typedef struct qb_update_ctl {
     int32_t n_ranks, rank;
     double* d_peer_mailbox[QB_MAX_RANKS]; /* [r] = rank r's mailbox as mapped in THIS process */
     int32_t* d_error_flag;     /* optional device int, set to 1 if a peer never answered */
-    /* Optional, n_ranks > 1: device-accessible pinned host block of QB_MAX_RANKS + 1 doubles.  The launch stores every
-     * rank's own sum w' of its LAST fused step in [0, n_ranks) — the shard masses a following resample splits its
-     * offspring by, known without another pass or collective — and then the launch tag in [QB_MAX_RANKS]. */
+    /* Optional, n_ranks > 1: device-accessible pinned host block of 4 * ceil(QB_MAX_RANKS / 3) doubles, 32-byte
+     * aligned.  After releasing its stats block the launch stores every rank's own sum w' of its LAST fused step —
+     * the shard masses a following resample splits its offspring by, known without another pass or collective — as
+     * groups {sum[3g], sum[3g+1], sum[3g+2], tag}, one 32-byte store each (no system fence): valid when every group
+     * that holds a rank carries the launch tag. */
     double* h_shard_norms;
 } qb_update_ctl;
 /* One launch: w_out[i] = (w_in[i] * stats_in[INV_NORM]) * L(outcome | x_i; ep)

@@ -238,16 +238,33 @@ __device__ void peer_allreduce(const UpdateParams& p, double* sums, double* scra
         }
         sums[threadIdx.x] = any_bad ? nan("") : t;
     }
-    if (p.shard_norms != nullptr && threadIdx.x < G) {
-        // the shard masses a following resample splits its offspring by: rank r's own sum w' of the last fused step
-        const int k = 3 * (p.nsteps - 1);
-        const unsigned int lo = scr[threadIdx.x * nw + 2 * k], hi = scr[threadIdx.x * nw + 2 * k + 1];
-        p.shard_norms[threadIdx.x] = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
-        __threadfence_system();
-    }
     __syncthreads();
-    if (p.shard_norms != nullptr && threadIdx.x == 0)
-        *reinterpret_cast<volatile double*>(p.shard_norms + QB_MAX_RANKS) = any_bad ? -1.0 : p.tag;
+}
+
+// The shard masses a following resample splits its offspring by: rank r's own sum w' of the last fused step, taken
+// from the rows the all-reduce received.  Written AFTER the stats block has been released (nothing on the device
+// waits for it) and, like the stats mirror, without a system-scope fence: 32-byte vector stores {3 sums, tag}, each a
+// single aligned PCIe write; the host accepts the block when every group carries the launch's tag.
+__device__ void publish_shard_norms(const UpdateParams& p, const double* scratch) {
+    const int G = p.n_ranks;
+    const int g = static_cast<int>(threadIdx.x) - 32;      // warp 1: thread 0 is busy publishing the stats block
+    if (g < 0 || 3 * g >= G) return;
+    const unsigned int* scr = reinterpret_cast<const unsigned int*>(scratch);
+    const int nw = 6 * p.nsteps;
+    const int k = 3 * (p.nsteps - 1);
+    double v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int r = 3 * g + j;
+        v[j] = 0.0;
+        if (r < G) {
+            const unsigned int lo = scr[r * nw + 2 * k], hi = scr[r * nw + 2 * k + 1];
+            v[j] = __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+        }
+    }
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p.shard_norms + 4 * g), "d"(v[0]), "d"(v[1]),
+                 "d"(v[2]), "d"(p.tag)
+                 : "memory");
 }
 
 // MLEModel's power is applied by the one-update kernels only (fused launches keep the plain likelihood and their
@@ -600,6 +617,8 @@ __global__ void __launch_bounds__(UPD_THREADS, (KF == 1) ? 2 : 3) fused_update_k
         if (tid == 0) {
             publish(p, sums);
             if (!CHAIN) *p.ticket = 0u;  // ready for the next launch on this stream
+        } else if (p.n_ranks > 1 && p.shard_norms != nullptr && tid >= 32) {
+            publish_shard_norms(p, peer_scratch);
         }
     }
 }
@@ -835,6 +854,8 @@ extern "C" int qb_fused_update_multi(const qb_model* model, const qb_expparams* 
     QB_REQUIRE(p.mirror == nullptr || (reinterpret_cast<uintptr_t>(p.mirror) & 31) == 0, QB_ERR_INVALID_ARGUMENT,
                "qb_fused_update: the host mirror must be 32-byte aligned");
     QB_REQUIRE(p.n_ranks <= QB_MAX_RANKS, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: at most %d ranks", QB_MAX_RANKS);
+    QB_REQUIRE(p.shard_norms == nullptr || (reinterpret_cast<uintptr_t>(p.shard_norms) & 31) == 0, QB_ERR_INVALID_ARGUMENT,
+               "qb_fused_update: h_shard_norms must be 32-byte aligned");
     for (int r = 0; r < QB_MAX_RANKS; ++r) p.peer_mbox[r] = (ctl && r < p.n_ranks) ? ctl->d_peer_mailbox[r] : nullptr;
     if (p.n_ranks > 1) {
         QB_REQUIRE(p.rank >= 0 && p.rank < p.n_ranks, QB_ERR_INVALID_ARGUMENT, "qb_fused_update: bad rank");

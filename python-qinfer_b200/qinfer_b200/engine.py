@@ -39,6 +39,9 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+SHARD_NORMS_SLOT = 4 * ((_lib.QB_MAX_RANKS + 2) // 3)     # doubles per slot of qb_update_ctl.h_shard_norms
+
+
 class DeviceCloud(object):
     def __init__(self, desc, n, device=None, capacity=None):
         self.lib = _lib.load()
@@ -219,7 +222,7 @@ class DeviceCloud(object):
             for slot, c in enumerate(self._ctls):
                 ctypes.memmove(ctypes.byref(c), ctypes.byref(self._ctl), ctypes.sizeof(_lib.QbUpdateCtl))
                 c.h_mirror = self.mirror.data_ptr() + slot * MIRROR_SLOT * 8
-                c.h_shard_norms = (self._shard_norms.data_ptr() + slot * (_lib.QB_MAX_RANKS + 1) * 8
+                c.h_shard_norms = (self._shard_norms.data_ptr() + slot * SHARD_NORMS_SLOT * 8
                                    if self._shard_norms is not None else None)
                 c.zero_weight_thresh = zero_weight_thresh
                 c.resample_below = resample_below
@@ -261,7 +264,7 @@ class DeviceCloud(object):
     def enable_shard_norms(self):
         """Sharded clouds: every update launch also publishes each rank's own sum w' (the shard masses)."""
         if self._shard_norms is None:
-            self._shard_norms = torch.zeros((2 * (_lib.QB_MAX_RANKS + 1),), dtype=torch.float64, pin_memory=True)
+            self._shard_norms = torch.zeros((2 * SHARD_NORMS_SLOT,), dtype=torch.float64, pin_memory=True)
             self._shard_norms_np = self._shard_norms.numpy()
             self._ctl_key = None
 
@@ -271,10 +274,19 @@ class DeviceCloud(object):
         tag = self._slot_tag[self.cur]
         if self._shard_norms is None or not tag:
             return None
-        row = self._shard_norms_np[self.cur * (_lib.QB_MAX_RANKS + 1):(self.cur + 1) * (_lib.QB_MAX_RANKS + 1)]
-        if row[_lib.QB_MAX_RANKS] != float(tag):
-            return None
-        return row[:n_ranks].copy()
+        row = self._shard_norms_np[self.cur * SHARD_NORMS_SLOT:(self.cur + 1) * SHARD_NORMS_SLOT].reshape(-1, 4)
+        groups = (n_ranks + 2) // 3
+        # groups of {3 sums, tag}, one 32-byte store each, issued right after the stats block the host has already
+        # seen: wait for them (whether the masses exist must not depend on timing — every rank takes the same path)
+        spins, t0 = 0, None
+        while not np.all(row[:groups, 3] == float(tag)):
+            spins += 1
+            if spins > 2000:
+                if t0 is None:
+                    t0 = time.perf_counter()
+                elif time.perf_counter() - t0 > 10.0:
+                    raise _lib.QbError("timed out waiting for the shard masses of update launch %d" % tag)
+        return row[:groups, :3].reshape(-1)[:n_ranks].copy()
 
     @nvtx_range('qb.cloud.wait_stats')
     def wait_stats(self, slot, tag, nsteps=1, timeout_s=120.0):

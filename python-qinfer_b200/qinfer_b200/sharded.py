@@ -186,6 +186,12 @@ class ShardComm(object):
         self.dist.all_gather_into_tensor(out, mine, group=self.group)
         return [int(v) for v in out.tolist()]
 
+    def broadcast_int(self, value, device):
+        """Rank 0's ``value`` (a non-negative int below 2^63) on every rank: one small collective."""
+        t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        self.dist.broadcast(t, src=self._global_rank(0), group=self.group)
+        return int(t.item())
+
     def all_gather_object(self, obj):
         out = [None] * self.world
         self.dist.all_gather_object(out, obj, group=self.group)
@@ -447,13 +453,42 @@ class _DeviceOps(object):
         return out[:m * c.d]
 
 
+_MAILBOX_CACHE = {}      # (group, world, rank, device) -> PeerMailboxes released by a closed updater
+_WARMED = set()          # groups whose NCCL channels the resample exchange has already created
+
+
+def _group_key(comm):
+    return (id(comm.group) if comm.group is not None else 0, comm.world, comm.rank, torch.cuda.current_device())
+
+
 class PeerMailboxes(object):
-    """One mailbox per rank, mapped into every peer process through CUDA IPC."""
+    """One mailbox per rank, mapped into every peer process through CUDA IPC.
+
+    Creating one costs milliseconds (cudaMalloc, handle exchange, cudaIpcOpenMemHandle on every peer), so a closed
+    updater RELEASES its mailboxes to a per-process cache and the next sharded updater of the same group reuses them.
+    Rows are validated by the launch tag they carry: the new cloud continues the tag sequence where the previous one
+    stopped (``last_tag``; identical on every rank, the ranks issue the same launches), so a stale row never matches."""
+
+    @classmethod
+    def acquire(cls, comm):
+        mb = _MAILBOX_CACHE.pop(_group_key(comm), None)
+        if mb is None:
+            mb = cls(comm)
+        mb.comm = comm
+        return mb
+
+    def release(self, last_tag):
+        """Park the mapping for the next updater (every rank's launches have drained: synchronize + barrier)."""
+        torch.cuda.synchronize()
+        self.comm.barrier()
+        self.last_tag = max(int(last_tag), self.last_tag)
+        _MAILBOX_CACHE[_group_key(self.comm)] = self
 
     def __init__(self, comm):
         lib = _lib.load()
         self.lib = lib
         self.comm = comm
+        self.last_tag = 0
         mine = ctypes.c_void_p()
         _lib.check(lib.qb_mailbox_create(comm.world, ctypes.byref(mine)))
         self.mine = mine
@@ -534,12 +569,15 @@ def _make_sharded_updater_class():
             self._n_ess = float(self._n_global)
             # "split" resample: the multinomial split is drawn by every rank from the SAME counter-based host
             # generator (rank 0's resampler seed), the offspring from per-rank Philox streams
-            seeds = self._comm.all_gather_object(int(getattr(self.resampler, '_seed', 0x5EED)))
-            self._split_rng = np.random.Generator(np.random.Philox(key=int(seeds[0]) & ((1 << 64) - 1)))
-            self._stream_seed = (int(seeds[0]) + 0x9E3779B97F4A7C15 * (self._comm.rank + 1)) & ((1 << 64) - 1)
+            seed0 = self._comm.broadcast_int(int(getattr(self.resampler, '_seed', 0x5EED)) & ((1 << 63) - 1),
+                                             self._cloud.device)
+            self._split_rng = np.random.Generator(np.random.Philox(key=seed0 & ((1 << 64) - 1)))
+            self._stream_seed = (seed0 + 0x9E3779B97F4A7C15 * (self._comm.rank + 1)) & ((1 << 64) - 1)
             self.last_exchange = (0, 0)
             self._sample_calls = 0
-            self._warm_collectives()
+            if _group_key(self._comm) not in _WARMED:
+                self._warm_collectives()
+                _WARMED.add(_group_key(self._comm))
 
         def _warm_collectives(self):
             """Create the NCCL channels the resample exchange uses now, not inside the first resample."""
@@ -563,18 +601,23 @@ def _make_sharded_updater_class():
             return self._slab_capacity(n)
 
         def _rebuild_cloud(self, n):
+            launches_tag = self._cloud._tag if self._cloud is not None else 0
             super(ShardedSMCUpdater, self)._rebuild_cloud(n)
             if self._comm.world > 1:
                 if self._mail is None:
-                    self._mail = PeerMailboxes(self._comm)
+                    self._mail = PeerMailboxes.acquire(self._comm)
+                self._mail.last_tag = max(self._mail.last_tag, launches_tag)
+                self._cloud._tag = self._mail.last_tag          # never reuse a tag the mailbox rows may still carry
                 self._mail.install(self._cloud._ctl)
                 self._cloud.enable_shard_norms()      # every update publishes the shard masses a resample splits by
             self._ops = _DeviceOps(self._cloud, self._comm.world)
 
         def close(self):
+            """Collective: drain this updater's launches on every rank and park the peer mailboxes for the next
+            sharded updater of this group (``qinfer_b200.sharded.shutdown()`` unmaps them for good)."""
             if self._mail is not None:
                 self._flush()
-                self._mail.close()
+                self._mail.release(self._cloud._tag)
                 self._mail = None
 
         @property
@@ -1047,6 +1090,14 @@ def _make_sharded_updater_class():
                 self._cloud.resample_events.append(ev)
 
     return ShardedSMCUpdater
+
+
+def shutdown():
+    """Unmap and free every cached peer mailbox (collective; call before destroying the process group if the process
+    goes on living — at interpreter exit the driver does it)."""
+    for key in list(_MAILBOX_CACHE):
+        _MAILBOX_CACHE.pop(key).close()
+    _WARMED.clear()
 
 
 _cls = None
