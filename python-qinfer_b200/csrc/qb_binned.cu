@@ -414,10 +414,11 @@ __global__ void __launch_bounds__(SUMS_THREADS) binned_sums_tma_kernel(const __g
     __shared__ double mred[NW * NOUT];
     __shared__ double scan_tot[NW];
     __shared__ double eighth[STAGES][SUMS_CONSUMERS];
-    __shared__ unsigned int arrived[STAGES];
     __shared__ unsigned int is_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t bar0 = smem_u32(ssm);          // full[s] at bar0 + 8 s, empty[s] at bar0 + 64 + 8 s
+    // full[s] at bar0 + 8 s, done[s] (every consumer warp has stored its part of the bin sum) at bar0 + 32 + 8 s,
+    // empty[s] at bar0 + 64 + 8 s
+    const uint32_t bar0 = smem_u32(ssm);
     unsigned char* ring = ssm + 128;
     const uint32_t ring0 = smem_u32(ring);
     const int64_t full_bins = p.n / BIN;
@@ -427,8 +428,8 @@ __global__ void __launch_bounds__(SUMS_THREADS) binned_sums_tma_kernel(const __g
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(bar0 + 8 * s, 1);
+            mbar_init(bar0 + 32 + 8 * s, SUMS_CONSUMERS);
             mbar_init(bar0 + 64 + 8 * s, SUMS_CONSUMERS);
-            arrived[s] = 0u;
         }
         mbar_fence_init();
     }
@@ -498,15 +499,14 @@ __global__ void __launch_bounds__(SUMS_THREADS) binned_sums_tma_kernel(const __g
             sub = warp_sum(sub);
             if (lane == 0) {
                 eighth[s][wid] = sub;
-                __threadfence_block();
-                if (atomicAdd(&arrived[s], 1u) == SUMS_CONSUMERS - 1) {     // last warp of this bin: fixed-order sum
-                    __threadfence_block();
+                mbar_arrive(bar0 + 32 + 8 * s);               // (release) my part of this bin's sum is in place
+                if (wid == 0) {                               // warp 0 collects: fixed-order sum of the eight parts
+                    mbar_wait(bar0 + 32 + 8 * s, phase);      // (acquire) every consumer warp has stored its part
                     double tot = 0.0;
 #pragma unroll
-                    for (int q = 0; q < SUMS_CONSUMERS; ++q) tot += *reinterpret_cast<volatile double*>(&eighth[s][q]);
+                    for (int q = 0; q < SUMS_CONSUMERS; ++q) tot += eighth[s][q];
                     p.bounds[t] = tot;
                     p.counts[t] = 0u;
-                    arrived[s] = 0u;
                 }
                 mbar_arrive(bar0 + 64 + 8 * s);   // only now may the producer refill stage s (and eighth[s] be reused)
             }

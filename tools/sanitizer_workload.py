@@ -45,6 +45,13 @@ if world > 1:
                                resampler=qb.LiuWestResampler(rng='philox', scan='fast', seed=5), lazy=lazy)
         print(rank, "sharded lazy=%s" % lazy, drive(up))
         up.close()
+    # parity mode: exact scan chained across the slabs (parallel replay kernel: slabs >= 32768), shared legacy stream
+    np.random.seed(12)
+    up = ShardedSMCUpdater(qb.SimplePrecessionModel(min_freq=0.05), n * world,
+                           cases.FixedPrior(np.random.RandomState(3 + rank).random_sample((n, 1))),
+                           resampler=qb.LiuWestResampler(rng='mt19937', scan='exact'))
+    print(rank, "sharded parity mode", drive(up, 25))
+    up.close()
     dist.destroy_process_group()
     sys.exit(0)
 
@@ -60,6 +67,20 @@ for rng in ("numpy", "mt19937"):
     up = qb.SMCUpdater(qb.SimplePrecessionModel(), n, cases.FixedPrior(prior),
                        resampler=qb.LiuWestResampler(rng=rng, scan='exact'))
     print("parity mode rng=%s" % rng, drive(up))
+# small clouds: the single-CTA parity resample (d = 1 with retries, d = 3)
+np.random.seed(2)
+up = qb.SMCUpdater(qb.SimplePrecessionModel(min_freq=0.3), 1000, cases.FixedPrior(0.3 + 0.4 * prior[:1000]),
+                   resampler=qb.LiuWestResampler(rng='numpy', scan='exact'))
+print("small cloud d=1", drive(up))
+sm = qb.RandomizedBenchmarkingModel()
+x3 = np.column_stack([0.9 + 0.1 * prior[:3000, 0], 0.6 * prior[3000:6000, 0], 0.4 * prior[6000:9000, 0]])
+up = qb.SMCUpdater(sm, 3000, cases.FixedPrior(x3), resampler=qb.LiuWestResampler(rng='numpy', scan='exact'))
+ep3 = np.empty((1,), dtype=sm.expparams_dtype)
+for k in range(12):
+    ep3['m'] = 1 + 7 * k
+    up.update(k % 2, ep3)
+up.resample()
+print("small cloud d=3", up.est_mean(), up.resample_count)
 # RB under BinomialModel (d = 3, retries), batch_update
 inp = cases.rb_inputs(n_particles=n, n_updates=30)
 model = qb.BinomialModel(qb.RandomizedBenchmarkingModel())
