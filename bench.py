@@ -241,7 +241,9 @@ def workload_config(n_per_gpu, world):
             "l2_policy": "inputs larger than L2: each update streams 240 MB (x, w in, w out) through a 126 MB L2",
             "resampler": "rng=philox (device), scan=fast, draw=binned (multinomial counts per bin of 2048 + in-bin "
                          "draws from a shared-memory CDF)",
-            "updater": "lazy=True (speculative launch pipelining)"}
+            "updater": "lazy=True (speculative launch pipelining)",
+            "warm_up": "process warm-up at full size, then 25 ms of SM spin-up (the sampler start-up / gc / barrier "
+                       "before a timed region leave the GPU idle and its clocks low), then the W warm-up steps"}
 
 
 def reference_config(n, world):
@@ -323,6 +325,21 @@ class CudaBackend(object):
 
     def sync(self):
         self.torch.cuda.synchronize()
+
+    def spin_up(self, ms=25.0):
+        """Keep the SMs busy for ``ms`` on a scratch buffer.  The host-side preparations of a timed region (clock
+        sampler start-up, garbage collection, barrier) leave the GPU idle for hundreds of milliseconds, its clocks
+        fall back to idle, and the first ~millisecond afterwards runs below the clocks of a busy device — comparable
+        to a whole 20-step region.  This is process warm-up; the W warm-up steps follow it."""
+        torch = self.torch
+        buf = getattr(self, "_spin_buf", None)
+        if buf is None:
+            buf = self._spin_buf = torch.ones((1 << 24,), dtype=torch.float64, device="cuda")
+        t_end = time.perf_counter() + ms * 1e-3
+        while time.perf_counter() < t_end:
+            for _ in range(8):
+                buf.mul_(1.0)
+            torch.cuda.synchronize()
 
     def resampler(self, mode, seed):
         if mode == 'parity':
@@ -453,16 +470,18 @@ def timed_run(be, n, prior, ts, outcomes, warm, steps, mode='throughput', fuse=1
     up = be.new_updater(n, prior, mode=mode, fuse=fuse, seed=seed)
     if mode == 'parity':
         np.random.seed(0)
-    drive(up, ts, outcomes, 0, warm)
-    up._flush()
-    be.collect_resample_events(up)
-    l0, u0 = be.launch_counts(up)
-    r0 = up.resample_count
     if clocks is not None:
         clocks.start()
         clocks.wait_first_sample()                   # nvidia-smi's start-up stays outside the timed region
     gc.collect()                                     # (before the barrier: a collection takes milliseconds and would
     gc.disable()                                     #  skew the ranks' entry into the timed region)
+    if hasattr(be, "spin_up"):
+        be.spin_up()                                 # the preparations above left the GPU idle: clocks back up first
+    drive(up, ts, outcomes, 0, warm)                 # the W untimed warm-up steps, right before the timed ones
+    up._flush()
+    be.collect_resample_events(up)
+    l0, u0 = be.launch_counts(up)
+    r0 = up.resample_count
     be.barrier()
     t = be.timer()
     t.start()
@@ -489,6 +508,8 @@ def e2e_run(be, n, pinned_prior, ts, outcomes, warm, steps, fuse=1, seed=1000):
     then the read-back of the whole posterior cloud, timed separately."""
     prior = pinned_prior.numpy()
     gc.collect()
+    if hasattr(be, "spin_up"):
+        be.spin_up()
     be.barrier()
     t0 = time.perf_counter()
     t = be.timer()
