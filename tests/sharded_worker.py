@@ -146,12 +146,17 @@ def main():
         rs = np.random.RandomState(17)
         problems = []
         n1 = 200003                                                         # slabs >= 32768: the parallel replay scan
-        problems.append((qb.SimplePrecessionModel(min_freq=0.35), 0.3 + 0.4 * rs.random_sample((n1, 1))))
+        problems.append((qb.SimplePrecessionModel(min_freq=0.35), 0.3 + 0.4 * rs.random_sample((n1, 1)), {}))
         n3 = 50001                                                          # small slabs: the one-lane kernel
         problems.append((qb.RandomizedBenchmarkingModel(),
                          np.column_stack([0.9 + 0.1 * rs.random_sample(n3), 0.6 * rs.random_sample(n3),
-                                          0.4 * rs.random_sample(n3)])))
-        for model, xs in problems:
+                                          0.4 * rs.random_sample(n3)]), {}))
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import cases                                                        # noqa: E402
+        basis2 = qb.pauli_basis(2)                                          # d = 16: the generic-d staged kernels
+        problems.append((qb.TomographyModel(basis2), cases.ginibre_coords(rs, 20001, np.asarray(basis2.data)),
+                         dict(canonicalize=False)))
+        for model, xs, kw in problems:
             n_par = xs.shape[0]
             lay = ShardLayout(n_par, world)
             plo, phi = lay.offsets[rank], lay.offsets[rank + 1]
@@ -160,7 +165,7 @@ def main():
             w /= w.sum()
             np.random.seed(4242)                                            # the same legacy state on every rank
             up = ShardedSMCUpdater(model, n_par, Fixed(xs[plo:phi]),
-                                   resampler=qb.LiuWestResampler(a=0.9, rng='mt19937', scan='exact'))
+                                   resampler=qb.LiuWestResampler(a=0.9, rng='mt19937', scan='exact'), **kw)
             up.particle_weights = w[plo:phi]
             up.resample()
             js = up.last_parity_js.cpu().numpy()
@@ -170,21 +175,24 @@ def main():
             want = np.cumsum(w).searchsorted(np.random.RandomState(4242).random_sample(n_par), side='right')
             check(np.array_equal(js, want[plo:phi]), "parity: js differ from np.cumsum/searchsorted in %d slots"
                   % int(np.sum(js != want[plo:phi])))
-            check(iters > 2, "parity: the retry loop did not run (%d iterations)" % iters)
+            check(iters > 2 or xs.shape[1] == 16, "parity: the retry loop did not run (%d iterations)" % iters)
             check(bool(np.all(np.asarray(model.are_models_valid(locs)))), "parity: invalid particles left")
             up.close()
             if rank == 0:
                 np.random.seed(4242)
                 ref = qb.SMCUpdater(model, n_par, Fixed(xs),
-                                    resampler=qb.LiuWestResampler(a=0.9, rng='mt19937', scan='exact'))
+                                    resampler=qb.LiuWestResampler(a=0.9, rng='mt19937', scan='exact'), **kw)
                 ref.particle_weights = w
                 ref.resample()
                 check(np.array_equal(ref._cloud._js.cpu().numpy()[plo:phi], js), "parity: js differ from single GPU")
                 check(ref.resampler.last_n_iters == iters, "parity: %d iterations vs %d on one GPU"
                       % (iters, ref.resampler.last_n_iters))
                 check(np.random.random() == after, "parity: legacy stream position differs from single GPU")
-                # (locations: same js, same variates; the global mean / covariance are reduced in another order)
-                check(np.allclose(locs, ref.particle_locations[plo:phi], rtol=1e-12, atol=1e-14),
+                # (locations: same js, same variates; the global mean / covariance are reduced in another order.
+                # Two-qubit states share x_0 = 1/2: the covariance is singular, and the square root of an
+                # eigenvalue that is zero up to rounding (+-1e-17) moves by 1e-9 with the summation order)
+                check(np.allclose(locs, ref.particle_locations[plo:phi], rtol=1e-12,
+                                  atol=1e-7 if xs.shape[1] == 16 else 1e-14),
                       "parity: locations differ from single GPU by %r"
                       % float(np.max(np.abs(locs - ref.particle_locations[plo:phi]))))
         # ... and free-running: the sharded parity trajectory follows the single-GPU parity trajectory
