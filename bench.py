@@ -667,6 +667,16 @@ def resample_roofline(run, n):
             "note": "event-timed around resample(), host work and syncs included"}
 
 
+def guarded(name, fn):
+    """Run one EXTRA sub-record; an exception becomes {"ok": false, "error": ...} instead of costing the whole line."""
+    try:
+        return fn()
+    except Exception as e:        # noqa: BLE001 - anything: the headline measurement is already in hand
+        import traceback
+        sys.stderr.write("bench.py: sub-record %s failed:\n%s\n" % (name, traceback.format_exc()))
+        return {"ok": False, "error": "%s: %s" % (type(e).__name__, e)}
+
+
 def gpu_arm(args, rank, world, local_rank, backend=None):
     be = backend if backend is not None else CudaBackend(local_rank, world)
     n = args.particles
@@ -692,43 +702,57 @@ def gpu_arm(args, rank, world, local_rank, backend=None):
         rec_bytes = 64                                   # experiment record in (t, outcome, flags); stats block out
         h2d = n * 8.0 / steps + rec_bytes                # prior upload amortised + per-step experiment record
         d2h = 64 + 8.0 / steps                           # per-step stats block + the posterior mean
-        if extras and world == 1 and args.fuse == 1:
+        # The sub-records below are EXTRAS: whatever happens in one of them, the headline line is still printed
+        # (`guarded` turns an exception into an {"ok": false, "error": ...} sub-record).
+        def fused_record():
             # the same K updates, 8 fused per launch
             f = timed_run(be, n, prior, ts, outcomes, warm, steps, fuse=8, seed=1000)
-            fused = {"updates_per_launch_max": 8, "value": n * steps / (f["elapsed_ms"] * 1e-3), "unit": UNIT,
-                     "ms_per_step": f["elapsed_ms"] / steps, "update_launches": f["update_launches"],
-                     "resamples": f["resamples"],
-                     "note": "same workload and semantics (per-step n_ess check, speculative + roll-back); the fused "
-                             "kernel is fp64-pipe bound, not HBM bound"}
+            return {"updates_per_launch_max": 8, "value": n * steps / (f["elapsed_ms"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": f["elapsed_ms"] / steps, "update_launches": f["update_launches"],
+                    "resamples": f["resamples"],
+                    "note": "same workload and semantics (per-step n_ess check, speculative + roll-back); the fused "
+                            "kernel is fp64-pipe bound, not HBM bound"}
+
+        def parity_record():
             # the bit-exact mode: legacy MT19937 stream continued on the device, exact (np.cumsum-rounding) scan
             p = timed_run(be, n, prior, ts, outcomes, warm, steps, mode='parity', fuse=1)
-            parity = {"resampler": "rng=mt19937 (NumPy's legacy stream, generated on the device), scan=exact, staged "
-                                   "draw: resample indices bit-identical to the reference under np.random.seed",
-                      "value": n * steps / (p["elapsed_ms"] * 1e-3), "unit": UNIT,
-                      "ms_per_step": p["elapsed_ms"] / steps, "resamples": p["resamples"],
-                      "resample_ms_each": [round(v, 3) for v in p["resample_ms_each"]],
-                      "posterior_mean": p["posterior_mean"]}
-            if n == PARTICLES_PER_GPU and not args.no_north_star:
-                big = 10 ** 8
-                bts, bout = make_data(205)
-                s = timed_run(be, big, make_prior(big, 7), bts, bout, 5, 200, fuse=1, seed=2000)
-                sr = roofline_record(s, big, 200)
-                star = {"workload": "SimplePrecessionModel, N = 1e8 particles on ONE GPU, 200 updates (north_star)",
-                        "value": big * 200 / (s["elapsed_ms"] * 1e-3), "unit": UNIT,
-                        "ms_per_step": s["elapsed_ms"] / 200, "resamples": s["resamples"],
-                        "resample_ms_each": [round(v, 3) for v in s["resample_ms_each"]],
-                        "roofline_frac": sr["frac"], "avg_update_launch_ms": sr["avg_launch_ms"],
-                        "target": ">= 1e9 particle-updates/s at >= 60 % of the HBM roofline"}
-        if extras and world == 8 and n == PARTICLES_PER_GPU:
+            return {"resampler": "rng=mt19937 (NumPy's legacy stream, generated on the device), scan=exact, staged "
+                                 "draw: resample indices bit-identical to the reference under np.random.seed",
+                    "value": n * steps / (p["elapsed_ms"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": p["elapsed_ms"] / steps, "resamples": p["resamples"],
+                    "resample_ms_each": [round(v, 3) for v in p["resample_ms_each"]],
+                    "posterior_mean": p["posterior_mean"]}
+
+        def north_star_record():
+            big = 10 ** 8
+            bts, bout = make_data(205)
+            s = timed_run(be, big, make_prior(big, 7), bts, bout, 5, 200, fuse=1, seed=2000)
+            sr = roofline_record(s, big, 200)
+            return {"workload": "SimplePrecessionModel, N = 1e8 particles on ONE GPU, 200 updates (north_star)",
+                    "value": big * 200 / (s["elapsed_ms"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": s["elapsed_ms"] / 200, "resamples": s["resamples"],
+                    "resample_ms_each": [round(v, 3) for v in s["resample_ms_each"]],
+                    "roofline_frac": sr["frac"], "avg_update_launch_ms": sr["avg_launch_ms"],
+                    "target": ">= 1e9 particle-updates/s at >= 60 % of the HBM roofline"}
+
+        def c5_record():
             nc = C5_PARTICLES_PER_GPU
             c = timed_run(be, nc, make_prior(nc, 199 + rank), ts, outcomes, warm, steps, fuse=args.fuse,
                           seed=3000 + rank)
             c_ms = be.reduce([c["elapsed_ms"]])[0]
-            c5 = {"workload": "C5: N = 1e8 over 8 GPUs, 1.25e7 particles per GPU, same %d steps" % steps,
-                  "value": nc * world * steps / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms / steps,
-                  "resamples": c["resamples"]}
+            return {"workload": "C5: N = 1e8 over 8 GPUs, 1.25e7 particles per GPU, same %d steps" % steps,
+                    "value": nc * world * steps / (c_ms * 1e-3), "unit": UNIT, "ms_per_step": c_ms / steps,
+                    "resamples": c["resamples"]}
+
+        if extras and world == 1 and args.fuse == 1:
+            fused = guarded("fused_f1", fused_record)
+            parity = guarded("parity_mode", parity_record)
+            if n == PARTICLES_PER_GPU and not args.no_north_star:
+                star = guarded("north_star_1e8", north_star_record)
+        if extras and world == 8 and n == PARTICLES_PER_GPU:
+            c5 = guarded("c5", c5_record)
         if extras and world > 1:
-            shard = sharded_check(be, rank, world)
+            shard = guarded("sharded_check", lambda: sharded_check(be, rank, world))
 
     elapsed_ms, core_ms = be.reduce([run["elapsed_ms"], e2e["core_ms"]])
     launches = int(be.reduce([run["launches"]], op="sum")[0])
@@ -763,10 +787,10 @@ def gpu_arm(args, rank, world, local_rank, backend=None):
             if extras:
                 with warnings.catch_warnings():
                     warnings.simplefilter("ignore")
-                    line["check"] = prefix_check(be, n, post)
+                    line["check"] = guarded("check", lambda: prefix_check(be, n, post))
         print(json.dumps(line))
         sys.stdout.flush()
-        bad = [k for k in ("check", "sharded_check") if k in line and not line[k]["ok"]]
+        bad = [k for k in ("check", "sharded_check") if k in line and not line[k].get("ok", False)]
         if bad:
             sys.stderr.write("bench.py: in-run correctness check failed: %s\n" % ", ".join(bad))
     be.finish()

@@ -163,3 +163,30 @@ def test_reference_arm_describes_its_own_algorithm():
     cfg = bench.reference_config(12345, 1)
     assert "MT19937" in cfg["resampler"] and "philox" not in cfg["resampler"].lower()
     assert "lazy" not in cfg["updater"] and cfg["workload"] == bench.workload_config(bench.PARTICLES_PER_GPU, 1)["workload"]
+
+
+def test_a_failing_extra_does_not_cost_the_headline_line(capsys):
+    """An exception inside a sub-record (here: the parity-mode pass) becomes {"ok": false, "error": ...}; the headline
+    JSON line with value / e2e / roofline is still printed and the process does not fail."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Flaky(_FakeBackend):
+        def new_updater(self, n, prior, mode='throughput', **kw):
+            if mode == 'parity' and kw.get('seed') == 1000:        # the parity-mode PASS (the warm-up uses seed 5)
+                raise RuntimeError("simulated failure of an extra")
+            return _FakeBackend.new_updater(self, n, prior, mode=mode, **kw)
+
+    class Args(object):
+        pass
+    args = Args()
+    args.particles, args.steps, args.warmup = 1200, 20, 5
+    args.fuse, args.no_extras, args.no_north_star, args.no_cpu_baseline = 1, False, True, True
+    line = bench.gpu_arm(args, 0, 1, 0, backend=Flaky())
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(out) == 1
+    d = json.loads(out[0])
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["roofline"]["frac"] > 0
+    assert d["parity_mode"]["ok"] is False and "simulated failure" in d["parity_mode"]["error"]
+    assert d["fused_f1"]["value"] > 0                        # the other extras still ran
+    assert line["value"] == d["value"]
