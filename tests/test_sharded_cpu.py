@@ -337,3 +337,43 @@ def test_parity_resample_equals_the_single_process_reference_algorithm(tmp_path,
         assert np.array_equal(got, want)
     else:
         np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+
+
+def _comm_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ShardComm()
+        cpu = torch.device("cpu")
+        # ragged all-gather of slabs of rows (width 3, unequal counts), in rank order
+        counts = [5, 2, 4][:world]
+        mine = torch.arange(counts[rank] * 3, dtype=torch.float64) + 100.0 * rank
+        ragged = comm.all_gather_ragged(mine, counts, 3)
+        seed = comm.broadcast_int(12345 + rank, cpu)                 # rank 0's value everywhere
+        ints = comm.all_gather_ints(7 * rank + 1, cpu)
+        # the chain: a running value travels rank to rank
+        carry = torch.zeros((1,), dtype=torch.float64)
+        if rank > 0:
+            comm.recv_prev(carry)
+        carry = carry + float(rank + 1)
+        if rank < world - 1:
+            comm.send_next(carry)
+        np.savez(os.path.join(out_dir, "c%d.npz" % rank), ragged=ragged.numpy(), seed=seed, ints=np.asarray(ints),
+                 carry=carry.numpy())
+        comm.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_comm_helpers_of_the_parity_mode(tmp_path):
+    world = 3
+    mp.spawn(_comm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    counts = [5, 2, 4]
+    want = np.concatenate([np.arange(counts[r] * 3, dtype=np.float64) + 100.0 * r for r in range(world)])
+    for r in range(world):
+        f = np.load(os.path.join(str(tmp_path), "c%d.npz" % r))
+        assert np.array_equal(f["ragged"], want)
+        assert int(f["seed"]) == 12345
+        assert list(f["ints"]) == [1, 8, 15]
+        assert float(f["carry"][0]) == sum(range(1, r + 2))          # 1, 1 + 2, 1 + 2 + 3
