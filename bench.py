@@ -230,6 +230,33 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def host_info():
+    """CPU model, library versions and BLAS threads of the box the CPU baseline ran on.  Best effort:
+    never raises."""
+    info = {}
+    try:
+        info["os_cpu_count"] = os.cpu_count()
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    info["cpu_model"] = ln.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    try:
+        import scipy
+        info["numpy"], info["scipy"] = np.__version__, scipy.__version__
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_info
+        info["blas_threads"] = sorted({int(d.get("num_threads", 0)) for d in threadpool_info()
+                                       if d.get("user_api") == "blas"})
+    except Exception:
+        pass
+    return info
+
+
 def workload_text(n_per_gpu, world):
     return ("C2 SimplePrecessionModel, %d particles/GPU x %d GPU, t_k=(9/8)^(k mod 100), LiuWest a=0.98, "
             "resample_thresh 0.5" % (n_per_gpu, world))
@@ -275,7 +302,8 @@ def reference_arm(args, rank, world):
                          "sample": "NumPy oracle port of qinfer.SMCUpdater+LiuWestResampler; each step = one update "
                                    "of a %d-particle sample (of the 10^7 workload), %d steps, %d resamples; NumPy "
                                    "ufunc loops are single-threaded, BLAS dot may use %d threads"
-                                   % (n, steps, up.resample_count, cpu_threads())},
+                                   % (n, steps, up.resample_count, cpu_threads()),
+                         "host": host_info()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -293,7 +321,8 @@ def cpu_baseline(n):
     total = float(np.sum(times))
     rec = {"value": n * m / total, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
            "sample": "NumPy oracle port, first %d updates of the schedule at N=%d incl. %d resamples, %.1f s"
-                     % (m, n, up.resample_count, total)}
+                     % (m, n, up.resample_count, total),
+           "host": host_info()}
     post = {"mean": float(up.est_mean()[0]), "cov": float(up.est_covariance_mtx()[0, 0]), "n_ess": float(up.n_ess),
             "resample_count": int(up.resample_count),
             "normalization_record": [float(np.ravel(v)[0]) for v in up.normalization_record]}

@@ -146,6 +146,7 @@ def test_gpu_arm_data_path_for_the_drivers_step_counts(steps, warmup, capsys, mo
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["frac"] == pytest.approx(rf["achieved"] / rf["peak"])
     assert rf["update_launches"] >= steps and "traffic" in rf and "dram_frac" in rf
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert isinstance(d["cpu_baseline"]["host"], dict) and "numpy" in d["cpu_baseline"]["host"]
     # the double resamples with the oracle's NumPy resampler under the same seed: the parity check is exact
     chk = d["check"]
     assert chk["ok"] and chk["parity_mean_rel_err"] < 1e-9 and chk["parity_resample_count"][0] == \
