@@ -1,8 +1,9 @@
 """Supplementary measurements of the other BASELINE.json configurations (C1, C3, C4) through the public API,
 with the NumPy oracle port of the reference timed beside each on a bounded sample.  Not the judged bench
-(bench.py measures C2); the output goes to profiles/ as context for DESIGN.md.
+(bench.py measures C2); the output goes to profiles/ as context for DESIGN.md.  It lives under tests/ because it
+times the oracle (test infrastructure) beside the device path; pytest does not collect it.
 
-    python tools/bench_configs.py [--quick]
+    python tests/bench_configs.py [--quick]
 """
 import json
 import os
